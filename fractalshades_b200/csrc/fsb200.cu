@@ -1,0 +1,995 @@
+/*
+ * fsb200.cu -- host side of libfsb200.so and its C ABI (include/fsb200.h).
+ *
+ * One process drives one GPU (fsb_init).  Per-frame tables live in HBM inside
+ * an fsb_frame; every calling host thread owns a stream plus scratch buffers,
+ * so the reference's thread-per-tile dispatch (mthreading.py:48-68) can call
+ * fsb_frame_run concurrently and the kernels overlap on the device.
+ *
+ * There is no CPU fallback: every compute entry point needs a CUDA device.
+ */
+#include "../../include/fsb200.h"
+#include "fsb_kernels.cuh"
+
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+using namespace fsb;
+
+namespace {
+
+thread_local std::string g_err;
+int g_device = -1;
+int g_sm_count = 0;
+std::mutex g_mutex;
+double *g_flush_buf = nullptr;
+const long long FLUSH_DOUBLES = (192LL << 20) / 8; /* 192 MiB > 126 MB L2 */
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                  \
+    do {                                                                          \
+        cudaError_t e_ = (call);                                                  \
+        if (e_ != cudaSuccess)                                                    \
+            return fail(-1, "CUDA error %s at %s:%d (%s)", cudaGetErrorName(e_), \
+                        __FILE__, __LINE__, cudaGetErrorString(e_));              \
+    } while (0)
+
+int ensure_init()
+{
+    if (g_device >= 0) return 0;
+    return fsb_init(0);
+}
+
+/* Per host-thread launch context. */
+struct Ctx {
+    cudaStream_t stream = nullptr, side = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evc0 = nullptr, evc1 = nullptr;
+    void *d_buf = nullptr;  long long d_cap = 0;      /* scratch for in/out   */
+    unsigned long long *d_ctl = nullptr;              /* [work, c0..c3, flag] */
+    unsigned long long *h_ctl = nullptr;              /* pinned mirror        */
+    ~Ctx()
+    {
+        if (d_buf) cudaFree(d_buf);
+        if (d_ctl) cudaFree(d_ctl);
+        if (h_ctl) cudaFreeHost(h_ctl);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (evc0) cudaEventDestroy(evc0);
+        if (evc1) cudaEventDestroy(evc1);
+        if (stream) cudaStreamDestroy(stream);
+        if (side) cudaStreamDestroy(side);
+    }
+};
+thread_local Ctx *t_ctx = nullptr;
+
+int get_ctx(Ctx **out)
+{
+    if (ensure_init() != 0) return -1;
+    if (!t_ctx) {
+        Ctx *c = new Ctx();
+        CK(cudaSetDevice(g_device));
+        CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+        CK(cudaEventCreate(&c->ev0));
+        CK(cudaEventCreate(&c->ev1));
+        CK(cudaEventCreate(&c->evc0));
+        CK(cudaEventCreate(&c->evc1));
+        CK(cudaMalloc(&c->d_ctl, 8 * sizeof(unsigned long long)));
+        CK(cudaHostAlloc(&c->h_ctl, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
+        t_ctx = c;
+    } else {
+        CK(cudaSetDevice(g_device));
+    }
+    *out = t_ctx;
+    return 0;
+}
+
+int ctx_reserve(Ctx *c, long long bytes)
+{
+    if (bytes <= c->d_cap) return 0;
+    if (c->d_buf) { CK(cudaFree(c->d_buf)); c->d_buf = nullptr; c->d_cap = 0; }
+    long long cap = bytes + (bytes >> 3);
+    CK(cudaMalloc(&c->d_buf, (size_t)cap));
+    c->d_cap = cap;
+    return 0;
+}
+
+inline long long align256(long long x) { return (x + 255) & ~255LL; }
+
+/* grid for the persistent pixel kernels */
+template <class K> int persistent_grid(K kernel, int block, long long npts, int *grid)
+{
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0));
+    if (per_sm < 1) per_sm = 1;
+    long long g = (long long)per_sm * g_sm_count;
+    long long need = (npts + block - 1) / block;
+    if (need < 1) need = 1;
+    if (g > need) g = need;
+    *grid = (int)g;
+    return 0;
+}
+
+/* launch + wait, polling the caller's interruption flag */
+int wait_kernel(Ctx *c, const volatile uint8_t *interrupted, bool *was_interrupted)
+{
+    *was_interrupted = false;
+    int one = 1;
+    for (;;) {
+        cudaError_t q = cudaEventQuery(c->ev1);
+        if (q == cudaSuccess) break;
+        if (q != cudaErrorNotReady) CK(q);
+        if (interrupted && *interrupted && !*was_interrupted) {
+            *was_interrupted = true;
+            c->h_ctl[7] = 1;
+            CK(cudaMemcpyAsync((int *)(c->d_ctl + 5), &one, sizeof(int),
+                               cudaMemcpyHostToDevice, c->side));
+        }
+        std::this_thread::sleep_for(std::chrono::microseconds(50));
+    }
+    return 0;
+}
+
+/* ---- kernel dispatch ------------------------------------------------------ */
+typedef void (*perturb_kernel_t)(FrameDev, long long, const C *, double *, int *,
+                                 signed char *, int *, unsigned long long *,
+                                 unsigned long long *, const volatile int *);
+
+template <bool XR, bool DC, bool DZ> perturb_kernel_t pick_m2_bla(bool bla)
+{
+    return bla ? k_perturb_m2<XR, DC, DZ, true> : k_perturb_m2<XR, DC, DZ, false>;
+}
+template <bool XR, bool DC> perturb_kernel_t pick_m2_dz(bool dz, bool bla)
+{
+    return dz ? pick_m2_bla<XR, DC, true>(bla) : pick_m2_bla<XR, DC, false>(bla);
+}
+template <bool XR> perturb_kernel_t pick_m2_dc(bool dc, bool dz, bool bla)
+{
+    return dc ? pick_m2_dz<XR, true>(dz, bla) : pick_m2_dz<XR, false>(dz, bla);
+}
+perturb_kernel_t pick_m2(bool xr, bool dc, bool dz, bool bla)
+{
+    return xr ? pick_m2_dc<true>(dc, dz, bla) : pick_m2_dc<false>(dc, dz, bla);
+}
+template <bool XR, bool H> perturb_kernel_t pick_bs_bla(bool bla)
+{
+    return bla ? k_perturb_bs<XR, H, true> : k_perturb_bs<XR, H, false>;
+}
+template <bool XR> perturb_kernel_t pick_bs_h(bool h, bool bla)
+{
+    return h ? pick_bs_bla<XR, true>(bla) : pick_bs_bla<XR, false>(bla);
+}
+perturb_kernel_t pick_bs(bool xr, bool h, bool bla)
+{
+    return xr ? pick_bs_h<true>(h, bla) : pick_bs_h<false>(h, bla);
+}
+
+} /* namespace */
+
+/* ======================================================================== */
+struct fsb_frame {
+    fsb_frame_desc d;
+    FrameDev dev;
+    int nz = 0;
+    bool bla_on = false;
+    std::vector<void *> owned;
+    double ms_upload = 0, ms_dzndc = 0, ms_bla = 0;
+    long long dzndc_len = 0;
+};
+
+namespace {
+
+/* Device copy of a host table, followed by `pad` zero elements.  The orbit and
+ * the dZndc path carry one zero pad element: a pixel that walks the whole
+ * orbit by BLA steps without a rebase ends with w_iter == L and the reference
+ * reads one element past its arrays there (undefined in the reference; defined
+ * as 0 here and in the oracle). */
+template <class T> int upload(fsb_frame *f, const T *host, long long n, const T **dev,
+                              long long pad = 0)
+{
+    *dev = nullptr;
+    if (!host || n <= 0) return 0;
+    void *p = nullptr;
+    CK(cudaMalloc(&p, (size_t)((n + pad) * (long long)sizeof(T))));
+    f->owned.push_back(p);
+    CK(cudaMemcpy(p, host, (size_t)(n * (long long)sizeof(T)), cudaMemcpyHostToDevice));
+    if (pad > 0)
+        CK(cudaMemset((char *)p + n * (long long)sizeof(T), 0, (size_t)(pad * (long long)sizeof(T))));
+    *dev = (const T *)p;
+    return 0;
+}
+
+double now_ms()
+{
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+/* Stateless lookup in the sorted Xrange index (perturbation.py:2519-2588). */
+long long h_xr_find(const int32_t *index, long long n, long long idx)
+{
+    long long lo = 0, hi = n;
+    while (lo < hi) {
+        long long mid = (lo + hi) >> 1;
+        if (index[mid] < idx) lo = mid + 1; else hi = mid;
+    }
+    return (lo < n && index[lo] == idx) ? lo : -1;
+}
+
+/* dZndc path, serial recurrence on the host (perturbation.py:2282-2336).
+ * dZ[i] = 2 Z[i-1] dZ[i-1] + scale ; Xrange variant keeps (mantissa, exp). */
+void host_dzndc_m2(const fsb_frame_desc &d, std::vector<C> &out, std::vector<int32_t> &oe)
+{
+    const long long L = d.L;
+    const C *Zn = (const C *)d.Zn_path;
+    const C *rxr = (const C *)d.ref_xr;
+    long long valid = L < d.ref_div_iter ? L : d.ref_div_iter;
+    XF scale_x = mkXF(d.scale_deriv, d.scale_deriv_e);
+    double scale = to_std(scale_x);
+    out.assign((size_t)L, mkC(0., 0.));
+    oe.assign(d.xr_detect ? (size_t)L : 0, 0);
+    if (valid < 2) return;
+    if (d.xr_detect) {
+        for (long long i = 1; i < valid; i++) {
+            long long k = d.n_xr > 0 ? h_xr_find(d.ref_index_xr, d.n_xr, i - 1) : -1;
+            XC rz = (k >= 0) ? mkXC(rxr[k], d.ref_xr_e[k]) : to_xr(Zn[i - 1]);
+            XC v = (2. * rz) * mkXC(out[i - 1], oe[i - 1]) + scale_x;
+            out[i] = v.m; oe[i] = v.e;
+        }
+        long long i = valid - 1;
+        if (i == d.ref_order - 1) {
+            XC v = (2. * Zn[i]) * mkXC(out[i], oe[i]) + scale_x;
+            out[0] = v.m; oe[0] = v.e;
+        }
+    } else {
+        for (long long i = 1; i < valid; i++) out[i] = (2. * Zn[i - 1]) * out[i - 1] + scale;
+        long long i = valid - 1;
+        if (i == d.ref_order - 1) out[0] = (2. * Zn[i]) * out[i] + scale;
+    }
+}
+
+/* dZndz path (perturbation.py:2466-2516) */
+void host_dzndz_m2(const fsb_frame_desc &d, std::vector<C> &out, std::vector<int32_t> &oe)
+{
+    const long long L = d.L;
+    const C *Zn = (const C *)d.Zn_path;
+    const C *rxr = (const C *)d.ref_xr;
+    long long valid = L < d.ref_div_iter ? L : d.ref_div_iter;
+    out.assign((size_t)L + 1, mkC(0., 0.));
+    oe.assign(d.xr_detect ? (size_t)L + 1 : 0, 0);
+    out[1] = mkC(1., 0.);
+    if (valid < 3) return;
+    if (d.xr_detect) {
+        for (long long i = 2; i < valid; i++) {
+            long long k = d.n_xr > 0 ? h_xr_find(d.ref_index_xr, d.n_xr, i - 1) : -1;
+            XC rz = (k >= 0) ? mkXC(rxr[k], d.ref_xr_e[k]) : to_xr(Zn[i - 1]);
+            XC v = (2. * rz) * mkXC(out[i - 1], oe[i - 1]);
+            out[i] = v.m; oe[i] = v.e;
+        }
+        long long i = valid - 1;
+        long long k = d.n_xr > 0 ? h_xr_find(d.ref_index_xr, d.n_xr, i) : -1;
+        XC rz = (k >= 0) ? mkXC(rxr[k], d.ref_xr_e[k]) : to_xr(Zn[i]);
+        XC v = (2. * rz) * mkXC(out[i], oe[i]);
+        out[L] = v.m; oe[L] = v.e;
+    } else {
+        for (long long i = 2; i < valid; i++) out[i] = (2. * Zn[i - 1]) * out[i - 1];
+        long long i = valid - 1;
+        out[L] = (2. * Zn[i]) * out[i];
+    }
+}
+
+/* burning_ship.py:441-532 on the host, plain double and Xrange */
+void h_bs_jac(int flavor, double x, double y, double &fxx, double &fxy, double &fyx, double &fyy)
+{
+    switch (flavor) {
+    case 1: fxx = 2. * x; fxy = -2. * y; fyx = 2. * sgn(x) * fabs(y); fyy = 2. * sgn(y) * fabs(x); break;
+    case 2: fxx = 2. * x; fxy = -2. * y; fyx = 2. * fabs(y); fyy = 2. * sgn(y) * x; break;
+    case 3: fxx = 2. * x; fxy = -2. * fabs(y); fyx = 2. * y; fyy = 2. * x; break;
+    case 4: { double s = sgn(x * x - y * y); fxx = 2. * s * x; fxy = -2. * s * y; fyx = 2. * y; fyy = 2. * x; break; }
+    default: { double s = sgn(x * x - y * y); fxx = 2. * s * x; fxy = -2. * s * y; fyx = 2. * sgn(x) * fabs(y); fyy = 2. * sgn(y) * fabs(x); break; }
+    }
+}
+void h_bs_jac(int flavor, XF x, XF y, XF &fxx, XF &fxy, XF &fyx, XF &fyy)
+{
+    switch (flavor) {
+    case 1: fxx = 2. * x; fxy = -2. * y; fyx = 2. * sgn_(x) * fabs_(y); fyy = 2. * sgn_(y) * fabs_(x); break;
+    case 2: fxx = 2. * x; fxy = -2. * y; fyx = 2. * fabs_(y); fyy = 2. * sgn_(y) * x; break;
+    case 3: fxx = 2. * x; fxy = -2. * fabs_(y); fyx = 2. * y; fyy = 2. * x; break;
+    case 4: { double s = sgn_(x * x - y * y); fxx = 2. * s * x; fxy = -2. * s * y; fyx = 2. * y; fyy = 2. * x; break; }
+    default: { double s = sgn_(x * x - y * y); fxx = 2. * s * x; fxy = -2. * s * y; fyx = 2. * sgn_(x) * fabs_(y); fyy = 2. * sgn_(y) * fabs_(x); break; }
+    }
+}
+
+/* perturbation.py:2339-2463 ; out = [dXnda | dXndb | dYnda | dYndb] */
+void host_dzndc_bs(const fsb_frame_desc &d, std::vector<double> &out, std::vector<int32_t> &oe)
+{
+    const long long L = d.L;
+    const double *Zn = d.Zn_path;
+    long long valid = L < d.ref_div_iter ? L : d.ref_div_iter;
+    XF scale_x = mkXF(d.scale_deriv, d.scale_deriv_e);
+    double scale = to_std(scale_x);
+    out.assign((size_t)(4 * L), 0.);
+    oe.assign(d.xr_detect ? (size_t)(4 * L) : 0, 0);
+    if (valid < 2) return;
+    double *A = out.data(), *B = A + L, *Cc = A + 2 * L, *D = A + 3 * L;
+    int32_t *Ae = oe.data(), *Be = Ae + L, *Ce = Ae + 2 * L, *De = Ae + 3 * L;
+    long long n_steps = valid - 1;
+    bool wrap = ((valid - 1) == d.ref_order - 1);
+    for (long long s = 0; s < n_steps + (wrap ? 1 : 0); s++) {
+        long long from_i = (s < n_steps) ? s : valid - 1;
+        long long to_i = (s < n_steps) ? s + 1 : 0;
+        double X = Zn[2 * from_i], Y = Zn[2 * from_i + 1];
+        if (d.xr_detect) {
+            long long k = d.n_xr > 0 ? h_xr_find(d.ref_index_xr, d.n_xr, from_i) : -1;
+            XF rx = (k >= 0) ? mkXF(d.ref_xr[k], d.ref_xr_e[k]) : to_xr(X);
+            XF ry = (k >= 0) ? mkXF(d.refy_xr[k], d.refy_xr_e[k]) : to_xr(Y);
+            XF fxx, fxy, fyx, fyy;
+            h_bs_jac(d.flavor, rx, ry, fxx, fxy, fyx, fyy);
+            XF a = mkXF(A[from_i], Ae[from_i]), b = mkXF(B[from_i], Be[from_i]);
+            XF c = mkXF(Cc[from_i], Ce[from_i]), dd = mkXF(D[from_i], De[from_i]);
+            XF na = fxx * a + fxy * c + scale_x;
+            XF nb = fxx * b + fxy * dd;
+            XF nc = fyx * a + fyy * c;
+            XF nd = fyx * b + fyy * dd - scale_x;
+            A[to_i] = na.m; Ae[to_i] = na.e; B[to_i] = nb.m; Be[to_i] = nb.e;
+            Cc[to_i] = nc.m; Ce[to_i] = nc.e; D[to_i] = nd.m; De[to_i] = nd.e;
+        } else {
+            double fxx, fxy, fyx, fyy;
+            h_bs_jac(d.flavor, X, Y, fxx, fxy, fyx, fyy);
+            double a = A[from_i], b = B[from_i], c = Cc[from_i], dd = D[from_i];
+            A[to_i] = fxx * a + fxy * c + scale;
+            B[to_i] = fxx * b + fxy * dd;
+            Cc[to_i] = fyx * a + fyy * c;
+            D[to_i] = fyx * b + fyy * dd - scale;
+        }
+    }
+}
+
+int stages_bla_of(long long L)
+{
+    int s = 0;
+    while ((1LL << s) < L) s++;
+    return s;
+}
+
+/* K5: BLA tree on the device */
+int build_bla(fsb_frame *f)
+{
+    const fsb_frame_desc &d = f->d;
+    long long comp_len = d.L / 8;
+    long long bla_len = 2 * comp_len;
+    int stages = stages_bla_of(d.L);
+    f->dev.bla_len = bla_len;
+    f->dev.stages_bla = stages;
+    if (comp_len == 0) return 0;
+    double kc_std = to_std(mkXF(d.kc, d.kc_e));
+    int width = (d.model == FSB_MODEL_M2) ? 4 : 8; /* doubles per node */
+    void *dM = nullptr, *dr = nullptr;
+    CK(cudaMalloc(&dM, (size_t)(bla_len * width * 8)));
+    f->owned.push_back(dM);
+    CK(cudaMalloc(&dr, (size_t)(bla_len * 8)));
+    f->owned.push_back(dr);
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, 0));
+    int block = 128;
+    int grid = (int)((comp_len + block - 1) / block);
+    if (d.model == FSB_MODEL_M2)
+        k_bla_leaf_m2<<<grid, block>>>(f->dev.Zn, comp_len, kc_std, d.BLA_eps, (C *)dM, (double *)dr);
+    else
+        k_bla_leaf_bs<<<grid, block>>>(d.flavor, f->dev.Zn, comp_len, kc_std, d.BLA_eps,
+                                       (double *)dM, (double *)dr);
+    for (int stg = 1; stg < stages - 3; stg++) {
+        long long n_out = (comp_len >> stg) + 1;
+        int g = (int)((n_out + block - 1) / block);
+        if (d.model == FSB_MODEL_M2)
+            k_bla_merge_m2<<<g, block>>>(comp_len, stg, kc_std, d.BLA_eps, (C *)dM, (double *)dr);
+        else
+            k_bla_merge_bs<<<g, block>>>(comp_len, stg, kc_std, d.BLA_eps, (double *)dM, (double *)dr);
+    }
+    CK(cudaEventRecord(e1, 0));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaGetLastError());
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    f->ms_bla = ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    f->dev.M_bla = (const double *)dM;
+    f->dev.r_bla = (const double *)dr;
+    return 0;
+}
+
+int frame_nz(const fsb_frame_desc &d)
+{
+    if (d.model == FSB_MODEL_M2)
+        return 1 + (d.calc_dzndz ? 1 : 0) + (d.calc_dzndc ? 1 : 0) + (d.calc_orbit ? 1 : 0);
+    return 2 + (d.calc_dzndc ? 4 : 0) + (d.calc_orbit ? 2 : 0);
+}
+
+} /* namespace */
+
+/* ======================================================================== */
+extern "C" {
+
+const char *fsb_last_error(void) { return g_err.c_str(); }
+
+const char *fsb_build_info(void)
+{
+#ifdef FSB_STRICT
+    return "fsb200 sm_100a fmad=off (IEEE-strict build)";
+#else
+    return "fsb200 sm_100a fmad=on (default build)";
+#endif
+}
+
+int fsb_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        fail(-1, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+        return -1;
+    }
+    return n;
+}
+
+int fsb_init(int device)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        return fail(-2, "no CUDA device available (%s): libfsb200 has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(-2, "device %d out of range (0..%d)", device, n - 1);
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(-2, "device %s is sm_%d%d; this library is built for sm_100a only",
+                    prop.name, prop.major, prop.minor);
+    g_device = device;
+    g_sm_count = prop.multiProcessorCount;
+    return 0;
+}
+
+void fsb_shutdown(void)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (g_flush_buf) { cudaFree(g_flush_buf); g_flush_buf = nullptr; }
+    if (t_ctx) { delete t_ctx; t_ctx = nullptr; }
+    g_device = -1;
+}
+
+int fsb_device_info(char *name, int name_cap, int *sm_count, int64_t *mem_bytes)
+{
+    if (ensure_init() != 0) return -1;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, g_device));
+    if (name && name_cap > 0) snprintf(name, (size_t)name_cap, "%s", prop.name);
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (mem_bytes) *mem_bytes = (int64_t)prop.totalGlobalMem;
+    return 0;
+}
+
+void *fsb_host_alloc(int64_t bytes)
+{
+    if (ensure_init() != 0) return nullptr;
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault) != cudaSuccess) {
+        fail(-1, "cudaHostAlloc(%lld) failed", (long long)bytes);
+        return nullptr;
+    }
+    return p;
+}
+void fsb_host_free(void *p) { if (p) cudaFreeHost(p); }
+void *fsb_dev_alloc(int64_t bytes)
+{
+    if (ensure_init() != 0) return nullptr;
+    void *p = nullptr;
+    if (cudaMalloc(&p, (size_t)bytes) != cudaSuccess) {
+        fail(-1, "cudaMalloc(%lld) failed", (long long)bytes);
+        return nullptr;
+    }
+    return p;
+}
+void fsb_dev_free(void *p) { if (p) cudaFree(p); }
+int fsb_memcpy_h2d(void *dst, const void *src, int64_t bytes)
+{
+    if (ensure_init() != 0) return -1;
+    CK(cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyHostToDevice));
+    return 0;
+}
+int fsb_memcpy_d2h(void *dst, const void *src, int64_t bytes)
+{
+    if (ensure_init() != 0) return -1;
+    CK(cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int fsb_dev_memset(void *dst, int value, int64_t bytes)
+{
+    if (ensure_init() != 0) return -1;
+    CK(cudaMemset(dst, value, (size_t)bytes));
+    return 0;
+}
+int fsb_flush_l2(void)
+{
+    if (ensure_init() != 0) return -1;
+    if (!g_flush_buf) {
+        CK(cudaMalloc(&g_flush_buf, (size_t)(FLUSH_DOUBLES * 8)));
+        CK(cudaMemset(g_flush_buf, 0, (size_t)(FLUSH_DOUBLES * 8)));
+    }
+    k_flush<<<g_sm_count * 8, 256>>>(g_flush_buf, FLUSH_DOUBLES);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    return 0;
+}
+
+/* ---- standard loops ------------------------------------------------------ */
+int fsb_std_nz(const fsb_std_desc *d)
+{
+    if (d->model == FSB_MODEL_M2) return 3 + (d->calc_d2zndc2 ? 1 : 0) + (d->calc_orbit ? 1 : 0);
+    return 6 + (d->calc_orbit ? 2 : 0);
+}
+
+static int std_launch(Ctx *c, const fsb_std_desc *d, long long npts, const C *d_c_pix,
+                      double *d_Z, signed char *d_sr, int *d_si,
+                      const volatile uint8_t *interrupted, fsb_stats *stats, bool *was_int)
+{
+    if (d->model != FSB_MODEL_M2 && d->model != FSB_MODEL_BS)
+        return fail(-3, "unsupported standard model %d", d->model);
+    if (d->model == FSB_MODEL_BS && (d->flavor < 1 || d->flavor > 5))
+        return fail(-3, "unsupported burning-ship flavor %d", d->flavor);
+    if (d->calc_orbit && d->backshift <= 0) return fail(-3, "calc_orbit needs backshift > 0");
+    StdDev p;
+    p.center_re = d->center_re; p.center_im = d->center_im; p.dx = d->dx;
+    for (int i = 0; i < 4; i++) p.lin_mat[i] = d->lin_mat[i];
+    p.max_iter = d->max_iter; p.Mdiv_sq = d->M_divergence_sq; p.eps_sq = d->epsilon_stationnary_sq;
+    p.calc_d2 = d->calc_d2zndc2; p.calc_orbit = d->calc_orbit; p.backshift = d->backshift;
+    p.flavor = d->flavor;
+    CK(cudaMemsetAsync(c->d_ctl, 0, 8 * sizeof(unsigned long long), c->stream));
+    const int block = 256;
+    int grid = 1;
+    if (d->model == FSB_MODEL_M2) { if (persistent_grid(k_std_m2, block, npts, &grid)) return -1; }
+    else { if (persistent_grid(k_std_bs, block, npts, &grid)) return -1; }
+    CK(cudaEventRecord(c->ev0, c->stream));
+    if (d->model == FSB_MODEL_M2)
+        k_std_m2<<<grid, block, 0, c->stream>>>(p, npts, d_c_pix, d_Z, d_sr, d_si, c->d_ctl,
+                                                c->d_ctl + 1, (const volatile int *)(c->d_ctl + 5));
+    else
+        k_std_bs<<<grid, block, 0, c->stream>>>(p, npts, d_c_pix, d_Z, d_sr, d_si, c->d_ctl,
+                                                c->d_ctl + 1, (const volatile int *)(c->d_ctl + 5));
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev1, c->stream));
+    if (wait_kernel(c, interrupted, was_int)) return -1;
+    CK(cudaStreamSynchronize(c->side));
+    CK(cudaMemcpyAsync(c->h_ctl, c->d_ctl, 5 * sizeof(unsigned long long),
+                       cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (stats) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        stats->kernel_ms = ms;
+        stats->n_iter_exec = (int64_t)c->h_ctl[1];
+        stats->n_bla_steps = 0;
+        stats->n_rebase = 0;
+        stats->sum_stop_iter = (int64_t)c->h_ctl[4];
+        stats->n_launches = 1;
+    }
+    return 0;
+}
+
+int fsb_std_run_device(const fsb_std_desc *d, int64_t npts, const double *d_c_pix, double *d_Z,
+                       int8_t *d_stop_reason, int32_t *d_stop_iter, fsb_stats *stats)
+{
+    Ctx *c;
+    if (get_ctx(&c)) return -1;
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (npts <= 0) return 0;
+    bool was_int = false;
+    return std_launch(c, d, npts, (const C *)d_c_pix, d_Z, (signed char *)d_stop_reason,
+                      d_stop_iter, nullptr, stats, &was_int);
+}
+
+int fsb_std_run(const fsb_std_desc *d, int64_t npts, const double *c_pix, double *Z,
+                int8_t *stop_reason, int32_t *stop_iter, const volatile uint8_t *interrupted,
+                fsb_stats *stats)
+{
+    Ctx *c;
+    if (get_ctx(&c)) return -1;
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (npts <= 0) return 0;
+    if (interrupted && *interrupted) return FSB_USER_INTERRUPTED;
+    const int nz = fsb_std_nz(d);
+    const long long zelem = (d->model == FSB_MODEL_M2) ? 16 : 8;
+    long long o_c = 0, o_Z = align256(o_c + npts * 16), o_si = align256(o_Z + nz * npts * zelem),
+              o_sr = align256(o_si + npts * 4), total = align256(o_sr + npts);
+    if (ctx_reserve(c, total)) return -1;
+    char *base = (char *)c->d_buf;
+    CK(cudaEventRecord(c->evc0, c->stream));
+    CK(cudaMemcpyAsync(base + o_c, c_pix, (size_t)(npts * 16), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(base + o_Z, 0, (size_t)(nz * npts * zelem), c->stream));
+    CK(cudaMemsetAsync(base + o_si, 0, (size_t)(npts * 4), c->stream));
+    CK(cudaMemsetAsync(base + o_sr, 0xff, (size_t)npts, c->stream));
+    CK(cudaEventRecord(c->evc1, c->stream));
+    bool was_int = false;
+    int rc = std_launch(c, d, npts, (const C *)(base + o_c), (double *)(base + o_Z),
+                        (signed char *)(base + o_sr), (int *)(base + o_si), interrupted, stats,
+                        &was_int);
+    if (rc) return rc;
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, c->evc0, c->evc1));
+    if (stats) stats->h2d_ms = ms;
+    CK(cudaEventRecord(c->evc0, c->stream));
+    CK(cudaMemcpyAsync(Z, base + o_Z, (size_t)(nz * npts * zelem), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(stop_iter, base + o_si, (size_t)(npts * 4), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(stop_reason, base + o_sr, (size_t)npts, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaEventRecord(c->evc1, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaEventElapsedTime(&ms, c->evc0, c->evc1));
+    if (stats) stats->d2h_ms = ms;
+    return was_int ? FSB_USER_INTERRUPTED : 0;
+}
+
+/* ---- perturbation frames -------------------------------------------------- */
+int fsb_frame_create(const fsb_frame_desc *desc, fsb_frame **out)
+{
+    if (ensure_init() != 0) return -1;
+    CK(cudaSetDevice(g_device));
+    if (!desc || !out) return fail(-3, "null argument");
+    *out = nullptr;
+    if (desc->model != FSB_MODEL_M2 && desc->model != FSB_MODEL_BS)
+        return fail(-3, "unsupported model %d (no fallback)", desc->model);
+    if (desc->model == FSB_MODEL_BS && (desc->flavor < 1 || desc->flavor > 5))
+        return fail(-3, "unsupported burning-ship flavor %d", desc->flavor);
+    if (desc->L < 2 || !desc->Zn_path) return fail(-3, "reference orbit missing or too short");
+    if (desc->calc_orbit && desc->backshift <= 0) return fail(-3, "calc_orbit needs backshift > 0");
+    if (desc->model == FSB_MODEL_BS && desc->calc_dzndz)
+        return fail(-3, "interior detection is not defined for the burning-ship family");
+    if (desc->n_xr > 0 && (!desc->ref_index_xr || !desc->ref_xr || !desc->ref_xr_e))
+        return fail(-3, "Xrange reference arrays missing");
+
+    fsb_frame *f = new fsb_frame();
+    f->d = *desc;
+    const fsb_frame_desc &d = f->d;
+    FrameDev &v = f->dev;
+    memset(&v, 0, sizeof v);
+    const long long L = d.L;
+    double t0 = now_ms();
+    int rc = 0;
+#define UP(expr) do { if ((rc = (expr)) != 0) { fsb_frame_destroy(f); return rc; } } while (0)
+    v.L = L;
+    UP(upload(f, (const C *)d.Zn_path, L, &v.Zn, 1));
+    v.n_xr = d.n_xr;
+    UP(upload(f, d.ref_index_xr, d.n_xr, &v.ref_index_xr));
+    if (d.model == FSB_MODEL_M2) {
+        UP(upload(f, (const C *)d.ref_xr, d.n_xr, &v.ref_xr));
+        UP(upload(f, d.ref_xr_e, d.n_xr, &v.ref_xr_e));
+    } else {
+        UP(upload(f, d.ref_xr, d.n_xr, &v.refx_xr));
+        UP(upload(f, d.ref_xr_e, d.n_xr, &v.refx_xr_e));
+        UP(upload(f, d.refy_xr, d.n_xr, &v.refy_xr));
+        UP(upload(f, d.refy_xr_e, d.n_xr, &v.refy_xr_e));
+    }
+    v.ref_div_iter = d.ref_div_iter;
+    v.ref_order = d.ref_order;
+    v.drift[0] = d.drift[0]; v.drift[1] = d.drift[1];
+    v.drift_e[0] = d.drift_e[0]; v.drift_e[1] = d.drift_e[1];
+    v.lin_scale = d.lin_scale; v.lin_scale_e = d.lin_scale_e;
+    for (int i = 0; i < 4; i++) v.lin_mat[i] = d.lin_mat[i];
+    v.max_iter = d.max_iter;
+    v.Mdiv_sq = d.M_divergence_sq;
+    v.eps_sq = d.epsilon_stationnary_sq;
+    v.calc_orbit = d.calc_orbit;
+    v.backshift = d.backshift;
+    v.flavor = d.flavor;
+    f->nz = frame_nz(d);
+    f->ms_upload = now_ms() - t0;
+
+    /* reference derivative paths */
+    t0 = now_ms();
+    if (d.calc_dzndc) {
+        if (d.model == FSB_MODEL_M2) {
+            if (d.dZndc) {
+                UP(upload(f, (const C *)d.dZndc, L, &v.dZndc, 1));
+                if (d.xr_detect) UP(upload(f, d.dZndc_e, L, &v.dZndc_e, 1));
+            } else {
+                std::vector<C> p; std::vector<int32_t> pe;
+                host_dzndc_m2(d, p, pe);
+                UP(upload(f, p.data(), L, &v.dZndc, 1));
+                if (d.xr_detect) UP(upload(f, (const int *)pe.data(), L, &v.dZndc_e, 1));
+            }
+        } else {
+            std::vector<double> p; std::vector<int32_t> pe;
+            const double *src = d.dZndc; const int32_t *srce = d.dZndc_e;
+            if (!src) { host_dzndc_bs(d, p, pe); src = p.data(); srce = pe.data(); }
+            const double *dp = nullptr; const int *dpe = nullptr;
+            UP(upload(f, src, 4 * L, &dp));
+            if (d.xr_detect) UP(upload(f, (const int *)srce, 4 * L, &dpe));
+            for (int j = 0; j < 4; j++) {
+                v.dP[j] = dp + j * L;
+                v.dP_e[j] = dpe ? dpe + j * L : nullptr;
+            }
+        }
+    }
+    if (d.calc_dzndz) {
+        if (d.dZndz) {
+            UP(upload(f, (const C *)d.dZndz, L + 1, &v.dZndz));
+            if (d.xr_detect) UP(upload(f, d.dZndz_e, L + 1, &v.dZndz_e));
+        } else {
+            std::vector<C> p; std::vector<int32_t> pe;
+            host_dzndz_m2(d, p, pe);
+            UP(upload(f, p.data(), L + 1, &v.dZndz));
+            if (d.xr_detect) UP(upload(f, (const int *)pe.data(), L + 1, &v.dZndz_e));
+        }
+    }
+    f->ms_dzndc = now_ms() - t0;
+
+    /* BLA tree */
+    f->bla_on = d.bla_activated != 0;
+    if (f->bla_on) {
+        if (d.M_bla && d.r_bla) {
+            int width = (d.model == FSB_MODEL_M2) ? 4 : 8;
+            UP(upload(f, d.M_bla, d.bla_len * width, &v.M_bla));
+            UP(upload(f, d.r_bla, d.bla_len, &v.r_bla));
+            v.bla_len = d.bla_len;
+            v.stages_bla = d.stages_bla;
+        } else {
+            UP(build_bla(f));
+        }
+        if (v.stages_bla <= 3 || v.bla_len == 0) f->bla_on = false;
+    }
+#undef UP
+    /* the descriptor copy must not keep caller pointers alive */
+    f->d.Zn_path = nullptr; f->d.ref_index_xr = nullptr; f->d.ref_xr = nullptr;
+    f->d.ref_xr_e = nullptr; f->d.refy_xr = nullptr; f->d.refy_xr_e = nullptr;
+    f->d.dZndc = nullptr; f->d.dZndc_e = nullptr; f->d.dZndz = nullptr; f->d.dZndz_e = nullptr;
+    f->d.M_bla = nullptr; f->d.r_bla = nullptr;
+    *out = f;
+    return 0;
+}
+
+int fsb_frame_destroy(fsb_frame *f)
+{
+    if (!f) return 0;
+    for (void *p : f->owned) cudaFree(p);
+    delete f;
+    return 0;
+}
+
+int fsb_frame_nz(const fsb_frame *f) { return f ? f->nz : -1; }
+int64_t fsb_frame_bla_len(const fsb_frame *f) { return f ? f->dev.bla_len : -1; }
+int fsb_frame_stages_bla(const fsb_frame *f) { return f ? f->dev.stages_bla : -1; }
+double fsb_frame_setup_ms(const fsb_frame *f, int what)
+{
+    if (!f) return -1.;
+    return what == 0 ? f->ms_upload : (what == 1 ? f->ms_dzndc : f->ms_bla);
+}
+
+int fsb_frame_get_bla(const fsb_frame *f, double *M_bla, double *r_bla)
+{
+    if (!f || !f->dev.M_bla) return fail(-3, "frame has no BLA table");
+    int width = (f->d.model == FSB_MODEL_M2) ? 4 : 8;
+    CK(cudaMemcpy(M_bla, f->dev.M_bla, (size_t)(f->dev.bla_len * width * 8), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(r_bla, f->dev.r_bla, (size_t)(f->dev.bla_len * 8), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int fsb_frame_get_dzndc(const fsb_frame *f, double *dZndc, int32_t *dZndc_e)
+{
+    if (!f) return fail(-3, "null frame");
+    const long long L = f->d.L;
+    if (f->d.model == FSB_MODEL_M2) {
+        if (!f->dev.dZndc) return fail(-3, "frame has no dZndc path");
+        CK(cudaMemcpy(dZndc, f->dev.dZndc, (size_t)(L * 16), cudaMemcpyDeviceToHost));
+        if (f->dev.dZndc_e && dZndc_e)
+            CK(cudaMemcpy(dZndc_e, f->dev.dZndc_e, (size_t)(L * 4), cudaMemcpyDeviceToHost));
+    } else {
+        if (!f->dev.dP[0]) return fail(-3, "frame has no dZndc path");
+        CK(cudaMemcpy(dZndc, f->dev.dP[0], (size_t)(4 * L * 8), cudaMemcpyDeviceToHost));
+        if (f->dev.dP_e[0] && dZndc_e)
+            CK(cudaMemcpy(dZndc_e, f->dev.dP_e[0], (size_t)(4 * L * 4), cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
+int fsb_frame_get_dzndz(const fsb_frame *f, double *dZndz, int32_t *dZndz_e)
+{
+    if (!f || !f->dev.dZndz) return fail(-3, "frame has no dZndz path");
+    const long long L = f->d.L;
+    CK(cudaMemcpy(dZndz, f->dev.dZndz, (size_t)((L + 1) * 16), cudaMemcpyDeviceToHost));
+    if (f->dev.dZndz_e && dZndz_e)
+        CK(cudaMemcpy(dZndz_e, f->dev.dZndz_e, (size_t)((L + 1) * 4), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+static int frame_launch(Ctx *c, fsb_frame *f, long long npts, const C *d_c_pix, double *d_Z,
+                        int *d_U, signed char *d_sr, int *d_si,
+                        const volatile uint8_t *interrupted, fsb_stats *stats, bool *was_int)
+{
+    const fsb_frame_desc &d = f->d;
+    perturb_kernel_t k = (d.model == FSB_MODEL_M2)
+        ? pick_m2(d.xr_detect != 0, d.calc_dzndc != 0, d.calc_dzndz != 0, f->bla_on)
+        : pick_bs(d.xr_detect != 0, d.calc_dzndc != 0, f->bla_on);
+    CK(cudaMemsetAsync(c->d_ctl, 0, 8 * sizeof(unsigned long long), c->stream));
+    const int block = 128;
+    int grid = 1;
+    if (persistent_grid(k, block, npts, &grid)) return -1;
+    CK(cudaEventRecord(c->ev0, c->stream));
+    k<<<grid, block, 0, c->stream>>>(f->dev, npts, d_c_pix, d_Z, d_U, d_sr, d_si, c->d_ctl,
+                                     c->d_ctl + 1, (const volatile int *)(c->d_ctl + 5));
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev1, c->stream));
+    if (wait_kernel(c, interrupted, was_int)) return -1;
+    CK(cudaStreamSynchronize(c->side));
+    CK(cudaMemcpyAsync(c->h_ctl, c->d_ctl, 5 * sizeof(unsigned long long),
+                       cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (stats) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        stats->kernel_ms = ms;
+        stats->n_iter_exec = (int64_t)c->h_ctl[1];
+        stats->n_bla_steps = (int64_t)c->h_ctl[2];
+        stats->n_rebase = (int64_t)c->h_ctl[3];
+        stats->sum_stop_iter = (int64_t)c->h_ctl[4];
+        stats->n_launches = 1;
+    }
+    return 0;
+}
+
+int fsb_frame_run_device(fsb_frame *f, int64_t npts, const double *d_c_pix, double *d_Z,
+                         int32_t *d_U, int8_t *d_stop_reason, int32_t *d_stop_iter,
+                         fsb_stats *stats)
+{
+    Ctx *c;
+    if (get_ctx(&c)) return -1;
+    if (!f) return fail(-3, "null frame");
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (npts <= 0) return 0;
+    bool was_int = false;
+    return frame_launch(c, f, npts, (const C *)d_c_pix, d_Z, d_U, (signed char *)d_stop_reason,
+                        d_stop_iter, nullptr, stats, &was_int);
+}
+
+int fsb_frame_run(fsb_frame *f, int64_t npts, const double *c_pix, double *Z, int32_t *U,
+                  int8_t *stop_reason, int32_t *stop_iter, const volatile uint8_t *interrupted,
+                  fsb_stats *stats)
+{
+    Ctx *c;
+    if (get_ctx(&c)) return -1;
+    if (!f) return fail(-3, "null frame");
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (npts <= 0) return 0;
+    if (interrupted && *interrupted) return FSB_USER_INTERRUPTED;
+    const int nz = f->nz;
+    const long long zelem = (f->d.model == FSB_MODEL_M2) ? 16 : 8;
+    long long o_c = 0, o_Z = align256(o_c + npts * 16), o_U = align256(o_Z + nz * npts * zelem),
+              o_si = align256(o_U + npts * 4), o_sr = align256(o_si + npts * 4),
+              total = align256(o_sr + npts);
+    if (ctx_reserve(c, total)) return -1;
+    char *base = (char *)c->d_buf;
+    CK(cudaEventRecord(c->evc0, c->stream));
+    CK(cudaMemcpyAsync(base + o_c, c_pix, (size_t)(npts * 16), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(base + o_Z, 0, (size_t)(o_si + npts * 4 - o_Z), c->stream));
+    CK(cudaMemsetAsync(base + o_sr, 0xff, (size_t)npts, c->stream));
+    CK(cudaEventRecord(c->evc1, c->stream));
+    bool was_int = false;
+    int rc = frame_launch(c, f, npts, (const C *)(base + o_c), (double *)(base + o_Z),
+                          (int *)(base + o_U), (signed char *)(base + o_sr), (int *)(base + o_si),
+                          interrupted, stats, &was_int);
+    if (rc) return rc;
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, c->evc0, c->evc1));
+    if (stats) stats->h2d_ms = ms;
+    CK(cudaEventRecord(c->evc0, c->stream));
+    CK(cudaMemcpyAsync(Z, base + o_Z, (size_t)(nz * npts * zelem), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(U, base + o_U, (size_t)(npts * 4), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(stop_iter, base + o_si, (size_t)(npts * 4), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(stop_reason, base + o_sr, (size_t)npts, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaEventRecord(c->evc1, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaEventElapsedTime(&ms, c->evc0, c->evc1));
+    if (stats) stats->d2h_ms = ms;
+    return was_int ? FSB_USER_INTERRUPTED : 0;
+}
+
+/* ---- unit-test / calibration entry points --------------------------------- */
+int fsb_xr_binop_c(int op, int64_t n, const double *a, const int32_t *ae, const double *b,
+                   const int32_t *be, double *out, int32_t *oute)
+{
+    if (ensure_init() != 0) return -1;
+    if (n <= 0) return 0;
+    C *da, *db, *dout; int *dae, *dbe, *doe;
+    CK(cudaMalloc(&da, n * 16)); CK(cudaMalloc(&db, n * 16)); CK(cudaMalloc(&dout, n * 16));
+    CK(cudaMalloc(&dae, n * 4)); CK(cudaMalloc(&dbe, n * 4)); CK(cudaMalloc(&doe, n * 4));
+    CK(cudaMemcpy(da, a, n * 16, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(db, b, n * 16, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dae, ae, n * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dbe, be, n * 4, cudaMemcpyHostToDevice));
+    k_xr_binop_c<<<(int)((n + 127) / 128), 128>>>(op, n, da, dae, db, dbe, dout, doe);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out, dout, n * 16, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(oute, doe, n * 4, cudaMemcpyDeviceToHost));
+    cudaFree(da); cudaFree(db); cudaFree(dout); cudaFree(dae); cudaFree(dbe); cudaFree(doe);
+    return 0;
+}
+
+int fsb_xr_to_standard_c(int64_t n, const double *a, const int32_t *ae, double *out)
+{
+    if (ensure_init() != 0) return -1;
+    if (n <= 0) return 0;
+    C *da, *dout; int *dae;
+    CK(cudaMalloc(&da, n * 16)); CK(cudaMalloc(&dout, n * 16)); CK(cudaMalloc(&dae, n * 4));
+    CK(cudaMemcpy(da, a, n * 16, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dae, ae, n * 4, cudaMemcpyHostToDevice));
+    k_xr_to_standard_c<<<(int)((n + 127) / 128), 128>>>(n, da, dae, dout);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out, dout, n * 16, cudaMemcpyDeviceToHost));
+    cudaFree(da); cudaFree(dout); cudaFree(dae);
+    return 0;
+}
+
+int fsb_hypot_test(int64_t n, const double *x, const double *y, double *out)
+{
+    if (ensure_init() != 0) return -1;
+    if (n <= 0) return 0;
+    double *dx, *dy, *dout;
+    CK(cudaMalloc(&dx, n * 8)); CK(cudaMalloc(&dy, n * 8)); CK(cudaMalloc(&dout, n * 8));
+    CK(cudaMemcpy(dx, x, n * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dy, y, n * 8, cudaMemcpyHostToDevice));
+    k_hypot<<<(int)((n + 127) / 128), 128>>>(n, dx, dy, dout);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out, dout, n * 8, cudaMemcpyDeviceToHost));
+    cudaFree(dx); cudaFree(dy); cudaFree(dout);
+    return 0;
+}
+
+double fsb_fp64_peak_tflops(int iters)
+{
+    if (ensure_init() != 0) return -1.;
+    double *dout = nullptr;
+    if (cudaMalloc(&dout, 8) != cudaSuccess) return -1.;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int block = 256, grid = g_sm_count * 8;
+    k_fp64_peak<<<grid, block>>>(1000, dout); /* warm-up */
+    cudaDeviceSynchronize();
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; rep++) {
+        cudaEventRecord(e0, 0);
+        k_fp64_peak<<<grid, block>>>(iters, dout);
+        cudaEventRecord(e1, 0);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(dout);
+    if (cudaGetLastError() != cudaSuccess) return -1.;
+    double flops = (double)grid * block * 8.0 * (double)iters * 2.0;
+    return flops / (best * 1e-3) / 1e12;
+}
+
+} /* extern "C" */

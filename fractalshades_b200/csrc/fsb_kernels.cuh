@@ -1,0 +1,1197 @@
+/*
+ * fsb_kernels.cuh -- sm_100a device kernels of libfsb200.
+ *
+ *   k_std_m2 / k_std_bs        standard escape-time loops
+ *                              (reference core.py:2935-3056,
+ *                               models/mandelbrot_M2.py:310-334,
+ *                               models/burning_ship.py:351-423)
+ *   k_perturb_m2<...>          holomorphic perturbation loop
+ *                              (perturbation.py:988-1400,
+ *                               models/mandelbrot_M2.py:591-627)
+ *   k_perturb_bs<...>          burning-ship family perturbation loop
+ *                              (perturbation.py:1406-1811,
+ *                               models/burning_ship.py:12-60,441-858)
+ *   k_bla_leaf_* / k_bla_merge_*  BLA tree build (perturbation.py:1819-2105)
+ *
+ * Work distribution: persistent CTAs; each warp takes 32 consecutive points of
+ * the tile-ordered point list from a global counter (warp-level work stealing),
+ * so a warp's lanes are neighbouring pixels of one image row: they follow the
+ * same reference-orbit index for most of their life (warp-uniform, L1-resident
+ * orbit/BLA reads) and the warp is released as soon as its slowest lane ends.
+ * Outputs are written as coalesced planes (one row of Z / U / stop_* each).
+ */
+#pragma once
+#include "fsb_math.cuh"
+
+namespace fsb {
+
+struct FrameDev {
+    long long L;
+    const C *Zn;
+    /* holomorphic */
+    const C *dZndc; const int *dZndc_e;
+    const C *dZndz; const int *dZndz_e;
+    const C *ref_xr; const int *ref_xr_e;
+    /* burning ship family */
+    const double *dP[4]; const int *dP_e[4];
+    const double *refx_xr; const int *refx_xr_e;
+    const double *refy_xr; const int *refy_xr_e;
+    long long n_xr; const int *ref_index_xr;
+    long long ref_div_iter, ref_order;
+    double drift[2]; int drift_e[2];
+    double lin_scale; int lin_scale_e;
+    double lin_mat[4];
+    const double *M_bla; const double *r_bla;
+    long long bla_len; int stages_bla;
+    long long max_iter;
+    double Mdiv_sq, eps_sq;
+    int calc_orbit; long long backshift;
+    int flavor;
+};
+
+struct StdDev {
+    double center_re, center_im, dx;
+    double lin_mat[4];
+    long long max_iter;
+    double Mdiv_sq, eps_sq;
+    int calc_d2, calc_orbit;
+    long long backshift;
+    int flavor;
+};
+
+/* Warp-level work stealing: lane 0 takes 32 points from the global counter. */
+/* Returns a negative value when the host raised the abort flag (the flag is read
+ * by lane 0 only so that the whole warp takes the same decision). */
+__device__ __forceinline__ long long grab32(unsigned long long *work,
+                                            const volatile int *abort_flag)
+{
+    long long base = 0;
+    if ((threadIdx.x & 31) == 0) {
+        if (*abort_flag) base = -1;
+        else base = (long long)atomicAdd(work, 32ULL);
+    }
+    return __shfl_sync(0xffffffffu, base, 0);
+}
+
+__device__ __forceinline__ void add_counters(unsigned long long *counters,
+                                             unsigned long long c0,
+                                             unsigned long long c1,
+                                             unsigned long long c2,
+                                             unsigned long long c3)
+{
+    for (int o = 16; o > 0; o >>= 1) {
+        c0 += __shfl_down_sync(0xffffffffu, c0, o);
+        c1 += __shfl_down_sync(0xffffffffu, c1, o);
+        c2 += __shfl_down_sync(0xffffffffu, c2, o);
+        c3 += __shfl_down_sync(0xffffffffu, c3, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(counters + 0, c0);
+        atomicAdd(counters + 1, c1);
+        atomicAdd(counters + 2, c2);
+        atomicAdd(counters + 3, c3);
+    }
+}
+
+__device__ __forceinline__ C ldC(const C *p, long long i)
+{
+    double2 v = __ldg(reinterpret_cast<const double2 *>(p) + i);
+    return mkC(v.x, v.y);
+}
+__device__ __forceinline__ void stC(double *Z, long long row, long long npts, long long i, C v)
+{
+    reinterpret_cast<double2 *>(Z)[row * npts + i] = make_double2(v.re, v.im);
+}
+
+/* ======================================================================== */
+/* Standard loops                                                            */
+
+__device__ __forceinline__ C c_from_pix(C pix, const double *lm, double dx, C center)
+{
+    /* core.py:3161-3194 */
+    double x1 = lm[0] * pix.re + lm[1] * pix.im;
+    double y1 = lm[2] * pix.re + lm[3] * pix.im;
+    return center + (dx * mkC(x1, y1));
+}
+
+__global__ void __launch_bounds__(256)
+k_std_m2(StdDev p, long long npts, const C *__restrict__ c_pix,
+         double *__restrict__ Z, signed char *__restrict__ stop_reason,
+         int *__restrict__ stop_iter, unsigned long long *work,
+         unsigned long long *counters, const volatile int *abort_flag)
+{
+    unsigned long long n_exec = 0, n_sum = 0;
+    for (;;) {
+        long long base = grab32(work, abort_flag);
+        if (base < 0 || base >= npts) break;
+        long long i = base + (threadIdx.x & 31);
+        if (i >= npts) continue;
+        C c = c_from_pix(ldC(c_pix, i), p.lin_mat, p.dx, mkC(p.center_re, p.center_im));
+        C zn = mkC(0., 0.), dzndz = zn, dzndc = zn, d2 = zn;
+        long long n_iter = 0, div_shift = 0, orbit_i1 = 0, orbit_i2 = 0;
+        C orbit_zn1 = zn, orbit_zn2 = zn;
+        int reason = -1;
+        for (;;) {
+            n_iter += 1;
+            int ret = 0;
+            if (n_iter >= p.max_iter) { reason = 0; ret = 1; }
+            else {
+                if (p.calc_d2) d2 = 2. * (d2 * zn + dzndc * dzndc);
+                dzndc = (2. * dzndc) * zn + 1.;
+                dzndz = (2. * dzndz) * zn;
+                zn = zn * zn + c;
+                if (n_iter == 1) dzndz = mkC(1., 0.);
+                n_exec++;
+                if (norm2(zn) > p.Mdiv_sq) { reason = 1; ret = 1; }
+                else if (norm2(dzndz) < p.eps_sq) { reason = 2; ret = 1; }
+            }
+            if (p.calc_orbit) {
+                long long div = n_iter / p.backshift;
+                if (div > div_shift) {
+                    div_shift = div;
+                    orbit_i2 = orbit_i1; orbit_zn2 = orbit_zn1;
+                    orbit_i1 = n_iter; orbit_zn1 = zn;
+                }
+            }
+            if (ret) break;
+        }
+        long long row = 0;
+        stC(Z, row++, npts, i, zn);
+        stC(Z, row++, npts, i, dzndz);
+        stC(Z, row++, npts, i, dzndc);
+        if (p.calc_d2) stC(Z, row++, npts, i, d2);
+        if (p.calc_orbit) {
+            C zo = orbit_zn2;
+            while (orbit_i2 < n_iter - p.backshift) { zo = zo * zo + c; orbit_i2 += 1; }
+            stC(Z, row++, npts, i, zo);
+        }
+        stop_reason[i] = (signed char)reason;
+        stop_iter[i] = (int)n_iter;
+        n_sum += (unsigned long long)n_iter;
+    }
+    add_counters(counters, n_exec, 0, 0, n_sum);
+}
+
+__device__ __forceinline__ void bs_iterate(int flavor, double xn, double yn, double a,
+                                           double b, double &ox, double &oy)
+{
+    /* burning_ship.py:82-122 */
+    switch (flavor) {
+    case 1: ox = xn * xn - yn * yn + a; oy = 2. * fabs(xn * yn) - b; break;
+    case 2: ox = xn * xn - yn * yn + a; oy = 2. * xn * fabs(yn) - b; break;
+    case 3: ox = xn * xn - yn * fabs(yn) + a; oy = 2. * xn * yn - b; break;
+    case 4: ox = fabs(xn * xn - yn * yn) + a; oy = 2. * xn * yn - b; break;
+    default: ox = fabs(xn * xn - yn * yn) + a; oy = 2. * fabs(xn * yn) - b; break;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_std_bs(StdDev p, long long npts, const C *__restrict__ c_pix,
+         double *__restrict__ Z, signed char *__restrict__ stop_reason,
+         int *__restrict__ stop_iter, unsigned long long *work,
+         unsigned long long *counters, const volatile int *abort_flag)
+{
+    unsigned long long n_exec = 0, n_sum = 0;
+    const int flavor = p.flavor;
+    for (;;) {
+        long long base = grab32(work, abort_flag);
+        if (base < 0 || base >= npts) break;
+        long long i = base + (threadIdx.x & 31);
+        if (i >= npts) continue;
+        C c = c_from_pix(ldC(c_pix, i), p.lin_mat, p.dx, mkC(p.center_re, p.center_im));
+        double a = c.re, b = c.im;
+        double X = 0., Y = 0., dXdA = 0., dXdB = 0., dYdA = 0., dYdB = 0.;
+        long long n_iter = 0, div_shift = 0, orbit_i1 = 0, orbit_i2 = 0;
+        double oxn1 = 0., oxn2 = 0., oyn1 = 0., oyn2 = 0.;
+        int reason = -1;
+        for (;;) {
+            n_iter += 1;
+            int ret = 0;
+            if (n_iter >= p.max_iter) { reason = 0; ret = 1; }
+            else {
+                double nx, ny, ndxa, ndxb, ndya, ndyb;
+                switch (flavor) {
+                case 1:
+                    nx = X * X - Y * Y + a;
+                    ny = 2. * fabs(X * Y) - b;
+                    ndxa = 2. * (X * dXdA - Y * dYdA) + 1.;
+                    ndxb = 2. * (X * dXdB - Y * dYdB);
+                    ndya = 2. * (fabs(X) * sgn(Y) * dYdA + sgn(X) * dXdA * fabs(Y));
+                    ndyb = 2. * (fabs(X) * sgn(Y) * dYdB + sgn(X) * dXdB * fabs(Y)) - 1.;
+                    break;
+                case 2:
+                    nx = X * X - Y * Y + a;
+                    ny = 2. * X * fabs(Y) - b;
+                    ndxa = 2. * (X * dXdA - Y * dYdA) + 1.;
+                    ndxb = 2. * (X * dXdB - Y * dYdB);
+                    ndya = 2. * (X * sgn(Y) * dYdA + dXdA * fabs(Y));
+                    ndyb = 2. * (X * sgn(Y) * dYdB + dXdB * fabs(Y)) - 1.;
+                    break;
+                case 3:
+                    nx = X * X - Y * fabs(Y) + a;
+                    ny = 2. * X * Y - b;
+                    ndxa = 2. * (X * dXdA - fabs(Y) * dYdA) + 1.;
+                    ndxb = 2. * (X * dXdB - fabs(Y) * dYdB);
+                    ndya = 2. * (dXdA * Y + X * dYdA);
+                    ndyb = 2. * (dXdB * Y + X * dYdB) - 1.;
+                    break;
+                case 4: {
+                    double x2my2 = X * X - Y * Y;
+                    nx = fabs(x2my2) + a;
+                    ny = 2. * X * Y - b;
+                    ndxa = 2. * sgn(x2my2) * (X * dXdA - Y * dYdA);
+                    ndxb = 2. * sgn(x2my2) * (X * dXdB - Y * dYdB);
+                    ndya = 2. * (dXdA * Y + X * dYdA);
+                    ndyb = 2. * (dXdB * Y + X * dYdB) - 1.;
+                    break;
+                }
+                default: {
+                    double x2my2 = X * X - Y * Y;
+                    nx = fabs(x2my2) + a;
+                    ny = 2. * fabs(X * Y) - b;
+                    ndxa = 2. * sgn(x2my2) * (X * dXdA - Y * dYdA);
+                    ndxb = 2. * sgn(x2my2) * (X * dXdB - Y * dYdB);
+                    ndya = 2. * (fabs(X) * sgn(Y) * dYdA + sgn(X) * dXdA * fabs(Y));
+                    ndyb = 2. * (fabs(X) * sgn(Y) * dYdB + sgn(X) * dXdB * fabs(Y)) - 1.;
+                    break;
+                }
+                }
+                X = nx; Y = ny; dXdA = ndxa; dXdB = ndxb; dYdA = ndya; dYdB = ndyb;
+                n_exec++;
+                if (X * X + Y * Y > p.Mdiv_sq) { reason = 1; ret = 1; }
+            }
+            if (p.calc_orbit) {
+                long long div = n_iter / p.backshift;
+                if (div > div_shift) {
+                    div_shift = div;
+                    orbit_i2 = orbit_i1; oxn2 = oxn1; oyn2 = oyn1;
+                    orbit_i1 = n_iter; oxn1 = X; oyn1 = Y;
+                }
+            }
+            if (ret) break;
+        }
+        Z[0 * npts + i] = X; Z[1 * npts + i] = Y;
+        Z[2 * npts + i] = dXdA; Z[3 * npts + i] = dXdB;
+        Z[4 * npts + i] = dYdA; Z[5 * npts + i] = dYdB;
+        if (p.calc_orbit) {
+            double xo = oxn2, yo = oyn2;
+            while (orbit_i2 < n_iter - p.backshift) {
+                double tx, ty;
+                bs_iterate(flavor, xo, yo, a, b, tx, ty);
+                xo = tx; yo = ty; orbit_i2 += 1;
+            }
+            Z[6 * npts + i] = xo; Z[7 * npts + i] = yo;
+        }
+        stop_reason[i] = (signed char)reason;
+        stop_iter[i] = (int)n_iter;
+        n_sum += (unsigned long long)n_iter;
+    }
+    add_counters(counters, n_exec, 0, 0, n_sum);
+}
+
+/* ======================================================================== */
+/* Reference-path access                                                     */
+
+/* Position of idx in the sorted ref_index_xr or -1: stateless equivalent of
+ * the cursor of perturbation.py:2519-2588. */
+__device__ __forceinline__ long long xr_find(const int *index, long long n, long long idx)
+{
+    long long lo = 0, hi = n;
+    while (lo < hi) {
+        long long mid = (lo + hi) >> 1;
+        if (__ldg(index + mid) < idx) lo = mid + 1; else hi = mid;
+    }
+    if (lo < n && __ldg(index + lo) == idx) return lo;
+    return -1;
+}
+
+__device__ __forceinline__ long long bla_index(long long i, int stg)
+{
+    return 2 * i + ((1LL << stg) - 1);
+}
+
+/* perturbation.py:2116-2170.  Returns the step (0 = no BLA applicable) and
+ * the node index. */
+__device__ __forceinline__ long long ref_bla_get(const double *__restrict__ r_bla,
+                                                 int stages_bla, C zn,
+                                                 long long n_iter,
+                                                 long long first_invalid,
+                                                 long long &index_out)
+{
+    if (stages_bla <= 3) return 0;
+    long long it = n_iter >> 3;
+    int stages = stages_bla - 1;
+    if (it != 0) {
+        int s = 3 + (__ffsll(it) - 1);
+        if (s < stages) stages = s;
+    }
+    long long invalid_step = first_invalid - n_iter;
+    double az = cabs_rn(zn);
+    for (int stg = stages; stg > 2; stg--) {
+        long long step = 1LL << stg;
+        if (step >= invalid_step) continue;
+        long long ib = bla_index(n_iter >> 3, stg - 3);
+        double r = __ldg(r_bla + ib);
+        if (az < r) { index_out = ib; return step; }
+    }
+    return 0;
+}
+
+/* ======================================================================== */
+/* Holomorphic perturbation (Mandelbrot power 2)                             */
+
+template <class T, class R>
+__device__ __forceinline__ T p_iter_zn(T z, R ref_zn, T c)
+{
+    return z * (z + 2. * ref_zn) + c; /* mandelbrot_M2.py:607-610 */
+}
+template <class T, class R, class D>
+__device__ __forceinline__ T p_iter_deriv(T z, T dz, R ref_zn, D ref_d)
+{
+    return 2. * ((ref_zn + z) * dz + ref_d * z); /* mandelbrot_M2.py:611-622 */
+}
+
+template <bool XR, bool DZNDC, bool DZNDZ, bool BLA>
+__global__ void __launch_bounds__(128)
+k_perturb_m2(FrameDev f, long long npts, const C *__restrict__ c_pix,
+             double *__restrict__ Z, int *__restrict__ U,
+             signed char *__restrict__ stop_reason, int *__restrict__ stop_iter,
+             unsigned long long *work, unsigned long long *counters,
+             const volatile int *abort_flag)
+{
+    unsigned long long n_exec = 0, n_bla = 0, n_reb = 0, n_sum = 0;
+    const long long L = f.L;
+    const bool has_xr = f.n_xr > 0;
+    const long long ref_order = f.ref_order, ref_div_iter = f.ref_div_iter;
+    const long long max_iter = f.max_iter;
+    long long first_invalid = L;
+    if (ref_div_iter < first_invalid) first_invalid = ref_div_iter;
+    if (ref_order < first_invalid) first_invalid = ref_order;
+    const long long w_wraped = L;
+    const XC record_zero = mkXC(mkC(0., 0.), 0);
+
+#define DZNDC_X(i) mkXC(ldC(f.dZndc, (i)), __ldg(f.dZndc_e + (i)))
+#define DZNDZ_X(i) mkXC(ldC(f.dZndz, (i)), __ldg(f.dZndz_e + (i)))
+#define REF_X(k) mkXC(ldC(f.ref_xr, (k)), __ldg(f.ref_xr_e + (k)))
+
+    for (;;) {
+        long long base = grab32(work, abort_flag);
+        if (base < 0 || base >= npts) break;
+        long long ipt = base + (threadIdx.x & 31);
+        if (ipt >= npts) continue;
+
+        /* perturbation.py:1026-1031, 2214-2230 */
+        C pix = ldC(c_pix, ipt);
+        XC c_xr;
+        {
+            double x1 = f.lin_mat[0] * pix.re + f.lin_mat[1] * pix.im;
+            double y1 = f.lin_mat[2] * pix.re + f.lin_mat[3] * pix.im;
+            c_xr = (mkXF(f.lin_scale, f.lin_scale_e) * mkC(x1, y1))
+                   + mkXC(mkC(f.drift[0], f.drift[1]), f.drift_e[0]);
+        }
+        const C c = to_std(c_xr);
+
+        C zn = mkC(0., 0.), dzndc = zn, dzndz = zn;
+        XC zn_x = to_xr(zn), dzndc_x = zn_x, dzndz_x = zn_x;
+
+        long long w_iter = 0, n_iter = 0;
+        long long div_shift = 0, orbit_i1 = 0, orbit_i2 = 0;
+        C orbit_zn1 = zn, orbit_zn2 = zn;
+        bool nullify_dZndz = false;
+        bool bool_dyn_rebase = true;
+        int stop = -1;
+
+        for (;;) {
+            /* ---- BLA step, perturbation.py:1121-1154 ---- */
+            if (BLA && (w_iter & 7) == 0) {
+                long long ib = 0;
+                long long step = ref_bla_get(f.r_bla, f.stages_bla, zn, w_iter,
+                                             first_invalid, ib);
+                if (step != 0) {
+                    const C *M = reinterpret_cast<const C *>(f.M_bla);
+                    C A = ldC(M, 2 * ib), B = ldC(M, 2 * ib + 1);
+                    n_iter += step;
+                    w_iter = (w_iter + step) % ref_order;
+                    if (XR) {
+                        zn_x = A * zn_x + B * c_xr;
+                        zn = to_std(zn_x);
+                        if (DZNDC) dzndc_x = A * dzndc_x;
+                        if (DZNDZ) dzndz_x = A * dzndz_x;
+                    } else {
+                        zn = A * zn + B * c;
+                        if (DZNDC) dzndc = A * dzndc;
+                        if (DZNDZ) dzndz = A * dzndz;
+                    }
+                    n_bla++;
+                    continue;
+                }
+            }
+
+            /* ---- full perturbation iteration, :1158-1209 ---- */
+            n_iter += 1;
+            n_exec++;
+            C ref_zn = ldC(f.Zn, w_iter);
+            XC ref_zn_x = record_zero;
+            if (XR) {
+                long long k = -1;
+                if (has_xr && w_iter != 0 && fabs(ref_zn.re) < 1.e-300 && fabs(ref_zn.im) < 1.e-300)
+                    k = xr_find(f.ref_index_xr, f.n_xr, w_iter);
+                ref_zn_x = (k >= 0) ? REF_X(k) : to_xr(ref_zn);
+            }
+            if (DZNDC) {
+                if (XR) {
+                    XC ref_d = bool_dyn_rebase ? record_zero : DZNDC_X(w_iter);
+                    dzndc_x = p_iter_deriv(zn_x, dzndc_x, ref_zn_x, ref_d);
+                } else {
+                    C ref_d = bool_dyn_rebase ? mkC(0., 0.) : ldC(f.dZndc, w_iter);
+                    dzndc = p_iter_deriv(zn, dzndc, ref_zn, ref_d);
+                }
+            }
+            if (DZNDZ) {
+                long long i = nullify_dZndz ? 0 : w_iter;
+                if (XR) dzndz_x = p_iter_deriv(zn_x, dzndz_x, ref_zn_x, DZNDZ_X(i));
+                else dzndz = p_iter_deriv(zn, dzndz, ref_zn, ldC(f.dZndz, i));
+            }
+            if (XR) {
+                zn_x = p_iter_zn(zn_x, ref_zn_x, c_xr);
+                zn = to_std(zn_x);
+            } else {
+                zn = p_iter_zn(zn, ref_zn, c);
+            }
+
+            w_iter += 1;
+            if (w_iter >= ref_order) w_iter = w_iter % ref_order;
+
+            if (n_iter >= max_iter) { stop = 0; break; } /* :1218 */
+
+            if (DZNDZ) { /* :1224-1246 */
+                long long i = 0;
+                if (!nullify_dZndz) {
+                    i = w_iter;
+                    if (n_iter == ref_order) i = w_wraped;
+                }
+                bool stationnary;
+                if (XR) stationnary = xr_lt(abs2(dzndz_x + DZNDZ_X(i)), f.eps_sq);
+                else stationnary = norm2(dzndz + ldC(f.dZndz, i)) < f.eps_sq;
+                if (stationnary) { stop = 2; break; }
+            }
+
+            /* ---- divergence, :1252-1279 ---- */
+            C ref_zn_next = ldC(f.Zn, w_iter);
+            long long knext = -1;
+            if (XR && has_xr && w_iter != 0 && fabs(ref_zn_next.re) < 1.e-300
+                && fabs(ref_zn_next.im) < 1.e-300)
+                knext = xr_find(f.ref_index_xr, f.n_xr, w_iter);
+            C ZZ = zn + ref_zn_next;
+            double full_sq_norm = norm2(ZZ);
+            if (f.calc_orbit) {
+                long long div = n_iter / f.backshift;
+                if (div > div_shift) {
+                    div_shift = div;
+                    orbit_i2 = orbit_i1; orbit_zn2 = orbit_zn1;
+                    orbit_i1 = n_iter; orbit_zn1 = ZZ;
+                }
+            }
+            if (full_sq_norm > f.Mdiv_sq) { stop = 1; break; }
+
+            /* ---- rebase: reference diverging, :1283-1313 ---- */
+            if (w_iter >= ref_div_iter - 1) {
+                zn = ZZ;
+                if (XR) {
+                    zn_x = to_xr(ZZ);
+                    if (DZNDC) dzndc_x = dzndc_x + DZNDC_X(w_iter);
+                    if (DZNDZ) {
+                        if (!nullify_dZndz) {
+                            long long i = (n_iter == ref_order) ? w_wraped : w_iter;
+                            dzndz_x = dzndz_x + DZNDZ_X(i);
+                        }
+                        nullify_dZndz = true;
+                    }
+                } else {
+                    if (DZNDC) dzndc = dzndc + ldC(f.dZndc, w_iter);
+                    if (DZNDZ) {
+                        if (!nullify_dZndz) {
+                            long long i = (n_iter == ref_order) ? w_wraped : w_iter;
+                            dzndz = dzndz + ldC(f.dZndz, i);
+                        }
+                        nullify_dZndz = true;
+                    }
+                }
+                w_iter = 0;
+                n_reb++;
+                continue;
+            }
+
+            /* ---- rebase: dynamic glitch, :1317-1372 ---- */
+            bool_dyn_rebase = (fabs(ZZ.re) <= fabs(zn.re)) && (fabs(ZZ.im) <= fabs(zn.im));
+            if (bool_dyn_rebase) {
+                if (XR) {
+                    XC ZZ_xr = (knext >= 0) ? (zn_x + REF_X(knext)) : (zn_x + ref_zn_next);
+                    if (xr_le(abs2(ZZ_xr), abs2(zn_x))) {
+                        zn_x = ZZ_xr;
+                        zn = to_std(ZZ_xr);
+                        if (DZNDC) dzndc_x = dzndc_x + DZNDC_X(w_iter);
+                        if (DZNDZ) {
+                            if (!nullify_dZndz) {
+                                long long i = (n_iter == ref_order) ? w_wraped : w_iter;
+                                dzndz_x = dzndz_x + DZNDZ_X(i);
+                            }
+                            nullify_dZndz = true;
+                        }
+                        w_iter = 0;
+                        n_reb++;
+                        continue;
+                    }
+                } else {
+                    zn = ZZ;
+                    if (DZNDC) dzndc = dzndc + ldC(f.dZndc, w_iter);
+                    if (DZNDZ) {
+                        if (!nullify_dZndz) {
+                            long long i = (n_iter == ref_order) ? w_wraped : w_iter;
+                            dzndz = dzndz + ldC(f.dZndz, i);
+                        }
+                        nullify_dZndz = true;
+                    }
+                    w_iter = 0;
+                    n_reb++;
+                    continue;
+                }
+            }
+        }
+
+        /* ---- epilogue, :1374-1398 ---- */
+        U[ipt] = (int)w_iter;
+        if (XR) {
+            zn = to_std(zn_x) + ldC(f.Zn, w_iter);
+            if (DZNDC) dzndc = to_std(dzndc_x + DZNDC_X(w_iter));
+        } else {
+            zn = zn + ldC(f.Zn, w_iter);
+            if (DZNDC) dzndc = dzndc + ldC(f.dZndc, w_iter);
+        }
+        long long row = 0;
+        stC(Z, row++, npts, ipt, zn);
+        if (DZNDZ) stC(Z, row++, npts, ipt, dzndz);
+        if (DZNDC) stC(Z, row++, npts, ipt, dzndc);
+        if (f.calc_orbit) {
+            C zo = orbit_zn2;
+            C CC = c + ldC(f.Zn, 1);
+            while (orbit_i2 < n_iter - f.backshift) { zo = zo * zo + CC; orbit_i2 += 1; }
+            stC(Z, row++, npts, ipt, zo);
+        }
+        stop_reason[ipt] = (signed char)stop;
+        stop_iter[ipt] = (int)n_iter;
+        n_sum += (unsigned long long)n_iter;
+    }
+#undef DZNDC_X
+#undef DZNDZ_X
+#undef REF_X
+    add_counters(counters, n_exec, n_bla, n_reb, n_sum);
+}
+
+/* ======================================================================== */
+/* Burning-ship family perturbation                                          */
+
+/* burning_ship.py:19-60 */
+template <class T> __device__ __forceinline__ T diffabs(T X, T x)
+{
+    if (X >= 0.) {
+        if ((X + x) >= 0.) return 1. * x;
+        return -(2. * X + x);
+    }
+    if ((X + x) <= 0.) return -x;
+    return (2. * X + x);
+}
+template <class T> __device__ __forceinline__ double ddiffabsdX(T X, T x)
+{
+    if (X >= 0.) { if ((X + x) >= 0.) return 0.; return -2.; }
+    if ((X + x) <= 0.) return 0.;
+    return 2.;
+}
+template <class T> __device__ __forceinline__ double ddiffabsdx(T X, T x)
+{
+    if (X >= 0.) { if ((X + x) >= 0.) return 1.; return -1.; }
+    if ((X + x) <= 0.) return -1.;
+    return 1.;
+}
+
+/* burning_ship.py:535-619 */
+template <class T>
+__device__ __forceinline__ void bs_p_iter_zn(int flavor, T &x, T &y, T rx, T ry, T a, T b)
+{
+    T nx, ny;
+    switch (flavor) {
+    case 1: {
+        T rxy = rx * ry;
+        nx = x * (x + 2. * rx) - y * (y + 2. * ry) + a;
+        ny = 2. * diffabs(rxy, x * y + x * ry + y * rx) - b;
+        break;
+    }
+    case 2:
+        nx = x * (x + 2. * rx) - y * (y + 2. * ry) + a;
+        ny = 2. * (rx * diffabs(ry, y) + x * fabs_(ry + y)) - b;
+        break;
+    case 3:
+        nx = x * (x + 2. * rx) - ry * diffabs(ry, y) - y * fabs_(ry + y) + a;
+        ny = 2. * (rx * y + ry * x + x * y) - b;
+        break;
+    case 4: {
+        T r2 = rx * rx - ry * ry;
+        nx = diffabs(r2, x * (x + 2. * rx) - y * (y + 2. * ry)) + a;
+        ny = 2. * (rx * y + ry * x + x * y) - b;
+        break;
+    }
+    default: {
+        T rxy = rx * ry;
+        T r2 = rx * rx - ry * ry;
+        nx = diffabs(r2, x * (x + 2. * rx) - y * (y + 2. * ry)) + a;
+        ny = 2. * diffabs(rxy, x * y + x * ry + y * rx) - b;
+        break;
+    }
+    }
+    x = nx; y = ny;
+}
+
+/* burning_ship.py:622-859 */
+template <class T>
+__device__ __forceinline__ void bs_p_iter_hessian(int flavor, T x, T y, T &dxa, T &dxb,
+                                                  T &dya, T &dyb, T rx, T ry, T rdxa,
+                                                  T rdxb, T rdya, T rdyb)
+{
+    T ndxa, ndxb, ndya, ndyb;
+    switch (flavor) {
+    case 1: {
+        T opX = rx * ry;
+        T dXa = rdxa * ry + rx * rdya;
+        T dXb = rdxb * ry + rx * rdyb;
+        T opx = x * y + x * ry + y * rx;
+        T dxa_ = dxa * y + x * dya + dxa * ry + x * rdya + dya * rx + y * rdxa;
+        T dxb_ = dxb * y + x * dyb + dxb * ry + x * rdyb + dyb * rx + y * rdxb;
+        double dX = ddiffabsdX(opX, opx), dx = ddiffabsdx(opX, opx);
+        ndxa = 2. * ((rx + x) * dxa + rdxa * x) - 2. * ((ry + y) * dya + rdya * y);
+        ndxb = 2. * ((rx + x) * dxb + rdxb * x) - 2. * ((ry + y) * dyb + rdyb * y);
+        ndya = 2. * (dX * dXa + dx * dxa_);
+        ndyb = 2. * (dX * dXb + dx * dxb_);
+        break;
+    }
+    case 2: {
+        T da = diffabs(ry, y);
+        double dX = ddiffabsdX(ry, y), dx = ddiffabsdx(ry, y);
+        T Yy = ry + y;
+        T ab = fabs_(Yy);
+        double sg = sgn_(Yy);
+        ndxa = 2. * (((rx + x) * dxa + rdxa * x) - ((ry + y) * dya + rdya * y));
+        ndxb = 2. * (((rx + x) * dxb + rdxb * x) - ((ry + y) * dyb + rdyb * y));
+        ndya = 2. * (rdxa * da + rx * (dX * rdya + dx * dya) + dxa * ab + x * sg * (rdya + dya));
+        ndyb = 2. * (rdxb * da + rx * (dX * rdyb + dx * dyb) + dxb * ab + x * sg * (rdyb + dyb));
+        break;
+    }
+    case 3: {
+        T da = diffabs(ry, y);
+        double dX = ddiffabsdX(ry, y), dx = ddiffabsdx(ry, y);
+        T Yy = ry + y;
+        T ab = fabs_(Yy);
+        double sg = sgn_(Yy);
+        ndxa = dxa * (x + 2. * rx) + x * (dxa + 2. * rdxa) - rdya * da
+               - ry * (rdya * dX + dya * dx) - dya * ab - y * sg * (rdya + dya);
+        ndxb = dxb * (x + 2. * rx) + x * (dxb + 2. * rdxb) - rdyb * da
+               - ry * (rdyb * dX + dyb * dx) - dyb * ab - y * sg * (rdyb + dyb);
+        ndya = 2. * (rdxa * y + rx * dya + rdya * x + ry * dxa + dxa * y + x * dya);
+        ndyb = 2. * (rdxb * y + rx * dyb + rdyb * x + ry * dxb + dxb * y + x * dyb);
+        break;
+    }
+    case 4: {
+        T opX = rx * rx - ry * ry;
+        T dXa = 2. * (rx * rdxa - ry * rdya);
+        T dXb = 2. * (rx * rdxb - ry * rdyb);
+        T opx = x * (x + 2. * rx) - y * (y + 2. * ry);
+        T dxa_ = dxa * (x + 2. * rx) + x * (dxa + 2. * rdxa) - dya * (y + 2. * ry) - y * (dya + 2. * rdya);
+        T dxb_ = dxb * (x + 2. * rx) + x * (dxb + 2. * rdxb) - dyb * (y + 2. * ry) - y * (dyb + 2. * rdyb);
+        double dX = ddiffabsdX(opX, opx), dx = ddiffabsdx(opX, opx);
+        ndxa = dX * dXa + dx * dxa_;
+        ndxb = dX * dXb + dx * dxb_;
+        ndya = 2. * (rdxa * y + rx * dya + rdya * x + ry * dxa + dxa * y + x * dya);
+        ndyb = 2. * (rdxb * y + rx * dyb + rdyb * x + ry * dxb + dxb * y + x * dyb);
+        break;
+    }
+    default: {
+        T opX = rx * rx - ry * ry;
+        T dXa = 2. * (rx * rdxa - ry * rdya);
+        T dXb = 2. * (rx * rdxb - ry * rdyb);
+        T opx = x * (x + 2. * rx) - y * (y + 2. * ry);
+        T dxa_ = dxa * (x + 2. * rx) + x * (dxa + 2. * rdxa) - dya * (y + 2. * ry) - y * (dya + 2. * rdya);
+        T dxb_ = dxb * (x + 2. * rx) + x * (dxb + 2. * rdxb) - dyb * (y + 2. * ry) - y * (dyb + 2. * rdyb);
+        double dX = ddiffabsdX(opX, opx), dx = ddiffabsdx(opX, opx);
+        ndxa = dX * dXa + dx * dxa_;
+        ndxb = dX * dXb + dx * dxb_;
+        T opX2 = rx * ry;
+        T dXa2 = rdxa * ry + rx * rdya;
+        T dXb2 = rdxb * ry + rx * rdyb;
+        T opx2 = x * y + x * ry + y * rx;
+        T dxa2 = dxa * y + x * dya + dxa * ry + x * rdya + dya * rx + y * rdxa;
+        T dxb2 = dxb * y + x * dyb + dxb * ry + x * rdyb + dyb * rx + y * rdxb;
+        double dX2 = ddiffabsdX(opX2, opx2), dx2 = ddiffabsdx(opX2, opx2);
+        ndya = 2. * (dX2 * dXa2 + dx2 * dxa2);
+        ndyb = 2. * (dX2 * dXb2 + dx2 * dxb2);
+        break;
+    }
+    }
+    dxa = ndxa; dxb = ndxb; dya = ndya; dyb = ndyb;
+}
+
+/* perturbation.py:1793-1811 */
+template <class T>
+__device__ __forceinline__ void apply_bla_bs(const double *M, T &x, T &y, T a, T b)
+{
+    T nx = M[0] * x + M[1] * y + M[4] * a + M[5] * b;
+    T ny = M[2] * x + M[3] * y + M[6] * a + M[7] * b;
+    x = nx; y = ny;
+}
+template <class T>
+__device__ __forceinline__ void apply_bla_deriv_bs(const double *M, T &dxa, T &dxb, T &dya, T &dyb)
+{
+    T a = M[0] * dxa + M[1] * dya;
+    T b = M[0] * dxb + M[1] * dyb;
+    T c = M[2] * dxa + M[3] * dya;
+    T d = M[2] * dxb + M[3] * dyb;
+    dxa = a; dxb = b; dya = c; dyb = d;
+}
+
+template <bool XR, bool HESS, bool BLA>
+__global__ void __launch_bounds__(128)
+k_perturb_bs(FrameDev f, long long npts, const C *__restrict__ c_pix,
+             double *__restrict__ Z, int *__restrict__ U,
+             signed char *__restrict__ stop_reason, int *__restrict__ stop_iter,
+             unsigned long long *work, unsigned long long *counters,
+             const volatile int *abort_flag)
+{
+    unsigned long long n_exec = 0, n_bla = 0, n_reb = 0, n_sum = 0;
+    const long long L = f.L;
+    const bool has_xr = f.n_xr > 0;
+    const int flavor = f.flavor;
+    const long long ref_order = f.ref_order, ref_div_iter = f.ref_div_iter;
+    long long first_invalid = L;
+    if (ref_div_iter < first_invalid) first_invalid = ref_div_iter;
+    if (ref_order < first_invalid) first_invalid = ref_order;
+    const XF record_zero = mkXF(0., 0);
+
+#define D_X(j, i) mkXF(__ldg(f.dP[j] + (i)), __ldg(f.dP_e[j] + (i)))
+#define D_S(j, i) __ldg(f.dP[j] + (i))
+
+    for (;;) {
+        long long base = grab32(work, abort_flag);
+        if (base < 0 || base >= npts) break;
+        long long ipt = base + (threadIdx.x & 31);
+        if (ipt >= npts) continue;
+
+        /* perturbation.py:2260-2280 */
+        C pix = ldC(c_pix, ipt);
+        XC c_xr;
+        {
+            double x1 = f.lin_mat[0] * pix.re + f.lin_mat[1] * pix.im;
+            double y1 = f.lin_mat[2] * pix.re + f.lin_mat[3] * pix.im;
+            c_xr = mkXF(f.lin_scale, f.lin_scale_e) * mkC(x1, y1);
+        }
+        const XF a_x = mkXF(c_xr.m.re, c_xr.e) + mkXF(f.drift[0], f.drift_e[0]);
+        const XF b_x = mkXF(c_xr.m.im, c_xr.e) + mkXF(f.drift[1], f.drift_e[1]);
+        const double a = to_std(a_x), b = to_std(b_x);
+
+        double x = 0., y = 0., dxa = 0., dxb = 0., dya = 0., dyb = 0.;
+        XF x_x = to_xr(0.), y_x = x_x, dxa_x = x_x, dxb_x = x_x, dya_x = x_x, dyb_x = x_x;
+
+        long long w_iter = 0, n_iter = 0;
+        long long div_shift = 0, orbit_i1 = 0, orbit_i2 = 0;
+        double oxn1 = 0., oxn2 = 0., oyn1 = 0., oyn2 = 0.;
+        bool bool_dyn_rebase = true;
+        int stop = -1;
+
+        for (;;) {
+            if (BLA && (w_iter & 7) == 0) {
+                long long ib = 0;
+                long long step = ref_bla_get(f.r_bla, f.stages_bla, mkC(x, y), w_iter,
+                                             first_invalid, ib);
+                if (step != 0) {
+                    double M[8];
+                    const double2 *Mp = reinterpret_cast<const double2 *>(f.M_bla + 8 * ib);
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        double2 v = __ldg(Mp + q);
+                        M[2 * q] = v.x; M[2 * q + 1] = v.y;
+                    }
+                    n_iter += step;
+                    w_iter = (w_iter + step) % ref_order;
+                    if (XR) {
+                        apply_bla_bs(M, x_x, y_x, a_x, b_x);
+                        x = to_std(x_x);
+                        y = to_std(y_x);
+                        if (HESS) apply_bla_deriv_bs(M, dxa_x, dxb_x, dya_x, dyb_x);
+                    } else {
+                        apply_bla_bs(M, x, y, a, b);
+                        if (HESS) apply_bla_deriv_bs(M, dxa, dxb, dya, dyb);
+                    }
+                    n_bla++;
+                    continue;
+                }
+            }
+
+            n_iter += 1;
+            n_exec++;
+            C ref_zn = ldC(f.Zn, w_iter);
+            XF rx_x = record_zero, ry_x = record_zero;
+            if (XR) {
+                long long k = -1;
+                if (has_xr && w_iter != 0 && (fabs(ref_zn.re) < 1.e-300 || fabs(ref_zn.im) < 1.e-300))
+                    k = xr_find(f.ref_index_xr, f.n_xr, w_iter);
+                if (k >= 0) {
+                    rx_x = mkXF(__ldg(f.refx_xr + k), __ldg(f.refx_xr_e + k));
+                    ry_x = mkXF(__ldg(f.refy_xr + k), __ldg(f.refy_xr_e + k));
+                } else {
+                    rx_x = to_xr(ref_zn.re);
+                    ry_x = to_xr(ref_zn.im);
+                }
+            }
+            if (HESS) {
+                if (XR) {
+                    XF ra = record_zero, rb = record_zero, rc = record_zero, rd = record_zero;
+                    if (!bool_dyn_rebase) {
+                        ra = D_X(0, w_iter); rb = D_X(1, w_iter);
+                        rc = D_X(2, w_iter); rd = D_X(3, w_iter);
+                    }
+                    bs_p_iter_hessian(flavor, x_x, y_x, dxa_x, dxb_x, dya_x, dyb_x,
+                                      rx_x, ry_x, ra, rb, rc, rd);
+                } else {
+                    double ra = 0., rb = 0., rc = 0., rd = 0.;
+                    if (!bool_dyn_rebase) {
+                        ra = D_S(0, w_iter); rb = D_S(1, w_iter);
+                        rc = D_S(2, w_iter); rd = D_S(3, w_iter);
+                    }
+                    bs_p_iter_hessian(flavor, x, y, dxa, dxb, dya, dyb, ref_zn.re,
+                                      ref_zn.im, ra, rb, rc, rd);
+                }
+            }
+            if (XR) {
+                bs_p_iter_zn(flavor, x_x, y_x, rx_x, ry_x, a_x, b_x);
+                x = to_std(x_x);
+                y = to_std(y_x);
+            } else {
+                bs_p_iter_zn(flavor, x, y, ref_zn.re, ref_zn.im, a, b);
+            }
+
+            /* max_iter test BEFORE w_iter += 1 (perturbation.py:1616-1625) */
+            if (n_iter >= f.max_iter) { stop = 0; break; }
+
+            w_iter += 1;
+            if (w_iter >= ref_order) w_iter = w_iter % ref_order;
+
+            C ref_next = ldC(f.Zn, w_iter);
+            long long knext = -1;
+            if (XR && has_xr && w_iter != 0
+                && (fabs(ref_next.re) < 1.e-300 || fabs(ref_next.im) < 1.e-300))
+                knext = xr_find(f.ref_index_xr, f.n_xr, w_iter);
+            double XX = x + ref_next.re, YY = y + ref_next.im;
+            double full_sq_norm = XX * XX + YY * YY;
+            if (f.calc_orbit) {
+                long long div = n_iter / f.backshift;
+                if (div > div_shift) {
+                    div_shift = div;
+                    orbit_i2 = orbit_i1; oxn2 = oxn1; oyn2 = oyn1;
+                    orbit_i1 = n_iter; oxn1 = XX; oyn1 = YY;
+                }
+            }
+            if (full_sq_norm > f.Mdiv_sq) { stop = 1; break; }
+
+            if (w_iter >= ref_div_iter - 1) {
+                x = XX; y = YY;
+                if (XR) {
+                    x_x = to_xr(XX); y_x = to_xr(YY);
+                    if (HESS) {
+                        dxa_x = dxa_x + D_X(0, w_iter); dxb_x = dxb_x + D_X(1, w_iter);
+                        dya_x = dya_x + D_X(2, w_iter); dyb_x = dyb_x + D_X(3, w_iter);
+                    }
+                } else if (HESS) {
+                    dxa += D_S(0, w_iter); dxb += D_S(1, w_iter);
+                    dya += D_S(2, w_iter); dyb += D_S(3, w_iter);
+                }
+                w_iter = 0;
+                n_reb++;
+                continue;
+            }
+
+            bool_dyn_rebase = (fabs(XX) <= fabs(x)) && (fabs(YY) <= fabs(y));
+            if (bool_dyn_rebase) {
+                if (XR) {
+                    XF XXx, YYx;
+                    if (knext >= 0) {
+                        XXx = x_x + mkXF(__ldg(f.refx_xr + knext), __ldg(f.refx_xr_e + knext));
+                        YYx = y_x + mkXF(__ldg(f.refy_xr + knext), __ldg(f.refy_xr_e + knext));
+                    } else {
+                        XXx = x_x + ref_next.re;
+                        YYx = y_x + ref_next.im;
+                    }
+                    if (xr_le(XXx * XXx + YYx * YYx, x_x * x_x + y_x * y_x)) {
+                        x_x = XXx; y_x = YYx;
+                        x = to_std(XXx); y = to_std(YYx);
+                        if (HESS) {
+                            dxa_x = dxa_x + D_X(0, w_iter); dxb_x = dxb_x + D_X(1, w_iter);
+                            dya_x = dya_x + D_X(2, w_iter); dyb_x = dyb_x + D_X(3, w_iter);
+                        }
+                        w_iter = 0;
+                        n_reb++;
+                        continue;
+                    }
+                } else {
+                    x = XX; y = YY;
+                    if (HESS) {
+                        dxa += D_S(0, w_iter); dxb += D_S(1, w_iter);
+                        dya += D_S(2, w_iter); dyb += D_S(3, w_iter);
+                    }
+                    w_iter = 0;
+                    n_reb++;
+                    continue;
+                }
+            }
+        }
+
+        U[ipt] = (int)w_iter;
+        C ref_zn = ldC(f.Zn, w_iter);
+        if (XR) {
+            x = to_std(x_x + ref_zn.re);
+            y = to_std(y_x + ref_zn.im);
+            if (HESS) {
+                dxa = to_std(dxa_x + D_X(0, w_iter)); dxb = to_std(dxb_x + D_X(1, w_iter));
+                dya = to_std(dya_x + D_X(2, w_iter)); dyb = to_std(dyb_x + D_X(3, w_iter));
+            }
+        } else {
+            x += ref_zn.re; y += ref_zn.im;
+            if (HESS) {
+                dxa += D_S(0, w_iter); dxb += D_S(1, w_iter);
+                dya += D_S(2, w_iter); dyb += D_S(3, w_iter);
+            }
+        }
+        long long row = 0;
+        Z[(row++) * npts + ipt] = x;
+        Z[(row++) * npts + ipt] = y;
+        if (HESS) {
+            Z[(row++) * npts + ipt] = dxa; Z[(row++) * npts + ipt] = dxb;
+            Z[(row++) * npts + ipt] = dya; Z[(row++) * npts + ipt] = dyb;
+        }
+        if (f.calc_orbit) {
+            double xo = oxn2, yo = oyn2;
+            C z1 = ldC(f.Zn, 1);
+            double AA = a + z1.re, BB = b + z1.im;
+            while (orbit_i2 < n_iter - f.backshift) {
+                double tx, ty;
+                bs_iterate(flavor, xo, yo, AA, BB, tx, ty);
+                xo = tx; yo = ty; orbit_i2 += 1;
+            }
+            Z[(row++) * npts + ipt] = xo; Z[(row++) * npts + ipt] = yo;
+        }
+        stop_reason[ipt] = (signed char)stop;
+        stop_iter[ipt] = (int)n_iter;
+        n_sum += (unsigned long long)n_iter;
+    }
+#undef D_X
+#undef D_S
+    add_counters(counters, n_exec, n_bla, n_reb, n_sum);
+}
+
+/* ======================================================================== */
+/* BLA tree build (K5).  Rounding is pinned with the _rn helpers so that the
+ * table is identical in the default and the -fmad=false build.              */
+
+/* r = min(r1, 0.95*max(0, (r2 - |B1| kc)/max(|A1|, eps))), perturbation.py:2021-2024 */
+__device__ __forceinline__ double merge_radius(double r1, double r2, double mA1,
+                                               double mB1, double kc_std, double eps)
+{
+    double num = add_rn(r2, -mul_rn(mB1, kc_std));
+    double r2_backw = mul_rn(0.95, pymax(0., num / pymax(mA1, eps)));
+    return pymin(r1, r2_backw);
+}
+
+/* one node = (A, B, r) ; merge node1 (first) then node2 */
+struct BlaNode { C A, B; double r; };
+__device__ __forceinline__ BlaNode bla_merge(BlaNode n1, BlaNode n2, double kc_std, double eps)
+{
+    BlaNode o;
+    o.A = cmul_rn(n2.A, n1.A);
+    o.B = cadd_rn(cmul_rn(n2.A, n1.B), n2.B);
+    o.r = merge_radius(n1.r, n2.r, cabs_rn(n1.A), cabs_rn(n1.B), kc_std, eps);
+    return o;
+}
+
+/* Leaf kernel: one thread per 8 orbit points; folds the three compressed
+ * levels (perturbation.py:1847-1874) and writes slot 2i. */
+__global__ void k_bla_leaf_m2(const C *__restrict__ Zn, long long comp_len,
+                              double kc_std, double eps, C *__restrict__ M,
+                              double *__restrict__ r)
+{
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= comp_len) return;
+    BlaNode n[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        C z = ldC(Zn, i * 8 + j);
+        n[j].A = mkC(mul_rn(2., z.re), mul_rn(2., z.im));
+        n[j].B = mkC(1., 0.);
+        n[j].r = mul_rn(eps, cabs_rn(n[j].A));
+    }
+#pragma unroll
+    for (int w = 1; w < 8; w <<= 1)
+#pragma unroll
+        for (int j = 0; j + w < 8; j += 2 * w) n[j] = bla_merge(n[j], n[j + w], kc_std, eps);
+    M[2 * (2 * i)] = n[0].A;
+    M[2 * (2 * i) + 1] = n[0].B;
+    r[2 * i] = n[0].r;
+    /* odd slots are written by the merge levels; clear this thread's one */
+    M[2 * (2 * i + 1)] = mkC(0., 0.);
+    M[2 * (2 * i + 1) + 1] = mkC(0., 0.);
+    r[2 * i + 1] = 0.;
+}
+
+/* Merge level stg >= 1 over comp_len nodes: one thread per output node
+ * (perturbation.py:1983-2024). */
+__global__ void k_bla_merge_m2(long long comp_len, int stg, double kc_std, double eps,
+                               C *__restrict__ M, double *__restrict__ r)
+{
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long step = 1LL << stg;
+    long long i = t * step;
+    if (i > comp_len - step) return;
+    long long ii = i + step / 2;
+    if (ii >= comp_len) return;
+    long long i1 = bla_index(i, stg - 1), i2 = bla_index(ii, stg - 1), ir = bla_index(i, stg);
+    BlaNode n1, n2;
+    n1.A = M[2 * i1]; n1.B = M[2 * i1 + 1]; n1.r = r[i1];
+    n2.A = M[2 * i2]; n2.B = M[2 * i2 + 1]; n2.r = r[i2];
+    BlaNode o = bla_merge(n1, n2, kc_std, eps);
+    M[2 * ir] = o.A; M[2 * ir + 1] = o.B; r[ir] = o.r;
+}
+
+/* ---- burning-ship family ---- */
+__device__ __forceinline__ void bs_jac(int flavor, double x, double y, double &fxx,
+                                       double &fxy, double &fyx, double &fyy)
+{
+    /* burning_ship.py:441-532 */
+    switch (flavor) {
+    case 1: fxx = mul_rn(2., x); fxy = mul_rn(-2., y); fyx = mul_rn(mul_rn(2., sgn(x)), fabs(y)); fyy = mul_rn(mul_rn(2., sgn(y)), fabs(x)); break;
+    case 2: fxx = mul_rn(2., x); fxy = mul_rn(-2., y); fyx = mul_rn(2., fabs(y)); fyy = mul_rn(mul_rn(2., sgn(y)), x); break;
+    case 3: fxx = mul_rn(2., x); fxy = mul_rn(-2., fabs(y)); fyx = mul_rn(2., y); fyy = mul_rn(2., x); break;
+    case 4: { double s = sgn(add_rn(mul_rn(x, x), -mul_rn(y, y))); fxx = mul_rn(mul_rn(2., s), x); fxy = mul_rn(mul_rn(-2., s), y); fyx = mul_rn(2., y); fyy = mul_rn(2., x); break; }
+    default: { double s = sgn(add_rn(mul_rn(x, x), -mul_rn(y, y))); fxx = mul_rn(mul_rn(2., s), x); fxy = mul_rn(mul_rn(-2., s), y); fyx = mul_rn(mul_rn(2., sgn(x)), fabs(y)); fyy = mul_rn(mul_rn(2., sgn(y)), fabs(x)); break; }
+    }
+}
+
+struct BlaNodeBS { double M[8]; double r; };
+__device__ __forceinline__ double fma2_rn(double a, double b, double c, double d)
+{
+    return add_rn(mul_rn(a, b), mul_rn(c, d)); /* a*b + c*d */
+}
+__device__ __forceinline__ BlaNodeBS bla_merge_bs(const BlaNodeBS &n1, const BlaNodeBS &n2,
+                                                  double kc_std, double eps)
+{
+    /* perturbation.py:2047-2105 */
+    BlaNodeBS o;
+    const double *M1 = n1.M, *M2 = n2.M;
+    o.M[0] = fma2_rn(M2[0], M1[0], M2[1], M1[2]);
+    o.M[1] = fma2_rn(M2[0], M1[1], M2[1], M1[3]);
+    o.M[2] = fma2_rn(M2[2], M1[0], M2[3], M1[2]);
+    o.M[3] = fma2_rn(M2[2], M1[1], M2[3], M1[3]);
+    o.M[4] = add_rn(fma2_rn(M2[0], M1[4], M2[1], M1[6]), M2[4]);
+    o.M[5] = add_rn(fma2_rn(M2[0], M1[5], M2[1], M1[7]), M2[5]);
+    o.M[6] = add_rn(fma2_rn(M2[2], M1[4], M2[3], M1[6]), M2[6]);
+    o.M[7] = add_rn(fma2_rn(M2[2], M1[5], M2[3], M1[7]), M2[7]);
+    double mA1 = pymax(pymax(pymax(fabs(M1[0]), fabs(M1[1])), fabs(M1[2])), fabs(M1[3]));
+    double mB1 = pymax(pymax(pymax(fabs(M1[4]), fabs(M1[5])), fabs(M1[6])), fabs(M1[7]));
+    o.r = merge_radius(n1.r, n2.r, mA1, mB1, kc_std, eps);
+    return o;
+}
+
+__global__ void k_bla_leaf_bs(int flavor, const C *__restrict__ Zn, long long comp_len,
+                              double kc_std, double eps, double *__restrict__ M,
+                              double *__restrict__ r)
+{
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= comp_len) return;
+    BlaNodeBS n[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        C z = ldC(Zn, i * 8 + j);
+        bs_jac(flavor, z.re, z.im, n[j].M[0], n[j].M[1], n[j].M[2], n[j].M[3]);
+        n[j].M[4] = 1.; n[j].M[5] = 0.; n[j].M[6] = 0.; n[j].M[7] = -1.;
+        n[j].r = mul_rn(eps, pymin(fabs(z.re), fabs(z.im)));
+    }
+#pragma unroll
+    for (int w = 1; w < 8; w <<= 1)
+#pragma unroll
+        for (int j = 0; j + w < 8; j += 2 * w) n[j] = bla_merge_bs(n[j], n[j + w], kc_std, eps);
+#pragma unroll
+    for (int d = 0; d < 8; d++) { M[8 * (2 * i) + d] = n[0].M[d]; M[8 * (2 * i + 1) + d] = 0.; }
+    r[2 * i] = n[0].r;
+    r[2 * i + 1] = 0.;
+}
+
+__global__ void k_bla_merge_bs(long long comp_len, int stg, double kc_std, double eps,
+                               double *__restrict__ M, double *__restrict__ r)
+{
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long step = 1LL << stg;
+    long long i = t * step;
+    if (i > comp_len - step) return;
+    long long ii = i + step / 2;
+    if (ii >= comp_len) return;
+    long long i1 = bla_index(i, stg - 1), i2 = bla_index(ii, stg - 1), ir = bla_index(i, stg);
+    BlaNodeBS n1, n2;
+#pragma unroll
+    for (int d = 0; d < 8; d++) { n1.M[d] = M[8 * i1 + d]; n2.M[d] = M[8 * i2 + d]; }
+    n1.r = r[i1]; n2.r = r[i2];
+    BlaNodeBS o = bla_merge_bs(n1, n2, kc_std, eps);
+#pragma unroll
+    for (int d = 0; d < 8; d++) M[8 * ir + d] = o.M[d];
+    r[ir] = o.r;
+}
+
+/* ======================================================================== */
+/* Unit-test and calibration kernels                                         */
+__global__ void k_xr_binop_c(int op, long long n, const C *a, const int *ae, const C *b,
+                             const int *be, C *out, int *oute)
+{
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    XC x = mkXC(a[i], ae[i]), y = mkXC(b[i], be[i]), r;
+    if (op == 0) r = x + y;
+    else if (op == 1) { C p, q; int e; coexp_c(x.m, x.e, y.m, y.e, p, q, e); r = mkXC(p - q, e); }
+    else r = x * y;
+    out[i] = r.m; oute[i] = r.e;
+}
+__global__ void k_xr_to_standard_c(long long n, const C *a, const int *ae, C *out)
+{
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = to_std(mkXC(a[i], ae[i]));
+}
+__global__ void k_hypot(long long n, const double *x, const double *y, double *out)
+{
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = hypot_rn(x[i], y[i]);
+}
+/* dependent-DFMA chains: 8 independent accumulators per thread */
+__global__ void __launch_bounds__(256) k_fp64_peak(int iters, double *out)
+{
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1., a2 = a0 + 2., a3 = a0 + 3.;
+    double a4 = a0 + 4., a5 = a0 + 5., a6 = a0 + 6., a7 = a0 + 7.;
+    const double m = 0.999999, c = 1e-7;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 12345.678) out[0] = s;
+}
+__global__ void k_flush(double *buf, long long n)
+{
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) buf[i] = buf[i] * 0.5 + 1.;
+}
+
+} /* namespace fsb */

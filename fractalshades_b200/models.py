@@ -1,0 +1,210 @@
+# -*- coding: utf-8 -*-
+"""
+Models on the hot path, with the reference's class names, constructor and
+`calc_std_div` signatures (models/mandelbrot_M2.py:61-71,432-444;
+models/burning_ship.py:230-238,971-981), field codes and stop codes.
+
+The plugin contract of the reference is kept (`calc_std_div` returns the dict
+of three factories `set_state / initialize / iterate`, utils.py:278-339,
+core.py:1918-1949); since numba closures cannot cross the C ABI, `initialize()`
+and `iterate()` return a `KernelSpec` naming the device-kernel variant.
+"""
+import numpy as np
+
+from . import settings
+from . import _native
+from .core import Fractal, KernelSpec, calc_options
+from .perturbation import PerturbationFractal
+
+BS_flavor_list = ("Burning ship", "Perpendicular burning ship", "Shark fin",
+                  "Celtic", "Buffalo")          # models/burning_ship.py:63-69
+
+
+def get_flavor_int(flavor):
+    if flavor not in BS_flavor_list:
+        raise ValueError(f"unknown burning-ship flavor {flavor!r}")
+    return BS_flavor_list.index(flavor) + 1
+
+
+def _set_potential(self):
+    self.potential_kind = "infinity"
+    self.potential_d = 2
+    self.potential_a_d = 1.
+    self.potential_M_cutoff = 1000.
+
+
+class Mandelbrot(Fractal):
+    """ Standard power-2 Mandelbrot (models/mandelbrot_M2.py:17-176) """
+
+    def __init__(self, directory: str):
+        super().__init__(directory)
+        _set_potential(self)
+        self.holomorphic = True
+
+    @calc_options
+    def calc_std_div(self, *, calc_name: str = "base_calc", subset=None,
+                     max_iter: int = 10000, M_divergence: float = 1000.,
+                     epsilon_stationnary: float = 0.01,
+                     calc_d2zndc2: bool = False, calc_orbit: bool = False,
+                     backshift: int = 0):
+        complex_codes = ["zn", "dzndz", "dzndc"]
+        if calc_d2zndc2:
+            complex_codes += ["d2zndc2"]
+        if calc_orbit:
+            complex_codes += ["zn_orbit"]
+        int_codes = []
+        stop_codes = ["max_iter", "divergence", "stationnary"]
+
+        def set_state():
+            def impl(instance):
+                instance.codes = (complex_codes, int_codes, stop_codes)
+                instance.complex_type = np.complex128
+                instance.potential_M = M_divergence
+                instance.backshift = backshift if calc_orbit else None
+            return impl
+
+        spec = KernelSpec(kind="std_M2", model=_native.FSB_MODEL_M2, flavor=0,
+                          max_iter=max_iter, M_divergence=M_divergence,
+                          epsilon_stationnary=epsilon_stationnary,
+                          calc_d2zndc2=calc_d2zndc2, calc_orbit=calc_orbit,
+                          backshift=backshift)
+        return {"set_state": set_state, "initialize": lambda: spec,
+                "iterate": lambda: spec}
+
+
+class Burning_ship(Fractal):
+    """ Standard Burning-ship family (models/burning_ship.py:125-429) """
+
+    def __init__(self, directory: str, flavor: str = "Burning ship"):
+        super().__init__(directory)
+        self.flavor = flavor
+        get_flavor_int(flavor)
+        _set_potential(self)
+        self.holomorphic = False
+
+    @calc_options
+    def calc_std_div(self, *, calc_name: str, subset, max_iter: int,
+                     M_divergence: float, calc_orbit: bool = False,
+                     backshift: int = 0):
+        complex_codes = ["xn", "yn", "dxnda", "dxndb", "dynda", "dyndb"]
+        if calc_orbit:
+            complex_codes += ["xn_orbit", "yn_orbit"]
+        int_codes = []
+        stop_codes = ["max_iter", "divergence", "stationnary"]
+
+        def set_state():
+            def impl(instance):
+                instance.codes = (complex_codes, int_codes, stop_codes)
+                instance.complex_type = np.float64
+                instance.potential_M = M_divergence
+                instance.backshift = backshift if calc_orbit else None
+            return impl
+
+        spec = KernelSpec(kind="std_BS", model=_native.FSB_MODEL_BS,
+                          flavor=get_flavor_int(self.flavor), max_iter=max_iter,
+                          M_divergence=M_divergence, calc_orbit=calc_orbit,
+                          backshift=backshift)
+        return {"set_state": set_state, "initialize": lambda: spec,
+                "iterate": lambda: spec}
+
+
+class Perturbation_mandelbrot(PerturbationFractal):
+    """ Arbitrary-precision power-2 Mandelbrot
+    (models/mandelbrot_M2.py:359-627) """
+
+    def __init__(self, directory: str):
+        super().__init__(directory)
+        _set_potential(self)
+        self.critical_pt = 0.
+        self.FP_code = "zn"
+        self.holomorphic = True
+
+    def FP_loop(self, NP_orbit, c0):
+        """ models/mandelbrot_M2.py:408-430 -> native MPFR orbit """
+        return self._native_orbit(NP_orbit, c0, flavor=None, exponent=2)
+
+    @calc_options
+    def calc_std_div(self, *, calc_name: str, subset, max_iter: int,
+                     M_divergence: float, epsilon_stationnary: float,
+                     BLA_eps: float = 1e-6, interior_detect: bool = False,
+                     calc_dzndc: bool = True, calc_orbit: bool = False,
+                     backshift: int = 0):
+        complex_codes = ["zn"]
+        if interior_detect:
+            complex_codes += ["dzndz"]
+        if calc_dzndc:
+            complex_codes += ["dzndc"]
+        if calc_orbit:
+            complex_codes += ["zn_orbit"]
+        int_codes = ["ref_cycle_iter"]
+        stop_codes = ["max_iter", "divergence", "stationnary"]
+        BLA_activated = ((BLA_eps is not None)
+                         and bool(self.dx < settings.newton_zoom_level))
+
+        def set_state():
+            def impl(instance):
+                instance.complex_type = np.complex128
+                instance.potential_M = M_divergence
+                instance.codes = (complex_codes, int_codes, stop_codes)
+                instance.calc_dZndz = interior_detect
+                instance.calc_dZndc = calc_dzndc
+            return impl
+
+        spec = KernelSpec(kind="perturb_M2", max_iter=max_iter,
+                          M_divergence=M_divergence,
+                          epsilon_stationnary=epsilon_stationnary,
+                          BLA_eps=BLA_eps, bla_activated=BLA_activated,
+                          calc_dzndc=calc_dzndc, calc_dzndz=interior_detect,
+                          calc_orbit=calc_orbit, backshift=backshift)
+        return {"set_state": set_state, "initialize": lambda: spec,
+                "iterate": lambda: spec}
+
+
+class Perturbation_burning_ship(PerturbationFractal):
+    """ Arbitrary-precision Burning-ship family
+    (models/burning_ship.py:863-1130) """
+
+    def __init__(self, directory: str, flavor: str = "Burning ship"):
+        super().__init__(directory)
+        self.flavor = flavor
+        get_flavor_int(flavor)
+        _set_potential(self)
+        self.critical_pt = 0.
+        self.FP_code = ["xn", "yn"]
+        self.holomorphic = False
+
+    def FP_loop(self, NP_orbit, c0):
+        """ models/burning_ship.py:937-968 """
+        return self._native_orbit(NP_orbit, c0,
+                                  flavor=get_flavor_int(self.flavor))
+
+    @calc_options
+    def calc_std_div(self, *, calc_name: str, subset, max_iter: int,
+                     M_divergence: float, BLA_eps: float = 1e-6,
+                     calc_hessian: bool = True, calc_orbit: bool = False,
+                     backshift: int = 0):
+        complex_codes = ["xn", "yn"]
+        if calc_hessian:
+            complex_codes += ["dxnda", "dxndb", "dynda", "dyndb"]
+        if calc_orbit:
+            complex_codes += ["xn_orbit", "yn_orbit"]
+        int_codes = ["ref_cycle_iter"]
+        stop_codes = ["max_iter", "divergence"]
+        BLA_activated = ((BLA_eps is not None)
+                         and bool(self.dx < settings.newton_zoom_level))
+
+        def set_state():
+            def impl(instance):
+                instance.complex_type = np.float64
+                instance.potential_M = M_divergence
+                instance.codes = (complex_codes, int_codes, stop_codes)
+                instance.backshift = backshift if calc_orbit else None
+            return impl
+
+        spec = KernelSpec(kind="perturb_BS", flavor=get_flavor_int(self.flavor),
+                          max_iter=max_iter, M_divergence=M_divergence,
+                          BLA_eps=BLA_eps, bla_activated=BLA_activated,
+                          calc_hessian=calc_hessian, calc_orbit=calc_orbit,
+                          backshift=backshift)
+        return {"set_state": set_state, "initialize": lambda: spec,
+                "iterate": lambda: spec}

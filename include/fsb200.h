@@ -1,0 +1,186 @@
+/*
+ * fsb200.h -- C ABI of libfsb200.so : the B200 (sm_100a) implementation of the
+ * Fractalshades per-pixel iteration hot path.
+ *
+ * Plain pointers and sizes only; no torch / numpy types.  Every entry point
+ * names the reference interface it replaces (GBillotey/Fractalshades v1.2.1,
+ * paths relative to src/fractalshades/):
+ *
+ *   fsb_std_run        <- Fractal.numba_cycle_call -> numba_cycles
+ *                         (core.py:2022-2027, 2935-2963) for the standard
+ *                         Mandelbrot / Burning-ship `calc_std_div`
+ *   fsb_frame_create   <- PerturbationFractal.get_cycle_indep_args
+ *                         (perturbation.py:431-562): per-frame tables; the
+ *                         dZndc/dZndz paths (numba_dZndc_path[_BS],
+ *                         numba_dZndz_path, perturbation.py:2282-2516) and the
+ *                         BLA tree (numba_make_BLA[_BS], :1819-1973) are
+ *                         computed by the library when not supplied
+ *   fsb_frame_run      <- PerturbationFractal.numba_cycle_call ->
+ *                         numba_cycles_perturb[_BS] (perturbation.py:414-428,
+ *                         988-1045, 1406-1451)
+ *   fsb_frame_run_device  same, with device-resident input/output (bench)
+ *
+ * Return codes: 0 ok, 1 = USER_INTERRUPTED (core.py:1280), < 0 error; the
+ * message is available from fsb_last_error() (thread-local).
+ * There is no CPU fallback: without a CUDA device every compute call fails.
+ *
+ * Array conventions are those of the reference (core.py:2044-2075): for npts
+ * points, c_pix is complex128[npts]; Z is (n_Z, npts) row-major, complex128
+ * for holomorphic models and float64 for the burning-ship family; U is
+ * (n_U, npts) int32; stop_reason (1, npts) int8; stop_iter (1, npts) int32.
+ * Xrange arrays (numpy_utils/xrange.py) are passed as a mantissa array plus an
+ * int32 exponent array.
+ */
+#ifndef FSB200_H
+#define FSB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FSB_OK 0
+#define FSB_USER_INTERRUPTED 1
+
+enum { FSB_MODEL_M2 = 0, FSB_MODEL_BS = 1 };
+
+typedef struct fsb_stats {
+    double kernel_ms;       /* CUDA-event time of the pixel kernel(s)            */
+    double h2d_ms;          /* host->device copies (0 for *_device entry points) */
+    double d2h_ms;          /* device->host copies                               */
+    int64_t n_iter_exec;    /* executed full iterations (not BLA-skipped)        */
+    int64_t n_bla_steps;    /* applied BLA steps                                 */
+    int64_t n_rebase;       /* rebases (both kinds)                              */
+    int64_t sum_stop_iter;  /* sum over pixels of stop_iter (effective iters)    */
+    int64_t n_launches;     /* kernels launched by this call                     */
+} fsb_stats;
+
+/* ---- library / device ---------------------------------------------------- */
+int fsb_device_count(void);            /* < 0 on CUDA error                     */
+int fsb_init(int device);              /* bind this process to one GPU          */
+void fsb_shutdown(void);
+const char *fsb_last_error(void);
+const char *fsb_build_info(void);      /* "fsb200 sm_100a fmad=on|off ..."      */
+int fsb_device_info(char *name, int name_cap, int *sm_count, int64_t *mem_bytes);
+
+/* pinned host memory and raw device memory (bench / tile scheduler) */
+void *fsb_host_alloc(int64_t bytes);
+void fsb_host_free(void *p);
+void *fsb_dev_alloc(int64_t bytes);
+void fsb_dev_free(void *p);
+int fsb_memcpy_h2d(void *dst_dev, const void *src_host, int64_t bytes);
+int fsb_memcpy_d2h(void *dst_host, const void *src_dev, int64_t bytes);
+int fsb_dev_memset(void *dst_dev, int value, int64_t bytes);
+/* write `bytes` of a scratch buffer: flushes the L2 between timed launches */
+int fsb_flush_l2(void);
+
+/* ---- standard escape-time loop ------------------------------------------- */
+typedef struct fsb_std_desc {
+    int32_t model;            /* FSB_MODEL_M2 / FSB_MODEL_BS                  */
+    int32_t flavor;           /* BS family flavour 1..5 (burning_ship.py:63)  */
+    double center_re, center_im;
+    double dx;
+    double lin_mat[4];        /* core.py:1470-1484                            */
+    int64_t max_iter;
+    double M_divergence_sq;
+    double epsilon_stationnary_sq;
+    int32_t calc_d2zndc2;
+    int32_t calc_orbit;
+    int64_t backshift;
+} fsb_std_desc;
+
+/* number of rows of Z for this description */
+int fsb_std_nz(const fsb_std_desc *d);
+
+int fsb_std_run(const fsb_std_desc *d, int64_t npts, const double *c_pix,
+                double *Z, int8_t *stop_reason, int32_t *stop_iter,
+                const volatile uint8_t *interrupted, fsb_stats *stats);
+int fsb_std_run_device(const fsb_std_desc *d, int64_t npts,
+                       const double *d_c_pix, double *d_Z,
+                       int8_t *d_stop_reason, int32_t *d_stop_iter,
+                       fsb_stats *stats);
+
+/* ---- perturbation frames ------------------------------------------------- */
+typedef struct fsb_frame fsb_frame;   /* opaque, owns the device tables */
+
+typedef struct fsb_frame_desc {
+    int32_t model;            /* FSB_MODEL_M2 (holomorphic) / FSB_MODEL_BS    */
+    int32_t flavor;
+    int64_t L;                /* len(Zn_path)                                 */
+    const double *Zn_path;    /* complex128[L]                                */
+    /* Xrange reference points (perturbation.py:317-375); n_xr may be 0 */
+    int64_t n_xr;
+    const int32_t *ref_index_xr;
+    const double *ref_xr;     /* M2: complex128[n_xr]; BS: refx float64[n_xr] */
+    const int32_t *ref_xr_e;
+    const double *refy_xr;    /* BS only                                      */
+    const int32_t *refy_xr_e;
+    int64_t ref_div_iter;
+    int64_t ref_order;        /* 1<<62 when the reference is not a cycle      */
+    double drift[2];          /* M2: complex mantissa; BS: {driftx, drifty}   */
+    int32_t drift_e[2];       /* M2: drift_e[0];       BS: {ex, ey}           */
+    double lin_scale;  int32_t lin_scale_e;  int32_t _pad0;
+    double lin_mat[4];
+    double kc;         int32_t kc_e;         int32_t _pad1;  /* BLA bound     */
+    double scale_deriv; int32_t scale_deriv_e; int32_t _pad2; /* = dx_xr      */
+    /* options of calc_std_div */
+    int32_t xr_detect;        /* xr_detect_activated (perturbation.py:152)    */
+    int32_t bla_activated;
+    int32_t calc_dzndc;       /* M2: calc_dzndc ; BS: calc_hessian            */
+    int32_t calc_dzndz;       /* interior_detect (M2 only)                    */
+    int32_t calc_orbit;
+    int32_t _pad3;
+    int64_t backshift;
+    int64_t max_iter;
+    double M_divergence_sq;
+    double epsilon_stationnary_sq;
+    double BLA_eps;
+    /* Optional caller-supplied tables (staged parity: feed the oracle's).
+     * NULL => computed by the library. */
+    const double *dZndc;      /* M2: complex128[L]; BS: float64[4][L]         */
+    const int32_t *dZndc_e;   /* xr_detect only; M2: [L]; BS: [4][L]          */
+    const double *dZndz;      /* complex128[L+1]                              */
+    const int32_t *dZndz_e;
+    const double *M_bla;      /* M2: complex128[2*bla_len]; BS: f64[8*bla_len]*/
+    const double *r_bla;      /* float64[bla_len]                             */
+    int64_t bla_len;
+    int32_t stages_bla;
+    int32_t _pad4;
+} fsb_frame_desc;
+
+int fsb_frame_create(const fsb_frame_desc *desc, fsb_frame **out);
+int fsb_frame_destroy(fsb_frame *f);
+int fsb_frame_nz(const fsb_frame *f);          /* rows of Z                    */
+int64_t fsb_frame_bla_len(const fsb_frame *f);
+int fsb_frame_stages_bla(const fsb_frame *f);
+double fsb_frame_setup_ms(const fsb_frame *f, int what); /* 0 upload, 1 dZndc, 2 BLA */
+/* read back the per-frame tables (tests) */
+int fsb_frame_get_bla(const fsb_frame *f, double *M_bla, double *r_bla);
+int fsb_frame_get_dzndc(const fsb_frame *f, double *dZndc, int32_t *dZndc_e);
+int fsb_frame_get_dzndz(const fsb_frame *f, double *dZndz, int32_t *dZndz_e);
+
+int fsb_frame_run(fsb_frame *f, int64_t npts, const double *c_pix, double *Z,
+                  int32_t *U, int8_t *stop_reason, int32_t *stop_iter,
+                  const volatile uint8_t *interrupted, fsb_stats *stats);
+int fsb_frame_run_device(fsb_frame *f, int64_t npts, const double *d_c_pix,
+                         double *d_Z, int32_t *d_U, int8_t *d_stop_reason,
+                         int32_t *d_stop_iter, fsb_stats *stats);
+
+/* ---- Xrange device arithmetic, exposed for unit tests --------------------
+ * (mirror of the reference's tests/test_numba_xr.py; runs on the GPU)
+ * op: 0 add, 1 sub, 2 mul ; complex operands (re, im interleaved) */
+int fsb_xr_binop_c(int op, int64_t n, const double *a, const int32_t *ae,
+                   const double *b, const int32_t *be, double *out,
+                   int32_t *oute);
+int fsb_xr_to_standard_c(int64_t n, const double *a, const int32_t *ae,
+                         double *out);
+int fsb_hypot_test(int64_t n, const double *x, const double *y, double *out);
+/* FP64 FMA-pipe microbenchmark: returns measured TFLOP/s (dependent DFMA
+ * chains, all SMs), used as the compute roofline denominator */
+double fsb_fp64_peak_tflops(int iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSB200_H */

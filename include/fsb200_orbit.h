@@ -1,0 +1,72 @@
+/*
+ * fsb200_orbit.h -- C ABI of libfsb200_orbit.so (host, no CUDA).
+ *
+ * Native full-precision reference orbit.  Each entry point replaces one
+ * function of the reference's Cython extension `fractalshades.mpmath_utils.
+ * FP_loop` (the only compiled component of the reference):
+ *
+ *   fsb_orbit_mandelbrot     <- perturbation_mandelbrot_FP_loop /
+ *                               perturbation_mandelbrotN_FP_loop
+ *                               (mpmath_utils/FP_loop.pyx:237-421)
+ *   fsb_orbit_burning_ship   <- perturbation_nonholomorphic_FP_loop
+ *                               (mpmath_utils/FP_loop.pyx:1828-1979)
+ *
+ * Plain pointers and sizes only.  All buffers are caller-owned.
+ */
+#ifndef FSB200_ORBIT_H
+#define FSB200_ORBIT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Flavours of the non-holomorphic family (FP_loop.pyx:1343-1347). */
+enum {
+    FSB_FLAVOR_BURNING_SHIP = 1,
+    FSB_FLAVOR_PERPENDICULAR_BS = 2,
+    FSB_FLAVOR_SHARK_FIN = 3,
+    FSB_FLAVOR_CELTIC = 4,
+    FSB_FLAVOR_BUFFALO = 5
+};
+
+/* One orbit point that underflows a double: value = (mx * 2^ex, my * 2^ey),
+ * mantissas in [0.5, 1) as returned by mpfr_get_d_2exp (FP_loop.pyx:424-454). */
+typedef struct fsb_orbit_xr {
+    int64_t index;
+    double mx;
+    double my;
+    int32_t ex;
+    int32_t ey;
+} fsb_orbit_xr;
+
+/*
+ * orbit      : out, 2*(max_iter+1) doubles (re, im interleaved); orbit[0:2]=0
+ * exponent   : 2 for z^2+c, >2 for z^n+c
+ * need_xrange: register points with |z| < 1e-300 into xr_out
+ * M          : escape radius for the reference point
+ * seed_x/y   : decimal strings of the reference point, parsed at prec_bits
+ * xr_out     : out, capacity xr_cap entries; *xr_count receives the number used
+ * returns    : first invalid orbit index (escape index, or max_iter+1 if the
+ *              orbit never escaped); < 0 on error (-2 bad argument, -3 bad
+ *              number string, -4 xr_out too small)
+ */
+int64_t fsb_orbit_mandelbrot(double *orbit, int64_t max_iter, uint32_t exponent,
+                             int need_xrange, double M, const char *seed_x,
+                             const char *seed_y, int64_t prec_bits,
+                             fsb_orbit_xr *xr_out, int64_t xr_cap,
+                             int64_t *xr_count);
+
+/* Same contract; `flavor` is one of FSB_FLAVOR_*; a point is registered as
+ * Xrange when |x| < 1e-300 or |y| < 1e-300 (FP_loop.pyx:1933). */
+int64_t fsb_orbit_burning_ship(double *orbit, int64_t max_iter, int flavor,
+                               int need_xrange, double M, const char *seed_x,
+                               const char *seed_y, int64_t prec_bits,
+                               fsb_orbit_xr *xr_out, int64_t xr_cap,
+                               int64_t *xr_count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSB200_ORBIT_H */

@@ -1,0 +1,135 @@
+# -*- coding: utf-8 -*-
+"""
+Parity cases shared by tools/gen_golden.py (which runs them through the live
+reference) and the test-suite (which re-runs them through the oracle and the
+CUDA path).  Views are those of the reference's own tests / examples
+(tests/test_perturbation.py, examples/batch_mode/*) at reduced `nx` so that
+the oracle finishes in seconds and the fixtures stay small.
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from fractalshades_b200.views import VIEWS  # noqa: E402
+
+_STD = dict(M_divergence=1e3, epsilon_stationnary=1e-3)
+
+CASES = {
+    # ---- standard escape-time loop (BASELINE config 1) ----
+    "std_M2_cfg1": dict(
+        kind="std_M2", x=-1.0, y=0.0, dx=5.0, nx=64,
+        calc=dict(max_iter=5000, M_divergence=1000., epsilon_stationnary=1e-3)),
+    "std_M2_seahorse_orbit": dict(
+        kind="std_M2", x=-0.746223962861, y=-0.0959468433527, dx=0.00745,
+        nx=64, theta_deg=20.,
+        calc=dict(max_iter=5000, M_divergence=1000., epsilon_stationnary=1e-3,
+                  calc_d2zndc2=True, calc_orbit=True, backshift=3)),
+    # ---- perturbation, fp64 range ----
+    "p_M2_E20": dict(
+        kind="perturb_M2", precision=30, x="-1.74928893611435556407228",
+        y="0.", dx="5.e-20", nx=64,
+        calc=dict(max_iter=50000, BLA_eps=1e-6, interior_detect=False,
+                  calc_dzndc=True, **_STD)),
+    "p_M2_E20_nobla_interior": dict(
+        kind="perturb_M2", precision=30, x="-1.74928893611435556407228",
+        y="0.", dx="5.e-20", nx=48,
+        calc=dict(max_iter=20000, BLA_eps=None, interior_detect=True,
+                  calc_dzndc=True, **_STD)),
+    "p_M2_int_E11": dict(
+        kind="perturb_M2", precision=17, x="-1.74920463345912691e+00",
+        y="-2.8684660237361114e-04", dx="5e-12", nx=64,
+        calc=dict(max_iter=50000, BLA_eps=1e-6, interior_detect=True,
+                  calc_dzndc=False, **_STD)),
+    "p_M2_divref_orbit": dict(
+        kind="perturb_M2", precision=18, x="-1.36768994867991128",
+        y="0.00949048853859240532", dx="2.477633848347765e-8", nx=64,
+        xy_ratio=1.6, theta_deg=30.,
+        calc=dict(max_iter=20000, BLA_eps=1e-6, interior_detect=False,
+                  calc_dzndc=True, calc_orbit=True, backshift=2, **_STD)),
+    "p_M2_flake": dict(
+        kind="perturb_M2", precision=200, x=VIEWS["glitch_dyn"]["x"],
+        y=VIEWS["glitch_dyn"]["y"], dx="1.8e-157", nx=64, xy_ratio=16 / 9.,
+        calc=dict(max_iter=50000, BLA_eps=1e-6, interior_detect=False,
+                  calc_dzndc=True, **_STD)),
+    "p_M2_shallow": dict(
+        kind="perturb_M2", precision=12, x="-0.75", y="0.1", dx="0.01", nx=48,
+        calc=dict(max_iter=2000, BLA_eps=1e-6, interior_detect=False,
+                  calc_dzndc=True, **_STD)),
+    "p_M2_E213": dict(
+        kind="perturb_M2", precision=224, x=VIEWS["M2_E213"]["x"],
+        y=VIEWS["M2_E213"]["y"], dx="3.226224123547768e-213", nx=48,
+        calc=dict(max_iter=350000, BLA_eps=1e-6, interior_detect=False,
+                  calc_dzndc=True, **_STD)),
+    "p_M2_deep250": dict(
+        kind="perturb_M2", precision=270, x=VIEWS["deep_julia_2608"]["x"][:290],
+        y=VIEWS["deep_julia_2608"]["y"][:290], dx="1e-250", nx=48,
+        xy_ratio=16 / 9.,
+        calc=dict(max_iter=200000, BLA_eps=1e-6, interior_detect=False,
+                  calc_dzndc=True, **_STD)),
+    # ---- perturbation, Xrange path (dx < 1e-300) ----
+    "p_M2_ultradeep_xr": dict(
+        kind="perturb_M2", precision=550,
+        x=VIEWS["ultradeep_interior_detect"]["x"],
+        y=VIEWS["ultradeep_interior_detect"]["y"], dx="5.06722630e-433",
+        nx=48,
+        calc=dict(max_iter=200000, BLA_eps=1e-6, interior_detect=True,
+                  calc_dzndc=True, **_STD)),
+    "p_M2_deep1000_xr": dict(
+        kind="perturb_M2", precision=1020,
+        x=VIEWS["deep_julia_2608"]["x"][:1040],
+        y=VIEWS["deep_julia_2608"]["y"][:1040], dx="1e-1000", nx=32,
+        xy_ratio=16 / 9.,
+        calc=dict(max_iter=1000000, BLA_eps=1e-6, interior_detect=False,
+                  calc_dzndc=True, **_STD)),
+    "p_M2_deep400_xr_nobla": dict(
+        kind="perturb_M2", precision=420,
+        x=VIEWS["deep_julia_2608"]["x"][:440],
+        y=VIEWS["deep_julia_2608"]["y"][:440], dx="1e-400", nx=24,
+        calc=dict(max_iter=250000, BLA_eps=None, interior_detect=False,
+                  calc_dzndc=True, **_STD)),
+}
+
+# Burning-ship family, standard loop: all five flavours
+for _i, _fl in enumerate(("Burning ship", "Perpendicular burning ship",
+                          "Shark fin", "Celtic", "Buffalo")):
+    CASES[f"std_BS_f{_i + 1}"] = dict(
+        kind="std_BS", init=dict(flavor=_fl), x=-0.5, y=-0.5, dx=3.0, nx=48,
+        theta_deg=10. * _i,
+        calc=dict(max_iter=800, M_divergence=1000.,
+                  calc_orbit=(_i == 0), backshift=(2 if _i == 0 else 0)))
+
+_BS = VIEWS["bs_deep_julia_2430"]
+# Burning-ship family, perturbation
+CASES["p_BS_f1_E30_skew"] = dict(
+    kind="perturb_BS", init=dict(flavor="Burning ship"), precision=50,
+    x=_BS["x"][:60], y=_BS["y"][:60], dx="1e-30", nx=48, xy_ratio=1.8,
+    theta_deg=12.0, skew=_BS["skew"],
+    calc=dict(max_iter=30000, M_divergence=1e3, BLA_eps=1e-6,
+              calc_hessian=True))
+CASES["p_BS_f1_E500_xr"] = dict(
+    kind="perturb_BS", init=dict(flavor="Burning ship"), precision=520,
+    x=_BS["x"][:540], y=_BS["y"][:540], dx="1e-500", nx=32, xy_ratio=1.8,
+    theta_deg=12.0, skew=_BS["skew"],
+    calc=dict(max_iter=100000, M_divergence=1e3, BLA_eps=1e-6,
+              calc_hessian=True))
+# boundary points found by bisection with the standard-loop oracle
+_BS_PTS = {
+    1: ("-1.7505941429008662", "0.0214423020148999"),
+    2: ("-1.3604879916723847", "0.0015808658322309468"),
+    3: ("-1.4477399868839198", "-0.6048320439477123"),
+    4: ("-1.760370697674034", "0.011733974791909326"),
+    5: ("-1.758364745737221", "0.024352431136909887"),
+}
+for _i, _fl in enumerate(("Perpendicular burning ship", "Shark fin", "Celtic",
+                          "Buffalo")):
+    CASES[f"p_BS_f{_i + 2}_E12"] = dict(
+        kind="perturb_BS", init=dict(flavor=_fl), precision=30,
+        x=_BS_PTS[_i + 2][0], y=_BS_PTS[_i + 2][1], dx="1e-12", nx=32,
+        calc=dict(max_iter=20000, M_divergence=1e3, BLA_eps=1e-6,
+                  calc_hessian=True, calc_orbit=(_i == 0),
+                  backshift=(2 if _i == 0 else 0)))
+CASES["p_BS_f1_E12_nohess_nobla"] = dict(
+    kind="perturb_BS", init=dict(flavor="Burning ship"), precision=30,
+    x=_BS_PTS[1][0], y=_BS_PTS[1][1], dx="1e-12", nx=32,
+    calc=dict(max_iter=20000, M_divergence=1e3, BLA_eps=None,
+              calc_hessian=False))

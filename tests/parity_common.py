@@ -1,0 +1,202 @@
+# -*- coding: utf-8 -*-
+"""
+Shared helpers of the parity tests: build a case's inputs with the PRODUCT's
+host code (fractalshades_b200: orbit, Xrange scalars, pixel grid), then run it
+through the CPU oracle and/or the CUDA path.
+"""
+import hashlib
+import json
+import os
+import tempfile
+
+import numpy as np
+
+import oracle_lib as ol
+from cases import CASES
+import fractalshades_b200 as fsb
+import fractalshades_b200.models as fsm
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+_CLS = {"std_M2": fsm.Mandelbrot, "std_BS": fsm.Burning_ship,
+        "perturb_M2": fsm.Perturbation_mandelbrot,
+        "perturb_BS": fsm.Perturbation_burning_ship}
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def load_golden(name, mode):
+    g = np.load(os.path.join(GOLDEN, f"{name}.{mode}.npz"))
+    meta = json.loads(str(g["meta"]))
+    return g, meta
+
+
+def make_fractal(name, workdir=None):
+    """ zoom() + option binding, WITHOUT touching the GPU """
+    case = CASES[name]
+    workdir = workdir or tempfile.mkdtemp(prefix="fsb_")
+    f = _CLS[case["kind"]](workdir, **case.get("init", {}))
+    zoom = dict(x=case["x"], y=case["y"], dx=case["dx"], nx=case["nx"],
+                xy_ratio=case.get("xy_ratio", 1.0),
+                theta_deg=case.get("theta_deg", 0.), **case.get("skew", {}))
+    if case["kind"].startswith("perturb"):
+        zoom["precision"] = case["precision"]
+    f.zoom(**zoom)
+    return f, case
+
+
+def bind_calc(f, case):
+    """ What the calc_options decorator + calc_hook do, minus the device frame:
+    returns the KernelSpec. """
+    kw = dict(calc_name="c", subset=None, **case["calc"])
+    ret = type(f).calc_std_div.__wrapped__(f, **kw)
+    for k, v in kw.items():
+        setattr(f, k, v)
+    ret["set_state"]()(f)
+    spec = ret["iterate"]()
+    f._kernel_options = vars(spec).copy()
+    return spec
+
+
+def all_c_pix(f):
+    return np.ascontiguousarray(np.concatenate(
+        [np.ravel(f.chunk_pixel_pos(cs, False, None)) for cs in f.chunk_slices()]))
+
+
+def host_tables(name):
+    """ Per-frame tables from the product's host code (no GPU). """
+    f, case = make_fractal(name)
+    bind_calc(f, case)
+    t = f.frame_tables()
+    return f, case, t
+
+
+def oracle_fill_tables(t):
+    """ dZndc / dZndz / BLA tables by the ORACLE builders (in place) """
+    xr = t["xr_detect"]
+    if t["kind"] == "perturb_M2":
+        if t["calc_dzndc"]:
+            t["dZndc"], t["dZndc_e"] = ol.dzndc_path_m2(
+                t["Zn_path"], t["ref_index_xr"], t["ref_xr"], t["ref_xr_e"],
+                t["ref_div_iter"], t["ref_order"], t["dx"], t["dx_e"], xr)
+        if t["calc_dzndz"]:
+            t["dZndz"], t["dZndz_e"] = ol.dzndz_path_m2(
+                t["Zn_path"], t["ref_index_xr"], t["ref_xr"], t["ref_xr_e"],
+                t["ref_div_iter"], t["ref_order"], xr)
+        if t["bla_activated"]:
+            (t["M_bla"], t["r_bla"], t["bla_len"], t["stages_bla"]
+             ) = ol.make_bla_m2(t["Zn_path"], t["kc"], t["kc_e"], t["BLA_eps"])
+    else:
+        if t["calc_hessian"]:
+            d4, e4 = ol.dzndc_path_bs(
+                t["flavor"], t["Zn_path"], t["ref_index_xr"], t["refx_xr"],
+                t["refx_xr_e"], t["refy_xr"], t["refy_xr_e"], t["ref_div_iter"],
+                t["ref_order"], t["dx"], t["dx_e"], xr)
+            for j, k in enumerate(("dXnda", "dXndb", "dYnda", "dYndb")):
+                t[k] = d4[j]
+                t[k + "_e"] = e4[j] if e4 is not None else None
+        if t["bla_activated"]:
+            (t["M_bla"], t["r_bla"], t["bla_len"], t["stages_bla"]
+             ) = ol.make_bla_bs(t["flavor"], t["Zn_path"], t["kc"], t["kc_e"],
+                                t["BLA_eps"])
+    return t
+
+
+def run_oracle(name, nthreads=0):
+    """ (Z, U, stop_reason, stop_iter, extra) through the CPU oracle """
+    case = CASES[name]
+    if case["kind"].startswith("std"):
+        f, case = make_fractal(name)
+        c_pix = all_c_pix(f)
+        center = complex(f.x, f.y)
+        if case["kind"] == "std_M2":
+            Z, U, sr, si = ol.std_m2(c_pix, center, f.dx, f.lin_mat,
+                                     nthreads=nthreads, **case["calc"])
+        else:
+            Z, U, sr, si = ol.std_bs(fsm.get_flavor_int(f.flavor), c_pix, center,
+                                     f.dx, f.lin_mat, nthreads=nthreads,
+                                     **case["calc"])
+        return Z, U, sr, si, {"c_pix": c_pix, "fractal": f}
+    f, case, t = host_tables(name)
+    oracle_fill_tables(t)
+    c_pix = all_c_pix(f)
+    Z, U, sr, si, cnt = ol.perturb(t, c_pix, nthreads)
+    return Z, U, sr, si, {"c_pix": c_pix, "tables": t, "fractal": f,
+                          "counters": cnt}
+
+
+def run_gpu_case(name, strict, use_oracle_tables=False, tables=None):
+    """ Same case through the CUDA path (C ABI via the product's Python).
+    Perturbation: device frame built from the host tables; the library
+    computes dZndc / BLA itself unless use_oracle_tables. """
+    from fractalshades_b200 import settings, _native
+    from fractalshades_b200.perturbation import create_frame
+    case = CASES[name]
+    if case["kind"].startswith("std"):
+        f, case = make_fractal(name)
+        spec = bind_calc(f, case)
+        settings.strict_ieee = strict
+        try:
+            indep = f.get_cycle_indep_args(spec, spec)
+            c_pix = all_c_pix(f)
+            n = c_pix.shape[0]
+            n_Z = len(f.codes[0])
+            Z = np.zeros((n_Z, n), f.complex_type)
+            U = np.zeros((0, n), np.int32)
+            sr = -np.ones((1, n), np.int8)
+            si = np.zeros((1, n), np.int32)
+            rc = f.numba_cycle_call((c_pix, Z, U, sr, si), indep)
+            assert rc == 0
+        finally:
+            settings.strict_ieee = False
+        return Z, U, sr, si, {"stats": fsb.Fractal._last_stats}
+    if tables is None:
+        f, case, t = host_tables(name)
+        c_pix = all_c_pix(f)
+        if use_oracle_tables:
+            oracle_fill_tables(t)
+    else:
+        t, c_pix = tables
+    frame = create_frame(t, strict=strict, use_tables=use_oracle_tables)
+    try:
+        n = c_pix.shape[0]
+        m2 = t["kind"] == "perturb_M2"
+        Z = np.zeros((frame.nz, n), np.complex128 if m2 else np.float64)
+        U = np.zeros((1, n), np.int32)
+        sr = -np.ones((1, n), np.int8)
+        si = np.zeros((1, n), np.int32)
+        rc = frame.run(c_pix, Z, U, sr, si)
+        assert rc == 0
+        extra = {"stats": frame.last_stats, "setup_ms": frame.setup_ms()}
+        if t["bla_activated"]:
+            extra["bla"] = frame.get_bla()
+        if (m2 and t["calc_dzndc"]) or ((not m2) and t["calc_hessian"]):
+            extra["dzndc"] = frame.get_dzndc()
+        if m2 and t["calc_dzndz"]:
+            extra["dzndz"] = frame.get_dzndz()
+    finally:
+        frame.close()
+    return Z, U, sr, si, extra
+
+
+def same_bits(a, b):
+    """ bit-for-bit equality treating any-NaN == any-NaN and -0 == +0 """
+    a = np.asarray(a)
+    b = np.asarray(b)
+    if a.shape != b.shape:
+        return False
+    if np.iscomplexobj(a):
+        return same_bits(a.real, b.real) and same_bits(a.imag, b.imag)
+    return bool(np.all((a == b) | (np.isnan(a) & np.isnan(b))))
+
+
+def frac_same(a, b):
+    a = np.asarray(a)
+    b = np.asarray(b)
+    if np.iscomplexobj(a):
+        ok = (((a.real == b.real) | (np.isnan(a.real) & np.isnan(b.real)))
+              & ((a.imag == b.imag) | (np.isnan(a.imag) & np.isnan(b.imag))))
+    else:
+        ok = (a == b) | (np.isnan(a) & np.isnan(b))
+    return float(np.mean(ok)) if ok.size else 1.0
