@@ -1,0 +1,495 @@
+#!/usr/bin/env python
+# -*- coding: utf-8 -*-
+"""
+bench.py -- headline benchmark of the per-pixel iteration hot path.
+
+    python bench.py --gpus N --steps K --warmup W [--workload config2]
+    python bench.py --impl reference ...      (CPU arm: oracle port, host cores)
+
+A "step" is one pass of the hot path over one whole frame (all tiles of the
+image, 8 294 400 points at 4K).  Metric (BASELINE.json): effective pixel-
+iterations per second = sum over pixels of stop_iter / time, BLA-skipped
+iterations counted, in Gpix-iter/s; s/frame is ms_per_step / 1000.
+
+  value   device-resident: c_pix and the output planes live in HBM, timed with
+          CUDA events on the launching stream (fsb_stats.kernel_ms), L2 flushed
+          between steps.
+  e2e     the reference-facing seam `numba_cycle_call` (-> fsb_frame_run) with
+          pinned HOST buffers: H2D of c_pix, kernel, D2H of Z/U/stop_* inside
+          the timed region (wall clock around the call).
+
+N > 1 (torchrun): every rank renders its own full frame (frames of a zoom
+movie are independent: weak scaling, no data-path collective);
+torch.distributed is used only for the barrier and the max-over-ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+from fractalshades_b200.views import VIEWS  # noqa: E402
+
+_DJ = VIEWS["deep_julia_2608"]
+_BS = VIEWS["bs_deep_julia_2430"]
+_STD = dict(M_divergence=1e3, epsilon_stationnary=1e-3)
+
+WORKLOADS = {
+    # BASELINE.json configs[0]
+    "config1": dict(
+        name="Mandelbrot calc_std_div 800x800 max_iter 5000 (x=-1, y=0, dx=5)",
+        kind="std_M2", x=-1.0, y=0.0, dx=5.0, nx=800, xy_ratio=1.0,
+        calc=dict(max_iter=5000, M_divergence=1000., epsilon_stationnary=1e-3)),
+    # BASELINE.json configs[1] -- the bench default
+    "config2": dict(
+        name="Perturbation_mandelbrot dx=1e-250 3840x2160 max_iter 1e6 BLA 1e-6 dzndc",
+        kind="perturb_M2", precision=270, x=_DJ["x"][:290], y=_DJ["y"][:290],
+        dx="1e-250", nx=3840, xy_ratio=16 / 9.,
+        calc=dict(max_iter=1000000, BLA_eps=1e-6, interior_detect=False,
+                  calc_dzndc=True, **_STD)),
+    # BASELINE.json configs[2]
+    "config3": dict(
+        name="Perturbation_mandelbrot dx=1e-1000 (Xrange) 3840x2160 max_iter 1e7 BLA+rebasing",
+        kind="perturb_M2", precision=1020, x=_DJ["x"][:1040], y=_DJ["y"][:1040],
+        dx="1e-1000", nx=3840, xy_ratio=16 / 9.,
+        calc=dict(max_iter=10000000, BLA_eps=1e-6, interior_detect=False,
+                  calc_dzndc=True, **_STD)),
+    # BASELINE.json configs[3]
+    "config4": dict(
+        name="Perturbation_burning_ship dx=1e-500 hessian 3840x2133",
+        kind="perturb_BS", init=dict(flavor="Burning ship"), precision=520,
+        x=_BS["x"][:540], y=_BS["y"][:540], dx="1e-500", nx=3840, xy_ratio=1.8,
+        theta_deg=12.0, skew=_BS["skew"],
+        calc=dict(max_iter=500000, M_divergence=1e3, BLA_eps=1e-6,
+                  calc_hessian=True)),
+}
+
+
+# ---------------------------------------------------------------------------
+def make_fractal(w, nx=None):
+    import fractalshades_b200.models as fsm
+    cls = {"std_M2": fsm.Mandelbrot, "std_BS": fsm.Burning_ship,
+           "perturb_M2": fsm.Perturbation_mandelbrot,
+           "perturb_BS": fsm.Perturbation_burning_ship}[w["kind"]]
+    f = cls(tempfile.mkdtemp(prefix="fsb_bench_"), **w.get("init", {}))
+    zoom = dict(x=w["x"], y=w["y"], dx=w["dx"], nx=nx or w["nx"],
+                xy_ratio=w["xy_ratio"], theta_deg=w.get("theta_deg", 0.),
+                **w.get("skew", {}))
+    if w["kind"].startswith("perturb"):
+        zoom["precision"] = w["precision"]
+    f.zoom(**zoom)
+    return f
+
+
+def frame_c_pix(f, tiles=None):
+    out = []
+    for cs in (tiles if tiles is not None else f.chunk_slices()):
+        out.append(np.ravel(f.chunk_pixel_pos(cs, False, None)))
+    return np.ascontiguousarray(np.concatenate(out))
+
+
+class ClockSampler:
+    """ nvidia-smi clocks / throttle reasons during the timed region """
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-i", str(self.device), "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                inside = (t0 - 0.05 <= ts <= t1 + 0.15)
+                if inside:
+                    sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+                if inside:
+                    for nme, val in zip(names, parts[5:9]):
+                        if val.lower().startswith("active"):
+                            reasons.add(nme)
+            except ValueError:
+                continue
+        if not sm:      # timed region shorter than the sampling period
+            sm = [float(p.split(",")[1]) for _, p in self.lines[-3:] if len(p.split(",")) > 2]
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(smax)) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def flops_per_unit(kind, w):
+    """ Algorithmic FP64 flops (FMA = 2) per executed iteration / BLA step,
+    counted from the reference source. """
+    if kind == "std_M2":
+        return 31., 0.
+    if kind == "perturb_M2":
+        c = w["calc"]
+        it = 17. + (18. if c.get("calc_dzndc") else 0.) + (23. if c.get("interior_detect") else 0.)
+        bla = 14. + (6. if c.get("calc_dzndc") else 0.) + (6. if c.get("interior_detect") else 0.)
+        return it, bla
+    if kind == "perturb_BS":
+        c = w["calc"]
+        it = 23. + (64. if c.get("calc_hessian") else 0.)
+        bla = 14. + (12. if c.get("calc_hessian") else 0.)
+        return it, bla
+    return 40., 0.
+
+
+# ---------------------------------------------------------------------------
+def oracle_frame(w, f, spec):
+    """ tables dict for the CPU oracle (test infrastructure, cpu_baseline only) """
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    import parity_common as pc
+    if w["kind"].startswith("std"):
+        return None
+    t = f.frame_tables()
+    t0 = time.time()
+    pc.oracle_fill_tables(t)
+    return t, time.time() - t0
+
+
+def oracle_run(w, f, t, c_pix, nthreads=0):
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    import oracle_lib as ol
+    import fractalshades_b200.models as fsm
+    if w["kind"] == "std_M2":
+        return ol.std_m2(c_pix, complex(f.x, f.y), float(f.dx), f.lin_mat,
+                         nthreads=nthreads, **w["calc"])[3]
+    if w["kind"] == "std_BS":
+        return ol.std_bs(fsm.get_flavor_int(f.flavor), c_pix, complex(f.x, f.y),
+                         float(f.dx), f.lin_mat, nthreads=nthreads, **w["calc"])[3]
+    return ol.perturb(t, c_pix, nthreads)[3]
+
+
+def bind_spec(f, w):
+    kw = dict(calc_name="bench", subset=None, **w["calc"])
+    ret = type(f).calc_std_div.__wrapped__(f, **kw)
+    for k, v in kw.items():
+        setattr(f, k, v)
+    ret["set_state"]()(f)
+    spec = ret["iterate"]()
+    f._kernel_options = vars(spec).copy()
+    return spec
+
+
+def cpu_sample(w, f, target_s=12.0, nthreads=0):
+    """ Time the oracle port on a bounded 1-in-k sample of the frame's tiles. """
+    spec = bind_spec(f, w)
+    t = None
+    t_tables = 0.
+    if w["kind"].startswith("perturb"):
+        t, t_tables = oracle_frame(w, f, spec)
+    tiles = list(f.chunk_slices())
+    # calibrate on one central tile
+    mid = tiles[len(tiles) // 2]
+    c0 = frame_c_pix(f, [mid])
+    t0 = time.time()
+    si = oracle_run(w, f, t, c0, nthreads)
+    dt = max(time.time() - t0, 1e-4)
+    n_tiles = int(max(1, min(len(tiles), target_s / dt)))
+    step = max(1, len(tiles) // n_tiles)
+    sample = tiles[::step][:n_tiles]
+    c = frame_c_pix(f, sample)
+    t0 = time.time()
+    si = oracle_run(w, f, t, c, nthreads)
+    dt = time.time() - t0
+    return {"iters": int(si.sum(dtype=np.int64)), "seconds": dt,
+            "n_tiles": len(sample), "n_tiles_total": len(tiles),
+            "npts": int(c.shape[0]), "tables_s": t_tables, "c_pix": c, "tables": t}
+
+
+def run_reference_arm(args, w, rank, world):
+    """ --impl reference: the reference's CPU implementation of the path.  The
+    reference is Python/numba and cannot travel to the GPU box, so this arm
+    times the oracle port (oracle/, C++/OpenMP restatement pinned bit-exact
+    against the reference) with all host threads, on a bounded sample. """
+    if rank != 0:
+        return
+    f = make_fractal(w, args.nx)
+    cores = os.cpu_count()
+    s = cpu_sample(w, f, target_s=args.cpu_seconds)
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.time()
+        si = oracle_run(w, f, s["tables"], s["c_pix"], 0)
+        if i >= args.warmup:
+            times.append(time.time() - t0)
+    iters = int(si.sum(dtype=np.int64))
+    ms = 1e3 * float(np.mean(times)) if times else 1e3 * s["seconds"]
+    val = iters / (ms * 1e-3) / 1e9
+    sample = (f"{s['n_tiles']} of {s['n_tiles_total']} tiles (1-in-"
+              f"{max(1, s['n_tiles_total'] // s['n_tiles'])}), {s['npts']} px")
+    line = {
+        "impl": "reference", "metric": "effective pixel-iterations per second",
+        "value": val, "unit": "Gpix-iter/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["name"], "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "Gpix-iter/s", "cores": cores,
+                         "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "Gpix-iter/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "s_per_frame_extrapolated": ms * 1e-3 * s["n_tiles_total"] / s["n_tiles"],
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
+    ap.add_argument("--nx", type=int, default=None, help="debug: override image width")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--strict", action="store_true", help="use the -fmad=false build")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    w = WORKLOADS[args.workload]
+
+    if args.impl == "reference":
+        run_reference_arm(args, w, rank, world)
+        return
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl")
+
+    import fractalshades_b200 as fsb
+    from fractalshades_b200 import _native, settings
+    settings.strict_ieee = bool(args.strict)
+    os.environ.setdefault("FSB200_DEVICE", str(local_rank))
+    lib = _native.cuda_lib()
+
+    # ---- per-frame setup (reference orbit, dZndc path, BLA tree) ----
+    t0 = time.time()
+    f = make_fractal(w, args.nx)
+    f.calc_std_div(calc_name="bench", subset=None, **w["calc"])
+    setup_s = time.time() - t0
+    indep = f._calc_data["bench"]["cycle_indep_args"]
+    perturb = (indep[0] == "perturb")
+    frame = indep[1] if perturb else None
+    setup_ms = frame.setup_ms() if perturb else {}
+
+    state = f._calc_data["bench"]["state"]
+    n_Z, n_U = len(state.codes[0]), len(state.codes[1])
+    zdt = np.dtype(state.complex_type)
+
+    c_host = frame_c_pix(f)
+    npts = int(c_host.shape[0])
+    c_pix = _native.pinned_empty((npts,), np.complex128)
+    c_pix[:] = c_host
+    del c_host
+    Z = _native.pinned_empty((n_Z, npts), zdt)
+    U = _native.pinned_empty((max(n_U, 1), npts), np.int32)
+    sr = _native.pinned_empty((1, npts), np.int8)
+    si = _native.pinned_empty((1, npts), np.int32)
+
+    # ---- device-resident buffers ----
+    def dalloc(nbytes):
+        p = lib.fsb_dev_alloc(int(nbytes))
+        if not p:
+            raise RuntimeError(lib.fsb_last_error().decode())
+        return p
+    d_c = dalloc(npts * 16)
+    d_Z = dalloc(n_Z * npts * zdt.itemsize)
+    d_U = dalloc(max(n_U, 1) * npts * 4)
+    d_sr = dalloc(npts)
+    d_si = dalloc(npts * 4)
+    _native.check(lib, lib.fsb_memcpy_h2d(d_c, _native.ptr(c_pix), npts * 16))
+
+    stats = _native.FsbStats()
+
+    def step_device():
+        if perturb:
+            rc = lib.fsb_frame_run_device(frame.ptr, npts, d_c, d_Z, d_U, d_sr, d_si, stats)
+        else:
+            rc = lib.fsb_std_run_device(indep[1], npts, d_c, d_Z, d_sr, d_si, stats)
+        _native.check(lib, rc)
+        return stats.kernel_ms
+
+    def step_e2e():
+        t0 = time.perf_counter()
+        rc = f.numba_cycle_call((c_pix, Z, U[:n_U], sr, si), indep)
+        assert rc == 0
+        return (time.perf_counter() - t0) * 1e3
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    # ---- warm-up ----
+    for _ in range(max(args.warmup, 1)):
+        step_device()
+    step_e2e()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+
+    # ---- timed: device-resident ----
+    barrier()
+    t_begin = time.time()
+    dev_ms = []
+    for _ in range(args.steps):
+        _native.check(lib, lib.fsb_flush_l2())      # untimed: cold L2 per step
+        dev_ms.append(step_device())
+    barrier()
+    kstats = stats.as_dict()
+    sum_iter = int(kstats["sum_stop_iter"])
+
+    # ---- timed: end to end through the seam, host buffers ----
+    barrier()
+    e2e_ms = []
+    for _ in range(args.steps):
+        e2e_ms.append(step_e2e())
+    barrier()
+    t_end = time.time()
+    clocks = sampler.stop(t_begin, t_end)
+
+    # correctness guard: the e2e outputs must be those of the device run
+    assert int(si.sum(dtype=np.int64)) == sum_iter, "e2e / device mismatch"
+
+    tot_dev = float(np.sum(dev_ms))
+    tot_e2e = float(np.sum(e2e_ms))
+    if dist is not None:
+        import torch
+        tt = torch.tensor([tot_dev, tot_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ss = torch.tensor([float(sum_iter)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(ss, op=dist.ReduceOp.SUM)
+        tot_dev, tot_e2e = float(tt[0]), float(tt[1])
+        sum_all = float(ss[0])
+    else:
+        sum_all = float(sum_iter)
+
+    ms_per_step = tot_dev / args.steps
+    value = sum_all / (ms_per_step * 1e-3) / 1e9
+    e2e_ms_per_step = tot_e2e / args.steps
+    e2e_value = sum_all / (e2e_ms_per_step * 1e-3) / 1e9
+
+    if rank == 0:
+        # ---- roofline of the pixel kernel: FP64 FMA pipe ----
+        f_it, f_bla = flops_per_unit(w["kind"], w)
+        flops = kstats["n_iter_exec"] * f_it + kstats["n_bla_steps"] * f_bla
+        kernel_ms = float(np.mean(dev_ms))
+        peak = float(lib.fsb_fp64_peak_tflops(200000))
+        achieved = flops / (kernel_ms * 1e-3) / 1e12
+        alg_bytes = npts * (16 + n_Z * zdt.itemsize + 4 * n_U + 4 + 1)
+        hbm_peak = 6533.8
+        try:
+            with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as fh:
+                hbm_peak = float(json.load(fh)["hbm_gbs"])
+            peak_src = "MEASURED_PEAKS.json"
+        except Exception:
+            hbm_peak, peak_src = 6650., "fallback"
+        roofline = {
+            "bound": "fp64",
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "frac": achieved / peak if peak > 0 else None,
+            "traffic": None,
+            "peak_source": "measured live: dependent-DFMA chains on all SMs (fsb_fp64_peak_tflops)",
+            "flops_per_iter": f_it, "flops_per_bla_step": f_bla,
+            "n_iter_exec": int(kstats["n_iter_exec"]),
+            "n_bla_steps": int(kstats["n_bla_steps"]),
+            "n_rebase": int(kstats["n_rebase"]),
+            "kernel_ms": kernel_ms,
+            "hbm": {"achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9,
+                    "peak": hbm_peak, "unit": "GB/s",
+                    "frac": alg_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
+                    "algorithmic_bytes": alg_bytes, "peak_source": peak_src},
+        }
+        cpu_baseline = None
+        if world == 1 and not args.no_cpu_baseline:
+            fc = make_fractal(w, args.nx)
+            s = cpu_sample(w, fc, target_s=args.cpu_seconds)
+            cpu_baseline = {
+                "value": s["iters"] / s["seconds"] / 1e9, "unit": "Gpix-iter/s",
+                "cores": os.cpu_count(), "kind": "port",
+                "sample": (f"{s['n_tiles']} of {s['n_tiles_total']} tiles, "
+                           f"{s['npts']} px, {s['seconds']:.2f} s; oracle "
+                           f"C++/OpenMP port (oracle/fs_oracle.cpp)"),
+                "s_per_frame_extrapolated": s["seconds"] * s["n_tiles_total"] / s["n_tiles"],
+                "tables_s": s["tables_s"],
+            }
+        h2d = npts * 16
+        d2h = npts * (n_Z * zdt.itemsize + 4 * n_U + 4 + 1)
+        line = {
+            "metric": "effective pixel-iterations per second",
+            "value": value, "unit": "Gpix-iter/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": w["name"], "npts_per_gpu": npts,
+                       "frames_per_step": world, "tile": 200,
+                       "l2": "flushed between timed steps (192 MiB write); "
+                             "inputs+outputs 473 MB > L2",
+                       "build": lib.fsb_build_info().decode()},
+            "s_per_frame": ms_per_step * 1e-3,
+            "e2e": {"value": e2e_value, "unit": "Gpix-iter/s",
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms_per_step,
+                    "s_per_frame": e2e_ms_per_step * 1e-3},
+            "gpu_launches": int(args.steps * kstats["n_launches"]),
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "clocks": clocks,
+            "setup": {"total_s": setup_s, **{k + "_ms": v for k, v in setup_ms.items()}},
+            "sum_stop_iter_per_frame": sum_iter,
+        }
+        print(json.dumps(line), flush=True)
+
+    for p in (d_c, d_Z, d_U, d_sr, d_si):
+        lib.fsb_dev_free(p)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

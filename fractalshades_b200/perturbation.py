@@ -327,7 +327,9 @@ class PerturbationFractal(Fractal):
         if order is not None:
             ref_orbit_len = min(order, ref_orbit_len)
         FP["ref_orbit_len"] = ref_orbit_len
-        Zn_path = np.empty([ref_orbit_len], dtype=np.complex128)
+        # (the reference uses np.empty: entries past the escape index are never
+        # read; zeros keep the BLA table deterministic there)
+        Zn_path = np.zeros([ref_orbit_len], dtype=np.complex128)
         i, partial_dict, xr_dict = self.FP_loop(Zn_path, ref_point)
         FP["partials"] = partial_dict
         FP["xr"] = xr_dict
