@@ -200,3 +200,25 @@ def frac_same(a, b):
     else:
         ok = (a == b) | (np.isnan(a) & np.isnan(b))
     return float(np.mean(ok)) if ok.size else 1.0
+
+
+def continuous_iter(kind, Zarr, n, M):
+    """ nu = n - log(log|z| / log M) / log 2, the reference's Continuous_iter_pp
+    for d = 2 (postproc.py:352-406,1001-1009), in fp64 """
+    mod = np.hypot(Zarr[0], Zarr[1]) if kind.endswith("BS") else np.abs(Zarr[0])
+    with np.errstate(all="ignore"):
+        return n - np.log(np.log(mod) / np.log(M)) / np.log(2.)
+
+
+def nu_within(kind, M, Za, na, Zb, nb, mask, tol=1e-9):
+    """ fraction of the masked (matching, escaped) pixels whose continuous
+    iteration agrees within `tol` relative; None when there is no such pixel """
+    if mask.sum() == 0:
+        return None
+    a = continuous_iter(kind, Za[:, mask], na[0, mask].astype(float), M)
+    b = continuous_iter(kind, Zb[:, mask], nb[0, mask].astype(float), M)
+    fin = np.isfinite(a) & np.isfinite(b)
+    if fin.sum() == 0:
+        return None
+    rel = np.abs(a[fin] - b[fin]) / np.maximum(np.abs(b[fin]), 1.)
+    return float(np.mean(rel < tol))

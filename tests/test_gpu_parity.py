@@ -1,0 +1,185 @@
+# -*- coding: utf-8 -*-
+"""
+GPU parity tests (pytest -m gpu): the CUDA path, called through the C ABI,
+against the CPU oracle on the same inputs and against the committed reference
+fixtures.
+
+  * libfsb200_strict.so (-fmad=false): stop_reason, stop_iter, U, Z and the
+    device-built tables are BIT-EXACT with the oracle on every case;
+  * libfsb200.so (default, FMA contraction -- the analogue of the reference's
+    fastmath): >= 99.9 % of pixels exact on well-conditioned views, continuous
+    iteration within 1e-9 relative; same floors against the fastmath reference
+    fixtures.
+"""
+import ctypes
+import threading
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import parity_common as pc
+from cases import CASES
+from test_oracle_golden import FAST_FLOOR, NU_FLOOR, ALL, PERTURB
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def oracle_results():
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            cache[name] = pc.run_oracle(name)
+        return cache[name]
+    return get
+
+
+def _tables_ref(t):
+    if t["kind"] == "perturb_M2":
+        return t.get("dZndc"), t.get("dZndc_e")
+    if t.get("dXnda") is None:
+        return None, None
+    d = np.stack([t[k] for k in ("dXnda", "dXndb", "dYnda", "dYndb")])
+    e = (np.stack([t[k + "_e"] for k in ("dXnda", "dXndb", "dYnda", "dYndb")])
+         if t.get("dXnda_e") is not None else None)
+    return d, e
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_strict_build_bit_exact(name, oracle_results):
+    Zo, Uo, sro, sio, ex = oracle_results(name)
+    tables = (ex["tables"], ex["c_pix"]) if name in PERTURB else None
+    if tables is not None:       # same orbit array for both sides
+        t = dict(tables[0])
+        tables = (t, tables[1])
+    Z, U, sr, si, gx = pc.run_gpu_case(name, strict=True, tables=tables)
+    assert np.array_equal(si, sio)
+    assert np.array_equal(sr, sro)
+    assert pc.same_bits(U, Uo)
+    assert pc.same_bits(Z, Zo)
+    if name in PERTURB:
+        t = ex["tables"]
+        if "bla" in gx:
+            M, r, n, stg = gx["bla"]
+            assert (n, stg) == (t["bla_len"], t["stages_bla"])
+            assert pc.same_bits(M, t["M_bla"]) and pc.same_bits(r, t["r_bla"])
+        if "dzndc" in gx:
+            d, de = gx["dzndc"]
+            dref, eref = _tables_ref(t)
+            assert pc.same_bits(d, dref)
+            if eref is not None:
+                assert np.array_equal(de, eref)
+        if "dzndz" in gx:
+            d, de = gx["dzndz"]
+            assert pc.same_bits(d, t["dZndz"])
+        st = gx["stats"]
+        cnt = ex["counters"]
+        assert (st["n_iter_exec"], st["n_bla_steps"], st["n_rebase"]) == tuple(int(c) for c in cnt)
+        assert st["sum_stop_iter"] == int(sio.sum(dtype=np.int64))
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_default_build_tolerance(name, oracle_results):
+    """ default (FMA) build vs the oracle and vs the fastmath reference:
+    >= 99.9 % identical stop_iter / stop_reason on well-conditioned views,
+    continuous iteration within 1e-9 relative """
+    Zo, Uo, sro, sio, ex = oracle_results(name)
+    Z, U, sr, si, gx = pc.run_gpu_case(name, strict=False)
+    floor = FAST_FLOOR[name]
+    same = (si == sio)[0] & (sr == sro)[0]
+    assert same.mean() >= floor, same.mean()
+    g, meta = pc.load_golden(name, "fast")
+    same_ref = (si == g["stop_iter"])[0] & (sr == g["stop_reason"])[0]
+    assert same_ref.mean() >= floor, same_ref.mean()
+    kind = CASES[name]["kind"]
+    M = float(CASES[name]["calc"]["M_divergence"])
+    for ref_Z, ref_n, msk in ((Zo, sio, same), (g["Z"], g["stop_iter"], same_ref)):
+        frac = pc.nu_within(kind, M, Z, si, ref_Z, ref_n, msk & (sr[0] == 1))
+        assert frac is None or frac >= NU_FLOOR[name], frac
+
+
+@pytest.mark.parametrize("name", ["p_M2_E20", "p_M2_ultradeep_xr", "p_BS_f1_E500_xr",
+                                  "p_M2_int_E11"])
+def test_staged_parity_oracle_tables(name, oracle_results):
+    """ stage (i) of SURVEY 8c: kernel fed with the ORACLE's dZndc / BLA tables """
+    Zo, Uo, sro, sio, ex = oracle_results(name)
+    Z, U, sr, si, gx = pc.run_gpu_case(name, strict=True, use_oracle_tables=True,
+                                       tables=(dict(ex["tables"]), ex["c_pix"]))
+    assert np.array_equal(si, sio) and np.array_equal(sr, sro)
+    assert pc.same_bits(Z, Zo) and pc.same_bits(U, Uo)
+
+
+def test_xrange_device_ops_match_oracle():
+    """ Xrange add / sub / mul and to_standard on the device == oracle, bit for
+    bit (mirror of the reference's tests/test_numba_xr.py on the GPU) """
+    from fractalshades_b200 import _native
+    rg = np.random.default_rng(1234)
+    n = 5000
+    def rnd():
+        m = ((rg.random(n) * 2 - 1) * np.exp2(rg.integers(-120, 120, n).astype(float))
+             + 1j * (rg.random(n) * 2 - 1) * np.exp2(rg.integers(-120, 120, n).astype(float)))
+        m[rg.random(n) < 0.02] = 0
+        m.imag[rg.random(n) < 0.05] = 0
+        e = rg.integers(-3000, 3000, n).astype(np.int32)
+        return np.ascontiguousarray(m), e
+    a, ae = rnd()
+    b, be = rnd()
+    be2 = (ae + rg.integers(-70, 70, n)).astype(np.int32)
+    for strict in (True, False):
+        lib = _native.cuda_lib(strict)
+        for op in (0, 1, 2):
+            for bb in (be, be2):
+                out = np.zeros(n, np.complex128)
+                oe = np.zeros(n, np.int32)
+                _native.check(lib, lib.fsb_xr_binop_c(op, n, _native.ptr(a), _native.ptr(ae),
+                                                      _native.ptr(b), _native.ptr(bb),
+                                                      _native.ptr(out), _native.ptr(oe)))
+                ro, re_ = ol.xr_binop_c(op, a, ae, b, bb)
+                if strict or op < 2:
+                    assert pc.same_bits(out, ro) and np.array_equal(oe, re_)
+                else:       # default build may contract the complex product
+                    assert np.array_equal(oe, re_)
+                    assert np.allclose(out, ro, rtol=1e-13, atol=0)
+        ae3 = (ae // 3).astype(np.int32)
+        out = np.zeros(n, np.complex128)
+        _native.check(lib, lib.fsb_xr_to_standard_c(n, _native.ptr(a), _native.ptr(ae3),
+                                                    _native.ptr(out)))
+        assert pc.same_bits(out, ol.xr_to_standard_c(a, ae3))
+
+
+def test_hypot_device_matches_oracle():
+    from fractalshades_b200 import _native
+    rg = np.random.default_rng(7)
+    n = 20000
+    x = rg.standard_normal(n) * np.exp2(rg.integers(-1070, 1020, n).astype(float))
+    y = rg.standard_normal(n) * np.exp2(rg.integers(-1070, 1020, n).astype(float))
+    x[:10] = 0
+    y[5:15] = 0
+    ref = np.array([ol.lib().fso_hypot(float(p), float(q)) for p, q in zip(x, y)])
+    for strict in (True, False):
+        lib = _native.cuda_lib(strict)
+        out = np.zeros(n)
+        _native.check(lib, lib.fsb_hypot_test(n, _native.ptr(x), _native.ptr(y), _native.ptr(out)))
+        assert pc.same_bits(out, ref)
+
+
+def test_empty_and_ragged_inputs():
+    """ empty point list, a single point, and a point count that is not a
+    multiple of the warp size """
+    from fractalshades_b200.perturbation import create_frame
+    f, case, t = pc.host_tables("p_M2_E20")
+    c_pix = pc.all_c_pix(f)
+    Zo, Uo, sro, sio, cnt = ol.perturb(pc.oracle_fill_tables(dict(t)), c_pix)
+    frame = create_frame(t, strict=True)
+    try:
+        for n in (0, 1, 33, 1000):
+            Z = np.zeros((frame.nz, n), np.complex128)
+            U = np.zeros((1, n), np.int32)
+            sr = -np.ones((1, n), np.int8)
+            si = np.zeros((1, n), np.int32)
+            assert frame.run(np.ascontiguousarray(c_pix[:n]), Z, U, sr, si) == 0
+            assert np.array_equal(si, sio[:, :n]) and pc.same_bits(Z, Zo[:, :n])
+    finally:
+        frame.close()

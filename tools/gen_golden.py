@@ -77,7 +77,11 @@ def run_one(name, mode):
                 for k, v in t.items()
                 if isinstance(v, (int, float, complex, bool, str, type(None)))}
         meta["scalars"] = scal
-        out["Zn_sha"] = sha(t["Zn_path"])
+        # entries past the escape index of the reference point are
+        # uninitialised memory in the reference (np.empty): hash the valid part
+        n_valid = min(len(t["Zn_path"]), t["ref_div_iter"] + 1)
+        out["Zn_sha"] = sha(t["Zn_path"][:n_valid])
+        out["Zn_valid"] = n_valid
         out["L"] = len(t["Zn_path"])
         if t.get("ref_index_xr") is not None:
             for k in ("ref_index_xr", "ref_xr", "ref_xr_e", "refx_xr",
