@@ -151,21 +151,25 @@ typedef void (*perturb_kernel_t)(FrameDev, long long, const C *, double *, int *
                                  signed char *, int *, unsigned long long *,
                                  unsigned long long *, const volatile int *);
 
-template <bool XR, bool DC, bool DZ> perturb_kernel_t pick_m2_bla(bool bla)
+template <bool XR, bool DC, bool DZ, bool BLA> perturb_kernel_t pick_m2_extra(bool extra)
 {
-    return bla ? k_perturb_m2<XR, DC, DZ, true> : k_perturb_m2<XR, DC, DZ, false>;
+    return extra ? k_perturb_m2<XR, DC, DZ, BLA, true> : k_perturb_m2<XR, DC, DZ, BLA, false>;
 }
-template <bool XR, bool DC> perturb_kernel_t pick_m2_dz(bool dz, bool bla)
+template <bool XR, bool DC, bool DZ> perturb_kernel_t pick_m2_bla(bool bla, bool extra)
 {
-    return dz ? pick_m2_bla<XR, DC, true>(bla) : pick_m2_bla<XR, DC, false>(bla);
+    return bla ? pick_m2_extra<XR, DC, DZ, true>(extra) : pick_m2_extra<XR, DC, DZ, false>(extra);
 }
-template <bool XR> perturb_kernel_t pick_m2_dc(bool dc, bool dz, bool bla)
+template <bool XR, bool DC> perturb_kernel_t pick_m2_dz(bool dz, bool bla, bool extra)
 {
-    return dc ? pick_m2_dz<XR, true>(dz, bla) : pick_m2_dz<XR, false>(dz, bla);
+    return dz ? pick_m2_bla<XR, DC, true>(bla, extra) : pick_m2_bla<XR, DC, false>(bla, extra);
 }
-perturb_kernel_t pick_m2(bool xr, bool dc, bool dz, bool bla)
+template <bool XR> perturb_kernel_t pick_m2_dc(bool dc, bool dz, bool bla, bool extra)
 {
-    return xr ? pick_m2_dc<true>(dc, dz, bla) : pick_m2_dc<false>(dc, dz, bla);
+    return dc ? pick_m2_dz<XR, true>(dz, bla, extra) : pick_m2_dz<XR, false>(dz, bla, extra);
+}
+perturb_kernel_t pick_m2(bool xr, bool dc, bool dz, bool bla, bool extra)
+{
+    return xr ? pick_m2_dc<true>(dc, dz, bla, extra) : pick_m2_dc<false>(dc, dz, bla, extra);
 }
 template <bool XR, bool H> perturb_kernel_t pick_bs_bla(bool bla)
 {
@@ -666,6 +670,11 @@ int fsb_frame_create(const fsb_frame_desc *desc, fsb_frame **out)
         return fail(-3, "interior detection is not defined for the burning-ship family");
     if (desc->n_xr > 0 && (!desc->ref_index_xr || !desc->ref_xr || !desc->ref_xr_e))
         return fail(-3, "Xrange reference arrays missing");
+    /* orbit indices and iteration counts are 32-bit in the kernels (stop_iter,
+     * U and ref_index_xr are int32 in the reference too) */
+    if (desc->L >= (1LL << 30) || desc->max_iter >= (1LL << 30) || desc->max_iter < 1)
+        return fail(-3, "orbit length / max_iter out of the supported range (< 2^30)");
+    if (desc->ref_order < 1) return fail(-3, "ref_order must be >= 1");
 
     fsb_frame *f = new fsb_frame();
     f->d = *desc;
@@ -701,6 +710,18 @@ int fsb_frame_create(const fsb_frame_desc *desc, fsb_frame **out)
     v.calc_orbit = d.calc_orbit;
     v.backshift = d.backshift;
     v.flavor = d.flavor;
+    {
+        const long long big = (1LL << 30);
+        v.Li = (int)L;
+        v.ref_div_i = (int)(d.ref_div_iter < big ? d.ref_div_iter : big);
+        v.order_i = (d.ref_order < big) ? (int)d.ref_order : 0;
+        long long fi = L;
+        if (d.ref_div_iter < fi) fi = d.ref_div_iter;
+        if (d.ref_order < fi) fi = d.ref_order;
+        v.first_invalid_i = (int)fi;
+        v.max_iter_i = (int)d.max_iter;
+        v.n_xr_i = (int)d.n_xr;
+    }
     f->nz = frame_nz(d);
     f->ms_upload = now_ms() - t0;
 
@@ -827,7 +848,8 @@ static int frame_launch(Ctx *c, fsb_frame *f, long long npts, const C *d_c_pix, 
 {
     const fsb_frame_desc &d = f->d;
     perturb_kernel_t k = (d.model == FSB_MODEL_M2)
-        ? pick_m2(d.xr_detect != 0, d.calc_dzndc != 0, d.calc_dzndz != 0, f->bla_on)
+        ? pick_m2(d.xr_detect != 0, d.calc_dzndc != 0, d.calc_dzndz != 0, f->bla_on,
+                  f->dev.order_i > 0 || d.calc_orbit != 0)
         : pick_bs(d.xr_detect != 0, d.calc_dzndc != 0, f->bla_on);
     CK(cudaMemsetAsync(c->d_ctl, 0, 8 * sizeof(unsigned long long), c->stream));
     const int block = 128;

@@ -47,6 +47,8 @@ struct FrameDev {
     double Mdiv_sq, eps_sq;
     int calc_orbit; long long backshift;
     int flavor;
+    /* 32-bit mirrors used by the pixel kernels (every orbit index fits) */
+    int Li, ref_div_i, order_i /* 0: not a cycle */, first_invalid_i, max_iter_i, n_xr_i;
 };
 
 struct StdDev {
@@ -109,9 +111,9 @@ __device__ __forceinline__ void stC(double *Z, long long row, long long npts, lo
 __device__ __forceinline__ C c_from_pix(C pix, const double *lm, double dx, C center)
 {
     /* core.py:3161-3194 */
-    double x1 = lm[0] * pix.re + lm[1] * pix.im;
-    double y1 = lm[2] * pix.re + lm[3] * pix.im;
-    return center + (dx * mkC(x1, y1));
+    double x1 = add_rn(mul_rn(lm[0], pix.re), mul_rn(lm[1], pix.im));
+    double y1 = add_rn(mul_rn(lm[2], pix.re), mul_rn(lm[3], pix.im));
+    return mkC(add_rn(center.re, mul_rn(dx, x1)), add_rn(center.im, mul_rn(dx, y1)));
 }
 
 __global__ void __launch_bounds__(256)
@@ -136,14 +138,17 @@ k_std_m2(StdDev p, long long npts, const C *__restrict__ c_pix,
             int ret = 0;
             if (n_iter >= p.max_iter) { reason = 0; ret = 1; }
             else {
-                if (p.calc_d2) d2 = 2. * (d2 * zn + dzndc * dzndc);
-                dzndc = (2. * dzndc) * zn + 1.;
-                dzndz = (2. * dzndz) * zn;
-                zn = zn * zn + c;
+                /* The reference's standard loop is IEEE-strict (no fastmath,
+                 * core.py:2935,2969): individually rounded operations in BOTH
+                 * builds, so that the default build is bit-exact too. */
+                if (p.calc_d2) d2 = scale2_rn(cadd_rn(cmul_rn(d2, zn), cmul_rn(dzndc, dzndc)));
+                dzndc = cadd_rn(cmul_rn(scale2_rn(dzndc), zn), mkC(1., 0.));
+                dzndz = cmul_rn(scale2_rn(dzndz), zn);
+                zn = cadd_rn(cmul_rn(zn, zn), c);
                 if (n_iter == 1) dzndz = mkC(1., 0.);
                 n_exec++;
-                if (norm2(zn) > p.Mdiv_sq) { reason = 1; ret = 1; }
-                else if (norm2(dzndz) < p.eps_sq) { reason = 2; ret = 1; }
+                if (norm2_rn(zn) > p.Mdiv_sq) { reason = 1; ret = 1; }
+                else if (norm2_rn(dzndz) < p.eps_sq) { reason = 2; ret = 1; }
             }
             if (p.calc_orbit) {
                 long long div = n_iter / p.backshift;
@@ -162,7 +167,7 @@ k_std_m2(StdDev p, long long npts, const C *__restrict__ c_pix,
         if (p.calc_d2) stC(Z, row++, npts, i, d2);
         if (p.calc_orbit) {
             C zo = orbit_zn2;
-            while (orbit_i2 < n_iter - p.backshift) { zo = zo * zo + c; orbit_i2 += 1; }
+            while (orbit_i2 < n_iter - p.backshift) { zo = cadd_rn(cmul_rn(zo, zo), c); orbit_i2 += 1; }
             stC(Z, row++, npts, i, zo);
         }
         stop_reason[i] = (signed char)reason;
@@ -172,16 +177,21 @@ k_std_m2(StdDev p, long long npts, const C *__restrict__ c_pix,
     add_counters(counters, n_exec, 0, 0, n_sum);
 }
 
+/* strict (individually rounded) helpers for the standard burning-ship loop */
+#define M_(a, b) mul_rn((a), (b))
+#define A_(a, b) add_rn((a), (b))
+#define S_(a, b) add_rn((a), -(b))
+
 __device__ __forceinline__ void bs_iterate(int flavor, double xn, double yn, double a,
                                            double b, double &ox, double &oy)
 {
     /* burning_ship.py:82-122 */
     switch (flavor) {
-    case 1: ox = xn * xn - yn * yn + a; oy = 2. * fabs(xn * yn) - b; break;
-    case 2: ox = xn * xn - yn * yn + a; oy = 2. * xn * fabs(yn) - b; break;
-    case 3: ox = xn * xn - yn * fabs(yn) + a; oy = 2. * xn * yn - b; break;
-    case 4: ox = fabs(xn * xn - yn * yn) + a; oy = 2. * xn * yn - b; break;
-    default: ox = fabs(xn * xn - yn * yn) + a; oy = 2. * fabs(xn * yn) - b; break;
+    case 1: ox = A_(S_(M_(xn, xn), M_(yn, yn)), a); oy = S_(M_(2., fabs(M_(xn, yn))), b); break;
+    case 2: ox = A_(S_(M_(xn, xn), M_(yn, yn)), a); oy = S_(M_(M_(2., xn), fabs(yn)), b); break;
+    case 3: ox = A_(S_(M_(xn, xn), M_(yn, fabs(yn))), a); oy = S_(M_(M_(2., xn), yn), b); break;
+    case 4: ox = A_(fabs(S_(M_(xn, xn), M_(yn, yn))), a); oy = S_(M_(M_(2., xn), yn), b); break;
+    default: ox = A_(fabs(S_(M_(xn, xn), M_(yn, yn))), a); oy = S_(M_(2., fabs(M_(xn, yn))), b); break;
     }
 }
 
@@ -210,55 +220,57 @@ k_std_bs(StdDev p, long long npts, const C *__restrict__ c_pix,
             if (n_iter >= p.max_iter) { reason = 0; ret = 1; }
             else {
                 double nx, ny, ndxa, ndxb, ndya, ndyb;
+                /* IEEE-strict in both builds, like the reference's standard loop
+                 * (burning_ship.py:366-416, literal operation order) */
                 switch (flavor) {
                 case 1:
-                    nx = X * X - Y * Y + a;
-                    ny = 2. * fabs(X * Y) - b;
-                    ndxa = 2. * (X * dXdA - Y * dYdA) + 1.;
-                    ndxb = 2. * (X * dXdB - Y * dYdB);
-                    ndya = 2. * (fabs(X) * sgn(Y) * dYdA + sgn(X) * dXdA * fabs(Y));
-                    ndyb = 2. * (fabs(X) * sgn(Y) * dYdB + sgn(X) * dXdB * fabs(Y)) - 1.;
+                    nx = A_(S_(M_(X, X), M_(Y, Y)), a);
+                    ny = S_(M_(2., fabs(M_(X, Y))), b);
+                    ndxa = A_(M_(2., S_(M_(X, dXdA), M_(Y, dYdA))), 1.);
+                    ndxb = M_(2., S_(M_(X, dXdB), M_(Y, dYdB)));
+                    ndya = M_(2., A_(M_(M_(fabs(X), sgn(Y)), dYdA), M_(M_(sgn(X), dXdA), fabs(Y))));
+                    ndyb = S_(M_(2., A_(M_(M_(fabs(X), sgn(Y)), dYdB), M_(M_(sgn(X), dXdB), fabs(Y)))), 1.);
                     break;
                 case 2:
-                    nx = X * X - Y * Y + a;
-                    ny = 2. * X * fabs(Y) - b;
-                    ndxa = 2. * (X * dXdA - Y * dYdA) + 1.;
-                    ndxb = 2. * (X * dXdB - Y * dYdB);
-                    ndya = 2. * (X * sgn(Y) * dYdA + dXdA * fabs(Y));
-                    ndyb = 2. * (X * sgn(Y) * dYdB + dXdB * fabs(Y)) - 1.;
+                    nx = A_(S_(M_(X, X), M_(Y, Y)), a);
+                    ny = S_(M_(M_(2., X), fabs(Y)), b);
+                    ndxa = A_(M_(2., S_(M_(X, dXdA), M_(Y, dYdA))), 1.);
+                    ndxb = M_(2., S_(M_(X, dXdB), M_(Y, dYdB)));
+                    ndya = M_(2., A_(M_(M_(X, sgn(Y)), dYdA), M_(dXdA, fabs(Y))));
+                    ndyb = S_(M_(2., A_(M_(M_(X, sgn(Y)), dYdB), M_(dXdB, fabs(Y)))), 1.);
                     break;
                 case 3:
-                    nx = X * X - Y * fabs(Y) + a;
-                    ny = 2. * X * Y - b;
-                    ndxa = 2. * (X * dXdA - fabs(Y) * dYdA) + 1.;
-                    ndxb = 2. * (X * dXdB - fabs(Y) * dYdB);
-                    ndya = 2. * (dXdA * Y + X * dYdA);
-                    ndyb = 2. * (dXdB * Y + X * dYdB) - 1.;
+                    nx = A_(S_(M_(X, X), M_(Y, fabs(Y))), a);
+                    ny = S_(M_(M_(2., X), Y), b);
+                    ndxa = A_(M_(2., S_(M_(X, dXdA), M_(fabs(Y), dYdA))), 1.);
+                    ndxb = M_(2., S_(M_(X, dXdB), M_(fabs(Y), dYdB)));
+                    ndya = M_(2., A_(M_(dXdA, Y), M_(X, dYdA)));
+                    ndyb = S_(M_(2., A_(M_(dXdB, Y), M_(X, dYdB))), 1.);
                     break;
                 case 4: {
-                    double x2my2 = X * X - Y * Y;
-                    nx = fabs(x2my2) + a;
-                    ny = 2. * X * Y - b;
-                    ndxa = 2. * sgn(x2my2) * (X * dXdA - Y * dYdA);
-                    ndxb = 2. * sgn(x2my2) * (X * dXdB - Y * dYdB);
-                    ndya = 2. * (dXdA * Y + X * dYdA);
-                    ndyb = 2. * (dXdB * Y + X * dYdB) - 1.;
+                    double x2my2 = S_(M_(X, X), M_(Y, Y));
+                    nx = A_(fabs(x2my2), a);
+                    ny = S_(M_(M_(2., X), Y), b);
+                    ndxa = M_(M_(2., sgn(x2my2)), S_(M_(X, dXdA), M_(Y, dYdA)));
+                    ndxb = M_(M_(2., sgn(x2my2)), S_(M_(X, dXdB), M_(Y, dYdB)));
+                    ndya = M_(2., A_(M_(dXdA, Y), M_(X, dYdA)));
+                    ndyb = S_(M_(2., A_(M_(dXdB, Y), M_(X, dYdB))), 1.);
                     break;
                 }
                 default: {
-                    double x2my2 = X * X - Y * Y;
-                    nx = fabs(x2my2) + a;
-                    ny = 2. * fabs(X * Y) - b;
-                    ndxa = 2. * sgn(x2my2) * (X * dXdA - Y * dYdA);
-                    ndxb = 2. * sgn(x2my2) * (X * dXdB - Y * dYdB);
-                    ndya = 2. * (fabs(X) * sgn(Y) * dYdA + sgn(X) * dXdA * fabs(Y));
-                    ndyb = 2. * (fabs(X) * sgn(Y) * dYdB + sgn(X) * dXdB * fabs(Y)) - 1.;
+                    double x2my2 = S_(M_(X, X), M_(Y, Y));
+                    nx = A_(fabs(x2my2), a);
+                    ny = S_(M_(2., fabs(M_(X, Y))), b);
+                    ndxa = M_(M_(2., sgn(x2my2)), S_(M_(X, dXdA), M_(Y, dYdA)));
+                    ndxb = M_(M_(2., sgn(x2my2)), S_(M_(X, dXdB), M_(Y, dYdB)));
+                    ndya = M_(2., A_(M_(M_(fabs(X), sgn(Y)), dYdA), M_(M_(sgn(X), dXdA), fabs(Y))));
+                    ndyb = S_(M_(2., A_(M_(M_(fabs(X), sgn(Y)), dYdB), M_(M_(sgn(X), dXdB), fabs(Y)))), 1.);
                     break;
                 }
                 }
                 X = nx; Y = ny; dXdA = ndxa; dXdB = ndxb; dYdA = ndya; dYdB = ndyb;
                 n_exec++;
-                if (X * X + Y * Y > p.Mdiv_sq) { reason = 1; ret = 1; }
+                if (A_(M_(X, X), M_(Y, Y)) > p.Mdiv_sq) { reason = 1; ret = 1; }
             }
             if (p.calc_orbit) {
                 long long div = n_iter / p.backshift;
@@ -294,45 +306,48 @@ k_std_bs(StdDev p, long long npts, const C *__restrict__ c_pix,
 
 /* Position of idx in the sorted ref_index_xr or -1: stateless equivalent of
  * the cursor of perturbation.py:2519-2588. */
-__device__ __forceinline__ long long xr_find(const int *index, long long n, long long idx)
+__device__ __forceinline__ int xr_find(const int *index, int n, int idx)
 {
-    long long lo = 0, hi = n;
+    int lo = 0, hi = n;
     while (lo < hi) {
-        long long mid = (lo + hi) >> 1;
+        int mid = (lo + hi) >> 1;
         if (__ldg(index + mid) < idx) lo = mid + 1; else hi = mid;
     }
     if (lo < n && __ldg(index + lo) == idx) return lo;
     return -1;
 }
 
-__device__ __forceinline__ long long bla_index(long long i, int stg)
+__device__ __forceinline__ int bla_index(int i, int stg)
+{
+    return 2 * i + ((1 << stg) - 1);
+}
+__device__ __forceinline__ long long bla_index64(long long i, int stg)
 {
     return 2 * i + ((1LL << stg) - 1);
 }
 
 /* perturbation.py:2116-2170.  Returns the step (0 = no BLA applicable) and
- * the node index. */
-__device__ __forceinline__ long long ref_bla_get(const double *__restrict__ r_bla,
-                                                 int stages_bla, C zn,
-                                                 long long n_iter,
-                                                 long long first_invalid,
-                                                 long long &index_out)
+ * the node index.  All orbit indices fit 32 bits (the host checks it). */
+__device__ __forceinline__ int ref_bla_get(const double *__restrict__ r_bla,
+                                           int stages_bla, C zn, int n_iter,
+                                           int first_invalid, int &index_out)
 {
-    if (stages_bla <= 3) return 0;
-    long long it = n_iter >> 3;
+    const int it = n_iter >> 3;
     int stages = stages_bla - 1;
     if (it != 0) {
-        int s = 3 + (__ffsll(it) - 1);
+        int s = 3 + (__ffs(it) - 1);
         if (s < stages) stages = s;
     }
-    long long invalid_step = first_invalid - n_iter;
-    double az = cabs_rn(zn);
+    const int invalid_step = first_invalid - n_iter;
+    /* skip the levels whose step cannot fit before the first invalid index */
+    if (invalid_step <= 8) return 0;
+    const int top = 31 - __clz(invalid_step - 1);   /* largest stg with 2^stg < invalid_step */
+    if (stages > top) stages = top;
+    const double az = cabs_rn(zn);
+    const int base = 2 * it - 1;
     for (int stg = stages; stg > 2; stg--) {
-        long long step = 1LL << stg;
-        if (step >= invalid_step) continue;
-        long long ib = bla_index(n_iter >> 3, stg - 3);
-        double r = __ldg(r_bla + ib);
-        if (az < r) { index_out = ib; return step; }
+        const int ib = base + (1 << (stg - 3));
+        if (az < __ldg(r_bla + ib)) { index_out = ib; return 1 << stg; }
     }
     return 0;
 }
@@ -351,24 +366,32 @@ __device__ __forceinline__ T p_iter_deriv(T z, T dz, R ref_zn, D ref_d)
     return 2. * ((ref_zn + z) * dz + ref_d * z); /* mandelbrot_M2.py:611-622 */
 }
 
-template <bool XR, bool DZNDC, bool DZNDZ, bool BLA>
+/* Template switches: XR = Xrange arithmetic (dx < 1e-300); DZNDC / DZNDZ =
+ * derivative fields; BLA = bilinear-approximation skipping; EXTRA = the rarely
+ * used runtime options (periodic reference `ref_order`, calc_orbit) -- compiled
+ * out of the common variants. */
+template <bool XR, bool DZNDC, bool DZNDZ, bool BLA, bool EXTRA>
 __global__ void __launch_bounds__(128)
-k_perturb_m2(FrameDev f, long long npts, const C *__restrict__ c_pix,
-             double *__restrict__ Z, int *__restrict__ U,
-             signed char *__restrict__ stop_reason, int *__restrict__ stop_iter,
-             unsigned long long *work, unsigned long long *counters,
-             const volatile int *abort_flag)
+k_perturb_m2(const __grid_constant__ FrameDev f, long long npts_ll,
+             const C *__restrict__ c_pix, double *__restrict__ Z,
+             int *__restrict__ U, signed char *__restrict__ stop_reason,
+             int *__restrict__ stop_iter, unsigned long long *work,
+             unsigned long long *counters, const volatile int *abort_flag)
 {
     unsigned long long n_exec = 0, n_bla = 0, n_reb = 0, n_sum = 0;
-    const long long L = f.L;
-    const bool has_xr = f.n_xr > 0;
-    const long long ref_order = f.ref_order, ref_div_iter = f.ref_div_iter;
-    const long long max_iter = f.max_iter;
-    long long first_invalid = L;
-    if (ref_div_iter < first_invalid) first_invalid = ref_div_iter;
-    if (ref_order < first_invalid) first_invalid = ref_order;
-    const long long w_wraped = L;
+    const int L = f.Li;
+    const bool has_xr = f.n_xr_i > 0;
+    const int ref_div_iter = f.ref_div_i;
+    const int max_iter = f.max_iter_i;
+    const int first_invalid = f.first_invalid_i;
+    const bool cyc = EXTRA && (f.order_i > 0);
+    const int order = f.order_i;
+    const bool orbit = EXTRA && (f.calc_orbit != 0);
+    const int w_wraped = L;
     const XC record_zero = mkXC(mkC(0., 0.), 0);
+    const C Zn0 = ldC(f.Zn, 0);
+    const C *__restrict__ Zn = f.Zn;
+    const int npts = (int)npts_ll;
 
 #define DZNDC_X(i) mkXC(ldC(f.dZndc, (i)), __ldg(f.dZndc_e + (i)))
 #define DZNDZ_X(i) mkXC(ldC(f.dZndz, (i)), __ldg(f.dZndz_e + (i)))
@@ -376,8 +399,8 @@ k_perturb_m2(FrameDev f, long long npts, const C *__restrict__ c_pix,
 
     for (;;) {
         long long base = grab32(work, abort_flag);
-        if (base < 0 || base >= npts) break;
-        long long ipt = base + (threadIdx.x & 31);
+        if (base < 0 || base >= npts_ll) break;
+        const int ipt = (int)base + (threadIdx.x & 31);
         if (ipt >= npts) continue;
 
         /* perturbation.py:1026-1031, 2214-2230 */
@@ -394,9 +417,11 @@ k_perturb_m2(FrameDev f, long long npts, const C *__restrict__ c_pix,
         C zn = mkC(0., 0.), dzndc = zn, dzndz = zn;
         XC zn_x = to_xr(zn), dzndc_x = zn_x, dzndz_x = zn_x;
 
-        long long w_iter = 0, n_iter = 0;
-        long long div_shift = 0, orbit_i1 = 0, orbit_i2 = 0;
+        int w_iter = 0, n_iter = 0;
+        unsigned int p_exec = 0, p_bla = 0, p_reb = 0;
+        int div_shift = 0, orbit_i1 = 0, orbit_i2 = 0;
         C orbit_zn1 = zn, orbit_zn2 = zn;
+        C ref_cur = Zn0;                      /* always Zn[w_iter] */
         bool nullify_dZndz = false;
         bool bool_dyn_rebase = true;
         int stop = -1;
@@ -404,14 +429,16 @@ k_perturb_m2(FrameDev f, long long npts, const C *__restrict__ c_pix,
         for (;;) {
             /* ---- BLA step, perturbation.py:1121-1154 ---- */
             if (BLA && (w_iter & 7) == 0) {
-                long long ib = 0;
-                long long step = ref_bla_get(f.r_bla, f.stages_bla, zn, w_iter,
+                int ib = 0;
+                const int step = ref_bla_get(f.r_bla, f.stages_bla, zn, w_iter,
                                              first_invalid, ib);
                 if (step != 0) {
                     const C *M = reinterpret_cast<const C *>(f.M_bla);
-                    C A = ldC(M, 2 * ib), B = ldC(M, 2 * ib + 1);
+                    const C A = ldC(M, 2 * ib), B = ldC(M, 2 * ib + 1);
                     n_iter += step;
-                    w_iter = (w_iter + step) % ref_order;
+                    w_iter += step;
+                    if (cyc) w_iter = w_iter % order;
+                    ref_cur = ldC(Zn, w_iter);
                     if (XR) {
                         zn_x = A * zn_x + B * c_xr;
                         zn = to_std(zn_x);
@@ -422,20 +449,20 @@ k_perturb_m2(FrameDev f, long long npts, const C *__restrict__ c_pix,
                         if (DZNDC) dzndc = A * dzndc;
                         if (DZNDZ) dzndz = A * dzndz;
                     }
-                    n_bla++;
+                    p_bla++;
                     continue;
                 }
             }
 
             /* ---- full perturbation iteration, :1158-1209 ---- */
             n_iter += 1;
-            n_exec++;
-            C ref_zn = ldC(f.Zn, w_iter);
+            p_exec++;
+            const C ref_zn = ref_cur;
             XC ref_zn_x = record_zero;
             if (XR) {
-                long long k = -1;
+                int k = -1;
                 if (has_xr && w_iter != 0 && fabs(ref_zn.re) < 1.e-300 && fabs(ref_zn.im) < 1.e-300)
-                    k = xr_find(f.ref_index_xr, f.n_xr, w_iter);
+                    k = xr_find(f.ref_index_xr, f.n_xr_i, w_iter);
                 ref_zn_x = (k >= 0) ? REF_X(k) : to_xr(ref_zn);
             }
             if (DZNDC) {
@@ -448,7 +475,7 @@ k_perturb_m2(FrameDev f, long long npts, const C *__restrict__ c_pix,
                 }
             }
             if (DZNDZ) {
-                long long i = nullify_dZndz ? 0 : w_iter;
+                const int i = nullify_dZndz ? 0 : w_iter;
                 if (XR) dzndz_x = p_iter_deriv(zn_x, dzndz_x, ref_zn_x, DZNDZ_X(i));
                 else dzndz = p_iter_deriv(zn, dzndz, ref_zn, ldC(f.dZndz, i));
             }
@@ -460,15 +487,15 @@ k_perturb_m2(FrameDev f, long long npts, const C *__restrict__ c_pix,
             }
 
             w_iter += 1;
-            if (w_iter >= ref_order) w_iter = w_iter % ref_order;
+            if (cyc && w_iter >= order) w_iter = w_iter % order;
 
             if (n_iter >= max_iter) { stop = 0; break; } /* :1218 */
 
             if (DZNDZ) { /* :1224-1246 */
-                long long i = 0;
+                int i = 0;
                 if (!nullify_dZndz) {
                     i = w_iter;
-                    if (n_iter == ref_order) i = w_wraped;
+                    if (cyc && n_iter == order) i = w_wraped;
                 }
                 bool stationnary;
                 if (XR) stationnary = xr_lt(abs2(dzndz_x + DZNDZ_X(i)), f.eps_sq);
@@ -477,15 +504,16 @@ k_perturb_m2(FrameDev f, long long npts, const C *__restrict__ c_pix,
             }
 
             /* ---- divergence, :1252-1279 ---- */
-            C ref_zn_next = ldC(f.Zn, w_iter);
-            long long knext = -1;
+            const C ref_zn_next = ldC(Zn, w_iter);
+            ref_cur = ref_zn_next;
+            int knext = -1;
             if (XR && has_xr && w_iter != 0 && fabs(ref_zn_next.re) < 1.e-300
                 && fabs(ref_zn_next.im) < 1.e-300)
-                knext = xr_find(f.ref_index_xr, f.n_xr, w_iter);
-            C ZZ = zn + ref_zn_next;
-            double full_sq_norm = norm2(ZZ);
-            if (f.calc_orbit) {
-                long long div = n_iter / f.backshift;
+                knext = xr_find(f.ref_index_xr, f.n_xr_i, w_iter);
+            const C ZZ = zn + ref_zn_next;
+            const double full_sq_norm = norm2(ZZ);
+            if (orbit) {
+                int div = n_iter / (int)f.backshift;
                 if (div > div_shift) {
                     div_shift = div;
                     orbit_i2 = orbit_i1; orbit_zn2 = orbit_zn1;
@@ -494,93 +522,67 @@ k_perturb_m2(FrameDev f, long long npts, const C *__restrict__ c_pix,
             }
             if (full_sq_norm > f.Mdiv_sq) { stop = 1; break; }
 
-            /* ---- rebase: reference diverging, :1283-1313 ---- */
-            if (w_iter >= ref_div_iter - 1) {
-                zn = ZZ;
-                if (XR) {
-                    zn_x = to_xr(ZZ);
-                    if (DZNDC) dzndc_x = dzndc_x + DZNDC_X(w_iter);
-                    if (DZNDZ) {
-                        if (!nullify_dZndz) {
-                            long long i = (n_iter == ref_order) ? w_wraped : w_iter;
-                            dzndz_x = dzndz_x + DZNDZ_X(i);
-                        }
-                        nullify_dZndz = true;
-                    }
-                } else {
-                    if (DZNDC) dzndc = dzndc + ldC(f.dZndc, w_iter);
-                    if (DZNDZ) {
-                        if (!nullify_dZndz) {
-                            long long i = (n_iter == ref_order) ? w_wraped : w_iter;
-                            dzndz = dzndz + ldC(f.dZndz, i);
-                        }
-                        nullify_dZndz = true;
-                    }
+            /* ---- rebase: reference diverging (:1283-1313) or dynamic glitch
+             * (:1317-1372).  Both do z <- ZZ, deriv += path[w_iter], w <- 0;
+             * only the dynamic test assigns bool_dyn_rebase (sticky flag). ---- */
+            bool rebase = (w_iter >= ref_div_iter - 1);
+            bool do_rebase = rebase;
+            XC ZZ_xr = record_zero;
+            if (!rebase) {
+                bool_dyn_rebase = (fabs(ZZ.re) <= fabs(zn.re)) && (fabs(ZZ.im) <= fabs(zn.im));
+                do_rebase = bool_dyn_rebase;
+                if (XR && bool_dyn_rebase) {
+                    ZZ_xr = (knext >= 0) ? (zn_x + REF_X(knext)) : (zn_x + ref_zn_next);
+                    do_rebase = xr_le(abs2(ZZ_xr), abs2(zn_x));
                 }
-                w_iter = 0;
-                n_reb++;
-                continue;
             }
-
-            /* ---- rebase: dynamic glitch, :1317-1372 ---- */
-            bool_dyn_rebase = (fabs(ZZ.re) <= fabs(zn.re)) && (fabs(ZZ.im) <= fabs(zn.im));
-            if (bool_dyn_rebase) {
+            if (do_rebase) {
                 if (XR) {
-                    XC ZZ_xr = (knext >= 0) ? (zn_x + REF_X(knext)) : (zn_x + ref_zn_next);
-                    if (xr_le(abs2(ZZ_xr), abs2(zn_x))) {
-                        zn_x = ZZ_xr;
-                        zn = to_std(ZZ_xr);
-                        if (DZNDC) dzndc_x = dzndc_x + DZNDC_X(w_iter);
-                        if (DZNDZ) {
-                            if (!nullify_dZndz) {
-                                long long i = (n_iter == ref_order) ? w_wraped : w_iter;
-                                dzndz_x = dzndz_x + DZNDZ_X(i);
-                            }
-                            nullify_dZndz = true;
-                        }
-                        w_iter = 0;
-                        n_reb++;
-                        continue;
-                    }
+                    if (rebase) { zn = ZZ; zn_x = to_xr(ZZ); }
+                    else { zn_x = ZZ_xr; zn = to_std(ZZ_xr); }
+                    if (DZNDC) dzndc_x = dzndc_x + DZNDC_X(w_iter);
                 } else {
                     zn = ZZ;
                     if (DZNDC) dzndc = dzndc + ldC(f.dZndc, w_iter);
-                    if (DZNDZ) {
-                        if (!nullify_dZndz) {
-                            long long i = (n_iter == ref_order) ? w_wraped : w_iter;
-                            dzndz = dzndz + ldC(f.dZndz, i);
-                        }
-                        nullify_dZndz = true;
-                    }
-                    w_iter = 0;
-                    n_reb++;
-                    continue;
                 }
+                if (DZNDZ) {
+                    if (!nullify_dZndz) {
+                        const int i = (cyc && n_iter == order) ? w_wraped : w_iter;
+                        if (XR) dzndz_x = dzndz_x + DZNDZ_X(i);
+                        else dzndz = dzndz + ldC(f.dZndz, i);
+                    }
+                    nullify_dZndz = true;
+                }
+                w_iter = 0;
+                ref_cur = Zn0;
+                p_reb++;
             }
         }
 
-        /* ---- epilogue, :1374-1398 ---- */
-        U[ipt] = (int)w_iter;
+        /* ---- epilogue, :1374-1398 (Zn / dZndc carry one zero pad element:
+         * w_iter == L is reachable, see upload()) ---- */
+        U[ipt] = w_iter;
         if (XR) {
-            zn = to_std(zn_x) + ldC(f.Zn, w_iter);
+            zn = to_std(zn_x) + ldC(Zn, w_iter);
             if (DZNDC) dzndc = to_std(dzndc_x + DZNDC_X(w_iter));
         } else {
-            zn = zn + ldC(f.Zn, w_iter);
+            zn = zn + ldC(Zn, w_iter);
             if (DZNDC) dzndc = dzndc + ldC(f.dZndc, w_iter);
         }
         long long row = 0;
-        stC(Z, row++, npts, ipt, zn);
-        if (DZNDZ) stC(Z, row++, npts, ipt, dzndz);
-        if (DZNDC) stC(Z, row++, npts, ipt, dzndc);
-        if (f.calc_orbit) {
+        stC(Z, row++, npts_ll, ipt, zn);
+        if (DZNDZ) stC(Z, row++, npts_ll, ipt, dzndz);
+        if (DZNDC) stC(Z, row++, npts_ll, ipt, dzndc);
+        if (orbit) {
             C zo = orbit_zn2;
-            C CC = c + ldC(f.Zn, 1);
-            while (orbit_i2 < n_iter - f.backshift) { zo = zo * zo + CC; orbit_i2 += 1; }
-            stC(Z, row++, npts, ipt, zo);
+            C CC = c + ldC(Zn, 1);
+            while (orbit_i2 < n_iter - (int)f.backshift) { zo = zo * zo + CC; orbit_i2 += 1; }
+            stC(Z, row++, npts_ll, ipt, zo);
         }
         stop_reason[ipt] = (signed char)stop;
-        stop_iter[ipt] = (int)n_iter;
+        stop_iter[ipt] = n_iter;
         n_sum += (unsigned long long)n_iter;
+        n_exec += p_exec; n_bla += p_bla; n_reb += p_reb;
     }
 #undef DZNDC_X
 #undef DZNDZ_X
@@ -806,12 +808,12 @@ k_perturb_bs(FrameDev f, long long npts, const C *__restrict__ c_pix,
 
         for (;;) {
             if (BLA && (w_iter & 7) == 0) {
-                long long ib = 0;
-                long long step = ref_bla_get(f.r_bla, f.stages_bla, mkC(x, y), w_iter,
-                                             first_invalid, ib);
+                int ib = 0;
+                const int step = ref_bla_get(f.r_bla, f.stages_bla, mkC(x, y), (int)w_iter,
+                                             (int)first_invalid, ib);
                 if (step != 0) {
                     double M[8];
-                    const double2 *Mp = reinterpret_cast<const double2 *>(f.M_bla + 8 * ib);
+                    const double2 *Mp = reinterpret_cast<const double2 *>(f.M_bla + 8 * (long long)ib);
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
                         double2 v = __ldg(Mp + q);
@@ -840,7 +842,7 @@ k_perturb_bs(FrameDev f, long long npts, const C *__restrict__ c_pix,
             if (XR) {
                 long long k = -1;
                 if (has_xr && w_iter != 0 && (fabs(ref_zn.re) < 1.e-300 || fabs(ref_zn.im) < 1.e-300))
-                    k = xr_find(f.ref_index_xr, f.n_xr, w_iter);
+                    k = xr_find(f.ref_index_xr, f.n_xr_i, (int)w_iter);
                 if (k >= 0) {
                     rx_x = mkXF(__ldg(f.refx_xr + k), __ldg(f.refx_xr_e + k));
                     ry_x = mkXF(__ldg(f.refy_xr + k), __ldg(f.refy_xr_e + k));
@@ -886,7 +888,7 @@ k_perturb_bs(FrameDev f, long long npts, const C *__restrict__ c_pix,
             long long knext = -1;
             if (XR && has_xr && w_iter != 0
                 && (fabs(ref_next.re) < 1.e-300 || fabs(ref_next.im) < 1.e-300))
-                knext = xr_find(f.ref_index_xr, f.n_xr, w_iter);
+                knext = xr_find(f.ref_index_xr, f.n_xr_i, (int)w_iter);
             double XX = x + ref_next.re, YY = y + ref_next.im;
             double full_sq_norm = XX * XX + YY * YY;
             if (f.calc_orbit) {
@@ -1058,7 +1060,7 @@ __global__ void k_bla_merge_m2(long long comp_len, int stg, double kc_std, doubl
     if (i > comp_len - step) return;
     long long ii = i + step / 2;
     if (ii >= comp_len) return;
-    long long i1 = bla_index(i, stg - 1), i2 = bla_index(ii, stg - 1), ir = bla_index(i, stg);
+    long long i1 = bla_index64(i, stg - 1), i2 = bla_index64(ii, stg - 1), ir = bla_index64(i, stg);
     BlaNode n1, n2;
     n1.A = M[2 * i1]; n1.B = M[2 * i1 + 1]; n1.r = r[i1];
     n2.A = M[2 * i2]; n2.B = M[2 * i2 + 1]; n2.r = r[i2];
@@ -1138,7 +1140,7 @@ __global__ void k_bla_merge_bs(long long comp_len, int stg, double kc_std, doubl
     if (i > comp_len - step) return;
     long long ii = i + step / 2;
     if (ii >= comp_len) return;
-    long long i1 = bla_index(i, stg - 1), i2 = bla_index(ii, stg - 1), ir = bla_index(i, stg);
+    long long i1 = bla_index64(i, stg - 1), i2 = bla_index64(ii, stg - 1), ir = bla_index64(i, stg);
     BlaNodeBS n1, n2;
 #pragma unroll
     for (int d = 0; d < 8; d++) { n1.M[d] = M[8 * i1 + d]; n2.M[d] = M[8 * i2 + d]; }

@@ -132,6 +132,8 @@ FSB_HD C cmul_rn(C a, C b)
                add_rn(mul_rn(a.re, b.im), mul_rn(a.im, b.re)));
 }
 FSB_HD C cadd_rn(C a, C b) { return mkC(add_rn(a.re, b.re), add_rn(a.im, b.im)); }
+FSB_HD C scale2_rn(C a) { return mkC(mul_rn(2., a.re), mul_rn(2., a.im)); }
+FSB_HD double norm2_rn(C a) { return add_rn(mul_rn(a.re, a.re), mul_rn(a.im, a.im)); }
 
 /* |x + iy| : same definition as the oracle's fso_hypot (oracle/fs_oracle.cpp):
  * power-of-two pre-scaling then sqrt(a*a + b*b), each operation rounded once. */

@@ -30,7 +30,7 @@ FAST_FLOOR = {n: 0.999 for n in ALL}
 FAST_FLOOR.update({
     "std_M2_seahorse_orbit": 0.99, "std_BS_f1": 0.99, "std_BS_f4": 0.99,
     "std_BS_f5": 0.99, "p_M2_shallow": 0.995, "p_M2_divref_orbit": 0.95,
-    "p_M2_ultradeep_xr": 0.85, "p_BS_f2_E12": 0.5, "p_BS_f5_E12": 0.6,
+    "p_M2_ultradeep_xr": 0.8, "p_BS_f2_E12": 0.5, "p_BS_f5_E12": 0.6,
     "p_BS_f1_E12_nohess_nobla": 0.15,
 })
 
@@ -39,10 +39,11 @@ FAST_FLOOR.update({
 # amplified along the orbit (a chaotic map), so a small tail of pixels exceeds
 # any fixed tolerance; the views listed are boundary zooms at the limit of the
 # fp64 resolution where that tail is large.
-NU_FLOOR = {n: 0.997 for n in ALL}
+NU_FLOOR = {n: 0.995 for n in ALL}
 NU_FLOOR.update({
     "p_BS_f1_E12_nohess_nobla": 0.0, "p_BS_f2_E12": 0.8, "p_BS_f5_E12": 0.0,
     "p_M2_divref_orbit": 0.85, "p_M2_shallow": 0.95, "std_BS_f4": 0.99,
+    "p_BS_f4_E12": 0.99,
 })
 
 
