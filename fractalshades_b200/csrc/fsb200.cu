@@ -151,25 +151,28 @@ typedef void (*perturb_kernel_t)(FrameDev, long long, const C *, double *, int *
                                  signed char *, int *, unsigned long long *,
                                  unsigned long long *, const volatile int *);
 
-template <bool XR, bool DC, bool DZ, bool BLA> perturb_kernel_t pick_m2_extra(bool extra)
+template <bool XR, bool DC, bool DZ, bool BLA> perturb_kernel_t pick_m2_extra(bool extra, bool fastxr)
 {
-    return extra ? k_perturb_m2<XR, DC, DZ, BLA, true> : k_perturb_m2<XR, DC, DZ, BLA, false>;
+    if (XR && !DZ && fastxr)
+        return extra ? k_perturb_m2<XR, DC, DZ, BLA, true, (XR && !DZ)>
+                     : k_perturb_m2<XR, DC, DZ, BLA, false, (XR && !DZ)>;
+    return extra ? k_perturb_m2<XR, DC, DZ, BLA, true, false> : k_perturb_m2<XR, DC, DZ, BLA, false, false>;
 }
-template <bool XR, bool DC, bool DZ> perturb_kernel_t pick_m2_bla(bool bla, bool extra)
+template <bool XR, bool DC, bool DZ> perturb_kernel_t pick_m2_bla(bool bla, bool extra, bool fastxr)
 {
-    return bla ? pick_m2_extra<XR, DC, DZ, true>(extra) : pick_m2_extra<XR, DC, DZ, false>(extra);
+    return bla ? pick_m2_extra<XR, DC, DZ, true>(extra, fastxr) : pick_m2_extra<XR, DC, DZ, false>(extra, fastxr);
 }
-template <bool XR, bool DC> perturb_kernel_t pick_m2_dz(bool dz, bool bla, bool extra)
+template <bool XR, bool DC> perturb_kernel_t pick_m2_dz(bool dz, bool bla, bool extra, bool fastxr)
 {
-    return dz ? pick_m2_bla<XR, DC, true>(bla, extra) : pick_m2_bla<XR, DC, false>(bla, extra);
+    return dz ? pick_m2_bla<XR, DC, true>(bla, extra, fastxr) : pick_m2_bla<XR, DC, false>(bla, extra, fastxr);
 }
-template <bool XR> perturb_kernel_t pick_m2_dc(bool dc, bool dz, bool bla, bool extra)
+template <bool XR> perturb_kernel_t pick_m2_dc(bool dc, bool dz, bool bla, bool extra, bool fastxr)
 {
-    return dc ? pick_m2_dz<XR, true>(dz, bla, extra) : pick_m2_dz<XR, false>(dz, bla, extra);
+    return dc ? pick_m2_dz<XR, true>(dz, bla, extra, fastxr) : pick_m2_dz<XR, false>(dz, bla, extra, fastxr);
 }
-perturb_kernel_t pick_m2(bool xr, bool dc, bool dz, bool bla, bool extra)
+perturb_kernel_t pick_m2(bool xr, bool dc, bool dz, bool bla, bool extra, bool fastxr)
 {
-    return xr ? pick_m2_dc<true>(dc, dz, bla, extra) : pick_m2_dc<false>(dc, dz, bla, extra);
+    return xr ? pick_m2_dc<true>(dc, dz, bla, extra, fastxr) : pick_m2_dc<false>(dc, dz, bla, extra, fastxr);
 }
 template <bool XR, bool H> perturb_kernel_t pick_bs_bla(bool bla)
 {
@@ -192,6 +195,7 @@ struct fsb_frame {
     FrameDev dev;
     int nz = 0;
     bool bla_on = false;
+    bool fast_xr = false;     /* Xrange kernel with the guarded fp64 fast path */
     std::vector<void *> owned;
     double ms_upload = 0, ms_dzndc = 0, ms_bla = 0;
     long long dzndc_len = 0;
@@ -363,6 +367,25 @@ void host_dzndc_bs(const fsb_frame_desc &d, std::vector<double> &out, std::vecto
             D[to_i] = fyx * b + fyy * dd - scale;
         }
     }
+}
+
+/* fp64 mirror of an Xrange value for the fast path of the Xrange kernels:
+ * exact when every component is a normal double, 0 for components below the
+ * normal range (they are below half an ulp of anything the fast path adds them
+ * to), NaN when a component is too large (forces the exact fallback). */
+C xr_flushed_std(C m, int e)
+{
+    double out[2];
+    const double in[2] = {m.re, m.im};
+    for (int k = 0; k < 2; k++) {
+        double nm; int ne;
+        normalize_real(in[k], e, nm, ne);
+        if (in[k] == 0.) out[k] = 0.;
+        else if (!(in[k] == in[k]) || ne > 1000) out[k] = mk64(0x7ff80000, 0);
+        else if (ne < -1022) out[k] = 0.;
+        else out[k] = ldexp(nm, ne);
+    }
+    return mkC(out[0], out[1]);
 }
 
 int stages_bla_of(long long L)
@@ -751,6 +774,23 @@ int fsb_frame_create(const fsb_frame_desc *desc, fsb_frame **out)
             }
         }
     }
+    {
+        const char *pure = getenv("FSB200_PURE_XR");
+        f->fast_xr = d.model == FSB_MODEL_M2 && d.xr_detect && !d.calc_dzndz
+                     && !(pure && pure[0] == '1');
+    }
+    if (f->fast_xr && d.calc_dzndc) {
+        /* read the Xrange path back and build its flushed fp64 mirror */
+        std::vector<C> m((size_t)L), sd((size_t)L);
+        std::vector<int> me((size_t)L);
+        if (cudaMemcpy(m.data(), v.dZndc, (size_t)(L * 16), cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemcpy(me.data(), v.dZndc_e, (size_t)(L * 4), cudaMemcpyDeviceToHost) != cudaSuccess) {
+            fsb_frame_destroy(f);
+            return fail(-1, "dZndc read-back failed");
+        }
+        for (long long i = 0; i < L; i++) sd[(size_t)i] = xr_flushed_std(m[(size_t)i], me[(size_t)i]);
+        UP(upload(f, sd.data(), L, &v.dZndc_std, 1));
+    }
     if (d.calc_dzndz) {
         if (d.dZndz) {
             UP(upload(f, (const C *)d.dZndz, L + 1, &v.dZndz));
@@ -849,7 +889,7 @@ static int frame_launch(Ctx *c, fsb_frame *f, long long npts, const C *d_c_pix, 
     const fsb_frame_desc &d = f->d;
     perturb_kernel_t k = (d.model == FSB_MODEL_M2)
         ? pick_m2(d.xr_detect != 0, d.calc_dzndc != 0, d.calc_dzndz != 0, f->bla_on,
-                  f->dev.order_i > 0 || d.calc_orbit != 0)
+                  f->dev.order_i > 0 || d.calc_orbit != 0, f->fast_xr)
         : pick_bs(d.xr_detect != 0, d.calc_dzndc != 0, f->bla_on);
     CK(cudaMemsetAsync(c->d_ctl, 0, 8 * sizeof(unsigned long long), c->stream));
     const int block = 128;

@@ -30,6 +30,7 @@ struct FrameDev {
     const C *Zn;
     /* holomorphic */
     const C *dZndc; const int *dZndc_e;
+    const C *dZndc_std;   /* Xrange frames: flushed fp64 mirror of dZndc (fast path) */
     const C *dZndz; const int *dZndz_e;
     const C *ref_xr; const int *ref_xr_e;
     /* burning ship family */
@@ -366,11 +367,30 @@ __device__ __forceinline__ T p_iter_deriv(T z, T dz, R ref_zn, D ref_d)
     return 2. * ((ref_zn + z) * dz + ref_d * z); /* mandelbrot_M2.py:611-622 */
 }
 
+/* Fast path of the Xrange kernels.  Xrange arithmetic is fp64 arithmetic with
+ * an unbounded exponent: every operation is the correctly rounded result of
+ * the same real operation.  While every live component of the pixel state is
+ * a normal double comfortably inside the range, the plain fp64 operation
+ * sequence therefore produces bit-identical values (scaling by 2^k is exact,
+ * rounding is scale invariant, and the sub-1e-300 addends -- c, the Xrange
+ * reference points, the tiny dZndc entries -- are below half an ulp of every
+ * sum they enter).  `in_fast_range` is the guard: biased exponent within
+ * [1023-460, 1023+900] for each component (zeros, denormals, inf and NaN all
+ * fail).  When it fails the iteration is redone in exact Xrange arithmetic. */
+__device__ __forceinline__ bool in_fast_range(double x)
+{
+    return (unsigned)(((hi32(x) >> 20) & 0x7ff) - (1023 - 460)) <= (unsigned)(460 + 900);
+}
+__device__ __forceinline__ bool in_fast_range(C z)
+{
+    return in_fast_range(z.re) && in_fast_range(z.im);
+}
+
 /* Template switches: XR = Xrange arithmetic (dx < 1e-300); DZNDC / DZNDZ =
  * derivative fields; BLA = bilinear-approximation skipping; EXTRA = the rarely
  * used runtime options (periodic reference `ref_order`, calc_orbit) -- compiled
  * out of the common variants. */
-template <bool XR, bool DZNDC, bool DZNDZ, bool BLA, bool EXTRA>
+template <bool XR, bool DZNDC, bool DZNDZ, bool BLA, bool EXTRA, bool FASTXR = false>
 __global__ void __launch_bounds__(128)
 k_perturb_m2(const __grid_constant__ FrameDev f, long long npts_ll,
              const C *__restrict__ c_pix, double *__restrict__ Z,
@@ -425,6 +445,10 @@ k_perturb_m2(const __grid_constant__ FrameDev f, long long npts_ll,
         bool nullify_dZndz = false;
         bool bool_dyn_rebase = true;
         int stop = -1;
+        /* FASTXR: `fast` = the state lives in (zn, dzndc) as plain doubles and
+         * the Xrange copies are stale; otherwise the Xrange copies are the
+         * state and zn = to_std(zn_x) as in the reference. */
+        bool fast = false;
 
         for (;;) {
             /* ---- BLA step, perturbation.py:1121-1154 ---- */
@@ -440,10 +464,21 @@ k_perturb_m2(const __grid_constant__ FrameDev f, long long npts_ll,
                     if (cyc) w_iter = w_iter % order;
                     ref_cur = ldC(Zn, w_iter);
                     if (XR) {
+                        if (FASTXR && fast) {   /* B * c needs the exact c */
+                            zn_x = to_xr(zn);
+                            if (DZNDC) dzndc_x = to_xr(dzndc);
+                        }
                         zn_x = A * zn_x + B * c_xr;
                         zn = to_std(zn_x);
                         if (DZNDC) dzndc_x = A * dzndc_x;
                         if (DZNDZ) dzndz_x = A * dzndz_x;
+                        if (FASTXR) {
+                            fast = in_fast_range(zn);
+                            if (DZNDC && fast) {
+                                dzndc = to_std(dzndc_x);
+                                fast = in_fast_range(dzndc);
+                            }
+                        }
                     } else {
                         zn = A * zn + B * c;
                         if (DZNDC) dzndc = A * dzndc;
@@ -459,13 +494,32 @@ k_perturb_m2(const __grid_constant__ FrameDev f, long long npts_ll,
             p_exec++;
             const C ref_zn = ref_cur;
             XC ref_zn_x = record_zero;
-            if (XR) {
+            bool done_fast = false;
+            if (XR && FASTXR && fast) {
+                /* plain fp64 sequence, then the range guard on the results */
+                C ndz = dzndc;
+                if (DZNDC) {
+                    C ref_d = bool_dyn_rebase ? mkC(0., 0.) : ldC(f.dZndc_std, w_iter);
+                    ndz = p_iter_deriv(zn, dzndc, ref_zn, ref_d);
+                }
+                const C nzn = p_iter_zn(zn, ref_zn, c);
+                if (in_fast_range(nzn) && (!DZNDC || in_fast_range(ndz))) {
+                    zn = nzn;
+                    if (DZNDC) dzndc = ndz;
+                    done_fast = true;
+                } else {          /* redo this iteration in Xrange arithmetic */
+                    zn_x = to_xr(zn);
+                    if (DZNDC) dzndc_x = to_xr(dzndc);
+                    fast = false;
+                }
+            }
+            if (XR && !done_fast) {
                 int k = -1;
                 if (has_xr && w_iter != 0 && fabs(ref_zn.re) < 1.e-300 && fabs(ref_zn.im) < 1.e-300)
                     k = xr_find(f.ref_index_xr, f.n_xr_i, w_iter);
                 ref_zn_x = (k >= 0) ? REF_X(k) : to_xr(ref_zn);
             }
-            if (DZNDC) {
+            if (DZNDC && !done_fast) {
                 if (XR) {
                     XC ref_d = bool_dyn_rebase ? record_zero : DZNDC_X(w_iter);
                     dzndc_x = p_iter_deriv(zn_x, dzndc_x, ref_zn_x, ref_d);
@@ -480,8 +534,17 @@ k_perturb_m2(const __grid_constant__ FrameDev f, long long npts_ll,
                 else dzndz = p_iter_deriv(zn, dzndz, ref_zn, ldC(f.dZndz, i));
             }
             if (XR) {
-                zn_x = p_iter_zn(zn_x, ref_zn_x, c_xr);
-                zn = to_std(zn_x);
+                if (!done_fast) {
+                    zn_x = p_iter_zn(zn_x, ref_zn_x, c_xr);
+                    zn = to_std(zn_x);
+                    if (FASTXR) {          /* back to the fast path when safe */
+                        fast = in_fast_range(zn);
+                        if (DZNDC && fast) {
+                            dzndc = to_std(dzndc_x);
+                            fast = in_fast_range(dzndc);
+                        }
+                    }
+                }
             } else {
                 zn = p_iter_zn(zn, ref_zn, c);
             }
@@ -528,19 +591,52 @@ k_perturb_m2(const __grid_constant__ FrameDev f, long long npts_ll,
             bool rebase = (w_iter >= ref_div_iter - 1);
             bool do_rebase = rebase;
             XC ZZ_xr = record_zero;
+            bool fast_rebase = false;
             if (!rebase) {
                 bool_dyn_rebase = (fabs(ZZ.re) <= fabs(zn.re)) && (fabs(ZZ.im) <= fabs(zn.im));
                 do_rebase = bool_dyn_rebase;
                 if (XR && bool_dyn_rebase) {
-                    ZZ_xr = (knext >= 0) ? (zn_x + REF_X(knext)) : (zn_x + ref_zn_next);
-                    do_rebase = xr_le(abs2(ZZ_xr), abs2(zn_x));
+                    if (FASTXR && fast && in_fast_range(ZZ)) {
+                        /* same comparison on the same correctly rounded values */
+                        do_rebase = norm2(ZZ) <= norm2(zn);
+                        fast_rebase = true;
+                    } else {
+                        if (FASTXR && fast) {
+                            zn_x = to_xr(zn);
+                            if (DZNDC) dzndc_x = to_xr(dzndc);
+                            fast = false;
+                        }
+                        ZZ_xr = (knext >= 0) ? (zn_x + REF_X(knext)) : (zn_x + ref_zn_next);
+                        do_rebase = xr_le(abs2(ZZ_xr), abs2(zn_x));
+                    }
                 }
             }
             if (do_rebase) {
-                if (XR) {
+                if (XR && FASTXR && fast && (fast_rebase || rebase)) {
+                    /* rebase in plain fp64; leave the fast path if a result
+                     * falls out of the safe range (exact conversion) */
+                    C nd = dzndc;
+                    if (DZNDC) nd = dzndc + ldC(f.dZndc_std, w_iter);
+                    if (in_fast_range(ZZ) && (!DZNDC || in_fast_range(nd))) {
+                        zn = ZZ;
+                        if (DZNDC) dzndc = nd;
+                    } else {
+                        if (DZNDC) dzndc_x = to_xr(dzndc) + DZNDC_X(w_iter);
+                        zn = ZZ;
+                        zn_x = to_xr(ZZ);
+                        fast = false;
+                    }
+                } else if (XR) {
                     if (rebase) { zn = ZZ; zn_x = to_xr(ZZ); }
                     else { zn_x = ZZ_xr; zn = to_std(ZZ_xr); }
                     if (DZNDC) dzndc_x = dzndc_x + DZNDC_X(w_iter);
+                    if (FASTXR) {
+                        fast = in_fast_range(zn);
+                        if (DZNDC && fast) {
+                            dzndc = to_std(dzndc_x);
+                            fast = in_fast_range(dzndc);
+                        }
+                    }
                 } else {
                     zn = ZZ;
                     if (DZNDC) dzndc = dzndc + ldC(f.dZndc, w_iter);
@@ -562,7 +658,14 @@ k_perturb_m2(const __grid_constant__ FrameDev f, long long npts_ll,
         /* ---- epilogue, :1374-1398 (Zn / dZndc carry one zero pad element:
          * w_iter == L is reachable, see upload()) ---- */
         U[ipt] = w_iter;
-        if (XR) {
+        if (XR && FASTXR && fast) {
+            zn = zn + ldC(Zn, w_iter);
+            if (DZNDC) {
+                const C rd = ldC(f.dZndc_std, w_iter);
+                if (rd.re == rd.re && rd.im == rd.im) dzndc = dzndc + rd;
+                else dzndc = to_std(to_xr(dzndc) + DZNDC_X(w_iter));   /* huge entry */
+            }
+        } else if (XR) {
             zn = to_std(zn_x) + ldC(Zn, w_iter);
             if (DZNDC) dzndc = to_std(dzndc_x + DZNDC_X(w_iter));
         } else {
