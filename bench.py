@@ -206,8 +206,18 @@ def bind_spec(f, w):
     return spec
 
 
+def host_threads():
+    """ all usable host cores (torchrun exports OMP_NUM_THREADS=1: the thread
+    count is therefore passed explicitly to the OpenMP port) """
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_sample(w, f, target_s=12.0, nthreads=0):
     """ Time the oracle port on a bounded 1-in-k sample of the frame's tiles. """
+    nthreads = nthreads or host_threads()
     spec = bind_spec(f, w)
     t = None
     t_tables = 0.
@@ -240,12 +250,12 @@ def run_reference_arm(args, w, rank, world):
     if rank != 0:
         return
     f = make_fractal(w, args.nx)
-    cores = os.cpu_count()
-    s = cpu_sample(w, f, target_s=args.cpu_seconds)
+    cores = host_threads()
+    s = cpu_sample(w, f, target_s=args.cpu_seconds, nthreads=cores)
     times = []
     for i in range(args.warmup + args.steps):
         t0 = time.time()
-        si = oracle_run(w, f, s["tables"], s["c_pix"], 0)
+        si = oracle_run(w, f, s["tables"], s["c_pix"], cores)
         if i >= args.warmup:
             times.append(time.time() - t0)
     iters = int(si.sum(dtype=np.int64))
@@ -450,7 +460,7 @@ def main():
             s = cpu_sample(w, fc, target_s=args.cpu_seconds)
             cpu_baseline = {
                 "value": s["iters"] / s["seconds"] / 1e9, "unit": "Gpix-iter/s",
-                "cores": os.cpu_count(), "kind": "port",
+                "cores": host_threads(), "kind": "port",
                 "sample": (f"{s['n_tiles']} of {s['n_tiles_total']} tiles, "
                            f"{s['npts']} px, {s['seconds']:.2f} s; oracle "
                            f"C++/OpenMP port (oracle/fs_oracle.cpp)"),
