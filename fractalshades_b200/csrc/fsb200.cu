@@ -57,23 +57,28 @@ int ensure_init()
 }
 
 /* Per host-thread launch context. */
+const int MAX_CHUNKS = 16;
+const int CTL_WORDS = 8;                 /* per chunk: [work, c0..c3, -, -, -] */
 struct Ctx {
-    cudaStream_t stream = nullptr, side = nullptr;
+    cudaStream_t stream = nullptr, side = nullptr;      /* compute / abort flag */
+    cudaStream_t s_alt = nullptr, s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evc0 = nullptr, evc1 = nullptr;
+    cudaEvent_t ev_h[MAX_CHUNKS] = {}, ev_k[MAX_CHUNKS] = {};
     void *d_buf = nullptr;  long long d_cap = 0;      /* scratch for in/out   */
-    unsigned long long *d_ctl = nullptr;              /* [work, c0..c3, flag] */
+    unsigned long long *d_ctl = nullptr;              /* MAX_CHUNKS control blocks + abort flag */
     unsigned long long *h_ctl = nullptr;              /* pinned mirror        */
+    int *d_abort() { return (int *)(d_ctl + MAX_CHUNKS * CTL_WORDS); }
     ~Ctx()
     {
         if (d_buf) cudaFree(d_buf);
         if (d_ctl) cudaFree(d_ctl);
         if (h_ctl) cudaFreeHost(h_ctl);
-        if (ev0) cudaEventDestroy(ev0);
-        if (ev1) cudaEventDestroy(ev1);
-        if (evc0) cudaEventDestroy(evc0);
-        if (evc1) cudaEventDestroy(evc1);
-        if (stream) cudaStreamDestroy(stream);
-        if (side) cudaStreamDestroy(side);
+        for (cudaEvent_t e : {ev0, ev1, evc0, evc1}) if (e) cudaEventDestroy(e);
+        for (int i = 0; i < MAX_CHUNKS; i++) {
+            if (ev_h[i]) cudaEventDestroy(ev_h[i]);
+            if (ev_k[i]) cudaEventDestroy(ev_k[i]);
+        }
+        for (cudaStream_t st : {stream, side, s_alt, s_h2d, s_d2h}) if (st) cudaStreamDestroy(st);
     }
 };
 thread_local Ctx *t_ctx = nullptr;
@@ -84,14 +89,16 @@ int get_ctx(Ctx **out)
     if (!t_ctx) {
         Ctx *c = new Ctx();
         CK(cudaSetDevice(g_device));
-        CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-        CK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
-        CK(cudaEventCreate(&c->ev0));
-        CK(cudaEventCreate(&c->ev1));
-        CK(cudaEventCreate(&c->evc0));
-        CK(cudaEventCreate(&c->evc1));
-        CK(cudaMalloc(&c->d_ctl, 8 * sizeof(unsigned long long)));
-        CK(cudaHostAlloc(&c->h_ctl, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
+        for (cudaStream_t *st : {&c->stream, &c->side, &c->s_alt, &c->s_h2d, &c->s_d2h})
+            CK(cudaStreamCreateWithFlags(st, cudaStreamNonBlocking));
+        for (cudaEvent_t *e : {&c->ev0, &c->ev1, &c->evc0, &c->evc1}) CK(cudaEventCreate(e));
+        for (int i = 0; i < MAX_CHUNKS; i++) {
+            CK(cudaEventCreateWithFlags(&c->ev_h[i], cudaEventDisableTiming));
+            CK(cudaEventCreate(&c->ev_k[i]));
+        }
+        const size_t ctl_bytes = (MAX_CHUNKS * CTL_WORDS + 2) * sizeof(unsigned long long);
+        CK(cudaMalloc(&c->d_ctl, ctl_bytes));
+        CK(cudaHostAlloc(&c->h_ctl, ctl_bytes, cudaHostAllocDefault));
         t_ctx = c;
     } else {
         CK(cudaSetDevice(g_device));
@@ -126,24 +133,44 @@ template <class K> int persistent_grid(K kernel, int block, long long npts, int 
     return 0;
 }
 
-/* launch + wait, polling the caller's interruption flag */
-int wait_kernel(Ctx *c, const volatile uint8_t *interrupted, bool *was_interrupted)
+/* wait for `done`, polling the caller's interruption flag */
+int wait_event(Ctx *c, cudaEvent_t done, const volatile uint8_t *interrupted,
+               bool *was_interrupted)
 {
     *was_interrupted = false;
-    int one = 1;
+    static const int one = 1;
     for (;;) {
-        cudaError_t q = cudaEventQuery(c->ev1);
+        cudaError_t q = cudaEventQuery(done);
         if (q == cudaSuccess) break;
         if (q != cudaErrorNotReady) CK(q);
         if (interrupted && *interrupted && !*was_interrupted) {
             *was_interrupted = true;
-            c->h_ctl[7] = 1;
-            CK(cudaMemcpyAsync((int *)(c->d_ctl + 5), &one, sizeof(int),
-                               cudaMemcpyHostToDevice, c->side));
+            CK(cudaMemcpyAsync(c->d_abort(), &one, sizeof(int), cudaMemcpyHostToDevice, c->side));
         }
         std::this_thread::sleep_for(std::chrono::microseconds(50));
     }
+    if (*was_interrupted) CK(cudaStreamSynchronize(c->side));
     return 0;
+}
+
+/* Chunking of a host-buffer call: the frame is cut into up to MAX_CHUNKS
+ * slabs of consecutive points so that the H2D copy of slab k+1, the kernel of
+ * slab k and the D2H copies of slab k-1 overlap (three copy/compute streams;
+ * kernels alternate between two streams so that the tail of one slab overlaps
+ * the head of the next). */
+struct Chunks { int n; long long beg[MAX_CHUNKS + 1]; };
+Chunks make_chunks(long long npts)
+{
+    Chunks ch;
+    long long want = npts / (1LL << 20);
+    if (want < 1) want = 1;
+    if (want > MAX_CHUNKS) want = MAX_CHUNKS;
+    if (npts < (1LL << 17)) want = 1;
+    long long per = ((npts + want - 1) / want + 31) & ~31LL;
+    ch.n = 0;
+    ch.beg[0] = 0;
+    for (long long b = 0; b < npts; b += per) ch.beg[++ch.n] = (b + per < npts) ? b + per : npts;
+    return ch;
 }
 
 /* ---- kernel dispatch ------------------------------------------------------ */
@@ -577,51 +604,52 @@ int fsb_std_nz(const fsb_std_desc *d)
     return 6 + (d->calc_orbit ? 2 : 0);
 }
 
-static int std_launch(Ctx *c, const fsb_std_desc *d, long long npts, const C *d_c_pix,
-                      double *d_Z, signed char *d_sr, int *d_si,
-                      const volatile uint8_t *interrupted, fsb_stats *stats, bool *was_int)
+static int std_fill(const fsb_std_desc *d, StdDev &p, long long zstride)
 {
     if (d->model != FSB_MODEL_M2 && d->model != FSB_MODEL_BS)
         return fail(-3, "unsupported standard model %d", d->model);
     if (d->model == FSB_MODEL_BS && (d->flavor < 1 || d->flavor > 5))
         return fail(-3, "unsupported burning-ship flavor %d", d->flavor);
     if (d->calc_orbit && d->backshift <= 0) return fail(-3, "calc_orbit needs backshift > 0");
-    StdDev p;
     p.center_re = d->center_re; p.center_im = d->center_im; p.dx = d->dx;
     for (int i = 0; i < 4; i++) p.lin_mat[i] = d->lin_mat[i];
     p.max_iter = d->max_iter; p.Mdiv_sq = d->M_divergence_sq; p.eps_sq = d->epsilon_stationnary_sq;
     p.calc_d2 = d->calc_d2zndc2; p.calc_orbit = d->calc_orbit; p.backshift = d->backshift;
     p.flavor = d->flavor;
-    CK(cudaMemsetAsync(c->d_ctl, 0, 8 * sizeof(unsigned long long), c->stream));
+    p.zstride = zstride;
+    return 0;
+}
+
+/* enqueue one kernel over points [0, n) of the given (offset) pointers */
+static int std_enqueue(Ctx *c, const fsb_std_desc *d, const StdDev &p, cudaStream_t st, int slot,
+                       long long n, const C *d_c_pix, double *d_Z, signed char *d_sr, int *d_si)
+{
+    unsigned long long *ctl = c->d_ctl + slot * CTL_WORDS;
+    CK(cudaMemsetAsync(ctl, 0, CTL_WORDS * sizeof(unsigned long long), st));
     const int block = 256;
     int grid = 1;
-    if (d->model == FSB_MODEL_M2) { if (persistent_grid(k_std_m2, block, npts, &grid)) return -1; }
-    else { if (persistent_grid(k_std_bs, block, npts, &grid)) return -1; }
-    CK(cudaEventRecord(c->ev0, c->stream));
+    if (d->model == FSB_MODEL_M2) { if (persistent_grid(k_std_m2, block, n, &grid)) return -1; }
+    else { if (persistent_grid(k_std_bs, block, n, &grid)) return -1; }
     if (d->model == FSB_MODEL_M2)
-        k_std_m2<<<grid, block, 0, c->stream>>>(p, npts, d_c_pix, d_Z, d_sr, d_si, c->d_ctl,
-                                                c->d_ctl + 1, (const volatile int *)(c->d_ctl + 5));
+        k_std_m2<<<grid, block, 0, st>>>(p, n, d_c_pix, d_Z, d_sr, d_si, ctl, ctl + 1, c->d_abort());
     else
-        k_std_bs<<<grid, block, 0, c->stream>>>(p, npts, d_c_pix, d_Z, d_sr, d_si, c->d_ctl,
-                                                c->d_ctl + 1, (const volatile int *)(c->d_ctl + 5));
+        k_std_bs<<<grid, block, 0, st>>>(p, n, d_c_pix, d_Z, d_sr, d_si, ctl, ctl + 1, c->d_abort());
     CK(cudaGetLastError());
-    CK(cudaEventRecord(c->ev1, c->stream));
-    if (wait_kernel(c, interrupted, was_int)) return -1;
-    CK(cudaStreamSynchronize(c->side));
-    CK(cudaMemcpyAsync(c->h_ctl, c->d_ctl, 5 * sizeof(unsigned long long),
-                       cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    if (stats) {
-        float ms = 0;
-        CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-        stats->kernel_ms = ms;
-        stats->n_iter_exec = (int64_t)c->h_ctl[1];
-        stats->n_bla_steps = 0;
-        stats->n_rebase = 0;
-        stats->sum_stop_iter = (int64_t)c->h_ctl[4];
-        stats->n_launches = 1;
-    }
     return 0;
+}
+
+static void gather_stats(Ctx *c, int n_slots, fsb_stats *stats)
+{
+    if (!stats) return;
+    stats->n_iter_exec = stats->n_bla_steps = stats->n_rebase = stats->sum_stop_iter = 0;
+    for (int k = 0; k < n_slots; k++) {
+        const unsigned long long *h = c->h_ctl + k * CTL_WORDS;
+        stats->n_iter_exec += (int64_t)h[1];
+        stats->n_bla_steps += (int64_t)h[2];
+        stats->n_rebase += (int64_t)h[3];
+        stats->sum_stop_iter += (int64_t)h[4];
+    }
+    stats->n_launches = n_slots;
 }
 
 int fsb_std_run_device(const fsb_std_desc *d, int64_t npts, const double *d_c_pix, double *d_Z,
@@ -631,10 +659,79 @@ int fsb_std_run_device(const fsb_std_desc *d, int64_t npts, const double *d_c_pi
     if (get_ctx(&c)) return -1;
     if (stats) memset(stats, 0, sizeof *stats);
     if (npts <= 0) return 0;
-    bool was_int = false;
-    return std_launch(c, d, npts, (const C *)d_c_pix, d_Z, (signed char *)d_stop_reason,
-                      d_stop_iter, nullptr, stats, &was_int);
+    StdDev p;
+    if (std_fill(d, p, npts)) return -3;
+    CK(cudaMemsetAsync(c->d_abort(), 0, sizeof(int), c->stream));
+    CK(cudaEventRecord(c->ev0, c->stream));
+    if (std_enqueue(c, d, p, c->stream, 0, npts, (const C *)d_c_pix, d_Z,
+                    (signed char *)d_stop_reason, d_stop_iter)) return -1;
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaMemcpyAsync(c->h_ctl, c->d_ctl, CTL_WORDS * sizeof(unsigned long long),
+                       cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    gather_stats(c, 1, stats);
+    if (stats) stats->kernel_ms = ms;
+    return 0;
 }
+
+} /* extern "C" */
+
+/* One output plane of a host-buffer call */
+struct Plane { char *host; long long dev_off; long long elem; };
+
+/* Host-buffer call: H2D of c_pix, kernels and D2H of the planes, pipelined
+ * over slabs of consecutive points.  `enqueue(stream, slot, n, a)` launches the
+ * kernel for points [a, a+n) into control block `slot`. */
+template <class Enqueue>
+static int run_pipelined(Ctx *c, long long npts, const double *c_pix, long long o_c,
+                         const Plane *planes, int n_planes, long long o_zero_beg,
+                         long long o_zero_end, long long o_sr, Enqueue enqueue,
+                         const volatile uint8_t *interrupted, fsb_stats *stats, bool *was_int)
+{
+    char *base = (char *)c->d_buf;
+    const Chunks ch = make_chunks(npts);
+    CK(cudaMemsetAsync(c->d_abort(), 0, sizeof(int), c->stream));
+    CK(cudaMemsetAsync(base + o_zero_beg, 0, (size_t)(o_zero_end - o_zero_beg), c->stream));
+    CK(cudaMemsetAsync(base + o_sr, 0xff, (size_t)npts, c->stream));
+    CK(cudaEventRecord(c->ev0, c->stream));
+    CK(cudaStreamWaitEvent(c->s_alt, c->ev0, 0));
+    CK(cudaStreamWaitEvent(c->s_d2h, c->ev0, 0));
+    for (int k = 0; k < ch.n; k++) {
+        const long long a = ch.beg[k], n = ch.beg[k + 1] - a;
+        CK(cudaMemcpyAsync(base + o_c + a * 16, c_pix + 2 * a, (size_t)(n * 16),
+                           cudaMemcpyHostToDevice, c->s_h2d));
+        CK(cudaEventRecord(c->ev_h[k], c->s_h2d));
+        cudaStream_t st = (k & 1) ? c->s_alt : c->stream;
+        CK(cudaStreamWaitEvent(st, c->ev_h[k], 0));
+        if (enqueue(st, k, n, a)) return -1;
+        CK(cudaEventRecord(c->ev_k[k], st));
+        CK(cudaStreamWaitEvent(c->s_d2h, c->ev_k[k], 0));
+        for (int r = 0; r < n_planes; r++)
+            CK(cudaMemcpyAsync(planes[r].host + a * planes[r].elem,
+                               base + planes[r].dev_off + a * planes[r].elem,
+                               (size_t)(n * planes[r].elem), cudaMemcpyDeviceToHost, c->s_d2h));
+    }
+    CK(cudaMemcpyAsync(c->h_ctl, c->d_ctl, (size_t)ch.n * CTL_WORDS * sizeof(unsigned long long),
+                       cudaMemcpyDeviceToHost, c->s_d2h));
+    CK(cudaEventRecord(c->ev1, c->s_d2h));
+    if (wait_event(c, c->ev1, interrupted, was_int)) return -1;
+    CK(cudaStreamSynchronize(c->s_d2h));
+    gather_stats(c, ch.n, stats);
+    if (stats) {
+        float ms_k = 0, ms_k2 = 0, ms_all = 0;
+        CK(cudaEventElapsedTime(&ms_k, c->ev0, c->ev_k[ch.n - 1]));
+        if (ch.n > 1) CK(cudaEventElapsedTime(&ms_k2, c->ev0, c->ev_k[ch.n - 2]));
+        CK(cudaEventElapsedTime(&ms_all, c->ev0, c->ev1));
+        stats->kernel_ms = ms_k > ms_k2 ? ms_k : ms_k2;   /* span of the slab kernels */
+        stats->h2d_ms = 0.;                               /* hidden behind the kernels */
+        stats->d2h_ms = ms_all - stats->kernel_ms;        /* exposed tail of the last slab */
+    }
+    return 0;
+}
+
+extern "C" {
 
 int fsb_std_run(const fsb_std_desc *d, int64_t npts, const double *c_pix, double *Z,
                 int8_t *stop_reason, int32_t *stop_iter, const volatile uint8_t *interrupted,
@@ -645,34 +742,29 @@ int fsb_std_run(const fsb_std_desc *d, int64_t npts, const double *c_pix, double
     if (stats) memset(stats, 0, sizeof *stats);
     if (npts <= 0) return 0;
     if (interrupted && *interrupted) return FSB_USER_INTERRUPTED;
+    StdDev p;
+    if (std_fill(d, p, npts)) return -3;
     const int nz = fsb_std_nz(d);
     const long long zelem = (d->model == FSB_MODEL_M2) ? 16 : 8;
     long long o_c = 0, o_Z = align256(o_c + npts * 16), o_si = align256(o_Z + nz * npts * zelem),
               o_sr = align256(o_si + npts * 4), total = align256(o_sr + npts);
     if (ctx_reserve(c, total)) return -1;
     char *base = (char *)c->d_buf;
-    CK(cudaEventRecord(c->evc0, c->stream));
-    CK(cudaMemcpyAsync(base + o_c, c_pix, (size_t)(npts * 16), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemsetAsync(base + o_Z, 0, (size_t)(nz * npts * zelem), c->stream));
-    CK(cudaMemsetAsync(base + o_si, 0, (size_t)(npts * 4), c->stream));
-    CK(cudaMemsetAsync(base + o_sr, 0xff, (size_t)npts, c->stream));
-    CK(cudaEventRecord(c->evc1, c->stream));
+    Plane planes[16];
+    int np = 0;
+    for (int r = 0; r < nz; r++)
+        planes[np++] = Plane{(char *)Z + r * npts * zelem, o_Z + r * npts * zelem, zelem};
+    planes[np++] = Plane{(char *)stop_iter, o_si, 4};
+    planes[np++] = Plane{(char *)stop_reason, o_sr, 1};
     bool was_int = false;
-    int rc = std_launch(c, d, npts, (const C *)(base + o_c), (double *)(base + o_Z),
-                        (signed char *)(base + o_sr), (int *)(base + o_si), interrupted, stats,
-                        &was_int);
+    auto enqueue = [&](cudaStream_t st, int slot, long long n, long long a) {
+        return std_enqueue(c, d, p, st, slot, n, (const C *)(base + o_c) + a,
+                           (double *)(base + o_Z + a * zelem), (signed char *)(base + o_sr) + a,
+                           (int *)(base + o_si) + a);
+    };
+    int rc = run_pipelined(c, npts, c_pix, o_c, planes, np, o_Z, o_si + npts * 4, o_sr, enqueue,
+                           interrupted, stats, &was_int);
     if (rc) return rc;
-    float ms = 0;
-    CK(cudaEventElapsedTime(&ms, c->evc0, c->evc1));
-    if (stats) stats->h2d_ms = ms;
-    CK(cudaEventRecord(c->evc0, c->stream));
-    CK(cudaMemcpyAsync(Z, base + o_Z, (size_t)(nz * npts * zelem), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(stop_iter, base + o_si, (size_t)(npts * 4), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(stop_reason, base + o_sr, (size_t)npts, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaEventRecord(c->evc1, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    CK(cudaEventElapsedTime(&ms, c->evc0, c->evc1));
-    if (stats) stats->d2h_ms = ms;
     return was_int ? FSB_USER_INTERRUPTED : 0;
 }
 
@@ -882,39 +974,24 @@ int fsb_frame_get_dzndz(const fsb_frame *f, double *dZndz, int32_t *dZndz_e)
     return 0;
 }
 
-static int frame_launch(Ctx *c, fsb_frame *f, long long npts, const C *d_c_pix, double *d_Z,
-                        int *d_U, signed char *d_sr, int *d_si,
-                        const volatile uint8_t *interrupted, fsb_stats *stats, bool *was_int)
+static int frame_enqueue(Ctx *c, fsb_frame *f, cudaStream_t st, int slot, long long n,
+                         long long zstride, const C *d_c_pix, double *d_Z, int *d_U,
+                         signed char *d_sr, int *d_si)
 {
     const fsb_frame_desc &d = f->d;
     perturb_kernel_t k = (d.model == FSB_MODEL_M2)
         ? pick_m2(d.xr_detect != 0, d.calc_dzndc != 0, d.calc_dzndz != 0, f->bla_on,
                   f->dev.order_i > 0 || d.calc_orbit != 0, f->fast_xr)
         : pick_bs(d.xr_detect != 0, d.calc_dzndc != 0, f->bla_on);
-    CK(cudaMemsetAsync(c->d_ctl, 0, 8 * sizeof(unsigned long long), c->stream));
+    unsigned long long *ctl = c->d_ctl + slot * CTL_WORDS;
+    CK(cudaMemsetAsync(ctl, 0, CTL_WORDS * sizeof(unsigned long long), st));
     const int block = 128;
     int grid = 1;
-    if (persistent_grid(k, block, npts, &grid)) return -1;
-    CK(cudaEventRecord(c->ev0, c->stream));
-    k<<<grid, block, 0, c->stream>>>(f->dev, npts, d_c_pix, d_Z, d_U, d_sr, d_si, c->d_ctl,
-                                     c->d_ctl + 1, (const volatile int *)(c->d_ctl + 5));
+    if (persistent_grid(k, block, n, &grid)) return -1;
+    FrameDev dv = f->dev;
+    dv.zstride = zstride;
+    k<<<grid, block, 0, st>>>(dv, n, d_c_pix, d_Z, d_U, d_sr, d_si, ctl, ctl + 1, c->d_abort());
     CK(cudaGetLastError());
-    CK(cudaEventRecord(c->ev1, c->stream));
-    if (wait_kernel(c, interrupted, was_int)) return -1;
-    CK(cudaStreamSynchronize(c->side));
-    CK(cudaMemcpyAsync(c->h_ctl, c->d_ctl, 5 * sizeof(unsigned long long),
-                       cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    if (stats) {
-        float ms = 0;
-        CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-        stats->kernel_ms = ms;
-        stats->n_iter_exec = (int64_t)c->h_ctl[1];
-        stats->n_bla_steps = (int64_t)c->h_ctl[2];
-        stats->n_rebase = (int64_t)c->h_ctl[3];
-        stats->sum_stop_iter = (int64_t)c->h_ctl[4];
-        stats->n_launches = 1;
-    }
     return 0;
 }
 
@@ -927,9 +1004,19 @@ int fsb_frame_run_device(fsb_frame *f, int64_t npts, const double *d_c_pix, doub
     if (!f) return fail(-3, "null frame");
     if (stats) memset(stats, 0, sizeof *stats);
     if (npts <= 0) return 0;
-    bool was_int = false;
-    return frame_launch(c, f, npts, (const C *)d_c_pix, d_Z, d_U, (signed char *)d_stop_reason,
-                        d_stop_iter, nullptr, stats, &was_int);
+    CK(cudaMemsetAsync(c->d_abort(), 0, sizeof(int), c->stream));
+    CK(cudaEventRecord(c->ev0, c->stream));
+    if (frame_enqueue(c, f, c->stream, 0, npts, npts, (const C *)d_c_pix, d_Z, d_U,
+                      (signed char *)d_stop_reason, d_stop_iter)) return -1;
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaMemcpyAsync(c->h_ctl, c->d_ctl, CTL_WORDS * sizeof(unsigned long long),
+                       cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    gather_stats(c, 1, stats);
+    if (stats) stats->kernel_ms = ms;
+    return 0;
 }
 
 int fsb_frame_run(fsb_frame *f, int64_t npts, const double *c_pix, double *Z, int32_t *U,
@@ -949,28 +1036,22 @@ int fsb_frame_run(fsb_frame *f, int64_t npts, const double *c_pix, double *Z, in
               total = align256(o_sr + npts);
     if (ctx_reserve(c, total)) return -1;
     char *base = (char *)c->d_buf;
-    CK(cudaEventRecord(c->evc0, c->stream));
-    CK(cudaMemcpyAsync(base + o_c, c_pix, (size_t)(npts * 16), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemsetAsync(base + o_Z, 0, (size_t)(o_si + npts * 4 - o_Z), c->stream));
-    CK(cudaMemsetAsync(base + o_sr, 0xff, (size_t)npts, c->stream));
-    CK(cudaEventRecord(c->evc1, c->stream));
+    Plane planes[16];
+    int np = 0;
+    for (int r = 0; r < nz; r++)
+        planes[np++] = Plane{(char *)Z + r * npts * zelem, o_Z + r * npts * zelem, zelem};
+    planes[np++] = Plane{(char *)U, o_U, 4};
+    planes[np++] = Plane{(char *)stop_iter, o_si, 4};
+    planes[np++] = Plane{(char *)stop_reason, o_sr, 1};
     bool was_int = false;
-    int rc = frame_launch(c, f, npts, (const C *)(base + o_c), (double *)(base + o_Z),
-                          (int *)(base + o_U), (signed char *)(base + o_sr), (int *)(base + o_si),
-                          interrupted, stats, &was_int);
+    auto enqueue = [&](cudaStream_t st, int slot, long long n, long long a) {
+        return frame_enqueue(c, f, st, slot, n, npts, (const C *)(base + o_c) + a,
+                             (double *)(base + o_Z + a * zelem), (int *)(base + o_U) + a,
+                             (signed char *)(base + o_sr) + a, (int *)(base + o_si) + a);
+    };
+    int rc = run_pipelined(c, npts, c_pix, o_c, planes, np, o_Z, o_si + npts * 4, o_sr, enqueue,
+                           interrupted, stats, &was_int);
     if (rc) return rc;
-    float ms = 0;
-    CK(cudaEventElapsedTime(&ms, c->evc0, c->evc1));
-    if (stats) stats->h2d_ms = ms;
-    CK(cudaEventRecord(c->evc0, c->stream));
-    CK(cudaMemcpyAsync(Z, base + o_Z, (size_t)(nz * npts * zelem), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(U, base + o_U, (size_t)(npts * 4), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(stop_iter, base + o_si, (size_t)(npts * 4), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(stop_reason, base + o_sr, (size_t)npts, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaEventRecord(c->evc1, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    CK(cudaEventElapsedTime(&ms, c->evc0, c->evc1));
-    if (stats) stats->d2h_ms = ms;
     return was_int ? FSB_USER_INTERRUPTED : 0;
 }
 

@@ -50,6 +50,7 @@ struct FrameDev {
     int flavor;
     /* 32-bit mirrors used by the pixel kernels (every orbit index fits) */
     int Li, ref_div_i, order_i /* 0: not a cycle */, first_invalid_i, max_iter_i, n_xr_i;
+    long long zstride;   /* row stride of the output planes (>= npts of the launch) */
 };
 
 struct StdDev {
@@ -60,6 +61,7 @@ struct StdDev {
     int calc_d2, calc_orbit;
     long long backshift;
     int flavor;
+    long long zstride;   /* row stride of the output planes */
 };
 
 /* Warp-level work stealing: lane 0 takes 32 points from the global counter. */
@@ -162,14 +164,14 @@ k_std_m2(StdDev p, long long npts, const C *__restrict__ c_pix,
             if (ret) break;
         }
         long long row = 0;
-        stC(Z, row++, npts, i, zn);
-        stC(Z, row++, npts, i, dzndz);
-        stC(Z, row++, npts, i, dzndc);
-        if (p.calc_d2) stC(Z, row++, npts, i, d2);
+        stC(Z, row++, p.zstride, i, zn);
+        stC(Z, row++, p.zstride, i, dzndz);
+        stC(Z, row++, p.zstride, i, dzndc);
+        if (p.calc_d2) stC(Z, row++, p.zstride, i, d2);
         if (p.calc_orbit) {
             C zo = orbit_zn2;
             while (orbit_i2 < n_iter - p.backshift) { zo = cadd_rn(cmul_rn(zo, zo), c); orbit_i2 += 1; }
-            stC(Z, row++, npts, i, zo);
+            stC(Z, row++, p.zstride, i, zo);
         }
         stop_reason[i] = (signed char)reason;
         stop_iter[i] = (int)n_iter;
@@ -283,9 +285,9 @@ k_std_bs(StdDev p, long long npts, const C *__restrict__ c_pix,
             }
             if (ret) break;
         }
-        Z[0 * npts + i] = X; Z[1 * npts + i] = Y;
-        Z[2 * npts + i] = dXdA; Z[3 * npts + i] = dXdB;
-        Z[4 * npts + i] = dYdA; Z[5 * npts + i] = dYdB;
+        Z[0 * p.zstride + i] = X; Z[1 * p.zstride + i] = Y;
+        Z[2 * p.zstride + i] = dXdA; Z[3 * p.zstride + i] = dXdB;
+        Z[4 * p.zstride + i] = dYdA; Z[5 * p.zstride + i] = dYdB;
         if (p.calc_orbit) {
             double xo = oxn2, yo = oyn2;
             while (orbit_i2 < n_iter - p.backshift) {
@@ -293,7 +295,7 @@ k_std_bs(StdDev p, long long npts, const C *__restrict__ c_pix,
                 bs_iterate(flavor, xo, yo, a, b, tx, ty);
                 xo = tx; yo = ty; orbit_i2 += 1;
             }
-            Z[6 * npts + i] = xo; Z[7 * npts + i] = yo;
+            Z[6 * p.zstride + i] = xo; Z[7 * p.zstride + i] = yo;
         }
         stop_reason[i] = (signed char)reason;
         stop_iter[i] = (int)n_iter;
@@ -673,14 +675,14 @@ k_perturb_m2(const __grid_constant__ FrameDev f, long long npts_ll,
             if (DZNDC) dzndc = dzndc + ldC(f.dZndc, w_iter);
         }
         long long row = 0;
-        stC(Z, row++, npts_ll, ipt, zn);
-        if (DZNDZ) stC(Z, row++, npts_ll, ipt, dzndz);
-        if (DZNDC) stC(Z, row++, npts_ll, ipt, dzndc);
+        stC(Z, row++, f.zstride, ipt, zn);
+        if (DZNDZ) stC(Z, row++, f.zstride, ipt, dzndz);
+        if (DZNDC) stC(Z, row++, f.zstride, ipt, dzndc);
         if (orbit) {
             C zo = orbit_zn2;
             C CC = c + ldC(Zn, 1);
             while (orbit_i2 < n_iter - (int)f.backshift) { zo = zo * zo + CC; orbit_i2 += 1; }
-            stC(Z, row++, npts_ll, ipt, zo);
+            stC(Z, row++, f.zstride, ipt, zo);
         }
         stop_reason[ipt] = (signed char)stop;
         stop_iter[ipt] = n_iter;
@@ -1073,11 +1075,11 @@ k_perturb_bs(FrameDev f, long long npts, const C *__restrict__ c_pix,
             }
         }
         long long row = 0;
-        Z[(row++) * npts + ipt] = x;
-        Z[(row++) * npts + ipt] = y;
+        Z[(row++) * f.zstride + ipt] = x;
+        Z[(row++) * f.zstride + ipt] = y;
         if (HESS) {
-            Z[(row++) * npts + ipt] = dxa; Z[(row++) * npts + ipt] = dxb;
-            Z[(row++) * npts + ipt] = dya; Z[(row++) * npts + ipt] = dyb;
+            Z[(row++) * f.zstride + ipt] = dxa; Z[(row++) * f.zstride + ipt] = dxb;
+            Z[(row++) * f.zstride + ipt] = dya; Z[(row++) * f.zstride + ipt] = dyb;
         }
         if (f.calc_orbit) {
             double xo = oxn2, yo = oyn2;
@@ -1088,7 +1090,7 @@ k_perturb_bs(FrameDev f, long long npts, const C *__restrict__ c_pix,
                 bs_iterate(flavor, xo, yo, AA, BB, tx, ty);
                 xo = tx; yo = ty; orbit_i2 += 1;
             }
-            Z[(row++) * npts + ipt] = xo; Z[(row++) * npts + ipt] = yo;
+            Z[(row++) * f.zstride + ipt] = xo; Z[(row++) * f.zstride + ipt] = yo;
         }
         stop_reason[ipt] = (signed char)stop;
         stop_iter[ipt] = (int)n_iter;

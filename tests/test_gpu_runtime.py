@@ -115,7 +115,7 @@ def test_user_interruption_returns_code_1():
     the call returns USER_INTERRUPTED """
     f = fsm.Perturbation_mandelbrot(tempfile.mkdtemp())
     v = fsb.VIEWS["deep_julia_2608"]
-    f.zoom(precision=420, x=v["x"][:440], y=v["y"][:440], dx="1e-400", nx=600,
+    f.zoom(precision=420, x=v["x"][:440], y=v["y"][:440], dx="1e-400", nx=2000,
            xy_ratio=1.0, theta_deg=0.)
     f.calc_std_div(calc_name="c", subset=None, max_iter=250000, M_divergence=1e3,
                    epsilon_stationnary=1e-3, BLA_eps=None, interior_detect=False,
@@ -127,7 +127,7 @@ def test_user_interruption_returns_code_1():
     U = np.zeros((1, n), np.int32)
     sr = -np.ones((1, n), np.int8)
     si = np.zeros((1, n), np.int32)
-    timer = threading.Timer(0.05, f.raise_interruption)
+    timer = threading.Timer(0.02, f.raise_interruption)
     timer.start()
     t0 = time.time()
     rc = f.numba_cycle_call((c_pix, Z, U, sr, si), indep)
