@@ -448,6 +448,7 @@ def main():
             "n_iter_exec": int(kstats["n_iter_exec"]),
             "n_bla_steps": int(kstats["n_bla_steps"]),
             "n_rebase": int(kstats["n_rebase"]),
+            "n_iter_fast": int(kstats.get("n_iter_fast", 0)),
             "kernel_ms": kernel_ms,
             "hbm": {"achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9,
                     "peak": hbm_peak, "unit": "GB/s",

@@ -25,7 +25,7 @@ class FsbStats(ctypes.Structure):
     _fields_ = [("kernel_ms", c_dbl), ("h2d_ms", c_dbl), ("d2h_ms", c_dbl),
                 ("n_iter_exec", c_i64), ("n_bla_steps", c_i64),
                 ("n_rebase", c_i64), ("sum_stop_iter", c_i64),
-                ("n_launches", c_i64)]
+                ("n_launches", c_i64), ("n_iter_fast", c_i64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -85,6 +85,9 @@ _libs = {}
 
 
 def lib_path(strict=False):
+    override = os.environ.get("FSB200_LIB")          # kernel A/B experiments
+    if override:
+        return override
     return os.path.join(_PKG, "libfsb200_strict.so" if strict else "libfsb200.so")
 
 

@@ -201,17 +201,18 @@ perturb_kernel_t pick_m2(bool xr, bool dc, bool dz, bool bla, bool extra, bool f
 {
     return xr ? pick_m2_dc<true>(dc, dz, bla, extra, fastxr) : pick_m2_dc<false>(dc, dz, bla, extra, fastxr);
 }
-template <bool XR, bool H> perturb_kernel_t pick_bs_bla(bool bla)
+template <bool XR, bool H> perturb_kernel_t pick_bs_bla(bool bla, bool fastxr)
 {
-    return bla ? k_perturb_bs<XR, H, true> : k_perturb_bs<XR, H, false>;
+    if (XR && fastxr) return bla ? k_perturb_bs<XR, H, true, XR> : k_perturb_bs<XR, H, false, XR>;
+    return bla ? k_perturb_bs<XR, H, true, false> : k_perturb_bs<XR, H, false, false>;
 }
-template <bool XR> perturb_kernel_t pick_bs_h(bool h, bool bla)
+template <bool XR> perturb_kernel_t pick_bs_h(bool h, bool bla, bool fastxr)
 {
-    return h ? pick_bs_bla<XR, true>(bla) : pick_bs_bla<XR, false>(bla);
+    return h ? pick_bs_bla<XR, true>(bla, fastxr) : pick_bs_bla<XR, false>(bla, fastxr);
 }
-perturb_kernel_t pick_bs(bool xr, bool h, bool bla)
+perturb_kernel_t pick_bs(bool xr, bool h, bool bla, bool fastxr)
 {
-    return xr ? pick_bs_h<true>(h, bla) : pick_bs_h<false>(h, bla);
+    return xr ? pick_bs_h<true>(h, bla, fastxr) : pick_bs_h<false>(h, bla, fastxr);
 }
 
 } /* namespace */
@@ -642,12 +643,14 @@ static void gather_stats(Ctx *c, int n_slots, fsb_stats *stats)
 {
     if (!stats) return;
     stats->n_iter_exec = stats->n_bla_steps = stats->n_rebase = stats->sum_stop_iter = 0;
+    stats->n_iter_fast = 0;
     for (int k = 0; k < n_slots; k++) {
         const unsigned long long *h = c->h_ctl + k * CTL_WORDS;
         stats->n_iter_exec += (int64_t)h[1];
         stats->n_bla_steps += (int64_t)h[2];
         stats->n_rebase += (int64_t)h[3];
         stats->sum_stop_iter += (int64_t)h[4];
+        stats->n_iter_fast += (int64_t)h[5];
     }
     stats->n_launches = n_slots;
 }
@@ -868,10 +871,25 @@ int fsb_frame_create(const fsb_frame_desc *desc, fsb_frame **out)
     }
     {
         const char *pure = getenv("FSB200_PURE_XR");
-        f->fast_xr = d.model == FSB_MODEL_M2 && d.xr_detect && !d.calc_dzndz
-                     && !(pure && pure[0] == '1');
+        f->fast_xr = d.xr_detect && !(pure && pure[0] == '1')
+                     && ((d.model == FSB_MODEL_M2 && !d.calc_dzndz)
+                         || (d.model == FSB_MODEL_BS && d.flavor <= 3));
     }
-    if (f->fast_xr && d.calc_dzndc) {
+    if (f->fast_xr && d.calc_dzndc && d.model == FSB_MODEL_BS) {
+        std::vector<double> m((size_t)(4 * L)), sd((size_t)(4 * L));
+        std::vector<int> me((size_t)(4 * L));
+        if (cudaMemcpy(m.data(), v.dP[0], (size_t)(4 * L * 8), cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemcpy(me.data(), v.dP_e[0], (size_t)(4 * L * 4), cudaMemcpyDeviceToHost) != cudaSuccess) {
+            fsb_frame_destroy(f);
+            return fail(-1, "dZndc read-back failed");
+        }
+        for (long long i = 0; i < 4 * L; i++)
+            sd[(size_t)i] = xr_flushed_std(mkC(m[(size_t)i], 0.), me[(size_t)i]).re;
+        const double *dp = nullptr;
+        UP(upload(f, sd.data(), 4 * L, &dp));
+        for (int j = 0; j < 4; j++) v.dP_std[j] = dp + j * L;
+    }
+    if (f->fast_xr && d.calc_dzndc && d.model == FSB_MODEL_M2) {
         /* read the Xrange path back and build its flushed fp64 mirror */
         std::vector<C> m((size_t)L), sd((size_t)L);
         std::vector<int> me((size_t)L);
@@ -982,7 +1000,7 @@ static int frame_enqueue(Ctx *c, fsb_frame *f, cudaStream_t st, int slot, long l
     perturb_kernel_t k = (d.model == FSB_MODEL_M2)
         ? pick_m2(d.xr_detect != 0, d.calc_dzndc != 0, d.calc_dzndz != 0, f->bla_on,
                   f->dev.order_i > 0 || d.calc_orbit != 0, f->fast_xr)
-        : pick_bs(d.xr_detect != 0, d.calc_dzndc != 0, f->bla_on);
+        : pick_bs(d.xr_detect != 0, d.calc_dzndc != 0, f->bla_on, f->fast_xr);
     unsigned long long *ctl = c->d_ctl + slot * CTL_WORDS;
     CK(cudaMemsetAsync(ctl, 0, CTL_WORDS * sizeof(unsigned long long), st));
     const int block = 128;

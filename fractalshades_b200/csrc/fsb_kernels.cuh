@@ -35,6 +35,7 @@ struct FrameDev {
     const C *ref_xr; const int *ref_xr_e;
     /* burning ship family */
     const double *dP[4]; const int *dP_e[4];
+    const double *dP_std[4];   /* Xrange frames: flushed fp64 mirrors (fast path) */
     const double *refx_xr; const int *refx_xr_e;
     const double *refy_xr; const int *refy_xr_e;
     long long n_xr; const int *ref_index_xr;
@@ -82,19 +83,22 @@ __device__ __forceinline__ void add_counters(unsigned long long *counters,
                                              unsigned long long c0,
                                              unsigned long long c1,
                                              unsigned long long c2,
-                                             unsigned long long c3)
+                                             unsigned long long c3,
+                                             unsigned long long c4 = 0)
 {
     for (int o = 16; o > 0; o >>= 1) {
         c0 += __shfl_down_sync(0xffffffffu, c0, o);
         c1 += __shfl_down_sync(0xffffffffu, c1, o);
         c2 += __shfl_down_sync(0xffffffffu, c2, o);
         c3 += __shfl_down_sync(0xffffffffu, c3, o);
+        c4 += __shfl_down_sync(0xffffffffu, c4, o);
     }
     if ((threadIdx.x & 31) == 0) {
         atomicAdd(counters + 0, c0);
         atomicAdd(counters + 1, c1);
         atomicAdd(counters + 2, c2);
         atomicAdd(counters + 3, c3);
+        if (c4) atomicAdd(counters + 4, c4);
     }
 }
 
@@ -400,7 +404,7 @@ k_perturb_m2(const __grid_constant__ FrameDev f, long long npts_ll,
              int *__restrict__ stop_iter, unsigned long long *work,
              unsigned long long *counters, const volatile int *abort_flag)
 {
-    unsigned long long n_exec = 0, n_bla = 0, n_reb = 0, n_sum = 0;
+    unsigned long long n_exec = 0, n_bla = 0, n_reb = 0, n_sum = 0, n_fast = 0;
     const int L = f.Li;
     const bool has_xr = f.n_xr_i > 0;
     const int ref_div_iter = f.ref_div_i;
@@ -440,7 +444,7 @@ k_perturb_m2(const __grid_constant__ FrameDev f, long long npts_ll,
         XC zn_x = to_xr(zn), dzndc_x = zn_x, dzndz_x = zn_x;
 
         int w_iter = 0, n_iter = 0;
-        unsigned int p_exec = 0, p_bla = 0, p_reb = 0;
+        unsigned int p_exec = 0, p_bla = 0, p_reb = 0, p_fast = 0;
         int div_shift = 0, orbit_i1 = 0, orbit_i2 = 0;
         C orbit_zn1 = zn, orbit_zn2 = zn;
         C ref_cur = Zn0;                      /* always Zn[w_iter] */
@@ -509,6 +513,7 @@ k_perturb_m2(const __grid_constant__ FrameDev f, long long npts_ll,
                     zn = nzn;
                     if (DZNDC) dzndc = ndz;
                     done_fast = true;
+                    p_fast++;
                 } else {          /* redo this iteration in Xrange arithmetic */
                     zn_x = to_xr(zn);
                     if (DZNDC) dzndc_x = to_xr(dzndc);
@@ -598,6 +603,7 @@ k_perturb_m2(const __grid_constant__ FrameDev f, long long npts_ll,
                 bool_dyn_rebase = (fabs(ZZ.re) <= fabs(zn.re)) && (fabs(ZZ.im) <= fabs(zn.im));
                 do_rebase = bool_dyn_rebase;
                 if (XR && bool_dyn_rebase) {
+
                     if (FASTXR && fast && in_fast_range(ZZ)) {
                         /* same comparison on the same correctly rounded values */
                         do_rebase = norm2(ZZ) <= norm2(zn);
@@ -687,16 +693,30 @@ k_perturb_m2(const __grid_constant__ FrameDev f, long long npts_ll,
         stop_reason[ipt] = (signed char)stop;
         stop_iter[ipt] = n_iter;
         n_sum += (unsigned long long)n_iter;
-        n_exec += p_exec; n_bla += p_bla; n_reb += p_reb;
+        n_exec += p_exec; n_bla += p_bla; n_reb += p_reb; n_fast += p_fast;
     }
 #undef DZNDC_X
 #undef DZNDZ_X
 #undef REF_X
-    add_counters(counters, n_exec, n_bla, n_reb, n_sum);
+    add_counters(counters, n_exec, n_bla, n_reb, n_sum, n_fast);
 }
 
 /* ======================================================================== */
 /* Burning-ship family perturbation                                          */
+
+/* burning_ship.py:82-122, as called from the perturbation loop's orbit
+ * back-shift (perturbation.py:1778-1787) */
+__device__ __forceinline__ void bs_iterate_perturb(int flavor, double xn, double yn, double a,
+                                                   double b, double &ox, double &oy)
+{
+    switch (flavor) {
+    case 1: ox = xn * xn - yn * yn + a; oy = 2. * fabs(xn * yn) - b; break;
+    case 2: ox = xn * xn - yn * yn + a; oy = 2. * xn * fabs(yn) - b; break;
+    case 3: ox = xn * xn - yn * fabs(yn) + a; oy = 2. * xn * yn - b; break;
+    case 4: ox = fabs(xn * xn - yn * yn) + a; oy = 2. * xn * yn - b; break;
+    default: ox = fabs(xn * xn - yn * yn) + a; oy = 2. * fabs(xn * yn) - b; break;
+    }
+}
 
 /* burning_ship.py:19-60 */
 template <class T> __device__ __forceinline__ T diffabs(T X, T x)
@@ -863,31 +883,48 @@ __device__ __forceinline__ void apply_bla_deriv_bs(const double *M, T &dxa, T &d
     dxa = a; dxb = b; dya = c; dyb = d;
 }
 
-template <bool XR, bool HESS, bool BLA>
+/* FASTXR: guarded fp64 fast path as in k_perturb_m2, enabled by the host for
+ * flavours 1-3 only.  On top of the result guard it requires the reference
+ * values themselves to be in range: the sign tests of diffabs() must see
+ * products that cannot underflow (flavours 4-5 multiply a possibly cancelled
+ * sum and are left on the exact Xrange path). */
+template <bool XR, bool HESS, bool BLA, bool FASTXR = false>
 __global__ void __launch_bounds__(128)
-k_perturb_bs(FrameDev f, long long npts, const C *__restrict__ c_pix,
-             double *__restrict__ Z, int *__restrict__ U,
-             signed char *__restrict__ stop_reason, int *__restrict__ stop_iter,
-             unsigned long long *work, unsigned long long *counters,
-             const volatile int *abort_flag)
+k_perturb_bs(const __grid_constant__ FrameDev f, long long npts_ll,
+             const C *__restrict__ c_pix, double *__restrict__ Z,
+             int *__restrict__ U, signed char *__restrict__ stop_reason,
+             int *__restrict__ stop_iter, unsigned long long *work,
+             unsigned long long *counters, const volatile int *abort_flag)
 {
-    unsigned long long n_exec = 0, n_bla = 0, n_reb = 0, n_sum = 0;
-    const long long L = f.L;
-    const bool has_xr = f.n_xr > 0;
+    unsigned long long n_exec = 0, n_bla = 0, n_reb = 0, n_sum = 0, n_fast = 0;
+    const int L = f.Li;
+    const bool has_xr = f.n_xr_i > 0;
     const int flavor = f.flavor;
-    const long long ref_order = f.ref_order, ref_div_iter = f.ref_div_iter;
-    long long first_invalid = L;
-    if (ref_div_iter < first_invalid) first_invalid = ref_div_iter;
-    if (ref_order < first_invalid) first_invalid = ref_order;
+    const int ref_div_iter = f.ref_div_i;
+    const int max_iter = f.max_iter_i;
+    const int first_invalid = f.first_invalid_i;
+    const bool cyc = f.order_i > 0;
+    const int order = f.order_i;
     const XF record_zero = mkXF(0., 0);
+    const C *__restrict__ Zn = f.Zn;
+    const C Zn0 = ldC(Zn, 0);
+    const int npts = (int)npts_ll;
+    (void)L;
 
 #define D_X(j, i) mkXF(__ldg(f.dP[j] + (i)), __ldg(f.dP_e[j] + (i)))
 #define D_S(j, i) __ldg(f.dP[j] + (i))
+#define D_F(j, i) __ldg(f.dP_std[j] + (i))
+#define TO_XR6() do { x_x = to_xr(x); y_x = to_xr(y); if (HESS) { dxa_x = to_xr(dxa); \
+        dxb_x = to_xr(dxb); dya_x = to_xr(dya); dyb_x = to_xr(dyb); } } while (0)
+#define TRY_FAST() do { fast = in_fast_range(x) && in_fast_range(y); \
+        if (HESS && fast) { dxa = to_std(dxa_x); dxb = to_std(dxb_x); dya = to_std(dya_x); \
+            dyb = to_std(dyb_x); fast = in_fast_range(dxa) && in_fast_range(dxb) \
+                && in_fast_range(dya) && in_fast_range(dyb); } } while (0)
 
     for (;;) {
         long long base = grab32(work, abort_flag);
-        if (base < 0 || base >= npts) break;
-        long long ipt = base + (threadIdx.x & 31);
+        if (base < 0 || base >= npts_ll) break;
+        const int ipt = (int)base + (threadIdx.x & 31);
         if (ipt >= npts) continue;
 
         /* perturbation.py:2260-2280 */
@@ -905,17 +942,20 @@ k_perturb_bs(FrameDev f, long long npts, const C *__restrict__ c_pix,
         double x = 0., y = 0., dxa = 0., dxb = 0., dya = 0., dyb = 0.;
         XF x_x = to_xr(0.), y_x = x_x, dxa_x = x_x, dxb_x = x_x, dya_x = x_x, dyb_x = x_x;
 
-        long long w_iter = 0, n_iter = 0;
-        long long div_shift = 0, orbit_i1 = 0, orbit_i2 = 0;
+        int w_iter = 0, n_iter = 0;
+        unsigned int p_exec = 0, p_bla = 0, p_reb = 0, p_fast = 0;
+        int div_shift = 0, orbit_i1 = 0, orbit_i2 = 0;
         double oxn1 = 0., oxn2 = 0., oyn1 = 0., oyn2 = 0.;
+        C ref_cur = Zn0;                     /* always Zn[w_iter] */
         bool bool_dyn_rebase = true;
         int stop = -1;
+        bool fast = false;    /* FASTXR: state lives in the plain doubles */
 
         for (;;) {
             if (BLA && (w_iter & 7) == 0) {
                 int ib = 0;
-                const int step = ref_bla_get(f.r_bla, f.stages_bla, mkC(x, y), (int)w_iter,
-                                             (int)first_invalid, ib);
+                const int step = ref_bla_get(f.r_bla, f.stages_bla, mkC(x, y), w_iter,
+                                             first_invalid, ib);
                 if (step != 0) {
                     double M[8];
                     const double2 *Mp = reinterpret_cast<const double2 *>(f.M_bla + 8 * (long long)ib);
@@ -925,79 +965,118 @@ k_perturb_bs(FrameDev f, long long npts, const C *__restrict__ c_pix,
                         M[2 * q] = v.x; M[2 * q + 1] = v.y;
                     }
                     n_iter += step;
-                    w_iter = (w_iter + step) % ref_order;
+                    w_iter += step;
+                    if (cyc) w_iter = w_iter % order;
+                    ref_cur = ldC(Zn, w_iter);
                     if (XR) {
+                        if (FASTXR && fast) TO_XR6();      /* M * (a, b) needs the exact a, b */
                         apply_bla_bs(M, x_x, y_x, a_x, b_x);
                         x = to_std(x_x);
                         y = to_std(y_x);
                         if (HESS) apply_bla_deriv_bs(M, dxa_x, dxb_x, dya_x, dyb_x);
+                        if (FASTXR) TRY_FAST();
                     } else {
                         apply_bla_bs(M, x, y, a, b);
                         if (HESS) apply_bla_deriv_bs(M, dxa, dxb, dya, dyb);
                     }
-                    n_bla++;
+                    p_bla++;
                     continue;
                 }
             }
 
             n_iter += 1;
-            n_exec++;
-            C ref_zn = ldC(f.Zn, w_iter);
-            XF rx_x = record_zero, ry_x = record_zero;
-            if (XR) {
-                long long k = -1;
-                if (has_xr && w_iter != 0 && (fabs(ref_zn.re) < 1.e-300 || fabs(ref_zn.im) < 1.e-300))
-                    k = xr_find(f.ref_index_xr, f.n_xr_i, (int)w_iter);
-                if (k >= 0) {
-                    rx_x = mkXF(__ldg(f.refx_xr + k), __ldg(f.refx_xr_e + k));
-                    ry_x = mkXF(__ldg(f.refy_xr + k), __ldg(f.refy_xr_e + k));
-                } else {
-                    rx_x = to_xr(ref_zn.re);
-                    ry_x = to_xr(ref_zn.im);
-                }
-            }
-            if (HESS) {
-                if (XR) {
-                    XF ra = record_zero, rb = record_zero, rc = record_zero, rd = record_zero;
-                    if (!bool_dyn_rebase) {
-                        ra = D_X(0, w_iter); rb = D_X(1, w_iter);
-                        rc = D_X(2, w_iter); rd = D_X(3, w_iter);
-                    }
-                    bs_p_iter_hessian(flavor, x_x, y_x, dxa_x, dxb_x, dya_x, dyb_x,
-                                      rx_x, ry_x, ra, rb, rc, rd);
-                } else {
+            p_exec++;
+            const C ref_zn = ref_cur;
+            int k = -1;
+            if (XR && has_xr && w_iter != 0 && (fabs(ref_zn.re) < 1.e-300 || fabs(ref_zn.im) < 1.e-300))
+                k = xr_find(f.ref_index_xr, f.n_xr_i, w_iter);
+
+            bool done_fast = false;
+            if (XR && FASTXR && fast && k < 0 && in_fast_range(ref_zn.re) && in_fast_range(ref_zn.im)) {
+                double ndxa = dxa, ndxb = dxb, ndya = dya, ndyb = dyb, nx = x, ny = y;
+                if (HESS) {
                     double ra = 0., rb = 0., rc = 0., rd = 0.;
                     if (!bool_dyn_rebase) {
-                        ra = D_S(0, w_iter); rb = D_S(1, w_iter);
-                        rc = D_S(2, w_iter); rd = D_S(3, w_iter);
+                        ra = D_F(0, w_iter); rb = D_F(1, w_iter);
+                        rc = D_F(2, w_iter); rd = D_F(3, w_iter);
                     }
-                    bs_p_iter_hessian(flavor, x, y, dxa, dxb, dya, dyb, ref_zn.re,
+                    bs_p_iter_hessian(flavor, x, y, ndxa, ndxb, ndya, ndyb, ref_zn.re,
                                       ref_zn.im, ra, rb, rc, rd);
                 }
+                bs_p_iter_zn(flavor, nx, ny, ref_zn.re, ref_zn.im, a, b);
+                bool ok = in_fast_range(nx) && in_fast_range(ny);
+                if (HESS) ok = ok && in_fast_range(ndxa) && in_fast_range(ndxb)
+                               && in_fast_range(ndya) && in_fast_range(ndyb);
+                if (ok) {
+                    x = nx; y = ny;
+                    if (HESS) { dxa = ndxa; dxb = ndxb; dya = ndya; dyb = ndyb; }
+                    done_fast = true;
+                    p_fast++;
+                } else {
+                    TO_XR6();
+                    fast = false;
+                }
+            } else if (XR && FASTXR && fast) {
+                TO_XR6();
+                fast = false;
             }
-            if (XR) {
-                bs_p_iter_zn(flavor, x_x, y_x, rx_x, ry_x, a_x, b_x);
-                x = to_std(x_x);
-                y = to_std(y_x);
-            } else {
-                bs_p_iter_zn(flavor, x, y, ref_zn.re, ref_zn.im, a, b);
+
+            if (!done_fast) {
+                XF rx_x = record_zero, ry_x = record_zero;
+                if (XR) {
+                    if (k >= 0) {
+                        rx_x = mkXF(__ldg(f.refx_xr + k), __ldg(f.refx_xr_e + k));
+                        ry_x = mkXF(__ldg(f.refy_xr + k), __ldg(f.refy_xr_e + k));
+                    } else {
+                        rx_x = to_xr(ref_zn.re);
+                        ry_x = to_xr(ref_zn.im);
+                    }
+                }
+                if (HESS) {
+                    if (XR) {
+                        XF ra = record_zero, rb = record_zero, rc = record_zero, rd = record_zero;
+                        if (!bool_dyn_rebase) {
+                            ra = D_X(0, w_iter); rb = D_X(1, w_iter);
+                            rc = D_X(2, w_iter); rd = D_X(3, w_iter);
+                        }
+                        bs_p_iter_hessian(flavor, x_x, y_x, dxa_x, dxb_x, dya_x, dyb_x,
+                                          rx_x, ry_x, ra, rb, rc, rd);
+                    } else {
+                        double ra = 0., rb = 0., rc = 0., rd = 0.;
+                        if (!bool_dyn_rebase) {
+                            ra = D_S(0, w_iter); rb = D_S(1, w_iter);
+                            rc = D_S(2, w_iter); rd = D_S(3, w_iter);
+                        }
+                        bs_p_iter_hessian(flavor, x, y, dxa, dxb, dya, dyb, ref_zn.re,
+                                          ref_zn.im, ra, rb, rc, rd);
+                    }
+                }
+                if (XR) {
+                    bs_p_iter_zn(flavor, x_x, y_x, rx_x, ry_x, a_x, b_x);
+                    x = to_std(x_x);
+                    y = to_std(y_x);
+                    if (FASTXR) TRY_FAST();
+                } else {
+                    bs_p_iter_zn(flavor, x, y, ref_zn.re, ref_zn.im, a, b);
+                }
             }
 
             /* max_iter test BEFORE w_iter += 1 (perturbation.py:1616-1625) */
-            if (n_iter >= f.max_iter) { stop = 0; break; }
+            if (n_iter >= max_iter) { stop = 0; break; }
 
             w_iter += 1;
-            if (w_iter >= ref_order) w_iter = w_iter % ref_order;
+            if (cyc && w_iter >= order) w_iter = w_iter % order;
 
-            C ref_next = ldC(f.Zn, w_iter);
-            long long knext = -1;
+            const C ref_next = ldC(Zn, w_iter);
+            ref_cur = ref_next;
+            int knext = -1;
             if (XR && has_xr && w_iter != 0
                 && (fabs(ref_next.re) < 1.e-300 || fabs(ref_next.im) < 1.e-300))
-                knext = xr_find(f.ref_index_xr, f.n_xr_i, (int)w_iter);
-            double XX = x + ref_next.re, YY = y + ref_next.im;
-            double full_sq_norm = XX * XX + YY * YY;
+                knext = xr_find(f.ref_index_xr, f.n_xr_i, w_iter);
+            const double XX = x + ref_next.re, YY = y + ref_next.im;
+            const double full_sq_norm = XX * XX + YY * YY;
             if (f.calc_orbit) {
-                long long div = n_iter / f.backshift;
+                int div = n_iter / (int)f.backshift;
                 if (div > div_shift) {
                     div_shift = div;
                     orbit_i2 = orbit_i1; oxn2 = oxn1; oyn2 = oyn1;
@@ -1006,44 +1085,88 @@ k_perturb_bs(FrameDev f, long long npts, const C *__restrict__ c_pix,
             }
             if (full_sq_norm > f.Mdiv_sq) { stop = 1; break; }
 
+            /* rebase: reference diverging (perturbation.py:1662-1686) */
             if (w_iter >= ref_div_iter - 1) {
-                x = XX; y = YY;
-                if (XR) {
-                    x_x = to_xr(XX); y_x = to_xr(YY);
-                    if (HESS) {
-                        dxa_x = dxa_x + D_X(0, w_iter); dxb_x = dxb_x + D_X(1, w_iter);
-                        dya_x = dya_x + D_X(2, w_iter); dyb_x = dyb_x + D_X(3, w_iter);
-                    }
-                } else if (HESS) {
-                    dxa += D_S(0, w_iter); dxb += D_S(1, w_iter);
-                    dya += D_S(2, w_iter); dyb += D_S(3, w_iter);
-                }
-                w_iter = 0;
-                n_reb++;
-                continue;
-            }
-
-            bool_dyn_rebase = (fabs(XX) <= fabs(x)) && (fabs(YY) <= fabs(y));
-            if (bool_dyn_rebase) {
-                if (XR) {
-                    XF XXx, YYx;
-                    if (knext >= 0) {
-                        XXx = x_x + mkXF(__ldg(f.refx_xr + knext), __ldg(f.refx_xr_e + knext));
-                        YYx = y_x + mkXF(__ldg(f.refy_xr + knext), __ldg(f.refy_xr_e + knext));
+                if (XR && FASTXR && fast) {
+                    double na = dxa, nb = dxb, nc = dya, nd = dyb;
+                    if (HESS) { na += D_F(0, w_iter); nb += D_F(1, w_iter); nc += D_F(2, w_iter); nd += D_F(3, w_iter); }
+                    bool ok = in_fast_range(XX) && in_fast_range(YY);
+                    if (HESS) ok = ok && in_fast_range(na) && in_fast_range(nb) && in_fast_range(nc) && in_fast_range(nd);
+                    if (ok) {
+                        x = XX; y = YY;
+                        if (HESS) { dxa = na; dxb = nb; dya = nc; dyb = nd; }
                     } else {
-                        XXx = x_x + ref_next.re;
-                        YYx = y_x + ref_next.im;
+                        TO_XR6();
+                        fast = false;
                     }
-                    if (xr_le(XXx * XXx + YYx * YYx, x_x * x_x + y_x * y_x)) {
-                        x_x = XXx; y_x = YYx;
-                        x = to_std(XXx); y = to_std(YYx);
+                }
+                if (!(XR && FASTXR && fast)) {
+                    x = XX; y = YY;
+                    if (XR) {
+                        x_x = to_xr(XX); y_x = to_xr(YY);
                         if (HESS) {
                             dxa_x = dxa_x + D_X(0, w_iter); dxb_x = dxb_x + D_X(1, w_iter);
                             dya_x = dya_x + D_X(2, w_iter); dyb_x = dyb_x + D_X(3, w_iter);
                         }
-                        w_iter = 0;
-                        n_reb++;
-                        continue;
+                        if (FASTXR) TRY_FAST();
+                    } else if (HESS) {
+                        dxa += D_S(0, w_iter); dxb += D_S(1, w_iter);
+                        dya += D_S(2, w_iter); dyb += D_S(3, w_iter);
+                    }
+                }
+                w_iter = 0;
+                ref_cur = Zn0;
+                p_reb++;
+                continue;
+            }
+
+            /* rebase: dynamic glitch (perturbation.py:1690-1744) */
+            bool_dyn_rebase = (fabs(XX) <= fabs(x)) && (fabs(YY) <= fabs(y));
+            if (bool_dyn_rebase) {
+                if (XR) {
+                    bool handled = false;
+                    if (FASTXR && fast && in_fast_range(XX) && in_fast_range(YY)) {
+                        /* same comparison on the same correctly rounded values */
+                        if (XX * XX + YY * YY <= x * x + y * y) {
+                            double na = dxa, nb = dxb, nc = dya, nd = dyb;
+                            if (HESS) { na += D_F(0, w_iter); nb += D_F(1, w_iter); nc += D_F(2, w_iter); nd += D_F(3, w_iter); }
+                            bool ok = true;
+                            if (HESS) ok = in_fast_range(na) && in_fast_range(nb) && in_fast_range(nc) && in_fast_range(nd);
+                            if (ok) {
+                                x = XX; y = YY;
+                                if (HESS) { dxa = na; dxb = nb; dya = nc; dyb = nd; }
+                                w_iter = 0;
+                                ref_cur = Zn0;
+                                p_reb++;
+                                continue;
+                            }
+                        } else {
+                            handled = true;      /* no rebase, stay on the fast path */
+                        }
+                    }
+                    if (!handled) {
+                        if (FASTXR && fast) { TO_XR6(); fast = false; }
+                        XF XXx, YYx;
+                        if (knext >= 0) {
+                            XXx = x_x + mkXF(__ldg(f.refx_xr + knext), __ldg(f.refx_xr_e + knext));
+                            YYx = y_x + mkXF(__ldg(f.refy_xr + knext), __ldg(f.refy_xr_e + knext));
+                        } else {
+                            XXx = x_x + ref_next.re;
+                            YYx = y_x + ref_next.im;
+                        }
+                        if (xr_le(XXx * XXx + YYx * YYx, x_x * x_x + y_x * y_x)) {
+                            x_x = XXx; y_x = YYx;
+                            x = to_std(XXx); y = to_std(YYx);
+                            if (HESS) {
+                                dxa_x = dxa_x + D_X(0, w_iter); dxb_x = dxb_x + D_X(1, w_iter);
+                                dya_x = dya_x + D_X(2, w_iter); dyb_x = dyb_x + D_X(3, w_iter);
+                            }
+                            if (FASTXR) TRY_FAST();
+                            w_iter = 0;
+                            ref_cur = Zn0;
+                            p_reb++;
+                            continue;
+                        }
                     }
                 } else {
                     x = XX; y = YY;
@@ -1052,15 +1175,27 @@ k_perturb_bs(FrameDev f, long long npts, const C *__restrict__ c_pix,
                         dya += D_S(2, w_iter); dyb += D_S(3, w_iter);
                     }
                     w_iter = 0;
-                    n_reb++;
+                    ref_cur = Zn0;
+                    p_reb++;
                     continue;
                 }
             }
         }
 
-        U[ipt] = (int)w_iter;
-        C ref_zn = ldC(f.Zn, w_iter);
-        if (XR) {
+        U[ipt] = w_iter;
+        const C ref_zn = ldC(Zn, w_iter);
+        if (XR && FASTXR && fast) {
+            x += ref_zn.re; y += ref_zn.im;
+            if (HESS) {
+                const double ra = D_F(0, w_iter), rb = D_F(1, w_iter), rc = D_F(2, w_iter), rd = D_F(3, w_iter);
+                if (ra == ra && rb == rb && rc == rc && rd == rd) {
+                    dxa += ra; dxb += rb; dya += rc; dyb += rd;
+                } else {                      /* huge table entry: exact path */
+                    dxa = to_std(to_xr(dxa) + D_X(0, w_iter)); dxb = to_std(to_xr(dxb) + D_X(1, w_iter));
+                    dya = to_std(to_xr(dya) + D_X(2, w_iter)); dyb = to_std(to_xr(dyb) + D_X(3, w_iter));
+                }
+            }
+        } else if (XR) {
             x = to_std(x_x + ref_zn.re);
             y = to_std(y_x + ref_zn.im);
             if (HESS) {
@@ -1083,22 +1218,26 @@ k_perturb_bs(FrameDev f, long long npts, const C *__restrict__ c_pix,
         }
         if (f.calc_orbit) {
             double xo = oxn2, yo = oyn2;
-            C z1 = ldC(f.Zn, 1);
+            C z1 = ldC(Zn, 1);
             double AA = a + z1.re, BB = b + z1.im;
-            while (orbit_i2 < n_iter - f.backshift) {
+            while (orbit_i2 < n_iter - (int)f.backshift) {
                 double tx, ty;
-                bs_iterate(flavor, xo, yo, AA, BB, tx, ty);
+                bs_iterate_perturb(flavor, xo, yo, AA, BB, tx, ty);
                 xo = tx; yo = ty; orbit_i2 += 1;
             }
             Z[(row++) * f.zstride + ipt] = xo; Z[(row++) * f.zstride + ipt] = yo;
         }
         stop_reason[ipt] = (signed char)stop;
-        stop_iter[ipt] = (int)n_iter;
+        stop_iter[ipt] = n_iter;
         n_sum += (unsigned long long)n_iter;
+        n_exec += p_exec; n_bla += p_bla; n_reb += p_reb; n_fast += p_fast;
     }
 #undef D_X
 #undef D_S
-    add_counters(counters, n_exec, n_bla, n_reb, n_sum);
+#undef D_F
+#undef TO_XR6
+#undef TRY_FAST
+    add_counters(counters, n_exec, n_bla, n_reb, n_sum, n_fast);
 }
 
 /* ======================================================================== */

@@ -54,6 +54,7 @@ typedef struct fsb_stats {
     int64_t n_rebase;       /* rebases (both kinds)                              */
     int64_t sum_stop_iter;  /* sum over pixels of stop_iter (effective iters)    */
     int64_t n_launches;     /* kernels launched by this call                     */
+    int64_t n_iter_fast;    /* Xrange frames: iterations done on the fp64 fast path */
 } fsb_stats;
 
 /* ---- library / device ---------------------------------------------------- */

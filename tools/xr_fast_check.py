@@ -30,7 +30,7 @@ if __name__ == "__main__":
         run(sys.argv[2], int(sys.argv[3]), sys.argv[4], int(sys.argv[5]))
         sys.exit(0)
     nx = int(os.environ.get("NX", "1280"))
-    for workload in ("config3",):
+    for workload in os.environ.get("WORKLOADS", "config3,config4").split(","):
         for strict in (1, 0):
             d = tempfile.mkdtemp()
             outs = []
