@@ -138,14 +138,15 @@ int wait_event(Ctx *c, cudaEvent_t done, const volatile uint8_t *interrupted,
                bool *was_interrupted)
 {
     *was_interrupted = false;
-    static const int one = 1;
     for (;;) {
         cudaError_t q = cudaEventQuery(done);
         if (q == cudaSuccess) break;
         if (q != cudaErrorNotReady) CK(q);
         if (interrupted && *interrupted && !*was_interrupted) {
             *was_interrupted = true;
-            CK(cudaMemcpyAsync(c->d_abort(), &one, sizeof(int), cudaMemcpyHostToDevice, c->side));
+            c->h_ctl[MAX_CHUNKS * CTL_WORDS] = 1;      /* pinned source */
+            CK(cudaMemcpyAsync(c->d_abort(), c->h_ctl + MAX_CHUNKS * CTL_WORDS, sizeof(int),
+                               cudaMemcpyHostToDevice, c->side));
         }
         std::this_thread::sleep_for(std::chrono::microseconds(50));
     }
@@ -701,7 +702,11 @@ static int run_pipelined(Ctx *c, long long npts, const double *c_pix, long long 
     CK(cudaEventRecord(c->ev0, c->stream));
     CK(cudaStreamWaitEvent(c->s_alt, c->ev0, 0));
     CK(cudaStreamWaitEvent(c->s_d2h, c->ev0, 0));
-    for (int k = 0; k < ch.n; k++) {
+    /* Slab k+1 (H2D + kernel) is enqueued before the host waits for slab k, so
+     * the device never idles; the host polls the interruption flag while it
+     * waits (with pageable host buffers the "async" copies block the host, which
+     * is why the D2H of slab k is only issued once its kernel has finished). */
+    auto enqueue_slab = [&](int k) -> int {
         const long long a = ch.beg[k], n = ch.beg[k + 1] - a;
         CK(cudaMemcpyAsync(base + o_c + a * 16, c_pix + 2 * a, (size_t)(n * 16),
                            cudaMemcpyHostToDevice, c->s_h2d));
@@ -710,7 +715,15 @@ static int run_pipelined(Ctx *c, long long npts, const double *c_pix, long long 
         CK(cudaStreamWaitEvent(st, c->ev_h[k], 0));
         if (enqueue(st, k, n, a)) return -1;
         CK(cudaEventRecord(c->ev_k[k], st));
-        CK(cudaStreamWaitEvent(c->s_d2h, c->ev_k[k], 0));
+        return 0;
+    };
+    if (enqueue_slab(0)) return -1;
+    for (int k = 0; k < ch.n; k++) {
+        if (k + 1 < ch.n && enqueue_slab(k + 1)) return -1;
+        bool wi = false;
+        if (wait_event(c, c->ev_k[k], interrupted, &wi)) return -1;
+        *was_int = *was_int || wi;
+        const long long a = ch.beg[k], n = ch.beg[k + 1] - a;
         for (int r = 0; r < n_planes; r++)
             CK(cudaMemcpyAsync(planes[r].host + a * planes[r].elem,
                                base + planes[r].dev_off + a * planes[r].elem,
@@ -719,7 +732,6 @@ static int run_pipelined(Ctx *c, long long npts, const double *c_pix, long long 
     CK(cudaMemcpyAsync(c->h_ctl, c->d_ctl, (size_t)ch.n * CTL_WORDS * sizeof(unsigned long long),
                        cudaMemcpyDeviceToHost, c->s_d2h));
     CK(cudaEventRecord(c->ev1, c->s_d2h));
-    if (wait_event(c, c->ev1, interrupted, was_int)) return -1;
     CK(cudaStreamSynchronize(c->s_d2h));
     gather_stats(c, ch.n, stats);
     if (stats) {
