@@ -225,6 +225,7 @@ struct fsb_frame {
     int nz = 0;
     bool bla_on = false;
     bool fast_xr = false;     /* Xrange kernel with the guarded fp64 fast path */
+    bool gpu_scan = false;    /* dZndc path by the GPU affine scan (K6) */
     std::vector<void *> owned;
     double ms_upload = 0, ms_dzndc = 0, ms_bla = 0;
     long long dzndc_len = 0;
@@ -402,7 +403,7 @@ void host_dzndc_bs(const fsb_frame_desc &d, std::vector<double> &out, std::vecto
  * exact when every component is a normal double, 0 for components below the
  * normal range (they are below half an ulp of anything the fast path adds them
  * to), NaN when a component is too large (forces the exact fallback). */
-C xr_flushed_std(C m, int e)
+[[maybe_unused]] C xr_flushed_std(C m, int e)
 {
     double out[2];
     const double in[2] = {m.re, m.im};
@@ -470,6 +471,80 @@ int build_bla(fsb_frame *f)
     cudaEventDestroy(e1);
     f->dev.M_bla = (const double *)dM;
     f->dev.r_bla = (const double *)dr;
+    return 0;
+}
+
+template <class T> int dev_zeros(fsb_frame *f, long long n, T **dev)
+{
+    void *p = nullptr;
+    CK(cudaMalloc(&p, (size_t)(n * (long long)sizeof(T))));
+    f->owned.push_back(p);
+    CK(cudaMemset(p, 0, (size_t)(n * (long long)sizeof(T))));
+    *dev = (T *)p;
+    return 0;
+}
+
+/* K6: dZndc path of a holomorphic frame by a parallel affine scan on the GPU
+ * (default build; the -fmad=false build keeps the serial host loop, which is
+ * bit-exact with the oracle). */
+int gpu_dzndc_m2(fsb_frame *f)
+{
+    const fsb_frame_desc &d = f->d;
+    FrameDev &v = f->dev;
+    const long long L = d.L;
+    const long long valid = L < d.ref_div_iter ? L : d.ref_div_iter;
+    const long long n_elem = valid - 1;
+    C *dm = nullptr;
+    int *de = nullptr;
+    if (dev_zeros(f, L + 1, &dm)) return -1;
+    if (d.xr_detect && dev_zeros(f, L + 1, &de)) return -1;
+    v.dZndc = dm;
+    v.dZndc_e = de;
+    if (n_elem <= 0) return 0;
+    const XF scale = mkXF(d.scale_deriv, d.scale_deriv_e);
+    const long long n_thr = (n_elem + SCAN_E - 1) / SCAN_E;
+    const int n_blk = (int)((n_thr + SCAN_T - 1) / SCAN_T);
+    AffXC *thr_agg = nullptr, *blk_agg = nullptr;
+    CK(cudaMalloc(&thr_agg, (size_t)n_blk * SCAN_T * sizeof(AffXC)));
+    CK(cudaMalloc(&blk_agg, (size_t)n_blk * sizeof(AffXC)));
+    k_dzndc_scan_local<<<n_blk, SCAN_T>>>(v, n_elem, scale, thr_agg, blk_agg);
+    k_dzndc_scan_blocks<<<1, 1024>>>(n_blk, blk_agg);
+    k_dzndc_scan_apply<<<n_blk, SCAN_T>>>(v, n_elem, scale, thr_agg, blk_agg, dm, de,
+                                          d.xr_detect ? nullptr : dm, d.xr_detect ? 1 : 0);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    cudaFree(thr_agg);
+    cudaFree(blk_agg);
+    /* periodic reference: the wrapped value is stored at index 0
+     * (perturbation.py:2315-2334) */
+    const long long i = valid - 1;
+    if (i == d.ref_order - 1) {
+        const C *Zn = (const C *)d.Zn_path;
+        C last; int last_e = 0;
+        CK(cudaMemcpy(&last, dm + i, sizeof(C), cudaMemcpyDeviceToHost));
+        if (d.xr_detect) {
+            CK(cudaMemcpy(&last_e, de + i, sizeof(int), cudaMemcpyDeviceToHost));
+            XC w = (2. * Zn[i]) * mkXC(last, last_e) + scale;
+            CK(cudaMemcpy(dm, &w.m, sizeof(C), cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(de, &w.e, sizeof(int), cudaMemcpyHostToDevice));
+        } else {
+            C w = (2. * Zn[i]) * last + to_std(scale);
+            CK(cudaMemcpy(dm, &w, sizeof(C), cudaMemcpyHostToDevice));
+        }
+    }
+    return 0;
+}
+
+/* flushed fp64 mirror of an Xrange table, built on the device */
+int gpu_flush_mirror(fsb_frame *f, const double *m, const int *e, long long n, int comps,
+                     long long pad, const double **out)
+{
+    double *o = nullptr;
+    if (dev_zeros(f, (n + pad) * comps, &o)) return -1;
+    const long long tot = n * comps;
+    k_flush_mirror<<<(int)((tot + 255) / 256), 256>>>(n, m, e, comps, o);
+    CK(cudaGetLastError());
+    *out = o;
     return 0;
 }
 
@@ -857,11 +932,21 @@ int fsb_frame_create(const fsb_frame_desc *desc, fsb_frame **out)
 
     /* reference derivative paths */
     t0 = now_ms();
+    {
+#ifdef FSB_STRICT
+        f->gpu_scan = false;              /* serial host loop: bit-exact with the oracle */
+#else
+        const char *host = getenv("FSB200_HOST_DZNDC");
+        f->gpu_scan = d.model == FSB_MODEL_M2 && !(host && host[0] == '1');
+#endif
+    }
     if (d.calc_dzndc) {
         if (d.model == FSB_MODEL_M2) {
             if (d.dZndc) {
                 UP(upload(f, (const C *)d.dZndc, L, &v.dZndc, 1));
                 if (d.xr_detect) UP(upload(f, d.dZndc_e, L, &v.dZndc_e, 1));
+            } else if (f->gpu_scan) {
+                UP(gpu_dzndc_m2(f));
             } else {
                 std::vector<C> p; std::vector<int32_t> pe;
                 host_dzndc_m2(d, p, pe);
@@ -888,31 +973,16 @@ int fsb_frame_create(const fsb_frame_desc *desc, fsb_frame **out)
                          || (d.model == FSB_MODEL_BS && d.flavor <= 3));
     }
     if (f->fast_xr && d.calc_dzndc && d.model == FSB_MODEL_BS) {
-        std::vector<double> m((size_t)(4 * L)), sd((size_t)(4 * L));
-        std::vector<int> me((size_t)(4 * L));
-        if (cudaMemcpy(m.data(), v.dP[0], (size_t)(4 * L * 8), cudaMemcpyDeviceToHost) != cudaSuccess ||
-            cudaMemcpy(me.data(), v.dP_e[0], (size_t)(4 * L * 4), cudaMemcpyDeviceToHost) != cudaSuccess) {
-            fsb_frame_destroy(f);
-            return fail(-1, "dZndc read-back failed");
-        }
-        for (long long i = 0; i < 4 * L; i++)
-            sd[(size_t)i] = xr_flushed_std(mkC(m[(size_t)i], 0.), me[(size_t)i]).re;
         const double *dp = nullptr;
-        UP(upload(f, sd.data(), 4 * L, &dp));
+        UP(gpu_flush_mirror(f, v.dP[0], v.dP_e[0], 4 * L, 1, 0, &dp));
         for (int j = 0; j < 4; j++) v.dP_std[j] = dp + j * L;
     }
     if (f->fast_xr && d.calc_dzndc && d.model == FSB_MODEL_M2) {
-        /* read the Xrange path back and build its flushed fp64 mirror */
-        std::vector<C> m((size_t)L), sd((size_t)L);
-        std::vector<int> me((size_t)L);
-        if (cudaMemcpy(m.data(), v.dZndc, (size_t)(L * 16), cudaMemcpyDeviceToHost) != cudaSuccess ||
-            cudaMemcpy(me.data(), v.dZndc_e, (size_t)(L * 4), cudaMemcpyDeviceToHost) != cudaSuccess) {
-            fsb_frame_destroy(f);
-            return fail(-1, "dZndc read-back failed");
-        }
-        for (long long i = 0; i < L; i++) sd[(size_t)i] = xr_flushed_std(m[(size_t)i], me[(size_t)i]);
-        UP(upload(f, sd.data(), L, &v.dZndc_std, 1));
+        const double *dp = nullptr;
+        UP(gpu_flush_mirror(f, (const double *)v.dZndc, v.dZndc_e, L, 2, 1, &dp));
+        v.dZndc_std = (const C *)dp;
     }
+    CK(cudaDeviceSynchronize());
     if (d.calc_dzndz) {
         if (d.dZndz) {
             UP(upload(f, (const C *)d.dZndz, L + 1, &v.dZndz));

@@ -1396,6 +1396,154 @@ __global__ void k_bla_merge_bs(long long comp_len, int stg, double kc_std, doubl
 }
 
 /* ======================================================================== */
+/* K6: dZndc reference-derivative path as a parallel affine scan.
+ *
+ * Reference: numba_dZndc_path (perturbation.py:2282-2336), a serial recurrence
+ *     d[i] = a_i d[i-1] + s ,  a_i = dfdz(Z[i-1]) = 2 Z[i-1] ,  d[0] = 0
+ * over the stored orbit (s = dx, the derivative scale).  Each step is the
+ * affine map d -> a d + s; maps compose as (A2,B2)o(A1,B1) = (A2 A1, A2 B1 + B2),
+ * so the path is an inclusive prefix "product" of maps and d[i] is its B part.
+ * All arithmetic is Xrange (the products leave the fp64 range after a few
+ * thousand points).  Three launches: thread-serial chunks + block scan,
+ * scan of the block aggregates, apply.  The association order differs from
+ * the serial loop, so results agree with it to rounding (~1e-13 relative),
+ * not bit for bit: the -fmad=false build keeps the serial host loop. */
+struct AffXC { XC A, B; };
+__device__ __forceinline__ AffXC aff_compose(const AffXC &first, const AffXC &then)
+{
+    AffXC o;
+    o.A = then.A * first.A;
+    o.B = then.A * first.B + then.B;
+    return o;
+}
+__device__ __forceinline__ XC scan_coef(const FrameDev &f, long long j)
+{
+    /* a = 2 * Z[j], with the Xrange value for the sub-1e-300 orbit points */
+    const C z = ldC(f.Zn, j);
+    int k = -1;
+    if (f.n_xr_i > 0 && j != 0 && fabs(z.re) < 1.e-300 && fabs(z.im) < 1.e-300)
+        k = xr_find(f.ref_index_xr, f.n_xr_i, (int)j);
+    const XC rz = (k >= 0) ? mkXC(ldC(f.ref_xr, k), __ldg(f.ref_xr_e + k)) : to_xr(z);
+    return 2. * rz;
+}
+
+constexpr int SCAN_E = 8;        /* elements per thread */
+constexpr int SCAN_T = 256;      /* threads per block   */
+
+/* phase 1: per-thread serial composition, block-level inclusive scan of the
+ * thread aggregates (stored to thr_agg), block aggregate to blk_agg */
+__global__ void __launch_bounds__(SCAN_T)
+k_dzndc_scan_local(FrameDev f, long long n_elem, XF scale, AffXC *__restrict__ thr_agg,
+                   AffXC *__restrict__ blk_agg)
+{
+    __shared__ AffXC sh[SCAN_T];
+    const long long t = blockIdx.x * (long long)SCAN_T + threadIdx.x;
+    const long long j0 = t * SCAN_E;
+    AffXC acc;
+    acc.A = mkXC(mkC(1., 0.), 0);
+    acc.B = mkXC(mkC(0., 0.), 0);
+    for (int q = 0; q < SCAN_E; q++) {
+        const long long j = j0 + q;
+        if (j < n_elem) {
+            AffXC m;
+            m.A = scan_coef(f, j);
+            m.B = mkXC(mkC(scale.m, 0.), scale.e);
+            acc = aff_compose(acc, m);
+        }
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int off = 1; off < SCAN_T; off <<= 1) {
+        AffXC prev = acc;
+        const bool has = threadIdx.x >= off;
+        if (has) prev = sh[threadIdx.x - off];
+        __syncthreads();
+        if (has) { acc = aff_compose(prev, acc); sh[threadIdx.x] = acc; }
+        __syncthreads();
+    }
+    thr_agg[t] = acc;
+    if (threadIdx.x == SCAN_T - 1) blk_agg[blockIdx.x] = acc;
+}
+
+/* phase 2: one block turns the block aggregates into exclusive prefixes */
+__global__ void __launch_bounds__(1024)
+k_dzndc_scan_blocks(int n_blk, AffXC *__restrict__ blk_agg)
+{
+    __shared__ AffXC sh[1024];
+    const int per = (n_blk + 1023) / 1024;
+    const int b0 = threadIdx.x * per;
+    AffXC acc;
+    acc.A = mkXC(mkC(1., 0.), 0);
+    acc.B = mkXC(mkC(0., 0.), 0);
+    for (int q = 0; q < per; q++)
+        if (b0 + q < n_blk) acc = aff_compose(acc, blk_agg[b0 + q]);
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        AffXC prev = acc;
+        const bool has = threadIdx.x >= off;
+        if (has) prev = sh[threadIdx.x - off];
+        __syncthreads();
+        if (has) { acc = aff_compose(prev, acc); sh[threadIdx.x] = acc; }
+        __syncthreads();
+    }
+    /* exclusive prefix of this thread's first block */
+    AffXC ex;
+    ex.A = mkXC(mkC(1., 0.), 0);
+    ex.B = mkXC(mkC(0., 0.), 0);
+    if (threadIdx.x > 0) ex = sh[threadIdx.x - 1];
+    for (int q = 0; q < per; q++) {
+        if (b0 + q < n_blk) {
+            const AffXC own = blk_agg[b0 + q];
+            blk_agg[b0 + q] = ex;
+            ex = aff_compose(ex, own);
+        }
+    }
+}
+
+/* phase 3: d at the start of each thread's chunk = B of (block prefix o thread
+ * prefix) applied to d[0] = 0; then the serial recurrence over the chunk */
+__global__ void __launch_bounds__(SCAN_T)
+k_dzndc_scan_apply(FrameDev f, long long n_elem, XF scale, const AffXC *__restrict__ thr_agg,
+                   const AffXC *__restrict__ blk_ex, C *__restrict__ out_m,
+                   int *__restrict__ out_e, C *__restrict__ out_std, int write_e)
+{
+    const long long t = blockIdx.x * (long long)SCAN_T + threadIdx.x;
+    const long long j0 = t * SCAN_E;
+    if (j0 >= n_elem) return;
+    AffXC pre = blk_ex[blockIdx.x];
+    if (threadIdx.x > 0) pre = aff_compose(pre, thr_agg[t - 1]);
+    XC d = pre.B;                         /* = d[j0] */
+    const XC s = mkXC(mkC(scale.m, 0.), scale.e);
+    for (int q = 0; q < SCAN_E; q++) {
+        const long long j = j0 + q;
+        if (j >= n_elem) break;
+        d = scan_coef(f, j) * d + s;      /* d[j + 1] */
+        if (write_e) { out_m[j + 1] = d.m; out_e[j + 1] = d.e; }
+        if (out_std) out_std[j + 1] = to_std(d);
+    }
+}
+
+/* flushed fp64 mirror of an Xrange table (fast path of the Xrange kernels):
+ * exact for normal components, 0 below the normal range, NaN when too large */
+__device__ __forceinline__ double flush_component(double m, int e)
+{
+    if (m == 0.) return 0.;
+    double nm; int ne;
+    normalize_real(m, e, nm, ne);
+    if (!(m == m) || ne > 1000) return mk64(0x7ff80000, 0);
+    if (ne < -1022) return 0.;
+    return ldexp(nm, ne);
+}
+__global__ void k_flush_mirror(long long n, const double *__restrict__ m, const int *__restrict__ e,
+                               int comps, double *__restrict__ out)
+{
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n * comps) return;
+    out[i] = flush_component(m[i], e[i / comps]);
+}
+
+/* ======================================================================== */
 /* Unit-test and calibration kernels                                         */
 __global__ void k_xr_binop_c(int op, long long n, const C *a, const int *ae, const C *b,
                              const int *be, C *out, int *oute)
