@@ -20,6 +20,7 @@ the frame into one launch (tiles are consecutive 1-D slabs of the memmaps, so
 a batch is a single contiguous range) and the persistent kernel load-balances
 at warp granularity.
 """
+import concurrent.futures
 import inspect
 import fnmatch
 import functools
@@ -536,6 +537,39 @@ class Fractal:
                 delattr(self, temp_attr)
 
     # -- the tile loop ---------------------------------------------------------
+    def _staging(self, npts, n_Z, n_U, complex_type):
+        """ Page-locked host staging buffers for one batch (kept and reused). """
+        key = (n_Z, max(n_U, 1), np.dtype(complex_type).str)
+        cur = getattr(self, "_staging_bufs", None)
+        if cur is not None and cur["key"] == key and cur["cap"] >= npts:
+            if cur["cap"] == npts:
+                return cur
+        if cur is not None and (cur["key"] != key or cur["cap"] < npts):
+            self._free_staging()
+            cur = None
+        if cur is None:
+            cur = {"key": key, "cap": npts,
+                   "c_pix": _native.pinned_empty((npts,), np.complex128),
+                   "Z": _native.pinned_empty((n_Z, npts), complex_type),
+                   "U": _native.pinned_empty((max(n_U, 1), npts), np.int32),
+                   "stop_reason": _native.pinned_empty((1, npts), np.int8),
+                   "stop_iter": _native.pinned_empty((1, npts), np.int32)}
+            self._staging_bufs = cur
+        return cur
+
+    def _free_staging(self):
+        cur = getattr(self, "_staging_bufs", None)
+        if cur is not None:
+            for k in ("c_pix", "Z", "U", "stop_reason", "stop_iter"):
+                _native.pinned_free(cur[k])
+            self._staging_bufs = None
+
+    def __del__(self):
+        try:
+            self._free_staging()
+        except Exception:
+            pass
+
     def calc_raw(self, calc_name, tile_validator=None):
         """ core.py:2724-2736 """
         if self._calc_data[calc_name]["need_new_mmap"]:
@@ -576,17 +610,31 @@ class Fractal:
         def flush(batch):
             if not batch or self.is_interrupted():
                 return
-            c_list, sizes = [], []
-            for rank, cs in batch:
-                (dep, _) = self.get_cycling_dep_args(calc_name, cs)
-                c_list.append(dep[0])
-                sizes.append(dep[0].shape[0])
-            c_pix = np.ascontiguousarray(np.concatenate(c_list))
-            npts = c_pix.shape[0]
-            Z = np.zeros([n_Z, npts], dtype=state.complex_type)
-            U = np.zeros([n_U, npts], dtype=self.int_type)
-            stop_reason = - np.ones([1, npts], dtype=self.termination_type)
-            stop_iter = np.zeros([1, npts], dtype=self.int_type)
+            sizes = [int(report[rank, self.REPORT_ITEMS.index("chunk_pts")])
+                     for rank, cs in batch]
+            npts = int(sum(sizes))
+            if npts == 0:
+                return
+            # page-locked staging buffers (reused across batches / frames): the
+            # H2D / D2H copies of the slab pipeline then run at full PCIe speed
+            bufs = self._staging(npts, n_Z, n_U, state.complex_type)
+            c_pix = bufs["c_pix"][:npts]
+            Z = bufs["Z"][:, :npts] if npts == bufs["cap"] else None
+            off = 0
+            for (rank, cs), n in zip(batch, sizes):
+                pix = np.ravel(self.chunk_pixel_pos(cs, False, None))
+                if state.subset is not None:
+                    pix = pix[np.asarray(state.subset[cs], dtype=bool)]
+                c_pix[off:off + n] = pix
+                off += n
+            if Z is None:        # batch smaller than the staging capacity
+                Z = np.zeros([n_Z, npts], dtype=state.complex_type)
+                U = np.zeros([n_U, npts], dtype=self.int_type)
+                stop_reason = - np.ones([1, npts], dtype=self.termination_type)
+                stop_iter = np.zeros([1, npts], dtype=self.int_type)
+            else:
+                U = bufs["U"][:n_U]
+                stop_reason, stop_iter = bufs["stop_reason"], bufs["stop_iter"]
             ret = self.numba_cycle_call((c_pix, Z, U, stop_reason, stop_iter), indep)
             for k, v in (getattr(Fractal, "_last_stats", None) or {}).items():
                 stats_acc[k] = stats_acc.get(k, 0) + v
@@ -597,16 +645,38 @@ class Fractal:
             mm = {k: self.get_data_memmap(calc_name, k, mode="r+")
                   for k in self.SAVE_ARRS}
             rep = self.get_report_memmap(calc_name, mode="r+")
-            off = 0
+            # tiles of consecutive ranks are consecutive slabs: group them into
+            # contiguous runs and copy each run of each field in one go, the
+            # copies spread over a few threads (numpy releases the GIL)
+            runs, off = [], 0
             for (rank, cs), n in zip(batch, sizes):
                 beg, end = int(rep[rank, 0]), int(rep[rank, 1])
                 assert end - beg == n
+                if runs and runs[-1][1] == beg:
+                    runs[-1][1] = end
+                else:
+                    runs.append([beg, end, off])
+                off += n
+            jobs = []
+            step = 1 << 20
+            for beg, end, o in runs:
                 for key in self.SAVE_ARRS:
                     for field, f_field in enumerate(rows[key]):
-                        mm[key][field, beg:end] = arrs[key][f_field, off:off + n]
-                off += n
-            for m in mm.values():
-                m.flush()
+                        for a0 in range(0, end - beg, step):
+                            a1 = min(a0 + step, end - beg)
+                            jobs.append((mm[key], field, beg + a0, beg + a1,
+                                         arrs[key], f_field, o + a0, o + a1))
+
+            def copy(job):
+                dst, field, b0, b1, src, f_field, s0, s1 = job
+                dst[field, b0:b1] = src[f_field, s0:s1]
+            if len(jobs) > 4 and settings.enable_multithreading:
+                with concurrent.futures.ThreadPoolExecutor(
+                        max_workers=min(8, os.cpu_count() or 1)) as pool:
+                    list(pool.map(copy, jobs))
+            else:
+                for job in jobs:
+                    copy(job)
             for rank, cs in batch:
                 rep[rank, done_col] = 1
             rep.flush()
