@@ -252,7 +252,9 @@ class PerturbationFractal(Fractal):
                  and FP["max_iter"] >= self.max_iter
                  and all(init_kwargs.get(k) == v
                          for k, v in FP["init_kwargs"].items())
-                 and FP.get("xr_detect", None) == self.xr_detect_activated)
+                 # an orbit registered with its Xrange points serves shallower
+                 # frames too (zoom movies); the converse does not hold
+                 and (bool(FP.get("xr_detect", False)) or not self.xr_detect_activated))
         return bool(match)
 
     def save_ref_point(self, FP_params, Zn_path):
