@@ -334,29 +334,42 @@ __device__ __forceinline__ long long bla_index64(long long i, int stg)
 }
 
 /* perturbation.py:2116-2170.  Returns the step (0 = no BLA applicable) and
- * the node index.  All orbit indices fit 32 bits (the host checks it). */
+ * the node index.  All orbit indices fit 32 bits (the host checks it).
+ *
+ * The reference walks the stages from the highest admissible one down and
+ * takes the first node with |z| < r.  A merged node's radius is
+ * min(r_first_half, ...) (perturbation.py:2021), so along one start index the
+ * radii never grow with the stage (and a NaN radius stays NaN upwards): a point
+ * that fails the lowest stored stage fails them all.  That stage is tested
+ * first -- about two checks in three end there -- and |z| >= max(|re|, |im|)
+ * (the rounded hypot is never below its larger argument) rejects most of those
+ * before the hypot is even evaluated.  Same node as the top-down walk. */
 __device__ __forceinline__ int ref_bla_get(const double *__restrict__ r_bla,
                                            int stages_bla, C zn, int n_iter,
                                            int first_invalid, int &index_out)
 {
     const int it = n_iter >> 3;
+    const int invalid_step = first_invalid - n_iter;
+    /* skip the levels whose step cannot fit before the first invalid index */
+    if (invalid_step <= 8 || stages_bla < 4) return 0;
+    const int base = 2 * it - 1;
+    const double r3 = __ldg(r_bla + base + 1);
+    if (!(fabs(zn.re) < r3 && fabs(zn.im) < r3)) return 0;
+    const double az = cabs_rn(zn);
+    if (!(az < r3)) return 0;
     int stages = stages_bla - 1;
     if (it != 0) {
         int s = 3 + (__ffs(it) - 1);
         if (s < stages) stages = s;
     }
-    const int invalid_step = first_invalid - n_iter;
-    /* skip the levels whose step cannot fit before the first invalid index */
-    if (invalid_step <= 8) return 0;
     const int top = 31 - __clz(invalid_step - 1);   /* largest stg with 2^stg < invalid_step */
     if (stages > top) stages = top;
-    const double az = cabs_rn(zn);
-    const int base = 2 * it - 1;
-    for (int stg = stages; stg > 2; stg--) {
+    for (int stg = stages; stg > 3; stg--) {
         const int ib = base + (1 << (stg - 3));
         if (az < __ldg(r_bla + ib)) { index_out = ib; return 1 << stg; }
     }
-    return 0;
+    index_out = base + 1;
+    return 8;
 }
 
 /* ======================================================================== */
