@@ -89,10 +89,15 @@ def make_fractal(w, nx=None):
     return f
 
 
-def frame_c_pix(f, tiles=None):
+def frame_c_pix(f, tiles=None, shapes=None):
+    """ tile-ordered pixel offsets (the scheduler's point list); `shapes`
+    collects the (width, height) of each tile """
     out = []
     for cs in (tiles if tiles is not None else f.chunk_slices()):
-        out.append(np.ravel(f.chunk_pixel_pos(cs, False, None)))
+        pos = f.chunk_pixel_pos(cs, False, None)
+        if shapes is not None:
+            shapes.append((pos.shape[1], pos.shape[0]))
+        out.append(np.ravel(pos))
     return np.ascontiguousarray(np.concatenate(out))
 
 
@@ -330,8 +335,12 @@ def main():
     n_Z, n_U = len(state.codes[0]), len(state.codes[1])
     zdt = np.dtype(state.complex_type)
 
-    c_host = frame_c_pix(f)
+    shapes = []
+    c_host = frame_c_pix(f, shapes=shapes)
     npts = int(c_host.shape[0])
+    from fractalshades_b200.core import tile_shape_arrays
+    tile_w, tile_h = tile_shape_arrays(shapes, npts)
+    n_tiles = int(tile_w.shape[0])
     c_pix = _native.pinned_empty((npts,), np.complex128)
     c_pix[:] = c_host
     del c_host
@@ -357,15 +366,19 @@ def main():
 
     def step_device():
         if perturb:
-            rc = lib.fsb_frame_run_device(frame.ptr, npts, d_c, d_Z, d_U, d_sr, d_si, stats)
+            rc = lib.fsb_frame_run_tiles_device(frame.ptr, n_tiles, _native.ptr(tile_w),
+                                                _native.ptr(tile_h), d_c, d_Z, d_U, d_sr,
+                                                d_si, stats)
         else:
-            rc = lib.fsb_std_run_device(indep[1], npts, d_c, d_Z, d_sr, d_si, stats)
+            rc = lib.fsb_std_run_tiles_device(indep[1], n_tiles, _native.ptr(tile_w),
+                                              _native.ptr(tile_h), d_c, d_Z, d_sr, d_si,
+                                              stats)
         _native.check(lib, rc)
         return stats.kernel_ms
 
     def step_e2e():
         t0 = time.perf_counter()
-        rc = f.numba_cycle_call((c_pix, Z, U[:n_U], sr, si), indep)
+        rc = f.numba_cycle_call((c_pix, Z, U[:n_U], sr, si), indep, tiles=shapes)
         assert rc == 0
         return (time.perf_counter() - t0) * 1e3
 

@@ -72,7 +72,8 @@ CUDA_SYMBOLS = [
     "fsb_build_info", "fsb_device_info", "fsb_host_alloc", "fsb_host_free",
     "fsb_dev_alloc", "fsb_dev_free", "fsb_memcpy_h2d", "fsb_memcpy_d2h",
     "fsb_dev_memset", "fsb_flush_l2", "fsb_std_nz", "fsb_std_run",
-    "fsb_std_run_device", "fsb_frame_create", "fsb_frame_destroy",
+    "fsb_std_run_device", "fsb_std_run_tiles", "fsb_std_run_tiles_device",
+    "fsb_frame_run_tiles", "fsb_frame_run_tiles_device", "fsb_frame_create", "fsb_frame_destroy",
     "fsb_frame_nz", "fsb_frame_bla_len", "fsb_frame_stages_bla",
     "fsb_frame_setup_ms", "fsb_frame_get_bla", "fsb_frame_get_dzndc",
     "fsb_frame_get_dzndz", "fsb_frame_run", "fsb_frame_run_device",
@@ -116,6 +117,17 @@ def _declare(lib):
     lib.fsb_std_run_device.argtypes = [ctypes.POINTER(FsbStdDesc), c_i64, c_vp,
                                        c_vp, c_vp, c_vp,
                                        ctypes.POINTER(FsbStats)]
+    lib.fsb_std_run_tiles.argtypes = [ctypes.POINTER(FsbStdDesc), c_i32, c_vp, c_vp,
+                                      c_vp, c_vp, c_vp, c_vp, c_vp,
+                                      ctypes.POINTER(FsbStats)]
+    lib.fsb_std_run_tiles_device.argtypes = [ctypes.POINTER(FsbStdDesc), c_i32, c_vp,
+                                             c_vp, c_vp, c_vp, c_vp, c_vp,
+                                             ctypes.POINTER(FsbStats)]
+    lib.fsb_frame_run_tiles.argtypes = [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                        c_vp, c_vp, c_vp, ctypes.POINTER(FsbStats)]
+    lib.fsb_frame_run_tiles_device.argtypes = [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp,
+                                               c_vp, c_vp, c_vp,
+                                               ctypes.POINTER(FsbStats)]
     lib.fsb_frame_create.argtypes = [ctypes.POINTER(FsbFrameDesc),
                                      ctypes.POINTER(c_vp)]
     lib.fsb_frame_destroy.argtypes = [c_vp]

@@ -301,10 +301,14 @@ class Fractal:
 
     # -- the seam -------------------------------------------------------------
     @staticmethod
-    def numba_cycle_call(cycle_dep_args, cycle_indep_args):
+    def numba_cycle_call(cycle_dep_args, cycle_indep_args, tiles=None):
         """ core.py:2022-2027.  Same in-place semantics: the caller-owned
         arrays of `cycle_dep_args` are filled; returns 0 or USER_INTERRUPTED.
-        The work is done by libfsb200 (fsb_std_run), never on the CPU. """
+        The work is done by libfsb200 (fsb_std_run), never on the CPU.
+
+        tiles (optional, not in the reference): [(width, height), ...] when
+        the point list is a concatenation of full row-major tiles; same
+        results, better lane occupancy on the GPU (fsb_std_run_tiles). """
         (c_pix, Z, U, stop_reason, stop_iter) = cycle_dep_args
         (kind, desc, interrupted) = cycle_indep_args
         assert kind == "std"
@@ -313,9 +317,16 @@ class Fractal:
         for a in (c_pix, Z, stop_reason, stop_iter):
             assert a.flags["C_CONTIGUOUS"]
         stats = _native.FsbStats()
-        rc = lib.fsb_std_run(desc, npts, _native.ptr(c_pix), _native.ptr(Z),
-                             _native.ptr(stop_reason), _native.ptr(stop_iter),
-                             _native.ptr(interrupted), stats)
+        if tiles is not None:
+            tw, th = tile_shape_arrays(tiles, npts)
+            rc = lib.fsb_std_run_tiles(
+                desc, tw.shape[0], _native.ptr(tw), _native.ptr(th),
+                _native.ptr(c_pix), _native.ptr(Z), _native.ptr(stop_reason),
+                _native.ptr(stop_iter), _native.ptr(interrupted), stats)
+        else:
+            rc = lib.fsb_std_run(desc, npts, _native.ptr(c_pix), _native.ptr(Z),
+                                 _native.ptr(stop_reason), _native.ptr(stop_iter),
+                                 _native.ptr(interrupted), stats)
         _native.check(lib, rc)
         Fractal._last_stats = stats.as_dict()
         return rc
@@ -621,10 +632,15 @@ class Fractal:
             c_pix = bufs["c_pix"][:npts]
             Z = bufs["Z"][:, :npts] if npts == bufs["cap"] else None
             off = 0
+            shapes = []          # full tiles: (width, height) for the patch mapping
             for (rank, cs), n in zip(batch, sizes):
-                pix = np.ravel(self.chunk_pixel_pos(cs, False, None))
+                pos = self.chunk_pixel_pos(cs, False, None)
+                pix = np.ravel(pos)
                 if state.subset is not None:
                     pix = pix[np.asarray(state.subset[cs], dtype=bool)]
+                    shapes = None
+                elif shapes is not None:
+                    shapes.append((pos.shape[1], pos.shape[0]))
                 c_pix[off:off + n] = pix
                 off += n
             if Z is None:        # batch smaller than the staging capacity
@@ -635,7 +651,8 @@ class Fractal:
             else:
                 U = bufs["U"][:n_U]
                 stop_reason, stop_iter = bufs["stop_reason"], bufs["stop_iter"]
-            ret = self.numba_cycle_call((c_pix, Z, U, stop_reason, stop_iter), indep)
+            ret = self.numba_cycle_call((c_pix, Z, U, stop_reason, stop_iter), indep,
+                                        tiles=shapes)
             for k, v in (getattr(Fractal, "_last_stats", None) or {}).items():
                 stats_acc[k] = stats_acc.get(k, 0) + v
             if ret == self.USER_INTERRUPTED:
@@ -703,11 +720,27 @@ class Fractal:
             calc_name, chunk_slice, final=True, jitter=jitter,
             supersampling=supersampling)
         indep = self._calc_data[calc_name]["cycle_indep_args"]
-        ret_code = self.numba_cycle_call(cycle_dep_args, indep)
+        tiles = None
+        if chunk_subset is None:
+            (ix, ixx, iy, iyy) = chunk_slice
+            ss = supersampling or 1
+            tiles = [((ixx - ix) * ss, (iyy - iy) * ss)]
+        ret_code = self.numba_cycle_call(cycle_dep_args, indep, tiles=tiles)
         if ret_code == self.USER_INTERRUPTED:
             return None
         (c_pix, Z, U, stop_reason, stop_iter) = cycle_dep_args
         return (chunk_subset, c_pix, Z, U, stop_reason, stop_iter)
+
+
+def tile_shape_arrays(tiles, npts):
+    """ [(width, height), ...] -> two int32 arrays for the *_run_tiles calls """
+    t = np.ascontiguousarray(np.asarray(tiles, dtype=np.int32).reshape(-1, 2))
+    tw = np.ascontiguousarray(t[:, 0])
+    th = np.ascontiguousarray(t[:, 1])
+    if int(np.sum(tw.astype(np.int64) * th)) != int(npts):
+        raise ValueError("tiles do not cover the point list: "
+                         f"{int(np.sum(tw.astype(np.int64) * th))} != {npts}")
+    return tw, th
 
 
 def _picklable(fp):

@@ -67,11 +67,13 @@ struct Ctx {
     void *d_buf = nullptr;  long long d_cap = 0;      /* scratch for in/out   */
     unsigned long long *d_ctl = nullptr;              /* MAX_CHUNKS control blocks + abort flag */
     unsigned long long *h_ctl = nullptr;              /* pinned mirror        */
+    int4 *d_tiles = nullptr;  long long tiles_cap = 0; /* tile descriptors of the running call */
     int *d_abort() { return (int *)(d_ctl + MAX_CHUNKS * CTL_WORDS); }
     ~Ctx()
     {
         if (d_buf) cudaFree(d_buf);
         if (d_ctl) cudaFree(d_ctl);
+        if (d_tiles) cudaFree(d_tiles);
         if (h_ctl) cudaFreeHost(h_ctl);
         for (cudaEvent_t e : {ev0, ev1, evc0, evc1}) if (e) cudaEventDestroy(e);
         for (int i = 0; i < MAX_CHUNKS; i++) {
@@ -154,15 +156,73 @@ int wait_event(Ctx *c, cudaEvent_t done, const volatile uint8_t *interrupted,
     return 0;
 }
 
+/* The point list of one call, as work units (see Tiling in fsb_kernels.cuh):
+ * a flat list (units of 32 consecutive points) or a concatenation of row-major
+ * tiles (units = 8 x 4 patches). */
+struct Units {
+    long long npts = 0;
+    int n_units = 0;
+    std::vector<int4> tiles;      /* empty: flat list */
+    const int4 *d_tiles = nullptr;
+    bool tiled() const { return !tiles.empty(); }
+};
+
+int units_flat(long long npts, Units &u)
+{
+    if (npts >= (1LL << 31) - 64) return fail(-3, "too many points in one call (%lld)", npts);
+    u.npts = npts;
+    u.n_units = (int)((npts + 31) / 32);
+    return 0;
+}
+
+int units_tiled(Ctx *c, int n_tiles, const int32_t *tw, const int32_t *th, cudaStream_t st, Units &u)
+{
+    if (n_tiles <= 0 || !tw || !th) return fail(-3, "empty tile list");
+    long long pts = 0, units = 0;
+    u.tiles.resize((size_t)n_tiles);
+    for (int k = 0; k < n_tiles; k++) {
+        if (tw[k] <= 0 || th[k] <= 0) return fail(-3, "tile %d has shape %d x %d", k, tw[k], th[k]);
+        u.tiles[(size_t)k] = make_int4((int)units, (int)pts, tw[k], th[k]);
+        pts += (long long)tw[k] * th[k];
+        units += (long long)((tw[k] + 7) / 8) * ((th[k] + 3) / 4);
+        if (pts >= (1LL << 31) - 64 || units >= (1LL << 31) - 64)
+            return fail(-3, "too many points in one call");
+    }
+    u.npts = pts;
+    u.n_units = (int)units;
+    if (n_tiles > c->tiles_cap) {
+        if (c->d_tiles) { CK(cudaFree(c->d_tiles)); c->d_tiles = nullptr; c->tiles_cap = 0; }
+        CK(cudaMalloc(&c->d_tiles, (size_t)(2 * n_tiles) * sizeof(int4)));
+        c->tiles_cap = 2 * n_tiles;
+    }
+    /* pageable source: the driver stages it before returning */
+    CK(cudaMemcpyAsync(c->d_tiles, u.tiles.data(), (size_t)n_tiles * sizeof(int4),
+                       cudaMemcpyHostToDevice, st));
+    u.d_tiles = c->d_tiles;
+    return 0;
+}
+
+Tiling tiling_of(const Units &u, int unit_lo, int unit_hi)
+{
+    Tiling t;
+    t.tiles = u.d_tiles;
+    t.n_tiles = (int)u.tiles.size();
+    t.unit_lo = unit_lo;
+    t.unit_hi = unit_hi;
+    return t;
+}
+
 /* Chunking of a host-buffer call: the frame is cut into up to MAX_CHUNKS
  * slabs of consecutive points so that the H2D copy of slab k+1, the kernel of
  * slab k and the D2H copies of slab k-1 overlap (three copy/compute streams;
  * kernels alternate between two streams so that the tail of one slab overlaps
- * the head of the next). */
-struct Chunks { int n; long long beg[MAX_CHUNKS + 1]; };
-Chunks make_chunks(long long npts)
+ * the head of the next).  Slabs end on unit boundaries: a multiple of 32 points
+ * of a flat list, whole tiles of a tile list. */
+struct Chunks { int n; long long beg[MAX_CHUNKS + 1]; int ubeg[MAX_CHUNKS + 1]; };
+Chunks make_chunks(const Units &u)
 {
     Chunks ch;
+    const long long npts = u.npts;
     long long want = npts / (1LL << 20);
     if (want < 1) want = 1;
     if (want > MAX_CHUNKS) want = MAX_CHUNKS;
@@ -170,14 +230,33 @@ Chunks make_chunks(long long npts)
     long long per = ((npts + want - 1) / want + 31) & ~31LL;
     ch.n = 0;
     ch.beg[0] = 0;
-    for (long long b = 0; b < npts; b += per) ch.beg[++ch.n] = (b + per < npts) ? b + per : npts;
+    ch.ubeg[0] = 0;
+    if (!u.tiled()) {
+        for (long long b = 0; b < npts; b += per) {
+            ++ch.n;
+            ch.beg[ch.n] = (b + per < npts) ? b + per : npts;
+            ch.ubeg[ch.n] = (int)((ch.beg[ch.n] + 31) / 32);
+        }
+        return ch;
+    }
+    const size_t nt = u.tiles.size();
+    for (size_t k = 0; k < nt; k++) {
+        const long long end = (k + 1 < nt) ? u.tiles[k + 1].y : npts;
+        const int uend = (k + 1 < nt) ? u.tiles[k + 1].x : u.n_units;
+        const bool last = (k + 1 == nt);
+        if (last || (end - ch.beg[ch.n] >= per && ch.n + 1 < MAX_CHUNKS)) {
+            ++ch.n;
+            ch.beg[ch.n] = end;
+            ch.ubeg[ch.n] = uend;
+        }
+    }
     return ch;
 }
 
 /* ---- kernel dispatch ------------------------------------------------------ */
 typedef void (*perturb_kernel_t)(FrameDev, long long, const C *, double *, int *,
                                  signed char *, int *, unsigned long long *,
-                                 unsigned long long *, const volatile int *);
+                                 unsigned long long *, const volatile int *, Tiling);
 
 template <bool XR, bool DC, bool DZ, bool BLA> perturb_kernel_t pick_m2_extra(bool extra, bool fastxr)
 {
@@ -697,20 +776,26 @@ static int std_fill(const fsb_std_desc *d, StdDev &p, long long zstride)
     return 0;
 }
 
-/* enqueue one kernel over points [0, n) of the given (offset) pointers */
+/* enqueue one kernel over the units [unit_lo, unit_hi) of the call's point list
+ * (whole-list pointers; p.zstride = npts of the list) */
 static int std_enqueue(Ctx *c, const fsb_std_desc *d, const StdDev &p, cudaStream_t st, int slot,
-                       long long n, const C *d_c_pix, double *d_Z, signed char *d_sr, int *d_si)
+                       const Units &u, int unit_lo, int unit_hi, const C *d_c_pix, double *d_Z,
+                       signed char *d_sr, int *d_si)
 {
     unsigned long long *ctl = c->d_ctl + slot * CTL_WORDS;
     CK(cudaMemsetAsync(ctl, 0, CTL_WORDS * sizeof(unsigned long long), st));
     const int block = 256;
     int grid = 1;
+    const long long n = 32LL * (unit_hi - unit_lo);
     if (d->model == FSB_MODEL_M2) { if (persistent_grid(k_std_m2, block, n, &grid)) return -1; }
     else { if (persistent_grid(k_std_bs, block, n, &grid)) return -1; }
+    const Tiling t = tiling_of(u, unit_lo, unit_hi);
     if (d->model == FSB_MODEL_M2)
-        k_std_m2<<<grid, block, 0, st>>>(p, n, d_c_pix, d_Z, d_sr, d_si, ctl, ctl + 1, c->d_abort());
+        k_std_m2<<<grid, block, 0, st>>>(p, u.npts, d_c_pix, d_Z, d_sr, d_si, ctl, ctl + 1,
+                                         c->d_abort(), t);
     else
-        k_std_bs<<<grid, block, 0, st>>>(p, n, d_c_pix, d_Z, d_sr, d_si, ctl, ctl + 1, c->d_abort());
+        k_std_bs<<<grid, block, 0, st>>>(p, u.npts, d_c_pix, d_Z, d_sr, d_si, ctl, ctl + 1,
+                                         c->d_abort(), t);
     CK(cudaGetLastError());
     return 0;
 }
@@ -731,18 +816,17 @@ static void gather_stats(Ctx *c, int n_slots, fsb_stats *stats)
     stats->n_launches = n_slots;
 }
 
-int fsb_std_run_device(const fsb_std_desc *d, int64_t npts, const double *d_c_pix, double *d_Z,
-                       int8_t *d_stop_reason, int32_t *d_stop_iter, fsb_stats *stats)
+} /* extern "C" */
+
+static int std_run_device_impl(Ctx *c, const fsb_std_desc *d, const Units &u, const double *d_c_pix,
+                               double *d_Z, int8_t *d_stop_reason, int32_t *d_stop_iter,
+                               fsb_stats *stats)
 {
-    Ctx *c;
-    if (get_ctx(&c)) return -1;
-    if (stats) memset(stats, 0, sizeof *stats);
-    if (npts <= 0) return 0;
     StdDev p;
-    if (std_fill(d, p, npts)) return -3;
+    if (std_fill(d, p, u.npts)) return -3;
     CK(cudaMemsetAsync(c->d_abort(), 0, sizeof(int), c->stream));
     CK(cudaEventRecord(c->ev0, c->stream));
-    if (std_enqueue(c, d, p, c->stream, 0, npts, (const C *)d_c_pix, d_Z,
+    if (std_enqueue(c, d, p, c->stream, 0, u, 0, u.n_units, (const C *)d_c_pix, d_Z,
                     (signed char *)d_stop_reason, d_stop_iter)) return -1;
     CK(cudaEventRecord(c->ev1, c->stream));
     CK(cudaMemcpyAsync(c->h_ctl, c->d_ctl, CTL_WORDS * sizeof(unsigned long long),
@@ -755,22 +839,49 @@ int fsb_std_run_device(const fsb_std_desc *d, int64_t npts, const double *d_c_pi
     return 0;
 }
 
+extern "C" {
+
+int fsb_std_run_device(const fsb_std_desc *d, int64_t npts, const double *d_c_pix, double *d_Z,
+                       int8_t *d_stop_reason, int32_t *d_stop_iter, fsb_stats *stats)
+{
+    Ctx *c;
+    if (get_ctx(&c)) return -1;
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (npts <= 0) return 0;
+    Units u;
+    if (units_flat(npts, u)) return -3;
+    return std_run_device_impl(c, d, u, d_c_pix, d_Z, d_stop_reason, d_stop_iter, stats);
+}
+
+int fsb_std_run_tiles_device(const fsb_std_desc *d, int32_t n_tiles, const int32_t *tile_w,
+                             const int32_t *tile_h, const double *d_c_pix, double *d_Z,
+                             int8_t *d_stop_reason, int32_t *d_stop_iter, fsb_stats *stats)
+{
+    Ctx *c;
+    if (get_ctx(&c)) return -1;
+    if (stats) memset(stats, 0, sizeof *stats);
+    Units u;
+    if (units_tiled(c, n_tiles, tile_w, tile_h, c->stream, u)) return -3;
+    return std_run_device_impl(c, d, u, d_c_pix, d_Z, d_stop_reason, d_stop_iter, stats);
+}
+
 } /* extern "C" */
 
 /* One output plane of a host-buffer call */
 struct Plane { char *host; long long dev_off; long long elem; };
 
 /* Host-buffer call: H2D of c_pix, kernels and D2H of the planes, pipelined
- * over slabs of consecutive points.  `enqueue(stream, slot, n, a)` launches the
- * kernel for points [a, a+n) into control block `slot`. */
+ * over slabs of consecutive points.  `enqueue(stream, slot, unit_lo, unit_hi)`
+ * launches the kernel for those units into control block `slot`. */
 template <class Enqueue>
-static int run_pipelined(Ctx *c, long long npts, const double *c_pix, long long o_c,
+static int run_pipelined(Ctx *c, const Units &u, const double *c_pix, long long o_c,
                          const Plane *planes, int n_planes, long long o_zero_beg,
                          long long o_zero_end, long long o_sr, Enqueue enqueue,
                          const volatile uint8_t *interrupted, fsb_stats *stats, bool *was_int)
 {
     char *base = (char *)c->d_buf;
-    const Chunks ch = make_chunks(npts);
+    const long long npts = u.npts;
+    const Chunks ch = make_chunks(u);
     CK(cudaMemsetAsync(c->d_abort(), 0, sizeof(int), c->stream));
     CK(cudaMemsetAsync(base + o_zero_beg, 0, (size_t)(o_zero_end - o_zero_beg), c->stream));
     CK(cudaMemsetAsync(base + o_sr, 0xff, (size_t)npts, c->stream));
@@ -788,7 +899,7 @@ static int run_pipelined(Ctx *c, long long npts, const double *c_pix, long long 
         CK(cudaEventRecord(c->ev_h[k], c->s_h2d));
         cudaStream_t st = (k & 1) ? c->s_alt : c->stream;
         CK(cudaStreamWaitEvent(st, c->ev_h[k], 0));
-        if (enqueue(st, k, n, a)) return -1;
+        if (enqueue(st, k, ch.ubeg[k], ch.ubeg[k + 1])) return -1;
         CK(cudaEventRecord(c->ev_k[k], st));
         return 0;
     };
@@ -823,15 +934,19 @@ static int run_pipelined(Ctx *c, long long npts, const double *c_pix, long long 
 
 extern "C" {
 
-int fsb_std_run(const fsb_std_desc *d, int64_t npts, const double *c_pix, double *Z,
-                int8_t *stop_reason, int32_t *stop_iter, const volatile uint8_t *interrupted,
-                fsb_stats *stats)
+} /* extern "C" */
+
+static int std_run_impl(Ctx *c, const fsb_std_desc *d, int32_t n_tiles, const int32_t *tile_w,
+                        const int32_t *tile_h, int64_t npts_flat, const double *c_pix, double *Z,
+                        int8_t *stop_reason, int32_t *stop_iter,
+                        const volatile uint8_t *interrupted, fsb_stats *stats)
 {
-    Ctx *c;
-    if (get_ctx(&c)) return -1;
     if (stats) memset(stats, 0, sizeof *stats);
-    if (npts <= 0) return 0;
     if (interrupted && *interrupted) return FSB_USER_INTERRUPTED;
+    Units u;
+    if (n_tiles > 0) { if (units_tiled(c, n_tiles, tile_w, tile_h, c->stream, u)) return -3; }
+    else if (units_flat(npts_flat, u)) return -3;
+    const long long npts = u.npts;
     StdDev p;
     if (std_fill(d, p, npts)) return -3;
     const int nz = fsb_std_nz(d);
@@ -847,15 +962,39 @@ int fsb_std_run(const fsb_std_desc *d, int64_t npts, const double *c_pix, double
     planes[np++] = Plane{(char *)stop_iter, o_si, 4};
     planes[np++] = Plane{(char *)stop_reason, o_sr, 1};
     bool was_int = false;
-    auto enqueue = [&](cudaStream_t st, int slot, long long n, long long a) {
-        return std_enqueue(c, d, p, st, slot, n, (const C *)(base + o_c) + a,
-                           (double *)(base + o_Z + a * zelem), (signed char *)(base + o_sr) + a,
-                           (int *)(base + o_si) + a);
+    auto enqueue = [&](cudaStream_t st, int slot, int unit_lo, int unit_hi) {
+        return std_enqueue(c, d, p, st, slot, u, unit_lo, unit_hi, (const C *)(base + o_c),
+                           (double *)(base + o_Z), (signed char *)(base + o_sr),
+                           (int *)(base + o_si));
     };
-    int rc = run_pipelined(c, npts, c_pix, o_c, planes, np, o_Z, o_si + npts * 4, o_sr, enqueue,
+    int rc = run_pipelined(c, u, c_pix, o_c, planes, np, o_Z, o_si + npts * 4, o_sr, enqueue,
                            interrupted, stats, &was_int);
     if (rc) return rc;
     return was_int ? FSB_USER_INTERRUPTED : 0;
+}
+
+extern "C" {
+
+int fsb_std_run(const fsb_std_desc *d, int64_t npts, const double *c_pix, double *Z,
+                int8_t *stop_reason, int32_t *stop_iter, const volatile uint8_t *interrupted,
+                fsb_stats *stats)
+{
+    Ctx *c;
+    if (get_ctx(&c)) return -1;
+    if (npts <= 0) { if (stats) memset(stats, 0, sizeof *stats); return 0; }
+    return std_run_impl(c, d, 0, nullptr, nullptr, npts, c_pix, Z, stop_reason, stop_iter,
+                        interrupted, stats);
+}
+
+int fsb_std_run_tiles(const fsb_std_desc *d, int32_t n_tiles, const int32_t *tile_w,
+                      const int32_t *tile_h, const double *c_pix, double *Z, int8_t *stop_reason,
+                      int32_t *stop_iter, const volatile uint8_t *interrupted, fsb_stats *stats)
+{
+    Ctx *c;
+    if (get_ctx(&c)) return -1;
+    if (n_tiles <= 0) return fail(-3, "empty tile list");
+    return std_run_impl(c, d, n_tiles, tile_w, tile_h, 0, c_pix, Z, stop_reason, stop_iter,
+                        interrupted, stats);
 }
 
 /* ---- perturbation frames -------------------------------------------------- */
@@ -1074,8 +1213,11 @@ int fsb_frame_get_dzndz(const fsb_frame *f, double *dZndz, int32_t *dZndz_e)
     return 0;
 }
 
-static int frame_enqueue(Ctx *c, fsb_frame *f, cudaStream_t st, int slot, long long n,
-                         long long zstride, const C *d_c_pix, double *d_Z, int *d_U,
+} /* extern "C" */
+
+/* enqueue one kernel over the units [unit_lo, unit_hi) of the call's point list */
+static int frame_enqueue(Ctx *c, fsb_frame *f, cudaStream_t st, int slot, const Units &u,
+                         int unit_lo, int unit_hi, const C *d_c_pix, double *d_Z, int *d_U,
                          signed char *d_sr, int *d_si)
 {
     const fsb_frame_desc &d = f->d;
@@ -1087,26 +1229,22 @@ static int frame_enqueue(Ctx *c, fsb_frame *f, cudaStream_t st, int slot, long l
     CK(cudaMemsetAsync(ctl, 0, CTL_WORDS * sizeof(unsigned long long), st));
     const int block = 128;
     int grid = 1;
-    if (persistent_grid(k, block, n, &grid)) return -1;
+    if (persistent_grid(k, block, 32LL * (unit_hi - unit_lo), &grid)) return -1;
     FrameDev dv = f->dev;
-    dv.zstride = zstride;
-    k<<<grid, block, 0, st>>>(dv, n, d_c_pix, d_Z, d_U, d_sr, d_si, ctl, ctl + 1, c->d_abort());
+    dv.zstride = u.npts;
+    k<<<grid, block, 0, st>>>(dv, u.npts, d_c_pix, d_Z, d_U, d_sr, d_si, ctl, ctl + 1,
+                              c->d_abort(), tiling_of(u, unit_lo, unit_hi));
     CK(cudaGetLastError());
     return 0;
 }
 
-int fsb_frame_run_device(fsb_frame *f, int64_t npts, const double *d_c_pix, double *d_Z,
-                         int32_t *d_U, int8_t *d_stop_reason, int32_t *d_stop_iter,
-                         fsb_stats *stats)
+static int frame_run_device_impl(Ctx *c, fsb_frame *f, const Units &u, const double *d_c_pix,
+                                 double *d_Z, int32_t *d_U, int8_t *d_stop_reason,
+                                 int32_t *d_stop_iter, fsb_stats *stats)
 {
-    Ctx *c;
-    if (get_ctx(&c)) return -1;
-    if (!f) return fail(-3, "null frame");
-    if (stats) memset(stats, 0, sizeof *stats);
-    if (npts <= 0) return 0;
     CK(cudaMemsetAsync(c->d_abort(), 0, sizeof(int), c->stream));
     CK(cudaEventRecord(c->ev0, c->stream));
-    if (frame_enqueue(c, f, c->stream, 0, npts, npts, (const C *)d_c_pix, d_Z, d_U,
+    if (frame_enqueue(c, f, c->stream, 0, u, 0, u.n_units, (const C *)d_c_pix, d_Z, d_U,
                       (signed char *)d_stop_reason, d_stop_iter)) return -1;
     CK(cudaEventRecord(c->ev1, c->stream));
     CK(cudaMemcpyAsync(c->h_ctl, c->d_ctl, CTL_WORDS * sizeof(unsigned long long),
@@ -1119,16 +1257,17 @@ int fsb_frame_run_device(fsb_frame *f, int64_t npts, const double *d_c_pix, doub
     return 0;
 }
 
-int fsb_frame_run(fsb_frame *f, int64_t npts, const double *c_pix, double *Z, int32_t *U,
-                  int8_t *stop_reason, int32_t *stop_iter, const volatile uint8_t *interrupted,
-                  fsb_stats *stats)
+static int frame_run_impl(Ctx *c, fsb_frame *f, int32_t n_tiles, const int32_t *tile_w,
+                          const int32_t *tile_h, int64_t npts_flat, const double *c_pix, double *Z,
+                          int32_t *U, int8_t *stop_reason, int32_t *stop_iter,
+                          const volatile uint8_t *interrupted, fsb_stats *stats)
 {
-    Ctx *c;
-    if (get_ctx(&c)) return -1;
-    if (!f) return fail(-3, "null frame");
     if (stats) memset(stats, 0, sizeof *stats);
-    if (npts <= 0) return 0;
     if (interrupted && *interrupted) return FSB_USER_INTERRUPTED;
+    Units u;
+    if (n_tiles > 0) { if (units_tiled(c, n_tiles, tile_w, tile_h, c->stream, u)) return -3; }
+    else if (units_flat(npts_flat, u)) return -3;
+    const long long npts = u.npts;
     const int nz = f->nz;
     const long long zelem = (f->d.model == FSB_MODEL_M2) ? 16 : 8;
     long long o_c = 0, o_Z = align256(o_c + npts * 16), o_U = align256(o_Z + nz * npts * zelem),
@@ -1144,15 +1283,70 @@ int fsb_frame_run(fsb_frame *f, int64_t npts, const double *c_pix, double *Z, in
     planes[np++] = Plane{(char *)stop_iter, o_si, 4};
     planes[np++] = Plane{(char *)stop_reason, o_sr, 1};
     bool was_int = false;
-    auto enqueue = [&](cudaStream_t st, int slot, long long n, long long a) {
-        return frame_enqueue(c, f, st, slot, n, npts, (const C *)(base + o_c) + a,
-                             (double *)(base + o_Z + a * zelem), (int *)(base + o_U) + a,
-                             (signed char *)(base + o_sr) + a, (int *)(base + o_si) + a);
+    auto enqueue = [&](cudaStream_t st, int slot, int unit_lo, int unit_hi) {
+        return frame_enqueue(c, f, st, slot, u, unit_lo, unit_hi, (const C *)(base + o_c),
+                             (double *)(base + o_Z), (int *)(base + o_U),
+                             (signed char *)(base + o_sr), (int *)(base + o_si));
     };
-    int rc = run_pipelined(c, npts, c_pix, o_c, planes, np, o_Z, o_si + npts * 4, o_sr, enqueue,
+    int rc = run_pipelined(c, u, c_pix, o_c, planes, np, o_Z, o_si + npts * 4, o_sr, enqueue,
                            interrupted, stats, &was_int);
     if (rc) return rc;
     return was_int ? FSB_USER_INTERRUPTED : 0;
+}
+
+extern "C" {
+
+int fsb_frame_run_device(fsb_frame *f, int64_t npts, const double *d_c_pix, double *d_Z,
+                         int32_t *d_U, int8_t *d_stop_reason, int32_t *d_stop_iter,
+                         fsb_stats *stats)
+{
+    Ctx *c;
+    if (get_ctx(&c)) return -1;
+    if (!f) return fail(-3, "null frame");
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (npts <= 0) return 0;
+    Units u;
+    if (units_flat(npts, u)) return -3;
+    return frame_run_device_impl(c, f, u, d_c_pix, d_Z, d_U, d_stop_reason, d_stop_iter, stats);
+}
+
+int fsb_frame_run_tiles_device(fsb_frame *f, int32_t n_tiles, const int32_t *tile_w,
+                               const int32_t *tile_h, const double *d_c_pix, double *d_Z,
+                               int32_t *d_U, int8_t *d_stop_reason, int32_t *d_stop_iter,
+                               fsb_stats *stats)
+{
+    Ctx *c;
+    if (get_ctx(&c)) return -1;
+    if (!f) return fail(-3, "null frame");
+    if (stats) memset(stats, 0, sizeof *stats);
+    Units u;
+    if (units_tiled(c, n_tiles, tile_w, tile_h, c->stream, u)) return -3;
+    return frame_run_device_impl(c, f, u, d_c_pix, d_Z, d_U, d_stop_reason, d_stop_iter, stats);
+}
+
+int fsb_frame_run(fsb_frame *f, int64_t npts, const double *c_pix, double *Z, int32_t *U,
+                  int8_t *stop_reason, int32_t *stop_iter, const volatile uint8_t *interrupted,
+                  fsb_stats *stats)
+{
+    Ctx *c;
+    if (get_ctx(&c)) return -1;
+    if (!f) return fail(-3, "null frame");
+    if (npts <= 0) { if (stats) memset(stats, 0, sizeof *stats); return 0; }
+    return frame_run_impl(c, f, 0, nullptr, nullptr, npts, c_pix, Z, U, stop_reason, stop_iter,
+                          interrupted, stats);
+}
+
+int fsb_frame_run_tiles(fsb_frame *f, int32_t n_tiles, const int32_t *tile_w,
+                        const int32_t *tile_h, const double *c_pix, double *Z, int32_t *U,
+                        int8_t *stop_reason, int32_t *stop_iter,
+                        const volatile uint8_t *interrupted, fsb_stats *stats)
+{
+    Ctx *c;
+    if (get_ctx(&c)) return -1;
+    if (!f) return fail(-3, "null frame");
+    if (n_tiles <= 0) return fail(-3, "empty tile list");
+    return frame_run_impl(c, f, n_tiles, tile_w, tile_h, 0, c_pix, Z, U, stop_reason, stop_iter,
+                          interrupted, stats);
 }
 
 /* ---- unit-test / calibration entry points --------------------------------- */

@@ -65,18 +65,60 @@ struct StdDev {
     long long zstride;   /* row stride of the output planes */
 };
 
-/* Warp-level work stealing: lane 0 takes 32 points from the global counter. */
-/* Returns a negative value when the host raised the abort flag (the flag is read
- * by lane 0 only so that the whole warp takes the same decision). */
-__device__ __forceinline__ long long grab32(unsigned long long *work,
-                                            const volatile int *abort_flag)
+/* Work units.  A launch covers units [unit_lo, unit_hi); one warp takes one unit
+ * at a time from a global counter (warp-level work stealing) and its 32 lanes
+ * take the unit's 32 points.
+ *   flat list   (tiles == nullptr): unit u = points [32u, 32u + 32)
+ *   tile list   the point list is a concatenation of row-major tiles
+ *               (core.py:1767-1830); a unit is an 8 x 4 pixel patch of one tile,
+ *               lane l -> (row l >> 3, column l & 7).  Neighbouring pixels leave the
+ *               loop at nearby iteration counts, and a compact footprint keeps
+ *               more lanes alive than a 32 x 1 strip (measured 4-8 %).
+ * Each tile descriptor is {first unit, first point, width, height}. */
+struct Tiling {
+    const int4 *tiles;
+    int n_tiles;
+    int unit_lo, unit_hi;
+};
+
+/* Takes the warp's next unit: returns false when the launch is exhausted or the
+ * host raised the abort flag (the flag is read by lane 0 only, so the whole
+ * warp takes the same decision).  `ipt` is this lane's point, `valid` false for
+ * the lanes that fall outside a ragged patch / the end of the list. */
+__device__ __forceinline__ bool grab_unit(unsigned long long *work,
+                                          const volatile int *abort_flag,
+                                          const Tiling &t, long long npts, int &ipt,
+                                          bool &valid)
 {
-    long long base = 0;
-    if ((threadIdx.x & 31) == 0) {
-        if (*abort_flag) base = -1;
-        else base = (long long)atomicAdd(work, 32ULL);
+    const int lane = threadIdx.x & 31;
+    int u = 0;
+    if (lane == 0) {
+        if (*abort_flag) u = -1;
+        else {
+            const unsigned long long g = atomicAdd(work, 1ULL);
+            u = (g < (unsigned long long)(t.unit_hi - t.unit_lo)) ? t.unit_lo + (int)g : -1;
+        }
     }
-    return __shfl_sync(0xffffffffu, base, 0);
+    u = __shfl_sync(0xffffffffu, u, 0);
+    if (u < 0) return false;
+    if (t.tiles == nullptr) {
+        const long long i = 32LL * u + lane;
+        ipt = (int)i;
+        valid = i < npts;
+        return true;
+    }
+    int lo = 0, hi = t.n_tiles - 1;          /* last tile whose first unit <= u */
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(&t.tiles[mid].x) <= u) lo = mid; else hi = mid - 1;
+    }
+    const int4 tl = __ldg(t.tiles + lo);
+    const int k = u - tl.x, per_row = (tl.z + 7) >> 3;
+    const int py = k / per_row, px = k - py * per_row;
+    const int r = 4 * py + (lane >> 3), col = 8 * px + (lane & 7);
+    valid = (r < tl.w) && (col < tl.z);
+    ipt = tl.y + r * tl.z + col;
+    return true;
 }
 
 __device__ __forceinline__ void add_counters(unsigned long long *counters,
@@ -127,14 +169,15 @@ __global__ void __launch_bounds__(256)
 k_std_m2(StdDev p, long long npts, const C *__restrict__ c_pix,
          double *__restrict__ Z, signed char *__restrict__ stop_reason,
          int *__restrict__ stop_iter, unsigned long long *work,
-         unsigned long long *counters, const volatile int *abort_flag)
+         unsigned long long *counters, const volatile int *abort_flag,
+         const Tiling tiling)
 {
     unsigned long long n_exec = 0, n_sum = 0;
     for (;;) {
-        long long base = grab32(work, abort_flag);
-        if (base < 0 || base >= npts) break;
-        long long i = base + (threadIdx.x & 31);
-        if (i >= npts) continue;
+        int ipt_; bool valid_;
+        if (!grab_unit(work, abort_flag, tiling, npts, ipt_, valid_)) break;
+        if (!valid_) continue;
+        const long long i = ipt_;
         C c = c_from_pix(ldC(c_pix, i), p.lin_mat, p.dx, mkC(p.center_re, p.center_im));
         C zn = mkC(0., 0.), dzndz = zn, dzndc = zn, d2 = zn;
         long long n_iter = 0, div_shift = 0, orbit_i1 = 0, orbit_i2 = 0;
@@ -206,15 +249,16 @@ __global__ void __launch_bounds__(256)
 k_std_bs(StdDev p, long long npts, const C *__restrict__ c_pix,
          double *__restrict__ Z, signed char *__restrict__ stop_reason,
          int *__restrict__ stop_iter, unsigned long long *work,
-         unsigned long long *counters, const volatile int *abort_flag)
+         unsigned long long *counters, const volatile int *abort_flag,
+         const Tiling tiling)
 {
     unsigned long long n_exec = 0, n_sum = 0;
     const int flavor = p.flavor;
     for (;;) {
-        long long base = grab32(work, abort_flag);
-        if (base < 0 || base >= npts) break;
-        long long i = base + (threadIdx.x & 31);
-        if (i >= npts) continue;
+        int ipt_; bool valid_;
+        if (!grab_unit(work, abort_flag, tiling, npts, ipt_, valid_)) break;
+        if (!valid_) continue;
+        const long long i = ipt_;
         C c = c_from_pix(ldC(c_pix, i), p.lin_mat, p.dx, mkC(p.center_re, p.center_im));
         double a = c.re, b = c.im;
         double X = 0., Y = 0., dXdA = 0., dXdB = 0., dYdA = 0., dYdB = 0.;
@@ -415,7 +459,8 @@ k_perturb_m2(const __grid_constant__ FrameDev f, long long npts_ll,
              const C *__restrict__ c_pix, double *__restrict__ Z,
              int *__restrict__ U, signed char *__restrict__ stop_reason,
              int *__restrict__ stop_iter, unsigned long long *work,
-             unsigned long long *counters, const volatile int *abort_flag)
+             unsigned long long *counters, const volatile int *abort_flag,
+             const Tiling tiling)
 {
     unsigned long long n_exec = 0, n_bla = 0, n_reb = 0, n_sum = 0, n_fast = 0;
     const int L = f.Li;
@@ -430,17 +475,15 @@ k_perturb_m2(const __grid_constant__ FrameDev f, long long npts_ll,
     const XC record_zero = mkXC(mkC(0., 0.), 0);
     const C Zn0 = ldC(f.Zn, 0);
     const C *__restrict__ Zn = f.Zn;
-    const int npts = (int)npts_ll;
 
 #define DZNDC_X(i) mkXC(ldC(f.dZndc, (i)), __ldg(f.dZndc_e + (i)))
 #define DZNDZ_X(i) mkXC(ldC(f.dZndz, (i)), __ldg(f.dZndz_e + (i)))
 #define REF_X(k) mkXC(ldC(f.ref_xr, (k)), __ldg(f.ref_xr_e + (k)))
 
     for (;;) {
-        long long base = grab32(work, abort_flag);
-        if (base < 0 || base >= npts_ll) break;
-        const int ipt = (int)base + (threadIdx.x & 31);
-        if (ipt >= npts) continue;
+        int ipt; bool valid_;
+        if (!grab_unit(work, abort_flag, tiling, npts_ll, ipt, valid_)) break;
+        if (!valid_) continue;
 
         /* perturbation.py:1026-1031, 2214-2230 */
         C pix = ldC(c_pix, ipt);
@@ -907,7 +950,8 @@ k_perturb_bs(const __grid_constant__ FrameDev f, long long npts_ll,
              const C *__restrict__ c_pix, double *__restrict__ Z,
              int *__restrict__ U, signed char *__restrict__ stop_reason,
              int *__restrict__ stop_iter, unsigned long long *work,
-             unsigned long long *counters, const volatile int *abort_flag)
+             unsigned long long *counters, const volatile int *abort_flag,
+             const Tiling tiling)
 {
     unsigned long long n_exec = 0, n_bla = 0, n_reb = 0, n_sum = 0, n_fast = 0;
     const int L = f.Li;
@@ -921,7 +965,6 @@ k_perturb_bs(const __grid_constant__ FrameDev f, long long npts_ll,
     const XF record_zero = mkXF(0., 0);
     const C *__restrict__ Zn = f.Zn;
     const C Zn0 = ldC(Zn, 0);
-    const int npts = (int)npts_ll;
     (void)L;
 
 #define D_X(j, i) mkXF(__ldg(f.dP[j] + (i)), __ldg(f.dP_e[j] + (i)))
@@ -935,10 +978,9 @@ k_perturb_bs(const __grid_constant__ FrameDev f, long long npts_ll,
                 && in_fast_range(dya) && in_fast_range(dyb); } } while (0)
 
     for (;;) {
-        long long base = grab32(work, abort_flag);
-        if (base < 0 || base >= npts_ll) break;
-        const int ipt = (int)base + (threadIdx.x & 31);
-        if (ipt >= npts) continue;
+        int ipt; bool valid_;
+        if (!grab_unit(work, abort_flag, tiling, npts_ll, ipt, valid_)) break;
+        if (!valid_) continue;
 
         /* perturbation.py:2260-2280 */
         C pix = ldC(c_pix, ipt);

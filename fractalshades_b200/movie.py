@@ -147,12 +147,17 @@ def render_frame_to_staging(f, calc_name):
     gkey = (f.nx, f.ny, f.xy_ratio)
     if _STAGE.get("grid") != gkey:       # pixel offsets depend on the grid only
         off = 0
+        shapes = []
         for cs in f.chunk_slices():
-            pix = np.ravel(f.chunk_pixel_pos(cs, False, None))
+            pos = f.chunk_pixel_pos(cs, False, None)
+            pix = np.ravel(pos)
+            shapes.append((pos.shape[1], pos.shape[0]))
             b["c_pix"][off:off + pix.shape[0]] = pix
             off += pix.shape[0]
         _STAGE["grid"] = gkey
-    rc = f.numba_cycle_call((b["c_pix"], b["Z"], b["U"][:n_U], b["sr"], b["si"]), indep)
+        _STAGE["tiles"] = shapes
+    rc = f.numba_cycle_call((b["c_pix"], b["Z"], b["U"][:n_U], b["sr"], b["si"]), indep,
+                            tiles=_STAGE["tiles"])
     if rc != 0:
         raise RuntimeError("frame interrupted")
     from .core import Fractal

@@ -82,13 +82,23 @@ class FrameHandle:
             self.ptr, _native.ptr(out), _native.ptr(oe)))
         return out, (oe if self.tables["xr_detect"] else None)
 
-    def run(self, c_pix, Z, U, stop_reason, stop_iter, interrupted=None):
+    def run(self, c_pix, Z, U, stop_reason, stop_iter, interrupted=None,
+            tiles=None):
         npts = c_pix.shape[0]
         stats = _native.FsbStats()
-        rc = self.lib.fsb_frame_run(
-            self.ptr, npts, _native.ptr(c_pix), _native.ptr(Z), _native.ptr(U),
-            _native.ptr(stop_reason), _native.ptr(stop_iter),
-            _native.ptr(interrupted), stats)
+        if tiles is not None:
+            from .core import tile_shape_arrays
+            tw, th = tile_shape_arrays(tiles, npts)
+            rc = self.lib.fsb_frame_run_tiles(
+                self.ptr, tw.shape[0], _native.ptr(tw), _native.ptr(th),
+                _native.ptr(c_pix), _native.ptr(Z), _native.ptr(U),
+                _native.ptr(stop_reason), _native.ptr(stop_iter),
+                _native.ptr(interrupted), stats)
+        else:
+            rc = self.lib.fsb_frame_run(
+                self.ptr, npts, _native.ptr(c_pix), _native.ptr(Z), _native.ptr(U),
+                _native.ptr(stop_reason), _native.ptr(stop_iter),
+                _native.ptr(interrupted), stats)
         _native.check(self.lib, rc)
         self.last_stats = stats.as_dict()
         return rc
@@ -437,10 +447,11 @@ class PerturbationFractal(Fractal):
             indep[1].close()
 
     @staticmethod
-    def numba_cycle_call(cycle_dep_args, cycle_indep_args):
-        """ perturbation.py:414-428 : per-tile entry point, in-place """
+    def numba_cycle_call(cycle_dep_args, cycle_indep_args, tiles=None):
+        """ perturbation.py:414-428 : per-tile entry point, in-place
+        (`tiles`: see Fractal.numba_cycle_call) """
         (kind, frame, interrupted) = cycle_indep_args
         (c_pix, Z, U, stop_reason, stop_iter) = cycle_dep_args
-        rc = frame.run(c_pix, Z, U, stop_reason, stop_iter, interrupted)
+        rc = frame.run(c_pix, Z, U, stop_reason, stop_iter, interrupted, tiles)
         Fractal._last_stats = frame.last_stats
         return rc

@@ -102,6 +102,21 @@ int fsb_std_run_device(const fsb_std_desc *d, int64_t npts,
                        int8_t *d_stop_reason, int32_t *d_stop_iter,
                        fsb_stats *stats);
 
+/* Tile-list variants.  The point list is the concatenation of n_tiles
+ * row-major tiles (tile k: tile_h[k] rows of tile_w[k] points, row 0 first --
+ * the layout of Fractal.chunk_pixel_pos, core.py:1767-1830, and of the memmap
+ * slabs, core.py:2362-2472); npts = sum(tile_w[k] * tile_h[k]).  Same results
+ * as the flat calls; a warp then works on an 8 x 4 pixel patch instead of a
+ * 32 x 1 strip, which keeps more lanes busy.  This is what the GPU tile
+ * scheduler (Fractal.compute_rawdata_dev, core.py:2515-2554) calls. */
+int fsb_std_run_tiles(const fsb_std_desc *d, int32_t n_tiles, const int32_t *tile_w,
+                      const int32_t *tile_h, const double *c_pix, double *Z,
+                      int8_t *stop_reason, int32_t *stop_iter,
+                      const volatile uint8_t *interrupted, fsb_stats *stats);
+int fsb_std_run_tiles_device(const fsb_std_desc *d, int32_t n_tiles, const int32_t *tile_w,
+                             const int32_t *tile_h, const double *d_c_pix, double *d_Z,
+                             int8_t *d_stop_reason, int32_t *d_stop_iter, fsb_stats *stats);
+
 /* ---- perturbation frames ------------------------------------------------- */
 typedef struct fsb_frame fsb_frame;   /* opaque, owns the device tables */
 
@@ -167,6 +182,16 @@ int fsb_frame_run(fsb_frame *f, int64_t npts, const double *c_pix, double *Z,
 int fsb_frame_run_device(fsb_frame *f, int64_t npts, const double *d_c_pix,
                          double *d_Z, int32_t *d_U, int8_t *d_stop_reason,
                          int32_t *d_stop_iter, fsb_stats *stats);
+
+/* tile-list variants, see fsb_std_run_tiles */
+int fsb_frame_run_tiles(fsb_frame *f, int32_t n_tiles, const int32_t *tile_w,
+                        const int32_t *tile_h, const double *c_pix, double *Z, int32_t *U,
+                        int8_t *stop_reason, int32_t *stop_iter,
+                        const volatile uint8_t *interrupted, fsb_stats *stats);
+int fsb_frame_run_tiles_device(fsb_frame *f, int32_t n_tiles, const int32_t *tile_w,
+                               const int32_t *tile_h, const double *d_c_pix, double *d_Z,
+                               int32_t *d_U, int8_t *d_stop_reason, int32_t *d_stop_iter,
+                               fsb_stats *stats);
 
 /* ---- Xrange device arithmetic, exposed for unit tests --------------------
  * (mirror of the reference's tests/test_numba_xr.py; runs on the GPU)

@@ -208,3 +208,84 @@ def test_full_size_properties_4k(full_4k):
         assert same.mean() >= 0.999, (rank, same.mean())
         rel = np.abs(Z[0, beg:end][same] - Zo[0][same]) / np.abs(Zo[0][same])
         assert np.median(rel) < 1e-9
+
+
+# ---------------------------------------------------------------------------
+# tile-list calls (8 x 4 patch mapping) == flat calls, bit for bit
+_TILE_SHAPES = [(200, 200), (1, 1), (7, 3), (9, 5), (40, 160), (8, 4), (33, 1), (1, 37),
+                (16, 9)]
+
+
+def _split_tiles(n, shapes):
+    """ tile shapes covering exactly n points (the last one is a 1-row strip) """
+    out, left = [], n
+    k = 0
+    while left > 0:
+        w, h = shapes[k % len(shapes)]
+        k += 1
+        if w * h > left:
+            out.append((left, 1))
+            break
+        out.append((w, h))
+        left -= w * h
+    return out
+
+
+@pytest.mark.parametrize("name", ["p_M2_E20", "p_M2_deep1000_xr", "p_M2_int_E11", "p_BS_f1_E30_skew", "p_BS_f1_E500_xr"])
+@pytest.mark.parametrize("strict", [True, False])
+def test_tile_list_calls_equal_flat_calls(name, strict):
+    from cases import CASES
+    if name not in CASES:
+        pytest.skip("case not defined")
+    from fractalshades_b200.perturbation import create_frame
+    f, case, t = pc.host_tables(name)
+    c_pix = pc.all_c_pix(f)
+    n = c_pix.shape[0]
+    tiles = _split_tiles(n, _TILE_SHAPES)
+    assert sum(w * h for w, h in tiles) == n
+    frame = create_frame(t, strict=strict)
+    try:
+        m2 = t["kind"] == "perturb_M2"
+        outs = []
+        for tl in (None, tiles):
+            Z = np.zeros((frame.nz, n), np.complex128 if m2 else np.float64)
+            U = np.zeros((1, n), np.int32)
+            sr = -np.ones((1, n), np.int8)
+            si = np.zeros((1, n), np.int32)
+            assert frame.run(c_pix, Z, U, sr, si, tiles=tl) == 0
+            outs.append((Z, U, sr, si, dict(frame.last_stats)))
+    finally:
+        frame.close()
+    a, b = outs
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    assert np.array_equal(a[3], b[3])
+    assert a[0].tobytes() == b[0].tobytes()
+    for k in ("n_iter_exec", "n_bla_steps", "n_rebase", "sum_stop_iter"):
+        assert a[4][k] == b[4][k]
+
+
+def test_tile_list_standard_loop_and_bad_tiles():
+    f = fsm.Mandelbrot(tempfile.mkdtemp())
+    f.zoom(x=-1.0, y=0.0, dx=5.0, nx=230, xy_ratio=1.0, theta_deg=0.)
+    f.calc_std_div(calc_name="s", subset=None, max_iter=2000, M_divergence=1000.,
+                   epsilon_stationnary=0.001)
+    indep = f._calc_data["s"]["cycle_indep_args"]
+    shapes, pix = [], []
+    for cs in f.chunk_slices():
+        pos = f.chunk_pixel_pos(cs, False, None)
+        shapes.append((pos.shape[1], pos.shape[0]))
+        pix.append(np.ravel(pos))
+    c_pix = np.ascontiguousarray(np.concatenate(pix))
+    n = c_pix.shape[0]
+    outs = []
+    for tl in (None, shapes):
+        Z = np.zeros((3, n), np.complex128)
+        U = np.zeros((0, n), np.int32)
+        sr = -np.ones((1, n), np.int8)
+        si = np.zeros((1, n), np.int32)
+        assert f.numba_cycle_call((c_pix, Z, U, sr, si), indep, tiles=tl) == 0
+        outs.append((Z, sr, si))
+    assert outs[0][0].tobytes() == outs[1][0].tobytes()
+    assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2])
+    with pytest.raises(ValueError):
+        f.numba_cycle_call((c_pix, Z, U, sr, si), indep, tiles=[(10, 10)])

@@ -27,13 +27,21 @@ from fractalshades_b200 import multi
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo")
 workdir = sys.argv[1]
-f = fsm.Mandelbrot(workdir)
-f.zoom(x=-1., y=0., dx=5., nx=500, xy_ratio=1.25, theta_deg=0.)
-# bind the calculation without creating a device frame
-kw = dict(calc_name="c", subset=None, max_iter=100, M_divergence=1000., epsilon_stationnary=1e-3)
-f.calc_std_div(**kw)
+def setup():
+    f = fsm.Mandelbrot(workdir)
+    f.zoom(x=-1., y=0., dx=5., nx=500, xy_ratio=1.25, theta_deg=0.)
+    # bind the calculation without creating a device frame
+    kw = dict(calc_name="c", subset=None, max_iter=100, M_divergence=1000., epsilon_stationnary=1e-3)
+    f.calc_std_div(**kw)
+    return f
+# rank 0 creates the directory, the parameter files and the memmaps first
 if rank == 0:
+    f = setup()
     f.init_report_mmap("c"); f.init_data_mmaps("c")
+    dist.barrier()
+else:
+    dist.barrier()
+    f = setup()
 dist.barrier()
 validator = multi.tile_validator(f, rank, world)
 n_mine = 0
@@ -81,7 +89,11 @@ def test_two_ranks_gloo_shared_memmaps():
     d = tempfile.mkdtemp()
     script = os.path.join(d, "worker.py")
     open(script, "w").write(WORKER % {"here": HERE})
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29653",
+    import socket
+    with socket.socket() as sk:          # a free rendezvous port
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
                WORLD_SIZE="2", OMP_NUM_THREADS="1")
     procs = []
     for rank in range(2):
