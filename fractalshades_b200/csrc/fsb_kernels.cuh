@@ -442,11 +442,59 @@ __device__ __forceinline__ T p_iter_deriv(T z, T dz, R ref_zn, D ref_d)
  * fail).  When it fails the iteration is redone in exact Xrange arithmetic. */
 __device__ __forceinline__ bool in_fast_range(double x)
 {
-    return (unsigned)(((hi32(x) >> 20) & 0x7ff) - (1023 - 460)) <= (unsigned)(460 + 900);
+    /* 2 * hi drops the sign bit; the exponent field then sits in bits 21-31 */
+    const unsigned lo = (unsigned)(1023 - 460) << 21, span = (unsigned)(460 + 900 + 1) << 21;
+    return 2u * (unsigned)hi32(x) - lo < span;
 }
 __device__ __forceinline__ bool in_fast_range(C z)
 {
     return in_fast_range(z.re) && in_fast_range(z.im);
+}
+
+/* Fused Xrange forms of the BLA step (perturbation.py:1139-1153).  Same real
+ * operations, in the same order and with the same roundings as the operator
+ * chain `A * z + B * c` of numba_xr.py (product mantissas, alignment to the
+ * larger exponent by exponent-field arithmetic clamped at 0, one rounded add
+ * per component) -- an Xrange value does not depend on how its mantissa /
+ * exponent split was normalised on the way, so only the bookkeeping is fused:
+ * one alignment instead of three normalisations. */
+__device__ __forceinline__ int cexp_field(C v)
+{
+    return max(expfield(v.re), expfield(v.im));
+}
+/* m * 2^shift on the exponent field (clamped at 0, mantissa bits kept, as
+ * _exp2_shift does); zeros pass through */
+__device__ __forceinline__ double xshift(double m, int shift)
+{
+    const int hi = hi32(m);
+    const int fld = (hi >> 20) & 0x7ff;
+    int nf = fld + shift;
+    nf = (fld == 0 || nf < 0) ? 0 : nf;
+    return mk64((hi & (int)0x800fffff) | (nf << 20), lo32(m));
+}
+__device__ __forceinline__ XC xr_lin(C A, XC z, C B, XC c)
+{
+    const C p = A * z.m, q = B * c.m;
+    const int fp = cexp_field(p), fq = cexp_field(q);
+    const int ep = z.e + (fp - 1023), eq = c.e + (fq - 1023);
+    int e = max(ep, eq);
+    if (fp == 0) e = eq;              /* a zero product does not set the exponent */
+    if (fq == 0) e = ep;
+    const int sp = (1023 - fp) - (e - ep), sq = (1023 - fq) - (e - eq);
+    return mkXC(mkC(xshift(p.re, sp) + xshift(q.re, sq), xshift(p.im, sp) + xshift(q.im, sq)), e);
+}
+__device__ __forceinline__ XC xr_mulc(C A, XC d)
+{
+    const C p = A * d.m;
+    const int fp = cexp_field(p);
+    return mkXC(mkC(xshift(p.re, 1023 - fp), xshift(p.im, 1023 - fp)), d.e + (fp - 1023));
+}
+/* to_standard of a value whose mantissa parts are below 4 in magnitude */
+__device__ __forceinline__ C to_std_small(XC x)
+{
+    if (x.e < -1200)        /* rounds to (signed) zero */
+        return mkC(mk64(hi32(x.m.re) & (int)0x80000000, 0), mk64(hi32(x.m.im) & (int)0x80000000, 0));
+    return to_std(x);
 }
 
 /* Template switches: XR = Xrange arithmetic (dx < 1e-300); DZNDC / DZNDZ =
@@ -530,10 +578,17 @@ k_perturb_m2(const __grid_constant__ FrameDev f, long long npts_ll,
                             zn_x = to_xr(zn);
                             if (DZNDC) dzndc_x = to_xr(dzndc);
                         }
+#ifdef FSB_GENERIC_XR_BLA   /* operator chain of numba_xr.py, kept for A/B checks */
                         zn_x = A * zn_x + B * c_xr;
                         zn = to_std(zn_x);
                         if (DZNDC) dzndc_x = A * dzndc_x;
                         if (DZNDZ) dzndz_x = A * dzndz_x;
+#else
+                        zn_x = xr_lin(A, zn_x, B, c_xr);
+                        zn = to_std_small(zn_x);
+                        if (DZNDC) dzndc_x = xr_mulc(A, dzndc_x);
+                        if (DZNDZ) dzndz_x = xr_mulc(A, dzndz_x);
+#endif
                         if (FASTXR) {
                             fast = in_fast_range(zn);
                             if (DZNDC && fast) {
@@ -632,10 +687,6 @@ k_perturb_m2(const __grid_constant__ FrameDev f, long long npts_ll,
             /* ---- divergence, :1252-1279 ---- */
             const C ref_zn_next = ldC(Zn, w_iter);
             ref_cur = ref_zn_next;
-            int knext = -1;
-            if (XR && has_xr && w_iter != 0 && fabs(ref_zn_next.re) < 1.e-300
-                && fabs(ref_zn_next.im) < 1.e-300)
-                knext = xr_find(f.ref_index_xr, f.n_xr_i, w_iter);
             const C ZZ = zn + ref_zn_next;
             const double full_sq_norm = norm2(ZZ);
             if (orbit) {
@@ -670,6 +721,11 @@ k_perturb_m2(const __grid_constant__ FrameDev f, long long npts_ll,
                             if (DZNDC) dzndc_x = to_xr(dzndc);
                             fast = false;
                         }
+                        /* Xrange value of the reference when it underflowed */
+                        int knext = -1;
+                        if (has_xr && w_iter != 0 && fabs(ref_zn_next.re) < 1.e-300
+                            && fabs(ref_zn_next.im) < 1.e-300)
+                            knext = xr_find(f.ref_index_xr, f.n_xr_i, w_iter);
                         ZZ_xr = (knext >= 0) ? (zn_x + REF_X(knext)) : (zn_x + ref_zn_next);
                         do_rebase = xr_le(abs2(ZZ_xr), abs2(zn_x));
                     }
