@@ -995,6 +995,59 @@ __device__ __forceinline__ void apply_bla_deriv_bs(const double *M, T &dxa, T &d
     dxa = a; dxb = b; dya = c; dyb = d;
 }
 
+/* Fused Xrange forms of apply_BLA_BS / apply_BLA_deriv_BS
+ * (perturbation.py:1793-1811), same idea as xr_lin: every product and every
+ * add of the reference's left-to-right chain is performed once, on mantissas
+ * aligned by exponent-field arithmetic; zero terms pass through an addition as
+ * in _coexp_ufunc (numba_xr.py:716-733). */
+#define XR_ZERO_E (-(1 << 28))
+__device__ __forceinline__ XF xf_prod(double M, XF v)
+{
+    const double p = M * v.m;
+    const int fld = expfield(p);
+    return mkXF(xshift(p, 1023 - fld), (fld == 0) ? XR_ZERO_E : v.e + (fld - 1023));
+}
+__device__ __forceinline__ XF xf_sum(XF s, XF p)
+{
+    const int se = (s.m == 0.) ? XR_ZERO_E : s.e;
+    const int e = max(se, p.e);
+    return mkXF(xshift(s.m, se - e) + xshift(p.m, p.e - e), e);
+}
+__device__ __forceinline__ XF xf_dot2(double m0, XF u, double m1, XF v)
+{
+    return xf_sum(xf_prod(m0, u), xf_prod(m1, v));
+}
+__device__ __forceinline__ XF xf_dot4(double m0, XF u, double m1, XF v, double m2, XF a,
+                                      double m3, XF b)
+{
+    return xf_sum(xf_sum(xf_dot2(m0, u, m1, v), xf_prod(m2, a)), xf_prod(m3, b));
+}
+__device__ __forceinline__ XF xf_clean(XF x)      /* zero results carry exponent 0 */
+{
+    return mkXF(x.m, (x.m == 0.) ? 0 : x.e);
+}
+/* to_standard of a value whose mantissa is below 4 in magnitude */
+__device__ __forceinline__ double to_std_small(XF x)
+{
+    if (x.e < -1200) return mk64(hi32(x.m) & (int)0x80000000, 0);
+    return to_std(x);
+}
+__device__ __forceinline__ void apply_bla_bs_xr(const double *M, XF &x, XF &y, XF a, XF b)
+{
+    const XF nx = xf_clean(xf_dot4(M[0], x, M[1], y, M[4], a, M[5], b));
+    const XF ny = xf_clean(xf_dot4(M[2], x, M[3], y, M[6], a, M[7], b));
+    x = nx; y = ny;
+}
+__device__ __forceinline__ void apply_bla_deriv_bs_xr(const double *M, XF &dxa, XF &dxb, XF &dya,
+                                                      XF &dyb)
+{
+    const XF a = xf_clean(xf_dot2(M[0], dxa, M[1], dya));
+    const XF b = xf_clean(xf_dot2(M[0], dxb, M[1], dyb));
+    const XF c = xf_clean(xf_dot2(M[2], dxa, M[3], dya));
+    const XF d = xf_clean(xf_dot2(M[2], dxb, M[3], dyb));
+    dxa = a; dxb = b; dya = c; dyb = d;
+}
+
 /* FASTXR: guarded fp64 fast path as in k_perturb_m2, enabled by the host for
  * flavours 1-3 only.  On top of the result guard it requires the reference
  * values themselves to be in range: the sign tests of diffabs() must see
@@ -1081,10 +1134,17 @@ k_perturb_bs(const __grid_constant__ FrameDev f, long long npts_ll,
                     ref_cur = ldC(Zn, w_iter);
                     if (XR) {
                         if (FASTXR && fast) TO_XR6();      /* M * (a, b) needs the exact a, b */
+#ifdef FSB_GENERIC_XR_BLA   /* operator chain of numba_xr.py, kept for A/B checks */
                         apply_bla_bs(M, x_x, y_x, a_x, b_x);
                         x = to_std(x_x);
                         y = to_std(y_x);
                         if (HESS) apply_bla_deriv_bs(M, dxa_x, dxb_x, dya_x, dyb_x);
+#else
+                        apply_bla_bs_xr(M, x_x, y_x, a_x, b_x);
+                        x = to_std_small(x_x);
+                        y = to_std_small(y_x);
+                        if (HESS) apply_bla_deriv_bs_xr(M, dxa_x, dxb_x, dya_x, dyb_x);
+#endif
                         if (FASTXR) TRY_FAST();
                     } else {
                         apply_bla_bs(M, x, y, a, b);
