@@ -281,18 +281,33 @@ perturb_kernel_t pick_m2(bool xr, bool dc, bool dz, bool bla, bool extra, bool f
 {
     return xr ? pick_m2_dc<true>(dc, dz, bla, extra, fastxr) : pick_m2_dc<false>(dc, dz, bla, extra, fastxr);
 }
-template <bool XR, bool H> perturb_kernel_t pick_bs_bla(bool bla, bool fastxr)
+template <bool XR, bool H, bool BLA, bool FX> perturb_kernel_t pick_bs_flavor(int flavor)
 {
-    if (XR && fastxr) return bla ? k_perturb_bs<XR, H, true, XR> : k_perturb_bs<XR, H, false, XR>;
-    return bla ? k_perturb_bs<XR, H, true, false> : k_perturb_bs<XR, H, false, false>;
+    if constexpr (!XR) {
+        return k_perturb_bs<XR, H, BLA, false, 0>;         /* small kernels: run-time flavour */
+    } else {
+        switch (flavor) {
+        case 1: return k_perturb_bs<XR, H, BLA, FX, 1>;
+        case 2: return k_perturb_bs<XR, H, BLA, FX, 2>;
+        case 3: return k_perturb_bs<XR, H, BLA, FX, 3>;
+        case 4: return k_perturb_bs<XR, H, BLA, false, 4>; /* no fp64 lane for flavours 4-5 */
+        default: return k_perturb_bs<XR, H, BLA, false, 5>;
+        }
+    }
 }
-template <bool XR> perturb_kernel_t pick_bs_h(bool h, bool bla, bool fastxr)
+template <bool XR, bool H> perturb_kernel_t pick_bs_bla(bool bla, bool fastxr, int flavor)
 {
-    return h ? pick_bs_bla<XR, true>(bla, fastxr) : pick_bs_bla<XR, false>(bla, fastxr);
+    if (XR && fastxr && flavor <= 3)
+        return bla ? pick_bs_flavor<XR, H, true, XR>(flavor) : pick_bs_flavor<XR, H, false, XR>(flavor);
+    return bla ? pick_bs_flavor<XR, H, true, false>(flavor) : pick_bs_flavor<XR, H, false, false>(flavor);
 }
-perturb_kernel_t pick_bs(bool xr, bool h, bool bla, bool fastxr)
+template <bool XR> perturb_kernel_t pick_bs_h(bool h, bool bla, bool fastxr, int flavor)
 {
-    return xr ? pick_bs_h<true>(h, bla, fastxr) : pick_bs_h<false>(h, bla, fastxr);
+    return h ? pick_bs_bla<XR, true>(bla, fastxr, flavor) : pick_bs_bla<XR, false>(bla, fastxr, flavor);
+}
+perturb_kernel_t pick_bs(bool xr, bool h, bool bla, bool fastxr, int flavor)
+{
+    return xr ? pick_bs_h<true>(h, bla, fastxr, flavor) : pick_bs_h<false>(h, bla, fastxr, flavor);
 }
 
 } /* namespace */
@@ -1224,7 +1239,7 @@ static int frame_enqueue(Ctx *c, fsb_frame *f, cudaStream_t st, int slot, const 
     perturb_kernel_t k = (d.model == FSB_MODEL_M2)
         ? pick_m2(d.xr_detect != 0, d.calc_dzndc != 0, d.calc_dzndz != 0, f->bla_on,
                   f->dev.order_i > 0 || d.calc_orbit != 0, f->fast_xr)
-        : pick_bs(d.xr_detect != 0, d.calc_dzndc != 0, f->bla_on, f->fast_xr);
+        : pick_bs(d.xr_detect != 0, d.calc_dzndc != 0, f->bla_on, f->fast_xr, d.flavor);
     unsigned long long *ctl = c->d_ctl + slot * CTL_WORDS;
     CK(cudaMemsetAsync(ctl, 0, CTL_WORDS * sizeof(unsigned long long), st));
     const int block = 128;

@@ -1053,7 +1053,11 @@ __device__ __forceinline__ void apply_bla_deriv_bs_xr(const double *M, XF &dxa, 
  * values themselves to be in range: the sign tests of diffabs() must see
  * products that cannot underflow (flavours 4-5 multiply a possibly cancelled
  * sum and are left on the exact Xrange path). */
-template <bool XR, bool HESS, bool BLA, bool FASTXR = false>
+/* FLAVOR: 1..5 = the flavour is a compile-time constant (Xrange kernels: one
+ * flavour per instance keeps the code a fifth of the size -- the all-flavour
+ * Xrange + hessian kernel was 18 000 instructions and spent two thirds of its
+ * time waiting on instruction fetch); 0 = read it from the frame. */
+template <bool XR, bool HESS, bool BLA, bool FASTXR = false, int FLAVOR = 0>
 __global__ void __launch_bounds__(128)
 k_perturb_bs(const __grid_constant__ FrameDev f, long long npts_ll,
              const C *__restrict__ c_pix, double *__restrict__ Z,
@@ -1065,7 +1069,7 @@ k_perturb_bs(const __grid_constant__ FrameDev f, long long npts_ll,
     unsigned long long n_exec = 0, n_bla = 0, n_reb = 0, n_sum = 0, n_fast = 0;
     const int L = f.Li;
     const bool has_xr = f.n_xr_i > 0;
-    const int flavor = f.flavor;
+    const int flavor = (FLAVOR > 0) ? FLAVOR : f.flavor;
     const int ref_div_iter = f.ref_div_i;
     const int max_iter = f.max_iter_i;
     const int first_invalid = f.first_invalid_i;

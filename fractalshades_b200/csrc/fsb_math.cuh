@@ -19,6 +19,15 @@
 #include <string.h>
 
 #define FSB_HD __host__ __device__ __forceinline__
+/* Real Xrange operators are real calls on the device: the burning-ship Xrange
+ * code chains some eighty of them per iteration, and inlined they put the
+ * kernel far beyond the instruction cache (it then waits on instruction fetch
+ * two cycles out of three). */
+#ifdef __CUDA_ARCH__
+#define FSB_XF_OP static __device__ __noinline__
+#else
+#define FSB_XF_OP static inline
+#endif
 
 namespace fsb {
 
@@ -205,7 +214,29 @@ FSB_HD XF to_xr(double v) { return normalize(v, 0); }
 FSB_HD XC to_xr(C v) { return normalize(v, 0); }
 
 /* numba_xr.py:802-829 */
-FSB_HD double to_std(XF x) { return ldexp(x.m, x.e); }
+/* m * 2^e: exact exponent-field arithmetic while the mantissa and the result
+ * are normal doubles (the common case, a dozen instructions); everything else
+ * -- zeros, denormal results, overflow -- goes to one out-of-line ldexp so that
+ * the many call sites stay small (instruction-cache footprint). */
+#ifdef __CUDA_ARCH__
+static __device__ __noinline__ double ldexp_slow(double m, int e) { return ldexp(m, e); }
+#endif
+FSB_HD double to_std(XF x)
+{
+#ifdef __CUDA_ARCH__
+    const int hi = hi32(x.m);
+    const int fld = (hi >> 20) & 0x7ff;
+    const int nf = fld + x.e;
+    if (fld != 0 && fld != 0x7ff && x.e > -8192 && x.e < 8192) {
+        if (nf > 0 && nf < 0x7ff) return mk64(hi + (x.e << 20), lo32(x.m));
+        if (nf < -53) return mk64(hi & (int)0x80000000, 0);    /* below half the smallest denormal */
+    }
+    if (x.m == 0.) return x.m;
+    return ldexp_slow(x.m, x.e);
+#else
+    return ldexp(x.m, x.e);
+#endif
+}
 FSB_HD C to_std(XC x)
 {
     XC n = normalize(x.m, x.e);
@@ -214,13 +245,13 @@ FSB_HD C to_std(XC x)
 }
 
 /* add / sub, numba_xr.py:318-388 */
-FSB_HD XF operator+(XF a, XF b)
+FSB_XF_OP XF operator+(XF a, XF b)
 {
     double x, y; int e;
     coexp_f(a.m, a.e, b.m, b.e, x, y, e);
     return mkXF(x + y, e);
 }
-FSB_HD XF operator-(XF a, XF b)
+FSB_XF_OP XF operator-(XF a, XF b)
 {
     double x, y; int e;
     coexp_f(a.m, a.e, b.m, b.e, x, y, e);
@@ -246,7 +277,7 @@ FSB_HD XC operator+(XC a, XF b)
 }
 
 /* mul, numba_xr.py:416-444 */
-FSB_HD XF xr_pack(double m, int e) { return need_renorm(m) ? normalize(m, e) : mkXF(m, e); }
+FSB_XF_OP XF xr_pack(double m, int e) { return need_renorm(m) ? normalize(m, e) : mkXF(m, e); }
 FSB_HD XC xr_pack(C m, int e) { return need_renorm(m) ? normalize(m, e) : mkXC(m, e); }
 FSB_HD XF operator*(XF a, XF b) { return xr_pack(a.m * b.m, a.e + b.e); }
 FSB_HD XF operator*(XF a, double b) { return xr_pack(a.m * b, a.e); }
