@@ -219,9 +219,9 @@ FSB_HD XC to_xr(C v) { return normalize(v, 0); }
  * -- zeros, denormal results, overflow -- goes to one out-of-line ldexp so that
  * the many call sites stay small (instruction-cache footprint). */
 #ifdef __CUDA_ARCH__
-static __device__ __noinline__ double ldexp_slow(double m, int e) { return ldexp(m, e); }
+static __device__ __forceinline__ double ldexp_slow(double m, int e) { return ldexp(m, e); }
 #endif
-FSB_HD double to_std(XF x)
+FSB_XF_OP double to_std(XF x)
 {
 #ifdef __CUDA_ARCH__
     const int hi = hi32(x.m);
