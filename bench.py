@@ -76,6 +76,8 @@ WORKLOADS = {
 # ---------------------------------------------------------------------------
 def make_fractal(w, nx=None):
     import fractalshades_b200.models as fsm
+    from fractalshades_b200 import settings
+    settings.no_newton = True      # reference point = image centre
     cls = {"std_M2": fsm.Mandelbrot, "std_BS": fsm.Burning_ship,
            "perturb_M2": fsm.Perturbation_mandelbrot,
            "perturb_BS": fsm.Perturbation_burning_ship}[w["kind"]]

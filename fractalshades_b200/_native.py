@@ -80,7 +80,8 @@ CUDA_SYMBOLS = [
     "fsb_xr_binop_c", "fsb_xr_to_standard_c", "fsb_hypot_test",
     "fsb_fp64_peak_tflops",
 ]
-ORBIT_SYMBOLS = ["fsb_orbit_mandelbrot", "fsb_orbit_burning_ship"]
+ORBIT_SYMBOLS = ["fsb_orbit_mandelbrot", "fsb_orbit_burning_ship",
+                 "fsb_ball_method_mandelbrot", "fsb_find_nucleus_mandelbrot"]
 
 _libs = {}
 
@@ -204,6 +205,13 @@ def load_orbit_lib():
         lib.fsb_orbit_mandelbrot.argtypes = [c_vp, c_i64, ctypes.c_uint32] + common
         lib.fsb_orbit_burning_ship.restype = c_i64
         lib.fsb_orbit_burning_ship.argtypes = [c_vp, c_i64, ctypes.c_int] + common
+        lib.fsb_ball_method_mandelbrot.restype = c_i64
+        lib.fsb_ball_method_mandelbrot.argtypes = [
+            ctypes.c_char_p, ctypes.c_char_p, c_i64, ctypes.c_char_p, c_i64, c_dbl]
+        lib.fsb_find_nucleus_mandelbrot.restype = ctypes.c_int
+        lib.fsb_find_nucleus_mandelbrot.argtypes = [
+            ctypes.c_char_p, ctypes.c_char_p, c_i64, c_i64, c_i64, ctypes.c_char_p,
+            ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_char_p, c_i64]
         _libs["orbit"] = lib
     return _libs["orbit"]
 

@@ -65,6 +65,20 @@ extern int mpc_sqr(fsb_mpc_struct *, const fsb_mpc_struct *, int);
 extern int mpc_add(fsb_mpc_struct *, const fsb_mpc_struct *, const fsb_mpc_struct *, int);
 extern int mpc_pow_ui(fsb_mpc_struct *, const fsb_mpc_struct *, unsigned long, int);
 
+extern int mpc_mul(fsb_mpc_struct *, const fsb_mpc_struct *, const fsb_mpc_struct *, int);
+extern int mpc_mul_si(fsb_mpc_struct *, const fsb_mpc_struct *, long, int);
+extern int mpc_mul_fr(fsb_mpc_struct *, const fsb_mpc_struct *, const fsb_mpfr_struct *, int);
+extern int mpc_add_ui(fsb_mpc_struct *, const fsb_mpc_struct *, unsigned long, int);
+extern int mpc_sub(fsb_mpc_struct *, const fsb_mpc_struct *, const fsb_mpc_struct *, int);
+extern int mpc_div(fsb_mpc_struct *, const fsb_mpc_struct *, const fsb_mpc_struct *, int);
+extern int mpc_abs(fsb_mpfr_struct *, const fsb_mpc_struct *, int);
+extern void mpc_swap(fsb_mpc_struct *, fsb_mpc_struct *);
+extern int mpfr_ui_div(fsb_mpfr_struct *, unsigned long, const fsb_mpfr_struct *, int);
+extern int mpfr_cmp_d(const fsb_mpfr_struct *, double);
+extern int mpfr_greaterequal_p(const fsb_mpfr_struct *, const fsb_mpfr_struct *);
+extern char *mpfr_get_str(char *, long *, int, size_t, const fsb_mpfr_struct *, int);
+extern void mpfr_free_str(char *);
+
 /* Thresholds: fs.settings.newton_zoom_level / xrange_zoom_level
  * (reference settings.py:14,22; captured at FP_loop.pyx:141-143). */
 static const double XR_TSHOLD = 1.e-300;
@@ -258,4 +272,159 @@ done:
     mpfr_clear(ysq);
     mpfr_clear(xy);
     return i;
+}
+
+
+/* ======================================================================== */
+/* Period (ball method) and nucleus (Newton) of the reference point           */
+
+/* one step of z <- z^2 + c with its derivative dz/dc <- 2 z dz/dc + 1, in the
+ * call order of iter_deriv_M2 / iter_M2 (FP_loop.pyx:158-190) */
+static void m2_step_deriv(fsb_mpc_struct *z, fsb_mpc_struct *dz, const fsb_mpc_struct *c,
+                          fsb_mpc_struct *tmp)
+{
+    mpc_mul(tmp, z, dz, RNDNN);
+    mpc_mul_si(dz, tmp, 2, RNDNN);
+    mpc_add_ui(dz, dz, 1, RNDNN);
+    mpc_sqr(tmp, z, RNDNN);
+    mpc_add(z, tmp, c, RNDNN);
+}
+
+/* FP_loop.pyx:605-758 : first i with |z_i / (dz_i/dc)| < px, -1 if none */
+int64_t fsb_ball_method_mandelbrot(const char *seed_x, const char *seed_y, int64_t prec_bits,
+                                   const char *seed_px, int64_t maxiter, double M_divergence)
+{
+    fsb_mpc_t c, z, dz, tmp, r;
+    fsb_mpfr_t ar, x_t, y_t, pix, inv_pix;
+    int64_t ret = -1, i;
+    mpc_init2(c, prec_bits); mpc_init2(z, prec_bits); mpc_init2(dz, prec_bits);
+    mpc_init2(tmp, prec_bits); mpc_init2(r, prec_bits);
+    mpfr_init2(ar, 54); mpfr_init2(x_t, prec_bits); mpfr_init2(y_t, prec_bits);
+    mpfr_init2(pix, prec_bits); mpfr_init2(inv_pix, prec_bits);
+    if (mpfr_set_str(x_t, seed_x, 10, RNDN) != 0 || mpfr_set_str(y_t, seed_y, 10, RNDN) != 0 ||
+        mpfr_set_str(pix, seed_px, 10, RNDN) != 0) {
+        ret = -3;
+        goto done;
+    }
+    mpc_set_fr_fr(c, x_t, y_t, RNDNN);
+    mpfr_ui_div(inv_pix, 1, pix, RNDN);
+    mpc_set_si_si(z, 0, 0, RNDNN);
+    mpc_set_si_si(dz, 0, 0, RNDNN);
+    for (i = 1; i <= maxiter; i++) {
+        m2_step_deriv(z, dz, c, tmp);
+        mpc_div(r, z, dz, RNDNN);
+        mpc_mul_fr(r, r, inv_pix, RNDNN);
+        if (hypot(mpfr_get_d(z->re, RNDN), mpfr_get_d(z->im, RNDN)) > M_divergence) break;
+        mpc_abs(ar, r, RNDN);
+        if (mpfr_cmp_d(ar, 1.) < 0) { ret = i; break; }
+    }
+done:
+    mpc_clear(c); mpc_clear(z); mpc_clear(dz); mpc_clear(tmp); mpc_clear(r);
+    mpfr_clear(ar); mpfr_clear(x_t); mpfr_clear(y_t); mpfr_clear(pix); mpfr_clear(inv_pix);
+    return ret;
+}
+
+/* "<sign>0.<digits>e<exp>" with enough digits for an exact round trip */
+static int put_decimal(char *out, int64_t cap, const fsb_mpfr_struct *v)
+{
+    long e = 0;
+    char *d = mpfr_get_str(NULL, &e, 10, 0, v, RNDN);
+    if (!d) return -1;
+    const char *digits = d;
+    int neg = (d[0] == '-');
+    if (neg) digits++;
+    size_t need = strlen(digits) + 40;
+    int rc = -1;
+    if ((int64_t)need <= cap) {
+        char ebuf[32];
+        int k = 0;
+        if (neg) out[k++] = '-';
+        out[k++] = '0'; out[k++] = '.';
+        strcpy(out + k, digits);
+        k += (int)strlen(digits);
+        out[k++] = 'e';
+        /* long to string */
+        long ev = e; int m = 0, j;
+        if (ev < 0) { out[k++] = '-'; ev = -ev; }
+        do { ebuf[m++] = (char)('0' + ev % 10); ev /= 10; } while (ev > 0);
+        for (j = m - 1; j >= 0; j--) out[k++] = ebuf[j];
+        out[k] = 0;
+        rc = 0;
+    }
+    mpfr_free_str(d);
+    return rc;
+}
+
+/* FP_loop.pyx:900-1118 (divide by the roots of the divisors of `order`) and
+ * :1159-1340 (any_nucleus != 0: plain Newton on z_order(c)).  Returns 1 when the
+ * descent converged to a point whose |z_order| passes eps_valid, 0 otherwise. */
+int fsb_find_nucleus_mandelbrot(const char *seed_x, const char *seed_y, int64_t prec_bits,
+                                int64_t order, int64_t max_newton, const char *seed_eps_cv,
+                                const char *seed_eps_valid, int any_nucleus, char *out_x,
+                                char *out_y, int64_t out_cap)
+{
+    fsb_mpc_t c, zr, dzr, h, dh, f, df, t1, t2;
+    fsb_mpfr_t x_t, y_t, abs_diff, eps;
+    int cv = 0;
+    int64_t i_newton, i;
+    if (order < 1) return -2;
+    mpc_init2(c, prec_bits); mpc_init2(zr, prec_bits); mpc_init2(dzr, prec_bits);
+    mpc_init2(h, prec_bits); mpc_init2(dh, prec_bits); mpc_init2(f, prec_bits);
+    mpc_init2(df, prec_bits); mpc_init2(t1, prec_bits); mpc_init2(t2, prec_bits);
+    mpfr_init2(x_t, prec_bits); mpfr_init2(y_t, prec_bits);
+    mpfr_init2(abs_diff, 54); mpfr_init2(eps, 54);
+    if (mpfr_set_str(x_t, seed_x, 10, RNDN) != 0 || mpfr_set_str(y_t, seed_y, 10, RNDN) != 0 ||
+        mpfr_set_str(eps, seed_eps_cv, 10, RNDN) != 0) {
+        cv = -3;
+        goto done;
+    }
+    mpc_set_fr_fr(c, x_t, y_t, RNDNN);
+    mpfr_mul_si(eps, eps, 64, RNDN);
+    for (i_newton = 0; i_newton < max_newton; i_newton++) {
+        mpc_set_si_si(zr, 0, 0, RNDNN);
+        mpc_set_si_si(dzr, 0, 0, RNDNN);
+        if (any_nucleus) {
+            for (i = 1; i <= order; i++) m2_step_deriv(zr, dzr, c, t1);
+            mpc_div(t1, zr, dzr, RNDNN);                 /* Newton step f / f' */
+            mpc_sub(c, c, t1, RNDNN);
+        } else {
+            mpc_set_si_si(h, 1, 0, RNDNN);
+            mpc_set_si_si(dh, 0, 0, RNDNN);
+            for (i = 1; i <= order; i++) {
+                mpc_mul_si(t1, dzr, 2, RNDNN);
+                mpc_mul(t2, t1, zr, RNDNN);
+                mpc_add_ui(dzr, t2, 1, RNDNN);
+                mpc_sqr(t1, zr, RNDNN);
+                mpc_add(zr, t1, c, RNDNN);
+                if (i < order && order % i == 0) {       /* h *= z_i ; dh += z_i' / z_i */
+                    mpc_mul(t1, h, zr, RNDNN);
+                    mpc_swap(t1, h);
+                    mpc_div(t1, dzr, zr, RNDNN);
+                    mpc_add(t2, t1, dh, RNDNN);
+                    mpc_swap(t2, dh);
+                }
+            }
+            mpc_div(f, zr, h, RNDNN);                    /* f = z / h */
+            mpc_mul(t1, zr, dh, RNDNN);
+            mpc_sub(t2, dzr, t1, RNDNN);
+            mpc_div(df, t2, h, RNDNN);                   /* f' = (z' - z dh) / h */
+            mpc_div(t1, f, df, RNDNN);
+            mpc_sub(t2, c, t1, RNDNN);
+            mpc_swap(t2, c);
+        }
+        mpc_abs(abs_diff, t1, RNDN);
+        if (mpfr_greaterequal_p(eps, abs_diff)) {
+            mpc_abs(abs_diff, zr, RNDN);
+            if (mpfr_set_str(eps, seed_eps_valid, 10, RNDN) != 0) { cv = -3; goto done; }
+            cv = mpfr_greaterequal_p(eps, abs_diff) ? 1 : 0;
+            break;
+        }
+    }
+    if (cv == 1 && (put_decimal(out_x, out_cap, c->re) != 0 || put_decimal(out_y, out_cap, c->im) != 0))
+        cv = -4;
+done:
+    mpc_clear(c); mpc_clear(zr); mpc_clear(dzr); mpc_clear(h); mpc_clear(dh); mpc_clear(f);
+    mpc_clear(df); mpc_clear(t1); mpc_clear(t2);
+    mpfr_clear(x_t); mpfr_clear(y_t); mpfr_clear(abs_diff); mpfr_clear(eps);
+    return cv;
 }

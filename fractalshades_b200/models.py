@@ -9,6 +9,9 @@ of three factories `set_state / initialize / iterate`, utils.py:278-339,
 core.py:1918-1949); since numba closures cannot cross the C ABI, `initialize()`
 and `iterate()` return a `KernelSpec` naming the device-kernel variant.
 """
+import ctypes
+
+import mpmath
 import numpy as np
 
 from . import settings
@@ -122,6 +125,55 @@ class Perturbation_mandelbrot(PerturbationFractal):
     def FP_loop(self, NP_orbit, c0):
         """ models/mandelbrot_M2.py:408-430 -> native MPFR orbit """
         return self._native_orbit(NP_orbit, c0, flavor=None, exponent=2)
+
+    @staticmethod
+    def _ball_method(c, px, maxiter, M_divergence):
+        """ models/mandelbrot_M2.py:634-650 -> fsb_ball_method_mandelbrot """
+        lib = _native.load_orbit_lib()
+        order = lib.fsb_ball_method_mandelbrot(
+            str(c.real).encode("utf8"), str(c.imag).encode("utf8"),
+            mpmath.mp.prec, str(px).encode("utf8"), int(maxiter),
+            float(M_divergence))
+        if order < -1:
+            raise RuntimeError(f"fsb_ball_method_mandelbrot failed ({order})")
+        return None if order == -1 else int(order)
+
+    @staticmethod
+    def _newton(c, order, eps_pixel, max_newton, eps_cv, any_nucleus):
+        if order is None:
+            raise ValueError("order shall be defined for Newton method")
+        seed_prec = mpmath.mp.prec
+        if max_newton is None:
+            max_newton = 80
+        if eps_cv is None:
+            eps_cv = mpmath.mpf(val=(2, -seed_prec))
+        cap = int(seed_prec * 0.31) + 64
+        bx = ctypes.create_string_buffer(cap)
+        by = ctypes.create_string_buffer(cap)
+        lib = _native.load_orbit_lib()
+        rc = lib.fsb_find_nucleus_mandelbrot(
+            str(c.real).encode("utf8"), str(c.imag).encode("utf8"), seed_prec,
+            int(order), int(max_newton), str(eps_cv).encode("utf8"),
+            str(eps_pixel).encode("utf8"), int(any_nucleus), bx, by, cap)
+        if rc < 0:
+            raise RuntimeError(f"fsb_find_nucleus_mandelbrot failed ({rc})")
+        if rc == 0:
+            return False, mpmath.mpc("nan", "nan")
+        return True, mpmath.mpc(mpmath.mpf(bx.value.decode()),
+                                mpmath.mpf(by.value.decode()))
+
+    @staticmethod
+    def find_nucleus(c, order, eps_pixel, max_newton=None, eps_cv=None):
+        """ models/mandelbrot_M2.py:654-685 : Newton descent on z_order(c) with
+        the roots of the divisors of `order` divided out """
+        return Perturbation_mandelbrot._newton(c, order, eps_pixel, max_newton,
+                                               eps_cv, False)
+
+    @staticmethod
+    def find_any_nucleus(c, order, eps_pixel, max_newton=None, eps_cv=None):
+        """ models/mandelbrot_M2.py:688-714 : plain Newton descent """
+        return Perturbation_mandelbrot._newton(c, order, eps_pixel, max_newton,
+                                               eps_cv, True)
 
     @calc_options
     def calc_std_div(self, *, calc_name: str, subset, max_iter: int,

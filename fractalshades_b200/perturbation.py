@@ -297,20 +297,72 @@ class PerturbationFractal(Fractal):
         return self._Zn_path
 
     def get_FP_orbit(self, c0=None, newton="cv", order=None, max_newton=None):
-        """ perturbation.py:651-768 without the Newton / ball-method branch
-        (settings.no_newton semantics: the image centre is the reference) """
+        """ perturbation.py:651-768 : reference point = the nucleus found by
+        the ball method + Newton descent around the image centre (periodic
+        reference, `ref_order` wrap), or the image centre itself when
+        settings.no_newton is set, the descent fails, or the model has no
+        native nucleus search. """
+        if newton == "step":
+            raise NotImplementedError("step option not Implemented (yet)")
         if self.ref_point_matching():
             return
         if self.dx > settings.newton_zoom_level:
             self.compute_critical_orbit(self.critical_pt)
             return
-        if not settings.no_newton:
-            raise NotImplementedError(
-                "Newton / ball-method nucleus search is outside the GPU hot "
-                "path; keep settings.no_newton = True")
         if c0 is None:
             c0 = self.x + 1j * self.y
-        self.compute_FP_orbit(c0, None)
+        if settings.no_newton or (newton is None) or (newton == "None"):
+            self.compute_FP_orbit(c0, None)
+            return
+        if not hasattr(self, "find_any_nucleus"):
+            # the burning-ship family: no native nucleus search (reference
+            # FP_loop.pyx:2217-2755) -- documented deviation, image centre
+            import warnings
+            warnings.warn(
+                f"{type(self).__name__}: no native nucleus search (ball method "
+                "+ Newton); the image centre is used as reference point, as "
+                "with settings.no_newton = True", RuntimeWarning)
+            self.compute_FP_orbit(c0, None)
+            return
+        if order is None:
+            order = self.ball_method(c0, self.dx * 1.0)
+            if order is None:            # ball method failed: image centre
+                self.compute_FP_orbit(c0, None)
+                return
+        max_attempt = 2
+        eps_pixel = self.dx * (1. / self.nx)
+
+        def descent(no_div_allowed=True):
+            if no_div_allowed:
+                try:
+                    return True, self.find_nucleus(c0, order, eps_pixel,
+                                                   max_newton=max_newton)
+                except NotImplementedError:
+                    pass
+            return False, self.find_any_nucleus(c0, order, eps_pixel,
+                                                max_newton=max_newton)
+        _, (newton_cv, nucleus) = descent()
+        attempt = 1
+        if not newton_cv:
+            while (not newton_cv) and attempt <= max_attempt:
+                attempt += 1
+                mpmath.mp.dps = int(1.25 * mpmath.mp.dps)
+                eps_pixel = self.dx * (1. / self.nx)
+                no_div, (newton_cv, nucleus) = descent()
+                if no_div and (not newton_cv) and (attempt == max_attempt):
+                    # last try: accept the cycles of the divisors of the order
+                    newton_cv, nucleus = self.find_any_nucleus(
+                        c0, order, eps_pixel, max_newton=max_newton)
+        if not newton_cv:
+            order = None                 # the reference cannot be wrapped
+            nucleus = c0
+        self.compute_FP_orbit(nucleus, order)
+
+    def ball_method(self, c, px, kind=1, M_divergence=1.e5):
+        """ perturbation.py:857-867 : first period of the nucleus around c """
+        if kind != 1:
+            raise NotImplementedError("ball method kind 2")
+        return self._ball_method(c, px, self.max_iter, M_divergence)
 
     def _fp_base(self, ref_point, order):
         init_kwargs = self.init_kwargs

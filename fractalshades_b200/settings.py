@@ -8,9 +8,12 @@ skip_calc = False              # settings.py:10
 newton_zoom_level = 1.e-5      # settings.py:14 ; also gates BLA
 std_zoom_level = 1.e-8         # settings.py:18
 xrange_zoom_level = 1.e-300    # settings.py:22
-# The ball-method / Newton nucleus search is not part of this hot path (SURVEY
-# section 8 f-1): the reference point is always the image centre.
-no_newton = True               # settings.py:25 (reference default: False)
+# False (the reference's default): the reference point of a perturbation frame
+# is the nucleus found by the ball method + Newton descent around the image
+# centre (holomorphic power-2 model; the burning-ship family has no native
+# nucleus search and uses the image centre with a warning).  True: always the
+# image centre -- what bench.py and the parity fixtures use.
+no_newton = False              # settings.py:25
 inspect_calc = False           # settings.py:30
 chunk_size = 200               # settings.py:34
 BLA_compression = 3            # settings.py:40 (fixed: the kernels fold 3 levels)

@@ -66,6 +66,32 @@ int64_t fsb_orbit_burning_ship(double *orbit, int64_t max_iter, int flavor,
                                fsb_orbit_xr *xr_out, int64_t xr_cap,
                                int64_t *xr_count);
 
+/* ---- period and nucleus of the reference point (holomorphic z^2 + c) ----
+ *   fsb_ball_method_mandelbrot   <- perturbation_mandelbrot_ball_method
+ *                                   (FP_loop.pyx:605-758): first iteration i
+ *                                   <= maxiter with |z_i / (dz_i/dc)| < px;
+ *                                   -1 when the point escapes first or no such
+ *                                   i exists, -3 on a bad number string
+ *   fsb_find_nucleus_mandelbrot  <- perturbation_mandelbrot_find_nucleus
+ *                                   (:900-1118, any_nucleus = 0: the roots of
+ *                                   the divisors of `order` are divided out) /
+ *                                   perturbation_mandelbrot_find_any_nucleus
+ *                                   (:1119-1340, any_nucleus = 1).
+ *                                   eps_cv is multiplied by 64 as in the
+ *                                   reference; converged and |z_order| <=
+ *                                   eps_valid -> returns 1 and writes the
+ *                                   nucleus as decimal strings (exact round
+ *                                   trip at prec_bits) into out_x / out_y
+ *                                   (capacity out_cap bytes each); 0 = did not
+ *                                   converge; < 0 error (-4: out_cap too small)
+ */
+int64_t fsb_ball_method_mandelbrot(const char *seed_x, const char *seed_y, int64_t prec_bits,
+                                   const char *seed_px, int64_t maxiter, double M_divergence);
+int fsb_find_nucleus_mandelbrot(const char *seed_x, const char *seed_y, int64_t prec_bits,
+                                int64_t order, int64_t max_newton, const char *seed_eps_cv,
+                                const char *seed_eps_valid, int any_nucleus, char *out_x,
+                                char *out_y, int64_t out_cap);
+
 #ifdef __cplusplus
 }
 #endif

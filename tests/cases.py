@@ -30,6 +30,17 @@ CASES = {
         y="0.", dx="5.e-20", nx=64,
         calc=dict(max_iter=50000, BLA_eps=1e-6, interior_detect=False,
                   calc_dzndc=True, **_STD)),
+    # reference's default flow: ball method + Newton -> periodic reference orbit
+    "p_M2_E20_newton": dict(
+        kind="perturb_M2", precision=30, x="-1.74928893611435556407228",
+        y="0.", dx="5.e-20", nx=64, newton=True,
+        calc=dict(max_iter=50000, BLA_eps=1e-6, interior_detect=False,
+                  calc_dzndc=True, **_STD)),
+    "p_M2_int_E11_newton": dict(
+        kind="perturb_M2", precision=17, x="-1.74920463345912691e+00",
+        y="-2.8684660237361114e-04", dx="5e-12", nx=64, newton=True,
+        calc=dict(max_iter=50000, BLA_eps=1e-6, interior_detect=True,
+                  calc_dzndc=True, **_STD)),
     "p_M2_E20_nobla_interior": dict(
         kind="perturb_M2", precision=30, x="-1.74928893611435556407228",
         y="0.", dx="5.e-20", nx=48,

@@ -22,3 +22,15 @@ def _build_native():
     import oracle_lib
     oracle_lib.build()
     yield
+
+
+@pytest.fixture(autouse=True)
+def _reference_point_is_image_centre():
+    """ The fixtures were generated with the image centre as reference point
+    (settings.no_newton = True on both sides); cases and
+    tests of the nucleus search switch it off themselves. """
+    from fractalshades_b200 import settings
+    old = settings.no_newton
+    settings.no_newton = True
+    yield
+    settings.no_newton = old

@@ -43,6 +43,9 @@ def make_fractal(name, workdir=None):
     if case["kind"].startswith("perturb"):
         zoom["precision"] = case["precision"]
     f.zoom(**zoom)
+    # cases flagged newton=True use the reference's default flow (nucleus
+    # search -> periodic reference); the flag is read when the orbit is built
+    f._case_newton = bool(case.get("newton", False))
     return f, case
 
 
@@ -66,9 +69,15 @@ def all_c_pix(f):
 
 def host_tables(name):
     """ Per-frame tables from the product's host code (no GPU). """
+    from fractalshades_b200 import settings
     f, case = make_fractal(name)
     bind_calc(f, case)
-    t = f.frame_tables()
+    old = settings.no_newton
+    settings.no_newton = not f._case_newton
+    try:
+        t = f.frame_tables()
+    finally:
+        settings.no_newton = old
     return f, case, t
 
 

@@ -30,7 +30,8 @@ def main():
     import mpmath
     import fractalshades_b200 as fsb
     import fractalshades_b200.models as fsm
-    from fractalshades_b200 import movie, multi
+    from fractalshades_b200 import movie, multi, settings
+    settings.no_newton = True      # reference point = image centre
     v = fsb.VIEWS["deep_julia_2608"]
     digits = int(-float(mpmath.log10(mpmath.mpf(args.dx_end)))) + 30
     directory = args.dir or os.path.join(tempfile.gettempdir(), "fsb_movie")

@@ -98,6 +98,42 @@ def _make_shim(fsx):
             xr[int(e.index)] = (x_Xr, y_Xr)
         return i, {}, xr
 
+    # period / nucleus search: same contract as FP_loop.pyx:605-758, 900-1340
+    lib.fsb_ball_method_mandelbrot.restype = ctypes.c_int64
+    lib.fsb_ball_method_mandelbrot.argtypes = [
+        ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int64, ctypes.c_char_p,
+        ctypes.c_int64, ctypes.c_double]
+    lib.fsb_find_nucleus_mandelbrot.restype = ctypes.c_int
+    lib.fsb_find_nucleus_mandelbrot.argtypes = [
+        ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int64, ctypes.c_int64,
+        ctypes.c_int64, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int,
+        ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int64]
+
+    def perturbation_mandelbrot_ball_method(seed_x, seed_y, seed_prec, seed_px,
+                                            maxiter, M_divergence):
+        return int(lib.fsb_ball_method_mandelbrot(seed_x, seed_y, seed_prec, seed_px,
+                                                  maxiter, M_divergence))
+
+    def _newton(any_nucleus):
+        def impl(seed_x, seed_y, seed_prec, order, max_newton, seed_eps_cv,
+                 seed_eps_valid):
+            import mpmath
+            cap = int(seed_prec * 0.31) + 64
+            bx = ctypes.create_string_buffer(cap)
+            by = ctypes.create_string_buffer(cap)
+            rc = lib.fsb_find_nucleus_mandelbrot(seed_x, seed_y, seed_prec, order,
+                                                 max_newton, seed_eps_cv, seed_eps_valid,
+                                                 any_nucleus, bx, by, cap)
+            if rc != 1:
+                return False, mpmath.mpc("nan", "nan")
+            with mpmath.workprec(seed_prec):
+                return True, mpmath.mpc(mpmath.mpf(bx.value.decode()),
+                                        mpmath.mpf(by.value.decode()))
+        return impl
+
+    shim.perturbation_mandelbrot_ball_method = perturbation_mandelbrot_ball_method
+    shim.perturbation_mandelbrot_find_nucleus = _newton(0)
+    shim.perturbation_mandelbrot_find_any_nucleus = _newton(1)
     shim.perturbation_mandelbrot_FP_loop = perturbation_mandelbrot_FP_loop
     shim.perturbation_mandelbrotN_FP_loop = perturbation_mandelbrotN_FP_loop
     shim.perturbation_nonholomorphic_FP_loop = perturbation_nonholomorphic_FP_loop
@@ -196,8 +232,15 @@ def run_case(case, workdir=None, keep_tables=True):
     if own:
         tmp = tempfile.TemporaryDirectory()
         workdir = tmp.name
-    f = make_fractal(case, workdir)
-    f.calc_raw("c")
+    fs = load_reference()
+    # cases flagged newton=True run the reference's default flow (ball method +
+    # Newton descent -> periodic reference); all others use the image centre
+    fs.settings.no_newton = not case.get("newton", False)
+    try:
+        f = make_fractal(case, workdir)
+        f.calc_raw("c")
+    finally:
+        fs.settings.no_newton = True
     out = {}
     for key in ("Z", "U", "stop_reason", "stop_iter"):
         out[key] = np.array(f.get_data_memmap("c", key, mode="r"))
