@@ -1058,7 +1058,7 @@ __device__ __forceinline__ void apply_bla_deriv_bs_xr(const double *M, XF &dxa, 
  * Xrange + hessian kernel was 18 000 instructions and spent two thirds of its
  * time waiting on instruction fetch); 0 = read it from the frame. */
 template <bool XR, bool HESS, bool BLA, bool FASTXR = false, int FLAVOR = 0>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, (XR ? 8 : 1))   /* Xrange: latency-bound, 32 warps/SM pay for the spills */
 k_perturb_bs(const __grid_constant__ FrameDev f, long long npts_ll,
              const C *__restrict__ c_pix, double *__restrict__ Z,
              int *__restrict__ U, signed char *__restrict__ stop_reason,
