@@ -77,6 +77,7 @@ CUDA_SYMBOLS = [
     "fsb_frame_nz", "fsb_frame_bla_len", "fsb_frame_stages_bla",
     "fsb_frame_setup_ms", "fsb_frame_get_bla", "fsb_frame_get_dzndc",
     "fsb_frame_get_dzndz", "fsb_frame_run", "fsb_frame_run_device",
+    "fsb_frame_run_pp", "fsb_postproc_run", "fsb_postproc_run_device",
     "fsb_xr_binop_c", "fsb_xr_to_standard_c", "fsb_hypot_test",
     "fsb_fp64_peak_tflops",
 ]

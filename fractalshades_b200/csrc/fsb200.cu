@@ -886,8 +886,9 @@ int fsb_std_run_tiles_device(const fsb_std_desc *d, int32_t n_tiles, const int32
 struct Plane { char *host; long long dev_off; long long elem; };
 
 /* Host-buffer call: H2D of c_pix, kernels and D2H of the planes, pipelined
- * over slabs of consecutive points.  `enqueue(stream, slot, unit_lo, unit_hi)`
- * launches the kernel for those units into control block `slot`. */
+ * over slabs of consecutive points.  `enqueue(stream, slot, unit_lo, unit_hi,
+ * a, n)` launches the kernel for those units (= points [a, a+n)) into control
+ * block `slot`. */
 template <class Enqueue>
 static int run_pipelined(Ctx *c, const Units &u, const double *c_pix, long long o_c,
                          const Plane *planes, int n_planes, long long o_zero_beg,
@@ -914,7 +915,7 @@ static int run_pipelined(Ctx *c, const Units &u, const double *c_pix, long long 
         CK(cudaEventRecord(c->ev_h[k], c->s_h2d));
         cudaStream_t st = (k & 1) ? c->s_alt : c->stream;
         CK(cudaStreamWaitEvent(st, c->ev_h[k], 0));
-        if (enqueue(st, k, ch.ubeg[k], ch.ubeg[k + 1])) return -1;
+        if (enqueue(st, k, ch.ubeg[k], ch.ubeg[k + 1], a, n)) return -1;
         CK(cudaEventRecord(c->ev_k[k], st));
         return 0;
     };
@@ -977,7 +978,7 @@ static int std_run_impl(Ctx *c, const fsb_std_desc *d, int32_t n_tiles, const in
     planes[np++] = Plane{(char *)stop_iter, o_si, 4};
     planes[np++] = Plane{(char *)stop_reason, o_sr, 1};
     bool was_int = false;
-    auto enqueue = [&](cudaStream_t st, int slot, int unit_lo, int unit_hi) {
+    auto enqueue = [&](cudaStream_t st, int slot, int unit_lo, int unit_hi, long long, long long) {
         return std_enqueue(c, d, p, st, slot, u, unit_lo, unit_hi, (const C *)(base + o_c),
                            (double *)(base + o_Z), (signed char *)(base + o_sr),
                            (int *)(base + o_si));
@@ -1272,10 +1273,52 @@ static int frame_run_device_impl(Ctx *c, fsb_frame *f, const Units &u, const dou
     return 0;
 }
 
+/* fsb_postproc_desc -> device parameters (row stride = npts of the call) */
+static int postproc_fill(const fsb_postproc_desc *d, long long zstride, int n_rows, PostprocDev &p)
+{
+    if (!d) return fail(-3, "null post-processing description");
+    const int need = d->holomorphic ? 1 : 2, need_d = d->holomorphic ? 1 : 4;
+    if (d->row_zn < 0 || d->row_zn + need > n_rows
+        || (d->row_dzndc >= 0 && d->row_dzndc + need_d > n_rows))
+        return fail(-3, "post-processing rows (%d, %d) outside the %d rows of Z", d->row_zn,
+                    d->row_dzndc, n_rows);
+    if (!(d->potential_d > 1.) || !(d->potential_M > 0.) || d->potential_a_d == 0.)
+        return fail(-3, "unsupported potential (d = %g, a_d = %g, M = %g)", d->potential_d,
+                    d->potential_a_d, d->potential_M);
+    p.holomorphic = d->holomorphic; p.row_zn = d->row_zn; p.row_d = d->row_dzndc;
+    p.zstride = zstride;
+    p.k = pow(fabs(d->potential_a_d), 1. / (d->potential_d - 1.));
+    p.log_Mk = log(d->potential_M * p.k);
+    p.inv_log_d = 1. / log(d->potential_d);
+    p.floor_iter = d->floor_iter; p.px_snap = d->px_snap;
+    p.has_skew = d->has_skew;
+    for (int i = 0; i < 4; i++) p.skew[i] = d->skew[i];
+    p.out_f64 = d->out_f64;
+    return 0;
+}
+
+static int postproc_enqueue(const PostprocDev &p, cudaStream_t st, long long first, long long n,
+                            const double *d_Z, const int *d_si, void *d_nu, void *d_dem,
+                            void *d_nx, void *d_ny)
+{
+    if (n <= 0 || (!d_nu && !d_dem && !d_nx)) return 0;
+    long long blocks = (n + 255) / 256;
+    const long long cap = (long long)g_sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    k_postproc<<<(int)blocks, 256, 0, st>>>(p, first, n, d_Z, d_si, d_nu, d_dem, d_nx, d_ny);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+/* pp == nullptr: the raw planes come back (Z, U, stop_iter, stop_reason).
+ * pp != nullptr: fused post-processing -- the raw planes stay in HBM and only
+ * the requested fields (pp_out: nu, dem, nx, ny) plus the non-null ones of
+ * stop_reason / stop_iter are copied to the host. */
 static int frame_run_impl(Ctx *c, fsb_frame *f, int32_t n_tiles, const int32_t *tile_w,
                           const int32_t *tile_h, int64_t npts_flat, const double *c_pix, double *Z,
                           int32_t *U, int8_t *stop_reason, int32_t *stop_iter,
-                          const volatile uint8_t *interrupted, fsb_stats *stats)
+                          const volatile uint8_t *interrupted, fsb_stats *stats,
+                          const fsb_postproc_desc *pp = nullptr, void *const *pp_out = nullptr)
 {
     if (stats) memset(stats, 0, sizeof *stats);
     if (interrupted && *interrupted) return FSB_USER_INTERRUPTED;
@@ -1285,27 +1328,56 @@ static int frame_run_impl(Ctx *c, fsb_frame *f, int32_t n_tiles, const int32_t *
     const long long npts = u.npts;
     const int nz = f->nz;
     const long long zelem = (f->d.model == FSB_MODEL_M2) ? 16 : 8;
+    PostprocDev pd;
+    long long oelem = 4;
+    if (pp) {
+        if (postproc_fill(pp, npts, nz, pd)) return -3;
+        oelem = pp->out_f64 ? 8 : 4;
+    }
     long long o_c = 0, o_Z = align256(o_c + npts * 16), o_U = align256(o_Z + nz * npts * zelem),
               o_si = align256(o_U + npts * 4), o_sr = align256(o_si + npts * 4),
-              total = align256(o_sr + npts);
+              o_pp = align256(o_sr + npts),
+              total = align256(o_pp + (pp ? 4 * align256(npts * oelem) : 0));
     if (ctx_reserve(c, total)) return -1;
     char *base = (char *)c->d_buf;
     Plane planes[16];
     int np = 0;
-    for (int r = 0; r < nz; r++)
-        planes[np++] = Plane{(char *)Z + r * npts * zelem, o_Z + r * npts * zelem, zelem};
-    planes[np++] = Plane{(char *)U, o_U, 4};
-    planes[np++] = Plane{(char *)stop_iter, o_si, 4};
-    planes[np++] = Plane{(char *)stop_reason, o_sr, 1};
+    void *d_pp[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (!pp) {
+        for (int r = 0; r < nz; r++)
+            planes[np++] = Plane{(char *)Z + r * npts * zelem, o_Z + r * npts * zelem, zelem};
+        planes[np++] = Plane{(char *)U, o_U, 4};
+        planes[np++] = Plane{(char *)stop_iter, o_si, 4};
+        planes[np++] = Plane{(char *)stop_reason, o_sr, 1};
+    } else {
+        for (int k = 0; k < 4; k++) {
+            if (!pp_out || !pp_out[k]) continue;
+            const long long off = o_pp + k * align256(npts * oelem);
+            d_pp[k] = base + off;
+            planes[np++] = Plane{(char *)pp_out[k], off, oelem};
+        }
+        if ((d_pp[2] == nullptr) != (d_pp[3] == nullptr))
+            return fail(-3, "the normal needs both of its output arrays");
+        if ((d_pp[1] || d_pp[2]) && pp->row_dzndc < 0)
+            return fail(-3, "distance estimate / normal need the derivative rows");
+        if (stop_iter) planes[np++] = Plane{(char *)stop_iter, o_si, 4};
+        if (stop_reason) planes[np++] = Plane{(char *)stop_reason, o_sr, 1};
+    }
     bool was_int = false;
-    auto enqueue = [&](cudaStream_t st, int slot, int unit_lo, int unit_hi) {
-        return frame_enqueue(c, f, st, slot, u, unit_lo, unit_hi, (const C *)(base + o_c),
-                             (double *)(base + o_Z), (int *)(base + o_U),
-                             (signed char *)(base + o_sr), (int *)(base + o_si));
+    auto enqueue = [&](cudaStream_t st, int slot, int unit_lo, int unit_hi, long long a,
+                       long long n) {
+        if (frame_enqueue(c, f, st, slot, u, unit_lo, unit_hi, (const C *)(base + o_c),
+                          (double *)(base + o_Z), (int *)(base + o_U),
+                          (signed char *)(base + o_sr), (int *)(base + o_si))) return -1;
+        if (pp) return postproc_enqueue(pd, st, a, n, (const double *)(base + o_Z),
+                                        (const int *)(base + o_si), d_pp[0], d_pp[1], d_pp[2],
+                                        d_pp[3]);
+        return 0;
     };
     int rc = run_pipelined(c, u, c_pix, o_c, planes, np, o_Z, o_si + npts * 4, o_sr, enqueue,
                            interrupted, stats, &was_int);
     if (rc) return rc;
+    if (stats && pp) stats->n_launches *= 2;
     return was_int ? FSB_USER_INTERRUPTED : 0;
 }
 
@@ -1362,6 +1434,67 @@ int fsb_frame_run_tiles(fsb_frame *f, int32_t n_tiles, const int32_t *tile_w,
     if (n_tiles <= 0) return fail(-3, "empty tile list");
     return frame_run_impl(c, f, n_tiles, tile_w, tile_h, 0, c_pix, Z, U, stop_reason, stop_iter,
                           interrupted, stats);
+}
+
+/* ---- post-processing (SURVEY f-3) ------------------------------------------ */
+int fsb_frame_run_pp(fsb_frame *f, int32_t n_tiles, const int32_t *tile_w, const int32_t *tile_h,
+                     int64_t npts, const double *c_pix, const fsb_postproc_desc *pp, void *nu,
+                     void *dem, void *normal_x, void *normal_y, int8_t *stop_reason,
+                     int32_t *stop_iter, const volatile uint8_t *interrupted, fsb_stats *stats)
+{
+    Ctx *c;
+    if (get_ctx(&c)) return -1;
+    if (!f) return fail(-3, "null frame");
+    if (!pp) return fail(-3, "null post-processing description");
+    if (n_tiles <= 0 && npts <= 0) { if (stats) memset(stats, 0, sizeof *stats); return 0; }
+    void *outs[4] = {nu, dem, normal_x, normal_y};
+    return frame_run_impl(c, f, n_tiles, tile_w, tile_h, npts, c_pix, nullptr, nullptr,
+                          stop_reason, stop_iter, interrupted, stats, pp, outs);
+}
+
+int fsb_postproc_run_device(const fsb_postproc_desc *pp, int64_t npts, int32_t n_rows,
+                            const double *d_Z, const int32_t *d_stop_iter, void *d_nu,
+                            void *d_dem, void *d_normal_x, void *d_normal_y)
+{
+    Ctx *c;
+    if (get_ctx(&c)) return -1;
+    if (npts <= 0) return 0;
+    PostprocDev pd;
+    if (postproc_fill(pp, npts, n_rows, pd)) return -3;
+    if ((d_dem || d_normal_x) && pp->row_dzndc < 0)
+        return fail(-3, "distance estimate / normal need the derivative rows");
+    if ((d_normal_x == nullptr) != (d_normal_y == nullptr))
+        return fail(-3, "the normal needs both of its output arrays");
+    if (postproc_enqueue(pd, c->stream, 0, npts, d_Z, d_stop_iter, d_nu, d_dem, d_normal_x,
+                         d_normal_y)) return -1;
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int fsb_postproc_run(const fsb_postproc_desc *pp, int64_t npts, int32_t n_rows, const double *Z,
+                     const int32_t *stop_iter, void *nu, void *dem, void *normal_x,
+                     void *normal_y)
+{
+    Ctx *c;
+    if (get_ctx(&c)) return -1;
+    if (npts <= 0) return 0;
+    if (!pp) return fail(-3, "null post-processing description");
+    const long long zelem = pp->holomorphic ? 16 : 8, oelem = pp->out_f64 ? 8 : 4;
+    const long long o_Z = 0, o_si = align256(n_rows * npts * zelem), o_pp = align256(o_si + npts * 4),
+                    total = o_pp + 4 * align256(npts * oelem);
+    if (ctx_reserve(c, total)) return -1;
+    char *base = (char *)c->d_buf;
+    CK(cudaMemcpyAsync(base + o_Z, Z, (size_t)(n_rows * npts * zelem), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(base + o_si, stop_iter, (size_t)(npts * 4), cudaMemcpyHostToDevice, c->stream));
+    void *host[4] = {nu, dem, normal_x, normal_y};
+    void *dev[4];
+    for (int k = 0; k < 4; k++) dev[k] = host[k] ? base + o_pp + k * align256(npts * oelem) : nullptr;
+    int rc = fsb_postproc_run_device(pp, npts, n_rows, (const double *)(base + o_Z),
+                                     (const int32_t *)(base + o_si), dev[0], dev[1], dev[2], dev[3]);
+    if (rc) return rc;
+    for (int k = 0; k < 4; k++)
+        if (host[k]) CK(cudaMemcpy(host[k], dev[k], (size_t)(npts * oelem), cudaMemcpyDeviceToHost));
+    return 0;
 }
 
 /* ---- unit-test / calibration entry points --------------------------------- */

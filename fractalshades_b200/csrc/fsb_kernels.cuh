@@ -1720,6 +1720,112 @@ __global__ void k_flush_mirror(long long n, const double *__restrict__ m, const 
 
 /* ======================================================================== */
 /* Unit-test and calibration kernels                                         */
+/* ======================================================================== */
+/* Post-processing of the raw fields                   */
+
+/* Continuous iteration number, distance estimate and normal vector of the
+ * potential, from the raw outputs of the pixel kernels while they are still in
+ * HBM (postproc.py:352-406 `Continuous_iter_pp`, :1001-1009; :684-731
+ * `DEM_pp`; :572-628 `DEM_normal_pp`, kind "potential", potential kind
+ * "infinity").  One thread per point; reads 36 (holomorphic) or 52 B, writes
+ * 4 B per requested field: HBM-bound.  The arithmetic is fp64 as in numpy; the
+ * results are rounded once to the requested output type (the reference's
+ * `settings.postproc_dtype`, float32 by default). */
+struct PostprocDev {
+    int holomorphic;          /* Z rows: complex128 (zn, dzndc) / float64 (xn, yn, 4 derivatives) */
+    int row_zn, row_d;        /* row of zn (xn) and of dzndc (dxnda) in Z; row_d < 0: no derivative */
+    long long zstride;
+    double k, log_Mk, inv_log_d;   /* |a_d|^(1/(d-1)), log(M k), 1 / log(d) */
+    double floor_iter;
+    double px_snap;           /* < 0: none */
+    int has_skew; double skew[4];
+    int out_f64;
+};
+
+template <class T> __device__ __forceinline__ void pp_store(void *p, long long i, double v)
+{
+    reinterpret_cast<T *>(p)[i] = (T)v;
+}
+
+__global__ void __launch_bounds__(256)
+k_postproc(PostprocDev p, long long first, long long n, const double *__restrict__ Z,
+           const int *__restrict__ stop_iter, void *__restrict__ out_nu,
+           void *__restrict__ out_dem, void *__restrict__ out_nx, void *__restrict__ out_ny)
+{
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n;
+         j += (long long)gridDim.x * blockDim.x) {
+        const long long i = first + j;
+        double zx, zy;
+        double dxa = 0., dxb = 0., dya = 0., dyb = 0.;     /* d(zn)/dc as a 2x2 real matrix */
+        if (p.holomorphic) {
+            const double2 z = __ldg(reinterpret_cast<const double2 *>(Z) + p.row_zn * p.zstride + i);
+            zx = z.x; zy = z.y;
+            if (p.row_d >= 0) {
+                const double2 d = __ldg(reinterpret_cast<const double2 *>(Z) + p.row_d * p.zstride + i);
+                dxa = d.x; dya = d.y;
+            }
+        } else {
+            zx = __ldg(Z + p.row_zn * p.zstride + i);
+            zy = __ldg(Z + (p.row_zn + 1) * p.zstride + i);
+            if (p.row_d >= 0) {
+                dxa = __ldg(Z + p.row_d * p.zstride + i);
+                dxb = __ldg(Z + (p.row_d + 1) * p.zstride + i);
+                dya = __ldg(Z + (p.row_d + 2) * p.zstride + i);
+                dyb = __ldg(Z + (p.row_d + 3) * p.zstride + i);
+            }
+        }
+        const double abs_zn = hypot(zx, zy);
+        if (out_nu) {
+            /* nu_frac = -log(log|zn k| / log(M k)) / log d, folded into (-1, 0] */
+            const double nu_frac = -(log(log(abs_zn * p.k) / p.log_Mk) * p.inv_log_d);
+            const double q = floor(-nu_frac);          /* np.divmod(-nu_frac, 1.) */
+            const double mod = -nu_frac - q;
+            /* the integer part moves into n (cast to the int type of stop_iter) */
+            const int n_i = stop_iter[i] - (int)q;
+            const double nu = ((double)n_i - p.floor_iter) + (-mod);
+            if (p.out_f64) pp_store<double>(out_nu, i, nu); else pp_store<float>(out_nu, i, nu);
+        }
+        if (out_dem) {
+            double abs_d;
+            if (p.holomorphic) abs_d = hypot(dxa, dya);
+            else {      /* largest singular value of the Jacobian */
+                const double Q = hypot(dxa + dyb, dxb - dya), R = hypot(dxa - dyb, dxb + dya);
+                abs_d = 0.5 * (Q + R);
+            }
+            double val = abs_zn * log(abs_zn) / abs_d;
+            if (p.px_snap >= 0. && val < p.px_snap) val = 0.;
+            if (p.out_f64) pp_store<double>(out_dem, i, val); else pp_store<float>(out_dem, i, val);
+        }
+        if (out_nx) {
+            double nx, ny;
+            if (p.holomorphic) {          /* zn / dzndc */
+                const double den = dxa * dxa + dya * dya;
+                /* numpy complex division (Smith's algorithm) */
+                if (fabs(dxa) >= fabs(dya)) {
+                    const double r = dya / dxa, dd = dxa + dya * r;
+                    nx = (zx + zy * r) / dd; ny = (zy - zx * r) / dd;
+                } else {
+                    const double r = dxa / dya, dd = dxa * r + dya;
+                    nx = (zx * r + zy) / dd; ny = (zy * r - zx) / dd;
+                }
+                (void)den;
+            } else {                      /* J^T zn */
+                nx = dxa * zx + dya * zy;
+                ny = dxb * zx + dyb * zy;
+            }
+            if (p.has_skew) {             /* contravariant: transposed matrix (core.py:3147-3158) */
+                const double ux = p.skew[0] * nx + p.skew[2] * ny;
+                const double uy = p.skew[1] * nx + p.skew[3] * ny;
+                nx = ux; ny = uy;
+            }
+            const double a = hypot(nx, ny);
+            nx /= a; ny /= a;
+            if (p.out_f64) { pp_store<double>(out_nx, i, nx); pp_store<double>(out_ny, i, ny); }
+            else { pp_store<float>(out_nx, i, nx); pp_store<float>(out_ny, i, ny); }
+        }
+    }
+}
+
 __global__ void k_xr_binop_c(int op, long long n, const C *a, const int *ae, const C *b,
                              const int *be, C *out, int *oute)
 {

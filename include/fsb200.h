@@ -193,6 +193,42 @@ int fsb_frame_run_tiles_device(fsb_frame *f, int32_t n_tiles, const int32_t *til
                                int32_t *d_U, int8_t *d_stop_reason, int32_t *d_stop_iter,
                                fsb_stats *stats);
 
+/* ---- post-processing of the raw fields on the device --------
+ * Continuous iteration number (postproc.py:352-406, 1001-1009), distance
+ * estimate (:684-731) and normal of the potential (:572-628, kind "potential")
+ * for the "infinity" potential of the divergent models, computed from the raw
+ * fields while they are still in HBM.  Outputs are float32 arrays of npts
+ * values (the reference's settings.postproc_dtype; float64 when out_f64), NULL
+ * = not wanted.  Values are only meaningful where stop_reason == 1. */
+typedef struct fsb_postproc_desc {
+    int32_t holomorphic;      /* 1: Z rows complex128 ; 0: float64 rows (xn, yn, dxnda..dyndb) */
+    int32_t row_zn;           /* row of zn (xn) in Z                            */
+    int32_t row_dzndc;        /* row of dzndc (dxnda); < 0: no derivative rows  */
+    int32_t has_skew;
+    double potential_d, potential_a_d, potential_M;   /* models' potential_* attributes */
+    double floor_iter;        /* Continuous_iter_pp(floor_iter=...)             */
+    double px_snap;           /* DEM_pp(px_snap=...), < 0: none                 */
+    double skew[4];           /* Fractal.skew, row-major                        */
+    int32_t out_f64;  int32_t _pad;
+} fsb_postproc_desc;
+
+/* fused: pixel kernels + post-processing in one call; Z / U never leave the
+ * device, only the requested fields (and stop_reason / stop_iter when not
+ * NULL) are copied back: 4-16 B per point instead of 41-60.  n_tiles > 0: tile
+ * list (npts ignored); n_tiles = 0: flat list of npts points. */
+int fsb_frame_run_pp(fsb_frame *f, int32_t n_tiles, const int32_t *tile_w,
+                     const int32_t *tile_h, int64_t npts, const double *c_pix,
+                     const fsb_postproc_desc *pp, void *nu, void *dem, void *normal_x,
+                     void *normal_y, int8_t *stop_reason, int32_t *stop_iter,
+                     const volatile uint8_t *interrupted, fsb_stats *stats);
+/* stand-alone: raw fields already on the device / on the host (n_rows rows of Z) */
+int fsb_postproc_run_device(const fsb_postproc_desc *pp, int64_t npts, int32_t n_rows,
+                            const double *d_Z, const int32_t *d_stop_iter, void *d_nu,
+                            void *d_dem, void *d_normal_x, void *d_normal_y);
+int fsb_postproc_run(const fsb_postproc_desc *pp, int64_t npts, int32_t n_rows,
+                     const double *Z, const int32_t *stop_iter, void *nu, void *dem,
+                     void *normal_x, void *normal_y);
+
 /* ---- Xrange device arithmetic, exposed for unit tests --------------------
  * (mirror of the reference's tests/test_numba_xr.py; runs on the GPU)
  * op: 0 add, 1 sub, 2 mul ; complex operands (re, im interleaved) */

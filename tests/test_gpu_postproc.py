@@ -1,0 +1,163 @@
+# -*- coding: utf-8 -*-
+"""
+GPU post-processing kernel against a numpy restatement of the
+reference's post-processing classes:
+  Continuous_iter_pp   postproc.py:352-406 + Continuous_iter_pp_infinity :1001-1009
+  DEM_pp               postproc.py:684-731
+  DEM_normal_pp        postproc.py:572-628 (kind "potential"), unskew core.py:3147-3158
+and the fused call (pixel kernels + post-processing) against the stand-alone one.
+"""
+import tempfile
+
+import numpy as np
+import pytest
+
+import fractalshades_b200.models as fsm
+from fractalshades_b200 import postproc as fpp
+
+pytestmark = pytest.mark.gpu
+
+
+def np_cont_iter(zn, stop_iter, d, a_d, M, floor_iter=0):
+    k = np.abs(a_d) ** (1. / (d - 1.))
+    with np.errstate(all="ignore"):
+        nu_frac = -(np.log(np.log(np.abs(zn * k)) / np.log(M * k)) / np.log(d))
+        nu_div, nu_mod = np.divmod(-nu_frac, 1.)
+        nu_frac = -nu_mod
+        n = stop_iter - nu_div.astype(stop_iter.dtype)
+    return (n - floor_iter) + nu_frac
+
+
+def np_dem(zn, deriv, holomorphic, px_snap=None):
+    abs_zn = np.abs(zn)
+    if holomorphic:
+        abs_d = np.abs(deriv)
+    else:
+        dXdA, dXdB, dYdA, dYdB = deriv
+        Q = np.hypot(dXdA + dYdB, dXdB - dYdA)
+        R = np.hypot(dXdA - dYdB, dXdB + dYdA)
+        abs_d = 0.5 * (Q + R)
+    with np.errstate(all="ignore"):
+        val = abs_zn * np.log(abs_zn) / abs_d
+    if px_snap is not None:
+        val = np.where(val < px_snap, 0., val)
+    return val
+
+
+def np_normal(zn, deriv, holomorphic, skew=None):
+    with np.errstate(all="ignore"):
+        if holomorphic:
+            normal = zn / deriv
+        else:
+            dXdA, dXdB, dYdA, dYdB = deriv
+            normal = ((dXdA * zn.real + dYdA * zn.imag)
+                      + 1j * (dXdB * zn.real + dYdB * zn.imag))
+        if skew is not None:
+            nx, ny = normal.real.copy(), normal.imag.copy()
+            ux = skew[0, 0] * nx + skew[1, 0] * ny
+            uy = skew[0, 1] * nx + skew[1, 1] * ny
+            normal = ux + 1j * uy
+        return normal / np.abs(normal)
+
+
+def _close(a, b, mask, rtol):
+    a, b = np.asarray(a, np.float64)[mask], np.asarray(b, np.float64)[mask]
+    ok = np.isfinite(b)
+    assert ok.mean() > 0.99
+    np.testing.assert_allclose(a[ok], b[ok], rtol=rtol, atol=rtol)
+
+
+def _m2():
+    f = fsm.Perturbation_mandelbrot(tempfile.mkdtemp())
+    f.zoom(precision=30, x="-1.74928893611435556407228", y="0.", dx="5.e-20", nx=300,
+           xy_ratio=1.5, theta_deg=0.)
+    f.calc_std_div(calc_name="c", subset=None, max_iter=50000, M_divergence=1e3,
+                   epsilon_stationnary=1e-3, BLA_eps=1e-6, interior_detect=False,
+                   calc_dzndc=True)
+    return f
+
+
+def _bs():
+    f = fsm.Perturbation_burning_ship(tempfile.mkdtemp(), flavor="Burning ship")
+    f.zoom(precision=50, x="0.533551593577038561769721161491702555962775680136595415306315189524970818968817900068355227861158570104764433694",
+           y="1.26175074578870311547721223871955368990255513054155186351034363459852900933566891849764050954410207620093433856",
+           dx="7.5e-30", nx=260, xy_ratio=1.3, theta_deg=12.0, has_skew=True,
+           skew_00=0.9, skew_01=-0.35, skew_10=0.2, skew_11=1.05)
+    f.calc_std_div(calc_name="c", subset=None, max_iter=30000, M_divergence=1e3,
+                   BLA_eps=1e-6, calc_hessian=True)
+    return f
+
+
+def _raw(f):
+    f.calc_raw("c")
+    Z = np.array(f.get_data_memmap("c", "Z", mode="r"))
+    si = np.array(f.get_data_memmap("c", "stop_iter", mode="r"))[0]
+    sr = np.array(f.get_data_memmap("c", "stop_reason", mode="r"))[0]
+    return Z, si, sr
+
+
+@pytest.mark.parametrize("model", ["m2", "bs"])
+def test_postproc_kernel_matches_numpy_restatement(model):
+    f = _m2() if model == "m2" else _bs()
+    Z, si, sr = _raw(f)
+    esc = sr == 1
+    assert esc.mean() > 0.3
+    holo = model == "m2"
+    if holo:
+        zn, deriv = Z[0], Z[1]
+    else:
+        zn, deriv = Z[0] + 1j * Z[1], (Z[2], Z[3], Z[4], Z[5])
+    skew = getattr(f, "skew", None)
+    ref = {"cont_iter": np_cont_iter(zn, si, 2, 1., 1e3, floor_iter=7),
+           "DEM": np_dem(zn, deriv, holo, px_snap=None)}
+    nrm = np_normal(zn, deriv, holo, None if skew is None else np.asarray(skew))
+    ref["normal_x"], ref["normal_y"] = nrm.real, nrm.imag
+    out64 = fpp.fields_from_raw(f, "c", Z, si, floor_iter=7, dtype=np.float64)
+    for k in fpp.FIELDS:
+        _close(out64[k], ref[k], esc, 1e-12)
+    out32 = fpp.fields_from_raw(f, "c", Z, si, floor_iter=7, dtype=np.float32)
+    for k in fpp.FIELDS:
+        assert out32[k].dtype == np.float32
+        a, b = out32[k][esc], ref[k].astype(np.float32)[esc]
+        ok = np.isfinite(b)
+        # one rounding to float32 on each side: equal, or neighbours when the
+        # fp64 values straddle a float32 rounding boundary
+        assert np.mean(a[ok] == b[ok]) > 0.999
+        np.testing.assert_allclose(a[ok], b[ok], rtol=2e-7, atol=1e-7)
+    # px_snap
+    snap = float(np.nanmedian(ref["DEM"][esc]))
+    o = fpp.fields_from_raw(f, "c", Z, si, fields=("DEM",), px_snap=snap, dtype=np.float64)
+    _close(o["DEM"], np_dem(zn, deriv, holo, px_snap=snap), esc, 1e-12)
+
+
+@pytest.mark.parametrize("model", ["m2", "bs"])
+def test_fused_frame_fields_equal_standalone(model):
+    f = _m2() if model == "m2" else _bs()
+    Z, si, sr = _raw(f)
+    alone = fpp.fields_from_raw(f, "c", Z, si)
+    fused, stats = fpp.frame_fields(f, "c", want_stop_iter=True)
+    assert np.array_equal(fused["stop_reason"], sr) and np.array_equal(fused["stop_iter"], si)
+    esc = sr == 1
+    for k in fpp.FIELDS:
+        assert fused[k].dtype == np.float32
+        assert np.array_equal(fused[k][esc], alone[k][esc], equal_nan=True), k
+    assert stats["sum_stop_iter"] == int(si.sum(dtype=np.int64))
+    img = fpp.to_image(f, fused["cont_iter"])
+    assert img.shape == (f.ny, f.nx)
+    (ix, ixx, iy, iyy) = list(f.chunk_slices())[1]
+    off = sum((a[1] - a[0]) * (a[3] - a[2]) for a in list(f.chunk_slices())[:1])
+    assert np.array_equal(img[iy:iyy, ix:ixx].ravel(),
+                          fused["cont_iter"][off:off + (ixx - ix) * (iyy - iy)], equal_nan=True)
+
+
+def test_postproc_errors():
+    f = fsm.Perturbation_mandelbrot(tempfile.mkdtemp())
+    f.zoom(precision=30, x="-1.74928893611435556407228", y="0.", dx="5.e-20", nx=64,
+           xy_ratio=1.0, theta_deg=0.)
+    f.calc_std_div(calc_name="c", subset=None, max_iter=2000, M_divergence=1e3,
+                   epsilon_stationnary=1e-3, BLA_eps=1e-6, interior_detect=False,
+                   calc_dzndc=False)
+    with pytest.raises(ValueError):
+        fpp.frame_fields(f, "c", fields=("DEM",))
+    out, _ = fpp.frame_fields(f, "c", fields=("cont_iter",))
+    assert set(out) == {"cont_iter", "stop_reason"}
