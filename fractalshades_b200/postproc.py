@@ -110,11 +110,47 @@ def fields_from_raw(fractal, calc_name, Z, stop_iter, fields=("cont_iter", "DEM"
     return out
 
 
+def _frame_staging(fractal, names, dtype):
+    """ Page-locked buffers of one frame geometry, kept on the fractal: the
+    tile-ordered pixel offsets (they depend on nx, ny, xy_ratio only) and one
+    output array per field. """
+    key = (fractal.nx, fractal.ny, fractal.xy_ratio, settings_chunk())
+    st = getattr(fractal, "_pp_staging", None)
+    if st is None or st["key"] != key:
+        if st is not None:
+            for a in st["bufs"].values():
+                _native.pinned_free(a)
+        shapes, pix = [], []
+        for cs in fractal.chunk_slices():
+            pos = fractal.chunk_pixel_pos(cs, False, None)
+            shapes.append((pos.shape[1], pos.shape[0]))
+            pix.append(np.ravel(pos))
+        npts = int(sum(p.shape[0] for p in pix))
+        c_pix = _native.pinned_empty((npts,), np.complex128)
+        c_pix[:] = np.concatenate(pix)
+        tw, th = tile_shape_arrays(shapes, npts)
+        st = {"key": key, "npts": npts, "tw": tw, "th": th, "bufs": {"c_pix": c_pix}}
+        fractal._pp_staging = st
+    for name, dt in names:
+        cur = st["bufs"].get(name)
+        if cur is None or cur.dtype != np.dtype(dt):
+            if cur is not None:
+                _native.pinned_free(cur)
+            st["bufs"][name] = _native.pinned_empty((st["npts"],), dt)
+    return st
+
+
+def settings_chunk():
+    from . import settings
+    return settings.chunk_size
+
+
 def frame_fields(fractal, calc_name, fields=("cont_iter", "DEM", "normal"), floor_iter=0,
-                 px_snap=None, dtype=np.float32, want_stop_iter=False):
+                 px_snap=None, dtype=np.float32, want_stop_iter=False, copy=True):
     """ Fused: pixel kernels + post-processing of one whole perturbation frame.
     Returns (dict of tile-ordered 1-D fields incl. "stop_reason", stats).
-    Use `to_image` for the (ny, nx) arrays. """
+    Use `to_image` for the (ny, nx) arrays.  copy=False returns views of the
+    page-locked staging buffers (overwritten by the next call). """
     lib = _declare(_native.cuda_lib())
     indep = fractal._calc_data[calc_name]["cycle_indep_args"]
     if indep[0] != "perturb":
@@ -122,27 +158,24 @@ def frame_fields(fractal, calc_name, fields=("cont_iter", "DEM", "normal"), floo
                                   "(use fields_from_raw for the standard models)")
     frame, interrupted = indep[1], indep[2]
     d, dtype, _ = make_desc(fractal, calc_name, floor_iter, px_snap, dtype)
-    shapes, pix = [], []
-    for cs in fractal.chunk_slices():
-        pos = fractal.chunk_pixel_pos(cs, False, None)
-        shapes.append((pos.shape[1], pos.shape[0]))
-        pix.append(np.ravel(pos))
-    c_pix = np.ascontiguousarray(np.concatenate(pix))
-    npts = c_pix.shape[0]
-    tw, th = tile_shape_arrays(shapes, npts)
-    out = _outputs(fields, npts, dtype, d.row_dzndc >= 0)
-    out["stop_reason"] = np.empty(npts, np.int8)
+    names = list(_outputs(fields, 0, dtype, d.row_dzndc >= 0))
+    want = [(k, dtype) for k in names] + [("stop_reason", np.int8)]
     if want_stop_iter:
-        out["stop_iter"] = np.empty(npts, np.int32)
+        want.append(("stop_iter", np.int32))
+    st = _frame_staging(fractal, want, dtype)
+    b, npts = st["bufs"], st["npts"]
+    out = {k: b[k] for k, _ in want}
     stats = _native.FsbStats()
-    rc = lib.fsb_frame_run_pp(frame.ptr, tw.shape[0], _native.ptr(tw), _native.ptr(th), npts,
-                              _native.ptr(c_pix), ctypes.byref(d),
-                              *[_native.ptr(out.get(k)) for k in FIELDS],
+    rc = lib.fsb_frame_run_pp(frame.ptr, st["tw"].shape[0], _native.ptr(st["tw"]),
+                              _native.ptr(st["th"]), npts, _native.ptr(b["c_pix"]),
+                              ctypes.byref(d), *[_native.ptr(out.get(k)) for k in FIELDS],
                               _native.ptr(out["stop_reason"]), _native.ptr(out.get("stop_iter")),
                               _native.ptr(interrupted), stats)
     _native.check(lib, rc)
     if rc != 0:
         raise RuntimeError("frame interrupted")
+    if copy:
+        out = {k: np.array(v) for k, v in out.items()}
     return out, stats.as_dict()
 
 
