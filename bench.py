@@ -453,11 +453,19 @@ def main():
             peak_src = "MEASURED_PEAKS.json"
         except Exception:
             hbm_peak, peak_src = 6650., "fallback"
+        traffic, traffic_src = None, None
+        try:       # dram bytes of one launch from the committed ncu capture (full 4K frames only)
+            with open(os.path.join(REPO, "profiles", "traffic.json")) as fh:
+                tj = json.load(fh).get(args.workload)
+            if tj and args.nx is None:
+                traffic, traffic_src = int(tj["bytes"]), tj["source"]
+        except Exception:
+            pass
         roofline = {
             "bound": "fp64",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
             "frac": achieved / peak if peak > 0 else None,
-            "traffic": None,
+            "traffic": traffic, "traffic_source": traffic_src,
             "peak_source": "measured live: dependent-DFMA chains on all SMs (fsb_fp64_peak_tflops)",
             "flops_per_iter": f_it, "flops_per_bla_step": f_bla,
             "n_iter_exec": int(kstats["n_iter_exec"]),
