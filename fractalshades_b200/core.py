@@ -378,8 +378,12 @@ class Fractal:
     def save_fingerprint(self, calc_name, fingerprint):
         path = self.fingerprint_path(calc_name)
         os.makedirs(os.path.dirname(path), exist_ok=True)
-        with open(path, 'wb+') as fp_file:
+        # several ranks may share the directory (tile sharding): the file
+        # appears atomically, a reader never sees it half written
+        tmp = f"{path}.{os.getpid()}.tmp"
+        with open(tmp, 'wb+') as fp_file:
             pickle.dump(_picklable(fingerprint), fp_file, pickle.HIGHEST_PROTOCOL)
+        os.replace(tmp, path)
 
     def reload_fingerprint(self, calc_name):
         with open(self.fingerprint_path(calc_name), 'rb') as tmpfile:

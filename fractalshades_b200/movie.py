@@ -55,8 +55,15 @@ class ZoomSequence:
         self.zoom_kwargs = dict(zoom_kwargs or {})
         self.widths = frame_widths(dx_start, dx_end, n_frames, precision)
 
+    def frame_dir(self, k):
+        return os.path.join(self.directory, f"frame_{k:04d}")
+
     def _fractal(self, k, directory=None):
-        f = self.model_cls(directory or self.directory, **self.model_kwargs)
+        """ Frame k lives in its own directory (parameter / fingerprint / report
+        files and memmaps are per frame: ranks never write the same file); the
+        orbit cache is the shared one under `self.directory`. """
+        f = self.model_cls(directory or self.frame_dir(k), **self.model_kwargs)
+        f.ref_point_dir = self.directory
         dx = self.widths[k]
         prec = min(self.precision, max(required_precision(dx, self.nx), 20))
         # zoom() sets mpmath.mp.dps: parse the centre at full precision first
@@ -100,11 +107,7 @@ class ZoomSequence:
             f.calc_std_div(calc_name="movie", subset=None, **self.calc_kwargs)
             t1 = time.time()
             if store:
-                fd = os.path.join(self.directory, f"frame_{k:04d}")
-                f.directory = fd
-                f.save_fingerprint("movie", f._calc_data["movie"]["state"].fingerprint)
-                f._calc_data["movie"]["need_new_mmap"] = True
-                f.calc_raw("movie")
+                f.calc_raw("movie")          # memmaps under frame_XXXX/data/
                 st = f.last_stats
             else:
                 st = render_frame_to_staging(f, "movie")

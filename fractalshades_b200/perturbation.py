@@ -232,7 +232,10 @@ class PerturbationFractal(Fractal):
         return bool(self.dx < settings.xrange_zoom_level)
 
     def ref_point_file(self):
-        return os.path.join(self.directory, "data", "ref_pt.dat")
+        # `ref_point_dir`: orbit cache shared by fractals that live in different
+        # directories (the frames of a zoom sequence)
+        base = getattr(self, "ref_point_dir", None) or self.directory
+        return os.path.join(base, "data", "ref_pt.dat")
 
     def ref_point_kc(self):
         """ perturbation.py:166-194 : bound on |dc| over the image, x 1.1 """
@@ -272,9 +275,11 @@ class PerturbationFractal(Fractal):
         self._Zn_path = Zn_path
         path = self.ref_point_file()
         os.makedirs(os.path.dirname(path), exist_ok=True)
-        with open(path, 'wb+') as tmpfile:
+        tmp = f"{path}.{os.getpid()}.tmp"      # atomic: other ranks may be reading
+        with open(tmp, 'wb+') as tmpfile:
             pickle.dump(FP_params, tmpfile, pickle.HIGHEST_PROTOCOL)
             pickle.dump(Zn_path, tmpfile, pickle.HIGHEST_PROTOCOL)
+        os.replace(tmp, path)
 
     def reload_ref_point(self, scan_only=False):
         with open(self.ref_point_file(), 'rb') as tmpfile:
