@@ -243,3 +243,31 @@ def test_native_orbit_known_answers():
     i = lib.fsb_orbit_mandelbrot(orb.ctypes.data, n, 2, 0, 2000., b"1.0", b"1.0", 100,
                                  buf, 8, ctypes.byref(cnt))
     assert 0 < i <= 6
+
+
+def test_fingerprint_file_is_written_atomically(tmp_path):
+    """ several ranks may share one directory: a reader must never see a
+    half-written fingerprint (the 8-GPU movie run raced on it) """
+    import threading
+    f = fsm.Mandelbrot(str(tmp_path))
+    f.zoom(x=-1., y=0., dx=5., nx=64, xy_ratio=1.0, theta_deg=0.)
+    fp = {"k": list(range(20000)), "name": "c"}
+    f.save_fingerprint("c", fp)
+    stop, errors = [False], []
+
+    def reader():
+        while not stop[0]:
+            try:
+                assert f.reload_fingerprint("c")["name"] == "c"
+            except Exception as e:      # EOFError / UnpicklingError on a torn file
+                errors.append(repr(e))
+                return
+    th = threading.Thread(target=reader)
+    th.start()
+    for _ in range(300):
+        f.save_fingerprint("c", fp)
+    stop[0] = True
+    th.join()
+    assert not errors, errors[:1]
+    assert [p for p in os.listdir(os.path.dirname(f.fingerprint_path("c")))
+            if p.endswith(".tmp")] == []

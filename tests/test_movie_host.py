@@ -53,4 +53,9 @@ def test_zoom_sequence_shares_one_orbit():
         assert abs(np.log2(t["lin_scale"]) + t["lin_scale_e"] - w[k] * np.log2(10)) < 1e-6
         assert t["kc"] > 0
     assert seen_xr == {False, True}
+    # one directory per frame (ranks never write the same parameter /
+    # fingerprint / report file), one shared orbit cache
+    dirs = {seq._fractal(k).directory for k in range(6)}
+    assert len(dirs) == 6 and all(os.path.dirname(p) == d for p in dirs)
+    assert {seq._fractal(k).ref_point_file() for k in range(6)} == {ref_file}
     assert sorted(sum((multi.frames_for_rank(6, r, 4) for r in range(4)), [])) == list(range(6))
