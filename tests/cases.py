@@ -144,3 +144,23 @@ CASES["p_BS_f1_E12_nohess_nobla"] = dict(
     x=_BS_PTS[1][0], y=_BS_PTS[1][1], dx="1e-12", nx=32,
     calc=dict(max_iter=20000, M_divergence=1e3, BLA_eps=None,
               calc_hessian=False))
+
+# Xrange depth for flavours 2-5: boundary points refined to 370 digits by
+# tools/find_bs_points.py (bisection with the native MPFR orbit)
+_BS_PTS_DEEP = {
+    2: ("-1.360487991749726900215933412585413412285941436379158985277606966498635261716098622422867771682228033068535518935593947357076960560050199605218706060749680904745216564414856079349951577490144456181921615837643147118666940547732646997181518864846452051695204455670188158206358173731996222868673070844837129912878140443866352112601196075982176312956362174529329299904832415",
+        "0.0015808658322309468"),
+    3: ("-1.447739947356317556357978548237778495646369402685350135930601575961449773077529696363655060114379075313955548508370405603817016044948045329721346977006988758372330218753579780494738912613058261725359625690988419821558257481687967166902943952736767044387784562930685975780898950021368075016650108359290776866492566128621467559846151414854370939045478590115324715970512931",
+        "-0.6048320439477123"),
+    4: ("-1.760370697674033990629647602248646769272164196525861499300163149203719957897864439338322827659524966514346500657140812071286660636210128949256738905621205132628675321665558581286312562176520968463586795207478191410050785873347963484571032346104172548153073753678276038822146254247271259723143412395751803705107699499051576986032176207405852407046871337707076056660839532",
+        "0.011733974791909326"),
+    5: ("-1.758364745737221",
+        "0.02435243123671457412747096729151485838826829360905491589504265390060499273229258730046411529559729038829435562100392963917617537209550025441909063863372456105101734638469804602015943204033310574818211732186262196166685204744482058449168705825576193112028437495897107990981970209824756389049187037777424330710506891329508576318294380939514132084838644631572261730179073714"),
+}
+for _i, _fl in enumerate(("Perpendicular burning ship", "Shark fin", "Celtic",
+                          "Buffalo")):
+    CASES[f"p_BS_f{_i + 2}_E330_xr"] = dict(
+        kind="perturb_BS", init=dict(flavor=_fl), precision=345,
+        x=_BS_PTS_DEEP[_i + 2][0], y=_BS_PTS_DEEP[_i + 2][1], dx="1e-330", nx=32,
+        calc=dict(max_iter=30000, M_divergence=1e3, BLA_eps=1e-6,
+                  calc_hessian=True))
