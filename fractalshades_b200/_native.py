@@ -31,12 +31,20 @@ class FsbStats(ctypes.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class FsbProjDesc(ctypes.Structure):
+    """ fsb_proj_desc: projection + dz/dc modifier parameters (all zero =
+    Cartesian, no modifier) """
+    _fields_ = [("kind", c_i32), ("dzndc_modifier", c_i32), ("hmoy", c_dbl),
+                ("pix_to_ht", c_dbl * 2), ("mod_param", c_dbl)]
+
+
 class FsbStdDesc(ctypes.Structure):
     _fields_ = [("model", c_i32), ("flavor", c_i32), ("center_re", c_dbl),
                 ("center_im", c_dbl), ("dx", c_dbl), ("lin_mat", c_dbl * 4),
                 ("max_iter", c_i64), ("M_divergence_sq", c_dbl),
                 ("epsilon_stationnary_sq", c_dbl), ("calc_d2zndc2", c_i32),
-                ("calc_orbit", c_i32), ("backshift", c_i64)]
+                ("calc_orbit", c_i32), ("backshift", c_i64),
+                ("proj", FsbProjDesc)]
 
 
 class FsbFrameDesc(ctypes.Structure):
@@ -54,7 +62,7 @@ class FsbFrameDesc(ctypes.Structure):
         ("M_divergence_sq", c_dbl), ("epsilon_stationnary_sq", c_dbl),
         ("BLA_eps", c_dbl), ("dZndc", c_vp), ("dZndc_e", c_vp), ("dZndz", c_vp),
         ("dZndz_e", c_vp), ("M_bla", c_vp), ("r_bla", c_vp), ("bla_len", c_i64),
-        ("stages_bla", c_i32), ("_pad4", c_i32),
+        ("stages_bla", c_i32), ("_pad4", c_i32), ("proj", FsbProjDesc),
     ]
 
 
@@ -65,6 +73,8 @@ class OrbitXr(ctypes.Structure):
 
 FSB_MODEL_M2 = 0
 FSB_MODEL_BS = 1
+FSB_PROJ_CARTESIAN, FSB_PROJ_EXPMAP = 0, 1
+FSB_DZNDC_MOD_NONE, FSB_DZNDC_MOD_EXPMAP, FSB_DZNDC_MOD_SEAM = 0, 1, 2
 
 # Every symbol declared in include/fsb200.h (checked by the CPU test-suite)
 CUDA_SYMBOLS = [
@@ -79,7 +89,7 @@ CUDA_SYMBOLS = [
     "fsb_frame_get_dzndz", "fsb_frame_run", "fsb_frame_run_device",
     "fsb_frame_run_pp", "fsb_postproc_run", "fsb_postproc_run_device",
     "fsb_xr_binop_c", "fsb_xr_to_standard_c", "fsb_hypot_test",
-    "fsb_fp64_peak_tflops",
+    "fsb_fp64_peak_tflops", "fsb_proj_apply",
 ]
 ORBIT_SYMBOLS = ["fsb_orbit_mandelbrot", "fsb_orbit_burning_ship",
                  "fsb_ball_method_mandelbrot", "fsb_find_nucleus_mandelbrot"]
@@ -150,6 +160,8 @@ def _declare(lib):
                                    c_vp, c_vp]
     lib.fsb_xr_to_standard_c.argtypes = [c_i64, c_vp, c_vp, c_vp]
     lib.fsb_hypot_test.argtypes = [c_i64, c_vp, c_vp, c_vp]
+    if hasattr(lib, "fsb_proj_apply"):     # absent from older A/B builds (FSB200_LIB)
+        lib.fsb_proj_apply.argtypes = [ctypes.POINTER(FsbProjDesc), c_i64, c_vp, c_vp, c_vp]
     lib.fsb_fp64_peak_tflops.argtypes = [ctypes.c_int]
     lib.fsb_fp64_peak_tflops.restype = c_dbl
     return lib

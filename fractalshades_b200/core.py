@@ -129,14 +129,18 @@ class Fractal:
         self.projection.adjust_to_zoom(self)
 
     def _set_projection(self, projection):
+        """ Cartesian and Expmap reduce to the parameters of fsb_proj_desc;
+        anything else cannot cross the C ABI and is refused (no fallback) """
         if projection is None or isinstance(projection, str):
             projection = _projection.Cartesian()
-        if not isinstance(projection, _projection.Cartesian):
+        if not isinstance(projection, _projection.Projection):
             raise NotImplementedError(
                 f"projection {type(projection).__name__} is not supported by "
-                "the GPU path (only Cartesian crosses the C ABI; no fallback)")
+                "the GPU path (Cartesian and Expmap cross the C ABI; no fallback)")
+        if type(projection).c_abi_desc is _projection.Projection.c_abi_desc:
+            projection.c_abi_desc()                 # raises: no parametric form
         self.projection = projection
-        self.zoom_kwargs["projection"] = type(projection).__name__
+        self.zoom_kwargs["projection"] = projection.fingerprint()
 
     def get_lin_mat(self):
         """ core.py:1470-1484 """
@@ -349,6 +353,11 @@ class Fractal:
         d.calc_d2zndc2 = int(bool(getattr(spec, "calc_d2zndc2", False)))
         d.calc_orbit = int(bool(spec.calc_orbit))
         d.backshift = int(spec.backshift or 0)
+        # pixel projection; the standard loops apply no dz/dc modifier
+        # (core.py:2035: the reference's own hook is commented out)
+        d.proj = self.projection.c_abi_desc()
+        d.proj.dzndc_modifier = _native.FSB_DZNDC_MOD_NONE
+        d.proj.mod_param = 0.
         return ("std", d, self._interrupted)
 
     def get_cycling_dep_args(self, calc_name, chunk_slice, final=False,

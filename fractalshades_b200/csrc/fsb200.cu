@@ -68,12 +68,14 @@ struct Ctx {
     unsigned long long *d_ctl = nullptr;              /* MAX_CHUNKS control blocks + abort flag */
     unsigned long long *h_ctl = nullptr;              /* pinned mirror        */
     int4 *d_tiles = nullptr;  long long tiles_cap = 0; /* tile descriptors of the running call */
+    C *d_proj = nullptr;  long long proj_cap = 0;     /* projected pixels of the running call */
     int *d_abort() { return (int *)(d_ctl + MAX_CHUNKS * CTL_WORDS); }
     ~Ctx()
     {
         if (d_buf) cudaFree(d_buf);
         if (d_ctl) cudaFree(d_ctl);
         if (d_tiles) cudaFree(d_tiles);
+        if (d_proj) cudaFree(d_proj);
         if (h_ctl) cudaFreeHost(h_ctl);
         for (cudaEvent_t e : {ev0, ev1, evc0, evc1}) if (e) cudaEventDestroy(e);
         for (int i = 0; i < MAX_CHUNKS; i++) {
@@ -253,6 +255,50 @@ Chunks make_chunks(const Units &u)
     return ch;
 }
 
+/* ---- projection passes ---------------------------------------------------- */
+/* Points covered by the units [unit_lo, unit_hi) of a call: a contiguous range
+ * (flat list: 32 points per unit; tile list: launches start and end on tile
+ * boundaries, see chunks_of). */
+int point_range(const Units &u, int unit_lo, int unit_hi, long long &lo, long long &hi)
+{
+    if (!u.tiled()) {
+        lo = 32LL * unit_lo;
+        hi = std::min(32LL * unit_hi, u.npts);
+        return 0;
+    }
+    lo = hi = -1;
+    for (const int4 &t : u.tiles) {
+        if (t.x == unit_lo) lo = t.y;
+        if (t.x == unit_hi) hi = t.y;
+    }
+    if (unit_hi == u.n_units) hi = u.npts;
+    if (lo < 0 || hi < 0) return fail(-1, "internal: launch not aligned on tile boundaries");
+    return 0;
+}
+/* scratch plane for the projected pixels of the running call (whole list:
+ * concurrent launches of one call work on disjoint point ranges) */
+int proj_scratch(Ctx *c, long long npts)
+{
+    if (npts <= c->proj_cap) return 0;
+    CK(cudaDeviceSynchronize());
+    if (c->d_proj) { CK(cudaFree(c->d_proj)); c->d_proj = nullptr; c->proj_cap = 0; }
+    CK(cudaMalloc(&c->d_proj, (size_t)npts * sizeof(C)));
+    c->proj_cap = npts;
+    return 0;
+}
+/* pixels -> projected pixels on stream st; *d_c_pix is redirected to the scratch */
+int enqueue_projection(Ctx *c, const ProjDev &P, const Units &u, int unit_lo, int unit_hi,
+                       cudaStream_t st, const C **d_c_pix, long long &lo, long long &hi)
+{
+    if (point_range(u, unit_lo, unit_hi, lo, hi)) return -1;
+    if (P.kind == FSB_PROJ_CARTESIAN || hi <= lo) return 0;
+    if (proj_scratch(c, u.npts)) return -1;
+    k_proj_range<<<(int)((hi - lo + 255) / 256), 256, 0, st>>>(P, lo, hi, *d_c_pix, c->d_proj);
+    CK(cudaGetLastError());
+    *d_c_pix = c->d_proj;
+    return 0;
+}
+
 /* ---- kernel dispatch ------------------------------------------------------ */
 typedef void (*perturb_kernel_t)(FrameDev, long long, const C *, double *, int *,
                                  signed char *, int *, unsigned long long *,
@@ -316,6 +362,7 @@ perturb_kernel_t pick_bs(bool xr, bool h, bool bla, bool fastxr, int flavor)
 struct fsb_frame {
     fsb_frame_desc d;
     FrameDev dev;
+    ProjDev proj;
     int nz = 0;
     bool bla_on = false;
     bool fast_xr = false;     /* Xrange kernel with the guarded fp64 fast path */
@@ -775,6 +822,20 @@ int fsb_std_nz(const fsb_std_desc *d)
     return 6 + (d->calc_orbit ? 2 : 0);
 }
 
+static int proj_fill(const fsb_proj_desc &d, ProjDev &p, bool allow_modifier)
+{
+    if (d.kind != FSB_PROJ_CARTESIAN && d.kind != FSB_PROJ_EXPMAP)
+        return fail(-3, "unsupported projection kind %d (no fallback)", d.kind);
+    if (d.dzndc_modifier < FSB_DZNDC_MOD_NONE || d.dzndc_modifier > FSB_DZNDC_MOD_SEAM)
+        return fail(-3, "unsupported dzndc modifier %d", d.dzndc_modifier);
+    if (d.dzndc_modifier != FSB_DZNDC_MOD_NONE && !allow_modifier)
+        return fail(-3, "dzndc modifier is only defined for perturbation frames");
+    p.kind = d.kind; p.mod_kind = d.dzndc_modifier;
+    p.hmoy = d.hmoy; p.k_re = d.pix_to_ht[0]; p.k_im = d.pix_to_ht[1];
+    p.mod_param = d.mod_param;
+    return 0;
+}
+
 static int std_fill(const fsb_std_desc *d, StdDev &p, long long zstride)
 {
     if (d->model != FSB_MODEL_M2 && d->model != FSB_MODEL_BS)
@@ -788,7 +849,8 @@ static int std_fill(const fsb_std_desc *d, StdDev &p, long long zstride)
     p.calc_d2 = d->calc_d2zndc2; p.calc_orbit = d->calc_orbit; p.backshift = d->backshift;
     p.flavor = d->flavor;
     p.zstride = zstride;
-    return 0;
+    ProjDev chk;
+    return proj_fill(d->proj, chk, false);
 }
 
 /* enqueue one kernel over the units [unit_lo, unit_hi) of the call's point list
@@ -805,6 +867,10 @@ static int std_enqueue(Ctx *c, const fsb_std_desc *d, const StdDev &p, cudaStrea
     if (d->model == FSB_MODEL_M2) { if (persistent_grid(k_std_m2, block, n, &grid)) return -1; }
     else { if (persistent_grid(k_std_bs, block, n, &grid)) return -1; }
     const Tiling t = tiling_of(u, unit_lo, unit_hi);
+    ProjDev P;
+    long long p_lo, p_hi;
+    if (proj_fill(d->proj, P, false)) return -1;
+    if (enqueue_projection(c, P, u, unit_lo, unit_hi, st, &d_c_pix, p_lo, p_hi)) return -1;
     if (d->model == FSB_MODEL_M2)
         k_std_m2<<<grid, block, 0, st>>>(p, u.npts, d_c_pix, d_Z, d_sr, d_si, ctl, ctl + 1,
                                          c->d_abort(), t);
@@ -1035,6 +1101,10 @@ int fsb_frame_create(const fsb_frame_desc *desc, fsb_frame **out)
     if (desc->L >= (1LL << 30) || desc->max_iter >= (1LL << 30) || desc->max_iter < 1)
         return fail(-3, "orbit length / max_iter out of the supported range (< 2^30)");
     if (desc->ref_order < 1) return fail(-3, "ref_order must be >= 1");
+    {
+        ProjDev chk;
+        if (proj_fill(desc->proj, chk, true)) return -3;
+    }
 
     fsb_frame *f = new fsb_frame();
     f->d = *desc;
@@ -1064,6 +1134,7 @@ int fsb_frame_create(const fsb_frame_desc *desc, fsb_frame **out)
     v.drift_e[0] = d.drift_e[0]; v.drift_e[1] = d.drift_e[1];
     v.lin_scale = d.lin_scale; v.lin_scale_e = d.lin_scale_e;
     for (int i = 0; i < 4; i++) v.lin_mat[i] = d.lin_mat[i];
+    proj_fill(d.proj, f->proj, true);
     v.max_iter = d.max_iter;
     v.Mdiv_sq = d.M_divergence_sq;
     v.eps_sq = d.epsilon_stationnary_sq;
@@ -1248,9 +1319,20 @@ static int frame_enqueue(Ctx *c, fsb_frame *f, cudaStream_t st, int slot, const 
     if (persistent_grid(k, block, 32LL * (unit_hi - unit_lo), &grid)) return -1;
     FrameDev dv = f->dev;
     dv.zstride = u.npts;
+    const C *d_c_raw = d_c_pix;
+    long long p_lo, p_hi;
+    if (enqueue_projection(c, f->proj, u, unit_lo, unit_hi, st, &d_c_pix, p_lo, p_hi)) return -1;
     k<<<grid, block, 0, st>>>(dv, u.npts, d_c_pix, d_Z, d_U, d_sr, d_si, ctl, ctl + 1,
                               c->d_abort(), tiling_of(u, unit_lo, unit_hi));
     CK(cudaGetLastError());
+    /* Z[dzndc] *= proj_dzndc_modifier(c_pix), perturbation.py:1387-1388, 1772-1776 */
+    if (f->proj.mod_kind != FSB_DZNDC_MOD_NONE && d.calc_dzndc && p_hi > p_lo) {
+        const int holo = (d.model == FSB_MODEL_M2);
+        const int row0 = holo ? (1 + (d.calc_dzndz ? 1 : 0)) : 2;
+        k_modifier_range<<<(int)((p_hi - p_lo + 255) / 256), 256, 0, st>>>(
+            f->proj, p_lo, p_hi, d_c_raw, d_Z, u.npts, holo, row0);
+        CK(cudaGetLastError());
+    }
     return 0;
 }
 
@@ -1446,6 +1528,10 @@ int fsb_frame_run_pp(fsb_frame *f, int32_t n_tiles, const int32_t *tile_w, const
     if (get_ctx(&c)) return -1;
     if (!f) return fail(-3, "null frame");
     if (!pp) return fail(-3, "null post-processing description");
+    /* the reference rotates / scales the derivatives with the projection's df
+     * in its post-processing (projection.py:375-453); not part of this kernel */
+    if (f->d.proj.kind != FSB_PROJ_CARTESIAN && (dem || normal_x || normal_y))
+        return fail(-3, "fused DEM / normal post-processing is only defined for the Cartesian projection");
     if (n_tiles <= 0 && npts <= 0) { if (stats) memset(stats, 0, sizeof *stats); return 0; }
     void *outs[4] = {nu, dem, normal_x, normal_y};
     return frame_run_impl(c, f, n_tiles, tile_w, tile_h, npts, c_pix, nullptr, nullptr,
@@ -1530,6 +1616,27 @@ int fsb_xr_to_standard_c(int64_t n, const double *a, const int32_t *ae, double *
     CK(cudaGetLastError());
     CK(cudaMemcpy(out, dout, n * 16, cudaMemcpyDeviceToHost));
     cudaFree(da); cudaFree(dout); cudaFree(dae);
+    return 0;
+}
+
+int fsb_proj_apply(const fsb_proj_desc *p, int64_t npts, const double *c_pix, double *out_pix,
+                   double *out_modifier)
+{
+    if (ensure_init() != 0) return -1;
+    if (!p) return fail(-3, "null argument");
+    ProjDev P;
+    if (proj_fill(*p, P, true)) return -3;
+    if (npts <= 0) return 0;
+    C *dp, *dq = nullptr; double *dm = nullptr;
+    CK(cudaMalloc(&dp, npts * 16));
+    if (out_pix) CK(cudaMalloc(&dq, npts * 16));
+    if (out_modifier) CK(cudaMalloc(&dm, npts * 8));
+    CK(cudaMemcpy(dp, c_pix, npts * 16, cudaMemcpyHostToDevice));
+    k_proj_apply<<<(int)((npts + 127) / 128), 128>>>(P, npts, dp, dq, dm);
+    CK(cudaGetLastError());
+    if (out_pix) CK(cudaMemcpy(out_pix, dq, npts * 16, cudaMemcpyDeviceToHost));
+    if (out_modifier) CK(cudaMemcpy(out_modifier, dm, npts * 8, cudaMemcpyDeviceToHost));
+    cudaFree(dp); cudaFree(dq); cudaFree(dm);
     return 0;
 }
 

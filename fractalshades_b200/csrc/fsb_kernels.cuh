@@ -25,6 +25,15 @@
 
 namespace fsb {
 
+/* Pixel projection (projection.py) and the derivative modifier applied at the
+ * end of the perturbation loops (perturbation.py:1387-1388, 1772-1776).
+ * kind: 0 Cartesian (identity), 1 Expmap; mod_kind: 0 none, 1 Expmap
+ * exp(Re(k pix) + mod_param), 2 Cartesian(expmap_seam) |pix + 1e-6| mod_param */
+struct ProjDev {
+    int kind, mod_kind;
+    double hmoy, k_re, k_im, mod_param;
+};
+
 struct FrameDev {
     long long L;
     const C *Zn;
@@ -152,6 +161,50 @@ __device__ __forceinline__ C ldC(const C *p, long long i)
 __device__ __forceinline__ void stC(double *Z, long long row, long long npts, long long i, C v)
 {
     reinterpret_cast<double2 *>(Z)[row * npts + i] = make_double2(v.re, v.im);
+}
+
+/* The projection and the modifier run as two small HBM-bound passes around
+ * the pixel kernel (same stream, same point range): the pixel kernels -- whose
+ * register allocation decides the frame time -- see already-projected pixels
+ * and are the same code for every projection (an in-kernel call, even behind
+ * a uniform branch, cost config 3 eight per cent).  16 B in / 16 B out per
+ * point; the modifier pass reads 16 B and rewrites the derivative rows. */
+__device__ __forceinline__ C project(const ProjDev &P, C pix)
+{
+    return (P.kind != 0) ? proj_expmap(pix, P.hmoy, mkC(P.k_re, P.k_im)) : pix;
+}
+__device__ __forceinline__ double dzndc_modifier(const ProjDev &P, C pix)
+{
+    return (P.mod_kind == 1) ? modifier_expmap(pix, mkC(P.k_re, P.k_im), P.mod_param)
+                             : modifier_seam(pix, P.mod_param);
+}
+__global__ void k_proj_range(ProjDev P, long long lo, long long hi, const C *__restrict__ in,
+                             C *__restrict__ out)
+{
+    const long long i = lo + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= hi) return;
+    const C q = project(P, ldC(in, i));
+    reinterpret_cast<double2 *>(out)[i] = make_double2(q.re, q.im);
+}
+/* perturbation.py:1387-1388 (complex row, numba's complex *= float) and
+ * :1772-1776 (four real rows) */
+__global__ void k_modifier_range(ProjDev P, long long lo, long long hi, const C *__restrict__ pix,
+                                 double *Z, long long zstride, int holomorphic, int row0)
+{
+    const long long i = lo + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= hi) return;
+    const double md = dzndc_modifier(P, ldC(pix, i));
+    if (holomorphic) {
+        double2 *row = reinterpret_cast<double2 *>(Z) + row0 * zstride;
+        const double2 v = row[i];
+        const C r = cmul_real_numba(mkC(v.x, v.y), md);
+        row[i] = make_double2(r.re, r.im);
+    } else {
+        for (int k = 0; k < 4; k++) {
+            double *row = Z + (row0 + k) * zstride;
+            row[i] = mul_rn(row[i], md);
+        }
+    }
 }
 
 /* ======================================================================== */
@@ -1842,6 +1895,14 @@ __global__ void k_xr_to_standard_c(long long n, const C *a, const int *ae, C *ou
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     out[i] = to_std(mkXC(a[i], ae[i]));
+}
+__global__ void k_proj_apply(ProjDev P, long long n, const C *pix, C *out_pix, double *out_mod)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const C v = ldC(pix, i);
+    if (out_pix) { const C q = project(P, v); reinterpret_cast<double2 *>(out_pix)[i] = make_double2(q.re, q.im); }
+    if (out_mod) out_mod[i] = (P.mod_kind != 0) ? dzndc_modifier(P, v) : 1.;
 }
 __global__ void k_hypot(long long n, const double *x, const double *y, double *out)
 {

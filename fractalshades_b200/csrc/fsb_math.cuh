@@ -320,4 +320,172 @@ FSB_HD double sgn(double x) { return (x < 0.) ? -1. : 1.; }
 FSB_HD double sgn_(double x) { return sgn(x); }
 FSB_HD double sgn_(XF x) { return (x.m < 0.) ? -1. : 1.; }
 
+
+/* ---- projections (projection.py) ------------------------------------------
+ * exp / sin / cos with a fixed operation sequence.  The reference evaluates
+ * the Expmap projection with numba's complex exp = libm exp, cos, sin
+ * (cmathimpl.exp_impl: r = exp(x); (r cos y, r sin y)).  libm results are not
+ * portable bit for bit (glibc on the host, CUDA's libdevice here: both < 1
+ * ulp but not identical), so the pixel -> c mapping uses the classic
+ * table-free algorithms below (the fdlibm ones: Cody-Waite reduction, a
+ * rational / polynomial kernel, error < 1 ulp) with every operation rounded
+ * individually -- no FMA contraction in either build -- which makes the
+ * projected pixel a pure function of its input on every platform: the CPU
+ * oracle restates the same sequence and agrees bit for bit. */
+FSB_HD double sub_rn(double a, double b) { return add_rn(a, -b); }
+FSB_HD double div_rn(double a, double b)
+{
+#ifdef __CUDA_ARCH__
+    return __ddiv_rn(a, b);
+#else
+    volatile double r = a / b; return r;
+#endif
+}
+FSB_HD double det_exp(double x)
+{
+    const double ln2HI = 6.93147180369123816490e-01, ln2LO = 1.90821492927058770002e-10,
+                 invln2 = 1.44269504088896338700e+00,
+                 P1 = 1.66666666666666019037e-01, P2 = -2.77777777770155933842e-03,
+                 P3 = 6.61375632143793436117e-05, P4 = -1.65339022054652515390e-06,
+                 P5 = 4.13813679705723846039e-08;
+    if (!(x == x)) return x;
+    if (x > 7.09782712893383973096e+02) return mk64(0x7ff00000, 0);
+    if (x < -7.45133219101941108420e+02) return 0.;
+    const double ax = fabs(x);
+    double hi = x, lo = 0.;
+    int k = 0;
+    if (ax > 0.34657359027997264) {                 /* 0.5 ln 2 */
+        if (ax < 1.0397207708399179) {              /* 1.5 ln 2 */
+            k = (x < 0.) ? -1 : 1;
+            hi = (x < 0.) ? add_rn(x, ln2HI) : sub_rn(x, ln2HI);
+            lo = (x < 0.) ? -ln2LO : ln2LO;
+        } else {
+            k = (int)add_rn(mul_rn(invln2, x), (x < 0.) ? -0.5 : 0.5);
+            const double t = (double)k;
+            hi = sub_rn(x, mul_rn(t, ln2HI));
+            lo = mul_rn(t, ln2LO);
+        }
+        x = sub_rn(hi, lo);
+    } else if (ax < 3.725290298461914e-09) {        /* 2^-28 */
+        return add_rn(1., x);
+    }
+    const double t = mul_rn(x, x);
+    double q = add_rn(P4, mul_rn(t, P5));
+    q = add_rn(P3, mul_rn(t, q));
+    q = add_rn(P2, mul_rn(t, q));
+    q = add_rn(P1, mul_rn(t, q));
+    const double c = sub_rn(x, mul_rn(t, q));
+    if (k == 0)
+        return sub_rn(1., sub_rn(div_rn(mul_rn(x, c), sub_rn(c, 2.)), x));
+    const double y = sub_rn(1., sub_rn(sub_rn(lo, div_rn(mul_rn(x, c), sub_rn(2., c))), hi));
+    const int k1 = k / 2;
+    return mul_rn(mul_rn(y, ldexp1(k1)), ldexp1(k - k1));   /* 2^k in two exact factors */
+}
+/* x = n pi/2 + (y0 + y1), |y0| <= pi/4 ; |x| < 2^20 pi/2 */
+FSB_HD int det_rem_pio2(double x, double &y0, double &y1)
+{
+    const double invpio2 = 6.36619772367581382433e-01,
+                 pio2_1 = 1.57079632673412561417e+00, pio2_1t = 6.07710050650619224932e-11,
+                 pio2_2 = 6.07710050630396597660e-11, pio2_2t = 2.02226624879595063154e-21,
+                 pio2_3 = 2.02226624871116645580e-21, pio2_3t = 8.47842766036889956997e-32;
+    const double ax = fabs(x);
+    if (ax <= 0.78539816339744830962) { y0 = x; y1 = 0.; return 0; }
+    const int n = (int)add_rn(mul_rn(ax, invpio2), 0.5);
+    const double fn = (double)n;
+    double r = sub_rn(ax, mul_rn(fn, pio2_1));
+    double w = mul_rn(fn, pio2_1t);
+    const int j = expfield(ax);
+    y0 = sub_rn(r, w);
+    if (j - expfield(y0) > 16) {
+        double t = r;
+        w = mul_rn(fn, pio2_2);
+        r = sub_rn(t, w);
+        w = sub_rn(mul_rn(fn, pio2_2t), sub_rn(sub_rn(t, r), w));
+        y0 = sub_rn(r, w);
+        if (j - expfield(y0) > 49) {
+            t = r;
+            w = mul_rn(fn, pio2_3);
+            r = sub_rn(t, w);
+            w = sub_rn(mul_rn(fn, pio2_3t), sub_rn(sub_rn(t, r), w));
+            y0 = sub_rn(r, w);
+        }
+    }
+    y1 = sub_rn(sub_rn(r, y0), w);
+    if (x < 0.) { y0 = -y0; y1 = -y1; return -n; }
+    return n;
+}
+FSB_HD double det_ksin(double x, double y)
+{
+    const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03,
+                 S3 = -1.98412698298579493134e-04, S4 = 2.75573137070700676789e-06,
+                 S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
+    if (fabs(x) < 7.450580596923828e-09) return x;           /* 2^-27 */
+    const double z = mul_rn(x, x), v = mul_rn(z, x);
+    double r = add_rn(S5, mul_rn(z, S6));
+    r = add_rn(S4, mul_rn(z, r));
+    r = add_rn(S3, mul_rn(z, r));
+    r = add_rn(S2, mul_rn(z, r));
+    return sub_rn(x, sub_rn(sub_rn(mul_rn(z, sub_rn(mul_rn(0.5, y), mul_rn(v, r))), y),
+                            mul_rn(v, S1)));
+}
+FSB_HD double det_kcos(double x, double y)
+{
+    const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03,
+                 C3 = 2.48015872894767294178e-05, C4 = -2.75573143513906633035e-07,
+                 C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
+    const double ax = fabs(x);
+    if (ax < 7.450580596923828e-09) return 1.;
+    const double z = mul_rn(x, x);
+    double r = add_rn(C5, mul_rn(z, C6));
+    r = add_rn(C4, mul_rn(z, r));
+    r = add_rn(C3, mul_rn(z, r));
+    r = add_rn(C2, mul_rn(z, r));
+    r = mul_rn(z, add_rn(C1, mul_rn(z, r)));
+    const double zr_xy = sub_rn(mul_rn(z, r), mul_rn(x, y));
+    if (ax < 0.3) return sub_rn(1., sub_rn(mul_rn(0.5, z), zr_xy));
+    const double qx = (ax > 0.78125) ? 0.28125 : mk64(hi32(ax) - 0x00200000, 0);   /* ~ |x| / 4 */
+    const double hz = sub_rn(mul_rn(0.5, z), qx);
+    return sub_rn(sub_rn(1., qx), sub_rn(hz, zr_xy));
+}
+FSB_HD void det_sincos(double x, double &s, double &c)
+{
+    if (!(fabs(x) < 1.6e6)) { s = c = mk64(0x7ff80000, 0); return; }   /* out of the supported range */
+    double y0, y1;
+    const int n = det_rem_pio2(x, y0, y1);
+    const double ks = det_ksin(y0, y1), kc = det_kcos(y0, y1);
+    switch (n & 3) {
+    case 0: s = ks; c = kc; break;
+    case 1: s = kc; c = -ks; break;
+    case 2: s = -ks; c = -kc; break;
+    default: s = -kc; c = ks; break;
+    }
+}
+
+/* projection.py:363-373 (Expmap.make_f_impl): exp(hmoy + pix_to_ht * pix), with
+ * numba's complex product and complex exp (cmathimpl.exp_impl) */
+FSB_HD C proj_expmap(C pix, double hmoy, C k)
+{
+    const C ht = cmul_rn(k, pix);
+    const double r = det_exp(add_rn(hmoy, ht.re));
+    double s, c;
+    det_sincos(add_rn(0., ht.im), s, c);        /* float + complex: (hmoy + re, 0 + im) */
+    return mkC(mul_rn(r, c), mul_rn(r, s));
+}
+/* projection.py:455-471 (Expmap.make_dzndc_modifier): exp(Re(pix_to_ht * pix) + hshift) */
+FSB_HD double modifier_expmap(C pix, C k, double hshift)
+{
+    const double h = add_rn(mul_rn(k.re, pix.re), -mul_rn(k.im, pix.im));
+    return det_exp(add_rn(h, hshift));
+}
+/* projection.py:205-219 (Cartesian.make_dzndc_modifier): |pix + 1e-6| * expmap_seam */
+FSB_HD double modifier_seam(C pix, double seam)
+{
+    return mul_rn(hypot_rn(add_rn(pix.re, 1.e-6), pix.im), seam);
+}
+/* complex128 *= float64 as numba lowers it: the float is cast to complex first */
+FSB_HD C cmul_real_numba(C z, double m)
+{
+    return mkC(add_rn(mul_rn(z.re, m), -mul_rn(z.im, 0.)), add_rn(mul_rn(z.re, 0.), mul_rn(z.im, m)));
+}
+
 } /* namespace fsb */

@@ -154,7 +154,16 @@ def create_frame(tables, strict=None, use_tables=False):
     for i in range(4):
         d.lin_mat[i] = lm[i]
     d.kc, d.kc_e = float(t["kc"]), int(t["kc_e"])
-    d.scale_deriv, d.scale_deriv_e = float(t["dx"]), int(t["dx_e"])
+    # perturbation.py:459-468: dx_xr, times the projection's own scale if any
+    d.scale_deriv = float(t.get("scale_deriv", t["dx"]))
+    d.scale_deriv_e = int(t.get("scale_deriv_e", t["dx_e"]))
+    pj = t.get("proj")
+    if pj is not None:
+        d.proj.kind = int(pj["kind"])
+        d.proj.dzndc_modifier = int(pj["dzndc_modifier"])
+        d.proj.hmoy = float(pj["hmoy"])
+        d.proj.pix_to_ht[0], d.proj.pix_to_ht[1] = float(pj["k_re"]), float(pj["k_im"])
+        d.proj.mod_param = float(pj["mod_param"])
     d.xr_detect = int(bool(t["xr_detect"]))
     d.bla_activated = int(bool(t["bla_activated"]))
     d.calc_orbit = int(bool(t.get("calc_orbit", False)))
@@ -482,8 +491,18 @@ class PerturbationFractal(Fractal):
         t["xr_detect"] = self.xr_detect_activated
         t["lin_mat"] = np.array(self.lin_mat, np.float64)
         t["lin_scale"], t["lin_scale_e"] = self.lin_scale_xr
+        # perturbation.py:459-468 : scale of the derivatives = dx, times the
+        # projection-induced scale (Xrange_array product: mantissa product,
+        # exponents added, renormalised)
+        t["scale_deriv"], t["scale_deriv_e"] = t["dx"], t["dx_e"]
         if self.projection.scale != 1.:
-            raise NotImplementedError("projection-induced derivative scale")
+            sm, se = fsx.mpf_to_xr(self.projection.scale)
+            m, k = np.frexp(t["dx"] * sm)
+            t["scale_deriv"], t["scale_deriv_e"] = float(m), int(t["dx_e"] + se + k)
+        pd = self.projection.c_abi_desc()
+        t["proj"] = dict(kind=pd.kind, dzndc_modifier=pd.dzndc_modifier, hmoy=pd.hmoy,
+                         k_re=pd.pix_to_ht[0], k_im=pd.pix_to_ht[1],
+                         mod_param=pd.mod_param)
         self.kc = kc = self.ref_point_kc()
         if kc[0] == 0.:
             raise RuntimeError("Resolution is too low for this zoom depth.")
@@ -498,6 +517,15 @@ class PerturbationFractal(Fractal):
         self._frame_tables = tables
         frame = create_frame(tables)
         return ("perturb", frame, self._interrupted)
+
+    def reset_bla_tree(self, cycle_indep_args):
+        """ perturbation.py:565-580 : new frame after `projection.set_exp_zoom_step`
+        (BLA validity radii and derivative scale of the step); like the
+        reference it simply rebuilds the frame with the same options """
+        self._release_indep_args(cycle_indep_args)
+        tables = self.frame_tables()
+        self._frame_tables = tables
+        return ("perturb", create_frame(tables), self._interrupted)
 
     def _release_indep_args(self, indep):
         if indep is not None and indep[0] == "perturb":

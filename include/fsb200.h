@@ -76,6 +76,33 @@ int fsb_dev_memset(void *dst_dev, int value, int64_t bytes);
 /* write `bytes` of a scratch buffer: flushes the L2 between timed launches */
 int fsb_flush_l2(void);
 
+/* ---- pixel projection --------------------------------------
+ * The numba closures `proj_impl` and `proj_dzndc_modifier` of cycle_indep_args
+ * (perturbation.py:537-549; `Fractal.proj_impl`, core.py:2037-2041) as plain
+ * parameters.  All zero = Cartesian without modifier.
+ *   FSB_PROJ_EXPMAP      projection.Expmap.make_f_impl (projection.py:363-373):
+ *                        pix -> exp(hmoy + pix_to_ht * pix)
+ *   FSB_DZNDC_MOD_EXPMAP Expmap.make_dzndc_modifier (:455-471): the dz/dc rows
+ *                        are multiplied by exp(Re(pix_to_ht * pix) + mod_param),
+ *                        mod_param = hshift (hmoy, or hmoy - exp_step_hmoy in a
+ *                        step of a large exponential zoom, :316-331)
+ *   FSB_DZNDC_MOD_SEAM   Cartesian(expmap_seam).make_dzndc_modifier (:205-219):
+ *                        |pix + 1e-6| * mod_param, mod_param = expmap_seam
+ * exp / sin / cos are evaluated with a fixed operation sequence (error < 1
+ * ulp), identical in both builds and in the CPU oracle. */
+enum { FSB_PROJ_CARTESIAN = 0, FSB_PROJ_EXPMAP = 1 };
+enum { FSB_DZNDC_MOD_NONE = 0, FSB_DZNDC_MOD_EXPMAP = 1, FSB_DZNDC_MOD_SEAM = 2 };
+typedef struct fsb_proj_desc {
+    int32_t kind;             /* FSB_PROJ_*                                    */
+    int32_t dzndc_modifier;   /* FSB_DZNDC_MOD_* (perturbation frames only)    */
+    double hmoy;              /* Expmap: (hmin + hmax) / 2                     */
+    double pix_to_ht[2];      /* Expmap.pix_to_ht (:306-313), complex          */
+    double mod_param;
+} fsb_proj_desc;
+/* the projection alone / the modifier alone on a list of pixels (tests) */
+int fsb_proj_apply(const fsb_proj_desc *p, int64_t npts, const double *c_pix,
+                   double *out_pix, double *out_modifier);
+
 /* ---- standard escape-time loop ------------------------------------------- */
 typedef struct fsb_std_desc {
     int32_t model;            /* FSB_MODEL_M2 / FSB_MODEL_BS                  */
@@ -89,6 +116,7 @@ typedef struct fsb_std_desc {
     int32_t calc_d2zndc2;
     int32_t calc_orbit;
     int64_t backshift;
+    fsb_proj_desc proj;       /* dzndc_modifier must be 0 (core.py:2035)      */
 } fsb_std_desc;
 
 /* number of rows of Z for this description */
@@ -163,6 +191,7 @@ typedef struct fsb_frame_desc {
     int64_t bla_len;
     int32_t stages_bla;
     int32_t _pad4;
+    fsb_proj_desc proj;
 } fsb_frame_desc;
 
 int fsb_frame_create(const fsb_frame_desc *desc, fsb_frame **out);

@@ -1594,4 +1594,233 @@ void fso_xr_abs2_c(int64_t n, const double *a, const int32_t *ae, double *out,
     }
 }
 
+
+/* ======================================================================== */
+/* Projections: projection.py:363-373 (Expmap.make_f_impl), :455-471
+ * (Expmap.make_dzndc_modifier), :205-219 (Cartesian.make_dzndc_modifier) and
+ * the final `Z[dzndc] *= proj_dzndc_modifier(c_pix)` of the perturbation loops
+ * (perturbation.py:1387-1388, 1772-1776).
+ *
+ * The reference evaluates them with numba's complex exp (cmathimpl.exp_impl:
+ * r = exp(x), c = cos(y), s = sin(y) -> (r c, r s)) on top of the C library.
+ *   det = 0  the C library functions, i.e. what the reference executes on this
+ *            host: pinned bit for bit by the strict fixtures;
+ *   det = 1  exp / sin / cos by a fixed sequence of individually rounded
+ *            operations (Cody-Waite reduction + the classic fdlibm kernels,
+ *            error < 1 ulp): a platform-independent definition, which the CUDA
+ *            library evaluates with the same sequence -> bit-exact GPU parity.
+ * The two differ by at most 1 ulp per function value (checked in tests/). */
+
+static const double LN2HI = 6.93147180369123816490e-01, LN2LO = 1.90821492927058770002e-10,
+                    INVLN2 = 1.44269504088896338700e+00;
+
+static double pow2i(int e)         /* exact 2^e, 0 below the subnormal range */
+{
+    return ldexp(1., e);
+}
+
+double fso_det_exp(double x)
+{
+    static const double P1 = 1.66666666666666019037e-01, P2 = -2.77777777770155933842e-03,
+                        P3 = 6.61375632143793436117e-05, P4 = -1.65339022054652515390e-06,
+                        P5 = 4.13813679705723846039e-08;
+    if (x != x) return x;
+    if (x > 7.09782712893383973096e+02) return INFINITY;
+    if (x < -7.45133219101941108420e+02) return 0.;
+    double ax = fabs(x), hi = x, lo = 0.;
+    int k = 0;
+    if (ax > 0.34657359027997264) {
+        if (ax < 1.0397207708399179) {
+            if (x < 0.) { k = -1; hi = x + LN2HI; lo = -LN2LO; }
+            else { k = 1; hi = x - LN2HI; lo = LN2LO; }
+        } else {
+            double h = (x < 0.) ? -0.5 : 0.5;
+            double kk = INVLN2 * x;
+            k = (int)(kk + h);
+            double t = (double)k;
+            double th = t * LN2HI;
+            hi = x - th;
+            lo = t * LN2LO;
+        }
+        x = hi - lo;
+    } else if (ax < 3.725290298461914e-09) {
+        return 1. + x;
+    }
+    double t = x * x;
+    double q = t * P5; q = P4 + q;
+    q = t * q; q = P3 + q;
+    q = t * q; q = P2 + q;
+    q = t * q; q = P1 + q;
+    double tq = t * q;
+    double c = x - tq;
+    double xc = x * c;
+    if (k == 0) {
+        double d = c - 2.;
+        double r = xc / d;
+        r = r - x;
+        return 1. - r;
+    }
+    double d = 2. - c;
+    double r = xc / d;
+    r = lo - r;
+    r = r - hi;
+    double y = 1. - r;
+    int k1 = k / 2;
+    y = y * pow2i(k1);
+    return y * pow2i(k - k1);
+}
+
+static int expfield_(double x) { return (int)((d2b(x) >> 52) & 0x7ff); }
+
+static int det_rem_pio2(double x, double *y0, double *y1)
+{
+    static const double invpio2 = 6.36619772367581382433e-01,
+        pio2_1 = 1.57079632673412561417e+00, pio2_1t = 6.07710050650619224932e-11,
+        pio2_2 = 6.07710050630396597660e-11, pio2_2t = 2.02226624879595063154e-21,
+        pio2_3 = 2.02226624871116645580e-21, pio2_3t = 8.47842766036889956997e-32;
+    double ax = fabs(x);
+    if (ax <= 0.78539816339744830962) { *y0 = x; *y1 = 0.; return 0; }
+    double nn = ax * invpio2;
+    int n = (int)(nn + 0.5);
+    double fn = (double)n;
+    double p = fn * pio2_1;
+    double r = ax - p;
+    double w = fn * pio2_1t;
+    int j = expfield_(ax);
+    double z0 = r - w;
+    if (j - expfield_(z0) > 16) {
+        double t = r;
+        w = fn * pio2_2;
+        r = t - w;
+        double u = t - r; u = u - w;
+        w = fn * pio2_2t; w = w - u;
+        z0 = r - w;
+        if (j - expfield_(z0) > 49) {
+            t = r;
+            w = fn * pio2_3;
+            r = t - w;
+            u = t - r; u = u - w;
+            w = fn * pio2_3t; w = w - u;
+            z0 = r - w;
+        }
+    }
+    double z1 = r - z0; z1 = z1 - w;
+    if (x < 0.) { *y0 = -z0; *y1 = -z1; return -n; }
+    *y0 = z0; *y1 = z1;
+    return n;
+}
+
+static double det_ksin(double x, double y)
+{
+    static const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03,
+        S3 = -1.98412698298579493134e-04, S4 = 2.75573137070700676789e-06,
+        S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
+    if (fabs(x) < 7.450580596923828e-09) return x;
+    double z = x * x, v = z * x;
+    double r = z * S6; r = S5 + r;
+    r = z * r; r = S4 + r;
+    r = z * r; r = S3 + r;
+    r = z * r; r = S2 + r;
+    double hy = 0.5 * y, vr = v * r;
+    double a = hy - vr;
+    a = z * a;
+    a = a - y;
+    double b = v * S1;
+    a = a - b;
+    return x - a;
+}
+
+static double det_kcos(double x, double y)
+{
+    static const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03,
+        C3 = 2.48015872894767294178e-05, C4 = -2.75573143513906633035e-07,
+        C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
+    double ax = fabs(x);
+    if (ax < 7.450580596923828e-09) return 1.;
+    double z = x * x;
+    double r = z * C6; r = C5 + r;
+    r = z * r; r = C4 + r;
+    r = z * r; r = C3 + r;
+    r = z * r; r = C2 + r;
+    r = z * r; r = C1 + r;
+    r = z * r;
+    double zr = z * r, xy = x * y;
+    double e = zr - xy;
+    double hz = 0.5 * z;
+    if (ax < 0.3) { double a = hz - e; return 1. - a; }
+    double qx;
+    if (ax > 0.78125) qx = 0.28125;
+    else qx = b2d((int64_t)((uint64_t)(((d2b(ax) >> 32) - 0x00200000) & 0xffffffffLL) << 32));
+    hz = hz - qx;
+    double a = 1. - qx;
+    double b = hz - e;
+    return a - b;
+}
+
+void fso_det_sincos(double x, double *s, double *c)
+{
+    if (!(fabs(x) < 1.6e6)) { *s = *c = NAN; return; }
+    double y0, y1;
+    int n = det_rem_pio2(x, &y0, &y1);
+    double ks = det_ksin(y0, y1), kc = det_kcos(y0, y1);
+    switch (n & 3) {
+    case 0: *s = ks; *c = kc; break;
+    case 1: *s = kc; *c = -ks; break;
+    case 2: *s = -ks; *c = -kc; break;
+    default: *s = -kc; *c = ks; break;
+    }
+}
+
+void fso_proj_expmap(int64_t n, const double *pix, double hmoy, double k_re, double k_im,
+                     int det, double *out)
+{
+    const C k = mkC(k_re, k_im);
+    for (int64_t i = 0; i < n; i++) {
+        C ht = k * path_c(pix, i);           /* pix_to_ht * pix (float factor cast to complex) */
+        double x = hmoy + ht.re;             /* float + complex: (hmoy + re, 0 + im) */
+        double y = 0. + ht.im;
+        double r, s, c;
+        if (det) { r = fso_det_exp(x); fso_det_sincos(y, &s, &c); }
+        else { c = cos(y); s = sin(y); r = exp(x); }
+        out[2 * i] = r * c;
+        out[2 * i + 1] = r * s;
+    }
+}
+
+void fso_modifier_expmap(int64_t n, const double *pix, double k_re, double k_im, double hshift,
+                         int det, double *out)
+{
+    for (int64_t i = 0; i < n; i++) {
+        double a = k_re * pix[2 * i], b = k_im * pix[2 * i + 1];
+        double h = a - b;                    /* np.real(pix_to_ht * cpix) */
+        h = h + hshift;
+        out[i] = det ? fso_det_exp(h) : exp(h);
+    }
+}
+
+void fso_modifier_seam(int64_t n, const double *pix, double seam, int det, double *out)
+{
+    for (int64_t i = 0; i < n; i++) {
+        double re = pix[2 * i] + 1.e-6, im = pix[2 * i + 1] + 0.;
+        double a = det ? fso_hypot(re, im) : hypot(re, im);    /* np.abs(complex) */
+        out[i] = a * seam;
+    }
+}
+
+/* complex128 row *= float64 : numba casts the float to complex first */
+void fso_apply_modifier_c(int64_t n, double *row, const double *mod)
+{
+    for (int64_t i = 0; i < n; i++) {
+        C z = path_c(row, i);
+        C m = mkC(mod[i], 0.);
+        C r = z * m;
+        row[2 * i] = r.re; row[2 * i + 1] = r.im;
+    }
+}
+
+void fso_apply_modifier_f(int64_t n, double *row, const double *mod)
+{
+    for (int64_t i = 0; i < n; i++) row[i] = row[i] * mod[i];
+}
+
 } /* extern "C" */

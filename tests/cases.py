@@ -164,3 +164,71 @@ for _i, _fl in enumerate(("Perpendicular burning ship", "Shark fin", "Celtic",
         x=_BS_PTS_DEEP[_i + 2][0], y=_BS_PTS_DEEP[_i + 2][1], dx="1e-330", nx=32,
         calc=dict(max_iter=30000, M_divergence=1e3, BLA_eps=1e-6,
                   calc_hessian=True))
+
+
+# ---- projections: Expmap and the Cartesian expmap seam ----
+def make_projection(mod, spec):
+    """ Build the case's projection with `mod` = the reference's
+    fractalshades.projection or fractalshades_b200.projection """
+    if spec is None:
+        return mod.Cartesian()
+    spec = dict(spec)
+    kind = spec.pop("kind")
+    spec.pop("step", None)
+    return {"expmap": mod.Expmap, "cartesian": mod.Cartesian}[kind](**spec)
+
+
+import math as _math   # noqa: E402
+
+# examples/projections/P04-deep_expmap.py (vertical, 20 decades)
+CASES["p_M2_expmap_E20_vert"] = dict(
+    kind="perturb_M2", precision=31, x="-0.18476527944640054234980108927",
+    y="1.0532419344392547587734377701", dx="7.603772829116657e-20", nx=200,
+    xy_ratio=1.6666,
+    proj=dict(kind="expmap", hmin=0.0, hmax=_math.log(1.e20) + 0.3,
+              orientation="vertical"),
+    calc=dict(max_iter=20000, M_divergence=1000.0, epsilon_stationnary=0.01,
+              BLA_eps=1e-6, interior_detect=True, calc_dzndc=True))
+# examples/movies/with_DEM/zoom_script_DEM.py: 55 decades, rotates_df=False,
+# here as one frame (horizontal) and as one step of the stepped flow
+_DEM_X = "-1.929319698524937920226708049698305350754670432084006734339806946"
+_DEM_Y = "-0.0000000000000000007592779387989739090287550144163328879329853232537252481600401185"
+CASES["p_M2_expmap_E55_horiz"] = dict(
+    kind="perturb_M2", precision=70, x=_DEM_X, y=_DEM_Y,
+    dx="7.032184999234219e-55", nx=400, xy_ratio=1.0,
+    proj=dict(kind="expmap", hmin=0.0, hmax=127.5, rotates_df=False,
+              orientation="horizontal"),
+    calc=dict(max_iter=20000, M_divergence=1000.0, epsilon_stationnary=0.001,
+              BLA_eps=1e-6, interior_detect=False, calc_dzndc=True))
+CASES["p_M2_expmap_E55_step"] = dict(
+    kind="perturb_M2", precision=70, x=_DEM_X, y=_DEM_Y,
+    dx="7.032184999234219e-55", nx=400, xy_ratio=1.0,
+    proj=dict(kind="expmap", hmin=0.0, hmax=127.5, rotates_df=False,
+              orientation="horizontal", step=(20.0, 10.0)),
+    calc=dict(max_iter=20000, M_divergence=1000.0, epsilon_stationnary=0.001,
+              BLA_eps=1e-6, interior_detect=False, calc_dzndc=True))
+# the Cartesian end of the same movie: derivative seam
+CASES["p_M2_seam_E55"] = dict(
+    kind="perturb_M2", precision=70, x=_DEM_X, y=_DEM_Y,
+    dx="1.4064369998468438e-54", nx=64, xy_ratio=1.0,
+    proj=dict(kind="cartesian", expmap_seam=1.0),
+    calc=dict(max_iter=20000, M_divergence=1000.0, epsilon_stationnary=0.001,
+              BLA_eps=1e-6, interior_detect=False, calc_dzndc=True))
+# burning ship: the modifier scales the four Jacobian rows
+CASES["p_BS_f1_expmap_E30"] = dict(
+    kind="perturb_BS", init=dict(flavor="Burning ship"), precision=50,
+    x=_BS["x"][:60], y=_BS["y"][:60], dx="1e-30", nx=160, xy_ratio=1.0,
+    theta_deg=12.0, skew=_BS["skew"],
+    proj=dict(kind="expmap", hmin=0.0, hmax=30.0, orientation="horizontal"),
+    calc=dict(max_iter=30000, M_divergence=1e3, BLA_eps=1e-6,
+              calc_hessian=True))
+# standard loops: examples/projections/P01-feigenbaum_expmap.py view
+CASES["std_M2_expmap"] = dict(
+    kind="std_M2", x=-1.40115519, y=0.0, dx=1e-06, nx=200, xy_ratio=1.0,
+    proj=dict(kind="expmap", hmin=0.0, hmax=_math.log(1.e7) + 0.3),
+    calc=dict(max_iter=20000, M_divergence=1000., epsilon_stationnary=0.01))
+CASES["std_BS_f1_expmap"] = dict(
+    kind="std_BS", init=dict(flavor="Burning ship"), x=-1.75, y=-0.03, dx=1e-3,
+    nx=120, xy_ratio=1.0,
+    proj=dict(kind="expmap", hmin=0.0, hmax=7.0, orientation="vertical"),
+    calc=dict(max_iter=800, M_divergence=1000.))

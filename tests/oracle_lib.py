@@ -246,10 +246,78 @@ def perturb_bs(t, c_pix, nthreads=0):
     return Z, U, sr, si, cnt
 
 
-def perturb(t, c_pix, nthreads=0):
+def perturb(t, c_pix, nthreads=0, det=False):
+    """ projection of the pixels, the loop, then the dz/dc modifier.  det: see
+    fs_oracle.h (C-library or platform-independent exp / sin / cos) """
+    pj = t.get("proj")
+    pix = project(pj, c_pix, det)
     if t["kind"] == "perturb_M2":
-        return perturb_m2(t, c_pix, nthreads)
-    return perturb_bs(t, c_pix, nthreads)
+        out = perturb_m2(t, pix, nthreads)
+    else:
+        out = perturb_bs(t, pix, nthreads)
+    apply_modifier(t, out[0], modifier(pj, c_pix, det))
+    return out
+
+
+# ---------------------------------------------------------------------------
+# projections (fso_proj_expmap & co); `pj` = the "proj" dict of the frame tables
+def project(pj, c_pix, det):
+    c_pix = _c128(c_pix)
+    if pj is None or int(pj["kind"]) == 0:
+        return c_pix
+    out = np.empty_like(c_pix)
+    lib().fso_proj_expmap(c_i64(c_pix.shape[0]), c_vp(_p(c_pix)), c_dbl(pj["hmoy"]),
+                          c_dbl(pj["k_re"]), c_dbl(pj["k_im"]), int(bool(det)),
+                          c_vp(_p(out)))
+    return out
+
+
+def modifier(pj, c_pix, det):
+    """ proj_dzndc_modifier(c_pix) for every pixel, or None """
+    if pj is None or int(pj["dzndc_modifier"]) == 0:
+        return None
+    c_pix = _c128(c_pix)
+    out = np.empty(c_pix.shape[0], np.float64)
+    if int(pj["dzndc_modifier"]) == 1:
+        lib().fso_modifier_expmap(c_i64(out.size), c_vp(_p(c_pix)), c_dbl(pj["k_re"]),
+                                  c_dbl(pj["k_im"]), c_dbl(pj["mod_param"]),
+                                  int(bool(det)), c_vp(_p(out)))
+    else:
+        lib().fso_modifier_seam(c_i64(out.size), c_vp(_p(c_pix)), c_dbl(pj["mod_param"]),
+                                int(bool(det)), c_vp(_p(out)))
+    return out
+
+
+def apply_modifier(t, Z, mod):
+    """ perturbation.py:1387-1388 / 1772-1776 on the derivative rows of Z """
+    if mod is None:
+        return
+    n = Z.shape[1]
+    if t["kind"] == "perturb_M2":
+        if t.get("calc_dzndc"):
+            row = 1 + int(bool(t.get("calc_dzndz")))
+            r = np.ascontiguousarray(Z[row])
+            lib().fso_apply_modifier_c(c_i64(n), c_vp(_p(r)), c_vp(_p(mod)))
+            Z[row] = r
+    elif t.get("calc_hessian"):
+        for row in range(2, 6):
+            r = np.ascontiguousarray(Z[row])
+            lib().fso_apply_modifier_f(c_i64(n), c_vp(_p(r)), c_vp(_p(mod)))
+            Z[row] = r
+
+
+def det_exp(x):
+    lib().fso_det_exp.restype = c_dbl
+    return np.array([lib().fso_det_exp(c_dbl(v)) for v in np.ravel(x)])
+
+
+def det_sincos(x):
+    s, c = c_dbl(), c_dbl()
+    out = np.empty((np.size(x), 2))
+    for i, v in enumerate(np.ravel(x)):
+        lib().fso_det_sincos(c_dbl(v), ctypes.byref(s), ctypes.byref(c))
+        out[i] = s.value, c.value
+    return out
 
 
 # ---------------------------------------------------------------------------

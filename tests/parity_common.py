@@ -37,15 +37,22 @@ def make_fractal(name, workdir=None):
     case = CASES[name]
     workdir = workdir or tempfile.mkdtemp(prefix="fsb_")
     f = _CLS[case["kind"]](workdir, **case.get("init", {}))
+    from fractalshades_b200 import projection as _proj
+    from cases import make_projection
     zoom = dict(x=case["x"], y=case["y"], dx=case["dx"], nx=case["nx"],
                 xy_ratio=case.get("xy_ratio", 1.0),
-                theta_deg=case.get("theta_deg", 0.), **case.get("skew", {}))
+                theta_deg=case.get("theta_deg", 0.),
+                projection=make_projection(_proj, case.get("proj")),
+                **case.get("skew", {}))
     if case["kind"].startswith("perturb"):
         zoom["precision"] = case["precision"]
     f.zoom(**zoom)
     # cases flagged newton=True use the reference's default flow (nucleus
     # search -> periodic reference); the flag is read when the orbit is built
     f._case_newton = bool(case.get("newton", False))
+    step = (case.get("proj") or {}).get("step")
+    if step is not None:      # one step of a stepped exponential zoom
+        f.projection.set_exp_zoom_step(*step)
     return f, case
 
 
@@ -88,7 +95,8 @@ def oracle_fill_tables(t):
         if t["calc_dzndc"]:
             t["dZndc"], t["dZndc_e"] = ol.dzndc_path_m2(
                 t["Zn_path"], t["ref_index_xr"], t["ref_xr"], t["ref_xr_e"],
-                t["ref_div_iter"], t["ref_order"], t["dx"], t["dx_e"], xr)
+                t["ref_div_iter"], t["ref_order"], t.get("scale_deriv", t["dx"]),
+                t.get("scale_deriv_e", t["dx_e"]), xr)
         if t["calc_dzndz"]:
             t["dZndz"], t["dZndz_e"] = ol.dzndz_path_m2(
                 t["Zn_path"], t["ref_index_xr"], t["ref_xr"], t["ref_xr_e"],
@@ -101,7 +109,8 @@ def oracle_fill_tables(t):
             d4, e4 = ol.dzndc_path_bs(
                 t["flavor"], t["Zn_path"], t["ref_index_xr"], t["refx_xr"],
                 t["refx_xr_e"], t["refy_xr"], t["refy_xr_e"], t["ref_div_iter"],
-                t["ref_order"], t["dx"], t["dx_e"], xr)
+                t["ref_order"], t.get("scale_deriv", t["dx"]),
+                t.get("scale_deriv_e", t["dx_e"]), xr)
             for j, k in enumerate(("dXnda", "dXndb", "dYnda", "dYndb")):
                 t[k] = d4[j]
                 t[k + "_e"] = e4[j] if e4 is not None else None
@@ -112,12 +121,18 @@ def oracle_fill_tables(t):
     return t
 
 
-def run_oracle(name, nthreads=0):
-    """ (Z, U, stop_reason, stop_iter, extra) through the CPU oracle """
+def run_oracle(name, nthreads=0, det=False):
+    """ (Z, U, stop_reason, stop_iter, extra) through the CPU oracle.  det:
+    projections evaluated with the C library (False: what the reference runs,
+    pinned by the fixtures) or with the platform-independent sequence shared
+    with the CUDA library (True: the GPU parity target); see fs_oracle.h """
     case = CASES[name]
     if case["kind"].startswith("std"):
         f, case = make_fractal(name)
-        c_pix = all_c_pix(f)
+        c_pix0 = all_c_pix(f)
+        pd = f.projection.c_abi_desc()
+        c_pix = ol.project(dict(kind=pd.kind, hmoy=pd.hmoy, k_re=pd.pix_to_ht[0],
+                                k_im=pd.pix_to_ht[1]), c_pix0, det)
         center = complex(f.x, f.y)
         if case["kind"] == "std_M2":
             Z, U, sr, si = ol.std_m2(c_pix, center, f.dx, f.lin_mat,
@@ -126,11 +141,11 @@ def run_oracle(name, nthreads=0):
             Z, U, sr, si = ol.std_bs(fsm.get_flavor_int(f.flavor), c_pix, center,
                                      f.dx, f.lin_mat, nthreads=nthreads,
                                      **case["calc"])
-        return Z, U, sr, si, {"c_pix": c_pix, "fractal": f}
+        return Z, U, sr, si, {"c_pix": c_pix0, "fractal": f}
     f, case, t = host_tables(name)
     oracle_fill_tables(t)
     c_pix = all_c_pix(f)
-    Z, U, sr, si, cnt = ol.perturb(t, c_pix, nthreads)
+    Z, U, sr, si, cnt = ol.perturb(t, c_pix, nthreads, det)
     return Z, U, sr, si, {"c_pix": c_pix, "tables": t, "fractal": f,
                           "counters": cnt}
 

@@ -30,8 +30,10 @@ def oracle_results():
     cache = {}
 
     def get(name):
+        # det=True: projections evaluated with the platform-independent exp /
+        # sin / cos sequence the CUDA library uses (no effect on Cartesian cases)
         if name not in cache:
-            cache[name] = pc.run_oracle(name)
+            cache[name] = pc.run_oracle(name, det=True)
         return cache[name]
     return get
 
@@ -163,6 +165,77 @@ def test_hypot_device_matches_oracle():
         out = np.zeros(n)
         _native.check(lib, lib.fsb_hypot_test(n, _native.ptr(x), _native.ptr(y), _native.ptr(out)))
         assert pc.same_bits(out, ref)
+
+
+def test_projection_device_matches_oracle():
+    """ Expmap projection and both dz/dc modifiers on the device == the
+    oracle's platform-independent sequence, bit for bit, in both builds; and
+    within a few ulp of the C-library evaluation the reference runs (each of
+    exp / sin / cos is within 1 ulp; a component is a rounded product of two) """
+    from fractalshades_b200 import _native
+    rg = np.random.default_rng(11)
+    n = 40000
+    pix = np.ascontiguousarray((rg.random(n) - 0.5) + 1j * (rg.random(n) - 0.5))
+    pix[:4] = [0., 0.5 + 0.5j, -0.5 - 0.5j, 1e-9j]
+    for pj in (dict(kind=1, dzndc_modifier=1, hmoy=23.17, k_re=46.35, k_im=0., mod_param=23.17),
+               dict(kind=1, dzndc_modifier=1, hmoy=63.75, k_re=0., k_im=2 * np.pi, mod_param=-3.5),
+               dict(kind=1, dzndc_modifier=1, hmoy=350., k_re=700., k_im=0., mod_param=0.25),
+               dict(kind=0, dzndc_modifier=2, hmoy=0., k_re=0., k_im=0., mod_param=1.0)):
+        d = _native.FsbProjDesc()
+        d.kind, d.dzndc_modifier, d.hmoy = pj["kind"], pj["dzndc_modifier"], pj["hmoy"]
+        d.pix_to_ht[0], d.pix_to_ht[1], d.mod_param = pj["k_re"], pj["k_im"], pj["mod_param"]
+        ref_p, ref_m = ol.project(pj, pix, True), ol.modifier(pj, pix, True)
+        libm_p, libm_m = ol.project(pj, pix, False), ol.modifier(pj, pix, False)
+        for strict in (True, False):
+            lib = _native.cuda_lib(strict)
+            out_p = np.zeros(n, np.complex128)
+            out_m = np.zeros(n)
+            _native.check(lib, lib.fsb_proj_apply(ctypes.byref(d), n, _native.ptr(pix),
+                                                  _native.ptr(out_p), _native.ptr(out_m)))
+            assert pc.same_bits(out_p, ref_p) and pc.same_bits(out_m, ref_m)
+        fin = np.isfinite(libm_p.real) & np.isfinite(libm_p.imag)
+        for a, b in ((ref_p.real[fin], libm_p.real[fin]), (ref_p.imag[fin], libm_p.imag[fin]),
+                     (ref_m, libm_m)):
+            assert np.all(np.abs(a - b) <= 4 * np.spacing(np.abs(b)))
+
+
+def test_expmap_through_the_api_tiles_and_steps():
+    """ zoom(projection=Expmap) -> calc_std_div -> calc_raw (tile scheduler,
+    projection passes per slab) == the flat call; then one step of a stepped
+    exponential zoom through reset_bla_tree """
+    import tempfile
+    import fractalshades_b200.models as fsm
+    from fractalshades_b200 import projection, settings
+    case = CASES["p_M2_expmap_E55_horiz"]
+    settings.no_newton = True
+    settings.strict_ieee = True
+    try:
+        f = fsm.Perturbation_mandelbrot(tempfile.mkdtemp())
+        proj = projection.Expmap(hmin=0., hmax=127.5, rotates_df=False)
+        f.zoom(precision=case["precision"], x=case["x"], y=case["y"], dx=case["dx"],
+               nx=case["nx"], xy_ratio=1.0, theta_deg=0., projection=proj)
+        f.calc_std_div(calc_name="c", subset=None, **case["calc"])
+        f.calc_raw("c")
+        Z = np.array(f.get_data_memmap("c", "Z", mode="r"))
+        si = np.array(f.get_data_memmap("c", "stop_iter", mode="r"))
+        Zo, Uo, sro, sio, ex = pc.run_oracle("p_M2_expmap_E55_horiz", det=True)
+        assert np.array_equal(si, sio) and pc.same_bits(Z, Zo)
+        # step: new BLA radii, derivative scale and modifier shift
+        proj.set_exp_zoom_step(20.0, 10.0)
+        data = f._calc_data["c"]
+        data["cycle_indep_args"] = f.reset_bla_tree(data["cycle_indep_args"])
+        c_pix = pc.all_c_pix(f)
+        n = c_pix.size
+        Z2 = np.zeros((2, n), np.complex128)
+        U2 = np.zeros((1, n), np.int32)
+        sr2 = -np.ones((1, n), np.int8)
+        si2 = np.zeros((1, n), np.int32)
+        assert f.numba_cycle_call((c_pix, Z2, U2, sr2, si2), data["cycle_indep_args"]) == 0
+        Zs, Us, srs, sis, exs = pc.run_oracle("p_M2_expmap_E55_step", det=True)
+        assert np.array_equal(si2, sis) and pc.same_bits(Z2, Zs)
+        f._release_indep_args(data["cycle_indep_args"])
+    finally:
+        settings.strict_ieee = False
 
 
 def test_empty_and_ragged_inputs():

@@ -202,10 +202,15 @@ def test_product_fails_loudly_without_gpu():
 def test_unsupported_features_are_refused():
     f = fsm.Mandelbrot(tempfile.mkdtemp())
 
-    class Expmap(fsb.projection.Projection):
-        pass
+    class Swirl(fsb.projection.Projection):      # a user mapping: no parametric form
+        def __init__(self):
+            pass
     with pytest.raises(NotImplementedError):
-        f.zoom(x=0., y=0., dx=1., nx=64, xy_ratio=1., theta_deg=0., projection=Expmap())
+        f.zoom(x=0., y=0., dx=1., nx=64, xy_ratio=1., theta_deg=0., projection=Swirl())
+    with pytest.raises(NotImplementedError):
+        fsb.projection.Generic_mapping(lambda z: z, lambda z: 1.)
+    with pytest.raises(ValueError):
+        fsb.projection.Expmap(hmin=2., hmax=1.)
     with pytest.raises(ValueError):
         fsm.Burning_ship(tempfile.mkdtemp(), flavor="nope")
     with pytest.raises(TypeError):

@@ -16,6 +16,7 @@ orbit, Xrange scalars, pixel grid) and checked against the fixtures too.
 import numpy as np
 import pytest
 
+import oracle_lib as ol
 import parity_common as pc
 from cases import CASES
 
@@ -35,6 +36,9 @@ FAST_FLOOR.update({
     # buffalo at 1e-330 on a boundary point: the reference's own strict and
     # fastmath compilations agree on 84.8 % of the pixels
     "p_BS_f5_E330_xr": 0.8,
+    # Expmap views (the reference's strict and fastmath compilations agree on
+    # exactly these fractions: 99.77 % here)
+    "std_BS_f1_expmap": 0.995,
 })
 
 # Fraction of matching escaped pixels whose continuous-iteration value agrees
@@ -47,6 +51,8 @@ NU_FLOOR.update({
     "p_BS_f1_E12_nohess_nobla": 0.0, "p_BS_f2_E12": 0.8, "p_BS_f5_E12": 0.0,
     "p_M2_divref_orbit": 0.85, "p_M2_shallow": 0.95, "std_BS_f4": 0.99,
     "p_BS_f4_E12": 0.99, "p_BS_f5_E330_xr": 0.9,
+    # 55-decade exponential maps: reference strict-vs-fastmath = 98.7 %
+    "p_M2_expmap_E55_horiz": 0.98, "p_M2_expmap_E55_step": 0.98,
 })
 
 
@@ -155,3 +161,48 @@ def test_oracle_vs_fastmath_reference(name, oracle_results):
     M = float(CASES[name]["calc"]["M_divergence"])
     frac = pc.nu_within(kind, M, Z, si, g["Z"], g["stop_iter"], same & (sr[0] == 1))
     assert frac is None or frac >= NU_FLOOR[name], frac
+
+
+PROJ = [n for n in ALL if CASES[n].get("proj")]
+
+
+def test_projection_functions_within_one_ulp_of_libm():
+    """ the platform-independent exp / sin / cos (fs_oracle.h, det = 1) against
+    the C library the reference calls: never more than 1 ulp apart """
+    rg = np.random.default_rng(3)
+    x = np.concatenate([(rg.random(20000) - 0.5) * 1400., (rg.random(5000) - 0.5) * 2.,
+                        (rg.random(2000) - 0.5) * 1e-6, [0., 709.7, -745., -740., 1e-300]])
+    e = ol.det_exp(x)
+    assert np.all(np.abs(e - np.exp(x)) <= np.spacing(np.exp(x)))
+    t = np.concatenate([(rg.random(20000) - 0.5) * 2 * np.pi, (rg.random(5000) - 0.5) * 4000.,
+                        (rg.random(2000) - 0.5) * 1e-5, [0., np.pi, -np.pi, np.pi / 2, np.pi / 4]])
+    sc = ol.det_sincos(t)
+    assert np.all(np.abs(sc[:, 0] - np.sin(t)) <= np.spacing(np.abs(np.sin(t))))
+    assert np.all(np.abs(sc[:, 1] - np.cos(t)) <= np.spacing(np.abs(np.cos(t))))
+
+
+@pytest.mark.parametrize("name", PROJ)
+def test_oracle_projection_modes_agree(name, oracle_results):
+    """ the only inexact link of the projection cases: oracle with the C
+    library (bit-exact with the strict fixtures above) vs oracle with the
+    platform-independent sequence (bit-exact with the CUDA library): pixel
+    coordinates within 1 ulp, integer outputs equal on >= 99.9 % of the pixels """
+    Z, U, sr, si, ex = oracle_results(name)
+    Zd, Ud, srd, sid, exd = pc.run_oracle(name, det=True)
+    same = (si == sid)[0] & (sr == srd)[0]
+    assert same.mean() >= min(FAST_FLOOR[name], 0.999), same.mean()
+    kind = CASES[name]["kind"]
+    M = float(CASES[name]["calc"]["M_divergence"])
+    frac = pc.nu_within(kind, M, Z, si, Zd, sid, same & (sr[0] == 1))
+    assert frac is None or frac >= NU_FLOOR[name], frac
+
+
+def test_expmap_zoom_adjusts_the_grid_like_the_reference():
+    """ xy_ratio / nx imposed by the projection (projection.py:339-360) and the
+    pixel grid of the fixtures (sha of c_pix from the live reference) """
+    for name in PROJ:
+        g, meta = pc.load_golden(name, "strict")
+        f, case = pc.make_fractal(name)
+        assert (f.nx, f.ny) == (int(g["nx"]), int(g["ny"]))
+        assert f.xy_ratio == float(g["xy_ratio"])
+        assert pc.sha(pc.all_c_pix(f)) == str(g["c_pix_sha"])

@@ -58,11 +58,16 @@ def run_one(name, mode):
     f = r["fractal"]
     out = {"Z": r["Z"], "U": r["U"], "stop_reason": r["stop_reason"],
            "stop_iter": r["stop_iter"], "c_pix_sha": sha(r["c_pix"]),
+           "xy_ratio": float(f.xy_ratio),
            "nx": r["nx"], "ny": r["ny"], "lin_mat": r["lin_mat"]}
     import numba
     meta = {"case": name, "mode": mode, "numba": numba.__version__,
             "numpy": np.__version__, "ref_seconds": round(t_ref, 3)}
     if case["kind"].startswith("std"):
+        import ref_tables as rt2
+        pj = rt2.proj_from_reference(f.projection)
+        r["c_pix_raw"] = r["c_pix"]
+        r["c_pix"] = ol.project(pj, r["c_pix"], False)
         if case["kind"] == "std_M2":
             Z, U, sr, si = ol.std_m2(r["c_pix"], complex(f.x, f.y), f.dx,
                                      f.lin_mat, **case["calc"])

@@ -186,7 +186,9 @@ def make_fractal(case, workdir):
     fs = load_reference()
     import fractalshades.models as fsm
     kind = case["kind"]
-    proj = fs.projection.Cartesian()
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    from cases import make_projection
+    proj = make_projection(fs.projection, case.get("proj"))
     if kind == "std_M2":
         f = fsm.Mandelbrot(workdir)
         f.zoom(x=case["x"], y=case["y"], dx=case["dx"], nx=case["nx"],
@@ -219,6 +221,13 @@ def make_fractal(case, workdir):
         f.calc_std_div(calc_name="c", subset=None, **case["calc"])
     else:
         raise ValueError(kind)
+    step = (case.get("proj") or {}).get("step")
+    if step is not None:
+        # one step of the stepped exponential zoom (core.py:891-963): the
+        # projection is told the step bounds, then the frame tables are rebuilt
+        proj.set_exp_zoom_step(*step)
+        data = f._calc_data["c"]
+        data["cycle_indep_args"] = f.reset_bla_tree(data["cycle_indep_args"])
     return f
 
 

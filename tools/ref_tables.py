@@ -17,6 +17,24 @@ def _xr1(arr):
     return m.ravel()[0], int(e.ravel()[0])
 
 
+def proj_from_reference(projection):
+    """ the reference's projection object -> the plain "proj" dict """
+    import fractalshades as fs
+    p = projection
+    d = dict(kind=0, dzndc_modifier=0, hmoy=0., k_re=0., k_im=0., mod_param=0.)
+    if isinstance(p, fs.projection.Expmap):
+        k = complex(p.pix_to_ht)
+        hshift = (p.hmoy - p.exp_step_hmoy) if p.use_step else p.hmoy
+        d.update(kind=1, dzndc_modifier=1, hmoy=float(p.hmoy), k_re=k.real,
+                 k_im=k.imag, mod_param=float(hshift))
+    elif isinstance(p, fs.projection.Cartesian):
+        if p.expmap_seam is not None:
+            d.update(dzndc_modifier=2, mod_param=float(p.expmap_seam))
+    else:
+        raise ValueError(type(p))
+    return d
+
+
 def tables_from_reference(f, indep):
     """ f: reference Fractal instance after calc_std_div ; indep: its tuple """
     holomorphic = indep[0]
@@ -84,6 +102,7 @@ def tables_from_reference(f, indep):
             t["refx_xr"] = t["refx_xr_e"] = t["refy_xr"] = t["refy_xr_e"] = None
         t["driftx"], t["driftx_e"] = _xr1(driftx_xr)
         t["drifty"], t["drifty_e"] = _xr1(drifty_xr)
+    t["proj"] = proj_from_reference(f.projection)
     t["ref_div_iter"] = int(ref_div_iter)
     t["ref_order"] = int(ref_order)
     t["lin_mat"] = np.array(lin_mat, np.float64)
