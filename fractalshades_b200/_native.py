@@ -62,7 +62,7 @@ class FsbFrameDesc(ctypes.Structure):
         ("M_divergence_sq", c_dbl), ("epsilon_stationnary_sq", c_dbl),
         ("BLA_eps", c_dbl), ("dZndc", c_vp), ("dZndc_e", c_vp), ("dZndz", c_vp),
         ("dZndz_e", c_vp), ("M_bla", c_vp), ("r_bla", c_vp), ("bla_len", c_i64),
-        ("stages_bla", c_i32), ("_pad4", c_i32), ("proj", FsbProjDesc),
+        ("stages_bla", c_i32), ("nexp", c_i32), ("proj", FsbProjDesc),
     ]
 
 

@@ -327,6 +327,22 @@ perturb_kernel_t pick_m2(bool xr, bool dc, bool dz, bool bla, bool extra, bool f
 {
     return xr ? pick_m2_dc<true>(dc, dz, bla, extra, fastxr) : pick_m2_dc<false>(dc, dz, bla, extra, fastxr);
 }
+/* Perturbation_mandelbrot_N: the same loop with the binomial model formulas
+ * (EXTRA variants: runtime ref_order wrap; no fp64 fast lane) */
+template <bool XR, bool DC, bool DZ> perturb_kernel_t pick_mn_bla(bool bla)
+{
+    return bla ? k_perturb_m2<XR, DC, DZ, true, true, false, true>
+               : k_perturb_m2<XR, DC, DZ, false, true, false, true>;
+}
+template <bool XR> perturb_kernel_t pick_mn_dc(bool dc, bool dz, bool bla)
+{
+    if (dc) return dz ? pick_mn_bla<XR, true, true>(bla) : pick_mn_bla<XR, true, false>(bla);
+    return dz ? pick_mn_bla<XR, false, true>(bla) : pick_mn_bla<XR, false, false>(bla);
+}
+perturb_kernel_t pick_mn(bool xr, bool dc, bool dz, bool bla)
+{
+    return xr ? pick_mn_dc<true>(dc, dz, bla) : pick_mn_dc<false>(dc, dz, bla);
+}
 template <bool XR, bool H, bool BLA, bool FX> perturb_kernel_t pick_bs_flavor(int flavor)
 {
     if constexpr (!XR) {
@@ -411,6 +427,16 @@ long long h_xr_find(const int32_t *index, long long n, long long idx)
     return (lo < n && index[lo] == idx) ? lo : -1;
 }
 
+/* dfdz of the holomorphic models: 2 z (mandelbrot_M2.py:599-602) or
+ * N z^(N-1) by repeated products (mandelbrot_Mn.py:643-649) */
+template <class T> T h_dfdz(int nexp, T z)
+{
+    if (nexp == 0) return 2. * z;
+    T tmp = z;
+    for (int k = 2; k < nexp; k++) tmp = tmp * z;
+    return (double)nexp * tmp;
+}
+
 /* dZndc path, serial recurrence on the host (perturbation.py:2282-2336).
  * dZ[i] = 2 Z[i-1] dZ[i-1] + scale ; Xrange variant keeps (mantissa, exp). */
 void host_dzndc_m2(const fsb_frame_desc &d, std::vector<C> &out, std::vector<int32_t> &oe)
@@ -428,18 +454,18 @@ void host_dzndc_m2(const fsb_frame_desc &d, std::vector<C> &out, std::vector<int
         for (long long i = 1; i < valid; i++) {
             long long k = d.n_xr > 0 ? h_xr_find(d.ref_index_xr, d.n_xr, i - 1) : -1;
             XC rz = (k >= 0) ? mkXC(rxr[k], d.ref_xr_e[k]) : to_xr(Zn[i - 1]);
-            XC v = (2. * rz) * mkXC(out[i - 1], oe[i - 1]) + scale_x;
+            XC v = h_dfdz(d.nexp, rz) * mkXC(out[i - 1], oe[i - 1]) + scale_x;
             out[i] = v.m; oe[i] = v.e;
         }
         long long i = valid - 1;
         if (i == d.ref_order - 1) {
-            XC v = (2. * Zn[i]) * mkXC(out[i], oe[i]) + scale_x;
+            XC v = h_dfdz(d.nexp, Zn[i]) * mkXC(out[i], oe[i]) + scale_x;
             out[0] = v.m; oe[0] = v.e;
         }
     } else {
-        for (long long i = 1; i < valid; i++) out[i] = (2. * Zn[i - 1]) * out[i - 1] + scale;
+        for (long long i = 1; i < valid; i++) out[i] = h_dfdz(d.nexp, Zn[i - 1]) * out[i - 1] + scale;
         long long i = valid - 1;
-        if (i == d.ref_order - 1) out[0] = (2. * Zn[i]) * out[i] + scale;
+        if (i == d.ref_order - 1) out[0] = h_dfdz(d.nexp, Zn[i]) * out[i] + scale;
     }
 }
 
@@ -458,18 +484,18 @@ void host_dzndz_m2(const fsb_frame_desc &d, std::vector<C> &out, std::vector<int
         for (long long i = 2; i < valid; i++) {
             long long k = d.n_xr > 0 ? h_xr_find(d.ref_index_xr, d.n_xr, i - 1) : -1;
             XC rz = (k >= 0) ? mkXC(rxr[k], d.ref_xr_e[k]) : to_xr(Zn[i - 1]);
-            XC v = (2. * rz) * mkXC(out[i - 1], oe[i - 1]);
+            XC v = h_dfdz(d.nexp, rz) * mkXC(out[i - 1], oe[i - 1]);
             out[i] = v.m; oe[i] = v.e;
         }
         long long i = valid - 1;
         long long k = d.n_xr > 0 ? h_xr_find(d.ref_index_xr, d.n_xr, i) : -1;
         XC rz = (k >= 0) ? mkXC(rxr[k], d.ref_xr_e[k]) : to_xr(Zn[i]);
-        XC v = (2. * rz) * mkXC(out[i], oe[i]);
+        XC v = h_dfdz(d.nexp, rz) * mkXC(out[i], oe[i]);
         out[L] = v.m; oe[L] = v.e;
     } else {
-        for (long long i = 2; i < valid; i++) out[i] = (2. * Zn[i - 1]) * out[i - 1];
+        for (long long i = 2; i < valid; i++) out[i] = h_dfdz(d.nexp, Zn[i - 1]) * out[i - 1];
         long long i = valid - 1;
-        out[L] = (2. * Zn[i]) * out[i];
+        out[L] = h_dfdz(d.nexp, Zn[i]) * out[i];
     }
 }
 
@@ -590,7 +616,8 @@ int build_bla(fsb_frame *f)
     int block = 128;
     int grid = (int)((comp_len + block - 1) / block);
     if (d.model == FSB_MODEL_M2)
-        k_bla_leaf_m2<<<grid, block>>>(f->dev.Zn, comp_len, kc_std, d.BLA_eps, (C *)dM, (double *)dr);
+        k_bla_leaf_m2<<<grid, block>>>(f->dev.Zn, comp_len, kc_std, d.BLA_eps, (C *)dM, (double *)dr,
+                                       d.nexp);
     else
         k_bla_leaf_bs<<<grid, block>>>(d.flavor, f->dev.Zn, comp_len, kc_std, d.BLA_eps,
                                        (double *)dM, (double *)dr);
@@ -1101,6 +1128,11 @@ int fsb_frame_create(const fsb_frame_desc *desc, fsb_frame **out)
     if (desc->L >= (1LL << 30) || desc->max_iter >= (1LL << 30) || desc->max_iter < 1)
         return fail(-3, "orbit length / max_iter out of the supported range (< 2^30)");
     if (desc->ref_order < 1) return fail(-3, "ref_order must be >= 1");
+    if (desc->nexp != 0) {
+        if (desc->model != FSB_MODEL_M2) return fail(-3, "nexp is only defined for the holomorphic model");
+        if (desc->nexp < 2 || desc->nexp > 32) return fail(-3, "exponent %d out of the supported range [2, 32]", desc->nexp);
+        if (desc->calc_orbit) return fail(-3, "calc_orbit is not supported for the power-N model");
+    }
     {
         ProjDev chk;
         if (proj_fill(desc->proj, chk, true)) return -3;
@@ -1117,6 +1149,13 @@ int fsb_frame_create(const fsb_frame_desc *desc, fsb_frame **out)
 #define UP(expr) do { if ((rc = (expr)) != 0) { fsb_frame_destroy(f); return rc; } } while (0)
     v.L = L;
     UP(upload(f, (const C *)d.Zn_path, L, &v.Zn, 1));
+    v.nexp = d.nexp;
+    if (d.nexp > 0) {            /* comb(N, k) as float64, mandelbrot_Mn.py:636-639 */
+        double cb[33];
+        cb[0] = 1.;
+        for (int k = 1; k <= d.nexp; k++) cb[k] = cb[k - 1] * (double)(d.nexp - k + 1) / (double)k;
+        UP(upload(f, cb, (long long)d.nexp + 1, &v.cbinom));
+    }
     v.n_xr = d.n_xr;
     UP(upload(f, d.ref_index_xr, d.n_xr, &v.ref_index_xr));
     if (d.model == FSB_MODEL_M2) {
@@ -1163,7 +1202,7 @@ int fsb_frame_create(const fsb_frame_desc *desc, fsb_frame **out)
         f->gpu_scan = false;              /* serial host loop: bit-exact with the oracle */
 #else
         const char *host = getenv("FSB200_HOST_DZNDC");
-        f->gpu_scan = d.model == FSB_MODEL_M2 && !(host && host[0] == '1');
+        f->gpu_scan = d.model == FSB_MODEL_M2 && d.nexp == 0 && !(host && host[0] == '1');
 #endif
     }
     if (d.calc_dzndc) {
@@ -1195,7 +1234,7 @@ int fsb_frame_create(const fsb_frame_desc *desc, fsb_frame **out)
     {
         const char *pure = getenv("FSB200_PURE_XR");
         f->fast_xr = d.xr_detect && !(pure && pure[0] == '1')
-                     && ((d.model == FSB_MODEL_M2 && !d.calc_dzndz)
+                     && ((d.model == FSB_MODEL_M2 && !d.calc_dzndz && d.nexp == 0)
                          || (d.model == FSB_MODEL_BS && d.flavor <= 3));
     }
     if (f->fast_xr && d.calc_dzndc && d.model == FSB_MODEL_BS) {
@@ -1309,8 +1348,10 @@ static int frame_enqueue(Ctx *c, fsb_frame *f, cudaStream_t st, int slot, const 
 {
     const fsb_frame_desc &d = f->d;
     perturb_kernel_t k = (d.model == FSB_MODEL_M2)
-        ? pick_m2(d.xr_detect != 0, d.calc_dzndc != 0, d.calc_dzndz != 0, f->bla_on,
-                  f->dev.order_i > 0 || d.calc_orbit != 0, f->fast_xr)
+        ? (d.nexp != 0
+               ? pick_mn(d.xr_detect != 0, d.calc_dzndc != 0, d.calc_dzndz != 0, f->bla_on)
+               : pick_m2(d.xr_detect != 0, d.calc_dzndc != 0, d.calc_dzndz != 0, f->bla_on,
+                         f->dev.order_i > 0 || d.calc_orbit != 0, f->fast_xr))
         : pick_bs(d.xr_detect != 0, d.calc_dzndc != 0, f->bla_on, f->fast_xr, d.flavor);
     unsigned long long *ctl = c->d_ctl + slot * CTL_WORDS;
     CK(cudaMemsetAsync(ctl, 0, CTL_WORDS * sizeof(unsigned long long), st));

@@ -61,6 +61,10 @@ struct FrameDev {
     /* 32-bit mirrors used by the pixel kernels (every orbit index fits) */
     int Li, ref_div_i, order_i /* 0: not a cycle */, first_invalid_i, max_iter_i, n_xr_i;
     long long zstride;   /* row stride of the output planes (>= npts of the launch) */
+    /* Perturbation_mandelbrot_N (appended: the offsets above are those of every
+     * other kernel): exponent and comb(N, k) as doubles, k = 0..N */
+    int nexp;
+    const double *cbinom;
 };
 
 struct StdDev {
@@ -483,6 +487,47 @@ __device__ __forceinline__ T p_iter_deriv(T z, T dz, R ref_zn, D ref_d)
     return 2. * ((ref_zn + z) * dz + ref_d * z); /* mandelbrot_M2.py:611-622 */
 }
 
+/* Power-N Mandelbrot (models/mandelbrot_Mn.py:628-742): full binomial
+ * expansions, written once for complex128 and Xrange like the reference's
+ * numba closures.  Cb[k] = comb(N, k) as float64. */
+template <class T>
+__device__ __forceinline__ T mn_dfdz(int nexp, T z)              /* :643-649 */
+{
+    T tmp = z;
+    for (int k = 2; k < nexp; k++) tmp = tmp * z;
+    return (double)nexp * tmp;
+}
+template <class T, class R>
+__device__ __forceinline__ T mn_iter_zn(int nexp, const double *__restrict__ Cb, T z, R ref_zn, T c)
+{
+    T tmp = z * (z + __ldg(Cb + 1) * ref_zn);                     /* :656-668 */
+    R pk = ref_zn;
+    for (int k = 2; k < nexp; k++) {
+        pk = pk * ref_zn;
+        tmp = z * (tmp + __ldg(Cb + k) * pk);
+    }
+    return tmp + c;
+}
+template <class T, class R, class D>
+__device__ __forceinline__ T mn_iter_deriv(int nexp, const double *__restrict__ Cb, T z, T dz,
+                                           R ref_zn, D ref_d)   /* :670-728 */
+{
+    const double c1 = __ldg(Cb + 1);
+    T mul = z + c1 * ref_zn;
+    T tmp = z * mul;
+    T dtmp = dz * mul + z * (dz + c1 * ref_d);
+    R pk = ref_zn;
+    for (int k = 2; k < nexp; k++) {
+        const double ck = __ldg(Cb + k);
+        D dpk = ((double)k * pk) * ref_d;
+        pk = pk * ref_zn;
+        mul = tmp + ck * pk;
+        dtmp = dz * mul + z * (dtmp + ck * dpk);
+        tmp = z * mul;
+    }
+    return dtmp;
+}
+
 /* Fast path of the Xrange kernels.  Xrange arithmetic is fp64 arithmetic with
  * an unbounded exponent: every operation is the correctly rounded result of
  * the same real operation.  While every live component of the pixel state is
@@ -554,7 +599,8 @@ __device__ __forceinline__ C to_std_small(XC x)
  * derivative fields; BLA = bilinear-approximation skipping; EXTRA = the rarely
  * used runtime options (periodic reference `ref_order`, calc_orbit) -- compiled
  * out of the common variants. */
-template <bool XR, bool DZNDC, bool DZNDZ, bool BLA, bool EXTRA, bool FASTXR = false>
+template <bool XR, bool DZNDC, bool DZNDZ, bool BLA, bool EXTRA, bool FASTXR = false,
+          bool POWN = false /* Perturbation_mandelbrot_N: binomial forms, exponent f.nexp */>
 __global__ void __launch_bounds__(128)
 k_perturb_m2(const __grid_constant__ FrameDev f, long long npts_ll,
              const C *__restrict__ c_pix, double *__restrict__ Z,
@@ -693,20 +739,28 @@ k_perturb_m2(const __grid_constant__ FrameDev f, long long npts_ll,
             if (DZNDC && !done_fast) {
                 if (XR) {
                     XC ref_d = bool_dyn_rebase ? record_zero : DZNDC_X(w_iter);
-                    dzndc_x = p_iter_deriv(zn_x, dzndc_x, ref_zn_x, ref_d);
+                    if (POWN) dzndc_x = mn_iter_deriv(f.nexp, f.cbinom, zn_x, dzndc_x, ref_zn_x, ref_d);
+                    else dzndc_x = p_iter_deriv(zn_x, dzndc_x, ref_zn_x, ref_d);
                 } else {
                     C ref_d = bool_dyn_rebase ? mkC(0., 0.) : ldC(f.dZndc, w_iter);
-                    dzndc = p_iter_deriv(zn, dzndc, ref_zn, ref_d);
+                    if (POWN) dzndc = mn_iter_deriv(f.nexp, f.cbinom, zn, dzndc, ref_zn, ref_d);
+                    else dzndc = p_iter_deriv(zn, dzndc, ref_zn, ref_d);
                 }
             }
             if (DZNDZ) {
                 const int i = nullify_dZndz ? 0 : w_iter;
-                if (XR) dzndz_x = p_iter_deriv(zn_x, dzndz_x, ref_zn_x, DZNDZ_X(i));
-                else dzndz = p_iter_deriv(zn, dzndz, ref_zn, ldC(f.dZndz, i));
+                if (XR) {
+                    if (POWN) dzndz_x = mn_iter_deriv(f.nexp, f.cbinom, zn_x, dzndz_x, ref_zn_x, DZNDZ_X(i));
+                    else dzndz_x = p_iter_deriv(zn_x, dzndz_x, ref_zn_x, DZNDZ_X(i));
+                } else {
+                    if (POWN) dzndz = mn_iter_deriv(f.nexp, f.cbinom, zn, dzndz, ref_zn, ldC(f.dZndz, i));
+                    else dzndz = p_iter_deriv(zn, dzndz, ref_zn, ldC(f.dZndz, i));
+                }
             }
             if (XR) {
                 if (!done_fast) {
-                    zn_x = p_iter_zn(zn_x, ref_zn_x, c_xr);
+                    if (POWN) zn_x = mn_iter_zn(f.nexp, f.cbinom, zn_x, ref_zn_x, c_xr);
+                    else zn_x = p_iter_zn(zn_x, ref_zn_x, c_xr);
                     zn = to_std(zn_x);
                     if (FASTXR) {          /* back to the fast path when safe */
                         fast = in_fast_range(zn);
@@ -717,7 +771,8 @@ k_perturb_m2(const __grid_constant__ FrameDev f, long long npts_ll,
                     }
                 }
             } else {
-                zn = p_iter_zn(zn, ref_zn, c);
+                if (POWN) zn = mn_iter_zn(f.nexp, f.cbinom, zn, ref_zn, c);
+                else zn = p_iter_zn(zn, ref_zn, c);
             }
 
             w_iter += 1;
@@ -1496,7 +1551,7 @@ __device__ __forceinline__ BlaNode bla_merge(BlaNode n1, BlaNode n2, double kc_s
  * levels (perturbation.py:1847-1874) and writes slot 2i. */
 __global__ void k_bla_leaf_m2(const C *__restrict__ Zn, long long comp_len,
                               double kc_std, double eps, C *__restrict__ M,
-                              double *__restrict__ r)
+                              double *__restrict__ r, int nexp)
 {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= comp_len) return;
@@ -1504,7 +1559,13 @@ __global__ void k_bla_leaf_m2(const C *__restrict__ Zn, long long comp_len,
 #pragma unroll
     for (int j = 0; j < 8; j++) {
         C z = ldC(Zn, i * 8 + j);
-        n[j].A = mkC(mul_rn(2., z.re), mul_rn(2., z.im));
+        if (nexp == 0) {
+            n[j].A = mkC(mul_rn(2., z.re), mul_rn(2., z.im));
+        } else {                  /* dfdz = N z^(N-1), mandelbrot_Mn.py:643-649 */
+            C t = z;
+            for (int k = 2; k < nexp; k++) t = cmul_rn(t, z);
+            n[j].A = mkC(mul_rn((double)nexp, t.re), mul_rn((double)nexp, t.im));
+        }
         n[j].B = mkC(1., 0.);
         n[j].r = mul_rn(eps, cabs_rn(n[j].A));
     }

@@ -212,6 +212,72 @@ class Perturbation_mandelbrot(PerturbationFractal):
                 "iterate": lambda: spec}
 
 
+class Perturbation_mandelbrot_N(PerturbationFractal):
+    """ Arbitrary-precision power-N Mandelbrot z -> z^N + c
+    (models/mandelbrot_Mn.py:387-742): same perturbation loop, model formulas
+    as full binomial expansions.  No native nucleus search for N > 2
+    (FP_loop.pyx: perturbation_mandelbrotN_ball_method / find_nucleus): the
+    image centre is the reference point, as with settings.no_newton. """
+
+    def __init__(self, directory: str, exponent: int):
+        super().__init__(directory)
+        if int(exponent) != exponent or not (2 <= exponent <= 32):
+            raise ValueError("exponent shall be an integer in [2, 32]")
+        self.exponent = int(exponent)
+        self.potential_kind = "infinity"
+        self.potential_d = self.exponent
+        self.potential_a_d = 1.
+        self.potential_M_cutoff = 1000.
+        self.critical_pt = 0.
+        self.FP_code = "zn"
+        self.holomorphic = True
+
+    def FP_loop(self, NP_orbit, c0):
+        """ models/mandelbrot_Mn.py:438-460 -> native MPFR orbit """
+        return self._native_orbit(NP_orbit, c0, flavor=None, exponent=self.exponent)
+
+    @calc_options
+    def calc_std_div(self, *, calc_name: str, subset, max_iter: int,
+                     M_divergence: float, epsilon_stationnary: float,
+                     BLA_eps: float = 1e-6, interior_detect: bool = False,
+                     calc_dzndc: bool = True, calc_orbit: bool = False,
+                     backshift: int = 0):
+        """ models/mandelbrot_Mn.py:463-606 """
+        if calc_orbit:
+            # the reference back-shifts the stored orbit point with zn ** N,
+            # i.e. the C library's polar-form cpow: no bit-defined restatement
+            raise NotImplementedError(
+                "calc_orbit is not supported for Perturbation_mandelbrot_N")
+        complex_codes = ["zn"]
+        if interior_detect:
+            complex_codes += ["dzndz"]
+        if calc_dzndc:
+            complex_codes += ["dzndc"]
+        int_codes = ["ref_cycle_iter"]
+        stop_codes = ["max_iter", "divergence", "stationnary"]
+        BLA_activated = ((BLA_eps is not None)
+                         and bool(self.dx < settings.newton_zoom_level))
+        nexp = self.exponent
+
+        def set_state():
+            def impl(instance):
+                instance.complex_type = np.complex128
+                instance.potential_M = M_divergence
+                instance.codes = (complex_codes, int_codes, stop_codes)
+                instance.calc_dZndz = interior_detect
+                instance.calc_dZndc = calc_dzndc
+            return impl
+
+        spec = KernelSpec(kind="perturb_M2", nexp=nexp, max_iter=max_iter,
+                          M_divergence=M_divergence,
+                          epsilon_stationnary=epsilon_stationnary,
+                          BLA_eps=BLA_eps, bla_activated=BLA_activated,
+                          calc_dzndc=calc_dzndc, calc_dzndz=interior_detect,
+                          calc_orbit=False, backshift=0)
+        return {"set_state": set_state, "initialize": lambda: spec,
+                "iterate": lambda: spec}
+
+
 class Perturbation_burning_ship(PerturbationFractal):
     """ Arbitrary-precision Burning-ship family
     (models/burning_ship.py:863-1130) """

@@ -123,6 +123,7 @@ def create_frame(tables, strict=None, use_tables=False):
     m2 = (t["kind"] == "perturb_M2")
     d.model = _native.FSB_MODEL_M2 if m2 else _native.FSB_MODEL_BS
     d.flavor = int(t.get("flavor", 0))
+    d.nexp = int(t.get("nexp", 0) or 0) if m2 else 0    # Perturbation_mandelbrot_N
     d.L = len(t["Zn_path"])
     d.Zn_path = arr(t["Zn_path"], np.complex128)
     idx = t.get("ref_index_xr")

@@ -190,7 +190,11 @@ typedef struct fsb_frame_desc {
     const double *r_bla;      /* float64[bla_len]                             */
     int64_t bla_len;
     int32_t stages_bla;
-    int32_t _pad4;
+    /* FSB_MODEL_M2 only.  0: Perturbation_mandelbrot (models/mandelbrot_M2.py:
+     * 591-627); N in [2, 32]: Perturbation_mandelbrot_N with exponent N -- the
+     * binomial forms of p_iter_zn / p_iter_dzndc / p_iter_dzndz and dfdz =
+     * N z^(N-1) (models/mandelbrot_Mn.py:628-742); calc_orbit must be 0 */
+    int32_t nexp;
     fsb_proj_desc proj;
 } fsb_frame_desc;
 

@@ -539,6 +539,50 @@ static inline T p_iter_deriv(T z, T dz, R ref_zn, D ref_d)
     return 2. * ((ref_zn + z) * dz + ref_d * z);
 }
 
+/* Power-N Mandelbrot, models/mandelbrot_Mn.py:628-742: full binomial
+ * expansions, C_binom[k] = comb(N, k) as float64 */
+template <class T>
+static inline T mn_dfdz(int nexp, T z)               /* :643-649 */
+{
+    T tmp = z;
+    for (int k = 2; k < nexp; k++) tmp = tmp * z;
+    return (double)nexp * tmp;
+}
+template <class T> static inline T dfdz_(int nexp, T z) { return nexp ? mn_dfdz(nexp, z) : 2. * z; }
+template <class T, class R>
+static inline T mn_iter_zn(int nexp, const double *Cb, T z, R ref_zn, T c)   /* :656-668 */
+{
+    T tmp = z * (z + Cb[1] * ref_zn);
+    R pk = ref_zn;
+    for (int k = 2; k < nexp; k++) {
+        pk = pk * ref_zn;
+        tmp = z * (tmp + Cb[k] * pk);
+    }
+    return tmp + c;
+}
+template <class T, class R, class D>
+static inline T mn_iter_deriv(int nexp, const double *Cb, T z, T dz, R ref_zn, D ref_d) /* :670-728 */
+{
+    T mul = z + Cb[1] * ref_zn;
+    T tmp = z * mul;
+    T dtmp = dz * mul + z * (dz + Cb[1] * ref_d);
+    R pk = ref_zn;
+    for (int k = 2; k < nexp; k++) {
+        D dpk = ((double)k * pk) * ref_d;
+        pk = pk * ref_zn;
+        mul = tmp + Cb[k] * pk;
+        dtmp = dz * mul + z * (dtmp + Cb[k] * dpk);
+        tmp = z * mul;
+    }
+    return dtmp;
+}
+static inline void binomials(int nexp, double *Cb)
+{
+    Cb[0] = 1.;
+    for (int k = 1; k <= nexp; k++) Cb[k] = Cb[k - 1] * (double)(nexp - k + 1) / (double)k;
+}
+#define FSO_MAX_NEXP 32
+
 /* perturbation.py:1065-1400 */
 template <bool XR>
 static void perturb_m2_pixel(const fso_frame_m2 *f, C pix, double *Z,
@@ -550,6 +594,9 @@ static void perturb_m2_pixel(const fso_frame_m2 *f, C pix, double *Z,
     const bool calc_dzndc = f->calc_dzndc, calc_dzndz = f->calc_dzndz;
     const int64_t ref_order = f->ref_order, ref_div_iter = f->ref_div_iter;
     const int64_t max_iter = f->max_iter;
+    const int nexp = f->nexp;           /* 0: Perturbation_mandelbrot ; N: ..._mandelbrot_N */
+    double Cb[FSO_MAX_NEXP + 1];
+    if (nexp > 0) binomials(nexp, Cb);
 
     /* perturbation.py:1026-1031 */
     XC c_xr = c_xr_from_pix(pix, f->lin_mat, mkXF(f->lin_scale, f->lin_scale_e),
@@ -618,22 +665,26 @@ static void perturb_m2_pixel(const fso_frame_m2 *f, C pix, double *Z,
         if (calc_dzndc) {
             if (XR) {
                 XC ref_d = bool_dyn_rebase ? record_zero : DZNDC_X(w_iter);
-                dzndc_x = p_iter_deriv(zn_x, dzndc_x, ref_zn_x, ref_d);
+                dzndc_x = nexp ? mn_iter_deriv(nexp, Cb, zn_x, dzndc_x, ref_zn_x, ref_d)
+                               : p_iter_deriv(zn_x, dzndc_x, ref_zn_x, ref_d);
             } else {
                 C ref_d = bool_dyn_rebase ? mkC(0., 0.) : path_c(f->dZndc, w_iter);
-                dzndc = p_iter_deriv(zn, dzndc, ref_zn, ref_d);
+                dzndc = nexp ? mn_iter_deriv(nexp, Cb, zn, dzndc, ref_zn, ref_d)
+                             : p_iter_deriv(zn, dzndc, ref_zn, ref_d);
             }
         }
         if (calc_dzndz) {
             int64_t i = nullify_dZndz ? 0 : w_iter;
-            if (XR) dzndz_x = p_iter_deriv(zn_x, dzndz_x, ref_zn_x, DZNDZ_X(i));
-            else dzndz = p_iter_deriv(zn, dzndz, ref_zn, path_c(f->dZndz, i));
+            if (XR) dzndz_x = nexp ? mn_iter_deriv(nexp, Cb, zn_x, dzndz_x, ref_zn_x, DZNDZ_X(i))
+                                   : p_iter_deriv(zn_x, dzndz_x, ref_zn_x, DZNDZ_X(i));
+            else dzndz = nexp ? mn_iter_deriv(nexp, Cb, zn, dzndz, ref_zn, path_c(f->dZndz, i))
+                              : p_iter_deriv(zn, dzndz, ref_zn, path_c(f->dZndz, i));
         }
         if (XR) {
-            zn_x = p_iter_zn(zn_x, ref_zn_x, c_xr);
+            zn_x = nexp ? mn_iter_zn(nexp, Cb, zn_x, ref_zn_x, c_xr) : p_iter_zn(zn_x, ref_zn_x, c_xr);
             zn = to_std(zn_x);
         } else {
-            zn = p_iter_zn(zn, ref_zn, c);
+            zn = nexp ? mn_iter_zn(nexp, Cb, zn, ref_zn, c) : p_iter_zn(zn, ref_zn, c);
         }
 
         w_iter += 1;
@@ -1331,6 +1382,14 @@ int fso_perturb_bs(const fso_frame_bs *f, int64_t npts, const double *c_pix,
 int fso_make_bla_m2(const double *Zn_path, int64_t L, double kc_m,
                     int32_t kc_e, double eps, double *M_bla, double *r_bla)
 {
+    return fso_make_bla_mn(0, Zn_path, L, kc_m, kc_e, eps, M_bla, r_bla);
+}
+
+/* nexp = 0: Perturbation_mandelbrot (dfdz = 2 z); N >= 2: ..._mandelbrot_N
+ * (dfdz = N z^(N-1) by repeated products, mandelbrot_Mn.py:643-649) */
+int fso_make_bla_mn(int nexp, const double *Zn_path, int64_t L, double kc_m,
+                    int32_t kc_e, double eps, double *M_bla, double *r_bla)
+{
     double kc_std = to_std(mkXF(kc_m, kc_e));
     const int k_comp = 8;
     int64_t comp_len = L / k_comp;
@@ -1344,7 +1403,8 @@ int fso_make_bla_m2(const double *Zn_path, int64_t L, double kc_m,
         memset(tr, 0, sizeof(tr));
         for (int j = 0; j < k_comp; j++) {
             C Zn_i = path_c(Zn_path, i * k_comp + j);
-            tM[2 * (2 * j)] = 2. * Zn_i; /* dfdz, mandelbrot_M2.py:599-602 */
+            tM[2 * (2 * j)] = nexp ? mn_dfdz(nexp, Zn_i)
+                                   : 2. * Zn_i; /* dfdz, mandelbrot_M2.py:599-602 */
             tM[2 * (2 * j) + 1] = mkC(1., 0.);
             tr[2 * j] = eps * cabs_(tM[2 * (2 * j)]);
         }
@@ -1394,6 +1454,16 @@ int fso_dzndc_path_m2(const double *Zn_path, int64_t L, int64_t n_xr,
                       int64_t ref_order, double scale_m, int32_t scale_e,
                       int xr_detect, double *out, int32_t *out_e)
 {
+    return fso_dzndc_path_mn(0, Zn_path, L, n_xr, ref_index_xr, ref_xr, ref_xr_e,
+                             ref_div_iter, ref_order, scale_m, scale_e, xr_detect, out, out_e);
+}
+
+int fso_dzndc_path_mn(int nexp, const double *Zn_path, int64_t L, int64_t n_xr,
+                      const int32_t *ref_index_xr, const double *ref_xr,
+                      const int32_t *ref_xr_e, int64_t ref_div_iter,
+                      int64_t ref_order, double scale_m, int32_t scale_e,
+                      int xr_detect, double *out, int32_t *out_e)
+{
     int64_t valid_pts = L < ref_div_iter ? L : ref_div_iter;
     XF scale_x = mkXF(scale_m, scale_e);
     double scale = to_std(scale_x);
@@ -1406,26 +1476,36 @@ int fso_dzndc_path_m2(const double *Zn_path, int64_t L, int64_t n_xr,
             C ref_zn = path_c(Zn_path, i - 1);
             int64_t k = n_xr > 0 ? xr_find(ref_index_xr, n_xr, i - 1) : -1;
             XC rz = (k >= 0) ? mkXC(path_c(ref_xr, k), ref_xr_e[k]) : to_xr(ref_zn);
-            XC v = (2. * rz) * mkXC(o[i - 1], out_e[i - 1]) + scale_x;
+            XC v = dfdz_(nexp, rz) * mkXC(o[i - 1], out_e[i - 1]) + scale_x;
             o[i] = v.m; out_e[i] = v.e;
         }
         i = valid_pts - 1;
         if (i == ref_order - 1) {
-            XC v = (2. * path_c(Zn_path, i)) * mkXC(o[i], out_e[i]) + scale_x;
+            XC v = dfdz_(nexp, path_c(Zn_path, i)) * mkXC(o[i], out_e[i]) + scale_x;
             o[0] = v.m; out_e[0] = v.e;
         }
     } else {
         for (i = 1; i < valid_pts; i++)
-            o[i] = (2. * path_c(Zn_path, i - 1)) * o[i - 1] + scale;
+            o[i] = dfdz_(nexp, path_c(Zn_path, i - 1)) * o[i - 1] + scale;
         i = valid_pts - 1;
         if (i == ref_order - 1)
-            o[0] = (2. * path_c(Zn_path, i)) * o[i] + scale;
+            o[0] = dfdz_(nexp, path_c(Zn_path, i)) * o[i] + scale;
     }
     return 0;
 }
 
 /* perturbation.py:2466-2516 */
 int fso_dzndz_path_m2(const double *Zn_path, int64_t L, int64_t n_xr,
+                      const int32_t *ref_index_xr, const double *ref_xr,
+                      const int32_t *ref_xr_e, int64_t ref_div_iter,
+                      int64_t ref_order, int xr_detect, double *out,
+                      int32_t *out_e)
+{
+    return fso_dzndz_path_mn(0, Zn_path, L, n_xr, ref_index_xr, ref_xr, ref_xr_e,
+                             ref_div_iter, ref_order, xr_detect, out, out_e);
+}
+
+int fso_dzndz_path_mn(int nexp, const double *Zn_path, int64_t L, int64_t n_xr,
                       const int32_t *ref_index_xr, const double *ref_xr,
                       const int32_t *ref_xr_e, int64_t ref_div_iter,
                       int64_t ref_order, int xr_detect, double *out,
@@ -1443,20 +1523,20 @@ int fso_dzndz_path_m2(const double *Zn_path, int64_t L, int64_t n_xr,
             C ref_zn = path_c(Zn_path, i - 1);
             int64_t k = n_xr > 0 ? xr_find(ref_index_xr, n_xr, i - 1) : -1;
             XC rz = (k >= 0) ? mkXC(path_c(ref_xr, k), ref_xr_e[k]) : to_xr(ref_zn);
-            XC v = (2. * rz) * mkXC(o[i - 1], out_e[i - 1]);
+            XC v = dfdz_(nexp, rz) * mkXC(o[i - 1], out_e[i - 1]);
             o[i] = v.m; out_e[i] = v.e;
         }
         i = valid_pts - 1;
         C ref_zn = path_c(Zn_path, i);
         int64_t k = n_xr > 0 ? xr_find(ref_index_xr, n_xr, i) : -1;
         XC rz = (k >= 0) ? mkXC(path_c(ref_xr, k), ref_xr_e[k]) : to_xr(ref_zn);
-        XC v = (2. * rz) * mkXC(o[i], out_e[i]);
+        XC v = dfdz_(nexp, rz) * mkXC(o[i], out_e[i]);
         o[L] = v.m; out_e[L] = v.e;
     } else {
         for (i = 2; i < valid_pts; i++)
-            o[i] = (2. * path_c(Zn_path, i - 1)) * o[i - 1];
+            o[i] = dfdz_(nexp, path_c(Zn_path, i - 1)) * o[i - 1];
         i = valid_pts - 1;
-        o[L] = (2. * path_c(Zn_path, i)) * o[i];
+        o[L] = dfdz_(nexp, path_c(Zn_path, i)) * o[i];
     }
     return 0;
 }

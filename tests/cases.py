@@ -232,3 +232,52 @@ CASES["std_BS_f1_expmap"] = dict(
     nx=120, xy_ratio=1.0,
     proj=dict(kind="expmap", hmin=0.0, hmax=7.0, orientation="vertical"),
     calc=dict(max_iter=800, M_divergence=1000.))
+
+
+# ---- Perturbation_mandelbrot_N (models/mandelbrot_Mn.py:387-742): boundary
+# points found by tools/find_mn_points.py.  kind "perturb_M2" (same loop, same
+# tables); init["exponent"] selects the power-N class.
+_MN_PTS = {
+    3: ("0.21480616146988719579945680880778255",
+        "0.72961232293977439159891361761556509"),
+    4: ("-0.65487208557069640038326065370157834",
+        "0.46859010696337050047907581712697293"),
+    5: ("0.351110383579925899931787250019077539000760490700596205803325571051937185272628815179798649674656372116452474161818304145015560421660991822330770457612782251125566412916330544429869243478142030281842380541534604809596919425096614823236551004761306001432908634047555106974113284791152784436351615197467046056965649546391424679397423614881773389893555234761885894384434092268284",
+        "0.701480511439901199909049666692103385334347320934128274404434094735916247030171753573064866232875162821936632215757738860020747228881322429774360610150376334834088550555107392573158991304189373709123174055379473079462559233462153097648734673015074668577211512063406809298817713054870379248468820263289394742620866061855232905863231486509031186524740313015847859179245456357711"),
+}
+CASES["p_M3_E20"] = dict(
+    kind="perturb_M2", init=dict(exponent=3), precision=40, x=_MN_PTS[3][0],
+    y=_MN_PTS[3][1], dx="3.e-20", nx=64, xy_ratio=1.25, theta_deg=25.,
+    calc=dict(max_iter=20000, BLA_eps=1e-6, interior_detect=False,
+              calc_dzndc=True, **_STD))
+CASES["p_M4_E18_interior"] = dict(
+    kind="perturb_M2", init=dict(exponent=4), precision=40, x=_MN_PTS[4][0],
+    y=_MN_PTS[4][1], dx="2.e-18", nx=48,
+    calc=dict(max_iter=20000, BLA_eps=1e-6, interior_detect=True,
+              calc_dzndc=True, **_STD))
+CASES["p_M3_E20_nobla"] = dict(
+    kind="perturb_M2", init=dict(exponent=3), precision=40, x=_MN_PTS[3][0],
+    y=_MN_PTS[3][1], dx="3.e-20", nx=32,
+    calc=dict(max_iter=8000, BLA_eps=None, interior_detect=True,
+              calc_dzndc=False, **_STD))
+# Xrange depth: the reference cannot compile the derivative closures there
+# (`k * ref_zn_pk`, mandelbrot_Mn.py:712, is int64 x Xrange, which numba_xr's
+# mul overload rejects), so the reference-pinned case has no derivative
+CASES["p_M5_E340_xr"] = dict(
+    kind="perturb_M2", init=dict(exponent=5), precision=360, x=_MN_PTS[5][0],
+    y=_MN_PTS[5][1], dx="1.e-340", nx=32,
+    calc=dict(max_iter=30000, BLA_eps=1e-6, interior_detect=False,
+              calc_dzndc=False, **_STD))
+CASES["p_M2n_E20"] = dict(        # exponent 2 through the binomial forms
+    kind="perturb_M2", init=dict(exponent=2), precision=30,
+    x="-1.74928893611435556407228", y="0.", dx="5.e-20", nx=48,
+    calc=dict(max_iter=50000, BLA_eps=1e-6, interior_detect=True,
+              calc_dzndc=True, **_STD))
+# same model on a boundary point of iteration depth ~5000: every pixel differs,
+# and the view is chaotic at the fp64 resolution (low fastmath floor)
+CASES["p_M3_E20_chaotic"] = dict(
+    kind="perturb_M2", init=dict(exponent=3), precision=40,
+    x="0.21459138481025131313267883316524207",
+    y="0.72918276962050262626535766633048414", dx="3.e-20", nx=48,
+    calc=dict(max_iter=20000, BLA_eps=1e-6, interior_detect=True,
+              calc_dzndc=True, **_STD))

@@ -37,6 +37,7 @@ class FrameM2(ctypes.Structure):
         ("bla_activated", c_i32), ("calc_dzndc", c_i32), ("calc_dzndz", c_i32),
         ("calc_orbit", c_i32), ("backshift", c_i64), ("max_iter", c_i64),
         ("M_divergence_sq", c_dbl), ("epsilon_stationnary_sq", c_dbl),
+        ("nexp", c_i32), ("_pad", c_i32),
     ]
 
 
@@ -168,6 +169,7 @@ def _frame_m2(t, keep):
     f.max_iter = int(t["max_iter"])
     f.M_divergence_sq = float(t["M_divergence"]) ** 2
     f.epsilon_stationnary_sq = float(t.get("epsilon_stationnary", 0.)) ** 2
+    f.nexp = int(t.get("nexp", 0) or 0)       # Perturbation_mandelbrot_N
     return f
 
 
@@ -322,13 +324,13 @@ def det_sincos(x):
 
 # ---------------------------------------------------------------------------
 # per-frame tables
-def make_bla_m2(Zn_path, kc, kc_e, eps):
+def make_bla_m2(Zn_path, kc, kc_e, eps, nexp=0):
     Zn = _c128(Zn_path)
     L = Zn.shape[0]
     bla_len = 2 * (L // 8)
     M = np.zeros(2 * bla_len, np.complex128)
     r = np.zeros(bla_len, np.float64)
-    stages = lib().fso_make_bla_m2(c_vp(_p(Zn)), c_i64(L), c_dbl(kc),
+    stages = lib().fso_make_bla_mn(int(nexp or 0), c_vp(_p(Zn)), c_i64(L), c_dbl(kc),
                                    c_i32(kc_e), c_dbl(eps), c_vp(_p(M)),
                                    c_vp(_p(r)))
     return M, r, bla_len, stages
@@ -347,14 +349,14 @@ def make_bla_bs(flavor, Zn_path, kc, kc_e, eps):
 
 
 def dzndc_path_m2(Zn_path, ref_index_xr, ref_xr, ref_xr_e, ref_div_iter,
-                  ref_order, scale, scale_e, xr_detect):
+                  ref_order, scale, scale_e, xr_detect, nexp=0):
     Zn = _c128(Zn_path)
     L = Zn.shape[0]
     idx, rx, rxe = _i32(ref_index_xr), _c128(ref_xr), _i32(ref_xr_e)
     n_xr = 0 if idx is None else idx.shape[0]
     out = np.zeros(L, np.complex128)
     oe = np.zeros(L, np.int32)
-    lib().fso_dzndc_path_m2(c_vp(_p(Zn)), c_i64(L), c_i64(n_xr), c_vp(_p(idx)),
+    lib().fso_dzndc_path_mn(int(nexp or 0), c_vp(_p(Zn)), c_i64(L), c_i64(n_xr), c_vp(_p(idx)),
                             c_vp(_p(rx)), c_vp(_p(rxe)), c_i64(ref_div_iter),
                             c_i64(ref_order), c_dbl(scale), c_i32(scale_e),
                             int(bool(xr_detect)), c_vp(_p(out)), c_vp(_p(oe)))
@@ -362,14 +364,14 @@ def dzndc_path_m2(Zn_path, ref_index_xr, ref_xr, ref_xr_e, ref_div_iter,
 
 
 def dzndz_path_m2(Zn_path, ref_index_xr, ref_xr, ref_xr_e, ref_div_iter,
-                  ref_order, xr_detect):
+                  ref_order, xr_detect, nexp=0):
     Zn = _c128(Zn_path)
     L = Zn.shape[0]
     idx, rx, rxe = _i32(ref_index_xr), _c128(ref_xr), _i32(ref_xr_e)
     n_xr = 0 if idx is None else idx.shape[0]
     out = np.zeros(L + 1, np.complex128)
     oe = np.zeros(L + 1, np.int32)
-    lib().fso_dzndz_path_m2(c_vp(_p(Zn)), c_i64(L), c_i64(n_xr), c_vp(_p(idx)),
+    lib().fso_dzndz_path_mn(int(nexp or 0), c_vp(_p(Zn)), c_i64(L), c_i64(n_xr), c_vp(_p(idx)),
                             c_vp(_p(rx)), c_vp(_p(rxe)), c_i64(ref_div_iter),
                             c_i64(ref_order), int(bool(xr_detect)),
                             c_vp(_p(out)), c_vp(_p(oe)))

@@ -36,7 +36,10 @@ def make_fractal(name, workdir=None):
     """ zoom() + option binding, WITHOUT touching the GPU """
     case = CASES[name]
     workdir = workdir or tempfile.mkdtemp(prefix="fsb_")
-    f = _CLS[case["kind"]](workdir, **case.get("init", {}))
+    cls = _CLS[case["kind"]]
+    if "exponent" in case.get("init", {}):
+        cls = fsm.Perturbation_mandelbrot_N
+    f = cls(workdir, **case.get("init", {}))
     from fractalshades_b200 import projection as _proj
     from cases import make_projection
     zoom = dict(x=case["x"], y=case["y"], dx=case["dx"], nx=case["nx"],
@@ -96,14 +99,15 @@ def oracle_fill_tables(t):
             t["dZndc"], t["dZndc_e"] = ol.dzndc_path_m2(
                 t["Zn_path"], t["ref_index_xr"], t["ref_xr"], t["ref_xr_e"],
                 t["ref_div_iter"], t["ref_order"], t.get("scale_deriv", t["dx"]),
-                t.get("scale_deriv_e", t["dx_e"]), xr)
+                t.get("scale_deriv_e", t["dx_e"]), xr, t.get("nexp", 0))
         if t["calc_dzndz"]:
             t["dZndz"], t["dZndz_e"] = ol.dzndz_path_m2(
                 t["Zn_path"], t["ref_index_xr"], t["ref_xr"], t["ref_xr_e"],
-                t["ref_div_iter"], t["ref_order"], xr)
+                t["ref_div_iter"], t["ref_order"], xr, t.get("nexp", 0))
         if t["bla_activated"]:
             (t["M_bla"], t["r_bla"], t["bla_len"], t["stages_bla"]
-             ) = ol.make_bla_m2(t["Zn_path"], t["kc"], t["kc_e"], t["BLA_eps"])
+             ) = ol.make_bla_m2(t["Zn_path"], t["kc"], t["kc_e"], t["BLA_eps"],
+                                t.get("nexp", 0))
     else:
         if t["calc_hessian"]:
             d4, e4 = ol.dzndc_path_bs(

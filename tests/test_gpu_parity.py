@@ -238,6 +238,28 @@ def test_expmap_through_the_api_tiles_and_steps():
         settings.strict_ieee = False
 
 
+def test_power_n_xrange_with_derivatives_matches_oracle():
+    """ Perturbation_mandelbrot_N below 1e-300 WITH dz/dc and dz/dz: the
+    reference cannot compile this combination (int64 x Xrange in
+    mandelbrot_Mn.py:712), so there is no fixture; the formulas are the same
+    templates as the fp64 case (pinned there) instantiated for Xrange, and the
+    CUDA strict build must agree with the oracle bit for bit """
+    f, case, t = pc.host_tables("p_M5_E340_xr")
+    t["calc_dzndc"] = True
+    t["calc_dzndz"] = True
+    c_pix = pc.all_c_pix(f)
+    pc.oracle_fill_tables(t)
+    Zo, Uo, sro, sio, cnt = ol.perturb(t, c_pix)
+    Z, U, sr, si, gx = pc.run_gpu_case("p_M5_E340_xr", strict=True, tables=(dict(t), c_pix))
+    assert Z.shape[0] == 3
+    assert np.array_equal(si, sio) and np.array_equal(sr, sro)
+    assert pc.same_bits(Z, Zo) and pc.same_bits(U, Uo)
+    d, de = gx["dzndc"]
+    assert pc.same_bits(d, t["dZndc"]) and np.array_equal(de, t["dZndc_e"])
+    Z2, U2, sr2, si2, _ = pc.run_gpu_case("p_M5_E340_xr", strict=False, tables=(dict(t), c_pix))
+    assert ((si2 == sio) & (sr2 == sro)).mean() >= 0.999
+
+
 def test_empty_and_ragged_inputs():
     """ empty point list, a single point, and a point count that is not a
     multiple of the warp size """

@@ -39,6 +39,9 @@ FAST_FLOOR.update({
     # Expmap views (the reference's strict and fastmath compilations agree on
     # exactly these fractions: 99.77 % here)
     "std_BS_f1_expmap": 0.995,
+    # power-3 boundary point of iteration depth ~5000 at the fp64 resolution:
+    # reference strict-vs-fastmath = 70.5 %
+    "p_M3_E20_chaotic": 0.6,
 })
 
 # Fraction of matching escaped pixels whose continuous-iteration value agrees
@@ -53,6 +56,7 @@ NU_FLOOR.update({
     "p_BS_f4_E12": 0.99, "p_BS_f5_E330_xr": 0.9,
     # 55-decade exponential maps: reference strict-vs-fastmath = 98.7 %
     "p_M2_expmap_E55_horiz": 0.98, "p_M2_expmap_E55_step": 0.98,
+    "p_M3_E20_chaotic": 0.5,
 })
 
 

@@ -204,7 +204,10 @@ def make_fractal(case, workdir):
                **case.get("skew", {}))
         f.calc_std_div(calc_name="c", subset=None, **case["calc"])
     elif kind == "perturb_M2":
-        f = fsm.Perturbation_mandelbrot(workdir)
+        if "exponent" in case.get("init", {}):
+            f = fsm.Perturbation_mandelbrot_N(workdir, **case["init"])
+        else:
+            f = fsm.Perturbation_mandelbrot(workdir)
         f.zoom(precision=case["precision"], x=case["x"], y=case["y"],
                dx=case["dx"], nx=case["nx"],
                xy_ratio=case.get("xy_ratio", 1.0),

@@ -54,6 +54,8 @@ def tables_from_reference(f, indep):
          _proj, lin_mat, lin_scale_xr, kc, M_bla, r_bla, bla_len, stages_bla,
          _mod, _intr) = indep
         t["kind"] = "perturb_M2"
+        t["nexp"] = (int(f.exponent)
+                     if type(f).__name__ == "Perturbation_mandelbrot_N" else 0)
         t["epsilon_stationnary"] = float(f.epsilon_stationnary)
         t["calc_dzndc"] = bool(f.calc_dZndc)
         t["calc_dzndz"] = bool(f.calc_dZndz)
