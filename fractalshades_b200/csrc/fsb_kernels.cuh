@@ -642,6 +642,8 @@ k_perturb_m2(const __grid_constant__ FrameDev f, long long npts_ll,
                    + mkXC(mkC(f.drift[0], f.drift[1]), f.drift_e[0]);
         }
         const C c = to_std(c_xr);
+        /* |c| < 2^-1600: lets the fp64 lane of the Xrange kernel take BLA steps */
+        const bool c_tiny = XR && FASTXR && (c_xr.e + cexp_field(c_xr.m) - 1023 < -1600);
 
         C zn = mkC(0., 0.), dzndc = zn, dzndz = zn;
         XC zn_x = to_xr(zn), dzndc_x = zn_x, dzndz_x = zn_x;
@@ -672,7 +674,26 @@ k_perturb_m2(const __grid_constant__ FrameDev f, long long npts_ll,
                     w_iter += step;
                     if (cyc) w_iter = w_iter % order;
                     ref_cur = ldC(Zn, w_iter);
-                    if (XR) {
+                    bool bla_fast = false;
+                    if (XR && FASTXR && fast && c_tiny) {
+                        /* fp64 form of the step.  With every component of A z a
+                         * normal double >= 2^-460 and |B c| <= 2^1025 |c| < 2^-575,
+                         * the B c term is far below half an ulp of the sums it
+                         * enters: fl(A z) IS the correctly rounded Xrange result
+                         * (same products, same roundings; scaling by 2^k is exact).
+                         * Out-of-range results or a non-finite B: exact path below. */
+                        const C nz = A * zn;
+                        C nd = dzndc;
+                        if (DZNDC) nd = A * dzndc;
+                        if (in_fast_range(nz) && (!DZNDC || in_fast_range(nd))
+                            && expfield(B.re) != 0x7ff && expfield(B.im) != 0x7ff) {
+                            zn = nz;
+                            if (DZNDC) dzndc = nd;
+                            bla_fast = true;
+                        }
+                    }
+                    if (bla_fast) {
+                    } else if (XR) {
                         if (FASTXR && fast) {   /* B * c needs the exact c */
                             zn_x = to_xr(zn);
                             if (DZNDC) dzndc_x = to_xr(dzndc);
@@ -1214,6 +1235,8 @@ k_perturb_bs(const __grid_constant__ FrameDev f, long long npts_ll,
         const XF a_x = mkXF(c_xr.m.re, c_xr.e) + mkXF(f.drift[0], f.drift_e[0]);
         const XF b_x = mkXF(c_xr.m.im, c_xr.e) + mkXF(f.drift[1], f.drift_e[1]);
         const double a = to_std(a_x), b = to_std(b_x);
+        const bool ab_tiny = XR && FASTXR && (a_x.e + expfield(a_x.m) - 1023 < -1600)
+                             && (b_x.e + expfield(b_x.m) - 1023 < -1600);
 
         double x = 0., y = 0., dxa = 0., dxb = 0., dya = 0., dyb = 0.;
         XF x_x = to_xr(0.), y_x = x_x, dxa_x = x_x, dxb_x = x_x, dya_x = x_x, dyb_x = x_x;
@@ -1244,7 +1267,27 @@ k_perturb_bs(const __grid_constant__ FrameDev f, long long npts_ll,
                     w_iter += step;
                     if (cyc) w_iter = w_iter % order;
                     ref_cur = ldC(Zn, w_iter);
-                    if (XR) {
+                    bool bla_fast = false;
+                    if (XR && FASTXR && fast && ab_tiny) {
+                        /* fp64 form of the step, see k_perturb_m2: with |a|, |b| <
+                         * 2^-1600 the (a, b) terms are far below half an ulp of the
+                         * in-range sums they would enter */
+                        const double nx = M[0] * x + M[1] * y, ny = M[2] * x + M[3] * y;
+                        double na = dxa, nb = dxb, nc = dya, nd = dyb;
+                        if (HESS) apply_bla_deriv_bs(M, na, nb, nc, nd);
+                        bool ok = in_fast_range(nx) && in_fast_range(ny)
+                                  && expfield(M[4]) != 0x7ff && expfield(M[5]) != 0x7ff
+                                  && expfield(M[6]) != 0x7ff && expfield(M[7]) != 0x7ff;
+                        if (HESS) ok = ok && in_fast_range(na) && in_fast_range(nb)
+                                       && in_fast_range(nc) && in_fast_range(nd);
+                        if (ok) {
+                            x = nx; y = ny;
+                            if (HESS) { dxa = na; dxb = nb; dya = nc; dyb = nd; }
+                            bla_fast = true;
+                        }
+                    }
+                    if (bla_fast) {
+                    } else if (XR) {
                         if (FASTXR && fast) TO_XR6();      /* M * (a, b) needs the exact a, b */
 #ifdef FSB_GENERIC_XR_BLA   /* operator chain of numba_xr.py, kept for A/B checks */
                         apply_bla_bs(M, x_x, y_x, a_x, b_x);
