@@ -44,7 +44,7 @@ class FsbStdDesc(ctypes.Structure):
                 ("max_iter", c_i64), ("M_divergence_sq", c_dbl),
                 ("epsilon_stationnary_sq", c_dbl), ("calc_d2zndc2", c_i32),
                 ("calc_orbit", c_i32), ("backshift", c_i64),
-                ("proj", FsbProjDesc)]
+                ("proj", FsbProjDesc), ("nexp", c_i32), ("_pad", c_i32)]
 
 
 class FsbFrameDesc(ctypes.Structure):

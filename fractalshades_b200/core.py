@@ -353,6 +353,7 @@ class Fractal:
         d.calc_d2zndc2 = int(bool(getattr(spec, "calc_d2zndc2", False)))
         d.calc_orbit = int(bool(spec.calc_orbit))
         d.backshift = int(spec.backshift or 0)
+        d.nexp = int(getattr(spec, "nexp", 0) or 0)         # Mandelbrot_N
         # pixel projection; the standard loops apply no dz/dc modifier
         # (core.py:2035: the reference's own hook is commented out)
         d.proj = self.projection.c_abi_desc()

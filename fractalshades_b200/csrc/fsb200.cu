@@ -870,6 +870,12 @@ static int std_fill(const fsb_std_desc *d, StdDev &p, long long zstride)
     if (d->model == FSB_MODEL_BS && (d->flavor < 1 || d->flavor > 5))
         return fail(-3, "unsupported burning-ship flavor %d", d->flavor);
     if (d->calc_orbit && d->backshift <= 0) return fail(-3, "calc_orbit needs backshift > 0");
+    if (d->nexp != 0) {
+        if (d->model != FSB_MODEL_M2) return fail(-3, "nexp is only defined for the Mandelbrot model");
+        if (d->nexp < 2 || d->nexp > 32) return fail(-3, "exponent %d out of the supported range [2, 32]", d->nexp);
+        if (d->calc_orbit) return fail(-3, "calc_orbit is not supported for the power-N model");
+    }
+    p.nexp = d->nexp;
     p.center_re = d->center_re; p.center_im = d->center_im; p.dx = d->dx;
     for (int i = 0; i < 4; i++) p.lin_mat[i] = d->lin_mat[i];
     p.max_iter = d->max_iter; p.Mdiv_sq = d->M_divergence_sq; p.eps_sq = d->epsilon_stationnary_sq;
@@ -891,14 +897,18 @@ static int std_enqueue(Ctx *c, const fsb_std_desc *d, const StdDev &p, cudaStrea
     const int block = 256;
     int grid = 1;
     const long long n = 32LL * (unit_hi - unit_lo);
-    if (d->model == FSB_MODEL_M2) { if (persistent_grid(k_std_m2, block, n, &grid)) return -1; }
+    if (d->model == FSB_MODEL_M2 && d->nexp != 0) { if (persistent_grid(k_std_mn, block, n, &grid)) return -1; }
+    else if (d->model == FSB_MODEL_M2) { if (persistent_grid(k_std_m2, block, n, &grid)) return -1; }
     else { if (persistent_grid(k_std_bs, block, n, &grid)) return -1; }
     const Tiling t = tiling_of(u, unit_lo, unit_hi);
     ProjDev P;
     long long p_lo, p_hi;
     if (proj_fill(d->proj, P, false)) return -1;
     if (enqueue_projection(c, P, u, unit_lo, unit_hi, st, &d_c_pix, p_lo, p_hi)) return -1;
-    if (d->model == FSB_MODEL_M2)
+    if (d->model == FSB_MODEL_M2 && d->nexp != 0)
+        k_std_mn<<<grid, block, 0, st>>>(p, u.npts, d_c_pix, d_Z, d_sr, d_si, ctl, ctl + 1,
+                                         c->d_abort(), t);
+    else if (d->model == FSB_MODEL_M2)
         k_std_m2<<<grid, block, 0, st>>>(p, u.npts, d_c_pix, d_Z, d_sr, d_si, ctl, ctl + 1,
                                          c->d_abort(), t);
     else

@@ -76,6 +76,7 @@ struct StdDev {
     long long backshift;
     int flavor;
     long long zstride;   /* row stride of the output planes */
+    int nexp;            /* k_std_mn: exponent of Mandelbrot_N */
 };
 
 /* Work units.  A launch covers units [unit_lo, unit_hi); one warp takes one unit
@@ -277,6 +278,76 @@ k_std_m2(StdDev p, long long npts, const C *__restrict__ c_pix,
             while (orbit_i2 < n_iter - p.backshift) { zo = cadd_rn(cmul_rn(zo, zo), c); orbit_i2 += 1; }
             stC(Z, row++, p.zstride, i, zo);
         }
+        stop_reason[i] = (signed char)reason;
+        stop_iter[i] = (int)n_iter;
+        n_sum += (unsigned long long)n_iter;
+    }
+    add_counters(counters, n_exec, 0, 0, n_sum);
+}
+
+/* Mandelbrot_N.calc_std_div (models/mandelbrot_Mn.py:300-350): z -> z^N + c with
+ * dzndc, dzndz (and d2zndc2).  The reference forms z^(N-1) with numba's complex
+ * power -- a product for exponent 2, else the C library's polar form (CPython
+ * _Py_c_pow: hypot, pow, atan2, cos, sin), which has no bit-defined portable
+ * restatement and "loses a lot of precision" (numba's own comment).  Here the
+ * power is a left-to-right product chain of individually rounded operations:
+ * identical to the reference for N = 3, a few ulp from it otherwise (and more
+ * accurate); the oracle has both forms. */
+__device__ __forceinline__ C cpow_chain(C a, int n)
+{
+    if (n == 0) return mkC(1., 0.);
+    C r = a;
+    for (int k = 1; k < n; k++) r = cmul_rn(r, a);
+    return r;
+}
+__device__ __forceinline__ C cscale_rn(double s, C a) { return mkC(mul_rn(s, a.re), mul_rn(s, a.im)); }
+
+__global__ void __launch_bounds__(256)
+k_std_mn(StdDev p, long long npts, const C *__restrict__ c_pix,
+         double *__restrict__ Z, signed char *__restrict__ stop_reason,
+         int *__restrict__ stop_iter, unsigned long long *work,
+         unsigned long long *counters, const volatile int *abort_flag,
+         const Tiling tiling)
+{
+    unsigned long long n_exec = 0, n_sum = 0;
+    const int deg = p.nexp;
+    const double fdeg = (double)deg, fdeg_m1 = (double)(deg - 1);
+    for (;;) {
+        int ipt_; bool valid_;
+        if (!grab_unit(work, abort_flag, tiling, npts, ipt_, valid_)) break;
+        if (!valid_) continue;
+        const long long i = ipt_;
+        C c = c_from_pix(ldC(c_pix, i), p.lin_mat, p.dx, mkC(p.center_re, p.center_im));
+        C zn = mkC(0., 0.), dzndz = zn, dzndc = zn, d2 = zn;
+        long long n_iter = 0;
+        int reason = -1;
+        for (;;) {
+            n_iter += 1;
+            if (n_iter >= p.max_iter) { reason = 0; break; }
+            C zn_m1, zn_m;
+            if (p.calc_d2) {
+                const C zn_m2 = cpow_chain(zn, deg - 2);
+                zn_m1 = cmul_rn(zn_m2, zn);
+                zn_m = cmul_rn(zn_m1, zn);
+                d2 = cscale_rn(fdeg, cadd_rn(cmul_rn(d2, zn_m1),
+                                             cmul_rn(cmul_rn(cscale_rn(fdeg_m1, dzndz), dzndc), zn_m2)));
+            } else {
+                zn_m1 = cpow_chain(zn, deg - 1);
+                zn_m = cmul_rn(zn_m1, zn);
+            }
+            dzndc = cadd_rn(cmul_rn(cscale_rn(fdeg, dzndc), zn_m1), mkC(1., 0.));
+            dzndz = cmul_rn(cscale_rn(fdeg, dzndz), zn_m1);
+            zn = cadd_rn(zn_m, c);
+            if (n_iter == 1) dzndz = mkC(1., 0.);
+            n_exec++;
+            if (norm2_rn(zn) > p.Mdiv_sq) { reason = 1; break; }
+            if (norm2_rn(dzndz) < p.eps_sq) { reason = 2; break; }
+        }
+        long long row = 0;
+        stC(Z, row++, p.zstride, i, zn);
+        stC(Z, row++, p.zstride, i, dzndz);
+        stC(Z, row++, p.zstride, i, dzndc);
+        if (p.calc_d2) stC(Z, row++, p.zstride, i, d2);
         stop_reason[i] = (signed char)reason;
         stop_iter[i] = (int)n_iter;
         n_sum += (unsigned long long)n_iter;
@@ -486,6 +557,25 @@ __device__ __forceinline__ T p_iter_deriv(T z, T dz, R ref_zn, D ref_d)
 {
     return 2. * ((ref_zn + z) * dz + ref_d * z); /* mandelbrot_M2.py:611-622 */
 }
+
+#if !defined(FSB_STRICT) && defined(FSB_FMA_CHAIN)
+/* Default build, fp64 operands: the same two formulas as explicit FMA chains
+ * (the reference's loops are numba fastmath: LLVM contracts and re-associates
+ * them on FMA hosts, so no particular rounding sequence is "the" reference). */
+__device__ __forceinline__ C p_iter_zn(C z, C ref_zn, C c)
+{
+    const double tr = fma(2., ref_zn.re, z.re), ti = fma(2., ref_zn.im, z.im);
+    return mkC(fma(z.re, tr, fma(-z.im, ti, c.re)), fma(z.re, ti, fma(z.im, tr, c.im)));
+}
+__device__ __forceinline__ C p_iter_deriv(C z, C dz, C ref_zn, C ref_d)
+{
+    /* s = 2 (Z + z) = (z + 2 Z) + z ; d = 2 Z' : both doublings are exact */
+    const double sr = fma(2., ref_zn.re, z.re) + z.re, si = fma(2., ref_zn.im, z.im) + z.im;
+    const double dr = ref_d.re + ref_d.re, di = ref_d.im + ref_d.im;
+    return mkC(fma(sr, dz.re, fma(-si, dz.im, fma(dr, z.re, -(di * z.im)))),
+               fma(sr, dz.im, fma(si, dz.re, fma(dr, z.im, di * z.re))));
+}
+#endif
 
 /* Power-N Mandelbrot (models/mandelbrot_Mn.py:628-742): full binomial
  * expansions, written once for complex128 and Xrange like the reference's

@@ -75,6 +75,54 @@ class Mandelbrot(Fractal):
                 "iterate": lambda: spec}
 
 
+class Mandelbrot_N(Fractal):
+    """ Standard power-N Mandelbrot z -> z^N + c (models/mandelbrot_Mn.py:20-350).
+    z^(N-1) is evaluated as a product chain (see k_std_mn): identical to the
+    reference for N = 3, a few ulp from its C-library polar form otherwise. """
+
+    def __init__(self, directory: str, exponent: int):
+        super().__init__(directory)
+        if int(exponent) != exponent or not (2 <= exponent <= 32):
+            raise ValueError("exponent shall be an integer in [2, 32]")
+        self.exponent = int(exponent)
+        self.potential_kind = "infinity"
+        self.potential_d = self.exponent
+        self.potential_a_d = 1.
+        self.holomorphic = True
+
+    @calc_options
+    def calc_std_div(self, *, calc_name: str, subset=None, max_iter: int,
+                     M_divergence: float, epsilon_stationnary: float,
+                     calc_d2zndc2: bool = False, calc_orbit: bool = False,
+                     backshift: int = 0):
+        """ models/mandelbrot_Mn.py:63-145 """
+        if calc_orbit:
+            raise NotImplementedError(
+                "calc_orbit is not supported for Mandelbrot_N (the reference "
+                "back-shifts with the C library's polar-form complex power)")
+        complex_codes = ["zn", "dzndz", "dzndc"]
+        if calc_d2zndc2:
+            complex_codes += ["d2zndc2"]
+        int_codes = []
+        stop_codes = ["max_iter", "divergence", "stationnary"]
+
+        def set_state():
+            def impl(instance):
+                instance.codes = (complex_codes, int_codes, stop_codes)
+                instance.complex_type = np.complex128
+                instance.potential_M = M_divergence
+                instance.backshift = None
+            return impl
+
+        spec = KernelSpec(kind="std_M2", model=_native.FSB_MODEL_M2, flavor=0,
+                          nexp=self.exponent, max_iter=max_iter,
+                          M_divergence=M_divergence,
+                          epsilon_stationnary=epsilon_stationnary,
+                          calc_d2zndc2=calc_d2zndc2, calc_orbit=False, backshift=0)
+        return {"set_state": set_state, "initialize": lambda: spec,
+                "iterate": lambda: spec}
+
+
 class Burning_ship(Fractal):
     """ Standard Burning-ship family (models/burning_ship.py:125-429) """
 

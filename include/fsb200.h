@@ -117,6 +117,11 @@ typedef struct fsb_std_desc {
     int32_t calc_orbit;
     int64_t backshift;
     fsb_proj_desc proj;       /* dzndc_modifier must be 0 (core.py:2035)      */
+    /* FSB_MODEL_M2 only.  0: Mandelbrot (models/mandelbrot_M2.py:310-334);
+     * N in [2, 32]: Mandelbrot_N.calc_std_div, z -> z^N + c (models/
+     * mandelbrot_Mn.py:63-350), z^(N-1) as a product chain; calc_orbit must be 0 */
+    int32_t nexp;
+    int32_t _pad;
 } fsb_std_desc;
 
 /* number of rows of Z for this description */

@@ -380,6 +380,70 @@ static void std_m2_pixel(C c, int64_t max_iter, double Mdiv_sq, double epscv_sq,
     *niter = (int32_t)n_iter;
 }
 
+/* Power-N standard loop: core.py:2965-3004 + mandelbrot_Mn.py:300-350.
+ * `_zn ** deg_m1` is numba's complex power: a product when the exponent is 2,
+ * else numba_cpow -> CPython's _Py_c_pow, the polar form on top of the C
+ * library (hypot, pow, atan2, cos, sin).
+ *   use_cpow = 1  that polar form: what the reference executes (pinned by the
+ *                 strict fixtures);
+ *   use_cpow = 0  the power as a left-to-right product chain: the platform-
+ *                 independent definition the CUDA library evaluates (identical
+ *                 for N = 3 without d2zndc2, a few ulp away otherwise). */
+static inline C c_pow_int(C a, int n, int use_cpow)
+{
+    if (n == 2) return a * a;                       /* numbers.py:1008-1022 */
+    if (use_cpow) {
+        if (n == 0) return mkC(1., 0.);
+        if (a.re == 0. && a.im == 0.) return mkC(0., 0.);
+        double vabs = hypot(a.re, a.im);
+        double len = pow(vabs, (double)n);
+        double at = atan2(a.im, a.re);
+        double phase = at * (double)n;
+        return mkC(len * cos(phase), len * sin(phase));
+    }
+    if (n == 0) return mkC(1., 0.);
+    C r = a;
+    for (int k = 1; k < n; k++) r = r * a;
+    return r;
+}
+
+static void std_mn_pixel(int deg, int use_cpow, C c, int64_t max_iter, double Mdiv_sq,
+                         double epscv_sq, int calc_d2, double *Z, int64_t stride,
+                         int8_t *stop, int32_t *niter)
+{
+    C zn = mkC(0., 0.), dzndz = zn, dzndc = zn, d2 = zn;
+    const double fdeg = (double)deg, fdeg_m1 = (double)(deg - 1);
+    int64_t n_iter = 0;
+    int8_t reason = -1;
+    for (;;) {
+        n_iter += 1;
+        if (n_iter >= max_iter) { reason = 0; break; }
+        C zn_m1, zn_m;
+        if (calc_d2) {
+            C zn_m2 = c_pow_int(zn, deg - 2, use_cpow);
+            zn_m1 = zn_m2 * zn;
+            zn_m = zn_m1 * zn;
+            d2 = fdeg * (d2 * zn_m1 + ((fdeg_m1 * dzndz) * dzndc) * zn_m2);
+        } else {
+            zn_m1 = c_pow_int(zn, deg - 1, use_cpow);
+            zn_m = zn_m1 * zn;
+        }
+        dzndc = (fdeg * dzndc) * zn_m1 + 1.;
+        dzndz = (fdeg * dzndz) * zn_m1;
+        zn = zn_m + c;
+        if (n_iter == 1) dzndz = mkC(1., 0.);
+        if (zn.re * zn.re + zn.im * zn.im > Mdiv_sq) { reason = 1; break; }
+        if (dzndz.re * dzndz.re + dzndz.im * dzndz.im < epscv_sq) { reason = 2; break; }
+    }
+    int row = 0;
+    Z[2 * stride * row] = zn.re; Z[2 * stride * row + 1] = zn.im; row++;
+    Z[2 * stride * row] = dzndz.re; Z[2 * stride * row + 1] = dzndz.im; row++;
+    Z[2 * stride * row] = dzndc.re; Z[2 * stride * row + 1] = dzndc.im; row++;
+    if (calc_d2) { Z[2 * stride * row] = d2.re; Z[2 * stride * row + 1] = d2.im; row++; }
+    *stop = reason;
+    *niter = (int32_t)n_iter;
+}
+
 static inline double sgn(double x) { return (x < 0.) ? -1. : 1.; } /* burning_ship.py:12-17 */
 
 /* burning_ship.py:82-122 */
@@ -1315,6 +1379,23 @@ int fso_std_m2(int64_t npts, const double *c_pix, double center_re,
         C c = c_from_pix(path_c(c_pix, i), lin_mat, dx, center);
         std_m2_pixel(c, max_iter, Mdiv_sq, epscv_sq, calc_d2zndc2, calc_orbit,
                      backshift, Z + 2 * i, npts, stop_reason + i, stop_iter + i);
+    }
+    return 0;
+}
+
+int fso_std_mn(int nexp, int use_cpow, int64_t npts, const double *c_pix, double center_re,
+               double center_im, double dx, const double *lin_mat,
+               int64_t max_iter, double Mdiv_sq, double epscv_sq,
+               int calc_d2zndc2, double *Z, int8_t *stop_reason, int32_t *stop_iter,
+               int nthreads)
+{
+    C center = mkC(center_re, center_im);
+    int nt = resolve_threads(nthreads);
+#pragma omp parallel for schedule(dynamic, 64) num_threads(nt)
+    for (int64_t i = 0; i < npts; i++) {
+        C c = c_from_pix(path_c(c_pix, i), lin_mat, dx, center);
+        std_mn_pixel(nexp, use_cpow, c, max_iter, Mdiv_sq, epscv_sq, calc_d2zndc2,
+                     Z + 2 * i, npts, stop_reason + i, stop_iter + i);
     }
     return 0;
 }

@@ -281,3 +281,16 @@ CASES["p_M3_E20_chaotic"] = dict(
     y="0.72918276962050262626535766633048414", dx="3.e-20", nx=48,
     calc=dict(max_iter=20000, BLA_eps=1e-6, interior_detect=True,
               calc_dzndc=True, **_STD))
+
+# ---- Mandelbrot_N, standard loop (models/mandelbrot_Mn.py:20-350) ----
+CASES["std_M3"] = dict(        # z^2 is a product in numba: bit-defined
+    kind="std_M2", init=dict(exponent=3), x=0.0, y=0.0, dx=3.0, nx=64,
+    calc=dict(max_iter=2000, M_divergence=1000., epsilon_stationnary=1e-3))
+CASES["std_M6_d2"] = dict(     # examples/interactive_standard/S03: exponent 6
+    kind="std_M2", init=dict(exponent=6), x=0.0, y=0.0, dx=2.6, nx=64,
+    theta_deg=15.,
+    calc=dict(max_iter=2000, M_divergence=1000., epsilon_stationnary=1e-3,
+              calc_d2zndc2=True))
+CASES["std_M4_zoom"] = dict(
+    kind="std_M2", init=dict(exponent=4), x=-0.6548, y=0.4686, dx=2e-3, nx=64,
+    calc=dict(max_iter=3000, M_divergence=1000., epsilon_stationnary=1e-3))

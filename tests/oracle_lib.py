@@ -119,6 +119,23 @@ def std_m2(c_pix, center, dx, lin_mat, max_iter, M_divergence,
     return Z, np.zeros((0, n), np.int32), sr, si
 
 
+def std_mn(nexp, c_pix, center, dx, lin_mat, max_iter, M_divergence,
+           epsilon_stationnary, calc_d2zndc2=False, use_cpow=True, nthreads=0):
+    """ Mandelbrot_N; use_cpow: see fs_oracle.h """
+    c_pix = _c128(c_pix)
+    n = c_pix.shape[0]
+    Z = np.zeros((3 + int(calc_d2zndc2), n), np.complex128)
+    sr = np.full((1, n), -1, np.int8)
+    si = np.zeros((1, n), np.int32)
+    lm = _f64(lin_mat).ravel()
+    lib().fso_std_mn(int(nexp), int(bool(use_cpow)), c_i64(n), c_vp(_p(c_pix)),
+                     c_dbl(center.real), c_dbl(center.imag), c_dbl(dx), c_vp(_p(lm)),
+                     c_i64(max_iter), c_dbl(M_divergence ** 2),
+                     c_dbl(epsilon_stationnary ** 2), int(calc_d2zndc2), c_vp(_p(Z)),
+                     c_vp(_p(sr)), c_vp(_p(si)), int(nthreads))
+    return Z, np.zeros((0, n), np.int32), sr, si
+
+
 def std_bs(flavor, c_pix, center, dx, lin_mat, max_iter, M_divergence,
            calc_orbit=False, backshift=0, nthreads=0):
     c_pix = _c128(c_pix)

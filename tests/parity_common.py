@@ -38,7 +38,8 @@ def make_fractal(name, workdir=None):
     workdir = workdir or tempfile.mkdtemp(prefix="fsb_")
     cls = _CLS[case["kind"]]
     if "exponent" in case.get("init", {}):
-        cls = fsm.Perturbation_mandelbrot_N
+        cls = (fsm.Perturbation_mandelbrot_N if case["kind"].startswith("perturb")
+               else fsm.Mandelbrot_N)
     f = cls(workdir, **case.get("init", {}))
     from fractalshades_b200 import projection as _proj
     from cases import make_projection
@@ -138,7 +139,12 @@ def run_oracle(name, nthreads=0, det=False):
         c_pix = ol.project(dict(kind=pd.kind, hmoy=pd.hmoy, k_re=pd.pix_to_ht[0],
                                 k_im=pd.pix_to_ht[1]), c_pix0, det)
         center = complex(f.x, f.y)
-        if case["kind"] == "std_M2":
+        if case["kind"] == "std_M2" and "exponent" in case.get("init", {}):
+            # det: product chain (the CUDA definition) instead of the C
+            # library's polar-form power the reference runs
+            Z, U, sr, si = ol.std_mn(f.exponent, c_pix, center, f.dx, f.lin_mat,
+                                     use_cpow=not det, nthreads=nthreads, **case["calc"])
+        elif case["kind"] == "std_M2":
             Z, U, sr, si = ol.std_m2(c_pix, center, f.dx, f.lin_mat,
                                      nthreads=nthreads, **case["calc"])
         else:

@@ -68,7 +68,10 @@ def run_one(name, mode):
         pj = rt2.proj_from_reference(f.projection)
         r["c_pix_raw"] = r["c_pix"]
         r["c_pix"] = ol.project(pj, r["c_pix"], False)
-        if case["kind"] == "std_M2":
+        if case["kind"] == "std_M2" and "exponent" in case.get("init", {}):
+            Z, U, sr, si = ol.std_mn(f.exponent, r["c_pix"], complex(f.x, f.y), f.dx,
+                                     f.lin_mat, **case["calc"])
+        elif case["kind"] == "std_M2":
             Z, U, sr, si = ol.std_m2(r["c_pix"], complex(f.x, f.y), f.dx,
                                      f.lin_mat, **case["calc"])
         else:

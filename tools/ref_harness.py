@@ -190,7 +190,10 @@ def make_fractal(case, workdir):
     from cases import make_projection
     proj = make_projection(fs.projection, case.get("proj"))
     if kind == "std_M2":
-        f = fsm.Mandelbrot(workdir)
+        if "exponent" in case.get("init", {}):
+            f = fsm.Mandelbrot_N(workdir, **case["init"])
+        else:
+            f = fsm.Mandelbrot(workdir)
         f.zoom(x=case["x"], y=case["y"], dx=case["dx"], nx=case["nx"],
                xy_ratio=case.get("xy_ratio", 1.0),
                theta_deg=case.get("theta_deg", 0.), projection=proj,
