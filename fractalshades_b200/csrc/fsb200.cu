@@ -383,6 +383,7 @@ struct fsb_frame {
     bool bla_on = false;
     bool fast_xr = false;     /* Xrange kernel with the guarded fp64 fast path */
     bool gpu_scan = false;    /* dZndc path by the GPU affine scan (K6) */
+    bool gpu_scan_bs = false; /* same for the four Jacobian paths of the burning-ship family */
     std::vector<void *> owned;
     double ms_upload = 0, ms_dzndc = 0, ms_bla = 0;
     long long dzndc_len = 0;
@@ -698,6 +699,73 @@ int gpu_dzndc_m2(fsb_frame *f)
         } else {
             C w = (2. * Zn[i]) * last + to_std(scale);
             CK(cudaMemcpy(dm, &w, sizeof(C), cudaMemcpyHostToDevice));
+        }
+    }
+    return 0;
+}
+
+/* Same for the four Jacobian paths of a burning-ship frame (SURVEY f-2):
+ * k_dzndc_bs_scan_* ; out = [dXnda | dXndb | dYnda | dYndb], L entries each. */
+int gpu_dzndc_bs(fsb_frame *f)
+{
+    const fsb_frame_desc &d = f->d;
+    FrameDev &v = f->dev;
+    const long long L = d.L;
+    const long long valid = L < d.ref_div_iter ? L : d.ref_div_iter;
+    const long long n_elem = valid - 1;
+    double *dm = nullptr;
+    int *de = nullptr;
+    const bool dbg = getenv("FSB200_DEBUG_TIMING") != nullptr;
+    double tq = now_ms();
+    if (dev_zeros(f, 4 * L + 4, &dm)) return -1;
+    if (d.xr_detect && dev_zeros(f, 4 * L + 4, &de)) return -1;
+    if (dbg) { cudaDeviceSynchronize(); fprintf(stderr, "bs scan: zeros %.3f ms\n", now_ms() - tq); tq = now_ms(); }
+    for (int j = 0; j < 4; j++) {
+        v.dP[j] = dm + j * L;
+        v.dP_e[j] = de ? de + j * L : nullptr;
+    }
+    if (n_elem <= 0) return 0;
+    const XF scale = mkXF(d.scale_deriv, d.scale_deriv_e);
+    const long long n_thr = (n_elem + SCAN_E - 1) / SCAN_E;
+    const int n_blk = (int)((n_thr + SCANB_T - 1) / SCANB_T);
+    AffBS *thr_agg = nullptr, *blk_agg = nullptr;
+    CK(cudaMalloc(&thr_agg, (size_t)n_blk * SCANB_T * sizeof(AffBS)));
+    CK(cudaMalloc(&blk_agg, (size_t)n_blk * sizeof(AffBS)));
+    k_dzndc_bs_scan_local<<<n_blk, SCANB_T>>>(v, n_elem, scale, thr_agg, blk_agg);
+    k_dzndc_bs_scan_blocks<<<1, SCANB_T>>>(n_blk, blk_agg);
+    k_dzndc_bs_scan_apply<<<n_blk, SCANB_T>>>(v, n_elem, scale, thr_agg, blk_agg, dm, de, L,
+                                              d.xr_detect ? 1 : 0);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    if (dbg) { fprintf(stderr, "bs scan: kernels %.3f ms\n", now_ms() - tq); tq = now_ms(); }
+    cudaFree(thr_agg);
+    cudaFree(blk_agg);
+    if (dbg) { fprintf(stderr, "bs scan: free %.3f ms\n", now_ms() - tq); tq = now_ms(); }
+    /* periodic reference: the wrapped value goes to index 0 (perturbation.py:2440-2461) */
+    const long long i = valid - 1;
+    if (i == d.ref_order - 1) {
+        double m4[4]; int e4[4] = {0, 0, 0, 0};
+        for (int j = 0; j < 4; j++) {
+            CK(cudaMemcpy(&m4[j], dm + j * L + i, sizeof(double), cudaMemcpyDeviceToHost));
+            if (de) CK(cudaMemcpy(&e4[j], de + j * L + i, sizeof(int), cudaMemcpyDeviceToHost));
+        }
+        const double X = d.Zn_path[2 * i], Y = d.Zn_path[2 * i + 1];
+        long long k = d.n_xr > 0 ? h_xr_find(d.ref_index_xr, d.n_xr, i) : -1;
+        XF rx = (k >= 0) ? mkXF(d.ref_xr[k], d.ref_xr_e[k]) : to_xr(X);
+        XF ry = (k >= 0) ? mkXF(d.refy_xr[k], d.refy_xr_e[k]) : to_xr(Y);
+        XF fxx, fxy, fyx, fyy;
+        h_bs_jac(d.flavor, rx, ry, fxx, fxy, fyx, fyy);
+        XF a = mkXF(m4[0], e4[0]), b = mkXF(m4[1], e4[1]), c = mkXF(m4[2], e4[2]), dd = mkXF(m4[3], e4[3]);
+        XF w[4] = {fxx * a + fxy * c + scale, fxx * b + fxy * dd, fyx * a + fyy * c,
+                   fyx * b + fyy * dd - scale};
+        for (int j = 0; j < 4; j++) {
+            if (de) {
+                CK(cudaMemcpy(dm + j * L, &w[j].m, sizeof(double), cudaMemcpyHostToDevice));
+                CK(cudaMemcpy(de + j * L, &w[j].e, sizeof(int), cudaMemcpyHostToDevice));
+            } else {
+                const double ws = to_std(w[j]);
+                CK(cudaMemcpy(dm + j * L, &ws, sizeof(double), cudaMemcpyHostToDevice));
+            }
         }
     }
     return 0;
@@ -1213,6 +1281,7 @@ int fsb_frame_create(const fsb_frame_desc *desc, fsb_frame **out)
 #else
         const char *host = getenv("FSB200_HOST_DZNDC");
         f->gpu_scan = d.model == FSB_MODEL_M2 && d.nexp == 0 && !(host && host[0] == '1');
+        f->gpu_scan_bs = d.model == FSB_MODEL_BS && !(host && host[0] == '1');
 #endif
     }
     if (d.calc_dzndc) {
@@ -1228,6 +1297,8 @@ int fsb_frame_create(const fsb_frame_desc *desc, fsb_frame **out)
                 UP(upload(f, p.data(), L, &v.dZndc, 1));
                 if (d.xr_detect) UP(upload(f, (const int *)pe.data(), L, &v.dZndc_e, 1));
             }
+        } else if (!d.dZndc && f->gpu_scan_bs) {
+            UP(gpu_dzndc_bs(f));
         } else {
             std::vector<double> p; std::vector<int32_t> pe;
             const double *src = d.dZndc; const int32_t *srce = d.dZndc_e;

@@ -691,7 +691,10 @@ __device__ __forceinline__ C to_std_small(XC x)
  * out of the common variants. */
 template <bool XR, bool DZNDC, bool DZNDZ, bool BLA, bool EXTRA, bool FASTXR = false,
           bool POWN = false /* Perturbation_mandelbrot_N: binomial forms, exponent f.nexp */>
-__global__ void __launch_bounds__(128)
+#ifndef FSB_M2XR_MINB
+#define FSB_M2XR_MINB 1
+#endif
+__global__ void __launch_bounds__(128, ((XR && FASTXR) ? FSB_M2XR_MINB : 1))
 k_perturb_m2(const __grid_constant__ FrameDev f, long long npts_ll,
              const C *__restrict__ c_pix, double *__restrict__ Z,
              int *__restrict__ U, signed char *__restrict__ stop_reason,
@@ -1277,7 +1280,10 @@ __device__ __forceinline__ void apply_bla_deriv_bs_xr(const double *M, XF &dxa, 
  * Xrange + hessian kernel was 18 000 instructions and spent two thirds of its
  * time waiting on instruction fetch); 0 = read it from the frame. */
 template <bool XR, bool HESS, bool BLA, bool FASTXR = false, int FLAVOR = 0>
-__global__ void __launch_bounds__(128, (XR ? 8 : 1))   /* Xrange: latency-bound, 32 warps/SM pay for the spills */
+#ifndef FSB_BS_MINB
+#define FSB_BS_MINB 8
+#endif
+__global__ void __launch_bounds__(128, (XR ? FSB_BS_MINB : 1))   /* Xrange: latency-bound, 32 warps/SM pay for the spills */
 k_perturb_bs(const __grid_constant__ FrameDev f, long long npts_ll,
              const C *__restrict__ c_pix, double *__restrict__ Z,
              int *__restrict__ U, signed char *__restrict__ stop_reason,
@@ -1943,6 +1949,152 @@ k_dzndc_scan_apply(FrameDev f, long long n_elem, XF scale, const AffXC *__restri
         d = scan_coef(f, j) * d + s;      /* d[j + 1] */
         if (write_e) { out_m[j + 1] = d.m; out_e[j + 1] = d.e; }
         if (out_std) out_std[j + 1] = to_std(d);
+    }
+}
+
+/* ---- the same scan for the burning-ship family --------------------------------
+ * J[n+1] = F(Z_n) J[n] + S, J = [[dXnda, dXndb], [dYnda, dYndb]], F the 2x2
+ * Jacobian of the flavour, S = diag(scale, -scale) (perturbation.py:2339-2463):
+ * an affine map on 2x2 real matrices; composition (F2, S2) o (F1, S1) =
+ * (F2 F1, F2 S1 + S2).  Real Xrange arithmetic throughout. */
+struct AffBS { XF F[4], S[4]; };
+__device__ __forceinline__ void mat2_mul(const XF *a, const XF *b, XF *o)
+{
+    o[0] = a[0] * b[0] + a[1] * b[2];
+    o[1] = a[0] * b[1] + a[1] * b[3];
+    o[2] = a[2] * b[0] + a[3] * b[2];
+    o[3] = a[2] * b[1] + a[3] * b[3];
+}
+__device__ __forceinline__ AffBS affbs_identity()
+{
+    AffBS o;
+    o.F[0] = mkXF(1., 0); o.F[1] = mkXF(0., 0); o.F[2] = mkXF(0., 0); o.F[3] = mkXF(1., 0);
+    for (int k = 0; k < 4; k++) o.S[k] = mkXF(0., 0);
+    return o;
+}
+__device__ __forceinline__ AffBS affbs_compose(const AffBS &first, const AffBS &then)
+{
+    AffBS o;
+    XF t[4];
+    mat2_mul(then.F, first.F, o.F);
+    mat2_mul(then.F, first.S, t);
+    for (int k = 0; k < 4; k++) o.S[k] = t[k] + then.S[k];
+    return o;
+}
+/* burning_ship.py:441-532 for Xrange operands */
+__device__ __forceinline__ void bs_jac_xf(int flavor, XF x, XF y, XF *F)
+{
+    switch (flavor) {
+    case 1: F[0] = 2. * x; F[1] = -2. * y; F[2] = (2. * sgn_(x)) * fabs_(y); F[3] = (2. * sgn_(y)) * fabs_(x); break;
+    case 2: F[0] = 2. * x; F[1] = -2. * y; F[2] = 2. * fabs_(y); F[3] = (2. * sgn_(y)) * x; break;
+    case 3: F[0] = 2. * x; F[1] = -2. * fabs_(y); F[2] = 2. * y; F[3] = 2. * x; break;
+    case 4: { const double sg = sgn_(x * x - y * y); F[0] = (2. * sg) * x; F[1] = (-2. * sg) * y; F[2] = 2. * y; F[3] = 2. * x; break; }
+    default: { const double sg = sgn_(x * x - y * y); F[0] = (2. * sg) * x; F[1] = (-2. * sg) * y;
+               F[2] = (2. * sgn_(x)) * fabs_(y); F[3] = (2. * sgn_(y)) * fabs_(x); break; }
+    }
+}
+__device__ __forceinline__ void scan_coef_bs(const FrameDev &f, long long j, XF *F)
+{
+    const C z = ldC(f.Zn, j);
+    int k = -1;
+    if (f.n_xr_i > 0) k = xr_find(f.ref_index_xr, f.n_xr_i, (int)j);
+    const XF rx = (k >= 0) ? mkXF(__ldg(f.refx_xr + k), __ldg(f.refx_xr_e + k)) : to_xr(z.re);
+    const XF ry = (k >= 0) ? mkXF(__ldg(f.refy_xr + k), __ldg(f.refy_xr_e + k)) : to_xr(z.im);
+    bs_jac_xf(f.flavor, rx, ry, F);
+}
+__device__ __forceinline__ AffBS scan_elem_bs(const FrameDev &f, long long j, XF scale)
+{
+    AffBS m;
+    scan_coef_bs(f, j, m.F);
+    m.S[0] = scale; m.S[1] = mkXF(0., 0); m.S[2] = mkXF(0., 0); m.S[3] = -scale;
+    return m;
+}
+
+constexpr int SCANB_T = 128;
+
+__global__ void __launch_bounds__(SCANB_T)
+k_dzndc_bs_scan_local(FrameDev f, long long n_elem, XF scale, AffBS *__restrict__ thr_agg,
+                      AffBS *__restrict__ blk_agg)
+{
+    __shared__ AffBS sh[SCANB_T];
+    const long long t = blockIdx.x * (long long)SCANB_T + threadIdx.x;
+    const long long j0 = t * SCAN_E;
+    AffBS acc = affbs_identity();
+    for (int q = 0; q < SCAN_E; q++) {
+        const long long j = j0 + q;
+        if (j < n_elem) acc = affbs_compose(acc, scan_elem_bs(f, j, scale));
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int off = 1; off < SCANB_T; off <<= 1) {
+        AffBS prev = acc;
+        const bool has = threadIdx.x >= off;
+        if (has) prev = sh[threadIdx.x - off];
+        __syncthreads();
+        if (has) { acc = affbs_compose(prev, acc); sh[threadIdx.x] = acc; }
+        __syncthreads();
+    }
+    thr_agg[t] = acc;
+    if (threadIdx.x == SCANB_T - 1) blk_agg[blockIdx.x] = acc;
+}
+
+__global__ void __launch_bounds__(SCANB_T)
+k_dzndc_bs_scan_blocks(int n_blk, AffBS *__restrict__ blk_agg)
+{
+    __shared__ AffBS sh[SCANB_T];
+    const int per = (n_blk + SCANB_T - 1) / SCANB_T;
+    const int b0 = threadIdx.x * per;
+    AffBS acc = affbs_identity();
+    for (int q = 0; q < per; q++)
+        if (b0 + q < n_blk) acc = affbs_compose(acc, blk_agg[b0 + q]);
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int off = 1; off < SCANB_T; off <<= 1) {
+        AffBS prev = acc;
+        const bool has = threadIdx.x >= off;
+        if (has) prev = sh[threadIdx.x - off];
+        __syncthreads();
+        if (has) { acc = affbs_compose(prev, acc); sh[threadIdx.x] = acc; }
+        __syncthreads();
+    }
+    AffBS ex = affbs_identity();
+    if (threadIdx.x > 0) ex = sh[threadIdx.x - 1];
+    for (int q = 0; q < per; q++) {
+        if (b0 + q < n_blk) {
+            const AffBS own = blk_agg[b0 + q];
+            blk_agg[b0 + q] = ex;
+            ex = affbs_compose(ex, own);
+        }
+    }
+}
+
+/* out_m / out_e: four planes of `plane` entries each (dXnda | dXndb | dYnda | dYndb) */
+__global__ void __launch_bounds__(SCANB_T)
+k_dzndc_bs_scan_apply(FrameDev f, long long n_elem, XF scale, const AffBS *__restrict__ thr_agg,
+                      const AffBS *__restrict__ blk_ex, double *__restrict__ out_m,
+                      int *__restrict__ out_e, long long plane, int xr)
+{
+    const long long t = blockIdx.x * (long long)SCANB_T + threadIdx.x;
+    const long long j0 = t * SCAN_E;
+    if (j0 >= n_elem) return;
+    AffBS pre = blk_ex[blockIdx.x];
+    if (threadIdx.x > 0) pre = affbs_compose(pre, thr_agg[t - 1]);
+    XF a = pre.S[0], b = pre.S[1], c = pre.S[2], d = pre.S[3];      /* J[j0] */
+    for (int q = 0; q < SCAN_E; q++) {
+        const long long j = j0 + q;
+        if (j >= n_elem) break;
+        XF F[4];
+        scan_coef_bs(f, j, F);
+        const XF na = F[0] * a + F[1] * c + scale;
+        const XF nb = F[0] * b + F[1] * d;
+        const XF nc = F[2] * a + F[3] * c;
+        const XF nd = F[2] * b + F[3] * d - scale;
+        a = na; b = nb; c = nc; d = nd;
+        const XF v[4] = {a, b, c, d};
+        for (int k = 0; k < 4; k++) {
+            if (xr) { out_m[k * plane + j + 1] = v[k].m; out_e[k * plane + j + 1] = v[k].e; }
+            else out_m[k * plane + j + 1] = to_std(v[k]);
+        }
     }
 }
 

@@ -307,3 +307,44 @@ def test_gpu_dzndc_scan_matches_serial_path(name, oracle_results):
         assert np.all(np.abs(ae[nz] - be[nz]) <= 1)
         rel = np.abs(a[nz] * scale - b[nz]) / np.abs(b[nz])
         assert rel.max() < 1e-9, rel.max()
+
+
+@pytest.mark.parametrize("name", ["p_BS_f1_E30_skew", "p_BS_f1_E500_xr", "p_BS_f2_E12",
+                                  "p_BS_f3_E12", "p_BS_f4_E12", "p_BS_f5_E12",
+                                  "p_BS_f5_E330_xr", "p_BS_f1_expmap_E30"])
+def test_gpu_dzndc_scan_bs_matches_serial_path(name, oracle_results):
+    """ SURVEY f-2 for the burning-ship family: the four Jacobian paths by a
+    parallel affine scan over 2x2 real Xrange matrices (default build); the
+    oracle runs the serial recurrence of perturbation.py:2339-2463.  Different
+    association order -> agreement to rounding; the frame computed from the
+    scanned tables meets the same floors as with the serial tables. """
+    Zo, Uo, sro, sio, ex = oracle_results(name)
+    t = ex["tables"]
+    Z, U, sr, si, gx = pc.run_gpu_case(name, strict=False, tables=(dict(t), ex["c_pix"]))
+    d, de = gx["dzndc"]
+    ref = np.stack([t[k] for k in ("dXnda", "dXndb", "dYnda", "dYndb")])
+    if de is None:
+        fin = np.isfinite(ref) & np.isfinite(d) & (np.abs(ref) > 1e-290)
+        assert fin.sum() > 10
+        rel = np.abs(d[fin] - ref[fin]) / np.abs(ref[fin])
+        # entries that cancelled to far below their neighbours carry the
+        # rounding of the larger terms: bound the bulk tightly, the tail loosely
+        assert np.quantile(rel, 0.999) < 1e-9, np.quantile(rel, 0.999)
+        assert rel.max() < 1e-6, rel.max()
+        assert np.array_equal(ref == 0, d == 0)
+    else:
+        ref_e = np.stack([t[k + "_e"] for k in ("dXnda", "dXndb", "dYnda", "dYndb")])
+        # compare values: log2|value| and the normalised mantissas
+        ma, ea = np.frexp(d.ravel())
+        mb, eb = np.frexp(ref.ravel())
+        ea = ea + de.ravel()
+        eb = eb + ref_e.ravel()
+        nz = mb != 0
+        assert np.array_equal(ma == 0, mb == 0)
+        assert np.all(np.abs(ea[nz] - eb[nz]) <= 1)
+        rel = np.abs(ma[nz] * np.exp2((ea[nz] - eb[nz]).astype(float)) - mb[nz]) / np.abs(mb[nz])
+        # entries that cancelled to far below their neighbours carry the
+        # rounding of the larger terms
+        assert np.quantile(rel, 0.999) < 1e-9, np.quantile(rel, 0.999)
+    same = (si == sio)[0] & (sr == sro)[0]
+    assert same.mean() >= FAST_FLOOR[name], same.mean()
