@@ -15,7 +15,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <map>
 #include <mutex>
+#include <unordered_map>
 #include <string>
 #include <thread>
 #include <vector>
@@ -54,6 +56,88 @@ int ensure_init()
 {
     if (g_device >= 0) return 0;
     return fsb_init(0);
+}
+
+/* ---- device-memory pool ---------------------------------------------------
+ * Per-frame tables (orbit, derivative paths, BLA tree: 0.1 - 0.5 GB) are
+ * created and destroyed once per frame; cudaMalloc / cudaFree of blocks that
+ * size cost ~10 ms each (map / unmap), 0.23 s per frame of a zoom movie.  Freed
+ * blocks are kept, keyed by size, and handed to the next frame (whose tables
+ * have the same sizes); FSB200_POOL_MB bounds the cached bytes (default 16 GB
+ * of the 180 GB of HBM), fsb_shutdown releases them. */
+struct Pool {
+    std::mutex mu;
+    std::multimap<size_t, void *> free_blocks;
+    std::unordered_map<void *, size_t> live;
+    size_t cached = 0;
+    size_t cap()
+    {
+        static size_t c = [] {
+            const char *e = getenv("FSB200_POOL_MB");
+            return (size_t)(e ? atoll(e) : 16384) << 20;
+        }();
+        return c;
+    }
+};
+Pool g_pool;
+size_t pool_round(size_t b)
+{
+    if (b < 1) b = 1;
+    const size_t g = (b < (1u << 20)) ? 512 : (2u << 20);
+    return (b + g - 1) / g * g;
+}
+void pool_trim()
+{
+    std::lock_guard<std::mutex> lock(g_pool.mu);
+    for (auto &kv : g_pool.free_blocks) cudaFree(kv.second);
+    g_pool.free_blocks.clear();
+    g_pool.cached = 0;
+}
+cudaError_t pool_alloc(void **p, size_t bytes)
+{
+    bytes = pool_round(bytes);
+    {
+        std::lock_guard<std::mutex> lock(g_pool.mu);
+        auto it = g_pool.free_blocks.lower_bound(bytes);
+        if (it != g_pool.free_blocks.end() && it->first <= bytes + bytes / 4) {
+            *p = it->second;
+            g_pool.live[*p] = it->first;
+            g_pool.cached -= it->first;
+            g_pool.free_blocks.erase(it);
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) {            /* give the cached blocks back and retry */
+        cudaGetLastError();
+        pool_trim();
+        e = cudaMalloc(p, bytes);
+    }
+    if (e == cudaSuccess) {
+        std::lock_guard<std::mutex> lock(g_pool.mu);
+        g_pool.live[*p] = bytes;
+    }
+    return e;
+}
+template <class T> cudaError_t pool_alloc(T **p, size_t bytes) { return pool_alloc((void **)p, bytes); }
+void pool_free(void *p)
+{
+    if (!p) return;
+    size_t bytes = 0;
+    {
+        std::lock_guard<std::mutex> lock(g_pool.mu);
+        auto it = g_pool.live.find(p);
+        if (it != g_pool.live.end()) {
+            bytes = it->second;
+            g_pool.live.erase(it);
+            if (g_pool.cached + bytes <= g_pool.cap()) {
+                g_pool.free_blocks.emplace(bytes, p);
+                g_pool.cached += bytes;
+                return;
+            }
+        }
+    }
+    cudaFree(p);
 }
 
 /* Per host-thread launch context. */
@@ -402,7 +486,7 @@ template <class T> int upload(fsb_frame *f, const T *host, long long n, const T 
     *dev = nullptr;
     if (!host || n <= 0) return 0;
     void *p = nullptr;
-    CK(cudaMalloc(&p, (size_t)((n + pad) * (long long)sizeof(T))));
+    CK(pool_alloc(&p, (size_t)((n + pad) * (long long)sizeof(T))));
     f->owned.push_back(p);
     CK(cudaMemcpy(p, host, (size_t)(n * (long long)sizeof(T)), cudaMemcpyHostToDevice));
     if (pad > 0)
@@ -606,9 +690,9 @@ int build_bla(fsb_frame *f)
     double kc_std = to_std(mkXF(d.kc, d.kc_e));
     int width = (d.model == FSB_MODEL_M2) ? 4 : 8; /* doubles per node */
     void *dM = nullptr, *dr = nullptr;
-    CK(cudaMalloc(&dM, (size_t)(bla_len * width * 8)));
+    CK(pool_alloc(&dM, (size_t)(bla_len * width * 8)));
     f->owned.push_back(dM);
-    CK(cudaMalloc(&dr, (size_t)(bla_len * 8)));
+    CK(pool_alloc(&dr, (size_t)(bla_len * 8)));
     f->owned.push_back(dr);
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
@@ -646,7 +730,7 @@ int build_bla(fsb_frame *f)
 template <class T> int dev_zeros(fsb_frame *f, long long n, T **dev)
 {
     void *p = nullptr;
-    CK(cudaMalloc(&p, (size_t)(n * (long long)sizeof(T))));
+    CK(pool_alloc(&p, (size_t)(n * (long long)sizeof(T))));
     f->owned.push_back(p);
     CK(cudaMemset(p, 0, (size_t)(n * (long long)sizeof(T))));
     *dev = (T *)p;
@@ -674,16 +758,16 @@ int gpu_dzndc_m2(fsb_frame *f)
     const long long n_thr = (n_elem + SCAN_E - 1) / SCAN_E;
     const int n_blk = (int)((n_thr + SCAN_T - 1) / SCAN_T);
     AffXC *thr_agg = nullptr, *blk_agg = nullptr;
-    CK(cudaMalloc(&thr_agg, (size_t)n_blk * SCAN_T * sizeof(AffXC)));
-    CK(cudaMalloc(&blk_agg, (size_t)n_blk * sizeof(AffXC)));
+    CK(pool_alloc(&thr_agg, (size_t)n_blk * SCAN_T * sizeof(AffXC)));
+    CK(pool_alloc(&blk_agg, (size_t)n_blk * sizeof(AffXC)));
     k_dzndc_scan_local<<<n_blk, SCAN_T>>>(v, n_elem, scale, thr_agg, blk_agg);
     k_dzndc_scan_blocks<<<1, 1024>>>(n_blk, blk_agg);
     k_dzndc_scan_apply<<<n_blk, SCAN_T>>>(v, n_elem, scale, thr_agg, blk_agg, dm, de,
                                           d.xr_detect ? nullptr : dm, d.xr_detect ? 1 : 0);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
-    cudaFree(thr_agg);
-    cudaFree(blk_agg);
+    pool_free(thr_agg);
+    pool_free(blk_agg);
     /* periodic reference: the wrapped value is stored at index 0
      * (perturbation.py:2315-2334) */
     const long long i = valid - 1;
@@ -729,8 +813,8 @@ int gpu_dzndc_bs(fsb_frame *f)
     const long long n_thr = (n_elem + SCAN_E - 1) / SCAN_E;
     const int n_blk = (int)((n_thr + SCANB_T - 1) / SCANB_T);
     AffBS *thr_agg = nullptr, *blk_agg = nullptr;
-    CK(cudaMalloc(&thr_agg, (size_t)n_blk * SCANB_T * sizeof(AffBS)));
-    CK(cudaMalloc(&blk_agg, (size_t)n_blk * sizeof(AffBS)));
+    CK(pool_alloc(&thr_agg, (size_t)n_blk * SCANB_T * sizeof(AffBS)));
+    CK(pool_alloc(&blk_agg, (size_t)n_blk * sizeof(AffBS)));
     k_dzndc_bs_scan_local<<<n_blk, SCANB_T>>>(v, n_elem, scale, thr_agg, blk_agg);
     k_dzndc_bs_scan_blocks<<<1, SCANB_T>>>(n_blk, blk_agg);
     k_dzndc_bs_scan_apply<<<n_blk, SCANB_T>>>(v, n_elem, scale, thr_agg, blk_agg, dm, de, L,
@@ -738,8 +822,8 @@ int gpu_dzndc_bs(fsb_frame *f)
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
     if (dbg) { fprintf(stderr, "bs scan: kernels %.3f ms\n", now_ms() - tq); tq = now_ms(); }
-    cudaFree(thr_agg);
-    cudaFree(blk_agg);
+    pool_free(thr_agg);
+    pool_free(blk_agg);
     if (dbg) { fprintf(stderr, "bs scan: free %.3f ms\n", now_ms() - tq); tq = now_ms(); }
     /* periodic reference: the wrapped value goes to index 0 (perturbation.py:2440-2461) */
     const long long i = valid - 1;
@@ -842,6 +926,7 @@ void fsb_shutdown(void)
 {
     std::lock_guard<std::mutex> lock(g_mutex);
     if (g_flush_buf) { cudaFree(g_flush_buf); g_flush_buf = nullptr; }
+    pool_trim();
     if (t_ctx) { delete t_ctx; t_ctx = nullptr; }
     g_device = -1;
 }
@@ -1369,7 +1454,7 @@ int fsb_frame_create(const fsb_frame_desc *desc, fsb_frame **out)
 int fsb_frame_destroy(fsb_frame *f)
 {
     if (!f) return 0;
-    for (void *p : f->owned) cudaFree(p);
+    for (void *p : f->owned) pool_free(p);
     delete f;
     return 0;
 }
