@@ -276,3 +276,23 @@ def test_fingerprint_file_is_written_atomically(tmp_path):
     assert not errors, errors[:1]
     assert [p for p in os.listdir(os.path.dirname(f.fingerprint_path("c")))
             if p.endswith(".tmp")] == []
+
+
+def test_pixel_grid_with_jitter_and_supersampling_matches_reference():
+    """ chunk_pixel_pos (core.py:1767-1830) incl. the per-tile re-seeded jitter
+    (default_rng(0)) and the supersampled grid: bit-identical to the live
+    reference (fixture: tools/gen_golden_grid.py) """
+    import hashlib
+    import json
+    g = np.load(os.path.join(REPO, "tests", "golden", "pixel_grid.npz"))
+    for k, m in enumerate(json.loads(str(g["meta"]))):
+        f = fsm.Mandelbrot(tempfile.mkdtemp())
+        f.zoom(x=-0.5, y=0.1, dx=2.5, nx=m["nx"], xy_ratio=m["xy_ratio"], theta_deg=0.)
+        shas, samples = [], []
+        for cs in f.chunk_slices():
+            p = np.ascontiguousarray(f.chunk_pixel_pos(cs, m["jitter"], m["supersampling"]))
+            shas.append(hashlib.sha256(p.tobytes()).hexdigest())
+            flat = p.ravel()
+            samples.append(flat[np.linspace(0, flat.size - 1, 16).astype(np.int64)])
+        assert np.array_equal(np.concatenate(samples), g[f"samples_{k}"]), m
+        assert shas == m["sha"], m
