@@ -742,7 +742,9 @@ k_perturb_m2(const __grid_constant__ FrameDev f, long long npts_ll,
         XC zn_x = to_xr(zn), dzndc_x = zn_x, dzndz_x = zn_x;
 
         int w_iter = 0, n_iter = 0;
-        unsigned int p_exec = 0, p_bla = 0, p_reb = 0, p_fast = 0;
+        /* executed iterations = n_iter - (iterations skipped by BLA steps); fast-lane
+         * iterations = executed - exact ones: nothing is counted per iteration */
+        unsigned int p_skip = 0, p_bla = 0, p_reb = 0, p_slow = 0;
         int div_shift = 0, orbit_i1 = 0, orbit_i2 = 0;
         C orbit_zn1 = zn, orbit_zn2 = zn;
         C ref_cur = Zn0;                      /* always Zn[w_iter] */
@@ -764,6 +766,7 @@ k_perturb_m2(const __grid_constant__ FrameDev f, long long npts_ll,
                     const C *M = reinterpret_cast<const C *>(f.M_bla);
                     const C A = ldC(M, 2 * ib), B = ldC(M, 2 * ib + 1);
                     n_iter += step;
+                    p_skip += (unsigned)step;
                     w_iter += step;
                     if (cyc) w_iter = w_iter % order;
                     ref_cur = ldC(Zn, w_iter);
@@ -821,7 +824,6 @@ k_perturb_m2(const __grid_constant__ FrameDev f, long long npts_ll,
 
             /* ---- full perturbation iteration, :1158-1209 ---- */
             n_iter += 1;
-            p_exec++;
             const C ref_zn = ref_cur;
             XC ref_zn_x = record_zero;
             bool done_fast = false;
@@ -837,7 +839,6 @@ k_perturb_m2(const __grid_constant__ FrameDev f, long long npts_ll,
                     zn = nzn;
                     if (DZNDC) dzndc = ndz;
                     done_fast = true;
-                    p_fast++;
                 } else {          /* redo this iteration in Xrange arithmetic */
                     zn_x = to_xr(zn);
                     if (DZNDC) dzndc_x = to_xr(dzndc);
@@ -845,6 +846,7 @@ k_perturb_m2(const __grid_constant__ FrameDev f, long long npts_ll,
                 }
             }
             if (XR && !done_fast) {
+                if (FASTXR) p_slow++;
                 int k = -1;
                 if (has_xr && w_iter != 0 && fabs(ref_zn.re) < 1.e-300 && fabs(ref_zn.im) < 1.e-300)
                     k = xr_find(f.ref_index_xr, f.n_xr_i, w_iter);
@@ -924,13 +926,15 @@ k_perturb_m2(const __grid_constant__ FrameDev f, long long npts_ll,
             /* ---- rebase: reference diverging (:1283-1313) or dynamic glitch
              * (:1317-1372).  Both do z <- ZZ, deriv += path[w_iter], w <- 0;
              * only the dynamic test assigns bool_dyn_rebase (sticky flag). ---- */
-            bool rebase = (w_iter >= ref_div_iter - 1);
-            bool do_rebase = rebase;
+            const bool rebase = (w_iter >= ref_div_iter - 1);
+            if (!rebase) {
+                bool_dyn_rebase = (fabs(ZZ.re) <= fabs(zn.re)) && (fabs(ZZ.im) <= fabs(zn.im));
+                if (!bool_dyn_rebase) continue;          /* the common case */
+            }
+            bool do_rebase = true;
             XC ZZ_xr = record_zero;
             bool fast_rebase = false;
             if (!rebase) {
-                bool_dyn_rebase = (fabs(ZZ.re) <= fabs(zn.re)) && (fabs(ZZ.im) <= fabs(zn.im));
-                do_rebase = bool_dyn_rebase;
                 if (XR && bool_dyn_rebase) {
 
                     if (FASTXR && fast && in_fast_range(ZZ)) {
@@ -1027,7 +1031,9 @@ k_perturb_m2(const __grid_constant__ FrameDev f, long long npts_ll,
         stop_reason[ipt] = (signed char)stop;
         stop_iter[ipt] = n_iter;
         n_sum += (unsigned long long)n_iter;
-        n_exec += p_exec; n_bla += p_bla; n_reb += p_reb; n_fast += p_fast;
+        const unsigned int p_exec = (unsigned)n_iter - p_skip;
+        n_exec += p_exec; n_bla += p_bla; n_reb += p_reb;
+        if (XR && FASTXR) n_fast += p_exec - p_slow;
     }
 #undef DZNDC_X
 #undef DZNDZ_X
@@ -1338,7 +1344,7 @@ k_perturb_bs(const __grid_constant__ FrameDev f, long long npts_ll,
         XF x_x = to_xr(0.), y_x = x_x, dxa_x = x_x, dxb_x = x_x, dya_x = x_x, dyb_x = x_x;
 
         int w_iter = 0, n_iter = 0;
-        unsigned int p_exec = 0, p_bla = 0, p_reb = 0, p_fast = 0;
+        unsigned int p_skip = 0, p_bla = 0, p_reb = 0, p_slow = 0;   /* as in k_perturb_m2 */
         int div_shift = 0, orbit_i1 = 0, orbit_i2 = 0;
         double oxn1 = 0., oxn2 = 0., oyn1 = 0., oyn2 = 0.;
         C ref_cur = Zn0;                     /* always Zn[w_iter] */
@@ -1360,6 +1366,7 @@ k_perturb_bs(const __grid_constant__ FrameDev f, long long npts_ll,
                         M[2 * q] = v.x; M[2 * q + 1] = v.y;
                     }
                     n_iter += step;
+                    p_skip += (unsigned)step;
                     w_iter += step;
                     if (cyc) w_iter = w_iter % order;
                     ref_cur = ldC(Zn, w_iter);
@@ -1407,7 +1414,6 @@ k_perturb_bs(const __grid_constant__ FrameDev f, long long npts_ll,
             }
 
             n_iter += 1;
-            p_exec++;
             const C ref_zn = ref_cur;
             int k = -1;
             if (XR && has_xr && w_iter != 0 && (fabs(ref_zn.re) < 1.e-300 || fabs(ref_zn.im) < 1.e-300))
@@ -1433,7 +1439,6 @@ k_perturb_bs(const __grid_constant__ FrameDev f, long long npts_ll,
                     x = nx; y = ny;
                     if (HESS) { dxa = ndxa; dxb = ndxb; dya = ndya; dyb = ndyb; }
                     done_fast = true;
-                    p_fast++;
                 } else {
                     TO_XR6();
                     fast = false;
@@ -1444,6 +1449,7 @@ k_perturb_bs(const __grid_constant__ FrameDev f, long long npts_ll,
             }
 
             if (!done_fast) {
+                if (XR && FASTXR) p_slow++;
                 XF rx_x = record_zero, ry_x = record_zero;
                 if (XR) {
                     if (k >= 0) {
@@ -1652,7 +1658,9 @@ k_perturb_bs(const __grid_constant__ FrameDev f, long long npts_ll,
         stop_reason[ipt] = (signed char)stop;
         stop_iter[ipt] = n_iter;
         n_sum += (unsigned long long)n_iter;
-        n_exec += p_exec; n_bla += p_bla; n_reb += p_reb; n_fast += p_fast;
+        const unsigned int p_exec = (unsigned)n_iter - p_skip;
+        n_exec += p_exec; n_bla += p_bla; n_reb += p_reb;
+        if (XR && FASTXR) n_fast += p_exec - p_slow;
     }
 #undef D_X
 #undef D_S
