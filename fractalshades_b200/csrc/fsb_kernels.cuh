@@ -691,10 +691,16 @@ __device__ __forceinline__ C to_std_small(XC x)
  * out of the common variants. */
 template <bool XR, bool DZNDC, bool DZNDZ, bool BLA, bool EXTRA, bool FASTXR = false,
           bool POWN = false /* Perturbation_mandelbrot_N: binomial forms, exponent f.nexp */>
-#ifndef FSB_M2XR_MINB
-#define FSB_M2XR_MINB 1
+/* Register caps (CTAs of 128 threads), measured on configs 2 and 3 on one box:
+ *   guarded-fp64 Xrange instance: 86 regs (5 CTAs/SM) 33.6 ms, 80 (6) 30.1, 72 (7) 30.3,
+ *     64 (8) 29.3, 56 (9) 29.0, 48 (10) 30.5 -- latency-bound, the spills are cheap;
+ *   fp64 instances: 48/56 regs 14.4 ms, 58-60 13.6-13.9, 63 (cap 72-88) 13.5.
+ * __launch_bounds__(128, 1) -- naming a minimum of one resident CTA -- made ptxas
+ * take 96 registers for the Xrange instance: 33.6 ms. */
+#ifndef FSB_M2_MAXNREG
+#define FSB_M2_MAXNREG ((XR && FASTXR) ? 56 : (XR ? 128 : 88))
 #endif
-__global__ void __launch_bounds__(128, ((XR && FASTXR) ? FSB_M2XR_MINB : 1))
+__global__ void __maxnreg__(FSB_M2_MAXNREG)
 k_perturb_m2(const __grid_constant__ FrameDev f, long long npts_ll,
              const C *__restrict__ c_pix, double *__restrict__ Z,
              int *__restrict__ U, signed char *__restrict__ stop_reason,
