@@ -1347,6 +1347,7 @@ int fsb_frame_create(const fsb_frame_desc *desc, fsb_frame **out)
         const long long big = (1LL << 30);
         v.Li = (int)L;
         v.ref_div_i = (int)(d.ref_div_iter < big ? d.ref_div_iter : big);
+        v.ref_div_m1_i = v.ref_div_i - 1;
         v.order_i = (d.ref_order < big) ? (int)d.ref_order : 0;
         long long fi = L;
         if (d.ref_div_iter < fi) fi = d.ref_div_iter;

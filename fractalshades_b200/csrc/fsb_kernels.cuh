@@ -65,6 +65,7 @@ struct FrameDev {
      * other kernel): exponent and comb(N, k) as doubles, k = 0..N */
     int nexp;
     const double *cbinom;
+    int ref_div_m1_i;    /* ref_div_i - 1: the rebase test compares against a constant-bank operand */
 };
 
 struct StdDev {
@@ -711,7 +712,7 @@ k_perturb_m2(const __grid_constant__ FrameDev f, long long npts_ll,
     unsigned long long n_exec = 0, n_bla = 0, n_reb = 0, n_sum = 0, n_fast = 0;
     const int L = f.Li;
     const bool has_xr = f.n_xr_i > 0;
-    const int ref_div_iter = f.ref_div_i;
+    const int ref_div_m1 = f.ref_div_m1_i;
     const int max_iter = f.max_iter_i;
     const int first_invalid = f.first_invalid_i;
     const bool cyc = EXTRA && (f.order_i > 0);
@@ -932,7 +933,7 @@ k_perturb_m2(const __grid_constant__ FrameDev f, long long npts_ll,
             /* ---- rebase: reference diverging (:1283-1313) or dynamic glitch
              * (:1317-1372).  Both do z <- ZZ, deriv += path[w_iter], w <- 0;
              * only the dynamic test assigns bool_dyn_rebase (sticky flag). ---- */
-            const bool rebase = (w_iter >= ref_div_iter - 1);
+            const bool rebase = (w_iter >= ref_div_m1);
             if (!rebase) {
                 bool_dyn_rebase = (fabs(ZZ.re) <= fabs(zn.re)) && (fabs(ZZ.im) <= fabs(zn.im));
                 if (!bool_dyn_rebase) continue;          /* the common case */
@@ -1295,7 +1296,11 @@ template <bool XR, bool HESS, bool BLA, bool FASTXR = false, int FLAVOR = 0>
 #ifndef FSB_BS_MINB
 #define FSB_BS_MINB 8
 #endif
+#ifdef FSB_BS_MAXNREG      /* occupancy sweeps with a register cap instead of a CTA count */
+__global__ void __maxnreg__(XR ? FSB_BS_MAXNREG : 128)
+#else
 __global__ void __launch_bounds__(128, (XR ? FSB_BS_MINB : 1))   /* Xrange: latency-bound, 32 warps/SM pay for the spills */
+#endif
 k_perturb_bs(const __grid_constant__ FrameDev f, long long npts_ll,
              const C *__restrict__ c_pix, double *__restrict__ Z,
              int *__restrict__ U, signed char *__restrict__ stop_reason,
@@ -1307,7 +1312,7 @@ k_perturb_bs(const __grid_constant__ FrameDev f, long long npts_ll,
     const int L = f.Li;
     const bool has_xr = f.n_xr_i > 0;
     const int flavor = (FLAVOR > 0) ? FLAVOR : f.flavor;
-    const int ref_div_iter = f.ref_div_i;
+    const int ref_div_m1 = f.ref_div_m1_i;
     const int max_iter = f.max_iter_i;
     const int first_invalid = f.first_invalid_i;
     const bool cyc = f.order_i > 0;
@@ -1520,7 +1525,7 @@ k_perturb_bs(const __grid_constant__ FrameDev f, long long npts_ll,
             if (full_sq_norm > f.Mdiv_sq) { stop = 1; break; }
 
             /* rebase: reference diverging (perturbation.py:1662-1686) */
-            if (w_iter >= ref_div_iter - 1) {
+            if (w_iter >= ref_div_m1) {
                 if (XR && FASTXR && fast) {
                     double na = dxa, nb = dxb, nc = dya, nd = dyb;
                     if (HESS) { na += D_F(0, w_iter); nb += D_F(1, w_iter); nc += D_F(2, w_iter); nd += D_F(3, w_iter); }
