@@ -537,12 +537,24 @@ __device__ __forceinline__ int ref_bla_get(const double *__restrict__ r_bla,
     }
     const int top = 31 - __clz(invalid_step - 1);   /* largest stg with 2^stg < invalid_step */
     if (stages > top) stages = top;
+#ifdef FSB_BLA_BSEARCH
+    /* the same monotonicity makes "|z| < r(stage)" true up to one stage and false
+     * above it: bisect instead of walking down from the top (stage 3 passed) */
+    int lo = 3, hi = stages;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (az < __ldg(r_bla + base + (1 << (mid - 3)))) lo = mid; else hi = mid - 1;
+    }
+    index_out = base + (1 << (lo - 3));
+    return 1 << lo;
+#else
     for (int stg = stages; stg > 3; stg--) {
         const int ib = base + (1 << (stg - 3));
         if (az < __ldg(r_bla + ib)) { index_out = ib; return 1 << stg; }
     }
     index_out = base + 1;
     return 8;
+#endif
 }
 
 /* ======================================================================== */
@@ -762,6 +774,9 @@ k_perturb_m2(const __grid_constant__ FrameDev f, long long npts_ll,
          * the Xrange copies are stale; otherwise the Xrange copies are the
          * state and zn = to_std(zn_x) as in the reference. */
         bool fast = false;
+        /* Measured and dropped: carrying ZZ = zn + Zn[w_iter] into the next iteration's
+         * derivative formula (the same sum, bit for bit) saves 2 of 31 FP64 instructions
+         * but takes 4 registers (62 -> 66, 7 CTAs/SM): config 2 13.59 -> 13.79 ms. */
 
         for (;;) {
             /* ---- BLA step, perturbation.py:1121-1154 ---- */
