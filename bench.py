@@ -41,6 +41,7 @@ from fractalshades_b200.views import VIEWS  # noqa: E402
 _DJ = VIEWS["deep_julia_2608"]
 _BS = VIEWS["bs_deep_julia_2430"]
 _STD = dict(M_divergence=1e3, epsilon_stationnary=1e-3)
+HEADLINE = "config3"     # BASELINE.json's target: the 1e-1000 4K frame
 
 WORKLOADS = {
     # BASELINE.json configs[0]
@@ -156,6 +157,12 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": float(max(smax)) if smax else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def bench_config(w, f, world):
+    """ `config` of the JSON line: the same keys and values in both arms """
+    return {"workload": w["name"], "npts_per_gpu": int(f.nx) * int(f.ny),
+            "frames_per_step": int(world), "tile": 200}
 
 
 def flops_per_unit(kind, w):
@@ -276,7 +283,8 @@ def run_reference_arm(args, w, rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": w["name"], "sample": sample},
+        "config": bench_config(w, f, args.gpus),
+        "build": "oracle/fs_oracle.cpp (C++/OpenMP port of the reference's numba loops)",
         "cpu_baseline": {"value": val, "unit": "Gpix-iter/s", "cores": cores,
                          "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "Gpix-iter/s", "h2d_bytes_per_step": 0,
@@ -287,42 +295,13 @@ def run_reference_arm(args, w, rank, world):
 
 
 # ---------------------------------------------------------------------------
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
-    ap.add_argument("--nx", type=int, default=None, help="debug: override image width")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--strict", action="store_true", help="use the -fmad=false build")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 0)
-
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    w = WORKLOADS[args.workload]
-
-    if args.impl == "reference":
-        run_reference_arm(args, w, rank, world)
-        return
-
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl")
-
-    import fractalshades_b200 as fsb
-    from fractalshades_b200 import _native, settings
-    settings.strict_ieee = bool(args.strict)
-    os.environ.setdefault("FSB200_DEVICE", str(local_rank))
-    lib = _native.cuda_lib()
-
+def run_workload(args, wname, lib, rank, local_rank, world, dist, with_cpu):
+    """ One workload on this rank's GPU: device-resident timing, end-to-end
+    timing through the seam with host buffers, roofline, optional CPU sample.
+    Returns the record on rank 0, None elsewhere. """
+    from fractalshades_b200 import _native
+    w = WORKLOADS[wname]
+    line = None
     # ---- per-frame setup (reference orbit, dZndc path, BLA tree) ----
     t0 = time.time()
     f = make_fractal(w, args.nx)
@@ -456,7 +435,7 @@ def main():
         traffic, traffic_src = None, None
         try:       # dram bytes of one launch from the committed ncu capture (full 4K frames only)
             with open(os.path.join(REPO, "profiles", "traffic.json")) as fh:
-                tj = json.load(fh).get(args.workload)
+                tj = json.load(fh).get(wname)
             if tj and args.nx is None:
                 traffic, traffic_src = int(tj["bytes"]), tj["source"]
         except Exception:
@@ -479,7 +458,7 @@ def main():
                     "algorithmic_bytes": alg_bytes, "peak_source": peak_src},
         }
         cpu_baseline = None
-        if world == 1 and not args.no_cpu_baseline:
+        if with_cpu:
             fc = make_fractal(w, args.nx)
             s = cpu_sample(w, fc, target_s=args.cpu_seconds)
             cpu_baseline = {
@@ -500,11 +479,10 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": w["name"], "npts_per_gpu": npts,
-                       "frames_per_step": world, "tile": 200,
-                       "l2": "flushed between timed steps (192 MiB write); "
-                             "inputs+outputs 473 MB > L2",
-                       "build": lib.fsb_build_info().decode()},
+            "config": bench_config(w, f, world),
+            "l2": "flushed between timed steps (192 MiB write); the planes of a "
+                  "frame (%d MB) exceed L2" % ((h2d + d2h) // 1000000),
+            "build": lib.fsb_build_info().decode(),
             "s_per_frame": ms_per_step * 1e-3,
             "e2e": {"value": e2e_value, "unit": "Gpix-iter/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -517,10 +495,70 @@ def main():
             "setup": {"total_s": setup_s, **{k + "_ms": v for k, v in setup_ms.items()}},
             "sum_stop_iter_per_frame": sum_iter,
         }
-        print(json.dumps(line), flush=True)
-
     for p in (d_c, d_Z, d_U, d_sr, d_si):
         lib.fsb_dev_free(p)
+    if perturb:
+        frame.close()
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=HEADLINE, choices=sorted(WORKLOADS),
+                    help="the workload of the headline line (BASELINE.json's target: config3)")
+    ap.add_argument("--also", default="config1,config2,config4",
+                    help="comma list of further workloads reported as sub-records under "
+                         "'workloads' (each with its own roofline / e2e / cpu_baseline); "
+                         "'none' to skip")
+    ap.add_argument("--nx", type=int, default=None, help="debug: override image width")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--strict", action="store_true", help="use the -fmad=false build")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    also = [x for x in args.also.split(",") if x and x != "none" and x != args.workload]
+    for x in also:
+        if x not in WORKLOADS:
+            ap.error(f"unknown workload {x}")
+
+    if args.impl == "reference":
+        run_reference_arm(args, WORKLOADS[args.workload], rank, world)
+        return
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl")
+
+    from fractalshades_b200 import _native, settings
+    settings.strict_ieee = bool(args.strict)
+    os.environ.setdefault("FSB200_DEVICE", str(local_rank))
+    lib = _native.cuda_lib()
+
+    with_cpu = (world == 1 and not args.no_cpu_baseline)
+    line = run_workload(args, args.workload, lib, rank, local_rank, world, dist, with_cpu)
+    subs = {}
+    for x in also:
+        rec = run_workload(args, x, lib, rank, local_rank, world, dist, with_cpu)
+        if rec is not None:
+            for k in ("n_gpus", "steps", "warmup", "higher_is_better", "vs_baseline",
+                      "data", "metric", "unit"):
+                rec.pop(k, None)
+            subs[x] = rec
+    if rank == 0:
+        if subs:
+            line["workloads"] = subs
+        print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
