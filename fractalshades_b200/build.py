@@ -41,7 +41,7 @@ def _run(cmd):
 
 def cuda_sources():
     return [os.path.join(CSRC, f) for f in
-            ("fsb200.cu", "fsb_kernels.cuh", "fsb_math.cuh")] + [
+            ("fsb200.cu", "fsb_kernels.cuh", "fsb_lane.cuh", "fsb_math.cuh")] + [
             os.path.join(INCLUDE, "fsb200.h")]
 
 

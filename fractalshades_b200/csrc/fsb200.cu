@@ -407,8 +407,17 @@ template <bool XR> perturb_kernel_t pick_m2_dc(bool dc, bool dz, bool bla, bool 
 {
     return dc ? pick_m2_dz<XR, true>(dz, bla, extra, fastxr) : pick_m2_dz<XR, false>(dz, bla, extra, fastxr);
 }
-perturb_kernel_t pick_m2(bool xr, bool dc, bool dz, bool bla, bool extra, bool fastxr)
+/* event-driven kernel (k_perturb_m2_v2): the common variants -- no interior
+ * detection, no periodic reference / calc_orbit, power 2; Xrange frames with
+ * the guarded fp64 lane */
+template <bool XR> perturb_kernel_t pick_m2_v2(bool dc, bool bla)
 {
+    if (dc) return bla ? k_perturb_m2_v2<XR, true, true> : k_perturb_m2_v2<XR, true, false>;
+    return bla ? k_perturb_m2_v2<XR, false, true> : k_perturb_m2_v2<XR, false, false>;
+}
+perturb_kernel_t pick_m2(bool xr, bool dc, bool dz, bool bla, bool extra, bool fastxr, bool v2)
+{
+    if (v2) return xr ? pick_m2_v2<true>(dc, bla) : pick_m2_v2<false>(dc, bla);
     return xr ? pick_m2_dc<true>(dc, dz, bla, extra, fastxr) : pick_m2_dc<false>(dc, dz, bla, extra, fastxr);
 }
 /* Perturbation_mandelbrot_N: the same loop with the binomial model formulas
@@ -466,6 +475,7 @@ struct fsb_frame {
     int nz = 0;
     bool bla_on = false;
     bool fast_xr = false;     /* Xrange kernel with the guarded fp64 fast path */
+    bool v2 = false;          /* event-driven kernel k_perturb_m2_v2 (interleaved orbit table) */
     bool gpu_scan = false;    /* dZndc path by the GPU affine scan (K6) */
     bool gpu_scan_bs = false; /* same for the four Jacobian paths of the burning-ship family */
     std::vector<void *> owned;
@@ -1442,6 +1452,33 @@ int fsb_frame_create(const fsb_frame_desc *desc, fsb_frame **out)
         }
         if (v.stages_bla <= 3 || v.bla_len == 0) f->bla_on = false;
     }
+    /* event-driven kernel: interleaved orbit table */
+    {
+        const char *old = getenv("FSB200_KERNEL_V1");
+        f->v2 = d.model == FSB_MODEL_M2 && d.nexp == 0 && !d.calc_dzndz && !d.calc_orbit
+                && v.order_i == 0 && (!d.xr_detect || f->fast_xr) && !(old && old[0] == '1');
+    }
+    if (f->v2) {
+        const long long n_rec = L + 16;
+        double4 *t2 = nullptr;
+        void *p = nullptr;
+        if (pool_alloc(&p, (size_t)(n_rec * 64)) != cudaSuccess) {
+            fsb_frame_destroy(f);
+            return fail(-1, "out of device memory for the orbit table (%lld records)", n_rec);
+        }
+        f->owned.push_back(p);
+        t2 = (double4 *)p;
+        const C *dsrc = d.calc_dzndc ? (d.xr_detect ? v.dZndc_std : v.dZndc) : nullptr;
+        k_build_t2<<<(int)((n_rec + 255) / 256), 256>>>(
+            n_rec, v.Zn, L + 1, dsrc, L + 1, FSB_TSCALE,
+            (f->bla_on && v.stages_bla >= 4) ? v.r_bla : nullptr, v.first_invalid_i, t2);
+        if (cudaGetLastError() != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+            fsb_frame_destroy(f);
+            return fail(-1, "orbit table kernel failed");
+        }
+        v.T2 = (const double *)t2;
+        v.esc_hi = esc_hi_of(v.Mdiv_sq);
+    }
 #undef UP
     /* the descriptor copy must not keep caller pointers alive */
     f->d.Zn_path = nullptr; f->d.ref_index_xr = nullptr; f->d.ref_xr = nullptr;
@@ -1518,7 +1555,7 @@ static int frame_enqueue(Ctx *c, fsb_frame *f, cudaStream_t st, int slot, const 
         ? (d.nexp != 0
                ? pick_mn(d.xr_detect != 0, d.calc_dzndc != 0, d.calc_dzndz != 0, f->bla_on)
                : pick_m2(d.xr_detect != 0, d.calc_dzndc != 0, d.calc_dzndz != 0, f->bla_on,
-                         f->dev.order_i > 0 || d.calc_orbit != 0, f->fast_xr))
+                         f->dev.order_i > 0 || d.calc_orbit != 0, f->fast_xr, f->v2))
         : pick_bs(d.xr_detect != 0, d.calc_dzndc != 0, f->bla_on, f->fast_xr, d.flavor);
     unsigned long long *ctl = c->d_ctl + slot * CTL_WORDS;
     CK(cudaMemsetAsync(ctl, 0, CTL_WORDS * sizeof(unsigned long long), st));

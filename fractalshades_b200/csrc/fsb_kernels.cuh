@@ -21,80 +21,9 @@
  * Outputs are written as coalesced planes (one row of Z / U / stop_* each).
  */
 #pragma once
-#include "fsb_math.cuh"
+#include "fsb_lane.cuh"
 
 namespace fsb {
-
-/* Pixel projection (projection.py) and the derivative modifier applied at the
- * end of the perturbation loops (perturbation.py:1387-1388, 1772-1776).
- * kind: 0 Cartesian (identity), 1 Expmap; mod_kind: 0 none, 1 Expmap
- * exp(Re(k pix) + mod_param), 2 Cartesian(expmap_seam) |pix + 1e-6| mod_param */
-struct ProjDev {
-    int kind, mod_kind;
-    double hmoy, k_re, k_im, mod_param;
-};
-
-struct FrameDev {
-    long long L;
-    const C *Zn;
-    /* holomorphic */
-    const C *dZndc; const int *dZndc_e;
-    const C *dZndc_std;   /* Xrange frames: flushed fp64 mirror of dZndc (fast path) */
-    const C *dZndz; const int *dZndz_e;
-    const C *ref_xr; const int *ref_xr_e;
-    /* burning ship family */
-    const double *dP[4]; const int *dP_e[4];
-    const double *dP_std[4];   /* Xrange frames: flushed fp64 mirrors (fast path) */
-    const double *refx_xr; const int *refx_xr_e;
-    const double *refy_xr; const int *refy_xr_e;
-    long long n_xr; const int *ref_index_xr;
-    long long ref_div_iter, ref_order;
-    double drift[2]; int drift_e[2];
-    double lin_scale; int lin_scale_e;
-    double lin_mat[4];
-    const double *M_bla; const double *r_bla;
-    long long bla_len; int stages_bla;
-    long long max_iter;
-    double Mdiv_sq, eps_sq;
-    int calc_orbit; long long backshift;
-    int flavor;
-    /* 32-bit mirrors used by the pixel kernels (every orbit index fits) */
-    int Li, ref_div_i, order_i /* 0: not a cycle */, first_invalid_i, max_iter_i, n_xr_i;
-    long long zstride;   /* row stride of the output planes (>= npts of the launch) */
-    /* Perturbation_mandelbrot_N (appended: the offsets above are those of every
-     * other kernel): exponent and comb(N, k) as doubles, k = 0..N */
-    int nexp;
-    const double *cbinom;
-    int ref_div_m1_i;    /* ref_div_i - 1: the rebase test compares against a constant-bank operand */
-};
-
-struct StdDev {
-    double center_re, center_im, dx;
-    double lin_mat[4];
-    long long max_iter;
-    double Mdiv_sq, eps_sq;
-    int calc_d2, calc_orbit;
-    long long backshift;
-    int flavor;
-    long long zstride;   /* row stride of the output planes */
-    int nexp;            /* k_std_mn: exponent of Mandelbrot_N */
-};
-
-/* Work units.  A launch covers units [unit_lo, unit_hi); one warp takes one unit
- * at a time from a global counter (warp-level work stealing) and its 32 lanes
- * take the unit's 32 points.
- *   flat list   (tiles == nullptr): unit u = points [32u, 32u + 32)
- *   tile list   the point list is a concatenation of row-major tiles
- *               (core.py:1767-1830); a unit is an 8 x 4 pixel patch of one tile,
- *               lane l -> (row l >> 3, column l & 7).  Neighbouring pixels leave the
- *               loop at nearby iteration counts, and a compact footprint keeps
- *               more lanes alive than a 32 x 1 strip (measured 4-8 %).
- * Each tile descriptor is {first unit, first point, width, height}. */
-struct Tiling {
-    const int4 *tiles;
-    int n_tiles;
-    int unit_lo, unit_hi;
-};
 
 /* Takes the warp's next unit: returns false when the launch is exhausted or the
  * host raised the abort flag (the flag is read by lane 0 only, so the whole
@@ -157,16 +86,6 @@ __device__ __forceinline__ void add_counters(unsigned long long *counters,
         atomicAdd(counters + 3, c3);
         if (c4) atomicAdd(counters + 4, c4);
     }
-}
-
-__device__ __forceinline__ C ldC(const C *p, long long i)
-{
-    double2 v = __ldg(reinterpret_cast<const double2 *>(p) + i);
-    return mkC(v.x, v.y);
-}
-__device__ __forceinline__ void stC(double *Z, long long row, long long npts, long long i, C v)
-{
-    reinterpret_cast<double2 *>(Z)[row * npts + i] = make_double2(v.re, v.im);
 }
 
 /* The projection and the modifier run as two small HBM-bound passes around
@@ -479,214 +398,6 @@ k_std_bs(StdDev p, long long npts, const C *__restrict__ c_pix,
         n_sum += (unsigned long long)n_iter;
     }
     add_counters(counters, n_exec, 0, 0, n_sum);
-}
-
-/* ======================================================================== */
-/* Reference-path access                                                     */
-
-/* Position of idx in the sorted ref_index_xr or -1: stateless equivalent of
- * the cursor of perturbation.py:2519-2588. */
-__device__ __forceinline__ int xr_find(const int *index, int n, int idx)
-{
-    int lo = 0, hi = n;
-    while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if (__ldg(index + mid) < idx) lo = mid + 1; else hi = mid;
-    }
-    if (lo < n && __ldg(index + lo) == idx) return lo;
-    return -1;
-}
-
-__device__ __forceinline__ int bla_index(int i, int stg)
-{
-    return 2 * i + ((1 << stg) - 1);
-}
-__device__ __forceinline__ long long bla_index64(long long i, int stg)
-{
-    return 2 * i + ((1LL << stg) - 1);
-}
-
-/* perturbation.py:2116-2170.  Returns the step (0 = no BLA applicable) and
- * the node index.  All orbit indices fit 32 bits (the host checks it).
- *
- * The reference walks the stages from the highest admissible one down and
- * takes the first node with |z| < r.  A merged node's radius is
- * min(r_first_half, ...) (perturbation.py:2021), so along one start index the
- * radii never grow with the stage (and a NaN radius stays NaN upwards): a point
- * that fails the lowest stored stage fails them all.  That stage is tested
- * first -- about two checks in three end there -- and |z| >= max(|re|, |im|)
- * (the rounded hypot is never below its larger argument) rejects most of those
- * before the hypot is even evaluated.  Same node as the top-down walk. */
-__device__ __forceinline__ int ref_bla_get(const double *__restrict__ r_bla,
-                                           int stages_bla, C zn, int n_iter,
-                                           int first_invalid, int &index_out)
-{
-    const int it = n_iter >> 3;
-    const int invalid_step = first_invalid - n_iter;
-    /* skip the levels whose step cannot fit before the first invalid index */
-    if (invalid_step <= 8 || stages_bla < 4) return 0;
-    const int base = 2 * it - 1;
-    const double r3 = __ldg(r_bla + base + 1);
-    if (!(fabs(zn.re) < r3 && fabs(zn.im) < r3)) return 0;
-    const double az = cabs_rn(zn);
-    if (!(az < r3)) return 0;
-    int stages = stages_bla - 1;
-    if (it != 0) {
-        int s = 3 + (__ffs(it) - 1);
-        if (s < stages) stages = s;
-    }
-    const int top = 31 - __clz(invalid_step - 1);   /* largest stg with 2^stg < invalid_step */
-    if (stages > top) stages = top;
-    /* Measured and dropped: bisecting the stage (the predicate is monotone, same node
-     * bit for bit) -- the walk from the top usually ends at its first or second node;
-     * config 2 13.58 -> 14.48 ms, config 3 28.9 -> 29.7 ms. */
-    for (int stg = stages; stg > 3; stg--) {
-        const int ib = base + (1 << (stg - 3));
-        if (az < __ldg(r_bla + ib)) { index_out = ib; return 1 << stg; }
-    }
-    index_out = base + 1;
-    return 8;
-}
-
-/* ======================================================================== */
-/* Holomorphic perturbation (Mandelbrot power 2)                             */
-
-template <class T, class R>
-__device__ __forceinline__ T p_iter_zn(T z, R ref_zn, T c)
-{
-    return z * (z + 2. * ref_zn) + c; /* mandelbrot_M2.py:607-610 */
-}
-template <class T, class R, class D>
-__device__ __forceinline__ T p_iter_deriv(T z, T dz, R ref_zn, D ref_d)
-{
-    return 2. * ((ref_zn + z) * dz + ref_d * z); /* mandelbrot_M2.py:611-622 */
-}
-
-#if !defined(FSB_STRICT) && defined(FSB_FMA_CHAIN)
-/* Default build, fp64 operands: the same two formulas as explicit FMA chains
- * (the reference's loops are numba fastmath: LLVM contracts and re-associates
- * them on FMA hosts, so no particular rounding sequence is "the" reference). */
-__device__ __forceinline__ C p_iter_zn(C z, C ref_zn, C c)
-{
-    const double tr = fma(2., ref_zn.re, z.re), ti = fma(2., ref_zn.im, z.im);
-    return mkC(fma(z.re, tr, fma(-z.im, ti, c.re)), fma(z.re, ti, fma(z.im, tr, c.im)));
-}
-__device__ __forceinline__ C p_iter_deriv(C z, C dz, C ref_zn, C ref_d)
-{
-    /* s = 2 (Z + z) = (z + 2 Z) + z ; d = 2 Z' : both doublings are exact */
-    const double sr = fma(2., ref_zn.re, z.re) + z.re, si = fma(2., ref_zn.im, z.im) + z.im;
-    const double dr = ref_d.re + ref_d.re, di = ref_d.im + ref_d.im;
-    return mkC(fma(sr, dz.re, fma(-si, dz.im, fma(dr, z.re, -(di * z.im)))),
-               fma(sr, dz.im, fma(si, dz.re, fma(dr, z.im, di * z.re))));
-}
-#endif
-
-/* Power-N Mandelbrot (models/mandelbrot_Mn.py:628-742): full binomial
- * expansions, written once for complex128 and Xrange like the reference's
- * numba closures.  Cb[k] = comb(N, k) as float64. */
-template <class T>
-__device__ __forceinline__ T mn_dfdz(int nexp, T z)              /* :643-649 */
-{
-    T tmp = z;
-    for (int k = 2; k < nexp; k++) tmp = tmp * z;
-    return (double)nexp * tmp;
-}
-template <class T, class R>
-__device__ __forceinline__ T mn_iter_zn(int nexp, const double *__restrict__ Cb, T z, R ref_zn, T c)
-{
-    T tmp = z * (z + __ldg(Cb + 1) * ref_zn);                     /* :656-668 */
-    R pk = ref_zn;
-    for (int k = 2; k < nexp; k++) {
-        pk = pk * ref_zn;
-        tmp = z * (tmp + __ldg(Cb + k) * pk);
-    }
-    return tmp + c;
-}
-template <class T, class R, class D>
-__device__ __forceinline__ T mn_iter_deriv(int nexp, const double *__restrict__ Cb, T z, T dz,
-                                           R ref_zn, D ref_d)   /* :670-728 */
-{
-    const double c1 = __ldg(Cb + 1);
-    T mul = z + c1 * ref_zn;
-    T tmp = z * mul;
-    T dtmp = dz * mul + z * (dz + c1 * ref_d);
-    R pk = ref_zn;
-    for (int k = 2; k < nexp; k++) {
-        const double ck = __ldg(Cb + k);
-        D dpk = ((double)k * pk) * ref_d;
-        pk = pk * ref_zn;
-        mul = tmp + ck * pk;
-        dtmp = dz * mul + z * (dtmp + ck * dpk);
-        tmp = z * mul;
-    }
-    return dtmp;
-}
-
-/* Fast path of the Xrange kernels.  Xrange arithmetic is fp64 arithmetic with
- * an unbounded exponent: every operation is the correctly rounded result of
- * the same real operation.  While every live component of the pixel state is
- * a normal double comfortably inside the range, the plain fp64 operation
- * sequence therefore produces bit-identical values (scaling by 2^k is exact,
- * rounding is scale invariant, and the sub-1e-300 addends -- c, the Xrange
- * reference points, the tiny dZndc entries -- are below half an ulp of every
- * sum they enter).  `in_fast_range` is the guard: biased exponent within
- * [1023-460, 1023+900] for each component (zeros, denormals, inf and NaN all
- * fail).  When it fails the iteration is redone in exact Xrange arithmetic. */
-__device__ __forceinline__ bool in_fast_range(double x)
-{
-    /* 2 * hi drops the sign bit; the exponent field then sits in bits 21-31 */
-    const unsigned lo = (unsigned)(1023 - 460) << 21, span = (unsigned)(460 + 900 + 1) << 21;
-    return 2u * (unsigned)hi32(x) - lo < span;
-}
-__device__ __forceinline__ bool in_fast_range(C z)
-{
-    return in_fast_range(z.re) && in_fast_range(z.im);
-}
-
-/* Fused Xrange forms of the BLA step (perturbation.py:1139-1153).  Same real
- * operations, in the same order and with the same roundings as the operator
- * chain `A * z + B * c` of numba_xr.py (product mantissas, alignment to the
- * larger exponent by exponent-field arithmetic clamped at 0, one rounded add
- * per component) -- an Xrange value does not depend on how its mantissa /
- * exponent split was normalised on the way, so only the bookkeeping is fused:
- * one alignment instead of three normalisations. */
-__device__ __forceinline__ int cexp_field(C v)
-{
-    return max(expfield(v.re), expfield(v.im));
-}
-/* m * 2^shift on the exponent field (clamped at 0, mantissa bits kept, as
- * _exp2_shift does); zeros pass through */
-__device__ __forceinline__ double xshift(double m, int shift)
-{
-    const int hi = hi32(m);
-    const int fld = (hi >> 20) & 0x7ff;
-    int nf = fld + shift;
-    nf = (fld == 0 || nf < 0) ? 0 : nf;
-    return mk64((hi & (int)0x800fffff) | (nf << 20), lo32(m));
-}
-__device__ __forceinline__ XC xr_lin(C A, XC z, C B, XC c)
-{
-    const C p = A * z.m, q = B * c.m;
-    const int fp = cexp_field(p), fq = cexp_field(q);
-    const int ep = z.e + (fp - 1023), eq = c.e + (fq - 1023);
-    int e = max(ep, eq);
-    if (fp == 0) e = eq;              /* a zero product does not set the exponent */
-    if (fq == 0) e = ep;
-    const int sp = (1023 - fp) - (e - ep), sq = (1023 - fq) - (e - eq);
-    return mkXC(mkC(xshift(p.re, sp) + xshift(q.re, sq), xshift(p.im, sp) + xshift(q.im, sq)), e);
-}
-__device__ __forceinline__ XC xr_mulc(C A, XC d)
-{
-    const C p = A * d.m;
-    const int fp = cexp_field(p);
-    return mkXC(mkC(xshift(p.re, 1023 - fp), xshift(p.im, 1023 - fp)), d.e + (fp - 1023));
-}
-/* to_standard of a value whose mantissa parts are below 4 in magnitude */
-__device__ __forceinline__ C to_std_small(XC x)
-{
-    if (x.e < -1200)        /* rounds to (signed) zero */
-        return mkC(mk64(hi32(x.m.re) & (int)0x80000000, 0), mk64(hi32(x.m.im) & (int)0x80000000, 0));
-    return to_std(x);
 }
 
 /* Template switches: XR = Xrange arithmetic (dx < 1e-300); DZNDC / DZNDZ =
@@ -1052,6 +763,150 @@ k_perturb_m2(const __grid_constant__ FrameDev f, long long npts_ll,
 #undef DZNDZ_X
 #undef REF_X
     add_counters(counters, n_exec, n_bla, n_reb, n_sum, n_fast);
+}
+
+/* ======================================================================== */
+/* Holomorphic perturbation, event-driven persistent kernel (fsb_lane.cuh).
+ *
+ * One warp = 32 resident lanes for the whole launch.  All 32 lanes run the hot
+ * iteration in lock step; after each iteration ONE warp vote decides whether
+ * any lane has an event, and only then does the warp enter the event section,
+ * where the lanes concerned run `lane_step` (divergent).  The hot loop
+ * therefore contains no divergent branch, no reconvergence barrier, no flag
+ * and no counter: per iteration 18 FP64 instructions (default build), two
+ * 32-byte loads of one orbit record, the integer pre-tests, one vote and one
+ * branch.
+ *
+ * Finished lanes take new pixels from the warp's current 8 x 4 patch / the next
+ * patch of the global queue once FSB_V2_REFILL_MIN lanes are free
+ * (escaped-lane compaction).  Measured on configs 2 and 3: compaction at any
+ * granularity below the whole warp LOSES -- lanes that start a pixel at
+ * different times sit at different phases of the 8-iteration BLA cadence and
+ * of the rebase cycle, every iteration then has some lane with an event, and
+ * the other lanes idle through it (REFILL_MIN = 1: 5.4x / 11.7x slower than
+ * 32; 28: +13 % / +15 %) -- so the default takes 32 new pixels when all 32
+ * lanes are free, which keeps neighbouring pixels in lock step. */
+#ifndef FSB_V2_MINB
+#define FSB_V2_MINB (XR ? 5 : 7)
+#endif
+#ifndef FSB_V2_UNROLL
+#define FSB_V2_UNROLL 1
+#endif
+#ifndef FSB_V2_REFILL_MIN      /* new pixels are taken once this many lanes are free */
+#define FSB_V2_REFILL_MIN 32
+#endif
+template <bool XR, bool DZNDC, bool BLA>
+__global__ void __launch_bounds__(128, FSB_V2_MINB)
+k_perturb_m2_v2(const __grid_constant__ FrameDev f, long long npts_ll,
+                const C *__restrict__ c_pix, double *__restrict__ Z,
+                int *__restrict__ U, signed char *__restrict__ stop_reason,
+                int *__restrict__ stop_iter, unsigned long long *work,
+                unsigned long long *counters, const volatile int *abort_flag,
+                const Tiling tiling)
+{
+    /* per-thread counter slots and (Xrange frames) hot-loop checkpoints */
+    __shared__ unsigned long long s_cnt[5][128];
+    __shared__ LaneCk s_ck[XR ? 128 : 1];
+#pragma unroll
+    for (int k = 0; k < 5; k++) s_cnt[k][threadIdx.x] = 0;
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    LaneM2 s;
+    lane_park(s, LF_NEED | LF_EV);
+    s.nbase = 0; s.ipt = 0; s.p_skip = s.p_bla = s.p_reb = s.p_slow = 0;
+    s.c_xr = mkXC(mkC(0., 0.), 0); s.c_tiny = false;
+    /* the warp's current unit: slots [pool_next, 32) are still to be handed out */
+    int pool_next = 32, u_first = 0, u_r0 = 0, u_c0 = 0, u_w = 0, u_h = 0;
+    bool exhausted = false;
+    const unsigned esc_hi = f.esc_hi;
+    const double4 *__restrict__ T2 = reinterpret_cast<const double4 *>(f.T2);
+    const int n_units = tiling.unit_hi - tiling.unit_lo;
+
+    for (;;) {
+        /* ---------------- event section ---------------- */
+        if ((s.flags & LF_EV) && !(s.flags & (LF_NEED | LF_DEAD)))
+            lane_step<XR, DZNDC, BLA>(f, s, c_pix, Z, U, stop_reason, stop_iter,
+                                      &s_cnt[0][threadIdx.x], 128, &s_ck[XR ? threadIdx.x : 0]);
+        unsigned need = __ballot_sync(FULL, (s.flags & LF_NEED) != 0);
+        if (need) {
+            const unsigned parked = __ballot_sync(FULL, (s.flags & (LF_NEED | LF_DEAD)) != 0);
+            if (__popc(parked) < FSB_V2_REFILL_MIN) {
+                if (s.flags & LF_NEED) s.flags &= ~LF_EV;      /* wait, parked */
+            } else {
+                while (need) {
+                    if (pool_next >= 32) {
+                        if (exhausted) break;
+                        int u = -1;
+                        if (lane == 0 && !*abort_flag) {
+                            const unsigned long long g = atomicAdd(work, 1ULL);
+                            if (g < (unsigned long long)n_units) u = tiling.unit_lo + (int)g;
+                        }
+                        u = __shfl_sync(FULL, u, 0);
+                        if (u < 0) { exhausted = true; break; }
+                        if (tiling.tiles == nullptr) {
+                            u_first = 32 * u; u_w = 0;
+                        } else {
+                            int lo = 0, hi = tiling.n_tiles - 1;   /* last tile whose first unit <= u */
+                            while (lo < hi) {
+                                const int mid = (lo + hi + 1) >> 1;
+                                if (__ldg(&tiling.tiles[mid].x) <= u) lo = mid; else hi = mid - 1;
+                            }
+                            const int4 tl = __ldg(tiling.tiles + lo);
+                            const int k = u - tl.x, per_row = (tl.z + 7) >> 3;
+                            const int py = k / per_row, px = k - py * per_row;
+                            u_first = tl.y; u_w = tl.z; u_h = tl.w; u_r0 = 4 * py; u_c0 = 8 * px;
+                        }
+                        pool_next = 0;
+                    }
+                    const int slot = pool_next + __popc(need & ((1u << lane) - 1u));
+                    if ((s.flags & LF_NEED) && slot < 32) {
+                        bool valid; int ipt;
+                        if (u_w == 0) {
+                            const long long i = (long long)u_first + slot;
+                            valid = i < npts_ll; ipt = (int)i;
+                        } else {
+                            const int r = u_r0 + (slot >> 3), col = u_c0 + (slot & 7);
+                            valid = (r < u_h) && (col < u_w);
+                            ipt = u_first + r * u_w + col;
+                        }
+                        if (valid) { s.ipt = ipt; s.flags = LF_INIT | LF_EV; }
+                    }
+                    pool_next = min(32, pool_next + __popc(need));
+                    need = __ballot_sync(FULL, (s.flags & LF_NEED) != 0);
+                }
+                if (need && (s.flags & LF_NEED)) lane_park(s, LF_DEAD);   /* nothing left */
+            }
+        }
+        if (__any_sync(FULL, (s.flags & LF_EV) != 0)) continue;
+        if (__all_sync(FULL, (s.flags & LF_DEAD) != 0)) break;
+
+        /* ---------------- hot loop ---------------- */
+        const bool alive = (s.flags & (LF_DEAD | LF_NEED)) == 0;
+        int code;
+        constexpr int kUnroll = FSB_V2_UNROLL;
+#pragma unroll kUnroll
+        for (;;) {
+            /* the record of index w: {Zn[w+1], k dZndc[w]} {Zn[w], r3(w+1), -} */
+            double t0, t1, t2, t3, Zr, Zi, r3n, pad;
+            const double4 *rec = T2 + 2 * (long long)s.w;
+            asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+                : "=d"(t0), "=d"(t1), "=d"(t2), "=d"(t3) : "l"(rec));
+            asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4+32];"
+                : "=d"(Zr), "=d"(Zi), "=d"(r3n), "=d"(pad) : "l"(rec));
+            code = m2_hot_iter<XR, DZNDC, BLA>(s, Zr, Zi, t0, t1, t2, t3, r3n, esc_hi, alive);
+            if (__any_sync(FULL, code != 0)) break;
+        }
+        if (code == 1) s.flags |= LF_EV | LF_ITER;
+        else if (code == 2) s.flags |= LF_EV | LF_BAD;
+        const C Zw = ldC(f.Zn, s.w);             /* the event section wants Zn[w] */
+        s.Zr = Zw.re; s.Zi = Zw.im;
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        unsigned long long tot = 0;
+        for (int t = 0; t < 128; t++) tot += s_cnt[threadIdx.x][t];
+        if (tot) atomicAdd(counters + threadIdx.x, tot);
+    }
 }
 
 /* ======================================================================== */
@@ -2123,23 +1978,35 @@ k_dzndc_bs_scan_apply(FrameDev f, long long n_elem, XF scale, const AffBS *__res
     }
 }
 
-/* flushed fp64 mirror of an Xrange table (fast path of the Xrange kernels):
- * exact for normal components, 0 below the normal range, NaN when too large */
-__device__ __forceinline__ double flush_component(double m, int e)
-{
-    if (m == 0.) return 0.;
-    double nm; int ne;
-    normalize_real(m, e, nm, ne);
-    if (!(m == m) || ne > 1000) return mk64(0x7ff80000, 0);
-    if (ne < -1022) return 0.;
-    return ldexp(nm, ne);
-}
 __global__ void k_flush_mirror(long long n, const double *__restrict__ m, const int *__restrict__ e,
                                int comps, double *__restrict__ out)
 {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n * comps) return;
     out[i] = flush_component(m[i], e[i / comps]);
+}
+
+/* Interleaved orbit table of k_perturb_m2_v2 (HBM-bound, once per frame):
+ *   T2[i] = {Zn[i+1], scale * d[i]} {Zn[i], r3(i+1), 0}, i in [0, n_rec)
+ * Zn holds n_zn valid elements, d (the dZndc path or its fp64 mirror; may be
+ * null) n_d; elements past the end read as 0.  r3(j) = r_bla[2 (j >> 3)] when
+ * the loop looks the BLA tree up at index j (j a multiple of 8 with more than
+ * 8 valid indices ahead, ref_bla_get), else 0. */
+__global__ void k_build_t2(long long n_rec, const C *__restrict__ Zn, long long n_zn,
+                           const C *__restrict__ d, long long n_d, double scale,
+                           const double *__restrict__ r_bla, int first_invalid,
+                           double4 *__restrict__ T2)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n_rec) return;
+    const C z1 = (i + 1 < n_zn) ? ldC(Zn, i + 1) : mkC(0., 0.);
+    const C z0 = (i < n_zn) ? ldC(Zn, i) : mkC(0., 0.);
+    const C dd = (d != nullptr && i < n_d) ? ldC(d, i) : mkC(0., 0.);
+    double r3 = 0.;
+    const long long j = i + 1;
+    if (r_bla != nullptr && (j & 7) == 0 && (long long)first_invalid - j > 8) r3 = __ldg(r_bla + 2 * (j >> 3));
+    T2[2 * i] = make_double4(z1.re, z1.im, mul_rn(scale, dd.re), mul_rn(scale, dd.im));
+    T2[2 * i + 1] = make_double4(z0.re, z0.im, r3, 0.);
 }
 
 /* ======================================================================== */

@@ -1,0 +1,858 @@
+/*
+ * fsb_lane.cuh -- per-frame device structures and the per-pixel ("lane") pieces
+ * of the perturbation loops, written once for the device kernels and for the
+ * host: table lookups (reference orbit, BLA tree), the model formulas, the
+ * fused Xrange forms, and the event-driven lane state machine of the
+ * persistent holomorphic kernel `k_perturb_m2_v2` (fsb_kernels.cuh).
+ *
+ * Everything here is `__host__ __device__`: the CPU test-suite compiles the very
+ * same state machine (tests/emul/) and checks it against the oracle bit for bit
+ * -- test infrastructure only; the product runs it on the GPU.
+ */
+#pragma once
+#include "fsb_math.cuh"
+
+namespace fsb {
+
+#ifdef __CUDA_ARCH__
+template <class T> __device__ __forceinline__ T ldg_(const T *p) { return __ldg(p); }
+__device__ __forceinline__ int ffs_(int x) { return __ffs(x); }
+__device__ __forceinline__ int clz_(int x) { return __clz(x); }
+#else
+template <class T> inline T ldg_(const T *p) { return *p; }
+inline int ffs_(int x) { return __builtin_ffs(x); }
+inline int clz_(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
+#endif
+FSB_HD int imax(int a, int b) { return a > b ? a : b; }
+FSB_HD int imin(int a, int b) { return a < b ? a : b; }
+
+/* Pixel projection (projection.py) and the derivative modifier applied at the
+ * end of the perturbation loops (perturbation.py:1387-1388, 1772-1776).
+ * kind: 0 Cartesian (identity), 1 Expmap; mod_kind: 0 none, 1 Expmap
+ * exp(Re(k pix) + mod_param), 2 Cartesian(expmap_seam) |pix + 1e-6| mod_param */
+struct ProjDev {
+    int kind, mod_kind;
+    double hmoy, k_re, k_im, mod_param;
+};
+
+struct FrameDev {
+    long long L;
+    const C *Zn;
+    /* holomorphic */
+    const C *dZndc; const int *dZndc_e;
+    const C *dZndc_std;   /* Xrange frames: flushed fp64 mirror of dZndc (fast path) */
+    const C *dZndz; const int *dZndz_e;
+    const C *ref_xr; const int *ref_xr_e;
+    /* burning ship family */
+    const double *dP[4]; const int *dP_e[4];
+    const double *dP_std[4];   /* Xrange frames: flushed fp64 mirrors (fast path) */
+    const double *refx_xr; const int *refx_xr_e;
+    const double *refy_xr; const int *refy_xr_e;
+    long long n_xr; const int *ref_index_xr;
+    long long ref_div_iter, ref_order;
+    double drift[2]; int drift_e[2];
+    double lin_scale; int lin_scale_e;
+    double lin_mat[4];
+    const double *M_bla; const double *r_bla;
+    long long bla_len; int stages_bla;
+    long long max_iter;
+    double Mdiv_sq, eps_sq;
+    int calc_orbit; long long backshift;
+    int flavor;
+    /* 32-bit mirrors used by the pixel kernels (every orbit index fits) */
+    int Li, ref_div_i, order_i /* 0: not a cycle */, first_invalid_i, max_iter_i, n_xr_i;
+    long long zstride;   /* row stride of the output planes (>= npts of the launch) */
+    /* Perturbation_mandelbrot_N (appended: the offsets above are those of every
+     * other kernel): exponent and comb(N, k) as doubles, k = 0..N */
+    int nexp;
+    const double *cbinom;
+    int ref_div_m1_i;    /* ref_div_i - 1: the rebase test compares against a constant-bank operand */
+    /* k_perturb_m2_v2: interleaved orbit table, one 64-byte record per index
+     *   T2[i] = {Zn[i+1], FSB_TSCALE * dZndc[i]} {Zn[i], r3(i+1), 0}
+     * (dZndc: the fp64 mirror in Xrange frames; r3(j): stage-3 BLA radius of index j where
+     * the loop looks the tree up, else 0) -- everything an iteration reads, in two 32-byte
+     * loads off one address -- and the exponent bound of the escape pre-test (both parts
+     * of Z + z below 2^k with 2^(2k+1) <= Mdiv_sq) */
+    const double *T2;
+    unsigned esc_hi;
+};
+
+struct StdDev {
+    double center_re, center_im, dx;
+    double lin_mat[4];
+    long long max_iter;
+    double Mdiv_sq, eps_sq;
+    int calc_d2, calc_orbit;
+    long long backshift;
+    int flavor;
+    long long zstride;   /* row stride of the output planes */
+    int nexp;            /* k_std_mn: exponent of Mandelbrot_N */
+};
+
+/* Work units.  A launch covers units [unit_lo, unit_hi); one warp takes one unit
+ * at a time from a global counter (warp-level work stealing) and its 32 lanes
+ * take the unit's 32 points.
+ *   flat list   (tiles == nullptr): unit u = points [32u, 32u + 32)
+ *   tile list   the point list is a concatenation of row-major tiles
+ *               (core.py:1767-1830); a unit is an 8 x 4 pixel patch of one tile,
+ *               lane l -> (row l >> 3, column l & 7).  Neighbouring pixels leave the
+ *               loop at nearby iteration counts, and a compact footprint keeps
+ *               more lanes alive than a 32 x 1 strip (measured 4-8 %).
+ * Each tile descriptor is {first unit, first point, width, height}. */
+struct Tiling {
+    const int4 *tiles;
+    int n_tiles;
+    int unit_lo, unit_hi;
+};
+
+FSB_HD C ldC(const C *p, long long i)
+{
+#ifdef __CUDA_ARCH__
+    double2 v = __ldg(reinterpret_cast<const double2 *>(p) + i);
+    return mkC(v.x, v.y);
+#else
+    return p[i];
+#endif
+}
+FSB_HD void stC(double *Z, long long row, long long npts, long long i, C v)
+{
+#ifdef __CUDA_ARCH__
+    reinterpret_cast<double2 *>(Z)[row * npts + i] = make_double2(v.re, v.im);
+#else
+    Z[2 * (row * npts + i)] = v.re; Z[2 * (row * npts + i) + 1] = v.im;
+#endif
+}
+
+/* ======================================================================== */
+/* Reference-path access                                                     */
+
+/* Position of idx in the sorted ref_index_xr or -1: stateless equivalent of
+ * the cursor of perturbation.py:2519-2588. */
+FSB_HD int xr_find(const int *index, int n, int idx)
+{
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (ldg_(index + mid) < idx) lo = mid + 1; else hi = mid;
+    }
+    if (lo < n && ldg_(index + lo) == idx) return lo;
+    return -1;
+}
+
+FSB_HD int bla_index(int i, int stg)
+{
+    return 2 * i + ((1 << stg) - 1);
+}
+FSB_HD long long bla_index64(long long i, int stg)
+{
+    return 2 * i + ((1LL << stg) - 1);
+}
+
+/* perturbation.py:2116-2170.  Returns the step (0 = no BLA applicable) and
+ * the node index.  All orbit indices fit 32 bits (the host checks it).
+ *
+ * The reference walks the stages from the highest admissible one down and
+ * takes the first node with |z| < r.  A merged node's radius is
+ * min(r_first_half, ...) (perturbation.py:2021), so along one start index the
+ * radii never grow with the stage (and a NaN radius stays NaN upwards): a point
+ * that fails the lowest stored stage fails them all.  That stage is tested
+ * first -- about two checks in three end there -- and |z| >= max(|re|, |im|)
+ * (the rounded hypot is never below its larger argument) rejects most of those
+ * before the hypot is even evaluated.  Same node as the top-down walk. */
+FSB_HD int ref_bla_get(const double *__restrict__ r_bla,
+                                           int stages_bla, C zn, int n_iter,
+                                           int first_invalid, int &index_out)
+{
+    const int it = n_iter >> 3;
+    const int invalid_step = first_invalid - n_iter;
+    /* skip the levels whose step cannot fit before the first invalid index */
+    if (invalid_step <= 8 || stages_bla < 4) return 0;
+    const int base = 2 * it - 1;
+    const double r3 = ldg_(r_bla + base + 1);
+    if (!(fabs(zn.re) < r3 && fabs(zn.im) < r3)) return 0;
+    const double az = cabs_rn(zn);
+    if (!(az < r3)) return 0;
+    int stages = stages_bla - 1;
+    if (it != 0) {
+        int s = 3 + (ffs_(it) - 1);
+        if (s < stages) stages = s;
+    }
+    const int top = 31 - clz_(invalid_step - 1);   /* largest stg with 2^stg < invalid_step */
+    if (stages > top) stages = top;
+    /* Measured and dropped: bisecting the stage (the predicate is monotone, same node
+     * bit for bit) -- the walk from the top usually ends at its first or second node;
+     * config 2 13.58 -> 14.48 ms, config 3 28.9 -> 29.7 ms. */
+    for (int stg = stages; stg > 3; stg--) {
+        const int ib = base + (1 << (stg - 3));
+        if (az < ldg_(r_bla + ib)) { index_out = ib; return 1 << stg; }
+    }
+    index_out = base + 1;
+    return 8;
+}
+
+/* ======================================================================== */
+/* Holomorphic perturbation (Mandelbrot power 2)                             */
+
+template <class T, class R>
+FSB_HD T p_iter_zn(T z, R ref_zn, T c)
+{
+    return z * (z + 2. * ref_zn) + c; /* mandelbrot_M2.py:607-610 */
+}
+template <class T, class R, class D>
+FSB_HD T p_iter_deriv(T z, T dz, R ref_zn, D ref_d)
+{
+    return 2. * ((ref_zn + z) * dz + ref_d * z); /* mandelbrot_M2.py:611-622 */
+}
+
+#if !defined(FSB_STRICT) && defined(FSB_FMA_CHAIN)
+/* Default build, fp64 operands: the same two formulas as explicit FMA chains
+ * (the reference's loops are numba fastmath: LLVM contracts and re-associates
+ * them on FMA hosts, so no particular rounding sequence is "the" reference). */
+FSB_HD C p_iter_zn(C z, C ref_zn, C c)
+{
+    const double tr = fma(2., ref_zn.re, z.re), ti = fma(2., ref_zn.im, z.im);
+    return mkC(fma(z.re, tr, fma(-z.im, ti, c.re)), fma(z.re, ti, fma(z.im, tr, c.im)));
+}
+FSB_HD C p_iter_deriv(C z, C dz, C ref_zn, C ref_d)
+{
+    /* s = 2 (Z + z) = (z + 2 Z) + z ; d = 2 Z' : both doublings are exact */
+    const double sr = fma(2., ref_zn.re, z.re) + z.re, si = fma(2., ref_zn.im, z.im) + z.im;
+    const double dr = ref_d.re + ref_d.re, di = ref_d.im + ref_d.im;
+    return mkC(fma(sr, dz.re, fma(-si, dz.im, fma(dr, z.re, -(di * z.im)))),
+               fma(sr, dz.im, fma(si, dz.re, fma(dr, z.im, di * z.re))));
+}
+#endif
+
+/* Power-N Mandelbrot (models/mandelbrot_Mn.py:628-742): full binomial
+ * expansions, written once for complex128 and Xrange like the reference's
+ * numba closures.  Cb[k] = comb(N, k) as float64. */
+template <class T>
+FSB_HD T mn_dfdz(int nexp, T z)              /* :643-649 */
+{
+    T tmp = z;
+    for (int k = 2; k < nexp; k++) tmp = tmp * z;
+    return (double)nexp * tmp;
+}
+template <class T, class R>
+FSB_HD T mn_iter_zn(int nexp, const double *__restrict__ Cb, T z, R ref_zn, T c)
+{
+    T tmp = z * (z + ldg_(Cb + 1) * ref_zn);                     /* :656-668 */
+    R pk = ref_zn;
+    for (int k = 2; k < nexp; k++) {
+        pk = pk * ref_zn;
+        tmp = z * (tmp + ldg_(Cb + k) * pk);
+    }
+    return tmp + c;
+}
+template <class T, class R, class D>
+FSB_HD T mn_iter_deriv(int nexp, const double *__restrict__ Cb, T z, T dz,
+                                           R ref_zn, D ref_d)   /* :670-728 */
+{
+    const double c1 = ldg_(Cb + 1);
+    T mul = z + c1 * ref_zn;
+    T tmp = z * mul;
+    T dtmp = dz * mul + z * (dz + c1 * ref_d);
+    R pk = ref_zn;
+    for (int k = 2; k < nexp; k++) {
+        const double ck = ldg_(Cb + k);
+        D dpk = ((double)k * pk) * ref_d;
+        pk = pk * ref_zn;
+        mul = tmp + ck * pk;
+        dtmp = dz * mul + z * (dtmp + ck * dpk);
+        tmp = z * mul;
+    }
+    return dtmp;
+}
+
+/* Fast path of the Xrange kernels.  Xrange arithmetic is fp64 arithmetic with
+ * an unbounded exponent: every operation is the correctly rounded result of
+ * the same real operation.  While every live component of the pixel state is
+ * a normal double comfortably inside the range, the plain fp64 operation
+ * sequence therefore produces bit-identical values (scaling by 2^k is exact,
+ * rounding is scale invariant, and the sub-1e-300 addends -- c, the Xrange
+ * reference points, the tiny dZndc entries -- are below half an ulp of every
+ * sum they enter).  `in_fast_range` is the guard: biased exponent within
+ * [1023-460, 1023+900] for each component (zeros, denormals, inf and NaN all
+ * fail).  When it fails the iteration is redone in exact Xrange arithmetic. */
+#ifndef FSB_FAST_LO      /* narrowed by the test-suite to exercise the guard paths */
+#define FSB_FAST_LO 460
+#define FSB_FAST_HI 900
+#endif
+FSB_HD bool in_fast_range(double x)
+{
+    /* 2 * hi drops the sign bit; the exponent field then sits in bits 21-31 */
+    const unsigned lo = (unsigned)(1023 - FSB_FAST_LO) << 21,
+                   span = (unsigned)(FSB_FAST_LO + FSB_FAST_HI + 1) << 21;
+    return 2u * (unsigned)hi32(x) - lo < span;
+}
+FSB_HD bool in_fast_range(C z)
+{
+    return in_fast_range(z.re) && in_fast_range(z.im);
+}
+
+/* Fused Xrange forms of the BLA step (perturbation.py:1139-1153).  Same real
+ * operations, in the same order and with the same roundings as the operator
+ * chain `A * z + B * c` of numba_xr.py (product mantissas, alignment to the
+ * larger exponent by exponent-field arithmetic clamped at 0, one rounded add
+ * per component) -- an Xrange value does not depend on how its mantissa /
+ * exponent split was normalised on the way, so only the bookkeeping is fused:
+ * one alignment instead of three normalisations. */
+FSB_HD int cexp_field(C v)
+{
+    return imax(expfield(v.re), expfield(v.im));
+}
+/* m * 2^shift on the exponent field (clamped at 0, mantissa bits kept, as
+ * _exp2_shift does); zeros pass through */
+FSB_HD double xshift(double m, int shift)
+{
+    const int hi = hi32(m);
+    const int fld = (hi >> 20) & 0x7ff;
+    int nf = fld + shift;
+    nf = (fld == 0 || nf < 0) ? 0 : nf;
+    return mk64((hi & (int)0x800fffff) | (nf << 20), lo32(m));
+}
+FSB_HD XC xr_lin(C A, XC z, C B, XC c)
+{
+    const C p = A * z.m, q = B * c.m;
+    const int fp = cexp_field(p), fq = cexp_field(q);
+    const int ep = z.e + (fp - 1023), eq = c.e + (fq - 1023);
+    int e = imax(ep, eq);
+    if (fp == 0) e = eq;              /* a zero product does not set the exponent */
+    if (fq == 0) e = ep;
+    const int sp = (1023 - fp) - (e - ep), sq = (1023 - fq) - (e - eq);
+    return mkXC(mkC(xshift(p.re, sp) + xshift(q.re, sq), xshift(p.im, sp) + xshift(q.im, sq)), e);
+}
+FSB_HD XC xr_mulc(C A, XC d)
+{
+    const C p = A * d.m;
+    const int fp = cexp_field(p);
+    return mkXC(mkC(xshift(p.re, 1023 - fp), xshift(p.im, 1023 - fp)), d.e + (fp - 1023));
+}
+/* to_standard of a value whose mantissa parts are below 4 in magnitude */
+FSB_HD C to_std_small(XC x)
+{
+    if (x.e < -1200)        /* rounds to (signed) zero */
+        return mkC(mk64(hi32(x.m.re) & (int)0x80000000, 0), mk64(hi32(x.m.im) & (int)0x80000000, 0));
+    return to_std(x);
+}
+
+
+/* flushed fp64 mirror of an Xrange table (fast path of the Xrange kernels):
+ * exact for normal components, 0 below the normal range, NaN when too large */
+FSB_HD double flush_component(double m, int e)
+{
+    if (m == 0.) return 0.;
+    double nm; int ne;
+    normalize_real(m, e, nm, ne);
+    if (!(m == m) || ne > 1000) return mk64(0x7ff80000, 0);
+    if (ne < -1022) return 0.;
+    return ldexp(nm, ne);
+}
+
+/* ======================================================================== */
+/* BLA lookup without the square root.
+ *
+ * `|z| < r` (perturbation.py:2158) is decided on squares: with
+ *   s = fl(fl((a up)^2) + fl((b up)^2))   -- the quantity hypot_rn takes the root of
+ *   q = fl((r up)^2)
+ * the rounded hypot is below r whenever s is below q by at least one unit of
+ * the HIGH word (a relative margin of 2^-21, far above the handful of ulp the
+ * roundings can move either side), and not below it whenever s is above q by
+ * that much.  High words closer than 2 (three cases in a million) are decided
+ * by the exact hypot.  Same decisions as `cabs_rn(z) < r`, bit for bit. */
+struct AbsSq { double s, up; C z; };
+FSB_HD AbsSq abs_sq(C z)
+{
+    AbsSq q;
+    q.z = z;
+    const double a = fabs(z.re), b = fabs(z.im);
+    const int ea = imax(expfield(a), expfield(b));
+    q.up = 1.;
+    if (ea > 1023 + 500) q.up = 0x1p-600;
+    else if (ea < 1023 - 500) q.up = 0x1p600;
+    const double au = mul_rn(a, q.up), bu = mul_rn(b, q.up);
+    q.s = add_rn(mul_rn(au, au), mul_rn(bu, bu));
+    return q;
+}
+FSB_HD bool abs_lt(const AbsSq &q, double r)
+{
+    const double ru = mul_rn(r, q.up);
+    const double r2 = mul_rn(ru, ru);
+    const int d = hi32(r2) - hi32(q.s);
+    /* non-negative, non-NaN operands order like their high words */
+    if (r == r && q.s == q.s && r >= 0.) {
+        if (d >= 2) return true;
+        if (d <= -2) return false;
+    }
+    return cabs_rn(q.z) < r;
+}
+
+/* perturbation.py:2116-2170 with the lookup order of ref_bla_get (lowest
+ * stored stage first) and the square-free comparison above. */
+FSB_HD int ref_bla_get2(const double *__restrict__ r_bla, int stages_bla, C zn, int w,
+                        int first_invalid, int &index_out)
+{
+    const int it = w >> 3;
+    const int invalid_step = first_invalid - w;
+    if (invalid_step <= 8 || stages_bla < 4) return 0;
+    const int base = 2 * it - 1;
+    const double r3 = ldg_(r_bla + base + 1);
+    if (!(fabs(zn.re) < r3 && fabs(zn.im) < r3)) return 0;
+    const AbsSq q = abs_sq(zn);
+    if (!abs_lt(q, r3)) return 0;
+    int stages = stages_bla - 1;
+    if (it != 0) stages = imin(stages, 3 + (ffs_(it) - 1));
+    stages = imin(stages, 31 - clz_(invalid_step - 1));   /* largest stg with 2^stg < invalid_step */
+    for (int stg = stages; stg > 3; stg--) {
+        const int ib = base + (1 << (stg - 3));
+        if (abs_lt(q, ldg_(r_bla + ib))) { index_out = ib; return 1 << stg; }
+    }
+    index_out = base + 1;
+    return 8;
+}
+
+/* ======================================================================== */
+/* Lane state machine of the persistent holomorphic kernel (k_perturb_m2_v2).
+ *
+ * The reference's per-pixel loop (perturbation.py:1076-1398) as an event-driven
+ * machine.  A lane's life alternates between
+ *   - the HOT iteration (`m2_hot_iter`): one full perturbation iteration on
+ *     plain doubles with the cheapest sufficient tests -- no table lookup
+ *     other than the orbit record, no flag, no counter;
+ *   - the EVENT step (`lane_step`): everything else, entered when a pre-test
+ *     of the hot iteration fires: exact stop tests, both rebase kinds, BLA
+ *     lookups and steps, the first iteration after a rebase (sticky
+ *     `bool_dyn_rebase`: reference derivative = 0), exact Xrange iterations,
+ *     pixel epilogue and the initialisation of the lane's next pixel.
+ * The pre-tests are necessary conditions evaluated on the high words
+ * (integer pipe): `w >= wlim` (max_iter, reference about to diverge),
+ * exponent of Z + z against the escape radius, |Z + z| <= |z| per component
+ * for the dynamic rebase, and |z| per component against the stage-3 BLA
+ * radius of the next index (carried by the orbit record, 0 where no lookup
+ * takes place); whatever fires, the event step re-evaluates the reference's
+ * tests exactly and in the reference's order, so the outputs do not depend on
+ * the pre-tests.  n_iter is not stored: n_iter = nbase + w between events. */
+enum : unsigned {
+    LF_EV = 1u,        /* something to do in the event section                     */
+    LF_ITER = 2u,      /* an iteration was performed: its stop / rebase tests are pending */
+    LF_DYN = 4u,       /* bool_dyn_rebase (sticky, perturbation.py:1116,1317)      */
+    LF_SLOW = 8u,      /* Xrange frames: state in Xrange form (not on the fp64 lane) */
+    LF_NEED = 16u,     /* pixel finished, waits for the next one                   */
+    LF_INIT = 32u,     /* a new pixel was assigned                                 */
+    LF_DEAD = 64u,     /* no pixel (none left, or waiting for the whole warp)      */
+    LF_BAD = 128u,     /* Xrange frames: the range guard of the hot loop failed    */
+    LF_CAREFUL = 256u  /* Xrange frames: replaying from the checkpoint, one guarded
+                        * iteration per event step, up to the failing one          */
+};
+
+#ifdef FSB_STRICT
+#define FSB_TSCALE 1.
+#else
+#define FSB_TSCALE 2.
+#endif
+/* Xrange frames: the hot loop returns to the event section at least this often
+ * (bounds the replay after a failed range guard) */
+#define FSB_XR_STRETCH 64
+
+struct LaneM2 {
+    double zr, zi;     /* delta z: the value (fp64 lane) or the Xrange mantissa (LF_SLOW) */
+    double dr, di;     /* delta z' likewise                                            */
+    double cr, ci;     /* c, standard                                                  */
+    double Zr, Zi;     /* Zn[w] (event section only)                                   */
+    int w, wlim, winc; /* reference index; the hot loop leaves when w >= wlim; 0 for parked lanes */
+    unsigned flags;
+    int ze, de;        /* LF_SLOW: exponents of (zr, zi) and (dr, di)                   */
+    int nbase;         /* n_iter - w                                                   */
+    int ipt;
+    unsigned p_skip, p_bla, p_reb, p_slow;
+    XC c_xr;
+    bool c_tiny;
+};
+/* state at the entry of the hot loop (Xrange frames; shared memory on the device) */
+struct LaneCk { double zr, zi, dr, di; int w; };
+
+/* one full iteration on doubles (mandelbrot_M2.py:607-622); (er, ei) is the
+ * table's derivative entry FSB_TSCALE * dZndc[w] (0 after a rebase).
+ * Default build: FMA chains, 2 (Z + z) formed as (2 Z + z) + z and the
+ * doubling of dZndc folded into the table -- 18 FP64 instructions; the
+ * reference's loops are numba fastmath (contracted and re-associated by LLVM),
+ * so no particular rounding sequence is "the" reference.  -fmad=false build:
+ * the literal operation order, bit-exact with the oracle. */
+template <bool DZNDC>
+FSB_HD void m2_iter_fp64(double zr, double zi, double dr, double di, double Zr, double Zi,
+                         double er, double ei, double cr, double ci, double &nzr, double &nzi,
+                         double &ndr, double &ndi)
+{
+#ifdef FSB_STRICT
+    const C z = mkC(zr, zi), ref = mkC(Zr, Zi);
+    if (DZNDC) {
+        const C nd = p_iter_deriv(z, mkC(dr, di), ref, mkC(er, ei));
+        ndr = nd.re; ndi = nd.im;
+    }
+    const C nz = p_iter_zn(z, ref, mkC(cr, ci));
+    nzr = nz.re; nzi = nz.im;
+#else
+    const double tr = fma(2., Zr, zr), ti = fma(2., Zi, zi);
+    if (DZNDC) {
+        const double sr = tr + zr, si = ti + zi;
+        ndr = fma(sr, dr, fma(-si, di, fma(er, zr, -(ei * zi))));
+        ndi = fma(sr, di, fma(si, dr, fma(er, zi, ei * zr)));
+    }
+    nzr = fma(zr, tr, fma(-zi, ti, cr));
+    nzi = fma(zr, ti, fma(zi, tr, ci));
+#endif
+}
+
+FSB_HD void lane_park(LaneM2 &s, unsigned flags)
+{
+    s.zr = s.zi = s.dr = s.di = s.cr = s.ci = 0.;
+    s.Zr = s.Zi = 0.;
+    s.w = 0; s.winc = 0; s.wlim = 0x7fffffff;
+    s.ze = s.de = 0;
+    s.flags = flags;
+}
+
+/* pixel epilogue, perturbation.py:1374-1398.  Counters of the launch (executed
+ * iterations, BLA steps, rebases, sum of stop_iter, fp64-lane iterations) go
+ * to the caller's slots cnt[k * cstride]: one private slot set per thread. */
+template <bool XR, bool DZNDC>
+FSB_HD void lane_finish(const FrameDev &f, LaneM2 &s, int stop, double *Z, int *U,
+                        signed char *stop_reason, int *stop_iter, unsigned long long *cnt,
+                        int cstride)
+{
+    const int w = s.w, ipt = s.ipt;
+    U[ipt] = w;
+    C zn, dz = mkC(0., 0.);
+    const C Zw = ldC(f.Zn, w);
+    if (XR && !(s.flags & LF_SLOW)) {
+        zn = mkC(s.zr, s.zi) + Zw;
+        if (DZNDC) {
+            const C rd = ldC(f.dZndc_std, w);
+            if (rd.re == rd.re && rd.im == rd.im) dz = mkC(s.dr, s.di) + rd;
+            else dz = to_std(to_xr(mkC(s.dr, s.di)) + mkXC(ldC(f.dZndc, w), ldg_(f.dZndc_e + w)));
+        }
+    } else if (XR) {
+        zn = to_std(mkXC(mkC(s.zr, s.zi), s.ze)) + Zw;
+        if (DZNDC) dz = to_std(mkXC(mkC(s.dr, s.di), s.de) + mkXC(ldC(f.dZndc, w), ldg_(f.dZndc_e + w)));
+    } else {
+        zn = mkC(s.zr, s.zi) + Zw;
+        if (DZNDC) dz = mkC(s.dr, s.di) + ldC(f.dZndc, w);
+    }
+    stC(Z, 0, f.zstride, ipt, zn);
+    if (DZNDC) stC(Z, 1, f.zstride, ipt, dz);
+    const int n_iter = s.nbase + w;
+    stop_reason[ipt] = (signed char)stop;
+    stop_iter[ipt] = n_iter;
+    const unsigned p_exec = (unsigned)n_iter - s.p_skip;
+    cnt[0] += p_exec;
+    cnt[cstride] += s.p_bla;
+    cnt[2 * cstride] += s.p_reb;
+    cnt[3 * cstride] += (unsigned long long)n_iter;
+    if (XR) cnt[4 * cstride] += p_exec - s.p_slow;
+    lane_park(s, LF_NEED | LF_EV);
+}
+
+/* Xrange state <-> fp64 lane */
+template <bool DZNDC> FSB_HD void lane_to_slow(LaneM2 &s)
+{
+    const XC zx = to_xr(mkC(s.zr, s.zi));
+    s.zr = zx.m.re; s.zi = zx.m.im; s.ze = zx.e;
+    if (DZNDC) {
+        const XC dx = to_xr(mkC(s.dr, s.di));
+        s.dr = dx.m.re; s.di = dx.m.im; s.de = dx.e;
+    }
+    s.flags = (s.flags | LF_SLOW) & ~LF_CAREFUL;
+}
+/* back to the fp64 lane when every live component is in the safe range;
+ * zstd = to_std of the Xrange z */
+template <bool DZNDC> FSB_HD void lane_try_fast(LaneM2 &s, C zstd)
+{
+    if (!in_fast_range(zstd)) return;
+    C dstd = mkC(0., 0.);
+    if (DZNDC) {
+        dstd = to_std(mkXC(mkC(s.dr, s.di), s.de));
+        if (!in_fast_range(dstd)) return;
+    }
+    s.zr = zstd.re; s.zi = zstd.im; s.ze = 0;
+    if (DZNDC) { s.dr = dstd.re; s.di = dstd.im; s.de = 0; }
+    s.flags &= ~LF_SLOW;
+}
+
+/* The event section of one lane: runs until the lane is armed for the hot
+ * loop (LF_EV cleared, wlim set) or its pixel has ended (LF_NEED). */
+template <bool XR, bool DZNDC, bool BLA>
+FSB_HD void lane_step(const FrameDev &f, LaneM2 &s, const C *c_pix, double *Z, int *U,
+                      signed char *stop_reason, int *stop_iter, unsigned long long *cnt,
+                      int cstride, LaneCk *ck)
+{
+    const C *Zn = f.Zn;
+    const bool has_xr = XR && f.n_xr_i > 0;
+#define L_DZNDC_X(i) mkXC(ldC(f.dZndc, (i)), ldg_(f.dZndc_e + (i)))
+#define L_REF_X(k) mkXC(ldC(f.ref_xr, (k)), ldg_(f.ref_xr_e + (k)))
+#define L_LOAD_Z() do { const C Zw_ = ldC(Zn, s.w); s.Zr = Zw_.re; s.Zi = Zw_.im; } while (0)
+
+    if (s.flags & LF_INIT) {
+        /* perturbation.py:1026-1031, 2214-2230 */
+        const C pix = ldC(c_pix, s.ipt);
+        const double x1 = f.lin_mat[0] * pix.re + f.lin_mat[1] * pix.im;
+        const double y1 = f.lin_mat[2] * pix.re + f.lin_mat[3] * pix.im;
+        s.c_xr = (mkXF(f.lin_scale, f.lin_scale_e) * mkC(x1, y1))
+                 + mkXC(mkC(f.drift[0], f.drift[1]), f.drift_e[0]);
+        const C c = to_std(s.c_xr);
+        s.cr = c.re; s.ci = c.im;
+        /* |c| < 2^-1600: lets the fp64 lane of an Xrange frame take BLA steps */
+        s.c_tiny = XR && (s.c_xr.e + cexp_field(s.c_xr.m) - 1023 < -1600);
+        s.zr = s.zi = s.dr = s.di = 0.;
+        s.ze = s.de = 0;
+        s.w = 0; s.winc = 1; s.nbase = 0;
+        L_LOAD_Z();
+        s.p_skip = s.p_bla = s.p_reb = s.p_slow = 0;
+        s.flags = LF_EV | LF_DYN | (XR ? LF_SLOW : 0u);
+    } else if (XR && (s.flags & LF_BAD)) {
+        /* the range guard failed somewhere after the checkpoint: back to it, then
+         * one guarded iteration at a time until the failing one is reached */
+        s.zr = ck->zr; s.zi = ck->zi; s.dr = ck->dr; s.di = ck->di; s.w = ck->w;
+        L_LOAD_Z();
+        s.flags = (s.flags & ~LF_BAD) | LF_CAREFUL;
+    }
+
+    for (;;) {
+        if (s.flags & LF_ITER) {
+            s.flags &= ~LF_ITER;
+            /* ---- stop tests of the iteration just done, :1218-1279 ---- */
+            if (s.nbase + s.w >= f.max_iter_i) {
+                lane_finish<XR, DZNDC>(f, s, 0, Z, U, stop_reason, stop_iter, cnt, cstride);
+                return;
+            }
+            const bool slow = XR && (s.flags & LF_SLOW);
+            const C zn = slow ? to_std(mkXC(mkC(s.zr, s.zi), s.ze)) : mkC(s.zr, s.zi);
+            const C ref_next = mkC(s.Zr, s.Zi);
+            const C ZZ = zn + ref_next;
+            if (norm2(ZZ) > f.Mdiv_sq) {
+                lane_finish<XR, DZNDC>(f, s, 1, Z, U, stop_reason, stop_iter, cnt, cstride);
+                return;
+            }
+            /* ---- rebase: reference diverging (:1283-1313) or dynamic glitch
+             * (:1317-1372); only the dynamic test assigns the sticky flag ---- */
+            const bool rebase = (s.w >= f.ref_div_m1_i);
+            bool go = rebase;
+            if (!rebase) {
+                const bool dyn = (fabs(ZZ.re) <= fabs(zn.re)) && (fabs(ZZ.im) <= fabs(zn.im));
+                s.flags = dyn ? (s.flags | LF_DYN) : (s.flags & ~LF_DYN);
+                go = dyn;
+            }
+            if (go) {
+                bool do_rebase = true, fast_rebase = false;
+                XC ZZ_xr = mkXC(mkC(0., 0.), 0);
+                if (XR && !rebase) {
+                    if (!slow && in_fast_range(ZZ)) {
+                        /* same comparison on the same correctly rounded values */
+                        do_rebase = norm2(ZZ) <= norm2(zn);
+                        fast_rebase = true;
+                    } else {
+                        if (!slow) lane_to_slow<DZNDC>(s);
+                        int knext = -1;
+                        if (has_xr && s.w != 0 && fabs(ref_next.re) < 1.e-300 && fabs(ref_next.im) < 1.e-300)
+                            knext = xr_find(f.ref_index_xr, f.n_xr_i, s.w);
+                        const XC zx = mkXC(mkC(s.zr, s.zi), s.ze);
+                        ZZ_xr = (knext >= 0) ? (zx + L_REF_X(knext)) : (zx + ref_next);
+                        do_rebase = xr_le(abs2(ZZ_xr), abs2(zx));
+                    }
+                }
+                if (do_rebase) {
+                    if (XR && !(s.flags & LF_SLOW) && (fast_rebase || rebase)) {
+                        /* rebase in plain fp64; leave the fp64 lane if a result falls
+                         * out of the safe range (exact conversion) */
+                        C nd = mkC(s.dr, s.di);
+                        if (DZNDC) nd = nd + ldC(f.dZndc_std, s.w);
+                        if (in_fast_range(ZZ) && (!DZNDC || in_fast_range(nd))) {
+                            s.zr = ZZ.re; s.zi = ZZ.im;
+                            if (DZNDC) { s.dr = nd.re; s.di = nd.im; }
+                        } else {
+                            if (DZNDC) {
+                                const XC dx = to_xr(mkC(s.dr, s.di)) + L_DZNDC_X(s.w);
+                                s.dr = dx.m.re; s.di = dx.m.im; s.de = dx.e;
+                            }
+                            const XC zx = to_xr(ZZ);
+                            s.zr = zx.m.re; s.zi = zx.m.im; s.ze = zx.e;
+                            s.flags = (s.flags | LF_SLOW) & ~LF_CAREFUL;
+                        }
+                    } else if (XR) {
+                        const XC zx = rebase ? to_xr(ZZ) : ZZ_xr;
+                        const C zstd = rebase ? ZZ : to_std(ZZ_xr);
+                        s.zr = zx.m.re; s.zi = zx.m.im; s.ze = zx.e;
+                        if (DZNDC) {
+                            const XC dx = mkXC(mkC(s.dr, s.di), s.de) + L_DZNDC_X(s.w);
+                            s.dr = dx.m.re; s.di = dx.m.im; s.de = dx.e;
+                        }
+                        lane_try_fast<DZNDC>(s, zstd);
+                    } else {
+                        s.zr = ZZ.re; s.zi = ZZ.im;
+                        if (DZNDC) {
+                            const C nd = mkC(s.dr, s.di) + ldC(f.dZndc, s.w);
+                            s.dr = nd.re; s.di = nd.im;
+                        }
+                    }
+                    s.nbase += s.w;
+                    s.w = 0;
+                    L_LOAD_Z();
+                    s.p_reb++;
+                }
+            }
+        }
+
+        /* ---- BLA steps, perturbation.py:1121-1154: no stop test in between ---- */
+        if (BLA) {
+            while ((s.w & 7) == 0) {
+                const bool slow = XR && (s.flags & LF_SLOW);
+                const C zn = slow ? to_std_small(mkXC(mkC(s.zr, s.zi), s.ze)) : mkC(s.zr, s.zi);
+                int ib = 0;
+                const int step = ref_bla_get2(f.r_bla, f.stages_bla, zn, s.w, f.first_invalid_i, ib);
+                if (step == 0) break;
+                const C *M = reinterpret_cast<const C *>(f.M_bla);
+                const C A = ldC(M, 2 * ib), B = ldC(M, 2 * ib + 1);
+                s.p_skip += (unsigned)step;
+                s.w += step;                       /* n_iter = nbase + w moves with it */
+                L_LOAD_Z();
+                s.p_bla++;
+                if (!XR) {
+                    const C nz = A * zn + B * mkC(s.cr, s.ci);
+                    s.zr = nz.re; s.zi = nz.im;
+                    if (DZNDC) { const C nd = A * mkC(s.dr, s.di); s.dr = nd.re; s.di = nd.im; }
+                    continue;
+                }
+                if (!slow && s.c_tiny) {
+                    /* fp64 form of the step.  With every component of A z a normal
+                     * double >= 2^-460 and |B c| <= 2^1025 |c| < 2^-575, the B c term is
+                     * far below half an ulp of the sums it enters: fl(A z) IS the
+                     * correctly rounded Xrange result.  Out-of-range results or a
+                     * non-finite B: exact path below. */
+                    const C nz = A * zn;
+                    C nd = mkC(s.dr, s.di);
+                    if (DZNDC) nd = A * nd;
+                    if (in_fast_range(nz) && (!DZNDC || in_fast_range(nd))
+                        && expfield(B.re) != 0x7ff && expfield(B.im) != 0x7ff) {
+                        s.zr = nz.re; s.zi = nz.im;
+                        if (DZNDC) { s.dr = nd.re; s.di = nd.im; }
+                        continue;
+                    }
+                }
+                if (!slow) lane_to_slow<DZNDC>(s);      /* B * c needs the exact c */
+                const XC zx = xr_lin(A, mkXC(mkC(s.zr, s.zi), s.ze), B, s.c_xr);
+                s.zr = zx.m.re; s.zi = zx.m.im; s.ze = zx.e;
+                if (DZNDC) {
+                    const XC dx = xr_mulc(A, mkXC(mkC(s.dr, s.di), s.de));
+                    s.dr = dx.m.re; s.di = dx.m.im; s.de = dx.e;
+                }
+                lane_try_fast<DZNDC>(s, to_std_small(zx));
+            }
+        }
+
+        if (!(s.flags & (LF_DYN | LF_SLOW | LF_CAREFUL))) break;      /* -> arm the hot loop */
+
+        /* ---- one full iteration here: reference derivative 0 after a rebase
+         * (sticky flag), exact Xrange arithmetic, or a guarded replay, :1158-1209 ---- */
+        const bool dyn = (s.flags & LF_DYN) != 0;
+        if (XR && (s.flags & LF_SLOW)) {
+            const C ref_zn = mkC(s.Zr, s.Zi);
+            int k = -1;
+            if (has_xr && s.w != 0 && fabs(ref_zn.re) < 1.e-300 && fabs(ref_zn.im) < 1.e-300)
+                k = xr_find(f.ref_index_xr, f.n_xr_i, s.w);
+            const XC ref_x = (k >= 0) ? L_REF_X(k) : to_xr(ref_zn);
+            XC zx = mkXC(mkC(s.zr, s.zi), s.ze);
+            if (DZNDC) {
+                const XC ref_d = dyn ? mkXC(mkC(0., 0.), 0) : L_DZNDC_X(s.w);
+                const XC dx = p_iter_deriv(zx, mkXC(mkC(s.dr, s.di), s.de), ref_x, ref_d);
+                s.dr = dx.m.re; s.di = dx.m.im; s.de = dx.e;
+            }
+            zx = p_iter_zn(zx, ref_x, s.c_xr);
+            s.zr = zx.m.re; s.zi = zx.m.im; s.ze = zx.e;
+            s.p_slow++;
+            lane_try_fast<DZNDC>(s, to_std(zx));
+        } else {
+            double er = 0., ei = 0.;
+            if (DZNDC && !dyn) {
+                const C rd = ldC(XR ? f.dZndc_std : f.dZndc, s.w);
+                er = mul_rn(FSB_TSCALE, rd.re); ei = mul_rn(FSB_TSCALE, rd.im);
+            }
+            double nzr, nzi, ndr = 0., ndi = 0.;
+            m2_iter_fp64<DZNDC>(s.zr, s.zi, s.dr, s.di, s.Zr, s.Zi, er, ei, s.cr, s.ci,
+                                nzr, nzi, ndr, ndi);
+            if (XR && !(in_fast_range(mkC(nzr, nzi)) && (!DZNDC || in_fast_range(mkC(ndr, ndi))))) {
+                /* out of the safe range: redo this iteration in Xrange arithmetic */
+                lane_to_slow<DZNDC>(s);
+                continue;
+            }
+            s.zr = nzr; s.zi = nzi;
+            if (DZNDC) { s.dr = ndr; s.di = ndi; }
+        }
+        s.w += 1;
+        L_LOAD_Z();
+        s.flags |= LF_ITER;
+        /* (a replay always meets its failing iteration; this bound is a safety net) */
+        if (XR && (s.flags & LF_CAREFUL) && s.w > ck->w + FSB_XR_STRETCH) s.flags &= ~LF_CAREFUL;
+    }
+
+    /* ---- arm the hot loop ---- */
+    int wl = imin(f.ref_div_m1_i, f.max_iter_i - s.nbase);
+    if (XR) {
+        wl = imin(wl, s.w + FSB_XR_STRETCH);
+        ck->zr = s.zr; ck->zi = s.zi; ck->dr = s.dr; ck->di = s.di; ck->w = s.w;
+    }
+    s.wlim = wl;
+    s.flags &= ~LF_EV;
+#undef L_DZNDC_X
+#undef L_REF_X
+#undef L_LOAD_Z
+}
+
+/* The hot iteration with its pre-tests.  Returns 0 when the lane can go on, 1
+ * when it must visit the event section for the tests of this iteration, 2
+ * (Xrange frames) when the range guard failed: the state is then garbage and
+ * the lane goes back to its checkpoint.  The orbit record of index w is
+ *   {Zn[w+1], FSB_TSCALE dZndc[w]} {Zn[w], r3(w+1), -}
+ * r3(w+1) = the stage-3 BLA radius of index w+1 where a lookup takes place
+ * (multiples of 8 inside the valid range), else 0. */
+template <bool XR, bool DZNDC, bool BLA>
+FSB_HD int m2_hot_iter(LaneM2 &s, double Zr, double Zi, double t0, double t1, double t2, double t3,
+                       double r3n, unsigned esc_hi, bool alive)
+{
+    double nzr, nzi, ndr = 0., ndi = 0.;
+    m2_iter_fp64<DZNDC>(s.zr, s.zi, s.dr, s.di, Zr, Zi, t2, t3, s.cr, s.ci, nzr, nzi, ndr, ndi);
+    s.zr = nzr; s.zi = nzi;
+    if (DZNDC) { s.dr = ndr; s.di = ndi; }
+    s.w += s.winc;
+    const double ZZr = nzr + t0, ZZi = nzi + t1;
+    const unsigned a = (unsigned)hi32(ZZr) & 0x7fffffffu, b = (unsigned)hi32(ZZi) & 0x7fffffffu;
+    const unsigned c = (unsigned)hi32(nzr) & 0x7fffffffu, d = (unsigned)hi32(nzi) & 0x7fffffffu;
+    /* |Z + z| <= |z| and |z| < r3 per component can only hold if they hold for the
+     * sign-stripped high words; a | b bounds both exponent fields from above */
+    bool ev = (s.w >= s.wlim) | ((a | b) >= esc_hi) | ((a <= c) & (b <= d));
+    if (BLA) {
+        const unsigned h3 = (unsigned)hi32(r3n);
+        ev = ev | ((c <= h3) & (d <= h3));
+    }
+    int code = (ev & alive) ? 1 : 0;
+    if (XR) {
+        bool bad = !(in_fast_range(nzr) & in_fast_range(nzi));
+        if (DZNDC) bad = bad | !(in_fast_range(ndr) & in_fast_range(ndi));
+        if (bad & alive) code = 2;
+    }
+    return code;
+}
+
+/* exponent-field bound of the escape pre-test: both parts of Z + z below 2^k
+ * imply |Z + z|^2 < 2^(2k+1) <= Mdiv_sq */
+inline unsigned esc_hi_of(double Mdiv_sq)
+{
+    if (!(Mdiv_sq > 0.)) return 0u;                     /* every iteration takes the exact test */
+    if (Mdiv_sq > 1.7e308) return 0x7ff00000u;
+    int e = 0;
+    frexp(Mdiv_sq, &e);                                 /* Mdiv_sq in [2^(e-1), 2^e) */
+    int k = (e - 2) / 2;                                /* 2k + 1 <= e - 1 */
+    if (e - 2 < 0) k = -((2 - e + 1) / 2);
+    if (k < -1000) return 0u;
+    return (unsigned)(k + 1023) << 20;
+}
+
+} /* namespace fsb */

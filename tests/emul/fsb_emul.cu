@@ -1,0 +1,170 @@
+/*
+ * fsb_emul.cu -- HOST emulation of the lane state machine of k_perturb_m2_v2.
+ *
+ * TEST INFRASTRUCTURE ONLY (built and loaded by tests/emul_lib.py, never by the
+ * product).  The event-driven pixel kernel is written as `__host__ __device__`
+ * per-lane functions (fractalshades_b200/csrc/fsb_lane.cuh: lane_step,
+ * m2_hot_iter); this file drives the very same functions one pixel at a time on
+ * the CPU, so that the `-m "not gpu"` suite can check the state machine against
+ * the oracle bit for bit (compiled with FSB_STRICT = the -fmad=false semantics)
+ * and to tolerance (default build formulas with libm's exact fma).  What it
+ * does not cover is the warp scheduling around the lanes (votes, refill): that
+ * is exercised by the GPU tests.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "../../fractalshades_b200/csrc/fsb_lane.cuh"
+
+using namespace fsb;
+
+extern "C" {
+
+typedef struct emul_frame {
+    int64_t L;                 /* orbit length; Zn_path holds L elements      */
+    const double *Zn_path;     /* complex128[L]                               */
+    const double *dZndc;       /* complex128[L] or NULL                       */
+    const int32_t *dZndc_e;    /* Xrange frames                               */
+    int64_t n_xr;
+    const int32_t *ref_index_xr;
+    const double *ref_xr;      /* complex128[n_xr]                            */
+    const int32_t *ref_xr_e;
+    int64_t ref_div_iter, ref_order;
+    double drift[2];
+    int32_t drift_e, lin_scale_e;
+    double lin_scale;
+    double lin_mat[4];
+    const double *M_bla, *r_bla;
+    int64_t bla_len;
+    int32_t stages_bla, xr_detect, bla_activated, calc_dzndc;
+    int64_t max_iter;
+    double M_divergence_sq;
+} emul_frame;
+
+int fsb_emul_strict(void)
+{
+#ifdef FSB_STRICT
+    return 1;
+#else
+    return 0;
+#endif
+}
+
+} /* extern "C" */
+
+/* counters: n_exec, n_bla, n_reb, n_sum, n_fast, hot iterations, event visits, failed guards */
+template <bool XR, bool DZNDC, bool BLA>
+static void run(const FrameDev &f, int64_t npts, const C *c_pix, double *Z, int32_t *U,
+                int8_t *sr, int32_t *si, unsigned long long *cnt)
+{
+    const double *T2 = f.T2;
+    for (int64_t ipt = 0; ipt < npts; ipt++) {
+        LaneM2 s;
+        LaneCk ck;
+        memset(&s, 0, sizeof s);
+        memset(&ck, 0, sizeof ck);
+        lane_park(s, 0u);
+        s.ipt = (int)ipt;
+        s.flags = LF_INIT | LF_EV;
+        for (;;) {
+            lane_step<XR, DZNDC, BLA>(f, s, c_pix, Z, U, (signed char *)sr, si, cnt, 1, &ck);
+            cnt[6]++;
+            if (s.flags & LF_NEED) break;
+            int code;
+            for (;;) {
+                const double *rec = T2 + 8 * (long long)s.w;
+                code = m2_hot_iter<XR, DZNDC, BLA>(s, rec[4], rec[5], rec[0], rec[1], rec[2], rec[3],
+                                                   rec[6], f.esc_hi, true);
+                cnt[5]++;
+                if (code != 0) break;
+            }
+            if (code == 1) s.flags |= LF_EV | LF_ITER;
+            else { s.flags |= LF_EV | LF_BAD; cnt[7]++; }
+            const C Zw = ldC(f.Zn, s.w);
+            s.Zr = Zw.re; s.Zi = Zw.im;
+        }
+    }
+}
+
+extern "C" int fsb_emul_perturb_m2(const emul_frame *e, int64_t npts, const double *c_pix, double *Z,
+                        int32_t *U, int8_t *sr, int32_t *si, uint64_t *counters)
+{
+    const int64_t L = e->L;
+    if (L >= (1LL << 30) || e->max_iter >= (1LL << 30)) return -3;
+    if (e->ref_order < (1LL << 30)) return -4;         /* periodic reference: not this kernel */
+    FrameDev f;
+    memset(&f, 0, sizeof f);
+    /* orbit and derivative path with the zero pad element of the device tables */
+    std::vector<C> Zn((size_t)L + 1, mkC(0., 0.)), dz, dz_std;
+    std::vector<int> dze;
+    memcpy(Zn.data(), e->Zn_path, (size_t)L * sizeof(C));
+    f.L = L; f.Li = (int)L;
+    f.Zn = Zn.data();
+    const bool xr = e->xr_detect != 0, dc = e->calc_dzndc != 0;
+    if (dc) {
+        dz.assign((size_t)L + 1, mkC(0., 0.));
+        memcpy(dz.data(), e->dZndc, (size_t)L * sizeof(C));
+        f.dZndc = dz.data();
+        if (xr) {
+            dze.assign((size_t)L + 1, 0);
+            memcpy(dze.data(), e->dZndc_e, (size_t)L * sizeof(int));
+            f.dZndc_e = dze.data();
+            dz_std.assign((size_t)L + 1, mkC(0., 0.));
+            for (int64_t i = 0; i < L; i++)
+                dz_std[(size_t)i] = mkC(flush_component(dz[(size_t)i].re, dze[(size_t)i]),
+                                        flush_component(dz[(size_t)i].im, dze[(size_t)i]));
+            f.dZndc_std = dz_std.data();
+        }
+    }
+    f.n_xr = e->n_xr; f.n_xr_i = (int)e->n_xr;
+    f.ref_index_xr = e->ref_index_xr;
+    f.ref_xr = (const C *)e->ref_xr; f.ref_xr_e = e->ref_xr_e;
+    f.ref_div_iter = e->ref_div_iter; f.ref_order = e->ref_order;
+    const long long big = (1LL << 30);
+    f.ref_div_i = (int)(e->ref_div_iter < big ? e->ref_div_iter : big);
+    f.ref_div_m1_i = f.ref_div_i - 1;
+    f.order_i = 0;
+    long long fi = L;
+    if (e->ref_div_iter < fi) fi = e->ref_div_iter;
+    f.first_invalid_i = (int)fi;
+    f.max_iter = e->max_iter; f.max_iter_i = (int)e->max_iter;
+    f.drift[0] = e->drift[0]; f.drift[1] = e->drift[1];
+    f.drift_e[0] = f.drift_e[1] = e->drift_e;
+    f.lin_scale = e->lin_scale; f.lin_scale_e = e->lin_scale_e;
+    for (int i = 0; i < 4; i++) f.lin_mat[i] = e->lin_mat[i];
+    f.M_bla = e->M_bla; f.r_bla = e->r_bla;
+    f.bla_len = e->bla_len; f.stages_bla = e->stages_bla;
+    f.Mdiv_sq = e->M_divergence_sq;
+    f.zstride = npts;
+    f.esc_hi = esc_hi_of(f.Mdiv_sq);
+    const bool bla = e->bla_activated != 0 && e->stages_bla > 3 && e->bla_len > 0;
+    /* interleaved orbit table, as k_build_t2 */
+    const int64_t n_rec = L + 16;
+    std::vector<double> T2((size_t)n_rec * 8, 0.);
+    const C *dsrc = dc ? (xr ? f.dZndc_std : f.dZndc) : nullptr;
+    for (int64_t i = 0; i < n_rec; i++) {
+        double *r = T2.data() + 8 * i;
+        if (i + 1 < L + 1) { r[0] = Zn[(size_t)i + 1].re; r[1] = Zn[(size_t)i + 1].im; }
+        if (dsrc && i < L + 1) { r[2] = mul_rn(FSB_TSCALE, dsrc[i].re); r[3] = mul_rn(FSB_TSCALE, dsrc[i].im); }
+        if (i < L + 1) { r[4] = Zn[(size_t)i].re; r[5] = Zn[(size_t)i].im; }
+        const int64_t j = i + 1;
+        if (bla && (j & 7) == 0 && (int64_t)f.first_invalid_i - j > 8) r[6] = e->r_bla[2 * (j >> 3)];
+    }
+    f.T2 = T2.data();
+
+    unsigned long long cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const C *cp = (const C *)c_pix;
+#define RUN(X, D, B) run<X, D, B>(f, npts, cp, Z, U, sr, si, cnt)
+    if (xr) {
+        if (dc) { if (bla) RUN(true, true, true); else RUN(true, true, false); }
+        else { if (bla) RUN(true, false, true); else RUN(true, false, false); }
+    } else {
+        if (dc) { if (bla) RUN(false, true, true); else RUN(false, true, false); }
+        else { if (bla) RUN(false, false, true); else RUN(false, false, false); }
+    }
+#undef RUN
+    if (counters) for (int k = 0; k < 8; k++) counters[k] = cnt[k];
+    return 0;
+}
