@@ -1458,6 +1458,13 @@ int fsb_frame_create(const fsb_frame_desc *desc, fsb_frame **out)
         f->v2 = d.model == FSB_MODEL_M2 && d.nexp == 0 && !d.calc_dzndz && !d.calc_orbit
                 && v.order_i == 0 && (!d.xr_detect || f->fast_xr) && !(old && old[0] == '1');
     }
+    if (f->v2 && f->bla_on) {
+        int *t = nullptr;
+        if (dev_zeros(f, 2 * v.bla_len, &t)) { fsb_frame_destroy(f); return -1; }
+        k_bla_r2hi<<<(int)((v.bla_len + 255) / 256), 256>>>(v.bla_len, v.r_bla, t, t + v.bla_len);
+        v.r2hi = t;
+        v.r2hi_up = t + v.bla_len;
+    }
     if (f->v2) {
         const long long n_rec = L + 16;
         double4 *t2 = nullptr;

@@ -787,7 +787,7 @@ k_perturb_m2(const __grid_constant__ FrameDev f, long long npts_ll,
  * 32; 28: +13 % / +15 %) -- so the default takes 32 new pixels when all 32
  * lanes are free, which keeps neighbouring pixels in lock step. */
 #ifndef FSB_V2_MINB
-#define FSB_V2_MINB (XR ? 5 : 7)
+#define FSB_V2_MINB 8
 #endif
 #ifndef FSB_V2_UNROLL
 #define FSB_V2_UNROLL 1
@@ -804,17 +804,16 @@ k_perturb_m2_v2(const __grid_constant__ FrameDev f, long long npts_ll,
                 unsigned long long *counters, const volatile int *abort_flag,
                 const Tiling tiling)
 {
-    /* per-thread counter slots and (Xrange frames) hot-loop checkpoints */
+    /* per-thread counter slots and the cold part of the lanes */
     __shared__ unsigned long long s_cnt[5][128];
-    __shared__ LaneCk s_ck[XR ? 128 : 1];
+    __shared__ LaneCold s_cold[128];
 #pragma unroll
-    for (int k = 0; k < 5; k++) s_cnt[k][threadIdx.x] = 0;
+    for (int q = 0; q < 5; q++) s_cnt[q][threadIdx.x] = 0;
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     LaneM2 s;
+    LaneCold &k = s_cold[threadIdx.x];
     lane_park(s, LF_NEED | LF_EV);
-    s.nbase = 0; s.ipt = 0; s.p_skip = s.p_bla = s.p_reb = s.p_slow = 0;
-    s.c_xr = mkXC(mkC(0., 0.), 0); s.c_tiny = false;
     /* the warp's current unit: slots [pool_next, 32) are still to be handed out */
     int pool_next = 32, u_first = 0, u_r0 = 0, u_c0 = 0, u_w = 0, u_h = 0;
     bool exhausted = false;
@@ -826,7 +825,7 @@ k_perturb_m2_v2(const __grid_constant__ FrameDev f, long long npts_ll,
         /* ---------------- event section ---------------- */
         if ((s.flags & LF_EV) && !(s.flags & (LF_NEED | LF_DEAD)))
             lane_step<XR, DZNDC, BLA>(f, s, c_pix, Z, U, stop_reason, stop_iter,
-                                      &s_cnt[0][threadIdx.x], 128, &s_ck[XR ? threadIdx.x : 0]);
+                                      &s_cnt[0][threadIdx.x], 128, k);
         unsigned need = __ballot_sync(FULL, (s.flags & LF_NEED) != 0);
         if (need) {
             const unsigned parked = __ballot_sync(FULL, (s.flags & (LF_NEED | LF_DEAD)) != 0);
@@ -852,8 +851,8 @@ k_perturb_m2_v2(const __grid_constant__ FrameDev f, long long npts_ll,
                                 if (__ldg(&tiling.tiles[mid].x) <= u) lo = mid; else hi = mid - 1;
                             }
                             const int4 tl = __ldg(tiling.tiles + lo);
-                            const int k = u - tl.x, per_row = (tl.z + 7) >> 3;
-                            const int py = k / per_row, px = k - py * per_row;
+                            const int ku = u - tl.x, per_row = (tl.z + 7) >> 3;
+                            const int py = ku / per_row, px = ku - py * per_row;
                             u_first = tl.y; u_w = tl.z; u_h = tl.w; u_r0 = 4 * py; u_c0 = 8 * px;
                         }
                         pool_next = 0;
@@ -869,7 +868,7 @@ k_perturb_m2_v2(const __grid_constant__ FrameDev f, long long npts_ll,
                             valid = (r < u_h) && (col < u_w);
                             ipt = u_first + r * u_w + col;
                         }
-                        if (valid) { s.ipt = ipt; s.flags = LF_INIT | LF_EV; }
+                        if (valid) { k.ipt = ipt; s.flags = LF_INIT | LF_EV; }
                     }
                     pool_next = min(32, pool_next + __popc(need));
                     need = __ballot_sync(FULL, (s.flags & LF_NEED) != 0);
@@ -1984,6 +1983,17 @@ __global__ void k_flush_mirror(long long n, const double *__restrict__ m, const 
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n * comps) return;
     out[i] = flush_component(m[i], e[i / comps]);
+}
+
+/* integer radius tables of the square-free BLA lookup (bla_r2hi) */
+__global__ void k_bla_r2hi(long long n, const double *__restrict__ r, int *__restrict__ t1,
+                           int *__restrict__ t2)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double v = r[i];
+    t1[i] = bla_r2hi(v, 1.);
+    t2[i] = bla_r2hi(v, 0x1p600);
 }
 
 /* Interleaved orbit table of k_perturb_m2_v2 (HBM-bound, once per frame):

@@ -75,6 +75,8 @@ struct FrameDev {
      * of Z + z below 2^k with 2^(2k+1) <= Mdiv_sq) */
     const double *T2;
     unsigned esc_hi;
+    /* high words of fl((r up)^2) per BLA node, up = 1 and 2^600 (bla_r2hi) */
+    const int *r2hi, *r2hi_up;
 };
 
 struct StdDev {
@@ -311,16 +313,20 @@ FSB_HD double xshift(double m, int shift)
     nf = (fld == 0 || nf < 0) ? 0 : nf;
     return mk64((hi & (int)0x800fffff) | (nf << 20), lo32(m));
 }
-FSB_HD XC xr_lin(C A, XC z, C B, XC c)
+/* p 2^pe + q 2^qe: the aligned Xrange addition of two mantissa pairs */
+FSB_HD XC xr_sum2(C p, int pe, C q, int qe)
 {
-    const C p = A * z.m, q = B * c.m;
     const int fp = cexp_field(p), fq = cexp_field(q);
-    const int ep = z.e + (fp - 1023), eq = c.e + (fq - 1023);
+    const int ep = pe + (fp - 1023), eq = qe + (fq - 1023);
     int e = imax(ep, eq);
     if (fp == 0) e = eq;              /* a zero product does not set the exponent */
     if (fq == 0) e = ep;
     const int sp = (1023 - fp) - (e - ep), sq = (1023 - fq) - (e - eq);
     return mkXC(mkC(xshift(p.re, sp) + xshift(q.re, sq), xshift(p.im, sp) + xshift(q.im, sq)), e);
+}
+FSB_HD XC xr_lin(C A, XC z, C B, XC c)
+{
+    return xr_sum2(A * z.m, z.e, B * c.m, c.e);
 }
 FSB_HD XC xr_mulc(C A, XC d)
 {
@@ -411,6 +417,86 @@ FSB_HD int ref_bla_get2(const double *__restrict__ r_bla, int stages_bla, C zn, 
     return 8;
 }
 
+#if defined(__CUDA_ARCH__) && defined(FSB_NOINLINE_EXACT)
+#define FSB_COLD_FN static __device__ __noinline__
+#else
+#define FSB_COLD_FN static inline
+#endif
+/* the rare exact decisions, out of line */
+FSB_COLD_FN bool abs_lt_exact(C z, double r) { return cabs_rn(z) < r; }
+FSB_COLD_FN int ref_bla_get2_cold(const double *r_bla, int stages_bla, C zn, int w, int first_invalid,
+                                  int *index_out)
+{
+    int ib = 0;
+    const int step = ref_bla_get2(r_bla, stages_bla, zn, w, first_invalid, ib);
+    *index_out = ib;
+    return step;
+}
+
+/* Table entry of the integer form of that comparison: the high word of
+ * fl(fl(r up)^2), or -2 when `|z| < r` can never hold (r = 0, negative or NaN:
+ * the difference with any high word of s, which is >= 0, is then <= -2).  One int32 per BLA node and scale: the lookup then
+ * costs an integer load, a subtraction and two compares per stage. */
+#define FSB_R2HI_NEVER (-2)
+FSB_HD int bla_r2hi(double r, double up)
+{
+    if (!(r > 0.)) return FSB_R2HI_NEVER;
+    const double ru = mul_rn(r, up);
+    return hi32(mul_rn(ru, ru));
+}
+
+/* perturbation.py:2116-2170 with the lookup order of ref_bla_get (lowest
+ * stored stage first) and the square-free comparison above, on the integer
+ * tables.  The per-component pre-test `|re|, |im| < r3` of ref_bla_get is
+ * implied by |z| < r3 and left out. */
+FSB_HD int ref_bla_get3_(const FrameDev &f, C zn, int w, int &index_out);
+FSB_HD int ref_bla_get3(const FrameDev &f, C zn, int w, int &index_out)
+{
+#if defined(FSB_DEBUG_BLA) && !defined(__CUDA_ARCH__)
+    int i2 = -1, i3 = -1;
+    const int s2 = ref_bla_get2(f.r_bla, f.stages_bla, zn, w, f.first_invalid_i, i2);
+    const int s3 = ref_bla_get3_(f, zn, w, i3);
+    if (s2 != s3 || (s2 && i2 != i3)) printf("BLA mismatch w %d z (%g, %g): %d/%d vs %d/%d\n", w, zn.re, zn.im, s2, i2, s3, i3);
+    index_out = i3;
+    return s3;
+#else
+    return ref_bla_get3_(f, zn, w, index_out);
+#endif
+}
+FSB_HD int ref_bla_get3_(const FrameDev &f, C zn, int w, int &index_out)
+{
+    const int it = w >> 3;
+    const int invalid_step = f.first_invalid_i - w;
+    if (invalid_step <= 8 || f.stages_bla < 4) return 0;
+    const int base = 2 * it - 1;
+    const double a = fabs(zn.re), b = fabs(zn.im);
+    const int ea = imax(expfield(a), expfield(b));
+    if (ea > 1023 + 500) {
+        int ib = 0;
+        const int step = ref_bla_get2_cold(f.r_bla, f.stages_bla, zn, w, f.first_invalid_i, &ib);
+        index_out = ib;
+        return step;
+    }
+    const bool tiny = ea < 1023 - 500;
+    const int *__restrict__ tab = tiny ? f.r2hi_up : f.r2hi;
+    const double up = tiny ? 0x1p600 : 1.;
+    const double au = mul_rn(a, up), bu = mul_rn(b, up);
+    /* s >= 0 or NaN (sign stripped, clamped: above every entry, no overflow below) */
+    const int hs = imin(hi32(add_rn(mul_rn(au, au), mul_rn(bu, bu))) & 0x7fffffff, 0x7ff80000);
+    const int d3 = ldg_(tab + base + 1) - hs;
+    if (d3 < 2 && (d3 <= -2 || !abs_lt_exact(zn, ldg_(f.r_bla + base + 1)))) return 0;
+    int stages = f.stages_bla - 1;
+    if (it != 0) stages = imin(stages, 3 + (ffs_(it) - 1));
+    stages = imin(stages, 31 - clz_(invalid_step - 1));   /* largest stg with 2^stg < invalid_step */
+    for (int stg = stages; stg > 3; stg--) {
+        const int ib = base + (1 << (stg - 3));
+        const int d = ldg_(tab + ib) - hs;
+        if (d >= 2 || (d > -2 && abs_lt_exact(zn, ldg_(f.r_bla + ib)))) { index_out = ib; return 1 << stg; }
+    }
+    index_out = base + 1;
+    return 8;
+}
+
 /* ======================================================================== */
 /* Lane state machine of the persistent holomorphic kernel (k_perturb_m2_v2).
  *
@@ -454,22 +540,40 @@ enum : unsigned {
  * (bounds the replay after a failed range guard) */
 #define FSB_XR_STRETCH 64
 
-struct LaneM2 {
+/* Rare paths of the event section.  Measured: making them real calls on the
+ * device (__noinline__, the lane passed through a copy) puts the lane in local
+ * memory -- 2.4 GB of DRAM writes per 4K frame, config 2 12.0 -> 15.9 ms -- so
+ * they stay inlined unless FSB_OUTLINE_COLD is defined. */
+#if defined(__CUDA_ARCH__) && defined(FSB_OUTLINE_COLD)
+#define FSB_COLD static __device__ __noinline__
+#define FSB_COLD_CALL(s, call) do { LaneM2 t_ = (s); call; (s) = t_; } while (0)
+#else
+#define FSB_COLD FSB_HD
+#define FSB_COLD_CALL(s, call) do { LaneM2 &t_ = (s); call; } while (0)
+#endif
+
+struct LaneM2 {        /* the part of a lane that lives in registers */
     double zr, zi;     /* delta z: the value (fp64 lane) or the Xrange mantissa (LF_SLOW) */
     double dr, di;     /* delta z' likewise                                            */
     double cr, ci;     /* c, standard                                                  */
     double Zr, Zi;     /* Zn[w] (event section only)                                   */
     int w, wlim, winc; /* reference index; the hot loop leaves when w >= wlim; 0 for parked lanes */
     unsigned flags;
+};
+/* state at the entry of the hot loop (Xrange frames) */
+struct LaneCk { double zr, zi, dr, di; int w; };
+/* the part only the event section touches: shared memory on the device (the
+ * register budget decides how many warps hide the latencies of the event
+ * section: 90 -> 7x registers per thread) */
+struct LaneCold {
+    XC c_xr;
     int ze, de;        /* LF_SLOW: exponents of (zr, zi) and (dr, di)                   */
     int nbase;         /* n_iter - w                                                   */
     int ipt;
     unsigned p_skip, p_bla, p_reb, p_slow;
-    XC c_xr;
-    bool c_tiny;
+    int c_tiny;
+    LaneCk ck;
 };
-/* state at the entry of the hot loop (Xrange frames; shared memory on the device) */
-struct LaneCk { double zr, zi, dr, di; int w; };
 
 /* one full iteration on doubles (mandelbrot_M2.py:607-622); (er, ei) is the
  * table's derivative entry FSB_TSCALE * dZndc[w] (0 after a rebase).
@@ -508,7 +612,6 @@ FSB_HD void lane_park(LaneM2 &s, unsigned flags)
     s.zr = s.zi = s.dr = s.di = s.cr = s.ci = 0.;
     s.Zr = s.Zi = 0.;
     s.w = 0; s.winc = 0; s.wlim = 0x7fffffff;
-    s.ze = s.de = 0;
     s.flags = flags;
 }
 
@@ -516,11 +619,11 @@ FSB_HD void lane_park(LaneM2 &s, unsigned flags)
  * iterations, BLA steps, rebases, sum of stop_iter, fp64-lane iterations) go
  * to the caller's slots cnt[k * cstride]: one private slot set per thread. */
 template <bool XR, bool DZNDC>
-FSB_HD void lane_finish(const FrameDev &f, LaneM2 &s, int stop, double *Z, int *U,
+FSB_COLD void lane_finish(const FrameDev &f, LaneM2 &s, LaneCold &k, int stop, double *Z, int *U,
                         signed char *stop_reason, int *stop_iter, unsigned long long *cnt,
                         int cstride)
 {
-    const int w = s.w, ipt = s.ipt;
+    const int w = s.w, ipt = k.ipt;
     U[ipt] = w;
     C zn, dz = mkC(0., 0.);
     const C Zw = ldC(f.Zn, w);
@@ -532,50 +635,163 @@ FSB_HD void lane_finish(const FrameDev &f, LaneM2 &s, int stop, double *Z, int *
             else dz = to_std(to_xr(mkC(s.dr, s.di)) + mkXC(ldC(f.dZndc, w), ldg_(f.dZndc_e + w)));
         }
     } else if (XR) {
-        zn = to_std(mkXC(mkC(s.zr, s.zi), s.ze)) + Zw;
-        if (DZNDC) dz = to_std(mkXC(mkC(s.dr, s.di), s.de) + mkXC(ldC(f.dZndc, w), ldg_(f.dZndc_e + w)));
+        zn = to_std(mkXC(mkC(s.zr, s.zi), k.ze)) + Zw;
+        if (DZNDC) dz = to_std(mkXC(mkC(s.dr, s.di), k.de) + mkXC(ldC(f.dZndc, w), ldg_(f.dZndc_e + w)));
     } else {
         zn = mkC(s.zr, s.zi) + Zw;
         if (DZNDC) dz = mkC(s.dr, s.di) + ldC(f.dZndc, w);
     }
     stC(Z, 0, f.zstride, ipt, zn);
     if (DZNDC) stC(Z, 1, f.zstride, ipt, dz);
-    const int n_iter = s.nbase + w;
+    const int n_iter = k.nbase + w;
     stop_reason[ipt] = (signed char)stop;
     stop_iter[ipt] = n_iter;
-    const unsigned p_exec = (unsigned)n_iter - s.p_skip;
+    const unsigned p_exec = (unsigned)n_iter - k.p_skip;
     cnt[0] += p_exec;
-    cnt[cstride] += s.p_bla;
-    cnt[2 * cstride] += s.p_reb;
+    cnt[cstride] += k.p_bla;
+    cnt[2 * cstride] += k.p_reb;
     cnt[3 * cstride] += (unsigned long long)n_iter;
-    if (XR) cnt[4 * cstride] += p_exec - s.p_slow;
+    if (XR) cnt[4 * cstride] += p_exec - k.p_slow;
     lane_park(s, LF_NEED | LF_EV);
 }
 
 /* Xrange state <-> fp64 lane */
-template <bool DZNDC> FSB_HD void lane_to_slow(LaneM2 &s)
+template <bool DZNDC> FSB_HD void lane_to_slow(LaneM2 &s, LaneCold &k)
 {
     const XC zx = to_xr(mkC(s.zr, s.zi));
-    s.zr = zx.m.re; s.zi = zx.m.im; s.ze = zx.e;
+    s.zr = zx.m.re; s.zi = zx.m.im; k.ze = zx.e;
     if (DZNDC) {
         const XC dx = to_xr(mkC(s.dr, s.di));
-        s.dr = dx.m.re; s.di = dx.m.im; s.de = dx.e;
+        s.dr = dx.m.re; s.di = dx.m.im; k.de = dx.e;
     }
     s.flags = (s.flags | LF_SLOW) & ~LF_CAREFUL;
 }
 /* back to the fp64 lane when every live component is in the safe range;
  * zstd = to_std of the Xrange z */
-template <bool DZNDC> FSB_HD void lane_try_fast(LaneM2 &s, C zstd)
+template <bool DZNDC> FSB_HD void lane_try_fast(LaneM2 &s, LaneCold &k, C zstd)
 {
     if (!in_fast_range(zstd)) return;
     C dstd = mkC(0., 0.);
     if (DZNDC) {
-        dstd = to_std(mkXC(mkC(s.dr, s.di), s.de));
+        dstd = to_std(mkXC(mkC(s.dr, s.di), k.de));
         if (!in_fast_range(dstd)) return;
     }
-    s.zr = zstd.re; s.zi = zstd.im; s.ze = 0;
-    if (DZNDC) { s.dr = dstd.re; s.di = dstd.im; s.de = 0; }
+    s.zr = zstd.re; s.zi = zstd.im; k.ze = 0;
+    if (DZNDC) { s.dr = dstd.re; s.di = dstd.im; k.de = 0; }
     s.flags &= ~LF_SLOW;
+}
+
+/* a new pixel, perturbation.py:1026-1031, 2214-2230 */
+template <bool XR>
+FSB_COLD void lane_init(const FrameDev &f, LaneM2 &s, LaneCold &k, const C *c_pix)
+{
+    const C pix = ldC(c_pix, k.ipt);
+    const double x1 = f.lin_mat[0] * pix.re + f.lin_mat[1] * pix.im;
+    const double y1 = f.lin_mat[2] * pix.re + f.lin_mat[3] * pix.im;
+    k.c_xr = (mkXF(f.lin_scale, f.lin_scale_e) * mkC(x1, y1))
+             + mkXC(mkC(f.drift[0], f.drift[1]), f.drift_e[0]);
+    const C c = to_std(k.c_xr);
+    s.cr = c.re; s.ci = c.im;
+    /* |c| < 2^-1600: lets the fp64 lane of an Xrange frame take BLA steps */
+    k.c_tiny = XR && (k.c_xr.e + cexp_field(k.c_xr.m) - 1023 < -1600);
+    s.zr = s.zi = s.dr = s.di = 0.;
+    k.ze = k.de = 0;
+    s.w = 0; s.winc = 1; k.nbase = 0;
+    const C Z0 = ldC(f.Zn, 0);
+    s.Zr = Z0.re; s.Zi = Z0.im;
+    k.p_skip = k.p_bla = k.p_reb = k.p_slow = 0;
+    s.flags = LF_EV | LF_DYN | (XR ? LF_SLOW : 0u);
+}
+
+/* rebase: reference diverging (:1283-1313, `rebase`) or dynamic glitch
+ * (:1317-1372); zn = the standard delta z, ZZ = zn + Zn[w] */
+template <bool XR, bool DZNDC>
+FSB_COLD void lane_rebase(const FrameDev &f, LaneM2 &s, LaneCold &k, C zn, C ZZ, bool rebase)
+{
+    const C *Zn = f.Zn;
+    const bool has_xr = XR && f.n_xr_i > 0;
+    const bool slow = XR && (s.flags & LF_SLOW);
+    const C ref_next = mkC(s.Zr, s.Zi);
+#define L_DZNDC_X(i) mkXC(ldC(f.dZndc, (i)), ldg_(f.dZndc_e + (i)))
+#define L_REF_X(k) mkXC(ldC(f.ref_xr, (k)), ldg_(f.ref_xr_e + (k)))
+#define L_LOAD_Z() do { const C Zw_ = ldC(Zn, s.w); s.Zr = Zw_.re; s.Zi = Zw_.im; } while (0)
+    bool do_rebase = true, fast_rebase = false;
+    XC ZZ_xr = mkXC(mkC(0., 0.), 0);
+    if (XR && !rebase) {
+        if (!slow && in_fast_range(ZZ)) {
+            /* same comparison on the same correctly rounded values */
+            do_rebase = norm2(ZZ) <= norm2(zn);
+            fast_rebase = true;
+        } else {
+            if (!slow) lane_to_slow<DZNDC>(s, k);
+            int knext = -1;
+            if (has_xr && s.w != 0 && fabs(ref_next.re) < 1.e-300 && fabs(ref_next.im) < 1.e-300)
+                knext = xr_find(f.ref_index_xr, f.n_xr_i, s.w);
+            const XC zx = mkXC(mkC(s.zr, s.zi), k.ze);
+            ZZ_xr = (knext >= 0) ? (zx + L_REF_X(knext)) : (zx + ref_next);
+            do_rebase = xr_le(abs2(ZZ_xr), abs2(zx));
+        }
+    }
+    if (do_rebase) {
+        if (XR && !(s.flags & LF_SLOW) && (fast_rebase || rebase)) {
+            /* rebase in plain fp64; leave the fp64 lane if a result falls
+             * out of the safe range (exact conversion) */
+            C nd = mkC(s.dr, s.di);
+            if (DZNDC) nd = nd + ldC(f.dZndc_std, s.w);
+            if (in_fast_range(ZZ) && (!DZNDC || in_fast_range(nd))) {
+                s.zr = ZZ.re; s.zi = ZZ.im;
+                if (DZNDC) { s.dr = nd.re; s.di = nd.im; }
+            } else {
+                if (DZNDC) {
+                    const XC dx = to_xr(mkC(s.dr, s.di)) + L_DZNDC_X(s.w);
+                    s.dr = dx.m.re; s.di = dx.m.im; k.de = dx.e;
+                }
+                const XC zx = to_xr(ZZ);
+                s.zr = zx.m.re; s.zi = zx.m.im; k.ze = zx.e;
+                s.flags = (s.flags | LF_SLOW) & ~LF_CAREFUL;
+            }
+        } else if (XR) {
+            const XC zx = rebase ? to_xr(ZZ) : ZZ_xr;
+            const C zstd = rebase ? ZZ : to_std(ZZ_xr);
+            s.zr = zx.m.re; s.zi = zx.m.im; k.ze = zx.e;
+            if (DZNDC) {
+                const XC dx = mkXC(mkC(s.dr, s.di), k.de) + L_DZNDC_X(s.w);
+                s.dr = dx.m.re; s.di = dx.m.im; k.de = dx.e;
+            }
+            lane_try_fast<DZNDC>(s, k, zstd);
+        } else {
+            s.zr = ZZ.re; s.zi = ZZ.im;
+            if (DZNDC) {
+                const C nd = mkC(s.dr, s.di) + ldC(f.dZndc, s.w);
+                s.dr = nd.re; s.di = nd.im;
+            }
+        }
+        k.nbase += s.w;
+        s.w = 0;
+        L_LOAD_Z();
+        k.p_reb++;
+    }
+
+#undef L_DZNDC_X
+#undef L_REF_X
+#undef L_LOAD_Z
+}
+
+/* one iteration by the operator chain of numba_xr.py (perturbation.py:1158-1209
+ * in Xrange arithmetic): whatever the fused forms of lane_step do not cover */
+template <bool DZNDC>
+FSB_COLD void lane_slow_generic(const FrameDev &f, LaneM2 &s, LaneCold &k, int kx, bool dyn)
+{
+    const C ref_zn = mkC(s.Zr, s.Zi);
+    const XC ref_x = (kx >= 0) ? mkXC(ldC(f.ref_xr, kx), ldg_(f.ref_xr_e + kx)) : to_xr(ref_zn);
+    XC zx = mkXC(mkC(s.zr, s.zi), k.ze);
+    if (DZNDC) {
+        const XC ref_d = dyn ? mkXC(mkC(0., 0.), 0) : mkXC(ldC(f.dZndc, s.w), ldg_(f.dZndc_e + s.w));
+        const XC dx = p_iter_deriv(zx, mkXC(mkC(s.dr, s.di), k.de), ref_x, ref_d);
+        s.dr = dx.m.re; s.di = dx.m.im; k.de = dx.e;
+    }
+    zx = p_iter_zn(zx, ref_x, k.c_xr);
+    s.zr = zx.m.re; s.zi = zx.m.im; k.ze = zx.e;
 }
 
 /* The event section of one lane: runs until the lane is armed for the hot
@@ -583,7 +799,7 @@ template <bool DZNDC> FSB_HD void lane_try_fast(LaneM2 &s, C zstd)
 template <bool XR, bool DZNDC, bool BLA>
 FSB_HD void lane_step(const FrameDev &f, LaneM2 &s, const C *c_pix, double *Z, int *U,
                       signed char *stop_reason, int *stop_iter, unsigned long long *cnt,
-                      int cstride, LaneCk *ck)
+                      int cstride, LaneCold &k)
 {
     const C *Zn = f.Zn;
     const bool has_xr = XR && f.n_xr_i > 0;
@@ -592,44 +808,31 @@ FSB_HD void lane_step(const FrameDev &f, LaneM2 &s, const C *c_pix, double *Z, i
 #define L_LOAD_Z() do { const C Zw_ = ldC(Zn, s.w); s.Zr = Zw_.re; s.Zi = Zw_.im; } while (0)
 
     if (s.flags & LF_INIT) {
-        /* perturbation.py:1026-1031, 2214-2230 */
-        const C pix = ldC(c_pix, s.ipt);
-        const double x1 = f.lin_mat[0] * pix.re + f.lin_mat[1] * pix.im;
-        const double y1 = f.lin_mat[2] * pix.re + f.lin_mat[3] * pix.im;
-        s.c_xr = (mkXF(f.lin_scale, f.lin_scale_e) * mkC(x1, y1))
-                 + mkXC(mkC(f.drift[0], f.drift[1]), f.drift_e[0]);
-        const C c = to_std(s.c_xr);
-        s.cr = c.re; s.ci = c.im;
-        /* |c| < 2^-1600: lets the fp64 lane of an Xrange frame take BLA steps */
-        s.c_tiny = XR && (s.c_xr.e + cexp_field(s.c_xr.m) - 1023 < -1600);
-        s.zr = s.zi = s.dr = s.di = 0.;
-        s.ze = s.de = 0;
-        s.w = 0; s.winc = 1; s.nbase = 0;
-        L_LOAD_Z();
-        s.p_skip = s.p_bla = s.p_reb = s.p_slow = 0;
-        s.flags = LF_EV | LF_DYN | (XR ? LF_SLOW : 0u);
+        FSB_COLD_CALL(s, (lane_init<XR>(f, t_, k, c_pix)));
     } else if (XR && (s.flags & LF_BAD)) {
         /* the range guard failed somewhere after the checkpoint: back to it, then
          * one guarded iteration at a time until the failing one is reached */
-        s.zr = ck->zr; s.zi = ck->zi; s.dr = ck->dr; s.di = ck->di; s.w = ck->w;
+        s.zr = k.ck.zr; s.zi = k.ck.zi; s.dr = k.ck.dr; s.di = k.ck.di; s.w = k.ck.w;
         L_LOAD_Z();
         s.flags = (s.flags & ~LF_BAD) | LF_CAREFUL;
     }
 
+    /* zc: the standard value of delta z, kept along (a lane enters on the fp64
+     * lane, or with z = 0) */
+    C zc = mkC(s.zr, s.zi);
     for (;;) {
         if (s.flags & LF_ITER) {
             s.flags &= ~LF_ITER;
             /* ---- stop tests of the iteration just done, :1218-1279 ---- */
-            if (s.nbase + s.w >= f.max_iter_i) {
-                lane_finish<XR, DZNDC>(f, s, 0, Z, U, stop_reason, stop_iter, cnt, cstride);
+            if (k.nbase + s.w >= f.max_iter_i) {
+                FSB_COLD_CALL(s, (lane_finish<XR, DZNDC>(f, t_, k, 0, Z, U, stop_reason, stop_iter, cnt, cstride)));
                 return;
             }
-            const bool slow = XR && (s.flags & LF_SLOW);
-            const C zn = slow ? to_std(mkXC(mkC(s.zr, s.zi), s.ze)) : mkC(s.zr, s.zi);
+            const C zn = zc;
             const C ref_next = mkC(s.Zr, s.Zi);
             const C ZZ = zn + ref_next;
             if (norm2(ZZ) > f.Mdiv_sq) {
-                lane_finish<XR, DZNDC>(f, s, 1, Z, U, stop_reason, stop_iter, cnt, cstride);
+                FSB_COLD_CALL(s, (lane_finish<XR, DZNDC>(f, t_, k, 1, Z, U, stop_reason, stop_iter, cnt, cstride)));
                 return;
             }
             /* ---- rebase: reference diverging (:1283-1313) or dynamic glitch
@@ -642,62 +845,8 @@ FSB_HD void lane_step(const FrameDev &f, LaneM2 &s, const C *c_pix, double *Z, i
                 go = dyn;
             }
             if (go) {
-                bool do_rebase = true, fast_rebase = false;
-                XC ZZ_xr = mkXC(mkC(0., 0.), 0);
-                if (XR && !rebase) {
-                    if (!slow && in_fast_range(ZZ)) {
-                        /* same comparison on the same correctly rounded values */
-                        do_rebase = norm2(ZZ) <= norm2(zn);
-                        fast_rebase = true;
-                    } else {
-                        if (!slow) lane_to_slow<DZNDC>(s);
-                        int knext = -1;
-                        if (has_xr && s.w != 0 && fabs(ref_next.re) < 1.e-300 && fabs(ref_next.im) < 1.e-300)
-                            knext = xr_find(f.ref_index_xr, f.n_xr_i, s.w);
-                        const XC zx = mkXC(mkC(s.zr, s.zi), s.ze);
-                        ZZ_xr = (knext >= 0) ? (zx + L_REF_X(knext)) : (zx + ref_next);
-                        do_rebase = xr_le(abs2(ZZ_xr), abs2(zx));
-                    }
-                }
-                if (do_rebase) {
-                    if (XR && !(s.flags & LF_SLOW) && (fast_rebase || rebase)) {
-                        /* rebase in plain fp64; leave the fp64 lane if a result falls
-                         * out of the safe range (exact conversion) */
-                        C nd = mkC(s.dr, s.di);
-                        if (DZNDC) nd = nd + ldC(f.dZndc_std, s.w);
-                        if (in_fast_range(ZZ) && (!DZNDC || in_fast_range(nd))) {
-                            s.zr = ZZ.re; s.zi = ZZ.im;
-                            if (DZNDC) { s.dr = nd.re; s.di = nd.im; }
-                        } else {
-                            if (DZNDC) {
-                                const XC dx = to_xr(mkC(s.dr, s.di)) + L_DZNDC_X(s.w);
-                                s.dr = dx.m.re; s.di = dx.m.im; s.de = dx.e;
-                            }
-                            const XC zx = to_xr(ZZ);
-                            s.zr = zx.m.re; s.zi = zx.m.im; s.ze = zx.e;
-                            s.flags = (s.flags | LF_SLOW) & ~LF_CAREFUL;
-                        }
-                    } else if (XR) {
-                        const XC zx = rebase ? to_xr(ZZ) : ZZ_xr;
-                        const C zstd = rebase ? ZZ : to_std(ZZ_xr);
-                        s.zr = zx.m.re; s.zi = zx.m.im; s.ze = zx.e;
-                        if (DZNDC) {
-                            const XC dx = mkXC(mkC(s.dr, s.di), s.de) + L_DZNDC_X(s.w);
-                            s.dr = dx.m.re; s.di = dx.m.im; s.de = dx.e;
-                        }
-                        lane_try_fast<DZNDC>(s, zstd);
-                    } else {
-                        s.zr = ZZ.re; s.zi = ZZ.im;
-                        if (DZNDC) {
-                            const C nd = mkC(s.dr, s.di) + ldC(f.dZndc, s.w);
-                            s.dr = nd.re; s.di = nd.im;
-                        }
-                    }
-                    s.nbase += s.w;
-                    s.w = 0;
-                    L_LOAD_Z();
-                    s.p_reb++;
-                }
+                FSB_COLD_CALL(s, (lane_rebase<XR, DZNDC>(f, t_, k, zn, ZZ, rebase)));
+                zc = (XR && (s.flags & LF_SLOW)) ? to_std_small(mkXC(mkC(s.zr, s.zi), k.ze)) : mkC(s.zr, s.zi);
             }
         }
 
@@ -705,23 +854,27 @@ FSB_HD void lane_step(const FrameDev &f, LaneM2 &s, const C *c_pix, double *Z, i
         if (BLA) {
             while ((s.w & 7) == 0) {
                 const bool slow = XR && (s.flags & LF_SLOW);
-                const C zn = slow ? to_std_small(mkXC(mkC(s.zr, s.zi), s.ze)) : mkC(s.zr, s.zi);
+                const C zn = zc;
                 int ib = 0;
+                #ifdef FSB_BLA_LOOKUP2
                 const int step = ref_bla_get2(f.r_bla, f.stages_bla, zn, s.w, f.first_invalid_i, ib);
+#else
+                const int step = ref_bla_get3(f, zn, s.w, ib);
+#endif
                 if (step == 0) break;
                 const C *M = reinterpret_cast<const C *>(f.M_bla);
                 const C A = ldC(M, 2 * ib), B = ldC(M, 2 * ib + 1);
-                s.p_skip += (unsigned)step;
+                k.p_skip += (unsigned)step;
                 s.w += step;                       /* n_iter = nbase + w moves with it */
                 L_LOAD_Z();
-                s.p_bla++;
+                k.p_bla++;
                 if (!XR) {
                     const C nz = A * zn + B * mkC(s.cr, s.ci);
-                    s.zr = nz.re; s.zi = nz.im;
+                    s.zr = nz.re; s.zi = nz.im; zc = nz;
                     if (DZNDC) { const C nd = A * mkC(s.dr, s.di); s.dr = nd.re; s.di = nd.im; }
                     continue;
                 }
-                if (!slow && s.c_tiny) {
+                if (!slow && k.c_tiny) {
                     /* fp64 form of the step.  With every component of A z a normal
                      * double >= 2^-460 and |B c| <= 2^1025 |c| < 2^-575, the B c term is
                      * far below half an ulp of the sums it enters: fl(A z) IS the
@@ -732,19 +885,20 @@ FSB_HD void lane_step(const FrameDev &f, LaneM2 &s, const C *c_pix, double *Z, i
                     if (DZNDC) nd = A * nd;
                     if (in_fast_range(nz) && (!DZNDC || in_fast_range(nd))
                         && expfield(B.re) != 0x7ff && expfield(B.im) != 0x7ff) {
-                        s.zr = nz.re; s.zi = nz.im;
+                        s.zr = nz.re; s.zi = nz.im; zc = nz;
                         if (DZNDC) { s.dr = nd.re; s.di = nd.im; }
                         continue;
                     }
                 }
-                if (!slow) lane_to_slow<DZNDC>(s);      /* B * c needs the exact c */
-                const XC zx = xr_lin(A, mkXC(mkC(s.zr, s.zi), s.ze), B, s.c_xr);
-                s.zr = zx.m.re; s.zi = zx.m.im; s.ze = zx.e;
+                if (!slow) lane_to_slow<DZNDC>(s, k);      /* B * c needs the exact c */
+                const XC zx = xr_lin(A, mkXC(mkC(s.zr, s.zi), k.ze), B, k.c_xr);
+                s.zr = zx.m.re; s.zi = zx.m.im; k.ze = zx.e;
                 if (DZNDC) {
-                    const XC dx = xr_mulc(A, mkXC(mkC(s.dr, s.di), s.de));
-                    s.dr = dx.m.re; s.di = dx.m.im; s.de = dx.e;
+                    const XC dx = xr_mulc(A, mkXC(mkC(s.dr, s.di), k.de));
+                    s.dr = dx.m.re; s.di = dx.m.im; k.de = dx.e;
                 }
-                lane_try_fast<DZNDC>(s, to_std_small(zx));
+                zc = to_std_small(zx);
+                lane_try_fast<DZNDC>(s, k, zc);
             }
         }
 
@@ -755,20 +909,51 @@ FSB_HD void lane_step(const FrameDev &f, LaneM2 &s, const C *c_pix, double *Z, i
         const bool dyn = (s.flags & LF_DYN) != 0;
         if (XR && (s.flags & LF_SLOW)) {
             const C ref_zn = mkC(s.Zr, s.Zi);
-            int k = -1;
+            int kx = -1;
             if (has_xr && s.w != 0 && fabs(ref_zn.re) < 1.e-300 && fabs(ref_zn.im) < 1.e-300)
-                k = xr_find(f.ref_index_xr, f.n_xr_i, s.w);
-            const XC ref_x = (k >= 0) ? L_REF_X(k) : to_xr(ref_zn);
-            XC zx = mkXC(mkC(s.zr, s.zi), s.ze);
-            if (DZNDC) {
-                const XC ref_d = dyn ? mkXC(mkC(0., 0.), 0) : L_DZNDC_X(s.w);
-                const XC dx = p_iter_deriv(zx, mkXC(mkC(s.dr, s.di), s.de), ref_x, ref_d);
-                s.dr = dx.m.re; s.di = dx.m.im; s.de = dx.e;
+                kx = xr_find(f.ref_index_xr, f.n_xr_i, s.w);
+            XC zx = mkXC(mkC(s.zr, s.zi), k.ze);
+            /* Fused exact forms of the two model formulas for a tiny z (the
+             * iterations that follow a rebase onto a sub-1e-138 value, before the first
+             * BLA node applies -- 6 % of the iterations of a 1e-1000 frame but, through
+             * the operator chain, a third of its instructions):
+             *   form 1  |z| < 2^-60 of either part of Z (both normal): z + 2 Z and Z + z
+             *           round to 2 Z and Z, so z' = (2 Z) z + c, z'' = 2 (Z dz + Zd z);
+             *   form 2  Z = 0 (index 0): z' = z z + c, z'' = 2 (z dz + Zd z).
+             * Same products, same aligned additions and same roundings as the chain
+             * of numba_xr operators (only the normalisations in between are skipped:
+             * an Xrange value does not depend on its mantissa / exponent split). */
+            int form = 0;
+#ifndef FSB_NO_FUSED_ITER
+            if (kx < 0) {
+                const int fzr = expfield(ref_zn.re), fzi = expfield(ref_zn.im);
+                const int Ez = k.ze + imax(expfield(s.zr), expfield(s.zi)) - 1023;
+                if (ref_zn.re == 0. && ref_zn.im == 0.) form = 2;
+                else if (fzr >= 64 && fzi >= 64 && fzr < 1600 && fzi < 1600
+                         && fzr - fzi <= 500 && fzi - fzr <= 500
+                         && Ez + 60 <= imin(fzr, fzi) - 1023) form = 1;
             }
-            zx = p_iter_zn(zx, ref_x, s.c_xr);
-            s.zr = zx.m.re; s.zi = zx.m.im; s.ze = zx.e;
-            s.p_slow++;
-            lane_try_fast<DZNDC>(s, to_std(zx));
+#endif
+            if (form != 0) {
+                const C zm = zx.m;
+                const C Az = (form == 1) ? mkC(2. * ref_zn.re, 2. * ref_zn.im) : zm;
+                const C Ad = (form == 1) ? ref_zn : zm;
+                if (DZNDC) {
+                    const XC D = dyn ? mkXC(mkC(0., 0.), 0) : L_DZNDC_X(s.w);
+                    XC dx = xr_sum2(Ad * mkC(s.dr, s.di), (form == 1) ? k.de : k.ze + k.de,
+                                    D.m * zm, D.e + k.ze);
+                    dx.e += 1;                                   /* 2. * ( ... ) */
+                    s.dr = dx.m.re; s.di = dx.m.im; k.de = dx.e;
+                }
+                zx = xr_sum2(Az * zm, (form == 1) ? k.ze : 2 * k.ze, k.c_xr.m, k.c_xr.e);
+                s.zr = zx.m.re; s.zi = zx.m.im; k.ze = zx.e;
+            } else {
+                FSB_COLD_CALL(s, (lane_slow_generic<DZNDC>(f, t_, k, kx, dyn)));
+                zx = mkXC(mkC(s.zr, s.zi), k.ze);
+            }
+            k.p_slow++;
+            zc = to_std_small(zx);
+            lane_try_fast<DZNDC>(s, k, zc);
         } else {
             double er = 0., ei = 0.;
             if (DZNDC && !dyn) {
@@ -780,24 +965,24 @@ FSB_HD void lane_step(const FrameDev &f, LaneM2 &s, const C *c_pix, double *Z, i
                                 nzr, nzi, ndr, ndi);
             if (XR && !(in_fast_range(mkC(nzr, nzi)) && (!DZNDC || in_fast_range(mkC(ndr, ndi))))) {
                 /* out of the safe range: redo this iteration in Xrange arithmetic */
-                lane_to_slow<DZNDC>(s);
+                lane_to_slow<DZNDC>(s, k);
                 continue;
             }
-            s.zr = nzr; s.zi = nzi;
+            s.zr = nzr; s.zi = nzi; zc = mkC(nzr, nzi);
             if (DZNDC) { s.dr = ndr; s.di = ndi; }
         }
         s.w += 1;
         L_LOAD_Z();
         s.flags |= LF_ITER;
         /* (a replay always meets its failing iteration; this bound is a safety net) */
-        if (XR && (s.flags & LF_CAREFUL) && s.w > ck->w + FSB_XR_STRETCH) s.flags &= ~LF_CAREFUL;
+        if (XR && (s.flags & LF_CAREFUL) && s.w > k.ck.w + FSB_XR_STRETCH) s.flags &= ~LF_CAREFUL;
     }
 
     /* ---- arm the hot loop ---- */
-    int wl = imin(f.ref_div_m1_i, f.max_iter_i - s.nbase);
+    int wl = imin(f.ref_div_m1_i, f.max_iter_i - k.nbase);
     if (XR) {
         wl = imin(wl, s.w + FSB_XR_STRETCH);
-        ck->zr = s.zr; ck->zi = s.zi; ck->dr = s.dr; ck->di = s.di; ck->w = s.w;
+        k.ck.zr = s.zr; k.ck.zi = s.zi; k.ck.dr = s.dr; k.ck.di = s.di; k.ck.w = s.w;
     }
     s.wlim = wl;
     s.flags &= ~LF_EV;

@@ -62,14 +62,14 @@ static void run(const FrameDev &f, int64_t npts, const C *c_pix, double *Z, int3
     const double *T2 = f.T2;
     for (int64_t ipt = 0; ipt < npts; ipt++) {
         LaneM2 s;
-        LaneCk ck;
+        LaneCold k;
         memset(&s, 0, sizeof s);
-        memset(&ck, 0, sizeof ck);
+        memset(&k, 0, sizeof k);
         lane_park(s, 0u);
-        s.ipt = (int)ipt;
+        k.ipt = (int)ipt;
         s.flags = LF_INIT | LF_EV;
         for (;;) {
-            lane_step<XR, DZNDC, BLA>(f, s, c_pix, Z, U, (signed char *)sr, si, cnt, 1, &ck);
+            lane_step<XR, DZNDC, BLA>(f, s, c_pix, Z, U, (signed char *)sr, si, cnt, 1, k);
             cnt[6]++;
             if (s.flags & LF_NEED) break;
             int code;
@@ -140,6 +140,16 @@ extern "C" int fsb_emul_perturb_m2(const emul_frame *e, int64_t npts, const doub
     f.zstride = npts;
     f.esc_hi = esc_hi_of(f.Mdiv_sq);
     const bool bla = e->bla_activated != 0 && e->stages_bla > 3 && e->bla_len > 0;
+    std::vector<int> r2hi;
+    if (bla) {                      /* as k_bla_r2hi */
+        r2hi.resize((size_t)(2 * e->bla_len));
+        for (int64_t i = 0; i < e->bla_len; i++) {
+            r2hi[(size_t)i] = bla_r2hi(e->r_bla[i], 1.);
+            r2hi[(size_t)(e->bla_len + i)] = bla_r2hi(e->r_bla[i], 0x1p600);
+        }
+        f.r2hi = r2hi.data();
+        f.r2hi_up = r2hi.data() + e->bla_len;
+    }
     /* interleaved orbit table, as k_build_t2 */
     const int64_t n_rec = L + 16;
     std::vector<double> T2((size_t)n_rec * 8, 0.);
