@@ -1466,24 +1466,30 @@ int fsb_frame_create(const fsb_frame_desc *desc, fsb_frame **out)
         v.r2hi_up = t + v.bla_len;
     }
     if (f->v2) {
-        const long long n_rec = L + 16;
-        double4 *t2 = nullptr;
-        void *p = nullptr;
-        if (pool_alloc(&p, (size_t)(n_rec * 64)) != cudaSuccess) {
+        const long long n_rec = L + 16, n_h3 = L / 8 + 4;
+        void *p = nullptr, *ph = nullptr;
+        if (pool_alloc(&p, (size_t)(n_rec * 32)) != cudaSuccess
+            || (f->owned.push_back(p), pool_alloc(&ph, (size_t)(n_h3 * 4))) != cudaSuccess) {
             fsb_frame_destroy(f);
             return fail(-1, "out of device memory for the orbit table (%lld records)", n_rec);
         }
-        f->owned.push_back(p);
-        t2 = (double4 *)p;
+        f->owned.push_back(ph);
         const C *dsrc = d.calc_dzndc ? (d.xr_detect ? v.dZndc_std : v.dZndc) : nullptr;
-        k_build_t2<<<(int)((n_rec + 255) / 256), 256>>>(
-            n_rec, v.Zn, L + 1, dsrc, L + 1, FSB_TSCALE,
-            (f->bla_on && v.stages_bla >= 4) ? v.r_bla : nullptr, v.first_invalid_i, t2);
+        k_build_t2<<<(int)((n_rec + 255) / 256), 256>>>(n_rec, v.Zn, L + 1, dsrc, L + 1, FSB_TSCALE,
+                                                          (double4 *)p);
+        /* a lookup needs its leaf: indices 8 j with j < bla_len / 2 */
+        const bool bla = f->bla_on && v.stages_bla >= 4;
+        long long n_leaf = bla ? v.bla_len / 2 : 0;
+        if (n_leaf > n_h3) n_leaf = n_h3;
+        if (cudaMemset(ph, 0, (size_t)(n_h3 * 4)) != cudaSuccess) { fsb_frame_destroy(f); return fail(-1, "memset failed"); }
+        if (n_leaf > 0)
+            k_build_h3<<<(int)((n_leaf + 255) / 256), 256>>>(n_leaf, v.r_bla, v.first_invalid_i, (unsigned *)ph);
         if (cudaGetLastError() != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
             fsb_frame_destroy(f);
             return fail(-1, "orbit table kernel failed");
         }
-        v.T2 = (const double *)t2;
+        v.T2 = (const double *)p;
+        v.h3 = (const unsigned *)ph;
         v.esc_hi = esc_hi_of(v.Mdiv_sq);
     }
 #undef UP

@@ -819,6 +819,7 @@ k_perturb_m2_v2(const __grid_constant__ FrameDev f, long long npts_ll,
     bool exhausted = false;
     const unsigned esc_hi = f.esc_hi;
     const double4 *__restrict__ T2 = reinterpret_cast<const double4 *>(f.T2);
+    const unsigned *__restrict__ h3tab = f.h3;
     const int n_units = tiling.unit_hi - tiling.unit_lo;
 
     for (;;) {
@@ -879,26 +880,36 @@ k_perturb_m2_v2(const __grid_constant__ FrameDev f, long long npts_ll,
         if (__any_sync(FULL, (s.flags & LF_EV) != 0)) continue;
         if (__all_sync(FULL, (s.flags & LF_DEAD) != 0)) break;
 
-        /* ---------------- hot loop ---------------- */
+        /* ---------------- hot loop ----------------
+         * Two iterations per trip on two register sets, so that Zn[w + 1] of one record
+         * is Zn[w] of the next iteration without a move.  Parked lanes run along on
+         * zeros (winc = 0); a second copy of the loop masks their pre-tests. */
         const bool alive = (s.flags & (LF_DEAD | LF_NEED)) == 0;
-        int code;
-        constexpr int kUnroll = FSB_V2_UNROLL;
-#pragma unroll kUnroll
-        for (;;) {
-            /* the record of index w: {Zn[w+1], k dZndc[w]} {Zn[w], r3(w+1), -} */
-            double t0, t1, t2, t3, Zr, Zi, r3n, pad;
-            const double4 *rec = T2 + 2 * (long long)s.w;
-            asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
-                : "=d"(t0), "=d"(t1), "=d"(t2), "=d"(t3) : "l"(rec));
-            asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4+32];"
-                : "=d"(Zr), "=d"(Zi), "=d"(r3n), "=d"(pad) : "l"(rec));
-            code = m2_hot_iter<XR, DZNDC, BLA>(s, Zr, Zi, t0, t1, t2, t3, r3n, esc_hi, alive);
-            if (__any_sync(FULL, code != 0)) break;
-        }
-        if (code == 1) s.flags |= LF_EV | LF_ITER;
-        else if (code == 2) s.flags |= LF_EV | LF_BAD;
-        const C Zw = ldC(f.Zn, s.w);             /* the event section wants Zn[w] */
-        s.Zr = Zw.re; s.Zi = Zw.im;
+        bool ev, bad;
+        double Zr = s.Zr, Zi = s.Zi;
+#define FSB_LD_REC(R, idx) do { const double4 *rec_ = T2 + (long long)(idx); \
+            asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" \
+                : "=d"(R##0), "=d"(R##1), "=d"(R##2), "=d"(R##3) : "l"(rec_)); } while (0)
+#define FSB_HOT_LOOP(MASK) do { \
+            double ra0, ra1, ra2, ra3, rb0, rb1, rb2, rb3; \
+            for (;;) { \
+                FSB_LD_REC(ra, s.w); \
+                m2_hot_iter<XR, DZNDC, BLA>(s, Zr, Zi, ra0, ra1, ra2, ra3, h3tab, esc_hi, ev, bad); \
+                if (MASK) { ev = ev & alive; bad = bad & alive; } \
+                if (__any_sync(FULL, ev | bad)) { Zr = ra0; Zi = ra1; break; } \
+                FSB_LD_REC(rb, s.w); \
+                m2_hot_iter<XR, DZNDC, BLA>(s, ra0, ra1, rb0, rb1, rb2, rb3, h3tab, esc_hi, ev, bad); \
+                if (MASK) { ev = ev & alive; bad = bad & alive; } \
+                Zr = rb0; Zi = rb1; \
+                if (__any_sync(FULL, ev | bad)) break; \
+            } } while (0)
+        if (__all_sync(FULL, alive)) FSB_HOT_LOOP(false);
+        else FSB_HOT_LOOP(true);
+#undef FSB_HOT_LOOP
+#undef FSB_LD_REC
+        if (XR && bad) s.flags |= LF_EV | LF_BAD;
+        else if (ev) s.flags |= LF_EV | LF_ITER;
+        s.Zr = Zr; s.Zi = Zi;                    /* Zn[w] for the event section */
     }
     __syncthreads();
     if (threadIdx.x < 5) {
@@ -1997,26 +2008,30 @@ __global__ void k_bla_r2hi(long long n, const double *__restrict__ r, int *__res
 }
 
 /* Interleaved orbit table of k_perturb_m2_v2 (HBM-bound, once per frame):
- *   T2[i] = {Zn[i+1], scale * d[i]} {Zn[i], r3(i+1), 0}, i in [0, n_rec)
+ *   T2[i] = {Zn[i+1], scale * d[i]}, i in [0, n_rec)
  * Zn holds n_zn valid elements, d (the dZndc path or its fp64 mirror; may be
- * null) n_d; elements past the end read as 0.  r3(j) = r_bla[2 (j >> 3)] when
- * the loop looks the BLA tree up at index j (j a multiple of 8 with more than
- * 8 valid indices ahead, ref_bla_get), else 0. */
+ * null) n_d; elements past the end read as 0. */
 __global__ void k_build_t2(long long n_rec, const C *__restrict__ Zn, long long n_zn,
                            const C *__restrict__ d, long long n_d, double scale,
-                           const double *__restrict__ r_bla, int first_invalid,
                            double4 *__restrict__ T2)
 {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n_rec) return;
     const C z1 = (i + 1 < n_zn) ? ldC(Zn, i + 1) : mkC(0., 0.);
-    const C z0 = (i < n_zn) ? ldC(Zn, i) : mkC(0., 0.);
     const C dd = (d != nullptr && i < n_d) ? ldC(d, i) : mkC(0., 0.);
-    double r3 = 0.;
-    const long long j = i + 1;
-    if (r_bla != nullptr && (j & 7) == 0 && (long long)first_invalid - j > 8) r3 = __ldg(r_bla + 2 * (j >> 3));
-    T2[2 * i] = make_double4(z1.re, z1.im, mul_rn(scale, dd.re), mul_rn(scale, dd.im));
-    T2[2 * i + 1] = make_double4(z0.re, z0.im, r3, 0.);
+    T2[i] = make_double4(z1.re, z1.im, mul_rn(scale, dd.re), mul_rn(scale, dd.im));
+}
+/* h3[j] = high word of r_bla[2 j] (stage-3 radius of index 8 j) when the loop
+ * looks the BLA tree up there (more than 8 valid indices ahead, ref_bla_get),
+ * else 0: the pre-test `|re|, |im| < r3` of the hot loop on high words */
+__global__ void k_build_h3(long long n, const double *__restrict__ r_bla, int first_invalid,
+                           unsigned *__restrict__ h3)
+{
+    const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    unsigned v = 0u;
+    if (r_bla != nullptr && (long long)first_invalid - 8 * j > 8) v = (unsigned)hi32(__ldg(r_bla + 2 * j));
+    h3[j] = v;
 }
 
 /* ======================================================================== */

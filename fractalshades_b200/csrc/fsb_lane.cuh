@@ -67,13 +67,16 @@ struct FrameDev {
     int nexp;
     const double *cbinom;
     int ref_div_m1_i;    /* ref_div_i - 1: the rebase test compares against a constant-bank operand */
-    /* k_perturb_m2_v2: interleaved orbit table, one 64-byte record per index
-     *   T2[i] = {Zn[i+1], FSB_TSCALE * dZndc[i]} {Zn[i], r3(i+1), 0}
-     * (dZndc: the fp64 mirror in Xrange frames; r3(j): stage-3 BLA radius of index j where
-     * the loop looks the tree up, else 0) -- everything an iteration reads, in two 32-byte
-     * loads off one address -- and the exponent bound of the escape pre-test (both parts
-     * of Z + z below 2^k with 2^(2k+1) <= Mdiv_sq) */
+    /* k_perturb_m2_v2: interleaved orbit table, one 32-byte record per index
+     *   T2[i] = {Zn[i+1], FSB_TSCALE * dZndc[i]}
+     * (dZndc: the fp64 mirror in Xrange frames) -- all an iteration reads, in ONE 32-byte
+     * load: the L1 -> register write-back path (32 lanes x bytes per load, broadcast or
+     * not) is what bounds the hot loop next to the FP64 pipe, measured at 90 % with
+     * 64-byte records; h3[j] = high word of the stage-3 BLA radius of index 8 j where the
+     * loop looks the tree up, else 0; and the exponent bound of the escape pre-test (both
+     * parts of Z + z below 2^k with 2^(2k+1) <= Mdiv_sq) */
     const double *T2;
+    const unsigned *h3;
     unsigned esc_hi;
     /* high words of fl((r up)^2) per BLA node, up = 1 and 2^600 (bla_r2hi) */
     const int *r2hi, *r2hi_up;
@@ -463,8 +466,14 @@ FSB_HD int ref_bla_get3(const FrameDev &f, C zn, int w, int &index_out)
     return ref_bla_get3_(f, zn, w, index_out);
 #endif
 }
+#if defined(FSB_DEBUG_WALK) && !defined(__CUDA_ARCH__)
+static long long g_walk_tests = 0, g_walk_lookups = 0, g_walk_pass3 = 0;
+#endif
 FSB_HD int ref_bla_get3_(const FrameDev &f, C zn, int w, int &index_out)
 {
+#if defined(FSB_DEBUG_WALK) && !defined(__CUDA_ARCH__)
+    g_walk_lookups++;
+#endif
     const int it = w >> 3;
     const int invalid_step = f.first_invalid_i - w;
     if (invalid_step <= 8 || f.stages_bla < 4) return 0;
@@ -488,7 +497,13 @@ FSB_HD int ref_bla_get3_(const FrameDev &f, C zn, int w, int &index_out)
     int stages = f.stages_bla - 1;
     if (it != 0) stages = imin(stages, 3 + (ffs_(it) - 1));
     stages = imin(stages, 31 - clz_(invalid_step - 1));   /* largest stg with 2^stg < invalid_step */
+#if defined(FSB_DEBUG_WALK) && !defined(__CUDA_ARCH__)
+    g_walk_pass3++;
+#endif
     for (int stg = stages; stg > 3; stg--) {
+#if defined(FSB_DEBUG_WALK) && !defined(__CUDA_ARCH__)
+        g_walk_tests++;
+#endif
         const int ib = base + (1 << (stg - 3));
         const int d = ldg_(tab + ib) - hs;
         if (d >= 2 || (d > -2 && abs_lt_exact(zn, ldg_(f.r_bla + ib)))) { index_out = ib; return 1 << stg; }
@@ -991,16 +1006,14 @@ FSB_HD void lane_step(const FrameDev &f, LaneM2 &s, const C *c_pix, double *Z, i
 #undef L_LOAD_Z
 }
 
-/* The hot iteration with its pre-tests.  Returns 0 when the lane can go on, 1
- * when it must visit the event section for the tests of this iteration, 2
- * (Xrange frames) when the range guard failed: the state is then garbage and
- * the lane goes back to its checkpoint.  The orbit record of index w is
- *   {Zn[w+1], FSB_TSCALE dZndc[w]} {Zn[w], r3(w+1), -}
- * r3(w+1) = the stage-3 BLA radius of index w+1 where a lookup takes place
- * (multiples of 8 inside the valid range), else 0. */
+/* The hot iteration with its pre-tests.  `ev`: the lane must visit the event
+ * section for the tests of this iteration; `bad` (Xrange frames): the range
+ * guard failed -- the state is then garbage and the lane goes back to its
+ * checkpoint.  (Zr, Zi) = Zn[w], carried from the previous record; the orbit
+ * record of index w is {Zn[w+1] = (t0, t1), FSB_TSCALE dZndc[w] = (t2, t3)}. */
 template <bool XR, bool DZNDC, bool BLA>
-FSB_HD int m2_hot_iter(LaneM2 &s, double Zr, double Zi, double t0, double t1, double t2, double t3,
-                       double r3n, unsigned esc_hi, bool alive)
+FSB_HD void m2_hot_iter(LaneM2 &s, double Zr, double Zi, double t0, double t1, double t2, double t3,
+                        const unsigned *__restrict__ h3tab, unsigned esc_hi, bool &ev, bool &bad)
 {
     double nzr, nzi, ndr = 0., ndi = 0.;
     m2_iter_fp64<DZNDC>(s.zr, s.zi, s.dr, s.di, Zr, Zi, t2, t3, s.cr, s.ci, nzr, nzi, ndr, ndi);
@@ -1012,18 +1025,18 @@ FSB_HD int m2_hot_iter(LaneM2 &s, double Zr, double Zi, double t0, double t1, do
     const unsigned c = (unsigned)hi32(nzr) & 0x7fffffffu, d = (unsigned)hi32(nzi) & 0x7fffffffu;
     /* |Z + z| <= |z| and |z| < r3 per component can only hold if they hold for the
      * sign-stripped high words; a | b bounds both exponent fields from above */
-    bool ev = (s.w >= s.wlim) | ((a | b) >= esc_hi) | ((a <= c) & (b <= d));
+    ev = (s.w >= s.wlim) | ((a | b) >= esc_hi) | ((a <= c) & (b <= d));
     if (BLA) {
-        const unsigned h3 = (unsigned)hi32(r3n);
+        /* the tree is looked up at multiples of 8: stage-3 radius of the new index */
+        unsigned h3 = 0u;
+        if ((s.w & 7) == 0) h3 = ldg_(h3tab + (s.w >> 3));
         ev = ev | ((c <= h3) & (d <= h3));
     }
-    int code = (ev & alive) ? 1 : 0;
+    bad = false;
     if (XR) {
-        bool bad = !(in_fast_range(nzr) & in_fast_range(nzi));
+        bad = !(in_fast_range(nzr) & in_fast_range(nzi));
         if (DZNDC) bad = bad | !(in_fast_range(ndr) & in_fast_range(ndi));
-        if (bad & alive) code = 2;
     }
-    return code;
 }
 
 /* exponent-field bound of the escape pre-test: both parts of Z + z below 2^k

@@ -72,18 +72,17 @@ static void run(const FrameDev &f, int64_t npts, const C *c_pix, double *Z, int3
             lane_step<XR, DZNDC, BLA>(f, s, c_pix, Z, U, (signed char *)sr, si, cnt, 1, k);
             cnt[6]++;
             if (s.flags & LF_NEED) break;
-            int code;
+            bool ev, bad;
             for (;;) {
-                const double *rec = T2 + 8 * (long long)s.w;
-                code = m2_hot_iter<XR, DZNDC, BLA>(s, rec[4], rec[5], rec[0], rec[1], rec[2], rec[3],
-                                                   rec[6], f.esc_hi, true);
+                const double *rec = T2 + 4 * (long long)s.w;
+                m2_hot_iter<XR, DZNDC, BLA>(s, s.Zr, s.Zi, rec[0], rec[1], rec[2], rec[3], f.h3,
+                                            f.esc_hi, ev, bad);
+                s.Zr = rec[0]; s.Zi = rec[1];
                 cnt[5]++;
-                if (code != 0) break;
+                if (ev | bad) break;
             }
-            if (code == 1) s.flags |= LF_EV | LF_ITER;
-            else { s.flags |= LF_EV | LF_BAD; cnt[7]++; }
-            const C Zw = ldC(f.Zn, s.w);
-            s.Zr = Zw.re; s.Zi = Zw.im;
+            if (XR && bad) { s.flags |= LF_EV | LF_BAD; cnt[7]++; }
+            else s.flags |= LF_EV | LF_ITER;
         }
     }
 }
@@ -150,19 +149,21 @@ extern "C" int fsb_emul_perturb_m2(const emul_frame *e, int64_t npts, const doub
         f.r2hi = r2hi.data();
         f.r2hi_up = r2hi.data() + e->bla_len;
     }
-    /* interleaved orbit table, as k_build_t2 */
-    const int64_t n_rec = L + 16;
-    std::vector<double> T2((size_t)n_rec * 8, 0.);
+    /* interleaved orbit table and pre-test words, as k_build_t2 / k_build_h3 */
+    const int64_t n_rec = L + 16, n_h3 = L / 8 + 4;
+    std::vector<double> T2((size_t)n_rec * 4, 0.);
+    std::vector<unsigned> h3((size_t)n_h3, 0u);
     const C *dsrc = dc ? (xr ? f.dZndc_std : f.dZndc) : nullptr;
     for (int64_t i = 0; i < n_rec; i++) {
-        double *r = T2.data() + 8 * i;
+        double *r = T2.data() + 4 * i;
         if (i + 1 < L + 1) { r[0] = Zn[(size_t)i + 1].re; r[1] = Zn[(size_t)i + 1].im; }
         if (dsrc && i < L + 1) { r[2] = mul_rn(FSB_TSCALE, dsrc[i].re); r[3] = mul_rn(FSB_TSCALE, dsrc[i].im); }
-        if (i < L + 1) { r[4] = Zn[(size_t)i].re; r[5] = Zn[(size_t)i].im; }
-        const int64_t j = i + 1;
-        if (bla && (j & 7) == 0 && (int64_t)f.first_invalid_i - j > 8) r[6] = e->r_bla[2 * (j >> 3)];
     }
+    if (bla)
+        for (int64_t j = 0; j < n_h3 && j < e->bla_len / 2; j++)
+            if ((int64_t)f.first_invalid_i - 8 * j > 8) h3[(size_t)j] = (unsigned)hi32(e->r_bla[2 * j]);
     f.T2 = T2.data();
+    f.h3 = h3.data();
 
     unsigned long long cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const C *cp = (const C *)c_pix;
@@ -176,5 +177,8 @@ extern "C" int fsb_emul_perturb_m2(const emul_frame *e, int64_t npts, const doub
     }
 #undef RUN
     if (counters) for (int k = 0; k < 8; k++) counters[k] = cnt[k];
+#ifdef FSB_DEBUG_WALK
+    printf("BLA lookups %lld, passed stage 3 %lld, stage tests in the walk %lld\n", g_walk_lookups, g_walk_pass3, g_walk_tests);
+#endif
     return 0;
 }
