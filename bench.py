@@ -295,11 +295,50 @@ def run_reference_arm(args, w, rank, world):
 
 
 # ---------------------------------------------------------------------------
+PP_FIELDS = {"config2": ("cont_iter", "DEM"), "config3": ("cont_iter", "DEM"),
+             "config4": ("cont_iter", "normal")}
+
+
+class Reducer:
+    """ max / sum over ranks on the device (torch.distributed is plumbing only) """
+
+    def __init__(self, dist):
+        self.dist = dist
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+
+    def _red(self, v, op):
+        if self.dist is None:
+            return float(v)
+        import torch
+        t = torch.tensor([float(v)], dtype=torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=op)
+        return float(t[0])
+
+    def max(self, v):
+        return self._red(v, self.dist.ReduceOp.MAX if self.dist else None)
+
+    def sum(self, v):
+        return self._red(v, self.dist.ReduceOp.SUM if self.dist else None)
+
+
 def run_workload(args, wname, lib, rank, local_rank, world, dist, with_cpu):
-    """ One workload on this rank's GPU: device-resident timing, end-to-end
-    timing through the seam with host buffers, roofline, optional CPU sample.
+    """ One workload on this rank's GPU:
+      value     device-resident full-frame launches (CUDA events, L2 flushed)
+      e2e       the public call a user makes for the frame's fields --
+                postproc.frame_fields (pixel kernels + fused post-processing,
+                fsb_frame_run_grid_pp) for the perturbation models, the raw seam
+                with per-tile axes for the standard ones -- host buffers, wall clock
+      e2e_raw   the reference-facing seam numba_cycle_call with the raw planes
+                (Z, U, stop_reason, stop_iter) coming back to pinned host memory
+      strong    one frame's tiles dealt to the N ranks (multi.tiles_for_rank),
+                every rank runs the public call on its share: s/frame vs N
     Returns the record on rank 0, None elsewhere. """
-    from fractalshades_b200 import _native
+    from fractalshades_b200 import _native, multi, postproc
+    from fractalshades_b200.core import TileAxes, tile_shape_arrays
+    red = Reducer(dist)
     w = WORKLOADS[wname]
     line = None
     # ---- per-frame setup (reference orbit, dZndc path, BLA tree) ----
@@ -316,15 +355,11 @@ def run_workload(args, wname, lib, rank, local_rank, world, dist, with_cpu):
     n_Z, n_U = len(state.codes[0]), len(state.codes[1])
     zdt = np.dtype(state.complex_type)
 
-    shapes = []
-    c_host = frame_c_pix(f, shapes=shapes)
-    npts = int(c_host.shape[0])
-    from fractalshades_b200.core import tile_shape_arrays
-    tile_w, tile_h = tile_shape_arrays(shapes, npts)
+    all_tiles = list(f.chunk_slices())
+    axes = TileAxes(f, all_tiles)
+    npts = axes.npts
+    tile_w, tile_h = axes.tw, axes.th
     n_tiles = int(tile_w.shape[0])
-    c_pix = _native.pinned_empty((npts,), np.complex128)
-    c_pix[:] = c_host
-    del c_host
     Z = _native.pinned_empty((n_Z, npts), zdt)
     U = _native.pinned_empty((max(n_U, 1), npts), np.int32)
     sr = _native.pinned_empty((1, npts), np.int8)
@@ -341,7 +376,9 @@ def run_workload(args, wname, lib, rank, local_rank, world, dist, with_cpu):
     d_U = dalloc(max(n_U, 1) * npts * 4)
     d_sr = dalloc(npts)
     d_si = dalloc(npts * 4)
-    _native.check(lib, lib.fsb_memcpy_h2d(d_c, _native.ptr(c_pix), npts * 16))
+    c_host = frame_c_pix(f)
+    _native.check(lib, lib.fsb_memcpy_h2d(d_c, _native.ptr(c_host), npts * 16))
+    del c_host
 
     stats = _native.FsbStats()
 
@@ -357,65 +394,102 @@ def run_workload(args, wname, lib, rank, local_rank, world, dist, with_cpu):
         _native.check(lib, rc)
         return stats.kernel_ms
 
-    def step_e2e():
+    def step_raw():
         t0 = time.perf_counter()
-        rc = f.numba_cycle_call((c_pix, Z, U[:n_U], sr, si), indep, tiles=shapes)
+        rc = f.numba_cycle_call((axes, Z, U[:n_U], sr, si), indep)
         assert rc == 0
         return (time.perf_counter() - t0) * 1e3
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
+    pp_fields = PP_FIELDS.get(wname) if perturb else None
+    pp_out = {}
+
+    def step_api(tiles=None):
+        """ the public call; returns (ms, sum of stop_iter of the points done) """
+        t0 = time.perf_counter()
+        if pp_fields:
+            out, st = postproc.frame_fields(f, "bench", fields=pp_fields, copy=False,
+                                            tiles=tiles)
+            pp_out.update(out)
+            n_it = int(st["sum_stop_iter"])
+        else:
+            assert tiles is None
+            rc = f.numba_cycle_call((axes, Z, U[:n_U], sr, si), indep)
+            assert rc == 0
+            n_it = int(type(f)._last_stats["sum_stop_iter"])
+        return (time.perf_counter() - t0) * 1e3, n_it
 
     # ---- warm-up ----
     for _ in range(max(args.warmup, 1)):
         step_device()
-    step_e2e()
+    step_raw()
+    step_api()
 
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.25)
 
     # ---- timed: device-resident ----
-    barrier()
+    red.barrier()
     t_begin = time.time()
     dev_ms = []
     for _ in range(args.steps):
         _native.check(lib, lib.fsb_flush_l2())      # untimed: cold L2 per step
         dev_ms.append(step_device())
-    barrier()
+    red.barrier()
     kstats = stats.as_dict()
     sum_iter = int(kstats["sum_stop_iter"])
 
-    # ---- timed: end to end through the seam, host buffers ----
-    barrier()
-    e2e_ms = []
+    # ---- timed: end to end, the public call (host buffers) ----
+    red.barrier()
+    api_ms = []
     for _ in range(args.steps):
-        e2e_ms.append(step_e2e())
-    barrier()
+        ms, n_it = step_api()
+        api_ms.append(ms)
+    red.barrier()
+    assert n_it == sum_iter, "e2e / device mismatch"
+    if pp_fields:
+        assert int(np.count_nonzero(pp_out["stop_reason"] >= 0)) == npts
+
+    # ---- timed: end to end through the seam, raw planes ----
+    red.barrier()
+    raw_ms = []
+    for _ in range(args.steps):
+        raw_ms.append(step_raw())
+    red.barrier()
     t_end = time.time()
     clocks = sampler.stop(t_begin, t_end)
-
     # correctness guard: the e2e outputs must be those of the device run
-    assert int(si.sum(dtype=np.int64)) == sum_iter, "e2e / device mismatch"
+    assert int(si.sum(dtype=np.int64)) == sum_iter, "seam / device mismatch"
 
-    tot_dev = float(np.sum(dev_ms))
-    tot_e2e = float(np.sum(e2e_ms))
-    if dist is not None:
-        import torch
-        tt = torch.tensor([tot_dev, tot_e2e], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ss = torch.tensor([float(sum_iter)], dtype=torch.float64, device="cuda")
-        dist.all_reduce(ss, op=dist.ReduceOp.SUM)
-        tot_dev, tot_e2e = float(tt[0]), float(tt[1])
-        sum_all = float(ss[0])
-    else:
-        sum_all = float(sum_iter)
+    # ---- strong scaling: ONE frame, its tiles dealt to the ranks ----
+    strong = None
+    if pp_fields:
+        mine = [all_tiles[t] for t in multi.tiles_for_rank(n_tiles, rank, world)]
+        step_api(mine)                                   # warm-up (staging of this share)
+        red.barrier()
+        s_ms, s_it = [], 0
+        for _ in range(args.steps):
+            red.barrier()
+            ms, s_it = step_api(mine)
+            s_ms.append(ms)
+        red.barrier()
+        t_strong = red.max(float(np.sum(s_ms))) / args.steps
+        it_strong = red.sum(float(s_it))
+        strong = {"s_per_frame": t_strong * 1e-3, "ms_per_frame": t_strong,
+                  "value": it_strong / (t_strong * 1e-3) / 1e9, "unit": "Gpix-iter/s",
+                  "tiles_per_rank": len(mine), "api": "postproc.frame_fields(tiles=rank's share)",
+                  "note": "one frame, tiles dealt round-robin to the ranks, max over ranks"}
+        assert world > 1 or int(it_strong) == sum_iter
+
+    tot_dev = red.max(float(np.sum(dev_ms)))
+    tot_api = red.max(float(np.sum(api_ms)))
+    tot_raw = red.max(float(np.sum(raw_ms)))
+    sum_all = red.sum(float(sum_iter))
 
     ms_per_step = tot_dev / args.steps
     value = sum_all / (ms_per_step * 1e-3) / 1e9
-    e2e_ms_per_step = tot_e2e / args.steps
-    e2e_value = sum_all / (e2e_ms_per_step * 1e-3) / 1e9
+    api_ms_per_step = tot_api / args.steps
+    raw_ms_per_step = tot_raw / args.steps
 
     if rank == 0:
         # ---- roofline of the pixel kernel: FP64 FMA pipe ----
@@ -425,7 +499,6 @@ def run_workload(args, wname, lib, rank, local_rank, world, dist, with_cpu):
         peak = float(lib.fsb_fp64_peak_tflops(200000))
         achieved = flops / (kernel_ms * 1e-3) / 1e12
         alg_bytes = npts * (16 + n_Z * zdt.itemsize + 4 * n_U + 4 + 1)
-        hbm_peak = 6533.8
         try:
             with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as fh:
                 hbm_peak = float(json.load(fh)["hbm_gbs"])
@@ -470,8 +543,19 @@ def run_workload(args, wname, lib, rank, local_rank, world, dist, with_cpu):
                 "s_per_frame_extrapolated": s["seconds"] * s["n_tiles_total"] / s["n_tiles"],
                 "tables_s": s["tables_s"],
             }
-        h2d = npts * 16
-        d2h = npts * (n_Z * zdt.itemsize + 4 * n_U + 4 + 1)
+            cal = numba_calibration(wname)
+            if cal:
+                cpu_baseline["numba_calibration"] = cal
+        h2d_axes = int(axes.axes.nbytes + tile_w.nbytes + tile_h.nbytes)
+        d2h_raw = npts * (n_Z * zdt.itemsize + 4 * n_U + 4 + 1)
+        if pp_fields:
+            n_f32 = len([k for k in pp_out if k not in ("stop_reason", "stop_iter")])
+            d2h_api = npts * (4 * n_f32 + 1)
+            api_name = ("postproc.frame_fields(fields=%s) -> fsb_frame_run_grid_pp"
+                        % (list(pp_fields),))
+        else:
+            d2h_api = d2h_raw
+            api_name = "Fractal.numba_cycle_call(TileAxes, ...) -> fsb_std_run_grid"
         line = {
             "metric": "effective pixel-iterations per second",
             "value": value, "unit": "Gpix-iter/s", "n_gpus": world,
@@ -481,13 +565,19 @@ def run_workload(args, wname, lib, rank, local_rank, world, dist, with_cpu):
             "data": "synthetic",
             "config": bench_config(w, f, world),
             "l2": "flushed between timed steps (192 MiB write); the planes of a "
-                  "frame (%d MB) exceed L2" % ((h2d + d2h) // 1000000),
+                  "frame (%d MB) exceed L2" % ((npts * 16 + d2h_raw) // 1000000),
             "build": lib.fsb_build_info().decode(),
             "s_per_frame": ms_per_step * 1e-3,
-            "e2e": {"value": e2e_value, "unit": "Gpix-iter/s",
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms_per_step,
-                    "s_per_frame": e2e_ms_per_step * 1e-3},
+            "e2e": {"value": sum_all / (api_ms_per_step * 1e-3) / 1e9, "unit": "Gpix-iter/s",
+                    "h2d_bytes_per_step": h2d_axes, "d2h_bytes_per_step": d2h_api,
+                    "ms_per_step": api_ms_per_step, "s_per_frame": api_ms_per_step * 1e-3,
+                    "api": api_name},
+            "e2e_raw": {"value": sum_all / (raw_ms_per_step * 1e-3) / 1e9, "unit": "Gpix-iter/s",
+                        "h2d_bytes_per_step": h2d_axes, "d2h_bytes_per_step": d2h_raw,
+                        "ms_per_step": raw_ms_per_step, "s_per_frame": raw_ms_per_step * 1e-3,
+                        "api": "numba_cycle_call(TileAxes, Z, U, stop_reason, stop_iter) "
+                               "-> fsb_frame_run_grid, raw planes to pinned host memory"},
+            "strong_scaling": strong,
             "gpu_launches": int(args.steps * kstats["n_launches"]),
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
@@ -497,9 +587,66 @@ def run_workload(args, wname, lib, rank, local_rank, world, dist, with_cpu):
         }
     for p in (d_c, d_Z, d_U, d_sr, d_si):
         lib.fsb_dev_free(p)
+    for a in (Z, U, sr, si):
+        _native.pinned_free(a)
     if perturb:
         frame.close()
     return line
+
+
+def numba_calibration(wname):
+    """ ratio oracle-port / numba-reference measured in the build container on the
+    same tile subsets (tools/calibrate_numba.py; the reference is a Python
+    package that cannot travel to the GPU box) """
+    try:
+        with open(os.path.join(REPO, "profiles", "numba_calibration.json")) as fh:
+            return json.load(fh).get(wname)
+    except Exception:
+        return None
+
+
+def run_movie(args, lib, rank, local_rank, world, dist):
+    """ BASELINE config 5: 64 frames 1e-10 -> 1e-2000 at 8K, frames dealt to the
+    ranks; one record: seconds per frame and effective Gpix-iter/s of the whole
+    job (orbit computed once, outside the timed span, as a movie would cache it) """
+    import mpmath
+    import fractalshades_b200.models as fsm
+    from fractalshades_b200 import movie, settings
+    from fractalshades_b200.views import VIEWS
+    red = Reducer(dist)
+    settings.no_newton = True
+    v = VIEWS["deep_julia_2608"]
+    dx_end, n_frames, nx = "1e-2000", args.movie_frames, (args.nx or 7680)
+    digits = int(-float(mpmath.log10(mpmath.mpf(dx_end)))) + 30
+    directory = os.path.join(tempfile.gettempdir(), "fsb_bench_movie")
+    seq = movie.ZoomSequence(
+        fsm.Perturbation_mandelbrot, directory, x=v["x"][:digits + 20], y=v["y"][:digits + 20],
+        dx_start="1e-10", dx_end=dx_end, n_frames=n_frames, nx=nx, xy_ratio=16 / 9.,
+        precision=digits,
+        calc_kwargs=dict(max_iter=3000000, M_divergence=1e3, epsilon_stationnary=1e-3,
+                         BLA_eps=1e-6, interior_detect=False, calc_dzndc=True))
+    t_orbit = seq.prepare_orbit(rank)
+    red.barrier()
+    t0 = time.time()
+    recs = seq.render(rank, world, store=False, pp_fields=("cont_iter", "DEM"))
+    total_s = time.time() - t0
+    red.barrier()
+    iters = sum(r["sum_stop_iter"] for r in recs)
+    kernel_ms = sum(r["kernel_ms"] for r in recs)
+    tmax, isum = red.max(total_s), red.sum(iters)
+    if rank != 0:
+        return None
+    return {"config": {"workload": "deep-zoom movie: %d frames dx 1e-10 -> %s at %dx%d, "
+                                   "max_iter 3e6, frames dealt to the ranks" %
+                                   (n_frames, dx_end, nx, int(nx * 9 / 16 + 0.5)),
+                       "frames_per_step": n_frames},
+            "value": isum / tmax / 1e9, "unit": "Gpix-iter/s", "wall_s": tmax,
+            "s_per_frame": tmax / n_frames, "orbit_s_once": t_orbit,
+            "api": "movie.ZoomSequence.render(pp_fields=('cont_iter', 'DEM'))",
+            "rank0": {"frames": len(recs), "kernel_ms_sum": kernel_ms,
+                      "setup_s_sum": sum(r["setup_s"] for r in recs),
+                      "render_s_sum": sum(r["render_s"] for r in recs),
+                      "first": recs[:2], "last": recs[-2:]}}
 
 
 def main():
@@ -510,7 +657,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=HEADLINE, choices=sorted(WORKLOADS),
                     help="the workload of the headline line (BASELINE.json's target: config3)")
-    ap.add_argument("--also", default="config1,config2,config4",
+    ap.add_argument("--movie-frames", type=int, default=64,
+                    help="config5 (with --also ...,config5): number of frames of the zoom movie")
+    ap.add_argument("--also", default="config1,config2,config4,config5",
                     help="comma list of further workloads reported as sub-records under "
                          "'workloads' (each with its own roofline / e2e / cpu_baseline); "
                          "'none' to skip")
@@ -526,7 +675,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     also = [x for x in args.also.split(",") if x and x != "none" and x != args.workload]
     for x in also:
-        if x not in WORKLOADS:
+        if x not in WORKLOADS and x != "config5":
             ap.error(f"unknown workload {x}")
 
     if args.impl == "reference":
@@ -549,7 +698,10 @@ def main():
     line = run_workload(args, args.workload, lib, rank, local_rank, world, dist, with_cpu)
     subs = {}
     for x in also:
-        rec = run_workload(args, x, lib, rank, local_rank, world, dist, with_cpu)
+        if x == "config5":
+            rec = run_movie(args, lib, rank, local_rank, world, dist)
+        else:
+            rec = run_workload(args, x, lib, rank, local_rank, world, dist, with_cpu)
         if rec is not None:
             for k in ("n_gpus", "steps", "warmup", "higher_is_better", "vs_baseline",
                       "data", "metric", "unit"):

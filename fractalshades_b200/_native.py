@@ -90,6 +90,7 @@ CUDA_SYMBOLS = [
     "fsb_frame_run_pp", "fsb_postproc_run", "fsb_postproc_run_device",
     "fsb_xr_binop_c", "fsb_xr_to_standard_c", "fsb_hypot_test",
     "fsb_fp64_peak_tflops", "fsb_proj_apply",
+    "fsb_std_run_grid", "fsb_frame_run_grid", "fsb_frame_run_grid_pp",
 ]
 ORBIT_SYMBOLS = ["fsb_orbit_mandelbrot", "fsb_orbit_burning_ship",
                  "fsb_ball_method_mandelbrot", "fsb_find_nucleus_mandelbrot"]
@@ -162,6 +163,12 @@ def _declare(lib):
     lib.fsb_hypot_test.argtypes = [c_i64, c_vp, c_vp, c_vp]
     if hasattr(lib, "fsb_proj_apply"):     # absent from older A/B builds (FSB200_LIB)
         lib.fsb_proj_apply.argtypes = [ctypes.POINTER(FsbProjDesc), c_i64, c_vp, c_vp, c_vp]
+    if hasattr(lib, "fsb_frame_run_grid"):
+        lib.fsb_std_run_grid.argtypes = [ctypes.POINTER(FsbStdDesc), c_i32, c_vp, c_vp,
+                                         c_vp, c_vp, c_vp, c_vp, c_vp,
+                                         ctypes.POINTER(FsbStats)]
+        lib.fsb_frame_run_grid.argtypes = [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                           c_vp, c_vp, c_vp, ctypes.POINTER(FsbStats)]
     lib.fsb_fp64_peak_tflops.argtypes = [ctypes.c_int]
     lib.fsb_fp64_peak_tflops.restype = c_dbl
     return lib

@@ -26,6 +26,7 @@ import fnmatch
 import functools
 import os
 import pickle
+import threading
 import types
 
 import numpy as np
@@ -91,7 +92,24 @@ def dic_flatten(dic, key_prefix="", sep="@"):
     return res
 
 
-class Fractal:
+_TLS = threading.local()
+
+
+class _FractalMeta(type):
+    """ `Fractal._last_stats`: counters of the calling thread's last seam call
+    (the seam is thread-safe, one launch context per host thread; a class
+    global would be overwritten by concurrent tile threads). """
+
+    @property
+    def _last_stats(cls):
+        return getattr(_TLS, "stats", None)
+
+    @_last_stats.setter
+    def _last_stats(cls, value):
+        _TLS.stats = value
+
+
+class Fractal(metaclass=_FractalMeta):
     REPORT_ITEMS = ["chunk1d_begin", "chunk1d_end", "chunk_pts", "done"]
     SAVE_ARRS = ["Z", "U", "stop_reason", "stop_iter"]
     USER_INTERRUPTED = USER_INTERRUPTED
@@ -196,6 +214,23 @@ class Fractal:
         cix, ciy = divmod(rank, cy)
         ix, iy = cix * cs, ciy * cs
         return (ix, min(ix + cs, self.nx), iy, min(iy + cs, self.ny))
+
+    def tile_axes(self, chunk_slice):
+        """ The two axes of a tile's pixel grid without jitter / supersampling:
+        `chunk_pixel_pos(cs, False, None)[r, c] == x[c] + 1j * y[r]`, bit for
+        bit (the grid calls of libfsb200 expand them on the device). """
+        data_type = self.float_type
+        (nx, ny) = (self.nx, self.ny)
+        (ix, ixx, iy, iyy) = chunk_slice
+        kx = 0.5 / (nx - 1)
+        ky = 0.5 / (ny - 1)
+        x_1d = np.linspace(kx * (2 * ix - nx + 1), kx * (2 * ixx - nx - 1),
+                           num=(ixx - ix), dtype=data_type)
+        y_1d = np.linspace(ky * (2 * iy - ny + 1), ky * (2 * iyy - ny - 1),
+                           num=(iyy - iy), dtype=data_type)
+        y = -y_1d
+        y /= self.xy_ratio
+        return x_1d, y
 
     def chunk_pixel_pos(self, chunk_slice, jitter, supersampling):
         """ core.py:1767-1830 : pixel offsets in fractions of dx, row 0 = top """
@@ -317,10 +352,20 @@ class Fractal:
         (kind, desc, interrupted) = cycle_indep_args
         assert kind == "std"
         lib = _native.cuda_lib()
-        npts = c_pix.shape[0]
-        for a in (c_pix, Z, stop_reason, stop_iter):
-            assert a.flags["C_CONTIGUOUS"]
         stats = _native.FsbStats()
+        if isinstance(c_pix, TileAxes):
+            # tile scheduler: pixel offsets expanded on the device from the axes
+            check_outputs(c_pix.npts, Z, None, stop_reason, stop_iter,
+                          lib.fsb_std_nz(desc), None)
+            rc = lib.fsb_std_run_grid(
+                desc, c_pix.tw.shape[0], _native.ptr(c_pix.tw), _native.ptr(c_pix.th),
+                _native.ptr(c_pix.axes), _native.ptr(Z), _native.ptr(stop_reason),
+                _native.ptr(stop_iter), _native.ptr(interrupted), stats)
+            _native.check(lib, rc)
+            Fractal._last_stats = stats.as_dict()
+            return rc
+        npts = c_pix.shape[0]
+        check_outputs(npts, Z, None, stop_reason, stop_iter, lib.fsb_std_nz(desc), c_pix)
         if tiles is not None:
             tw, th = tile_shape_arrays(tiles, npts)
             rc = lib.fsb_std_run_tiles(
@@ -595,12 +640,35 @@ class Fractal:
         except Exception:
             pass
 
+    def prepare_mmaps(self, calc_name):
+        """ Create the report / data memmaps of a calculation now (what calc_raw
+        does on its first call).  Multi-rank runs: rank 0 only, before a barrier
+        (multi.calc_raw_sharded). """
+        self.init_report_mmap(calc_name)
+        self.init_data_mmaps(calc_name)
+        self._calc_data[calc_name]["need_new_mmap"] = False
+
+    def bind_mmaps(self, calc_name):
+        """ Use the memmaps another rank has created (after a barrier). """
+        for key in ["report"] + self.SAVE_ARRS:
+            path = (self.report_path(calc_name) if key == "report"
+                    else self.data_path(calc_name)[key])
+            open_memmap(filename=path, mode="r+")        # raises if missing
+        self._calc_data[calc_name]["need_new_mmap"] = False
+
     def calc_raw(self, calc_name, tile_validator=None):
         """ core.py:2724-2736 """
         if self._calc_data[calc_name]["need_new_mmap"]:
-            self.init_report_mmap(calc_name)
-            self.init_data_mmaps(calc_name)
-            self._calc_data[calc_name]["need_new_mmap"] = False
+            if (getattr(tile_validator, "world", 1) > 1
+                    and not getattr(tile_validator, "files_ready", False)):
+                # creating truncates: a second rank doing it would wipe the
+                # `done` flags and slabs the first one has written
+                raise RuntimeError(
+                    "calc_raw with a multi-rank tile_validator: the memmaps must be created "
+                    "by one rank before the others open them -- use "
+                    "fractalshades_b200.multi.calc_raw_sharded (rank 0 creates, barrier, "
+                    "the others bind)")
+            self.prepare_mmaps(calc_name)
         self.compute_rawdata_dev(calc_name, chunk_slice=None,
                                  tile_validator=tile_validator)
 
@@ -643,20 +711,21 @@ class Fractal:
             # page-locked staging buffers (reused across batches / frames): the
             # H2D / D2H copies of the slab pipeline then run at full PCIe speed
             bufs = self._staging(npts, n_Z, n_U, state.complex_type)
-            c_pix = bufs["c_pix"][:npts]
             Z = bufs["Z"][:, :npts] if npts == bufs["cap"] else None
-            off = 0
-            shapes = []          # full tiles: (width, height) for the patch mapping
-            for (rank, cs), n in zip(batch, sizes):
-                pos = self.chunk_pixel_pos(cs, False, None)
-                pix = np.ravel(pos)
-                if state.subset is not None:
+            if state.subset is None:
+                # full tiles: only their axes cross PCIe, the pixel grid is
+                # built on the device (fsb_*_run_grid)
+                c_pix = TileAxes(self, [cs for rank, cs in batch])
+                shapes = None
+            else:
+                c_pix = bufs["c_pix"][:npts]
+                off = 0
+                shapes = None
+                for (rank, cs), n in zip(batch, sizes):
+                    pix = np.ravel(self.chunk_pixel_pos(cs, False, None))
                     pix = pix[np.asarray(state.subset[cs], dtype=bool)]
-                    shapes = None
-                elif shapes is not None:
-                    shapes.append((pos.shape[1], pos.shape[0]))
-                c_pix[off:off + n] = pix
-                off += n
+                    c_pix[off:off + n] = pix
+                    off += n
             if Z is None:        # batch smaller than the staging capacity
                 Z = np.zeros([n_Z, npts], dtype=state.complex_type)
                 U = np.zeros([n_U, npts], dtype=self.int_type)
@@ -667,7 +736,7 @@ class Fractal:
                 stop_reason, stop_iter = bufs["stop_reason"], bufs["stop_iter"]
             ret = self.numba_cycle_call((c_pix, Z, U, stop_reason, stop_iter), indep,
                                         tiles=shapes)
-            for k, v in (getattr(Fractal, "_last_stats", None) or {}).items():
+            for k, v in (Fractal._last_stats or {}).items():
                 stats_acc[k] = stats_acc.get(k, 0) + v
             if ret == self.USER_INTERRUPTED:
                 return
@@ -744,6 +813,49 @@ class Fractal:
             return None
         (c_pix, Z, U, stop_reason, stop_iter) = cycle_dep_args
         return (chunk_subset, c_pix, Z, U, stop_reason, stop_iter)
+
+
+class TileAxes:
+    """ Pixel offsets of a list of full tiles as per-tile axes (`tile_axes`):
+    passed in place of `c_pix` to `numba_cycle_call`, the library then builds
+    the pixel grid on the device (fsb_*_run_grid) -- 0.7 MB instead of 133 MB
+    over PCIe for a 4K frame.  Not in the reference: the GPU tile scheduler's
+    own argument. """
+
+    def __init__(self, fractal, chunk_slices):
+        ax, shapes = [], []
+        for cs in chunk_slices:
+            x, y = fractal.tile_axes(cs)
+            ax += [x, y]
+            shapes.append((x.shape[0], y.shape[0]))
+        self.shapes = shapes
+        self.axes = np.ascontiguousarray(np.concatenate(ax), dtype=np.float64)
+        self.npts = int(sum(w * h for w, h in shapes))
+        self.tw, self.th = tile_shape_arrays(shapes, self.npts)
+
+
+def check_outputs(npts, Z, U, stop_reason, stop_iter, nz, c_pix):
+    """ The seam trusts no caller for buffer sizes: the library copies
+    nz * npts elements into Z, npts into the others. """
+    def bad(name, a, shape, dtype=None):
+        return ValueError(f"{name}: expected C-contiguous {shape}"
+                          + (f" {np.dtype(dtype).name}" if dtype else "")
+                          + f", got {getattr(a, 'shape', None)} {getattr(a, 'dtype', None)}")
+    if c_pix is not None and (c_pix.dtype != np.complex128 or c_pix.ndim != 1
+                              or not c_pix.flags["C_CONTIGUOUS"]):
+        raise bad("c_pix", c_pix, (npts,), np.complex128)
+    if (Z.ndim != 2 or Z.shape[0] != nz or Z.shape[1] != npts
+            or not Z.flags["C_CONTIGUOUS"] or Z.dtype not in (np.complex128, np.float64)):
+        raise bad("Z", Z, (nz, npts))
+    if U is not None and (U.dtype != np.int32 or U.ndim != 2 or U.shape[0] < 1
+                          or U.shape[1] != npts or not U.flags["C_CONTIGUOUS"]):
+        raise bad("U", U, (">=1", npts), np.int32)
+    if (stop_reason.dtype != np.int8 or stop_reason.size != npts
+            or not stop_reason.flags["C_CONTIGUOUS"]):
+        raise bad("stop_reason", stop_reason, (1, npts), np.int8)
+    if (stop_iter.dtype != np.int32 or stop_iter.size != npts
+            or not stop_iter.flags["C_CONTIGUOUS"]):
+        raise bad("stop_iter", stop_iter, (1, npts), np.int32)
 
 
 def tile_shape_arrays(tiles, npts):

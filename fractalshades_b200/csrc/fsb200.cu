@@ -153,6 +153,7 @@ struct Ctx {
     unsigned long long *h_ctl = nullptr;              /* pinned mirror        */
     int4 *d_tiles = nullptr;  long long tiles_cap = 0; /* tile descriptors of the running call */
     C *d_proj = nullptr;  long long proj_cap = 0;     /* projected pixels of the running call */
+    char *d_axes = nullptr;  long long axes_cap = 0;  /* per-tile pixel axes of a grid call */
     int *d_abort() { return (int *)(d_ctl + MAX_CHUNKS * CTL_WORDS); }
     ~Ctx()
     {
@@ -160,6 +161,7 @@ struct Ctx {
         if (d_ctl) cudaFree(d_ctl);
         if (d_tiles) cudaFree(d_tiles);
         if (d_proj) cudaFree(d_proj);
+        if (d_axes) cudaFree(d_axes);
         if (h_ctl) cudaFreeHost(h_ctl);
         for (cudaEvent_t e : {ev0, ev1, evc0, evc1}) if (e) cudaEventDestroy(e);
         for (int i = 0; i < MAX_CHUNKS; i++) {
@@ -1155,8 +1157,35 @@ struct Plane { char *host; long long dev_off; long long elem; };
  * over slabs of consecutive points.  `enqueue(stream, slot, unit_lo, unit_hi,
  * a, n)` launches the kernel for those units (= points [a, a+n)) into control
  * block `slot`. */
+/* Grid calls: the pixel offsets come from per-tile axes (tile k: tile_w[k] x
+ * values then tile_h[k] y values; pix(r, col) = x[col] + i y[r], the layout of
+ * Fractal.chunk_pixel_pos without jitter, core.py:1767-1830) instead of a
+ * 16-byte-per-point array: a few hundred kB cross PCIe instead of 133 MB per 4K
+ * frame, and k_expand_grid writes the c_pix plane of each slab in HBM. */
+static int upload_axes(Ctx *c, const Units &u, const double *axes, cudaStream_t st,
+                       const long long **d_off, const double **d_ax)
+{
+    if (!u.tiled()) return fail(-3, "grid calls need a tile list");
+    const size_t nt = u.tiles.size();
+    std::vector<long long> off(nt);
+    long long tot = 0;
+    for (size_t k = 0; k < nt; k++) { off[k] = tot; tot += (long long)u.tiles[k].z + u.tiles[k].w; }
+    const long long bytes = (long long)nt * 8 + tot * 8;
+    if (bytes > c->axes_cap) {
+        if (c->d_axes) { CK(cudaFree(c->d_axes)); c->d_axes = nullptr; c->axes_cap = 0; }
+        CK(cudaMalloc(&c->d_axes, (size_t)(2 * bytes)));
+        c->axes_cap = 2 * bytes;
+    }
+    /* pageable sources: the driver stages them before returning */
+    CK(cudaMemcpyAsync(c->d_axes, off.data(), nt * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->d_axes + nt * 8, axes, (size_t)(tot * 8), cudaMemcpyHostToDevice, st));
+    *d_off = (const long long *)c->d_axes;
+    *d_ax = (const double *)(c->d_axes + nt * 8);
+    return 0;
+}
+
 template <class Enqueue>
-static int run_pipelined(Ctx *c, const Units &u, const double *c_pix, long long o_c,
+static int run_pipelined(Ctx *c, const Units &u, const double *c_pix, const double *axes, long long o_c,
                          const Plane *planes, int n_planes, long long o_zero_beg,
                          long long o_zero_end, long long o_sr, Enqueue enqueue,
                          const volatile uint8_t *interrupted, fsb_stats *stats, bool *was_int)
@@ -1167,6 +1196,12 @@ static int run_pipelined(Ctx *c, const Units &u, const double *c_pix, long long 
     CK(cudaMemsetAsync(c->d_abort(), 0, sizeof(int), c->stream));
     CK(cudaMemsetAsync(base + o_zero_beg, 0, (size_t)(o_zero_end - o_zero_beg), c->stream));
     CK(cudaMemsetAsync(base + o_sr, 0xff, (size_t)npts, c->stream));
+    const long long *d_ax_off = nullptr;
+    const double *d_ax = nullptr;
+    if (!c_pix) {
+        if (!axes) return fail(-3, "no pixel source");
+        if (upload_axes(c, u, axes, c->stream, &d_ax_off, &d_ax)) return -1;
+    }
     CK(cudaEventRecord(c->ev0, c->stream));
     CK(cudaStreamWaitEvent(c->s_alt, c->ev0, 0));
     CK(cudaStreamWaitEvent(c->s_d2h, c->ev0, 0));
@@ -1176,11 +1211,17 @@ static int run_pipelined(Ctx *c, const Units &u, const double *c_pix, long long 
      * is why the D2H of slab k is only issued once its kernel has finished). */
     auto enqueue_slab = [&](int k) -> int {
         const long long a = ch.beg[k], n = ch.beg[k + 1] - a;
-        CK(cudaMemcpyAsync(base + o_c + a * 16, c_pix + 2 * a, (size_t)(n * 16),
-                           cudaMemcpyHostToDevice, c->s_h2d));
-        CK(cudaEventRecord(c->ev_h[k], c->s_h2d));
         cudaStream_t st = (k & 1) ? c->s_alt : c->stream;
-        CK(cudaStreamWaitEvent(st, c->ev_h[k], 0));
+        if (c_pix) {
+            CK(cudaMemcpyAsync(base + o_c + a * 16, c_pix + 2 * a, (size_t)(n * 16),
+                               cudaMemcpyHostToDevice, c->s_h2d));
+            CK(cudaEventRecord(c->ev_h[k], c->s_h2d));
+            CK(cudaStreamWaitEvent(st, c->ev_h[k], 0));
+        } else if (n > 0) {
+            k_expand_grid<<<(int)((n + 255) / 256), 256, 0, st>>>(
+                u.d_tiles, (int)u.tiles.size(), d_ax_off, d_ax, a, n, (C *)(base + o_c));
+            CK(cudaGetLastError());
+        }
         if (enqueue(st, k, ch.ubeg[k], ch.ubeg[k + 1], a, n)) return -1;
         CK(cudaEventRecord(c->ev_k[k], st));
         return 0;
@@ -1221,7 +1262,8 @@ extern "C" {
 static int std_run_impl(Ctx *c, const fsb_std_desc *d, int32_t n_tiles, const int32_t *tile_w,
                         const int32_t *tile_h, int64_t npts_flat, const double *c_pix, double *Z,
                         int8_t *stop_reason, int32_t *stop_iter,
-                        const volatile uint8_t *interrupted, fsb_stats *stats)
+                        const volatile uint8_t *interrupted, fsb_stats *stats,
+                        const double *axes = nullptr)
 {
     if (stats) memset(stats, 0, sizeof *stats);
     if (interrupted && *interrupted) return FSB_USER_INTERRUPTED;
@@ -1249,7 +1291,7 @@ static int std_run_impl(Ctx *c, const fsb_std_desc *d, int32_t n_tiles, const in
                            (double *)(base + o_Z), (signed char *)(base + o_sr),
                            (int *)(base + o_si));
     };
-    int rc = run_pipelined(c, u, c_pix, o_c, planes, np, o_Z, o_si + npts * 4, o_sr, enqueue,
+    int rc = run_pipelined(c, u, c_pix, axes, o_c, planes, np, o_Z, o_si + npts * 4, o_sr, enqueue,
                            interrupted, stats, &was_int);
     if (rc) return rc;
     return was_int ? FSB_USER_INTERRUPTED : 0;
@@ -1658,7 +1700,8 @@ static int frame_run_impl(Ctx *c, fsb_frame *f, int32_t n_tiles, const int32_t *
                           const int32_t *tile_h, int64_t npts_flat, const double *c_pix, double *Z,
                           int32_t *U, int8_t *stop_reason, int32_t *stop_iter,
                           const volatile uint8_t *interrupted, fsb_stats *stats,
-                          const fsb_postproc_desc *pp = nullptr, void *const *pp_out = nullptr)
+                          const fsb_postproc_desc *pp = nullptr, void *const *pp_out = nullptr,
+                          const double *axes = nullptr)
 {
     if (stats) memset(stats, 0, sizeof *stats);
     if (interrupted && *interrupted) return FSB_USER_INTERRUPTED;
@@ -1714,7 +1757,7 @@ static int frame_run_impl(Ctx *c, fsb_frame *f, int32_t n_tiles, const int32_t *
                                         d_pp[3]);
         return 0;
     };
-    int rc = run_pipelined(c, u, c_pix, o_c, planes, np, o_Z, o_si + npts * 4, o_sr, enqueue,
+    int rc = run_pipelined(c, u, c_pix, axes, o_c, planes, np, o_Z, o_si + npts * 4, o_sr, enqueue,
                            interrupted, stats, &was_int);
     if (rc) return rc;
     if (stats && pp) stats->n_launches *= 2;
@@ -1794,6 +1837,48 @@ int fsb_frame_run_pp(fsb_frame *f, int32_t n_tiles, const int32_t *tile_w, const
     void *outs[4] = {nu, dem, normal_x, normal_y};
     return frame_run_impl(c, f, n_tiles, tile_w, tile_h, npts, c_pix, nullptr, nullptr,
                           stop_reason, stop_iter, interrupted, stats, pp, outs);
+}
+
+/* ---- grid calls: pixel offsets from per-tile axes ---------------------------- */
+int fsb_std_run_grid(const fsb_std_desc *d, int32_t n_tiles, const int32_t *tile_w,
+                     const int32_t *tile_h, const double *axes, double *Z, int8_t *stop_reason,
+                     int32_t *stop_iter, const volatile uint8_t *interrupted, fsb_stats *stats)
+{
+    Ctx *c;
+    if (get_ctx(&c)) return -1;
+    if (n_tiles <= 0 || !axes) return fail(-3, "empty tile list / null axes");
+    return std_run_impl(c, d, n_tiles, tile_w, tile_h, 0, nullptr, Z, stop_reason, stop_iter,
+                        interrupted, stats, axes);
+}
+
+int fsb_frame_run_grid(fsb_frame *f, int32_t n_tiles, const int32_t *tile_w, const int32_t *tile_h,
+                       const double *axes, double *Z, int32_t *U, int8_t *stop_reason,
+                       int32_t *stop_iter, const volatile uint8_t *interrupted, fsb_stats *stats)
+{
+    Ctx *c;
+    if (get_ctx(&c)) return -1;
+    if (!f) return fail(-3, "null frame");
+    if (n_tiles <= 0 || !axes) return fail(-3, "empty tile list / null axes");
+    return frame_run_impl(c, f, n_tiles, tile_w, tile_h, 0, nullptr, Z, U, stop_reason, stop_iter,
+                          interrupted, stats, nullptr, nullptr, axes);
+}
+
+int fsb_frame_run_grid_pp(fsb_frame *f, int32_t n_tiles, const int32_t *tile_w,
+                          const int32_t *tile_h, const double *axes, const fsb_postproc_desc *pp,
+                          void *nu, void *dem, void *normal_x, void *normal_y,
+                          int8_t *stop_reason, int32_t *stop_iter,
+                          const volatile uint8_t *interrupted, fsb_stats *stats)
+{
+    Ctx *c;
+    if (get_ctx(&c)) return -1;
+    if (!f) return fail(-3, "null frame");
+    if (!pp) return fail(-3, "null post-processing description");
+    if (f->d.proj.kind != FSB_PROJ_CARTESIAN && (dem || normal_x || normal_y))
+        return fail(-3, "fused DEM / normal post-processing is only defined for the Cartesian projection");
+    if (n_tiles <= 0 || !axes) return fail(-3, "empty tile list / null axes");
+    void *outs[4] = {nu, dem, normal_x, normal_y};
+    return frame_run_impl(c, f, n_tiles, tile_w, tile_h, 0, nullptr, nullptr, nullptr, stop_reason,
+                          stop_iter, interrupted, stats, pp, outs, axes);
 }
 
 int fsb_postproc_run_device(const fsb_postproc_desc *pp, int64_t npts, int32_t n_rows,

@@ -88,6 +88,28 @@ __device__ __forceinline__ void add_counters(unsigned long long *counters,
     }
 }
 
+/* c_pix plane of the points [a, a + n) of a tile-list call from the per-tile
+ * axes (fsb_*_run_grid): tile k holds tiles[k].z x values then tiles[k].w y
+ * values at axes[off[k]]; HBM-bound, 16 B written per point. */
+__global__ void k_expand_grid(const int4 *__restrict__ tiles, int n_tiles,
+                              const long long *__restrict__ off, const double *__restrict__ axes,
+                              long long a, long long n, C *__restrict__ c_pix)
+{
+    const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const long long i = a + j;
+    int lo = 0, hi = n_tiles - 1;            /* last tile whose first point <= i */
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if ((long long)__ldg(&tiles[mid].y) <= i) lo = mid; else hi = mid - 1;
+    }
+    const int4 tl = __ldg(tiles + lo);
+    const int local = (int)(i - tl.y);
+    const int r = local / tl.z, col = local - r * tl.z;
+    const double *ax = axes + __ldg(off + lo);
+    reinterpret_cast<double2 *>(c_pix)[i] = make_double2(__ldg(ax + col), __ldg(ax + tl.z + r));
+}
+
 /* The projection and the modifier run as two small HBM-bound passes around
  * the pixel kernel (same stream, same point range): the pixel kernels -- whose
  * register allocation decides the frame time -- see already-projected pixels

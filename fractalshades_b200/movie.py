@@ -96,10 +96,13 @@ class ZoomSequence:
             time.sleep(0.2)
         return 0.
 
-    def render(self, rank=0, world=1, store=False, on_frame=None):
-        """ Render this rank's frames.  store=False keeps the outputs in the
-        page-locked staging buffers only (benchmarks); store=True writes the
-        reference-layout memmaps under <directory>/frame_XXXX/. """
+    def render(self, rank=0, world=1, store=False, on_frame=None, pp_fields=None):
+        """ Render this rank's frames.  store=True writes the reference-layout
+        memmaps under <directory>/frame_XXXX/; store=False keeps the outputs in
+        page-locked staging buffers only (benchmarks): the raw planes, or --
+        pp_fields, e.g. ("cont_iter", "DEM") -- the post-processed float32
+        fields of the fused call (postproc.frame_fields: 9 B per point leave
+        the device instead of 41). """
         out = []
         for k in multi.frames_for_rank(self.n_frames, rank, world):
             t0 = time.time()
@@ -109,6 +112,9 @@ class ZoomSequence:
             if store:
                 f.calc_raw("movie")          # memmaps under frame_XXXX/data/
                 st = f.last_stats
+            elif pp_fields:
+                from . import postproc
+                _, st = postproc.frame_fields(f, "movie", fields=pp_fields, copy=False)
             else:
                 st = render_frame_to_staging(f, "movie")
             t2 = time.time()
@@ -140,7 +146,6 @@ def render_frame_to_staging(f, calc_name):
             _native.pinned_free(a)
         _STAGE["key"] = key
         _STAGE["bufs"] = {
-            "c_pix": _native.pinned_empty((npts,), np.complex128),
             "Z": _native.pinned_empty((n_Z, npts), state.complex_type),
             "U": _native.pinned_empty((max(n_U, 1), npts), np.int32),
             "sr": _native.pinned_empty((1, npts), np.int8),
@@ -148,19 +153,11 @@ def render_frame_to_staging(f, calc_name):
         _STAGE["grid"] = None
     b = _STAGE["bufs"]
     gkey = (f.nx, f.ny, f.xy_ratio)
-    if _STAGE.get("grid") != gkey:       # pixel offsets depend on the grid only
-        off = 0
-        shapes = []
-        for cs in f.chunk_slices():
-            pos = f.chunk_pixel_pos(cs, False, None)
-            pix = np.ravel(pos)
-            shapes.append((pos.shape[1], pos.shape[0]))
-            b["c_pix"][off:off + pix.shape[0]] = pix
-            off += pix.shape[0]
+    if _STAGE.get("grid") != gkey:       # the per-tile axes depend on the grid only
+        from .core import TileAxes
+        _STAGE["axes"] = TileAxes(f, list(f.chunk_slices()))
         _STAGE["grid"] = gkey
-        _STAGE["tiles"] = shapes
-    rc = f.numba_cycle_call((b["c_pix"], b["Z"], b["U"][:n_U], b["sr"], b["si"]), indep,
-                            tiles=_STAGE["tiles"])
+    rc = f.numba_cycle_call((_STAGE["axes"], b["Z"], b["U"][:n_U], b["sr"], b["si"]), indep)
     if rc != 0:
         raise RuntimeError("frame interrupted")
     from .core import Fractal

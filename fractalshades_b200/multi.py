@@ -29,10 +29,51 @@ def tiles_for_rank(n_tiles, rank, world, costs=None):
     return [int(t) for t in np.nonzero(owner == rank)[0]]
 
 
+class RankTiles:
+    """ `tile_validator` selecting one rank's tiles (callable on a chunk slice).
+    It also carries (rank, world), which lets `Fractal.calc_raw` refuse the one
+    unsafe use: several ranks creating the shared memmaps at the same time. """
+
+    def __init__(self, fractal, rank, world, costs=None):
+        self.rank, self.world = int(rank), int(world)
+        self.fractal = fractal
+        self.mine = set(tiles_for_rank(fractal.chunks_count, rank, world, costs))
+        self.files_ready = False      # set by calc_raw_sharded after the barrier
+
+    def __call__(self, chunk_slice):
+        return self.fractal.chunk_rank(chunk_slice) in self.mine
+
+
 def tile_validator(fractal, rank, world, costs=None):
-    """ A `tile_validator` for Fractal.calc_raw selecting this rank's tiles """
-    mine = set(tiles_for_rank(fractal.chunks_count, rank, world, costs))
-    return lambda chunk_slice: fractal.chunk_rank(chunk_slice) in mine
+    """ A `tile_validator` (core.py:2521-2523) selecting this rank's tiles.
+
+    ORDERING REQUIRED when the ranks share one directory: the report and data
+    memmaps must be created by ONE rank before any other rank opens them --
+    `Fractal.calc_raw` creates them with mode "w+", which truncates: a late rank
+    creating them again would wipe the `done` flags and the slabs the others
+    have already written.  Use `calc_raw_sharded`, which implements the
+    protocol (rank 0 creates, barrier, the others bind, everybody computes);
+    calling `calc_raw` directly with a validator of a rank > 0 while the files
+    still have to be created raises. """
+    return RankTiles(fractal, rank, world, costs)
+
+
+def calc_raw_sharded(fractal, calc_name, rank, world, barrier, costs=None):
+    """ One frame's tiles over `world` ranks sharing `fractal.directory`:
+    rank 0 creates the memmaps, `barrier()` (e.g. torch.distributed.barrier),
+    the other ranks bind to the existing files, every rank computes its own
+    tiles and writes its slabs (the final tile gather), `barrier()` again.
+    Every rank must have run the same calc_std_div(...) before. """
+    v = tile_validator(fractal, rank, world, costs)
+    if rank == 0:
+        fractal.prepare_mmaps(calc_name)
+    barrier()
+    if rank != 0:
+        fractal.bind_mmaps(calc_name)
+    v.files_ready = True
+    fractal.calc_raw(calc_name, tile_validator=v)
+    barrier()
+    return v
 
 
 def frames_for_rank(n_frames, rank, world):
@@ -41,14 +82,11 @@ def frames_for_rank(n_frames, rank, world):
     return list(range(rank, n_frames, max(world, 1)))
 
 
-def reduce_timing(total_ms, units, dist=None, device=None):
+def reduce_timing(total_ms, units, all_reduce_max=None, all_reduce_sum=None):
     """ (max over ranks of the timed duration, sum over ranks of the processed
-    units): the throughput of the whole job is sum / max """
-    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+    units): the throughput of the whole job is sum / max.  The two reductions
+    are callables supplied by the launcher (bench.py wraps torch.distributed);
+    this package itself has no torch dependency. """
+    if all_reduce_max is None or all_reduce_sum is None:
         return float(total_ms), float(units)
-    import torch
-    t = torch.tensor([float(total_ms)], dtype=torch.float64, device=device)
-    u = torch.tensor([float(units)], dtype=torch.float64, device=device)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dist.all_reduce(u, op=dist.ReduceOp.SUM)
-    return float(t[0]), float(u[0])
+    return float(all_reduce_max(float(total_ms))), float(all_reduce_sum(float(units)))

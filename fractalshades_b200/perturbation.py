@@ -84,8 +84,21 @@ class FrameHandle:
 
     def run(self, c_pix, Z, U, stop_reason, stop_iter, interrupted=None,
             tiles=None):
-        npts = c_pix.shape[0]
+        from .core import TileAxes, check_outputs
         stats = _native.FsbStats()
+        if isinstance(c_pix, TileAxes):
+            # tile scheduler: pixel offsets expanded on the device from the axes
+            check_outputs(c_pix.npts, Z, U, stop_reason, stop_iter, self.nz, None)
+            rc = self.lib.fsb_frame_run_grid(
+                self.ptr, c_pix.tw.shape[0], _native.ptr(c_pix.tw), _native.ptr(c_pix.th),
+                _native.ptr(c_pix.axes), _native.ptr(Z), _native.ptr(U),
+                _native.ptr(stop_reason), _native.ptr(stop_iter),
+                _native.ptr(interrupted), stats)
+            _native.check(self.lib, rc)
+            self.last_stats = stats.as_dict()
+            return rc
+        npts = c_pix.shape[0]
+        check_outputs(npts, Z, U, stop_reason, stop_iter, self.nz, c_pix)
         if tiles is not None:
             from .core import tile_shape_arrays
             tw, th = tile_shape_arrays(tiles, npts)

@@ -43,6 +43,8 @@ def _declare(lib):
     D = ctypes.POINTER(FsbPostprocDesc)
     lib.fsb_frame_run_pp.argtypes = [vp, i32, vp, vp, i64, vp, D, vp, vp, vp, vp, vp, vp, vp,
                                      ctypes.POINTER(_native.FsbStats)]
+    lib.fsb_frame_run_grid_pp.argtypes = [vp, i32, vp, vp, vp, D, vp, vp, vp, vp, vp, vp, vp,
+                                          ctypes.POINTER(_native.FsbStats)]
     lib.fsb_postproc_run.argtypes = [D, i64, i32, vp, vp, vp, vp, vp, vp]
     lib.fsb_postproc_run_device.argtypes = [D, i64, i32, vp, vp, vp, vp, vp, vp]
     lib._pp_declared = True
@@ -80,6 +82,22 @@ def make_desc(fractal, calc_name, floor_iter=0, px_snap=None, dtype=np.float32):
     return d, dtype, len(codes)
 
 
+def _check_projection(fractal, names):
+    """ The reference scales / rotates dzndc by the projection's derivative
+    before DEM and normals (Postproc.get_dzndc -> apply_df / apply_dfBS with
+    proj.df, postproc.py:184-206); k_postproc does not: refused, never
+    approximated. """
+    from . import projection as _projection
+    if not (set(names) & {"DEM", "normal_x", "normal_y"}):
+        return
+    proj = fractal.projection
+    if not (type(proj) is _projection.Cartesian and getattr(proj, "expmap_seam", None) is None):
+        raise NotImplementedError(
+            "GPU DEM / normal post-processing is defined for the plain Cartesian "
+            f"projection only (got {type(proj).__name__}): the projection derivative of "
+            "Postproc.get_dzndc is not applied by k_postproc")
+
+
 def _outputs(fields, npts, dtype, have_deriv):
     want = set(fields)
     if "normal" in want:
@@ -104,33 +122,34 @@ def fields_from_raw(fractal, calc_name, Z, stop_iter, fields=("cont_iter", "DEM"
     si = np.ascontiguousarray(np.ravel(stop_iter), dtype=np.int32)
     npts = Z.shape[1]
     out = _outputs(fields, npts, dtype, d.row_dzndc >= 0)
+    _check_projection(fractal, out)
     rc = lib.fsb_postproc_run(ctypes.byref(d), npts, Z.shape[0], _native.ptr(Z), _native.ptr(si),
                               *[_native.ptr(out.get(k)) for k in FIELDS])
     _native.check(lib, rc)
     return out
 
 
-def _frame_staging(fractal, names, dtype):
-    """ Page-locked buffers of one frame geometry, kept on the fractal: the
-    tile-ordered pixel offsets (they depend on nx, ny, xy_ratio only) and one
-    output array per field. """
-    key = (fractal.nx, fractal.ny, fractal.xy_ratio, settings_chunk())
-    st = getattr(fractal, "_pp_staging", None)
+_STAGING = {}
+
+
+def _frame_staging(fractal, names, dtype, tiles=None):
+    """ Per frame geometry, kept on the fractal: the per-tile pixel axes (they
+    depend on nx, ny, xy_ratio only; the pixel grid itself is built on the
+    device) and one page-locked output array per field. """
+    tiles = list(fractal.chunk_slices()) if tiles is None else list(tiles)
+    key = (fractal.nx, fractal.ny, fractal.xy_ratio, settings_chunk(), tuple(tiles))
+    # one staging set per process (the frames of a zoom movie share it; page-locked
+    # allocations of a few hundred MB cost more than an 8K frame's kernels)
+    st = _STAGING.get("cur")
     if st is None or st["key"] != key:
         if st is not None:
             for a in st["bufs"].values():
                 _native.pinned_free(a)
-        shapes, pix = [], []
-        for cs in fractal.chunk_slices():
-            pos = fractal.chunk_pixel_pos(cs, False, None)
-            shapes.append((pos.shape[1], pos.shape[0]))
-            pix.append(np.ravel(pos))
-        npts = int(sum(p.shape[0] for p in pix))
-        c_pix = _native.pinned_empty((npts,), np.complex128)
-        c_pix[:] = np.concatenate(pix)
-        tw, th = tile_shape_arrays(shapes, npts)
-        st = {"key": key, "npts": npts, "tw": tw, "th": th, "bufs": {"c_pix": c_pix}}
-        fractal._pp_staging = st
+        from .core import TileAxes
+        ta = TileAxes(fractal, tiles)
+        st = {"key": key, "npts": ta.npts, "tw": ta.tw, "th": ta.th, "axes": ta.axes,
+              "bufs": {}}
+        _STAGING["cur"] = st
     for name, dt in names:
         cur = st["bufs"].get(name)
         if cur is None or cur.dtype != np.dtype(dt):
@@ -146,11 +165,13 @@ def settings_chunk():
 
 
 def frame_fields(fractal, calc_name, fields=("cont_iter", "DEM", "normal"), floor_iter=0,
-                 px_snap=None, dtype=np.float32, want_stop_iter=False, copy=True):
-    """ Fused: pixel kernels + post-processing of one whole perturbation frame.
-    Returns (dict of tile-ordered 1-D fields incl. "stop_reason", stats).
-    Use `to_image` for the (ny, nx) arrays.  copy=False returns views of the
-    page-locked staging buffers (overwritten by the next call). """
+                 px_snap=None, dtype=np.float32, want_stop_iter=False, copy=True, tiles=None):
+    """ Fused: pixel kernels + post-processing of one whole perturbation frame
+    (or of the listed tiles: `tiles` = chunk slices, e.g. one rank's share of
+    the frame).  Returns (dict of tile-ordered 1-D fields incl. "stop_reason",
+    stats).  Use `to_image` for the (ny, nx) arrays of a whole frame.
+    copy=False returns views of the page-locked staging buffers (overwritten
+    by the next call). """
     lib = _declare(_native.cuda_lib())
     indep = fractal._calc_data[calc_name]["cycle_indep_args"]
     if indep[0] != "perturb":
@@ -159,18 +180,20 @@ def frame_fields(fractal, calc_name, fields=("cont_iter", "DEM", "normal"), floo
     frame, interrupted = indep[1], indep[2]
     d, dtype, _ = make_desc(fractal, calc_name, floor_iter, px_snap, dtype)
     names = list(_outputs(fields, 0, dtype, d.row_dzndc >= 0))
+    _check_projection(fractal, names)
     want = [(k, dtype) for k in names] + [("stop_reason", np.int8)]
     if want_stop_iter:
         want.append(("stop_iter", np.int32))
-    st = _frame_staging(fractal, want, dtype)
+    st = _frame_staging(fractal, want, dtype, tiles)
     b, npts = st["bufs"], st["npts"]
     out = {k: b[k] for k, _ in want}
     stats = _native.FsbStats()
-    rc = lib.fsb_frame_run_pp(frame.ptr, st["tw"].shape[0], _native.ptr(st["tw"]),
-                              _native.ptr(st["th"]), npts, _native.ptr(b["c_pix"]),
-                              ctypes.byref(d), *[_native.ptr(out.get(k)) for k in FIELDS],
-                              _native.ptr(out["stop_reason"]), _native.ptr(out.get("stop_iter")),
-                              _native.ptr(interrupted), stats)
+    rc = lib.fsb_frame_run_grid_pp(frame.ptr, st["tw"].shape[0], _native.ptr(st["tw"]),
+                                   _native.ptr(st["th"]), _native.ptr(st["axes"]),
+                                   ctypes.byref(d), *[_native.ptr(out.get(k)) for k in FIELDS],
+                                   _native.ptr(out["stop_reason"]),
+                                   _native.ptr(out.get("stop_iter")),
+                                   _native.ptr(interrupted), stats)
     _native.check(lib, rc)
     if rc != 0:
         raise RuntimeError("frame interrupted")

@@ -259,6 +259,30 @@ int fsb_frame_run_pp(fsb_frame *f, int32_t n_tiles, const int32_t *tile_w,
                      const fsb_postproc_desc *pp, void *nu, void *dem, void *normal_x,
                      void *normal_y, int8_t *stop_reason, int32_t *stop_iter,
                      const volatile uint8_t *interrupted, fsb_stats *stats);
+/* ---- grid calls (GPU tile scheduler) --------------------------------------
+ * Same as fsb_std_run_tiles / fsb_frame_run_tiles / fsb_frame_run_pp, but the
+ * pixel offsets are given by per-tile axes instead of a complex128[npts]
+ * array: `axes` holds, for each tile k in order, tile_w[k] x values then
+ * tile_h[k] y values, and the point (row r, column col) of tile k is
+ * x_k[col] + i y_k[r] -- exactly Fractal.chunk_pixel_pos without jitter
+ * (core.py:1767-1830: meshgrid of two linspace axes; y already negated and
+ * divided by xy_ratio).  The library expands them on the device (k_expand_grid):
+ * a 4K frame sends 0.7 MB over PCIe instead of 133 MB.  Replaces the c_pix
+ * argument built by Fractal.get_cycling_dep_args (core.py:2044-2075) for the
+ * tiles dispatched by compute_rawdata_dev (core.py:2515-2554). */
+int fsb_std_run_grid(const fsb_std_desc *d, int32_t n_tiles, const int32_t *tile_w,
+                     const int32_t *tile_h, const double *axes, double *Z,
+                     int8_t *stop_reason, int32_t *stop_iter,
+                     const volatile uint8_t *interrupted, fsb_stats *stats);
+int fsb_frame_run_grid(fsb_frame *f, int32_t n_tiles, const int32_t *tile_w,
+                       const int32_t *tile_h, const double *axes, double *Z, int32_t *U,
+                       int8_t *stop_reason, int32_t *stop_iter,
+                       const volatile uint8_t *interrupted, fsb_stats *stats);
+int fsb_frame_run_grid_pp(fsb_frame *f, int32_t n_tiles, const int32_t *tile_w,
+                          const int32_t *tile_h, const double *axes,
+                          const fsb_postproc_desc *pp, void *nu, void *dem, void *normal_x,
+                          void *normal_y, int8_t *stop_reason, int32_t *stop_iter,
+                          const volatile uint8_t *interrupted, fsb_stats *stats);
 /* stand-alone: raw fields already on the device / on the host (n_rows rows of Z) */
 int fsb_postproc_run_device(const fsb_postproc_desc *pp, int64_t npts, int32_t n_rows,
                             const double *d_Z, const int32_t *d_stop_iter, void *d_nu,

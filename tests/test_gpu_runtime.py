@@ -289,3 +289,39 @@ def test_tile_list_standard_loop_and_bad_tiles():
     assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2])
     with pytest.raises(ValueError):
         f.numba_cycle_call((c_pix, Z, U, sr, si), indep, tiles=[(10, 10)])
+
+
+def test_grid_calls_match_cpix_calls():
+    """ fsb_*_run_grid (pixel grid expanded on the device from per-tile axes) =
+    the c_pix calls, bit for bit, for a perturbation frame and a standard one """
+    from fractalshades_b200.core import TileAxes
+    for f in (_perturb_fractal(nx=450), None):
+        if f is None:
+            f = fsm.Mandelbrot(tempfile.mkdtemp())
+            f.zoom(x=-0.7, y=0.2, dx=2.5, nx=450, xy_ratio=1.5, theta_deg=20.)
+            f.calc_std_div(calc_name="c", subset=None, max_iter=2000, M_divergence=1e3,
+                           epsilon_stationnary=1e-3)
+        indep = f._calc_data["c"]["cycle_indep_args"]
+        state = f._calc_data["c"]["state"]
+        tiles = list(f.chunk_slices())
+        ta = TileAxes(f, tiles)
+        n = ta.npts
+        n_Z, n_U = len(state.codes[0]), len(state.codes[1])
+        out = []
+        for src in ("grid", "c_pix"):
+            Z = np.zeros((n_Z, n), state.complex_type)
+            U = np.zeros((n_U, n), np.int32)
+            sr = -np.ones((1, n), np.int8)
+            si = np.zeros((1, n), np.int32)
+            if src == "grid":
+                rc = f.numba_cycle_call((ta, Z, U, sr, si), indep)
+            else:
+                c_pix = np.ascontiguousarray(np.concatenate(
+                    [np.ravel(f.chunk_pixel_pos(cs, False, None)) for cs in tiles]))
+                rc = f.numba_cycle_call((c_pix, Z, U, sr, si), indep, tiles=ta.shapes)
+            assert rc == 0
+            out.append((Z, U, sr, si))
+        (Z0, U0, sr0, si0), (Z1, U1, sr1, si1) = out
+        assert np.array_equal(si0, si1) and np.array_equal(sr0, sr1) and np.array_equal(U0, U1)
+        assert pc.same_bits(Z0, Z1)
+        assert (sr0 >= 0).all()

@@ -296,3 +296,46 @@ def test_pixel_grid_with_jitter_and_supersampling_matches_reference():
             samples.append(flat[np.linspace(0, flat.size - 1, 16).astype(np.int64)])
         assert np.array_equal(np.concatenate(samples), g[f"samples_{k}"]), m
         assert shas == m["sha"], m
+
+
+def test_tile_axes_reproduce_the_pixel_grid():
+    """ the per-tile axes sent to the grid calls (fsb_*_run_grid expands them on
+    the device) give back chunk_pixel_pos bit for bit, ragged tiles included """
+    import fractalshades_b200.models as fsm
+    from fractalshades_b200.core import TileAxes
+    f = fsm.Mandelbrot(tempfile.mkdtemp())
+    f.zoom(x=-0.5, y=0.1, dx=3., nx=450, xy_ratio=16 / 9., theta_deg=10.)
+    tiles = list(f.chunk_slices())
+    ta = TileAxes(f, tiles)
+    assert ta.npts == f.nx * f.ny and ta.axes.dtype == np.float64
+    off = 0
+    for cs, (w, h) in zip(tiles, ta.shapes):
+        x, y = ta.axes[off:off + w], ta.axes[off + w:off + w + h]
+        off += w + h
+        pos = f.chunk_pixel_pos(cs, False, None)
+        assert pos.shape == (h, w)
+        assert np.array_equal(pos.real, np.broadcast_to(x[None, :], (h, w)))
+        assert np.array_equal(pos.imag, np.broadcast_to(y[:, None], (h, w)))
+    assert off == ta.axes.shape[0]
+
+
+def test_seam_validates_caller_buffers():
+    """ the library copies nz * npts elements into Z: a buffer of another shape
+    or type is refused before the call """
+    import pytest
+    from fractalshades_b200.core import check_outputs
+    n = 100
+    c = np.zeros(n, np.complex128)
+    Z = np.zeros((2, n), np.complex128)
+    U = np.zeros((1, n), np.int32)
+    sr = np.zeros((1, n), np.int8)
+    si = np.zeros((1, n), np.int32)
+    check_outputs(n, Z, U, sr, si, 2, c)
+    for bad in (dict(Z=np.zeros((1, n), np.complex128)), dict(Z=np.zeros((2, n - 1), np.complex128)),
+                dict(Z=np.zeros((2, n), np.float32)), dict(U=np.zeros((1, n), np.int64)),
+                dict(sr=np.zeros((1, n), np.int32)), dict(si=np.zeros((1, n + 1), np.int32)),
+                dict(c=np.zeros(n, np.float64)), dict(Z=np.zeros((n, 2), np.complex128).T)):
+        kw = dict(Z=Z, U=U, sr=sr, si=si, c=c)
+        kw.update(bad)
+        with pytest.raises(ValueError):
+            check_outputs(n, kw["Z"], kw["U"], kw["sr"], kw["si"], 2, kw["c"])

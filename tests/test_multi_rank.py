@@ -34,16 +34,19 @@ def setup():
     kw = dict(calc_name="c", subset=None, max_iter=100, M_divergence=1000., epsilon_stationnary=1e-3)
     f.calc_std_div(**kw)
     return f
-# rank 0 creates the directory, the parameter files and the memmaps first
+# the protocol of multi.calc_raw_sharded: rank 0 creates the directory, the
+# parameter files and the memmaps, barrier, the others bind to them
 if rank == 0:
     f = setup()
-    f.init_report_mmap("c"); f.init_data_mmaps("c")
+    f.prepare_mmaps("c")
     dist.barrier()
 else:
     dist.barrier()
     f = setup()
+    f.bind_mmaps("c")
 dist.barrier()
 validator = multi.tile_validator(f, rank, world)
+assert (validator.rank, validator.world) == (rank, world)
 n_mine = 0
 for cs in f.chunk_slices():
     if not validator(cs):
@@ -54,7 +57,14 @@ for cs in f.chunk_slices():
     f.update_data_mmaps("c", cs, Z, U, sr, si)
     f.update_report_mmap("c", cs)
     n_mine += 1
-tmax, usum = multi.reduce_timing(10.0 * (rank + 1), n_mine, dist)
+import torch
+def _red(op):
+    def f_(v):
+        t = torch.tensor([v], dtype=torch.float64)
+        dist.all_reduce(t, op=op)
+        return float(t[0])
+    return f_
+tmax, usum = multi.reduce_timing(10.0 * (rank + 1), n_mine, _red(dist.ReduceOp.MAX), _red(dist.ReduceOp.SUM))
 dist.barrier()
 if rank == 0:
     rep = np.array(f.get_report_memmap("c", mode="r"))
@@ -83,6 +93,28 @@ def test_tile_partition_properties():
     assert max(loads) / (sum(loads) / 8) < 1.02          # balanced within 2 %
     assert multi.frames_for_rank(64, 3, 8) == list(range(3, 64, 8))
     assert multi.reduce_timing(5., 7.) == (5., 7.)
+
+
+def test_calc_raw_refuses_concurrent_creation():
+    """ a rank > 0 validator must not be the one that creates (truncates) the
+    shared memmaps: calc_raw raises before touching any file or the GPU """
+    import pytest
+    import fractalshades_b200.models as fsm
+    f = fsm.Mandelbrot(tempfile.mkdtemp())
+    f.zoom(x=-1., y=0., dx=5., nx=64, xy_ratio=1., theta_deg=0.)
+    f.calc_std_div(calc_name="c", subset=None, max_iter=10, M_divergence=100.,
+                   epsilon_stationnary=1e-3)
+    v = multi.tile_validator(f, 1, 2)
+    assert f._calc_data["c"]["need_new_mmap"]
+    with pytest.raises(RuntimeError, match="calc_raw_sharded"):
+        f.calc_raw("c", tile_validator=v)
+    assert not os.path.exists(f.report_path("c"))
+    # binding to files that do not exist fails loudly too
+    with pytest.raises(FileNotFoundError):
+        f.bind_mmaps("c")
+    f.prepare_mmaps("c")
+    f.bind_mmaps("c")
+    assert not f._calc_data["c"]["need_new_mmap"]
 
 
 def test_two_ranks_gloo_shared_memmaps():

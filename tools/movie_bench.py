@@ -49,7 +49,18 @@ def main():
     total_s = time.time() - t0
     iters = sum(r["sum_stop_iter"] for r in recs)
     kernel_ms = sum(r["kernel_ms"] for r in recs)
-    tmax, isum = multi.reduce_timing(total_s * 1e3, iters, dist, device="cuda" if dist else None)
+    red_max = red_sum = None
+    if dist is not None:
+        import torch
+
+        def _red(op):
+            def f_(v):
+                t = torch.tensor([v], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=op)
+                return float(t[0])
+            return f_
+        red_max, red_sum = _red(dist.ReduceOp.MAX), _red(dist.ReduceOp.SUM)
+    tmax, isum = multi.reduce_timing(total_s * 1e3, iters, red_max, red_sum)
     if rank == 0:
         print(json.dumps({
             "workload": f"deep-zoom movie {args.frames} frames {args.dx_start}->{args.dx_end} at {args.nx}px",
