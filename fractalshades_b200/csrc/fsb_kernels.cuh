@@ -958,153 +958,6 @@ __device__ __forceinline__ void bs_iterate_perturb(int flavor, double xn, double
     }
 }
 
-/* burning_ship.py:19-60 */
-template <class T> __device__ __forceinline__ T diffabs(T X, T x)
-{
-    if (X >= 0.) {
-        if ((X + x) >= 0.) return 1. * x;
-        return -(2. * X + x);
-    }
-    if ((X + x) <= 0.) return -x;
-    return (2. * X + x);
-}
-template <class T> __device__ __forceinline__ double ddiffabsdX(T X, T x)
-{
-    if (X >= 0.) { if ((X + x) >= 0.) return 0.; return -2.; }
-    if ((X + x) <= 0.) return 0.;
-    return 2.;
-}
-template <class T> __device__ __forceinline__ double ddiffabsdx(T X, T x)
-{
-    if (X >= 0.) { if ((X + x) >= 0.) return 1.; return -1.; }
-    if ((X + x) <= 0.) return -1.;
-    return 1.;
-}
-
-/* burning_ship.py:535-619 */
-template <class T>
-__device__ __forceinline__ void bs_p_iter_zn(int flavor, T &x, T &y, T rx, T ry, T a, T b)
-{
-    T nx, ny;
-    switch (flavor) {
-    case 1: {
-        T rxy = rx * ry;
-        nx = x * (x + 2. * rx) - y * (y + 2. * ry) + a;
-        ny = 2. * diffabs(rxy, x * y + x * ry + y * rx) - b;
-        break;
-    }
-    case 2:
-        nx = x * (x + 2. * rx) - y * (y + 2. * ry) + a;
-        ny = 2. * (rx * diffabs(ry, y) + x * fabs_(ry + y)) - b;
-        break;
-    case 3:
-        nx = x * (x + 2. * rx) - ry * diffabs(ry, y) - y * fabs_(ry + y) + a;
-        ny = 2. * (rx * y + ry * x + x * y) - b;
-        break;
-    case 4: {
-        T r2 = rx * rx - ry * ry;
-        nx = diffabs(r2, x * (x + 2. * rx) - y * (y + 2. * ry)) + a;
-        ny = 2. * (rx * y + ry * x + x * y) - b;
-        break;
-    }
-    default: {
-        T rxy = rx * ry;
-        T r2 = rx * rx - ry * ry;
-        nx = diffabs(r2, x * (x + 2. * rx) - y * (y + 2. * ry)) + a;
-        ny = 2. * diffabs(rxy, x * y + x * ry + y * rx) - b;
-        break;
-    }
-    }
-    x = nx; y = ny;
-}
-
-/* burning_ship.py:622-859 */
-template <class T>
-__device__ __forceinline__ void bs_p_iter_hessian(int flavor, T x, T y, T &dxa, T &dxb,
-                                                  T &dya, T &dyb, T rx, T ry, T rdxa,
-                                                  T rdxb, T rdya, T rdyb)
-{
-    T ndxa, ndxb, ndya, ndyb;
-    switch (flavor) {
-    case 1: {
-        T opX = rx * ry;
-        T dXa = rdxa * ry + rx * rdya;
-        T dXb = rdxb * ry + rx * rdyb;
-        T opx = x * y + x * ry + y * rx;
-        T dxa_ = dxa * y + x * dya + dxa * ry + x * rdya + dya * rx + y * rdxa;
-        T dxb_ = dxb * y + x * dyb + dxb * ry + x * rdyb + dyb * rx + y * rdxb;
-        double dX = ddiffabsdX(opX, opx), dx = ddiffabsdx(opX, opx);
-        ndxa = 2. * ((rx + x) * dxa + rdxa * x) - 2. * ((ry + y) * dya + rdya * y);
-        ndxb = 2. * ((rx + x) * dxb + rdxb * x) - 2. * ((ry + y) * dyb + rdyb * y);
-        ndya = 2. * (dX * dXa + dx * dxa_);
-        ndyb = 2. * (dX * dXb + dx * dxb_);
-        break;
-    }
-    case 2: {
-        T da = diffabs(ry, y);
-        double dX = ddiffabsdX(ry, y), dx = ddiffabsdx(ry, y);
-        T Yy = ry + y;
-        T ab = fabs_(Yy);
-        double sg = sgn_(Yy);
-        ndxa = 2. * (((rx + x) * dxa + rdxa * x) - ((ry + y) * dya + rdya * y));
-        ndxb = 2. * (((rx + x) * dxb + rdxb * x) - ((ry + y) * dyb + rdyb * y));
-        ndya = 2. * (rdxa * da + rx * (dX * rdya + dx * dya) + dxa * ab + x * sg * (rdya + dya));
-        ndyb = 2. * (rdxb * da + rx * (dX * rdyb + dx * dyb) + dxb * ab + x * sg * (rdyb + dyb));
-        break;
-    }
-    case 3: {
-        T da = diffabs(ry, y);
-        double dX = ddiffabsdX(ry, y), dx = ddiffabsdx(ry, y);
-        T Yy = ry + y;
-        T ab = fabs_(Yy);
-        double sg = sgn_(Yy);
-        ndxa = dxa * (x + 2. * rx) + x * (dxa + 2. * rdxa) - rdya * da
-               - ry * (rdya * dX + dya * dx) - dya * ab - y * sg * (rdya + dya);
-        ndxb = dxb * (x + 2. * rx) + x * (dxb + 2. * rdxb) - rdyb * da
-               - ry * (rdyb * dX + dyb * dx) - dyb * ab - y * sg * (rdyb + dyb);
-        ndya = 2. * (rdxa * y + rx * dya + rdya * x + ry * dxa + dxa * y + x * dya);
-        ndyb = 2. * (rdxb * y + rx * dyb + rdyb * x + ry * dxb + dxb * y + x * dyb);
-        break;
-    }
-    case 4: {
-        T opX = rx * rx - ry * ry;
-        T dXa = 2. * (rx * rdxa - ry * rdya);
-        T dXb = 2. * (rx * rdxb - ry * rdyb);
-        T opx = x * (x + 2. * rx) - y * (y + 2. * ry);
-        T dxa_ = dxa * (x + 2. * rx) + x * (dxa + 2. * rdxa) - dya * (y + 2. * ry) - y * (dya + 2. * rdya);
-        T dxb_ = dxb * (x + 2. * rx) + x * (dxb + 2. * rdxb) - dyb * (y + 2. * ry) - y * (dyb + 2. * rdyb);
-        double dX = ddiffabsdX(opX, opx), dx = ddiffabsdx(opX, opx);
-        ndxa = dX * dXa + dx * dxa_;
-        ndxb = dX * dXb + dx * dxb_;
-        ndya = 2. * (rdxa * y + rx * dya + rdya * x + ry * dxa + dxa * y + x * dya);
-        ndyb = 2. * (rdxb * y + rx * dyb + rdyb * x + ry * dxb + dxb * y + x * dyb);
-        break;
-    }
-    default: {
-        T opX = rx * rx - ry * ry;
-        T dXa = 2. * (rx * rdxa - ry * rdya);
-        T dXb = 2. * (rx * rdxb - ry * rdyb);
-        T opx = x * (x + 2. * rx) - y * (y + 2. * ry);
-        T dxa_ = dxa * (x + 2. * rx) + x * (dxa + 2. * rdxa) - dya * (y + 2. * ry) - y * (dya + 2. * rdya);
-        T dxb_ = dxb * (x + 2. * rx) + x * (dxb + 2. * rdxb) - dyb * (y + 2. * ry) - y * (dyb + 2. * rdyb);
-        double dX = ddiffabsdX(opX, opx), dx = ddiffabsdx(opX, opx);
-        ndxa = dX * dXa + dx * dxa_;
-        ndxb = dX * dXb + dx * dxb_;
-        T opX2 = rx * ry;
-        T dXa2 = rdxa * ry + rx * rdya;
-        T dXb2 = rdxb * ry + rx * rdyb;
-        T opx2 = x * y + x * ry + y * rx;
-        T dxa2 = dxa * y + x * dya + dxa * ry + x * rdya + dya * rx + y * rdxa;
-        T dxb2 = dxb * y + x * dyb + dxb * ry + x * rdyb + dyb * rx + y * rdxb;
-        double dX2 = ddiffabsdX(opX2, opx2), dx2 = ddiffabsdx(opX2, opx2);
-        ndya = 2. * (dX2 * dXa2 + dx2 * dxa2);
-        ndyb = 2. * (dX2 * dXb2 + dx2 * dxb2);
-        break;
-    }
-    }
-    dxa = ndxa; dxb = ndxb; dya = ndya; dyb = ndyb;
-}
-
 /* perturbation.py:1793-1811 */
 template <class T>
 __device__ __forceinline__ void apply_bla_bs(const double *M, T &x, T &y, T a, T b)
@@ -1123,43 +976,6 @@ __device__ __forceinline__ void apply_bla_deriv_bs(const double *M, T &dxa, T &d
     dxa = a; dxb = b; dya = c; dyb = d;
 }
 
-/* Fused Xrange forms of apply_BLA_BS / apply_BLA_deriv_BS
- * (perturbation.py:1793-1811), same idea as xr_lin: every product and every
- * add of the reference's left-to-right chain is performed once, on mantissas
- * aligned by exponent-field arithmetic; zero terms pass through an addition as
- * in _coexp_ufunc (numba_xr.py:716-733). */
-#define XR_ZERO_E (-(1 << 28))
-__device__ __forceinline__ XF xf_prod(double M, XF v)
-{
-    const double p = M * v.m;
-    const int fld = expfield(p);
-    return mkXF(xshift(p, 1023 - fld), (fld == 0) ? XR_ZERO_E : v.e + (fld - 1023));
-}
-__device__ __forceinline__ XF xf_sum(XF s, XF p)
-{
-    const int se = (s.m == 0.) ? XR_ZERO_E : s.e;
-    const int e = max(se, p.e);
-    return mkXF(xshift(s.m, se - e) + xshift(p.m, p.e - e), e);
-}
-__device__ __forceinline__ XF xf_dot2(double m0, XF u, double m1, XF v)
-{
-    return xf_sum(xf_prod(m0, u), xf_prod(m1, v));
-}
-__device__ __forceinline__ XF xf_dot4(double m0, XF u, double m1, XF v, double m2, XF a,
-                                      double m3, XF b)
-{
-    return xf_sum(xf_sum(xf_dot2(m0, u, m1, v), xf_prod(m2, a)), xf_prod(m3, b));
-}
-__device__ __forceinline__ XF xf_clean(XF x)      /* zero results carry exponent 0 */
-{
-    return mkXF(x.m, (x.m == 0.) ? 0 : x.e);
-}
-/* to_standard of a value whose mantissa is below 4 in magnitude */
-__device__ __forceinline__ double to_std_small(XF x)
-{
-    if (x.e < -1200) return mk64(hi32(x.m) & (int)0x80000000, 0);
-    return to_std(x);
-}
 __device__ __forceinline__ void apply_bla_bs_xr(const double *M, XF &x, XF &y, XF a, XF b)
 {
     const XF nx = xf_clean(xf_dot4(M[0], x, M[1], y, M[4], a, M[5], b));
@@ -1352,7 +1168,29 @@ k_perturb_bs(const __grid_constant__ FrameDev f, long long npts_ll,
                 fast = false;
             }
 
-            if (!done_fast) {
+            bool done_tiny = false;
+#ifndef FSB_NO_FUSED_ITER
+            if (XR && !done_fast && flavor == 1 && k < 0
+                && bs_tiny_f1_ok(ref_zn.re, ref_zn.im, x_x, y_x)) {
+                /* fused exact forms for a tiny perturbation (fsb_lane.cuh) */
+                if (FASTXR) p_slow++;
+                if (HESS) {
+                    XF ra = record_zero, rb = record_zero, rc = record_zero, rd = record_zero;
+                    if (!bool_dyn_rebase) {
+                        ra = D_X(0, w_iter); rb = D_X(1, w_iter);
+                        rc = D_X(2, w_iter); rd = D_X(3, w_iter);
+                    }
+                    bs_tiny_f1_hessian(x_x, y_x, dxa_x, dxb_x, dya_x, dyb_x, ref_zn.re, ref_zn.im,
+                                       ra, rb, rc, rd);
+                }
+                bs_tiny_f1_zn(x_x, y_x, ref_zn.re, ref_zn.im, a_x, b_x);
+                x = to_std_small(x_x);
+                y = to_std_small(y_x);
+                if (FASTXR) TRY_FAST();
+                done_tiny = true;
+            }
+#endif
+            if (!done_fast && !done_tiny) {
                 if (XR && FASTXR) p_slow++;
                 XF rx_x = record_zero, ry_x = record_zero;
                 if (XR) {

@@ -292,7 +292,11 @@ FSB_HD bool in_fast_range(double x)
 }
 FSB_HD bool in_fast_range(C z)
 {
+#ifdef FSB_SC_GUARDS
     return in_fast_range(z.re) && in_fast_range(z.im);
+#else
+    return in_fast_range(z.re) & in_fast_range(z.im);
+#endif
 }
 
 /* Fused Xrange forms of the BLA step (perturbation.py:1139-1153).  Same real
@@ -316,15 +320,27 @@ FSB_HD double xshift(double m, int shift)
     nf = (fld == 0 || nf < 0) ? 0 : nf;
     return mk64((hi & (int)0x800fffff) | (nf << 20), lo32(m));
 }
-/* p 2^pe + q 2^qe: the aligned Xrange addition of two mantissa pairs */
+/* p 2^pe + q 2^qe: the aligned Xrange addition of two mantissa pairs.  When
+ * every part is a normal double and stays one after its shift, the shift is an
+ * addition on the high word (same bits as xshift). */
 FSB_HD XC xr_sum2(C p, int pe, C q, int qe)
 {
-    const int fp = cexp_field(p), fq = cexp_field(q);
+    const int hpr = hi32(p.re), hpi = hi32(p.im), hqr = hi32(q.re), hqi = hi32(q.im);
+    const int fpr = (hpr >> 20) & 0x7ff, fpi = (hpi >> 20) & 0x7ff;
+    const int fqr = (hqr >> 20) & 0x7ff, fqi = (hqi >> 20) & 0x7ff;
+    const int fp = imax(fpr, fpi), fq = imax(fqr, fqi);
     const int ep = pe + (fp - 1023), eq = qe + (fq - 1023);
     int e = imax(ep, eq);
     if (fp == 0) e = eq;              /* a zero product does not set the exponent */
     if (fq == 0) e = ep;
     const int sp = (1023 - fp) - (e - ep), sq = (1023 - fq) - (e - eq);
+#ifdef FSB_FAST_ALIGN   /* measured: slower (config 3 24.9 -> 26.1 ms: code size), off */
+    if (imin(imin(fpr, fpi) + sp, imin(fqr, fqi) + sq) >= 1 && imin(imin(fpr, fpi), imin(fqr, fqi)) >= 1) {
+        const int ap = sp << 20, aq = sq << 20;      /* (max field + shift <= 1023 by construction) */
+        return mkXC(mkC(mk64(hpr + ap, lo32(p.re)) + mk64(hqr + aq, lo32(q.re)),
+                        mk64(hpi + ap, lo32(p.im)) + mk64(hqi + aq, lo32(q.im))), e);
+    }
+#endif
     return mkXC(mkC(xshift(p.re, sp) + xshift(q.re, sq), xshift(p.im, sp) + xshift(q.im, sq)), e);
 }
 FSB_HD XC xr_lin(C A, XC z, C B, XC c)
@@ -334,8 +350,15 @@ FSB_HD XC xr_lin(C A, XC z, C B, XC c)
 FSB_HD XC xr_mulc(C A, XC d)
 {
     const C p = A * d.m;
-    const int fp = cexp_field(p);
-    return mkXC(mkC(xshift(p.re, 1023 - fp), xshift(p.im, 1023 - fp)), d.e + (fp - 1023));
+    const int hr = hi32(p.re), hi_ = hi32(p.im);
+    const int fr = (hr >> 20) & 0x7ff, fi = (hi_ >> 20) & 0x7ff;
+    const int fp = imax(fr, fi), sh = 1023 - fp;
+#ifdef FSB_FAST_ALIGN   /* measured: slower (config 3 24.9 -> 26.1 ms: code size), off */
+    if (imin(fr, fi) + sh >= 1 && imin(fr, fi) >= 1)
+        return mkXC(mkC(mk64(hr + (sh << 20), lo32(p.re)), mk64(hi_ + (sh << 20), lo32(p.im))),
+                    d.e + (fp - 1023));
+#endif
+    return mkXC(mkC(xshift(p.re, sh), xshift(p.im, sh)), d.e + (fp - 1023));
 }
 /* to_standard of a value whose mantissa parts are below 4 in magnitude */
 FSB_HD C to_std_small(XC x)
@@ -356,6 +379,268 @@ FSB_HD double flush_component(double m, int e)
     if (!(m == m) || ne > 1000) return mk64(0x7ff80000, 0);
     if (ne < -1022) return 0.;
     return ldexp(nm, ne);
+}
+
+/* ======================================================================== */
+/* Burning-ship family: model formulas and fused Xrange forms                */
+
+/* burning_ship.py:19-60 */
+template <class T> FSB_HD T diffabs(T X, T x)
+{
+    if (X >= 0.) {
+        if ((X + x) >= 0.) return 1. * x;
+        return -(2. * X + x);
+    }
+    if ((X + x) <= 0.) return -x;
+    return (2. * X + x);
+}
+template <class T> FSB_HD double ddiffabsdX(T X, T x)
+{
+    if (X >= 0.) { if ((X + x) >= 0.) return 0.; return -2.; }
+    if ((X + x) <= 0.) return 0.;
+    return 2.;
+}
+template <class T> FSB_HD double ddiffabsdx(T X, T x)
+{
+    if (X >= 0.) { if ((X + x) >= 0.) return 1.; return -1.; }
+    if ((X + x) <= 0.) return -1.;
+    return 1.;
+}
+
+/* burning_ship.py:535-619 */
+template <class T>
+FSB_HD void bs_p_iter_zn(int flavor, T &x, T &y, T rx, T ry, T a, T b)
+{
+    T nx, ny;
+    switch (flavor) {
+    case 1: {
+        T rxy = rx * ry;
+        nx = x * (x + 2. * rx) - y * (y + 2. * ry) + a;
+        ny = 2. * diffabs(rxy, x * y + x * ry + y * rx) - b;
+        break;
+    }
+    case 2:
+        nx = x * (x + 2. * rx) - y * (y + 2. * ry) + a;
+        ny = 2. * (rx * diffabs(ry, y) + x * fabs_(ry + y)) - b;
+        break;
+    case 3:
+        nx = x * (x + 2. * rx) - ry * diffabs(ry, y) - y * fabs_(ry + y) + a;
+        ny = 2. * (rx * y + ry * x + x * y) - b;
+        break;
+    case 4: {
+        T r2 = rx * rx - ry * ry;
+        nx = diffabs(r2, x * (x + 2. * rx) - y * (y + 2. * ry)) + a;
+        ny = 2. * (rx * y + ry * x + x * y) - b;
+        break;
+    }
+    default: {
+        T rxy = rx * ry;
+        T r2 = rx * rx - ry * ry;
+        nx = diffabs(r2, x * (x + 2. * rx) - y * (y + 2. * ry)) + a;
+        ny = 2. * diffabs(rxy, x * y + x * ry + y * rx) - b;
+        break;
+    }
+    }
+    x = nx; y = ny;
+}
+
+/* burning_ship.py:622-859 */
+template <class T>
+FSB_HD void bs_p_iter_hessian(int flavor, T x, T y, T &dxa, T &dxb,
+                                                  T &dya, T &dyb, T rx, T ry, T rdxa,
+                                                  T rdxb, T rdya, T rdyb)
+{
+    T ndxa, ndxb, ndya, ndyb;
+    switch (flavor) {
+    case 1: {
+        T opX = rx * ry;
+        T dXa = rdxa * ry + rx * rdya;
+        T dXb = rdxb * ry + rx * rdyb;
+        T opx = x * y + x * ry + y * rx;
+        T dxa_ = dxa * y + x * dya + dxa * ry + x * rdya + dya * rx + y * rdxa;
+        T dxb_ = dxb * y + x * dyb + dxb * ry + x * rdyb + dyb * rx + y * rdxb;
+        double dX = ddiffabsdX(opX, opx), dx = ddiffabsdx(opX, opx);
+        ndxa = 2. * ((rx + x) * dxa + rdxa * x) - 2. * ((ry + y) * dya + rdya * y);
+        ndxb = 2. * ((rx + x) * dxb + rdxb * x) - 2. * ((ry + y) * dyb + rdyb * y);
+        ndya = 2. * (dX * dXa + dx * dxa_);
+        ndyb = 2. * (dX * dXb + dx * dxb_);
+        break;
+    }
+    case 2: {
+        T da = diffabs(ry, y);
+        double dX = ddiffabsdX(ry, y), dx = ddiffabsdx(ry, y);
+        T Yy = ry + y;
+        T ab = fabs_(Yy);
+        double sg = sgn_(Yy);
+        ndxa = 2. * (((rx + x) * dxa + rdxa * x) - ((ry + y) * dya + rdya * y));
+        ndxb = 2. * (((rx + x) * dxb + rdxb * x) - ((ry + y) * dyb + rdyb * y));
+        ndya = 2. * (rdxa * da + rx * (dX * rdya + dx * dya) + dxa * ab + x * sg * (rdya + dya));
+        ndyb = 2. * (rdxb * da + rx * (dX * rdyb + dx * dyb) + dxb * ab + x * sg * (rdyb + dyb));
+        break;
+    }
+    case 3: {
+        T da = diffabs(ry, y);
+        double dX = ddiffabsdX(ry, y), dx = ddiffabsdx(ry, y);
+        T Yy = ry + y;
+        T ab = fabs_(Yy);
+        double sg = sgn_(Yy);
+        ndxa = dxa * (x + 2. * rx) + x * (dxa + 2. * rdxa) - rdya * da
+               - ry * (rdya * dX + dya * dx) - dya * ab - y * sg * (rdya + dya);
+        ndxb = dxb * (x + 2. * rx) + x * (dxb + 2. * rdxb) - rdyb * da
+               - ry * (rdyb * dX + dyb * dx) - dyb * ab - y * sg * (rdyb + dyb);
+        ndya = 2. * (rdxa * y + rx * dya + rdya * x + ry * dxa + dxa * y + x * dya);
+        ndyb = 2. * (rdxb * y + rx * dyb + rdyb * x + ry * dxb + dxb * y + x * dyb);
+        break;
+    }
+    case 4: {
+        T opX = rx * rx - ry * ry;
+        T dXa = 2. * (rx * rdxa - ry * rdya);
+        T dXb = 2. * (rx * rdxb - ry * rdyb);
+        T opx = x * (x + 2. * rx) - y * (y + 2. * ry);
+        T dxa_ = dxa * (x + 2. * rx) + x * (dxa + 2. * rdxa) - dya * (y + 2. * ry) - y * (dya + 2. * rdya);
+        T dxb_ = dxb * (x + 2. * rx) + x * (dxb + 2. * rdxb) - dyb * (y + 2. * ry) - y * (dyb + 2. * rdyb);
+        double dX = ddiffabsdX(opX, opx), dx = ddiffabsdx(opX, opx);
+        ndxa = dX * dXa + dx * dxa_;
+        ndxb = dX * dXb + dx * dxb_;
+        ndya = 2. * (rdxa * y + rx * dya + rdya * x + ry * dxa + dxa * y + x * dya);
+        ndyb = 2. * (rdxb * y + rx * dyb + rdyb * x + ry * dxb + dxb * y + x * dyb);
+        break;
+    }
+    default: {
+        T opX = rx * rx - ry * ry;
+        T dXa = 2. * (rx * rdxa - ry * rdya);
+        T dXb = 2. * (rx * rdxb - ry * rdyb);
+        T opx = x * (x + 2. * rx) - y * (y + 2. * ry);
+        T dxa_ = dxa * (x + 2. * rx) + x * (dxa + 2. * rdxa) - dya * (y + 2. * ry) - y * (dya + 2. * rdya);
+        T dxb_ = dxb * (x + 2. * rx) + x * (dxb + 2. * rdxb) - dyb * (y + 2. * ry) - y * (dyb + 2. * rdyb);
+        double dX = ddiffabsdX(opX, opx), dx = ddiffabsdx(opX, opx);
+        ndxa = dX * dXa + dx * dxa_;
+        ndxb = dX * dXb + dx * dxb_;
+        T opX2 = rx * ry;
+        T dXa2 = rdxa * ry + rx * rdya;
+        T dXb2 = rdxb * ry + rx * rdyb;
+        T opx2 = x * y + x * ry + y * rx;
+        T dxa2 = dxa * y + x * dya + dxa * ry + x * rdya + dya * rx + y * rdxa;
+        T dxb2 = dxb * y + x * dyb + dxb * ry + x * rdyb + dyb * rx + y * rdxb;
+        double dX2 = ddiffabsdX(opX2, opx2), dx2 = ddiffabsdx(opX2, opx2);
+        ndya = 2. * (dX2 * dXa2 + dx2 * dxa2);
+        ndyb = 2. * (dX2 * dXb2 + dx2 * dxb2);
+        break;
+    }
+    }
+    dxa = ndxa; dxb = ndxb; dya = ndya; dyb = ndyb;
+}
+
+/* Fused Xrange forms of apply_BLA_BS / apply_BLA_deriv_BS
+ * (perturbation.py:1793-1811), same idea as xr_lin: every product and every
+ * add of the reference's left-to-right chain is performed once, on mantissas
+ * aligned by exponent-field arithmetic; zero terms pass through an addition as
+ * in _coexp_ufunc (numba_xr.py:716-733). */
+#define XR_ZERO_E (-(1 << 28))
+FSB_HD XF xf_prod(double M, XF v)
+{
+    const double p = M * v.m;
+    const int fld = expfield(p);
+    return mkXF(xshift(p, 1023 - fld), (fld == 0) ? XR_ZERO_E : v.e + (fld - 1023));
+}
+FSB_HD XF xf_sum(XF s, XF p)
+{
+    const int se = (s.m == 0.) ? XR_ZERO_E : s.e;
+    const int e = imax(se, p.e);
+    return mkXF(xshift(s.m, se - e) + xshift(p.m, p.e - e), e);
+}
+FSB_HD XF xf_dot2(double m0, XF u, double m1, XF v)
+{
+    return xf_sum(xf_prod(m0, u), xf_prod(m1, v));
+}
+FSB_HD XF xf_dot4(double m0, XF u, double m1, XF v, double m2, XF a,
+                                      double m3, XF b)
+{
+    return xf_sum(xf_sum(xf_dot2(m0, u, m1, v), xf_prod(m2, a)), xf_prod(m3, b));
+}
+FSB_HD XF xf_clean(XF x)      /* zero results carry exponent 0 */
+{
+    return mkXF(x.m, (x.m == 0.) ? 0 : x.e);
+}
+/* to_standard of a value whose mantissa is below 4 in magnitude */
+FSB_HD double to_std_small(XF x)
+{
+    if (x.e < -1200) return mk64(hi32(x.m) & (int)0x80000000, 0);
+    return to_std(x);
+}
+
+/* ---- fused exact form of a burning-ship iteration for a tiny (x, y) ---------
+ * Flavour 1 ("Burning ship", burning_ship.py:539-553, 629-667) when the
+ * perturbation is far below the reference point: |x| < 2^-60 |X| and
+ * |y| < 2^-60 |Y|, X and Y normal doubles.  Then X + x, 2 X + x ... round to X,
+ * 2 X ..., |X Y + (x y + x Y + y X)| keeps the sign of X Y (diffabs and its two
+ * derivatives are linear: dX = 0, dx = sgn(X Y)), and x y is absorbed by x Y in
+ * the first addition of the chain.  What is left is evaluated with the SAME
+ * products and the SAME left-to-right aligned additions as the chain of
+ * numba_xr operators the reference runs (about eighty of them per iteration),
+ * skipping only the normalisations in between -- an Xrange value does not
+ * depend on its mantissa / exponent split.  1e-500 frames spend most of their
+ * instructions in the handful of tiny iterations that follow each rebase. */
+FSB_HD XF xf_mul(XF u, XF v)              /* u * v as a normalised term */
+{
+    const double p = u.m * v.m;
+    const int fld = expfield(p);
+    return mkXF(xshift(p, 1023 - fld), (fld == 0) ? XR_ZERO_E : u.e + v.e + (fld - 1023));
+}
+/* aligned sum of two Xrange reals, zero operands passing through (numba_xr.py:716-733) */
+FSB_HD XF xf_add(XF u, XF v)
+{
+    const int ue = (u.m == 0.) ? XR_ZERO_E : u.e, ve = (v.m == 0.) ? XR_ZERO_E : v.e;
+    const int e = imax(ue, ve);
+    return mkXF(xshift(u.m, ue - e) + xshift(v.m, ve - e), e);
+}
+FSB_HD XF xf_neg(XF u) { return mkXF(-u.m, u.e); }
+FSB_HD XF xf_dbl(XF u) { return mkXF(u.m, u.e + 1); }      /* 2. * u */
+/* true exponent of an Xrange real (very negative for 0) */
+FSB_HD int xf_expo(XF u) { return (u.m == 0.) ? XR_ZERO_E : u.e + expfield(u.m) - 1023; }
+
+FSB_HD bool bs_tiny_f1_ok(double rx, double ry, XF x, XF y)
+{
+    const int fx = expfield(rx), fy = expfield(ry);
+    return fx >= 64 && fx < 1600 && fy >= 64 && fy < 1600
+           && xf_expo(x) + 60 <= fx - 1023 && xf_expo(y) + 60 <= fy - 1023;
+}
+/* (x, y) <- one iteration; (a, b) = the pixel's c, (rx, ry) the reference point */
+FSB_HD void bs_tiny_f1_zn(XF &x, XF &y, double rx, double ry, XF a, XF b)
+{
+    /* nx = x * (x + 2. * rx) - y * (y + 2. * ry) + a */
+    const XF nx = xf_add(xf_add(xf_prod(2. * rx, x), xf_neg(xf_prod(2. * ry, y))), a);
+    /* ny = 2. * diffabs(rx * ry, x * y + x * ry + y * rx) - b */
+    XF s = xf_add(xf_prod(ry, x), xf_prod(rx, y));
+    if ((rx < 0.) != (ry < 0.)) s = xf_neg(s);          /* sign of X Y */
+    const XF ny = xf_add(xf_dbl(s), xf_neg(b));
+    x = xf_clean(nx); y = xf_clean(ny);
+}
+/* the four derivatives; (ra, rb, rc, rd) = the reference's dX/da, dX/db, dY/da, dY/db */
+FSB_HD void bs_tiny_f1_hessian(XF x, XF y, XF &dxa, XF &dxb, XF &dya, XF &dyb, double rx,
+                               double ry, XF ra, XF rb, XF rc, XF rd)
+{
+    const bool neg = (rx < 0.) != (ry < 0.);           /* sign of X Y */
+    /* ndxa = 2. * ((rx + x) * dxa + rdxa * x) - 2. * ((ry + y) * dya + rdya * y) */
+    const XF ndxa = xf_add(xf_dbl(xf_add(xf_prod(rx, dxa), xf_mul(ra, x))),
+                           xf_neg(xf_dbl(xf_add(xf_prod(ry, dya), xf_mul(rc, y)))));
+    const XF ndxb = xf_add(xf_dbl(xf_add(xf_prod(rx, dxb), xf_mul(rb, x))),
+                           xf_neg(xf_dbl(xf_add(xf_prod(ry, dyb), xf_mul(rd, y)))));
+    /* dxa_ = dxa * y + x * dya + dxa * ry + x * rdya + dya * rx + y * rdxa ;
+     * ndya = 2. * (0. * dXa + (+-1.) * dxa_) */
+    XF da = xf_add(xf_mul(dxa, y), xf_mul(x, dya));
+    da = xf_add(da, xf_prod(ry, dxa));
+    da = xf_add(da, xf_mul(x, rc));
+    da = xf_add(da, xf_prod(rx, dya));
+    da = xf_add(da, xf_mul(y, ra));
+    XF db = xf_add(xf_mul(dxb, y), xf_mul(x, dyb));
+    db = xf_add(db, xf_prod(ry, dxb));
+    db = xf_add(db, xf_mul(x, rd));
+    db = xf_add(db, xf_prod(rx, dyb));
+    db = xf_add(db, xf_mul(y, rb));
+    if (neg) { da = xf_neg(da); db = xf_neg(db); }
+    dxa = xf_clean(ndxa); dxb = xf_clean(ndxb);
+    dya = xf_clean(xf_dbl(da)); dyb = xf_clean(xf_dbl(db));
 }
 
 /* ======================================================================== */
@@ -898,8 +1183,13 @@ FSB_HD void lane_step(const FrameDev &f, LaneM2 &s, const C *c_pix, double *Z, i
                     const C nz = A * zn;
                     C nd = mkC(s.dr, s.di);
                     if (DZNDC) nd = A * nd;
+#ifdef FSB_SC_GUARDS
                     if (in_fast_range(nz) && (!DZNDC || in_fast_range(nd))
                         && expfield(B.re) != 0x7ff && expfield(B.im) != 0x7ff) {
+#else
+                    if (in_fast_range(nz) & (!DZNDC || in_fast_range(nd))
+                        & (imax(expfield(B.re), expfield(B.im)) != 0x7ff)) {
+#endif
                         s.zr = nz.re; s.zi = nz.im; zc = nz;
                         if (DZNDC) { s.dr = nd.re; s.di = nd.im; }
                         continue;
