@@ -1077,21 +1077,60 @@ FSB_COLD void lane_rebase(const FrameDev &f, LaneM2 &s, LaneCold &k, C zn, C ZZ,
 #undef L_LOAD_Z
 }
 
+struct RebIO { double zr, zi, dr, di, Zr, Zi; int w, ze, de, nbase; unsigned flags, p_reb; };
+#if defined(__CUDA_ARCH__) && defined(FSB_OUTLINE_REBASE)
+#define FSB_VALUE_CALL2 static __device__ __noinline__
+#else
+#define FSB_VALUE_CALL2 FSB_HD
+#endif
+template <bool XR, bool DZNDC>
+FSB_VALUE_CALL2 RebIO lane_rebase_v(const FrameDev &f, RebIO io, C zn, C ZZ, bool rebase)
+{
+    LaneM2 s;
+    LaneCold k;
+    s.zr = io.zr; s.zi = io.zi; s.dr = io.dr; s.di = io.di; s.Zr = io.Zr; s.Zi = io.Zi;
+    s.cr = s.ci = 0.; s.w = io.w; s.wlim = 0; s.winc = 1; s.flags = io.flags;
+    k.ze = io.ze; k.de = io.de; k.nbase = io.nbase; k.p_reb = io.p_reb;
+    lane_rebase<XR, DZNDC>(f, s, k, zn, ZZ, rebase);
+    io.zr = s.zr; io.zi = s.zi; io.dr = s.dr; io.di = s.di; io.Zr = s.Zr; io.Zi = s.Zi;
+    io.w = s.w; io.ze = k.ze; io.de = k.de; io.nbase = k.nbase; io.flags = s.flags; io.p_reb = k.p_reb;
+    return io;
+}
+
 /* one iteration by the operator chain of numba_xr.py (perturbation.py:1158-1209
- * in Xrange arithmetic): whatever the fused forms of lane_step do not cover */
+ * in Xrange arithmetic): whatever the fused forms of lane_step do not cover.
+ * Rare, and large once inlined.  FSB_OUTLINE_GENERIC / FSB_OUTLINE_REBASE make
+ * this and the Xrange rebase real calls on the device, with everything passed
+ * and returned BY VALUE so that the lane never has its address taken (no local
+ * memory, 0 bytes of stack).  Measured on config 3: 24.9 ms inlined, 25.1 ms with
+ * the generic iteration outlined, 26.5 ms with both -- the instruction cache is
+ * not what bounds this kernel (stall_no_instruction 0.65) -- so both stay inlined. */
+struct XC2 { XC z, d; };
+#if defined(__CUDA_ARCH__) && defined(FSB_OUTLINE_GENERIC)
+#define FSB_VALUE_CALL static __device__ __noinline__
+#else
+#define FSB_VALUE_CALL FSB_HD
+#endif
 template <bool DZNDC>
-FSB_COLD void lane_slow_generic(const FrameDev &f, LaneM2 &s, LaneCold &k, int kx, bool dyn)
+FSB_VALUE_CALL XC2 slow_generic_iter(XC zx, XC dx, XC ref_x, XC ref_d, XC c_xr)
+{
+    XC2 r;
+    r.d = dx;
+    if (DZNDC) r.d = p_iter_deriv(zx, dx, ref_x, ref_d);
+    r.z = p_iter_zn(zx, ref_x, c_xr);
+    return r;
+}
+template <bool DZNDC>
+FSB_HD void lane_slow_generic(const FrameDev &f, LaneM2 &s, LaneCold &k, int kx, bool dyn)
 {
     const C ref_zn = mkC(s.Zr, s.Zi);
     const XC ref_x = (kx >= 0) ? mkXC(ldC(f.ref_xr, kx), ldg_(f.ref_xr_e + kx)) : to_xr(ref_zn);
-    XC zx = mkXC(mkC(s.zr, s.zi), k.ze);
-    if (DZNDC) {
-        const XC ref_d = dyn ? mkXC(mkC(0., 0.), 0) : mkXC(ldC(f.dZndc, s.w), ldg_(f.dZndc_e + s.w));
-        const XC dx = p_iter_deriv(zx, mkXC(mkC(s.dr, s.di), k.de), ref_x, ref_d);
-        s.dr = dx.m.re; s.di = dx.m.im; k.de = dx.e;
-    }
-    zx = p_iter_zn(zx, ref_x, k.c_xr);
-    s.zr = zx.m.re; s.zi = zx.m.im; k.ze = zx.e;
+    XC ref_d = mkXC(mkC(0., 0.), 0);
+    if (DZNDC && !dyn) ref_d = mkXC(ldC(f.dZndc, s.w), ldg_(f.dZndc_e + s.w));
+    const XC2 r = slow_generic_iter<DZNDC>(mkXC(mkC(s.zr, s.zi), k.ze), mkXC(mkC(s.dr, s.di), k.de),
+                                           ref_x, ref_d, k.c_xr);
+    if (DZNDC) { s.dr = r.d.m.re; s.di = r.d.m.im; k.de = r.d.e; }
+    s.zr = r.z.m.re; s.zi = r.z.m.im; k.ze = r.z.e;
 }
 
 /* The event section of one lane: runs until the lane is armed for the hot
@@ -1145,6 +1184,18 @@ FSB_HD void lane_step(const FrameDev &f, LaneM2 &s, const C *c_pix, double *Z, i
                 go = dyn;
             }
             if (go) {
+#ifdef FSB_OUTLINE_REBASE
+                if (XR) {       /* Xrange frames: a real call, state by value (see slow_generic_iter) */
+                    RebIO io;
+                    io.zr = s.zr; io.zi = s.zi; io.dr = s.dr; io.di = s.di; io.Zr = s.Zr; io.Zi = s.Zi;
+                    io.w = s.w; io.ze = k.ze; io.de = k.de; io.nbase = k.nbase; io.flags = s.flags;
+                    io.p_reb = k.p_reb;
+                    io = lane_rebase_v<XR, DZNDC>(f, io, zn, ZZ, rebase);
+                    s.zr = io.zr; s.zi = io.zi; s.dr = io.dr; s.di = io.di; s.Zr = io.Zr; s.Zi = io.Zi;
+                    s.w = io.w; k.ze = io.ze; k.de = io.de; k.nbase = io.nbase; s.flags = io.flags;
+                    k.p_reb = io.p_reb;
+                } else
+#endif
                 FSB_COLD_CALL(s, (lane_rebase<XR, DZNDC>(f, t_, k, zn, ZZ, rebase)));
                 zc = (XR && (s.flags & LF_SLOW)) ? to_std_small(mkXC(mkC(s.zr, s.zi), k.ze)) : mkC(s.zr, s.zi);
             }

@@ -161,3 +161,57 @@ def test_postproc_errors():
         fpp.frame_fields(f, "c", fields=("DEM",))
     out, _ = fpp.frame_fields(f, "c", fields=("cont_iter",))
     assert set(out) == {"cont_iter", "stop_reason"}
+
+
+# ---------------------------------------------------------------------------
+# k_postproc pinned to the LIVE reference: fixtures generated by
+# tools/gen_golden_pp.py drive the reference's own Continuous_iter_pp, DEM_pp and
+# DEM_normal_pp (through Fractal.postproc, postproc_dtype float64) on the raw
+# arrays of its own calculation; the same raw arrays go through k_postproc.
+import json
+import os
+
+import parity_common as pc
+from cases import CASES
+
+PP_GOLDEN = ["std_M2_cfg1", "p_M2_E20", "p_M2_deep250", "p_BS_f1_E30_skew", "std_BS_f1"]
+
+
+@pytest.mark.parametrize("name", PP_GOLDEN)
+def test_postproc_kernel_matches_reference_fixture(name):
+    g = np.load(os.path.join(pc.GOLDEN, f"pp_{name}.npz"))
+    meta = json.loads(str(g["meta"]))
+    f, case = pc.make_fractal(name)
+    f.calc_std_div(calc_name="c", subset=None, **case["calc"])
+    codes = list(f._calc_data["c"]["state"].codes[0])
+    saved = meta["codes"]
+    # the fixture holds the reference's SAVED rows; k_postproc indexes the
+    # calculation's rows: put them back in place
+    Zs = np.asarray(g["Z"])
+    Z = np.zeros((len(codes), Zs.shape[1]), Zs.dtype)
+    for i, c in enumerate(saved):
+        Z[codes.index(c)] = Zs[i]
+    si = np.asarray(g["stop_iter"])
+    esc = np.asarray(g["stop_reason"])[0] == 1
+    assert esc.sum() > 100
+    out64 = fpp.fields_from_raw(f, "c", Z, si, fields=("cont_iter", "DEM", "normal"),
+                                dtype=np.float64)
+    out32 = fpp.fields_from_raw(f, "c", Z, si, fields=("cont_iter", "DEM", "normal"),
+                                dtype=np.float32)
+    rates = {}
+    for key in ("cont_iter", "DEM", "normal_x", "normal_y"):
+        ref = np.asarray(g[key], np.float64)
+        ok = esc & np.isfinite(ref)
+        assert ok.sum() > 100, key
+        # float64 outputs: the same formula evaluated by another libm (log, hypot)
+        np.testing.assert_allclose(out64[key][ok], ref[ok], rtol=1e-11, atol=1e-11)
+        # float32 outputs (the reference's default postproc_dtype): equal to the
+        # reference's float64 value rounded to float32, or its float32 neighbour
+        r32 = ref[ok].astype(np.float32)
+        same = out32[key][ok] == r32
+        nb = np.abs(out32[key][ok].astype(np.float64) - r32) <= np.spacing(np.abs(r32)).astype(np.float64)
+        rates[key] = float(same.mean())
+        assert same.mean() >= 0.999, (key, same.mean())
+        assert nb.all(), key
+    print("\nPP_PARITY", name, json.dumps(rates))
+    f._release_indep_args(f._calc_data["c"]["cycle_indep_args"])
