@@ -1508,7 +1508,7 @@ int fsb_frame_create(const fsb_frame_desc *desc, fsb_frame **out)
         v.r2hi_up = t + v.bla_len;
     }
     if (f->v2) {
-        const long long n_rec = L + 16, n_h3 = L / 8 + 4;
+        const long long n_rec = L + 16, n_h3 = FSB_H3_DIRECT ? n_rec : L / 8 + 4;
         void *p = nullptr, *ph = nullptr;
         if (pool_alloc(&p, (size_t)(n_rec * 32)) != cudaSuccess
             || (f->owned.push_back(p), pool_alloc(&ph, (size_t)(n_h3 * 4))) != cudaSuccess) {
@@ -1521,11 +1521,10 @@ int fsb_frame_create(const fsb_frame_desc *desc, fsb_frame **out)
                                                           (double4 *)p);
         /* a lookup needs its leaf: indices 8 j with j < bla_len / 2 */
         const bool bla = f->bla_on && v.stages_bla >= 4;
-        long long n_leaf = bla ? v.bla_len / 2 : 0;
-        if (n_leaf > n_h3) n_leaf = n_h3;
-        if (cudaMemset(ph, 0, (size_t)(n_h3 * 4)) != cudaSuccess) { fsb_frame_destroy(f); return fail(-1, "memset failed"); }
+        const long long n_leaf = bla ? v.bla_len / 2 : 0;
+        if (cudaMemsetAsync(ph, 0, (size_t)(n_h3 * 4)) != cudaSuccess) { fsb_frame_destroy(f); return fail(-1, "memset failed"); }
         if (n_leaf > 0)
-            k_build_h3<<<(int)((n_leaf + 255) / 256), 256>>>(n_leaf, v.r_bla, v.first_invalid_i, (unsigned *)ph);
+            k_build_h3<<<(int)((n_leaf + 255) / 256), 256>>>(n_leaf, n_h3, v.r_bla, v.first_invalid_i, (unsigned *)ph);
         if (cudaGetLastError() != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
             fsb_frame_destroy(f);
             return fail(-1, "orbit table kernel failed");

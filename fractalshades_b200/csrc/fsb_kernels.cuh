@@ -907,26 +907,56 @@ k_perturb_m2_v2(const __grid_constant__ FrameDev f, long long npts_ll,
          * is Zn[w] of the next iteration without a move.  Parked lanes run along on
          * zeros (winc = 0); a second copy of the loop masks their pre-tests. */
         const bool alive = (s.flags & (LF_DEAD | LF_NEED)) == 0;
-        bool ev, bad;
         double Zr = s.Zr, Zi = s.Zi;
 #define FSB_LD_REC(R, idx) do { const double4 *rec_ = T2 + (long long)(idx); \
             asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" \
                 : "=d"(R##0), "=d"(R##1), "=d"(R##2), "=d"(R##3) : "l"(rec_)); } while (0)
+#if FSB_HOT_RECOMPUTE
+#define FSB_HOT_LOOP(MASK) do { \
+            double ra0, ra1, ra2, ra3, rb0, rb1, rb2, rb3; \
+            for (;;) { \
+                bool ev, bad; \
+                FSB_LD_REC(ra, s.w); \
+                m2_hot_iter<XR, DZNDC, BLA>(s, Zr, Zi, ra2, ra3); \
+                m2_hot_flags<XR, DZNDC, BLA>(s, ra0, ra1, h3tab, esc_hi, ev, bad); \
+                bool any = ev | bad; \
+                if (MASK) any = any & alive; \
+                if (__any_sync(FULL, any)) { Zr = ra0; Zi = ra1; break; } \
+                FSB_LD_REC(rb, s.w); \
+                m2_hot_iter<XR, DZNDC, BLA>(s, ra0, ra1, rb2, rb3); \
+                m2_hot_flags<XR, DZNDC, BLA>(s, rb0, rb1, h3tab, esc_hi, ev, bad); \
+                any = ev | bad; \
+                if (MASK) any = any & alive; \
+                Zr = rb0; Zi = rb1; \
+                if (__any_sync(FULL, any)) break; \
+            } } while (0)
+        if (__all_sync(FULL, alive)) FSB_HOT_LOOP(false);
+        else FSB_HOT_LOOP(true);
+        /* which lanes, and why: the pre-tests once more on the state the loop left
+         * (the loop itself only carries their disjunction to the vote) */
+        bool ev, bad;
+        m2_hot_flags<XR, DZNDC, BLA>(s, Zr, Zi, h3tab, esc_hi, ev, bad);
+        if (!alive) { ev = false; bad = false; }
+#else
+        bool ev, bad;
 #define FSB_HOT_LOOP(MASK) do { \
             double ra0, ra1, ra2, ra3, rb0, rb1, rb2, rb3; \
             for (;;) { \
                 FSB_LD_REC(ra, s.w); \
-                m2_hot_iter<XR, DZNDC, BLA>(s, Zr, Zi, ra0, ra1, ra2, ra3, h3tab, esc_hi, ev, bad); \
+                m2_hot_iter<XR, DZNDC, BLA>(s, Zr, Zi, ra2, ra3); \
+                m2_hot_flags<XR, DZNDC, BLA>(s, ra0, ra1, h3tab, esc_hi, ev, bad); \
                 if (MASK) { ev = ev & alive; bad = bad & alive; } \
                 if (__any_sync(FULL, ev | bad)) { Zr = ra0; Zi = ra1; break; } \
                 FSB_LD_REC(rb, s.w); \
-                m2_hot_iter<XR, DZNDC, BLA>(s, ra0, ra1, rb0, rb1, rb2, rb3, h3tab, esc_hi, ev, bad); \
+                m2_hot_iter<XR, DZNDC, BLA>(s, ra0, ra1, rb2, rb3); \
+                m2_hot_flags<XR, DZNDC, BLA>(s, rb0, rb1, h3tab, esc_hi, ev, bad); \
                 if (MASK) { ev = ev & alive; bad = bad & alive; } \
                 Zr = rb0; Zi = rb1; \
                 if (__any_sync(FULL, ev | bad)) break; \
             } } while (0)
         if (__all_sync(FULL, alive)) FSB_HOT_LOOP(false);
         else FSB_HOT_LOOP(true);
+#endif
 #undef FSB_HOT_LOOP
 #undef FSB_LD_REC
         if (XR && bad) s.flags |= LF_EV | LF_BAD;
@@ -1881,17 +1911,15 @@ __global__ void k_build_t2(long long n_rec, const C *__restrict__ Zn, long long 
     const C dd = (d != nullptr && i < n_d) ? ldC(d, i) : mkC(0., 0.);
     T2[i] = make_double4(z1.re, z1.im, mul_rn(scale, dd.re), mul_rn(scale, dd.im));
 }
-/* h3[j] = high word of r_bla[2 j] (stage-3 radius of index 8 j) when the loop
- * looks the BLA tree up there (more than 8 valid indices ahead, ref_bla_get),
- * else 0: the pre-test `|re|, |im| < r3` of the hot loop on high words */
-__global__ void k_build_h3(long long n, const double *__restrict__ r_bla, int first_invalid,
-                           unsigned *__restrict__ h3)
+/* Pre-test words of the hot loop (table zeroed first): for every leaf j (index 8 j)
+ * where the loop looks the BLA tree up (more than 8 valid indices ahead,
+ * ref_bla_get), the high word of its stage-3 radius r_bla[2 j], in slot h3_slot(8 j). */
+__global__ void k_build_h3(long long n_leaf, long long n_slots, const double *__restrict__ r_bla,
+                           int first_invalid, unsigned *__restrict__ h3)
 {
     const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    unsigned v = 0u;
-    if (r_bla != nullptr && (long long)first_invalid - 8 * j > 8) v = (unsigned)hi32(__ldg(r_bla + 2 * j));
-    h3[j] = v;
+    if (j >= n_leaf || (long long)h3_slot((int)(8 * j)) >= n_slots) return;
+    if ((long long)first_invalid - 8 * j > 8) h3[h3_slot((int)(8 * j))] = (unsigned)hi32(__ldg(r_bla + 2 * j));
 }
 
 /* ======================================================================== */

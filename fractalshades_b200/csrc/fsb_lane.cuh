@@ -72,8 +72,8 @@ struct FrameDev {
      * (dZndc: the fp64 mirror in Xrange frames) -- all an iteration reads, in ONE 32-byte
      * load: the L1 -> register write-back path (32 lanes x bytes per load, broadcast or
      * not) is what bounds the hot loop next to the FP64 pipe, measured at 90 % with
-     * 64-byte records; h3[j] = high word of the stage-3 BLA radius of index 8 j where the
-     * loop looks the tree up, else 0; and the exponent bound of the escape pre-test (both
+     * 64-byte records; h3[h3_slot(w)] = high word of the stage-3 BLA radius of index w where
+     * the loop looks the tree up (w a multiple of 8), else 0; and the exponent bound of the escape pre-test (both
      * parts of Z + z below 2^k with 2^(2k+1) <= Mdiv_sq) */
     const double *T2;
     const unsigned *h3;
@@ -831,6 +831,28 @@ enum : unsigned {
                         * iteration per event step, up to the failing one          */
 };
 
+/* Build knobs of the hot loop.  Measured on B200 (round 2, config 2 / config 3, ms per 4K
+ * frame; default = 11.20 / 24.94):
+ *   FSB_H3_DIRECT=1      pre-test word table indexed by w (zeros off the multiples of 8):
+ *                        one unpredicated 4-byte load instead of predicate + shift +
+ *                        predicated load.  Four instructions fewer per iteration on paper;
+ *                        ptxas then breaks the two-register-set allocation of the loop
+ *                        (10-16 moves per trip, tools/sass_hotloop.py): 11.59 / 25.19.
+ *   FSB_HOT_RECOMPUTE=1  the loop carries only `ev | bad` to the vote and the flags are
+ *                        recomputed after it: 11.52 / 24.82 (two SELs saved, three moves added).
+ *   FSB_EVENT_PRETEST    the hot loop's necessary condition before every tree lookup of the
+ *                        event section (a chain of BLA steps ends in a failed lookup):
+ *                        11.28 / 24.79 -- inside the run-to-run noise.
+ * A `mov` through volatile asm does not pin esc_hi in a register either: ptxas
+ * rematerialises it from the constant bank all the same.  All off. */
+#ifndef FSB_H3_DIRECT
+#define FSB_H3_DIRECT 0
+#endif
+#ifndef FSB_HOT_RECOMPUTE
+#define FSB_HOT_RECOMPUTE 0
+#endif
+/* slot of index w in the pre-test word table */
+FSB_HD int h3_slot(int w) { return FSB_H3_DIRECT ? w : (w >> 3); }
 #ifdef FSB_STRICT
 #define FSB_TSCALE 1.
 #else
@@ -1207,7 +1229,14 @@ FSB_HD void lane_step(const FrameDev &f, LaneM2 &s, const C *c_pix, double *Z, i
                 const bool slow = XR && (s.flags & LF_SLOW);
                 const C zn = zc;
                 int ib = 0;
-                #ifdef FSB_BLA_LOOKUP2
+#ifdef FSB_EVENT_PRETEST
+                {   /* the hot loop's necessary condition first: most chains of steps end here */
+                    const unsigned h3 = ldg_(f.h3 + h3_slot(s.w));
+                    const unsigned c = (unsigned)hi32(zn.re) & 0x7fffffffu, d = (unsigned)hi32(zn.im) & 0x7fffffffu;
+                    if (!((c <= h3) & (d <= h3))) break;
+                }
+#endif
+#ifdef FSB_BLA_LOOKUP2
                 const int step = ref_bla_get2(f.r_bla, f.stages_bla, zn, s.w, f.first_invalid_i, ib);
 #else
                 const int step = ref_bla_get3(f, zn, s.w, ib);
@@ -1352,34 +1381,43 @@ FSB_HD void lane_step(const FrameDev &f, LaneM2 &s, const C *c_pix, double *Z, i
  * guard failed -- the state is then garbage and the lane goes back to its
  * checkpoint.  (Zr, Zi) = Zn[w], carried from the previous record; the orbit
  * record of index w is {Zn[w+1] = (t0, t1), FSB_TSCALE dZndc[w] = (t2, t3)}. */
+/* the pre-tests on the state AFTER an iteration: (Zr, Zi) = Zn[w] */
 template <bool XR, bool DZNDC, bool BLA>
-FSB_HD void m2_hot_iter(LaneM2 &s, double Zr, double Zi, double t0, double t1, double t2, double t3,
-                        const unsigned *__restrict__ h3tab, unsigned esc_hi, bool &ev, bool &bad)
+FSB_HD void m2_hot_flags(const LaneM2 &s, double Zr, double Zi, const unsigned *__restrict__ h3tab,
+                         unsigned esc_hi, bool &ev, bool &bad)
+{
+    const double ZZr = s.zr + Zr, ZZi = s.zi + Zi;
+    const unsigned a = (unsigned)hi32(ZZr) & 0x7fffffffu, b = (unsigned)hi32(ZZi) & 0x7fffffffu;
+    const unsigned c = (unsigned)hi32(s.zr) & 0x7fffffffu, d = (unsigned)hi32(s.zi) & 0x7fffffffu;
+    /* |Z + z| <= |z| and |z| < r3 per component can only hold if they hold for the
+     * sign-stripped high words; a | b bounds both exponent fields from above */
+    ev = (s.w >= s.wlim) | ((a | b) >= esc_hi) | ((a <= c) & (b <= d));
+    if (BLA) {
+        /* the tree is looked up at multiples of 8: h3tab[w] = high word of the stage-3
+         * radius of index w there, 0 elsewhere and where no lookup takes place */
+#if FSB_H3_DIRECT
+        const unsigned h3 = ldg_(h3tab + s.w);
+#else
+        unsigned h3 = 0u;
+        if ((s.w & 7) == 0) h3 = ldg_(h3tab + (s.w >> 3));
+#endif
+        ev = ev | ((c <= h3) & (d <= h3));
+    }
+    bad = false;
+    if (XR) {
+        bad = !(in_fast_range(s.zr) & in_fast_range(s.zi));
+        if (DZNDC) bad = bad | !(in_fast_range(s.dr) & in_fast_range(s.di));
+    }
+}
+template <bool XR, bool DZNDC, bool BLA>
+FSB_HD void m2_hot_iter(LaneM2 &s, double Zr, double Zi, double t2, double t3)
 {
     double nzr, nzi, ndr = 0., ndi = 0.;
     m2_iter_fp64<DZNDC>(s.zr, s.zi, s.dr, s.di, Zr, Zi, t2, t3, s.cr, s.ci, nzr, nzi, ndr, ndi);
     s.zr = nzr; s.zi = nzi;
     if (DZNDC) { s.dr = ndr; s.di = ndi; }
     s.w += s.winc;
-    const double ZZr = nzr + t0, ZZi = nzi + t1;
-    const unsigned a = (unsigned)hi32(ZZr) & 0x7fffffffu, b = (unsigned)hi32(ZZi) & 0x7fffffffu;
-    const unsigned c = (unsigned)hi32(nzr) & 0x7fffffffu, d = (unsigned)hi32(nzi) & 0x7fffffffu;
-    /* |Z + z| <= |z| and |z| < r3 per component can only hold if they hold for the
-     * sign-stripped high words; a | b bounds both exponent fields from above */
-    ev = (s.w >= s.wlim) | ((a | b) >= esc_hi) | ((a <= c) & (b <= d));
-    if (BLA) {
-        /* the tree is looked up at multiples of 8: stage-3 radius of the new index */
-        unsigned h3 = 0u;
-        if ((s.w & 7) == 0) h3 = ldg_(h3tab + (s.w >> 3));
-        ev = ev | ((c <= h3) & (d <= h3));
-    }
-    bad = false;
-    if (XR) {
-        bad = !(in_fast_range(nzr) & in_fast_range(nzi));
-        if (DZNDC) bad = bad | !(in_fast_range(ndr) & in_fast_range(ndi));
-    }
 }
-
 /* exponent-field bound of the escape pre-test: both parts of Z + z below 2^k
  * imply |Z + z|^2 < 2^(2k+1) <= Mdiv_sq */
 inline unsigned esc_hi_of(double Mdiv_sq)

@@ -75,9 +75,9 @@ static void run(const FrameDev &f, int64_t npts, const C *c_pix, double *Z, int3
             bool ev, bad;
             for (;;) {
                 const double *rec = T2 + 4 * (long long)s.w;
-                m2_hot_iter<XR, DZNDC, BLA>(s, s.Zr, s.Zi, rec[0], rec[1], rec[2], rec[3], f.h3,
-                                            f.esc_hi, ev, bad);
+                m2_hot_iter<XR, DZNDC, BLA>(s, s.Zr, s.Zi, rec[2], rec[3]);
                 s.Zr = rec[0]; s.Zi = rec[1];
+                m2_hot_flags<XR, DZNDC, BLA>(s, s.Zr, s.Zi, f.h3, f.esc_hi, ev, bad);
                 cnt[5]++;
                 if (ev | bad) break;
             }
@@ -150,7 +150,7 @@ extern "C" int fsb_emul_perturb_m2(const emul_frame *e, int64_t npts, const doub
         f.r2hi_up = r2hi.data() + e->bla_len;
     }
     /* interleaved orbit table and pre-test words, as k_build_t2 / k_build_h3 */
-    const int64_t n_rec = L + 16, n_h3 = L / 8 + 4;
+    const int64_t n_rec = L + 16, n_h3 = FSB_H3_DIRECT ? n_rec : L / 8 + 4;
     std::vector<double> T2((size_t)n_rec * 4, 0.);
     std::vector<unsigned> h3((size_t)n_h3, 0u);
     const C *dsrc = dc ? (xr ? f.dZndc_std : f.dZndc) : nullptr;
@@ -160,8 +160,8 @@ extern "C" int fsb_emul_perturb_m2(const emul_frame *e, int64_t npts, const doub
         if (dsrc && i < L + 1) { r[2] = mul_rn(FSB_TSCALE, dsrc[i].re); r[3] = mul_rn(FSB_TSCALE, dsrc[i].im); }
     }
     if (bla)
-        for (int64_t j = 0; j < n_h3 && j < e->bla_len / 2; j++)
-            if ((int64_t)f.first_invalid_i - 8 * j > 8) h3[(size_t)j] = (unsigned)hi32(e->r_bla[2 * j]);
+        for (int64_t j = 0; h3_slot((int)(8 * j)) < n_h3 && j < e->bla_len / 2; j++)
+            if ((int64_t)f.first_invalid_i - 8 * j > 8) h3[(size_t)h3_slot((int)(8 * j))] = (unsigned)hi32(e->r_bla[2 * j]);
     f.T2 = T2.data();
     f.h3 = h3.data();
 
