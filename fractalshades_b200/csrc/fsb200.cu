@@ -1508,7 +1508,7 @@ int fsb_frame_create(const fsb_frame_desc *desc, fsb_frame **out)
         v.r2hi_up = t + v.bla_len;
     }
     if (f->v2) {
-        const long long n_rec = L + 16, n_h3 = FSB_H3_DIRECT ? n_rec : L / 8 + 4;
+        const long long n_rec = L + 16 + FSB_STAGE_WIN /* a staged window may start at the last index */, n_h3 = FSB_H3_DIRECT ? n_rec : L / 8 + 4;
         void *p = nullptr, *ph = nullptr;
         if (pool_alloc(&p, (size_t)(n_rec * 32)) != cudaSuccess
             || (f->owned.push_back(p), pool_alloc(&ph, (size_t)(n_h3 * 4))) != cudaSuccess) {
@@ -1691,6 +1691,51 @@ static int postproc_enqueue(const PostprocDev &p, cudaStream_t st, long long fir
     return 0;
 }
 
+static int postproc_ext_fill(const fsb_postproc_desc *d, const fsb_postproc_ext *x, int n_rows,
+                             bool want_fl, bool want_shade, PostprocExtDev &e)
+{
+    if (!x) return fail(-3, "null field-lines / shading description");
+    memset(&e, 0, sizeof e);
+    if (want_fl) {
+        if (x->fl_n_iter < 1 || x->fl_n_iter > FSB_PP_MAX_FL)
+            return fail(-3, "field lines: n_iter = %d outside 1..%d", x->fl_n_iter, FSB_PP_MAX_FL);
+        const int need = d->holomorphic ? 1 : 2;
+        if (x->fl_row_orbit >= 0 && x->fl_row_orbit + need > n_rows)
+            return fail(-3, "field lines: orbit row %d outside the %d rows of Z", x->fl_row_orbit, n_rows);
+        const bool ok_model = d->holomorphic ? (x->fl_model >= 2 && x->fl_model <= 32)
+                                             : (x->fl_model <= -1 && x->fl_model >= -5);
+        if (!ok_model) return fail(-3, "field lines: model code %d does not fit the Z rows", x->fl_model);
+        e.fl_n = x->fl_n_iter; e.fl_row_orbit = x->fl_row_orbit; e.fl_backshift = x->fl_backshift;
+        e.fl_model = x->fl_model;
+        for (int i = 0; i < x->fl_n_iter; i++) { e.fl_k[i] = x->fl_k[i]; e.fl_phi[i] = x->fl_phi[i]; }
+        e.cx = x->c_center[0]; e.cy = x->c_center[1]; e.cs = x->c_scale;
+        for (int i = 0; i < 4; i++) e.cm[i] = x->c_lin_mat[i];
+    }
+    if (want_shade) {
+        if (x->n_lights < 1 || x->n_lights > FSB_PP_MAX_LIGHTS)
+            return fail(-3, "shading: %d light sources outside 1..%d", x->n_lights, FSB_PP_MAX_LIGHTS);
+        if (d->row_dzndc < 0) return fail(-3, "shading needs the derivative rows (normal map)");
+        e.n_lights = x->n_lights; e.ncoeff = x->normal_coeff;
+        for (int l = 0; l < x->n_lights; l++)
+            for (int i = 0; i < 8; i++) e.light[l][i] = x->light[l][i];
+    }
+    return 0;
+}
+
+static int postproc_ext_enqueue(const PostprocDev &p, const PostprocExtDev &e, cudaStream_t st,
+                                long long first, long long n, const double *d_Z, const int *d_si,
+                                const C *d_c, void *d_fl, void *d_shade, long long shade_stride)
+{
+    if (n <= 0 || (!d_fl && !d_shade)) return 0;
+    long long blocks = (n + 255) / 256;
+    const long long cap = (long long)g_sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    k_postproc_ext<<<(int)blocks, 256, 0, st>>>(p, e, first, n, d_Z, d_si, d_c, d_fl, d_shade,
+                                                shade_stride);
+    CK(cudaGetLastError());
+    return 0;
+}
+
 /* pp == nullptr: the raw planes come back (Z, U, stop_iter, stop_reason).
  * pp != nullptr: fused post-processing -- the raw planes stay in HBM and only
  * the requested fields (pp_out: nu, dem, nx, ny) plus the non-null ones of
@@ -1700,7 +1745,8 @@ static int frame_run_impl(Ctx *c, fsb_frame *f, int32_t n_tiles, const int32_t *
                           int32_t *U, int8_t *stop_reason, int32_t *stop_iter,
                           const volatile uint8_t *interrupted, fsb_stats *stats,
                           const fsb_postproc_desc *pp = nullptr, void *const *pp_out = nullptr,
-                          const double *axes = nullptr)
+                          const double *axes = nullptr, const fsb_postproc_ext *ext = nullptr,
+                          void *fl_out = nullptr, void *shade_out = nullptr)
 {
     if (stats) memset(stats, 0, sizeof *stats);
     if (interrupted && *interrupted) return FSB_USER_INTERRUPTED;
@@ -1712,19 +1758,29 @@ static int frame_run_impl(Ctx *c, fsb_frame *f, int32_t n_tiles, const int32_t *
     const long long zelem = (f->d.model == FSB_MODEL_M2) ? 16 : 8;
     PostprocDev pd;
     long long oelem = 4;
+    PostprocExtDev pe;
+    const bool use_ext = pp && ext && (fl_out || shade_out);
+    int n_shade = 0;
     if (pp) {
         if (postproc_fill(pp, npts, nz, pd)) return -3;
         oelem = pp->out_f64 ? 8 : 4;
+        if (use_ext) {
+            if (postproc_ext_fill(pp, ext, nz, fl_out != nullptr, shade_out != nullptr, pe)) return -3;
+            n_shade = shade_out ? 2 * pe.n_lights : 0;
+        }
     }
+    const long long pp_plane = align256(npts * oelem);
     long long o_c = 0, o_Z = align256(o_c + npts * 16), o_U = align256(o_Z + nz * npts * zelem),
               o_si = align256(o_U + npts * 4), o_sr = align256(o_si + npts * 4),
               o_pp = align256(o_sr + npts),
-              total = align256(o_pp + (pp ? 4 * align256(npts * oelem) : 0));
+              o_fl = o_pp + (pp ? 4 * pp_plane : 0), o_sh = o_fl + (use_ext ? pp_plane : 0),
+              total = align256(o_sh + n_shade * pp_plane);
     if (ctx_reserve(c, total)) return -1;
     char *base = (char *)c->d_buf;
     Plane planes[16];
     int np = 0;
     void *d_pp[4] = {nullptr, nullptr, nullptr, nullptr};
+    void *d_fl = nullptr, *d_sh = nullptr;
     if (!pp) {
         for (int r = 0; r < nz; r++)
             planes[np++] = Plane{(char *)Z + r * npts * zelem, o_Z + r * npts * zelem, zelem};
@@ -1742,6 +1798,16 @@ static int frame_run_impl(Ctx *c, fsb_frame *f, int32_t n_tiles, const int32_t *
             return fail(-3, "the normal needs both of its output arrays");
         if ((d_pp[1] || d_pp[2]) && pp->row_dzndc < 0)
             return fail(-3, "distance estimate / normal need the derivative rows");
+        if (use_ext && fl_out) {
+            d_fl = base + o_fl;
+            planes[np++] = Plane{(char *)fl_out, o_fl, oelem};
+        }
+        if (use_ext && shade_out) {
+            d_sh = base + o_sh;
+            /* rows of the caller's (2 n_lights, npts) array <-> device planes of pitch pp_plane */
+            for (int r = 0; r < n_shade; r++)
+                planes[np++] = Plane{(char *)shade_out + r * npts * oelem, o_sh + r * pp_plane, oelem};
+        }
         if (stop_iter) planes[np++] = Plane{(char *)stop_iter, o_si, 4};
         if (stop_reason) planes[np++] = Plane{(char *)stop_reason, o_sr, 1};
     }
@@ -1751,15 +1817,18 @@ static int frame_run_impl(Ctx *c, fsb_frame *f, int32_t n_tiles, const int32_t *
         if (frame_enqueue(c, f, st, slot, u, unit_lo, unit_hi, (const C *)(base + o_c),
                           (double *)(base + o_Z), (int *)(base + o_U),
                           (signed char *)(base + o_sr), (int *)(base + o_si))) return -1;
-        if (pp) return postproc_enqueue(pd, st, a, n, (const double *)(base + o_Z),
-                                        (const int *)(base + o_si), d_pp[0], d_pp[1], d_pp[2],
-                                        d_pp[3]);
+        if (pp && postproc_enqueue(pd, st, a, n, (const double *)(base + o_Z),
+                                   (const int *)(base + o_si), d_pp[0], d_pp[1], d_pp[2], d_pp[3]))
+            return -1;
+        if (use_ext) return postproc_ext_enqueue(pd, pe, st, a, n, (const double *)(base + o_Z),
+                                                 (const int *)(base + o_si), (const C *)(base + o_c),
+                                                 d_fl, d_sh, pp_plane / oelem);
         return 0;
     };
     int rc = run_pipelined(c, u, c_pix, axes, o_c, planes, np, o_Z, o_si + npts * 4, o_sr, enqueue,
                            interrupted, stats, &was_int);
     if (rc) return rc;
-    if (stats && pp) stats->n_launches *= 2;
+    if (stats && pp) stats->n_launches *= use_ext ? 3 : 2;
     return was_int ? FSB_USER_INTERRUPTED : 0;
 }
 
@@ -1878,6 +1947,77 @@ int fsb_frame_run_grid_pp(fsb_frame *f, int32_t n_tiles, const int32_t *tile_w,
     void *outs[4] = {nu, dem, normal_x, normal_y};
     return frame_run_impl(c, f, n_tiles, tile_w, tile_h, 0, nullptr, nullptr, nullptr, stop_reason,
                           stop_iter, interrupted, stats, pp, outs, axes);
+}
+
+int fsb_frame_run_grid_pp_ext(fsb_frame *f, int32_t n_tiles, const int32_t *tile_w,
+                              const int32_t *tile_h, const double *axes,
+                              const fsb_postproc_desc *pp, const fsb_postproc_ext *ext,
+                              void *nu, void *dem, void *normal_x, void *normal_y,
+                              void *fieldlines, void *shade, int8_t *stop_reason,
+                              int32_t *stop_iter, const volatile uint8_t *interrupted,
+                              fsb_stats *stats)
+{
+    Ctx *c;
+    if (get_ctx(&c)) return -1;
+    if (!f) return fail(-3, "null frame");
+    if (!pp) return fail(-3, "null post-processing description");
+    if ((fieldlines || shade) && !ext) return fail(-3, "null field-lines / shading description");
+    if (f->d.proj.kind != FSB_PROJ_CARTESIAN && (dem || normal_x || normal_y || fieldlines || shade))
+        return fail(-3, "fused DEM / normal / field-lines post-processing is only defined for the Cartesian projection");
+    if (n_tiles <= 0 || !axes) return fail(-3, "empty tile list / null axes");
+    void *outs[4] = {nu, dem, normal_x, normal_y};
+    return frame_run_impl(c, f, n_tiles, tile_w, tile_h, 0, nullptr, nullptr, nullptr, stop_reason,
+                          stop_iter, interrupted, stats, pp, outs, axes, ext, fieldlines, shade);
+}
+
+int fsb_postproc_ext_run_device(const fsb_postproc_desc *pp, const fsb_postproc_ext *ext,
+                                int64_t npts, int32_t n_rows, const double *d_Z,
+                                const int32_t *d_stop_iter, const double *d_c_pix,
+                                void *d_fieldlines, void *d_shade)
+{
+    Ctx *c;
+    if (get_ctx(&c)) return -1;
+    if (npts <= 0) return 0;
+    PostprocDev pd;
+    PostprocExtDev pe;
+    if (postproc_fill(pp, npts, n_rows, pd)) return -3;
+    if (postproc_ext_fill(pp, ext, n_rows, d_fieldlines != nullptr, d_shade != nullptr, pe)) return -3;
+    if (d_fieldlines && !d_c_pix) return fail(-3, "field lines need the pixel offsets");
+    if (postproc_ext_enqueue(pd, pe, c->stream, 0, npts, d_Z, d_stop_iter, (const C *)d_c_pix,
+                             d_fieldlines, d_shade, npts)) return -1;
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int fsb_postproc_ext_run(const fsb_postproc_desc *pp, const fsb_postproc_ext *ext, int64_t npts,
+                         int32_t n_rows, const double *Z, const int32_t *stop_iter,
+                         const double *c_pix, void *fieldlines, void *shade)
+{
+    Ctx *c;
+    if (get_ctx(&c)) return -1;
+    if (npts <= 0) return 0;
+    if (!pp || !ext) return fail(-3, "null post-processing description");
+    if (fieldlines && !c_pix) return fail(-3, "field lines need the pixel offsets");
+    const int n_shade = shade ? 2 * ext->n_lights : 0;
+    if (n_shade < 0 || n_shade > 2 * FSB_PP_MAX_LIGHTS) return fail(-3, "bad number of light sources");
+    const long long zelem = pp->holomorphic ? 16 : 8, oelem = pp->out_f64 ? 8 : 4;
+    const long long o_Z = 0, o_si = align256(n_rows * npts * zelem), o_c = align256(o_si + npts * 4),
+                    o_fl = align256(o_c + npts * 16), o_sh = align256(o_fl + npts * oelem),
+                    total = o_sh + align256(n_shade * npts * oelem);
+    if (ctx_reserve(c, total)) return -1;
+    char *base = (char *)c->d_buf;
+    CK(cudaMemcpyAsync(base + o_Z, Z, (size_t)(n_rows * npts * zelem), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(base + o_si, stop_iter, (size_t)(npts * 4), cudaMemcpyHostToDevice, c->stream));
+    if (c_pix) CK(cudaMemcpyAsync(base + o_c, c_pix, (size_t)(npts * 16), cudaMemcpyHostToDevice, c->stream));
+    int rc = fsb_postproc_ext_run_device(pp, ext, npts, n_rows, (const double *)(base + o_Z),
+                                         (const int32_t *)(base + o_si),
+                                         c_pix ? (const double *)(base + o_c) : nullptr,
+                                         fieldlines ? base + o_fl : nullptr,
+                                         shade ? base + o_sh : nullptr);
+    if (rc) return rc;
+    if (fieldlines) CK(cudaMemcpy(fieldlines, base + o_fl, (size_t)(npts * oelem), cudaMemcpyDeviceToHost));
+    if (shade) CK(cudaMemcpy(shade, base + o_sh, (size_t)(n_shade * npts * oelem), cudaMemcpyDeviceToHost));
+    return 0;
 }
 
 int fsb_postproc_run_device(const fsb_postproc_desc *pp, int64_t npts, int32_t n_rows,

@@ -833,6 +833,20 @@ k_perturb_m2_v2(const __grid_constant__ FrameDev f, long long npts_ll,
     for (int q = 0; q < 5; q++) s_cnt[q][threadIdx.x] = 0;
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
+#if FSB_STAGE_TMA
+    /* orbit staging experiment: one window of FSB_STAGE_WIN orbit records per warp,
+     * filled by a 1-D bulk copy (TMA) that completes on the warp's mbarrier */
+    __shared__ __align__(128) double4 s_win[4][FSB_STAGE_WIN];
+    __shared__ __align__(8) unsigned long long s_mbar[4];
+    const unsigned win_addr = (unsigned)__cvta_generic_to_shared(&s_win[threadIdx.x >> 5][0]);
+    const unsigned mbar_addr = (unsigned)__cvta_generic_to_shared(&s_mbar[threadIdx.x >> 5]);
+    unsigned win_phase = 0;
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mbar_addr));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+#endif
     LaneM2 s;
     LaneCold &k = s_cold[threadIdx.x];
     lane_park(s, LF_NEED | LF_EV);
@@ -954,6 +968,44 @@ k_perturb_m2_v2(const __grid_constant__ FrameDev f, long long npts_ll,
                 Zr = rb0; Zi = rb1; \
                 if (__any_sync(FULL, ev | bad)) break; \
             } } while (0)
+#if FSB_STAGE_TMA
+        /* staged loop: every lane alive and on the same reference index, whose wlim
+         * (arming: at most FSB_STAGE_WIN ahead of an index the warp has passed) lies
+         * inside the window */
+        const int w0 = __shfl_sync(FULL, s.w, 0);
+        if (__all_sync(FULL, alive && s.w == w0 && s.wlim <= w0 + FSB_STAGE_WIN)) {
+            if (lane == 0) {
+                const double4 *src = T2 + (long long)w0;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                             :: "r"(mbar_addr), "r"(FSB_STAGE_WIN * 32) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"(win_addr), "l"(src), "r"(FSB_STAGE_WIN * 32), "r"(mbar_addr) : "memory");
+            }
+            unsigned ok;
+            do {
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                             : "=r"(ok) : "r"(mbar_addr), "r"(win_phase) : "memory");
+            } while (!ok);
+            win_phase ^= 1u;
+#define FSB_LD_WIN(R, idx) do { const unsigned a_ = win_addr + 32u * (unsigned)((idx) - w0); \
+            asm volatile("ld.shared.v2.f64 {%0,%1}, [%4];\n\tld.shared.v2.f64 {%2,%3}, [%4+16];" \
+                : "=d"(R##0), "=d"(R##1), "=d"(R##2), "=d"(R##3) : "r"(a_)); } while (0)
+            double ra0, ra1, ra2, ra3, rb0, rb1, rb2, rb3;
+            for (;;) {
+                FSB_LD_WIN(ra, s.w);
+                m2_hot_iter<XR, DZNDC, BLA>(s, Zr, Zi, ra2, ra3);
+                m2_hot_flags<XR, DZNDC, BLA>(s, ra0, ra1, h3tab, esc_hi, ev, bad);
+                if (__any_sync(FULL, ev | bad)) { Zr = ra0; Zi = ra1; break; }
+                FSB_LD_WIN(rb, s.w);
+                m2_hot_iter<XR, DZNDC, BLA>(s, ra0, ra1, rb2, rb3);
+                m2_hot_flags<XR, DZNDC, BLA>(s, rb0, rb1, h3tab, esc_hi, ev, bad);
+                Zr = rb0; Zi = rb1;
+                if (__any_sync(FULL, ev | bad)) break;
+            }
+#undef FSB_LD_WIN
+            __syncwarp();
+        } else
+#endif
         if (__all_sync(FULL, alive)) FSB_HOT_LOOP(false);
         else FSB_HOT_LOOP(true);
 #endif
@@ -2026,6 +2078,155 @@ k_postproc(PostprocDev p, long long first, long long n, const double *__restrict
             nx /= a; ny /= a;
             if (p.out_f64) { pp_store<double>(out_nx, i, nx); pp_store<double>(out_ny, i, ny); }
             else { pp_store<float>(out_nx, i, nx); pp_store<float>(out_ny, i, ny); }
+        }
+    }
+}
+
+/* Field lines and Blinn coefficients (fsb_postproc_ext, include/fsb200.h).  One thread
+ * per point; reads the same raw rows as k_postproc plus the pixel offset. */
+struct PostprocExtDev {
+    int fl_n, fl_row_orbit, fl_backshift, fl_model;
+    double fl_k[FSB_PP_MAX_FL], fl_phi[FSB_PP_MAX_FL];
+    double cx, cy, cs, cm[4];
+    int n_lights;
+    double ncoeff;
+    double light[FSB_PP_MAX_LIGHTS][8];
+};
+
+__device__ __forceinline__ void pp_iterate(int model, double &x, double &y, double a, double b)
+{
+    if (model < 0) {                       /* xnyn_iterate, burning_ship.py:82-122 */
+        double ox, oy;
+        bs_iterate_perturb(-model, x, y, a, b, ox, oy);
+        x = ox; y = oy;
+        return;
+    }
+    double px = x, py = y;                 /* zn ** N + c */
+    for (int k = 1; k < model; k++) {
+        const double tx = px * x - py * y, ty = px * y + py * x;
+        px = tx; py = ty;
+    }
+    x = px + a; y = py + b;
+}
+/* Catmull-Rom polynomials, postproc.py:1020-1035 */
+__device__ __forceinline__ double cm_h0(double x) { return 0.5 * x * (-x + x * x); }
+__device__ __forceinline__ double cm_h1(double x) { return 0.5 * x * (1. + 4. * x - 3. * (x * x)); }
+__device__ __forceinline__ double cm_h2(double x) { return 1. + 0.5 * x * (-5. * x + 3. * (x * x)); }
+__device__ __forceinline__ double cm_h3(double x) { return 0.5 * x * (-1. + 2. * x - x * x); }
+
+__global__ void __launch_bounds__(256)
+k_postproc_ext(PostprocDev p, PostprocExtDev e, long long first, long long n,
+               const double *__restrict__ Z, const int *__restrict__ stop_iter,
+               const C *__restrict__ c_pix, void *__restrict__ out_fl, void *__restrict__ out_shade,
+               long long shade_stride)
+{
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n;
+         j += (long long)gridDim.x * blockDim.x) {
+        const long long i = first + j;
+        double zx, zy;
+        if (p.holomorphic) {
+            const double2 z = __ldg(reinterpret_cast<const double2 *>(Z) + p.row_zn * p.zstride + i);
+            zx = z.x; zy = z.y;
+        } else {
+            zx = __ldg(Z + p.row_zn * p.zstride + i);
+            zy = __ldg(Z + (p.row_zn + 1) * p.zstride + i);
+        }
+        if (out_fl && e.fl_n > 0) {
+            /* nu_frac and n of Continuous_iter_pp (postproc.py:352-406) */
+            const double abs_zn = hypot(zx, zy);
+            const double nu0 = -(log(log(abs_zn * p.k) / p.log_Mk) * p.inv_log_d);
+            const double q = floor(-nu0);
+            const double nu_frac = -(-nu0 - q);
+            const int n_i = stop_iter[i] - (int)q;
+            double ox = zx, oy = zy;
+            const bool backward = e.fl_row_orbit >= 0;
+            if (backward) {
+                if (p.holomorphic) {
+                    const double2 z = __ldg(reinterpret_cast<const double2 *>(Z) + e.fl_row_orbit * p.zstride + i);
+                    ox = z.x; oy = z.y;
+                } else {
+                    ox = __ldg(Z + e.fl_row_orbit * p.zstride + i);
+                    oy = __ldg(Z + (e.fl_row_orbit + 1) * p.zstride + i);
+                }
+            }
+            const C pix = ldC(c_pix, i);
+            const double ca = e.cx + e.cs * (e.cm[0] * pix.re + e.cm[1] * pix.im);
+            const double cb = e.cy + e.cs * (e.cm[2] * pix.re + e.cm[3] * pix.im);
+            double d = -nu_frac;
+            if (backward && e.fl_backshift > n_i) d = 1.;
+            const double a0 = cm_h0(d), a1 = cm_h1(d), a2 = cm_h2(d), a3 = cm_h3(d);
+            const double M_cutoff = 100000.;
+            /* sliding window of four orbit arguments */
+            double g0 = atan2(oy, ox), g1, g2, g3;
+            auto step = [&](double g) {
+                if (hypot(ox, oy) > M_cutoff) {
+                    double sn, cs;
+                    sincos(g, &sn, &cs);
+                    ox = cs * M_cutoff; oy = sn * M_cutoff;
+                    pp_iterate(e.fl_model, ox, oy, 0., 0.);
+                } else pp_iterate(e.fl_model, ox, oy, ca, cb);
+                return atan2(oy, ox);
+            };
+            g1 = step(g0); g2 = step(g1);
+            double val = 0.;
+            for (int t = 0; t < e.fl_n; t++) {
+                g3 = step(g2);
+                const double ph = e.fl_phi[t];
+                val += e.fl_k[t] * (a0 * sin(g0 + ph) + a1 * sin(g1 + ph) + a2 * sin(g2 + ph)
+                                    + a3 * sin(g3 + ph));
+                g0 = g1; g1 = g2; g2 = g3;
+            }
+            if (p.out_f64) pp_store<double>(out_fl, i, val); else pp_store<float>(out_fl, i, val);
+        }
+        if (out_shade && e.n_lights > 0) {
+            double dxa = 0., dxb = 0., dya = 0., dyb = 0.;
+            double nx, ny;
+            if (p.holomorphic) {
+                const double2 dd = __ldg(reinterpret_cast<const double2 *>(Z) + p.row_d * p.zstride + i);
+                dxa = dd.x; dya = dd.y;
+                if (fabs(dxa) >= fabs(dya)) {
+                    const double r = dya / dxa, den = dxa + dya * r;
+                    nx = (zx + zy * r) / den; ny = (zy - zx * r) / den;
+                } else {
+                    const double r = dxa / dya, den = dxa * r + dya;
+                    nx = (zx * r + zy) / den; ny = (zy * r - zx) / den;
+                }
+            } else {
+                dxa = __ldg(Z + p.row_d * p.zstride + i);
+                dxb = __ldg(Z + (p.row_d + 1) * p.zstride + i);
+                dya = __ldg(Z + (p.row_d + 2) * p.zstride + i);
+                dyb = __ldg(Z + (p.row_d + 3) * p.zstride + i);
+                nx = dxa * zx + dya * zy;
+                ny = dxb * zx + dyb * zy;
+            }
+            if (p.has_skew) {
+                const double ux = p.skew[0] * nx + p.skew[2] * ny;
+                const double uy = p.skew[1] * nx + p.skew[3] * ny;
+                nx = ux; ny = uy;
+            }
+            const double a = hypot(nx, ny);
+            nx /= a; ny /= a;
+            /* the layer reads the post array (float32 unless out_f64) and stores the
+             * scaled normal as complex64 (layers.py:499-506) */
+            if (!p.out_f64) { nx = (double)(float)nx; ny = (double)(float)ny; }
+            const float fx = (float)(nx * e.ncoeff), fy = (float)(ny * e.ncoeff);
+            nx = (double)fx; ny = (double)fy;
+            /* nz = sqrt(1. - nx ** 2 - ny ** 2) on float32 arrays (:877) */
+            const double nz = (double)__fsqrt_rn(__fsub_rn(__fsub_rn(1.f, __fmul_rn(fx, fx)), __fmul_rn(fy, fy)));
+            for (int l = 0; l < e.n_lights; l++) {
+                const double *L = e.light[l];
+                double lambert = L[0] * nx + L[1] * ny + L[2] * nz;
+                if (lambert < 0.) lambert = 0.;
+                double spec = 0.;
+                if (L[7] != 0.) {
+                    double sc = L[3] * nx + L[4] * ny + L[5] * nz;
+                    if (sc < 0.) sc = 0.;
+                    spec = pow(sc, L[6]);
+                }
+                const long long o0 = (2 * l) * shade_stride + i, o1 = (2 * l + 1) * shade_stride + i;
+                if (p.out_f64) { pp_store<double>(out_shade, o0, lambert); pp_store<double>(out_shade, o1, spec); }
+                else { pp_store<float>(out_shade, o0, lambert); pp_store<float>(out_shade, o1, spec); }
+            }
         }
     }
 }

@@ -848,6 +848,12 @@ enum : unsigned {
 #ifndef FSB_H3_DIRECT
 #define FSB_H3_DIRECT 0
 #endif
+#ifndef FSB_STAGE_TMA          /* orbit staging through shared memory by 1-D bulk copies (experiment, fsb_kernels.cuh) */
+#define FSB_STAGE_TMA 0
+#endif
+#ifndef FSB_STAGE_WIN          /* records per staged window */
+#define FSB_STAGE_WIN 64
+#endif
 #ifndef FSB_HOT_RECOMPUTE
 #define FSB_HOT_RECOMPUTE 0
 #endif
@@ -1365,6 +1371,9 @@ FSB_HD void lane_step(const FrameDev &f, LaneM2 &s, const C *c_pix, double *Z, i
 
     /* ---- arm the hot loop ---- */
     int wl = imin(f.ref_div_m1_i, f.max_iter_i - k.nbase);
+#if FSB_STAGE_TMA
+    wl = imin(wl, s.w + FSB_STAGE_WIN);      /* the staged loop reads one window of the orbit */
+#endif
     if (XR) {
         wl = imin(wl, s.w + FSB_XR_STRETCH);
         k.ck.zr = s.zr; k.ck.zi = s.zi; k.ck.dr = s.dr; k.ck.di = s.di; k.ck.w = s.w;

@@ -291,6 +291,56 @@ int fsb_postproc_run(const fsb_postproc_desc *pp, int64_t npts, int32_t n_rows,
                      const double *Z, const int32_t *stop_iter, void *nu, void *dem,
                      void *normal_x, void *normal_y);
 
+/* ---- field lines and Blinn shading (second part) -------------
+ * Fieldlines_pp (postproc.py:409-531; Fieldlines_pp_infinity[_BS] :1038-1160): the
+ * orbit is continued n_iter + 2 steps past the exit point with the model's
+ * zn_iterate / xnyn_iterate (mandelbrot_M2.py:13-15, mandelbrot_Mn.py:13-17,
+ * burning_ship.py:82-122), clamped on the circle of radius 1e5, and the sines of its
+ * arguments are blended with Catmull-Rom weights of the fractional iteration
+ * number.  Blinn_lighting.partial_shade (colors/layers.py:865-903) on the normal
+ * of DEM_normal_pp scaled by sin(max_slope) (Color_layer.apply_shade :493-507):
+ * the Lambert and the specular coefficient of each light source -- the two
+ * per-pixel factors of the shading; the colour arithmetic that multiplies them
+ * (XYZ of the base layer, k_diffuse, k_specular, light colour) stays with the
+ * caller's layers.  "infinity" potential, Cartesian projection. */
+#define FSB_PP_MAX_FL 32
+#define FSB_PP_MAX_LIGHTS 4
+typedef struct fsb_postproc_ext {
+    int32_t fl_n_iter;        /* Fieldlines_pp(n_iter); 0: no field-lines output      */
+    int32_t fl_row_orbit;     /* row of zn_orbit (xn_orbit) in Z; < 0: start from zn,
+                                 not backward (postproc.py:470-481)                   */
+    int32_t fl_backshift;     /* calc_orbit back-shift (context "backshift")          */
+    int32_t fl_model;         /* 2..32: z -> z^N + c ; -1..-5: burning-ship flavour   */
+    double fl_k[FSB_PP_MAX_FL];     /* k_arr   (geomspace(1, endpoint_k, n) / sum)    */
+    double fl_phi[FSB_PP_MAX_FL];   /* phi_arr (default_rng(0).random(n) swirl pi)    */
+    /* get_std_cpt (core.py:2781-2791, perturbation.py:197-208):
+     * c = center + scale * lin_mat . pix                                             */
+    double c_center[2], c_scale, c_lin_mat[4];
+    int32_t n_lights;  int32_t _pad;
+    double normal_coeff;      /* sin(Normal_map_layer.max_slope)                      */
+    /* per light: LSx, LSy, LSz, half_x, half_y, half_z, shininess, (k_specular != 0) */
+    double light[FSB_PP_MAX_LIGHTS][8];
+} fsb_postproc_ext;
+/* outputs (NULL = not wanted): fieldlines[npts]; shade[(2 n_lights) x npts] = rows
+ * lambert_0, specular_0, lambert_1, ... ; element type as fsb_postproc_desc.out_f64.
+ * c_pix: the pixel offsets of the points (complex128[npts]), needed by field lines. */
+int fsb_postproc_ext_run_device(const fsb_postproc_desc *pp, const fsb_postproc_ext *ext,
+                                int64_t npts, int32_t n_rows, const double *d_Z,
+                                const int32_t *d_stop_iter, const double *d_c_pix,
+                                void *d_fieldlines, void *d_shade);
+int fsb_postproc_ext_run(const fsb_postproc_desc *pp, const fsb_postproc_ext *ext,
+                         int64_t npts, int32_t n_rows, const double *Z,
+                         const int32_t *stop_iter, const double *c_pix, void *fieldlines,
+                         void *shade);
+/* fsb_frame_run_grid_pp with the two extra outputs */
+int fsb_frame_run_grid_pp_ext(fsb_frame *f, int32_t n_tiles, const int32_t *tile_w,
+                              const int32_t *tile_h, const double *axes,
+                              const fsb_postproc_desc *pp, const fsb_postproc_ext *ext,
+                              void *nu, void *dem, void *normal_x, void *normal_y,
+                              void *fieldlines, void *shade, int8_t *stop_reason,
+                              int32_t *stop_iter, const volatile uint8_t *interrupted,
+                              fsb_stats *stats);
+
 /* ---- Xrange device arithmetic, exposed for unit tests --------------------
  * (mirror of the reference's tests/test_numba_xr.py; runs on the GPU)
  * op: 0 add, 1 sub, 2 mul ; complex operands (re, im interleaved) */

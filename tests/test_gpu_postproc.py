@@ -174,7 +174,8 @@ import os
 import parity_common as pc
 from cases import CASES
 
-PP_GOLDEN = ["std_M2_cfg1", "p_M2_E20", "p_M2_deep250", "p_BS_f1_E30_skew", "std_BS_f1"]
+PP_GOLDEN = ["std_M2_cfg1", "p_M2_E20", "p_M2_deep250", "p_BS_f1_E30_skew", "std_BS_f1",
+             "std_M2_seahorse_orbit", "p_M2_divref_orbit", "p_BS_f2_E12"]
 
 
 @pytest.mark.parametrize("name", PP_GOLDEN)
@@ -213,5 +214,54 @@ def test_postproc_kernel_matches_reference_fixture(name):
         rates[key] = float(same.mean())
         assert same.mean() >= 0.999, (key, same.mean())
         assert nb.all(), key
+    # ---- Fieldlines_pp (postproc.py:409-531) and the Blinn coefficients
+    # (colors/layers.py:865-903), same fixtures ----
+    fl = fpp.Fieldlines_pp(**meta["fieldlines"])
+    lighting = fpp.Blinn_lighting(0.2, (1., 1., 1.))
+    for ls in meta["lights"]:
+        lighting.add_light_source(**ls)
+    c_pix = np.asarray(g["c_pix"])
+    for dt, tol_fl, tol_lam, tol_sp in ((np.float64, 1e-9, 1e-12, 1e-9), (np.float32, 2e-6, 2e-7, 2e-6)):
+        ext = fpp.fields_from_raw(f, "c", Z, si, fields=(), dtype=dt, c_pix=c_pix, fieldlines=fl,
+                                  lighting=lighting, max_slope=meta["max_slope"])
+        ref = np.asarray(g["fieldlines"], np.float64)
+        ok = esc & np.isfinite(ref)
+        assert ok.sum() > 100
+        # atan2 / sin / hypot of another libm, amplified by the angle doublings of the
+        # continued orbit: absolute tolerance on a value of magnitude <= 1
+        err = np.abs(ext["fieldlines"][ok].astype(np.float64) - ref[ok])
+        assert err.max() <= tol_fl, ("fieldlines", dt, err.max())
+        rates[f"fieldlines_maxerr_{np.dtype(dt).name}"] = float(err.max())
+        sh = np.asarray(g["shade"], np.float64)
+        assert ext["shade"].shape == sh.shape
+        for r in range(sh.shape[0]):
+            okr = esc & np.isfinite(sh[r])
+            tol = tol_lam if r % 2 == 0 else tol_sp
+            e2 = np.abs(ext["shade"][r][okr].astype(np.float64) - sh[r][okr])
+            assert e2.max() <= tol, ("shade row", r, dt, e2.max())
+        assert np.all(ext["shade"][3][esc] == 0.)          # second light: k_specular = 0
     print("\nPP_PARITY", name, json.dumps(rates))
     f._release_indep_args(f._calc_data["c"]["cycle_indep_args"])
+
+
+@pytest.mark.parametrize("model", ["m2", "bs"])
+def test_fused_fieldlines_and_shade_equal_standalone(model):
+    """ fsb_frame_run_grid_pp_ext against fsb_postproc_ext_run on the raw arrays """
+    f = _m2() if model == "m2" else _bs()
+    Z, si, sr = _raw(f)
+    fl = fpp.Fieldlines_pp(n_iter=5, swirl=0.5, endpoint_k=0.8)
+    lighting = fpp.Blinn_lighting(0.2, (1., 1., 1.), ls0=dict(
+        k_diffuse=1.8, k_specular=2., shininess=40., polar_angle=50., azimuth_angle=20.))
+    c_pix = np.concatenate([np.ravel(f.chunk_pixel_pos(cs, False, None)) for cs in f.chunk_slices()])
+    alone = fpp.fields_from_raw(f, "c", Z, si, c_pix=c_pix, fieldlines=fl, lighting=lighting)
+    fused, _ = fpp.frame_fields(f, "c", fieldlines=fl, lighting=lighting)
+    esc = sr == 1
+    assert np.array_equal(fused["stop_reason"], sr)
+    for k in fpp.FIELDS + ("fieldlines",):
+        assert np.array_equal(fused[k][esc], alone[k][esc], equal_nan=True), k
+    assert fused["shade"].shape == (2, Z.shape[1])
+    assert np.array_equal(fused["shade"][:, esc], alone["shade"][:, esc], equal_nan=True)
+    a = fused["fieldlines"][esc]
+    assert np.isfinite(a).mean() > 0.99 and np.nanstd(a) > 0.05       # a field, not a constant
+    lam = fused["shade"][0][esc]
+    assert np.nanmin(lam) >= 0. and np.nanmax(lam) <= 1.0000001 and np.nanstd(lam) > 0.01
