@@ -92,6 +92,7 @@ CUDA_SYMBOLS = [
     "fsb_fp64_peak_tflops", "fsb_proj_apply",
     "fsb_std_run_grid", "fsb_frame_run_grid", "fsb_frame_run_grid_pp",
     "fsb_postproc_ext_run", "fsb_postproc_ext_run_device", "fsb_frame_run_grid_pp_ext",
+    "fsb_postproc_run_proj", "fsb_postproc_run_proj_device",
 ]
 ORBIT_SYMBOLS = ["fsb_orbit_mandelbrot", "fsb_orbit_burning_ship",
                  "fsb_ball_method_mandelbrot", "fsb_find_nucleus_mandelbrot"]

@@ -1675,18 +1675,23 @@ static int postproc_fill(const fsb_postproc_desc *d, long long zstride, int n_ro
     p.has_skew = d->has_skew;
     for (int i = 0; i < 4; i++) p.skew[i] = d->skew[i];
     p.out_f64 = d->out_f64;
+    if (d->df_kind < 0 || d->df_kind > 3) return fail(-3, "unknown projection derivative %d", d->df_kind);
+    p.df_kind = d->row_dzndc >= 0 ? d->df_kind : 0;
+    p.df_kre = d->df_k[0]; p.df_kim = d->df_k[1];
     return 0;
 }
 
 static int postproc_enqueue(const PostprocDev &p, cudaStream_t st, long long first, long long n,
-                            const double *d_Z, const int *d_si, void *d_nu, void *d_dem,
-                            void *d_nx, void *d_ny)
+                            const double *d_Z, const int *d_si, const C *d_c, void *d_nu,
+                            void *d_dem, void *d_nx, void *d_ny)
 {
     if (n <= 0 || (!d_nu && !d_dem && !d_nx)) return 0;
+    if (p.df_kind != 0 && (d_dem || d_nx) && !d_c)
+        return fail(-3, "the projection derivative needs the pixel offsets (c_pix)");
     long long blocks = (n + 255) / 256;
     const long long cap = (long long)g_sm_count * 16;
     if (blocks > cap) blocks = cap;
-    k_postproc<<<(int)blocks, 256, 0, st>>>(p, first, n, d_Z, d_si, d_nu, d_dem, d_nx, d_ny);
+    k_postproc<<<(int)blocks, 256, 0, st>>>(p, first, n, d_Z, d_si, d_c, d_nu, d_dem, d_nx, d_ny);
     CK(cudaGetLastError());
     return 0;
 }
@@ -1708,6 +1713,8 @@ static int postproc_ext_fill(const fsb_postproc_desc *d, const fsb_postproc_ext 
         e.fl_n = x->fl_n_iter; e.fl_row_orbit = x->fl_row_orbit; e.fl_backshift = x->fl_backshift;
         e.fl_model = x->fl_model;
         for (int i = 0; i < x->fl_n_iter; i++) { e.fl_k[i] = x->fl_k[i]; e.fl_phi[i] = x->fl_phi[i]; }
+        e.P.kind = x->proj_kind == FSB_PROJ_EXPMAP ? 1 : 0;
+        e.P.hmoy = x->proj_hmoy; e.P.k_re = x->proj_k[0]; e.P.k_im = x->proj_k[1];
         e.cx = x->c_center[0]; e.cy = x->c_center[1]; e.cs = x->c_scale;
         for (int i = 0; i < 4; i++) e.cm[i] = x->c_lin_mat[i];
     }
@@ -1818,7 +1825,8 @@ static int frame_run_impl(Ctx *c, fsb_frame *f, int32_t n_tiles, const int32_t *
                           (double *)(base + o_Z), (int *)(base + o_U),
                           (signed char *)(base + o_sr), (int *)(base + o_si))) return -1;
         if (pp && postproc_enqueue(pd, st, a, n, (const double *)(base + o_Z),
-                                   (const int *)(base + o_si), d_pp[0], d_pp[1], d_pp[2], d_pp[3]))
+                                   (const int *)(base + o_si), (const C *)(base + o_c), d_pp[0],
+                                   d_pp[1], d_pp[2], d_pp[3]))
             return -1;
         if (use_ext) return postproc_ext_enqueue(pd, pe, st, a, n, (const double *)(base + o_Z),
                                                  (const int *)(base + o_si), (const C *)(base + o_c),
@@ -1897,10 +1905,8 @@ int fsb_frame_run_pp(fsb_frame *f, int32_t n_tiles, const int32_t *tile_w, const
     if (get_ctx(&c)) return -1;
     if (!f) return fail(-3, "null frame");
     if (!pp) return fail(-3, "null post-processing description");
-    /* the reference rotates / scales the derivatives with the projection's df
-     * in its post-processing (projection.py:375-453); not part of this kernel */
-    if (f->d.proj.kind != FSB_PROJ_CARTESIAN && (dem || normal_x || normal_y))
-        return fail(-3, "fused DEM / normal post-processing is only defined for the Cartesian projection");
+    /* the projection's df (projection.py:375-453) is part of the description (df_kind;
+     * 0 is what the stepped flow without rotation uses) */
     if (n_tiles <= 0 && npts <= 0) { if (stats) memset(stats, 0, sizeof *stats); return 0; }
     void *outs[4] = {nu, dem, normal_x, normal_y};
     return frame_run_impl(c, f, n_tiles, tile_w, tile_h, npts, c_pix, nullptr, nullptr,
@@ -1941,8 +1947,6 @@ int fsb_frame_run_grid_pp(fsb_frame *f, int32_t n_tiles, const int32_t *tile_w,
     if (get_ctx(&c)) return -1;
     if (!f) return fail(-3, "null frame");
     if (!pp) return fail(-3, "null post-processing description");
-    if (f->d.proj.kind != FSB_PROJ_CARTESIAN && (dem || normal_x || normal_y))
-        return fail(-3, "fused DEM / normal post-processing is only defined for the Cartesian projection");
     if (n_tiles <= 0 || !axes) return fail(-3, "empty tile list / null axes");
     void *outs[4] = {nu, dem, normal_x, normal_y};
     return frame_run_impl(c, f, n_tiles, tile_w, tile_h, 0, nullptr, nullptr, nullptr, stop_reason,
@@ -1962,8 +1966,8 @@ int fsb_frame_run_grid_pp_ext(fsb_frame *f, int32_t n_tiles, const int32_t *tile
     if (!f) return fail(-3, "null frame");
     if (!pp) return fail(-3, "null post-processing description");
     if ((fieldlines || shade) && !ext) return fail(-3, "null field-lines / shading description");
-    if (f->d.proj.kind != FSB_PROJ_CARTESIAN && (dem || normal_x || normal_y || fieldlines || shade))
-        return fail(-3, "fused DEM / normal / field-lines post-processing is only defined for the Cartesian projection");
+    if (fieldlines && (int)f->d.proj.kind != ext->proj_kind)
+        return fail(-3, "field lines: the projection of the description differs from the frame's");
     if (n_tiles <= 0 || !axes) return fail(-3, "empty tile list / null axes");
     void *outs[4] = {nu, dem, normal_x, normal_y};
     return frame_run_impl(c, f, n_tiles, tile_w, tile_h, 0, nullptr, nullptr, nullptr, stop_reason,
@@ -1983,6 +1987,8 @@ int fsb_postproc_ext_run_device(const fsb_postproc_desc *pp, const fsb_postproc_
     if (postproc_fill(pp, npts, n_rows, pd)) return -3;
     if (postproc_ext_fill(pp, ext, n_rows, d_fieldlines != nullptr, d_shade != nullptr, pe)) return -3;
     if (d_fieldlines && !d_c_pix) return fail(-3, "field lines need the pixel offsets");
+    if (d_shade && pd.df_kind != 0 && !d_c_pix)
+        return fail(-3, "the projection derivative needs the pixel offsets (c_pix)");
     if (postproc_ext_enqueue(pd, pe, c->stream, 0, npts, d_Z, d_stop_iter, (const C *)d_c_pix,
                              d_fieldlines, d_shade, npts)) return -1;
     CK(cudaStreamSynchronize(c->stream));
@@ -2020,9 +2026,10 @@ int fsb_postproc_ext_run(const fsb_postproc_desc *pp, const fsb_postproc_ext *ex
     return 0;
 }
 
-int fsb_postproc_run_device(const fsb_postproc_desc *pp, int64_t npts, int32_t n_rows,
-                            const double *d_Z, const int32_t *d_stop_iter, void *d_nu,
-                            void *d_dem, void *d_normal_x, void *d_normal_y)
+int fsb_postproc_run_proj_device(const fsb_postproc_desc *pp, int64_t npts, int32_t n_rows,
+                                 const double *d_Z, const int32_t *d_stop_iter,
+                                 const double *d_c_pix, void *d_nu, void *d_dem,
+                                 void *d_normal_x, void *d_normal_y)
 {
     Ctx *c;
     if (get_ctx(&c)) return -1;
@@ -2033,9 +2040,46 @@ int fsb_postproc_run_device(const fsb_postproc_desc *pp, int64_t npts, int32_t n
         return fail(-3, "distance estimate / normal need the derivative rows");
     if ((d_normal_x == nullptr) != (d_normal_y == nullptr))
         return fail(-3, "the normal needs both of its output arrays");
-    if (postproc_enqueue(pd, c->stream, 0, npts, d_Z, d_stop_iter, d_nu, d_dem, d_normal_x,
-                         d_normal_y)) return -1;
+    if (postproc_enqueue(pd, c->stream, 0, npts, d_Z, d_stop_iter, (const C *)d_c_pix, d_nu, d_dem,
+                         d_normal_x, d_normal_y)) return -3;
     CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int fsb_postproc_run_device(const fsb_postproc_desc *pp, int64_t npts, int32_t n_rows,
+                            const double *d_Z, const int32_t *d_stop_iter, void *d_nu,
+                            void *d_dem, void *d_normal_x, void *d_normal_y)
+{
+    return fsb_postproc_run_proj_device(pp, npts, n_rows, d_Z, d_stop_iter, nullptr, d_nu, d_dem,
+                                        d_normal_x, d_normal_y);
+}
+
+int fsb_postproc_run_proj(const fsb_postproc_desc *pp, int64_t npts, int32_t n_rows,
+                          const double *Z, const int32_t *stop_iter, const double *c_pix,
+                          void *nu, void *dem, void *normal_x, void *normal_y)
+{
+    Ctx *c;
+    if (get_ctx(&c)) return -1;
+    if (npts <= 0) return 0;
+    if (!pp) return fail(-3, "null post-processing description");
+    const long long zelem = pp->holomorphic ? 16 : 8, oelem = pp->out_f64 ? 8 : 4;
+    const long long o_Z = 0, o_si = align256(n_rows * npts * zelem), o_c = align256(o_si + npts * 4),
+                    o_pp = align256(o_c + npts * 16), total = o_pp + 4 * align256(npts * oelem);
+    if (ctx_reserve(c, total)) return -1;
+    char *base = (char *)c->d_buf;
+    CK(cudaMemcpyAsync(base + o_Z, Z, (size_t)(n_rows * npts * zelem), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(base + o_si, stop_iter, (size_t)(npts * 4), cudaMemcpyHostToDevice, c->stream));
+    if (c_pix) CK(cudaMemcpyAsync(base + o_c, c_pix, (size_t)(npts * 16), cudaMemcpyHostToDevice, c->stream));
+    void *host[4] = {nu, dem, normal_x, normal_y};
+    void *dev[4];
+    for (int k = 0; k < 4; k++) dev[k] = host[k] ? base + o_pp + k * align256(npts * oelem) : nullptr;
+    int rc = fsb_postproc_run_proj_device(pp, npts, n_rows, (const double *)(base + o_Z),
+                                          (const int32_t *)(base + o_si),
+                                          c_pix ? (const double *)(base + o_c) : nullptr, dev[0],
+                                          dev[1], dev[2], dev[3]);
+    if (rc) return rc;
+    for (int k = 0; k < 4; k++)
+        if (host[k]) CK(cudaMemcpy(host[k], dev[k], (size_t)(npts * oelem), cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -2043,26 +2087,7 @@ int fsb_postproc_run(const fsb_postproc_desc *pp, int64_t npts, int32_t n_rows, 
                      const int32_t *stop_iter, void *nu, void *dem, void *normal_x,
                      void *normal_y)
 {
-    Ctx *c;
-    if (get_ctx(&c)) return -1;
-    if (npts <= 0) return 0;
-    if (!pp) return fail(-3, "null post-processing description");
-    const long long zelem = pp->holomorphic ? 16 : 8, oelem = pp->out_f64 ? 8 : 4;
-    const long long o_Z = 0, o_si = align256(n_rows * npts * zelem), o_pp = align256(o_si + npts * 4),
-                    total = o_pp + 4 * align256(npts * oelem);
-    if (ctx_reserve(c, total)) return -1;
-    char *base = (char *)c->d_buf;
-    CK(cudaMemcpyAsync(base + o_Z, Z, (size_t)(n_rows * npts * zelem), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(base + o_si, stop_iter, (size_t)(npts * 4), cudaMemcpyHostToDevice, c->stream));
-    void *host[4] = {nu, dem, normal_x, normal_y};
-    void *dev[4];
-    for (int k = 0; k < 4; k++) dev[k] = host[k] ? base + o_pp + k * align256(npts * oelem) : nullptr;
-    int rc = fsb_postproc_run_device(pp, npts, n_rows, (const double *)(base + o_Z),
-                                     (const int32_t *)(base + o_si), dev[0], dev[1], dev[2], dev[3]);
-    if (rc) return rc;
-    for (int k = 0; k < 4; k++)
-        if (host[k]) CK(cudaMemcpy(host[k], dev[k], (size_t)(npts * oelem), cudaMemcpyDeviceToHost));
-    return 0;
+    return fsb_postproc_run_proj(pp, npts, n_rows, Z, stop_iter, nullptr, nu, dem, normal_x, normal_y);
 }
 
 /* ---- unit-test / calibration entry points --------------------------------- */

@@ -1996,7 +1996,51 @@ struct PostprocDev {
     double px_snap;           /* < 0: none */
     int has_skew; double skew[4];
     int out_f64;
+    int df_kind; double df_kre, df_kim;     /* fsb_postproc_desc.df_kind / df_k */
 };
+
+/* Postproc.get_dzndc (postproc.py:184-206): the dz/dc rows times the projection's
+ * derivative -- apply_df (:973-979) on a complex row, apply_dfBS (:981-999) on the
+ * four Jacobian rows -- with Expmap.df / dfBS (projection.py:375-453) */
+__device__ __forceinline__ void pp_apply_df(const PostprocDev &p, const C *__restrict__ c_pix,
+                                            long long i, double &dxa, double &dxb, double &dya,
+                                            double &dyb)
+{
+    if (p.df_kind == 0) return;
+    const C pix = ldC(c_pix, i);
+    const double h = p.df_kre * pix.re - p.df_kim * pix.im;      /* ht = k pix */
+    const double t = p.df_kre * pix.im + p.df_kim * pix.re;
+    if (p.holomorphic) {
+        double fr, fi;
+        if (p.df_kind == 3) { fr = exp(h); fi = 0.; }
+        else {
+            double sn, cs;
+            sincos(t, &sn, &cs);
+            const double r = (p.df_kind == 2) ? exp(h) : 1.;
+            fr = cs * r; fi = sn * r;
+        }
+        const double nr = fr * dxa - fi * dya, ni = fr * dya + fi * dxa;
+        dxa = nr; dya = ni;
+        return;
+    }
+    double m00, m01, m10, m11;
+    if (p.df_kind == 1) {
+        double sn, cs;
+        sincos(t, &sn, &cs);
+        m00 = cs; m01 = -sn; m10 = sn; m11 = cs;
+    } else if (p.df_kind == 2) {
+        double sn, cs;
+        sincos(t, &sn, &cs);
+        const double r = exp(h), cr = cs * r, sr = sn * r;
+        m00 = -sr; m01 = -cr; m10 = cr; m11 = -sr;
+    } else {
+        const double r = exp(h);
+        m00 = r; m01 = 0.; m10 = 0.; m11 = r;
+    }
+    const double a = dxa * m00 + dxb * m10, b = dxa * m01 + dxb * m11;
+    const double c = dya * m00 + dyb * m10, d = dya * m01 + dyb * m11;
+    dxa = a; dxb = b; dya = c; dyb = d;
+}
 
 template <class T> __device__ __forceinline__ void pp_store(void *p, long long i, double v)
 {
@@ -2005,8 +2049,9 @@ template <class T> __device__ __forceinline__ void pp_store(void *p, long long i
 
 __global__ void __launch_bounds__(256)
 k_postproc(PostprocDev p, long long first, long long n, const double *__restrict__ Z,
-           const int *__restrict__ stop_iter, void *__restrict__ out_nu,
-           void *__restrict__ out_dem, void *__restrict__ out_nx, void *__restrict__ out_ny)
+           const int *__restrict__ stop_iter, const C *__restrict__ c_pix,
+           void *__restrict__ out_nu, void *__restrict__ out_dem, void *__restrict__ out_nx,
+           void *__restrict__ out_ny)
 {
     for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n;
          j += (long long)gridDim.x * blockDim.x) {
@@ -2030,6 +2075,7 @@ k_postproc(PostprocDev p, long long first, long long n, const double *__restrict
                 dyb = __ldg(Z + (p.row_d + 3) * p.zstride + i);
             }
         }
+        if (p.row_d >= 0) pp_apply_df(p, c_pix, i, dxa, dxb, dya, dyb);
         const double abs_zn = hypot(zx, zy);
         if (out_nu) {
             /* nu_frac = -log(log|zn k| / log(M k)) / log d, folded into (-1, 0] */
@@ -2088,6 +2134,7 @@ struct PostprocExtDev {
     int fl_n, fl_row_orbit, fl_backshift, fl_model;
     double fl_k[FSB_PP_MAX_FL], fl_phi[FSB_PP_MAX_FL];
     double cx, cy, cs, cm[4];
+    ProjDev P;
     int n_lights;
     double ncoeff;
     double light[FSB_PP_MAX_LIGHTS][8];
@@ -2149,7 +2196,7 @@ k_postproc_ext(PostprocDev p, PostprocExtDev e, long long first, long long n,
                     oy = __ldg(Z + (e.fl_row_orbit + 1) * p.zstride + i);
                 }
             }
-            const C pix = ldC(c_pix, i);
+            const C pix = project(e.P, ldC(c_pix, i));
             const double ca = e.cx + e.cs * (e.cm[0] * pix.re + e.cm[1] * pix.im);
             const double cb = e.cy + e.cs * (e.cm[2] * pix.re + e.cm[3] * pix.im);
             double d = -nu_frac;
@@ -2184,6 +2231,7 @@ k_postproc_ext(PostprocDev p, PostprocExtDev e, long long first, long long n,
             if (p.holomorphic) {
                 const double2 dd = __ldg(reinterpret_cast<const double2 *>(Z) + p.row_d * p.zstride + i);
                 dxa = dd.x; dya = dd.y;
+                pp_apply_df(p, c_pix, i, dxa, dxb, dya, dyb);
                 if (fabs(dxa) >= fabs(dya)) {
                     const double r = dya / dxa, den = dxa + dya * r;
                     nx = (zx + zy * r) / den; ny = (zy - zx * r) / den;
@@ -2196,6 +2244,7 @@ k_postproc_ext(PostprocDev p, PostprocExtDev e, long long first, long long n,
                 dxb = __ldg(Z + (p.row_d + 1) * p.zstride + i);
                 dya = __ldg(Z + (p.row_d + 2) * p.zstride + i);
                 dyb = __ldg(Z + (p.row_d + 3) * p.zstride + i);
+                pp_apply_df(p, c_pix, i, dxa, dxb, dya, dyb);
                 nx = dxa * zx + dya * zy;
                 ny = dxb * zx + dyb * zy;
             }

@@ -40,7 +40,8 @@ class FsbPostprocDesc(ctypes.Structure):
                 ("potential_d", ctypes.c_double), ("potential_a_d", ctypes.c_double),
                 ("potential_M", ctypes.c_double), ("floor_iter", ctypes.c_double),
                 ("px_snap", ctypes.c_double), ("skew", ctypes.c_double * 4),
-                ("out_f64", ctypes.c_int32), ("_pad", ctypes.c_int32)]
+                ("out_f64", ctypes.c_int32), ("df_kind", ctypes.c_int32),
+                ("df_k", ctypes.c_double * 2)]
 
 
 PP_MAX_FL, PP_MAX_LIGHTS = 32, 4
@@ -52,9 +53,10 @@ class FsbPostprocExt(ctypes.Structure):
                 ("fl_k", ctypes.c_double * PP_MAX_FL), ("fl_phi", ctypes.c_double * PP_MAX_FL),
                 ("c_center", ctypes.c_double * 2), ("c_scale", ctypes.c_double),
                 ("c_lin_mat", ctypes.c_double * 4),
-                ("n_lights", ctypes.c_int32), ("_pad", ctypes.c_int32),
+                ("n_lights", ctypes.c_int32), ("proj_kind", ctypes.c_int32),
                 ("normal_coeff", ctypes.c_double),
-                ("light", (ctypes.c_double * 8) * PP_MAX_LIGHTS)]
+                ("light", (ctypes.c_double * 8) * PP_MAX_LIGHTS),
+                ("proj_hmoy", ctypes.c_double), ("proj_k", ctypes.c_double * 2)]
 
 
 class Fieldlines_pp:
@@ -139,6 +141,9 @@ def make_ext(fractal, calc_name, d, fieldlines=None, lighting=None, max_slope=70
         else:
             from .models import get_flavor_int
             x.fl_model = -int(get_flavor_int(fractal.flavor))
+        pd = fractal.projection.c_abi_desc()       # proj_impl of get_std_cpt
+        x.proj_kind, x.proj_hmoy = int(pd.kind), float(pd.hmoy)
+        x.proj_k[0], x.proj_k[1] = float(pd.pix_to_ht[0]), float(pd.pix_to_ht[1])
         x.c_center[0], x.c_center[1] = float(fractal.x), float(fractal.y)
         x.c_scale = float(fractal.dx)
         for i, v in enumerate(np.asarray(fractal.lin_mat, np.float64).ravel()):
@@ -170,6 +175,8 @@ def _declare(lib):
     lib.fsb_frame_run_grid_pp.argtypes = [vp, i32, vp, vp, vp, D, vp, vp, vp, vp, vp, vp, vp,
                                           ctypes.POINTER(_native.FsbStats)]
     lib.fsb_postproc_run.argtypes = [D, i64, i32, vp, vp, vp, vp, vp, vp]
+    lib.fsb_postproc_run_proj.argtypes = [D, i64, i32, vp, vp, vp, vp, vp, vp, vp]
+    lib.fsb_postproc_run_proj_device.argtypes = [D, i64, i32, vp, vp, vp, vp, vp, vp, vp]
     lib.fsb_postproc_run_device.argtypes = [D, i64, i32, vp, vp, vp, vp, vp, vp]
     lib._pp_declared = True
     return lib
@@ -203,23 +210,29 @@ def make_desc(fractal, calc_name, floor_iter=0, px_snap=None, dtype=np.float32):
     if dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
         raise ValueError("postproc dtype must be float32 or float64")
     d.out_f64 = int(dtype == np.dtype(np.float64))
+    d.df_kind, k = projection_df(fractal.projection)
+    d.df_k[0], d.df_k[1] = k.real, k.imag
     return d, dtype, len(codes)
 
 
-def _check_projection(fractal, names):
-    """ The reference scales / rotates dzndc by the projection's derivative
-    before DEM and normals (Postproc.get_dzndc -> apply_df / apply_dfBS with
-    proj.df, postproc.py:184-206); k_postproc does not: refused, never
-    approximated. """
+def projection_df(proj):
+    """ (df_kind, pix_to_ht) of fsb_postproc_desc: which derivative the
+    reference's Postproc.get_dzndc applies for this projection
+    (projection.py:188-192 Cartesian: none; :375-453 Expmap, stepped or not) """
     from . import projection as _projection
-    if not (set(names) & {"DEM", "normal_x", "normal_y"}):
-        return
-    proj = fractal.projection
-    if not (type(proj) is _projection.Cartesian and getattr(proj, "expmap_seam", None) is None):
-        raise NotImplementedError(
-            "GPU DEM / normal post-processing is defined for the plain Cartesian "
-            f"projection only (got {type(proj).__name__}): the projection derivative of "
-            "Postproc.get_dzndc is not applied by k_postproc")
+    if isinstance(proj, _projection.Expmap):
+        k = complex(proj.pix_to_ht)
+        if proj.use_step:
+            return (1 if proj.rotates_df else 0), k
+        return (2 if proj.rotates_df else 3), k
+    return 0, 0j
+
+
+def _check_projection(fractal, names):
+    """ Projections cross the C ABI as parameters: anything else has no GPU form """
+    from . import projection as _projection
+    if not isinstance(fractal.projection, (_projection.Cartesian, _projection.Expmap)):
+        raise NotImplementedError(f"no GPU post-processing for {type(fractal.projection).__name__}")
 
 
 def _outputs(fields, npts, dtype, have_deriv):
@@ -240,10 +253,7 @@ def _outputs(fields, npts, dtype, have_deriv):
 def _check_ext(fractal, d, fieldlines, lighting):
     if fieldlines is None and lighting is None:
         return
-    from . import projection as _projection
-    proj = fractal.projection
-    if not (type(proj) is _projection.Cartesian and getattr(proj, "expmap_seam", None) is None):
-        raise NotImplementedError("GPU field lines / shading: plain Cartesian projection only")
+    _check_projection(fractal, ())
     if lighting is not None and d.row_dzndc < 0:
         raise ValueError("shading needs the derivative fields (calc_dzndc / calc_hessian)")
 
@@ -263,19 +273,24 @@ def fields_from_raw(fractal, calc_name, Z, stop_iter, fields=("cont_iter", "DEM"
     out = _outputs(fields, npts, dtype, d.row_dzndc >= 0)
     _check_projection(fractal, out)
     _check_ext(fractal, d, fieldlines, lighting)
+    cp = None
+    if c_pix is not None:
+        cp = np.ascontiguousarray(np.ravel(c_pix), dtype=np.complex128)
+        if cp.shape[0] != npts:
+            raise ValueError("c_pix does not match Z")
+    if d.df_kind != 0 and d.row_dzndc >= 0 and cp is None \
+            and ((set(out) & {"DEM", "normal_x", "normal_y"}) or lighting is not None):
+        raise ValueError("this projection's derivative needs c_pix (the pixel offsets of the points)")
     if out:
-        rc = lib.fsb_postproc_run(ctypes.byref(d), npts, Z.shape[0], _native.ptr(Z), _native.ptr(si),
-                                  *[_native.ptr(out.get(k)) for k in FIELDS])
+        rc = lib.fsb_postproc_run_proj(ctypes.byref(d), npts, Z.shape[0], _native.ptr(Z),
+                                       _native.ptr(si), _native.ptr(cp),
+                                       *[_native.ptr(out.get(k)) for k in FIELDS])
         _native.check(lib, rc)
     if fieldlines is not None or lighting is not None:
         x = make_ext(fractal, calc_name, d, fieldlines, lighting, max_slope)
-        cp = None
         if fieldlines is not None:
-            if c_pix is None:
+            if cp is None:
                 raise ValueError("field lines need c_pix (the pixel offsets of the points)")
-            cp = np.ascontiguousarray(np.ravel(c_pix), dtype=np.complex128)
-            if cp.shape[0] != npts:
-                raise ValueError("c_pix does not match Z")
             out["fieldlines"] = np.empty(npts, dtype)
         if lighting is not None:
             out["shade"] = np.empty((2 * x.n_lights, npts), dtype)

@@ -247,7 +247,14 @@ typedef struct fsb_postproc_desc {
     double floor_iter;        /* Continuous_iter_pp(floor_iter=...)             */
     double px_snap;           /* DEM_pp(px_snap=...), < 0: none                 */
     double skew[4];           /* Fractal.skew, row-major                        */
-    int32_t out_f64;  int32_t _pad;
+    int32_t out_f64;
+    /* derivative of the projection applied to the dz/dc rows before DEM and normal
+     * (Postproc.get_dzndc -> apply_df / apply_dfBS, postproc.py:184-206, 973-999, with
+     * Expmap.df / dfBS, projection.py:375-453); needs the pixel offsets (c_pix):
+     * 0 none (Cartesian); 1 exp(i Im(k pix)) (stepped flow, rotates_df); 2 exp(k pix);
+     * 3 exp(Re(k pix)); k = Expmap.pix_to_ht                                         */
+    int32_t df_kind;
+    double df_k[2];
 } fsb_postproc_desc;
 
 /* fused: pixel kernels + post-processing in one call; Z / U never leave the
@@ -283,13 +290,22 @@ int fsb_frame_run_grid_pp(fsb_frame *f, int32_t n_tiles, const int32_t *tile_w,
                           const fsb_postproc_desc *pp, void *nu, void *dem, void *normal_x,
                           void *normal_y, int8_t *stop_reason, int32_t *stop_iter,
                           const volatile uint8_t *interrupted, fsb_stats *stats);
-/* stand-alone: raw fields already on the device / on the host (n_rows rows of Z) */
+/* stand-alone: raw fields already on the device / on the host (n_rows rows of Z);
+ * the *_proj forms take the pixel offsets a non-zero df_kind needs */
 int fsb_postproc_run_device(const fsb_postproc_desc *pp, int64_t npts, int32_t n_rows,
                             const double *d_Z, const int32_t *d_stop_iter, void *d_nu,
                             void *d_dem, void *d_normal_x, void *d_normal_y);
 int fsb_postproc_run(const fsb_postproc_desc *pp, int64_t npts, int32_t n_rows,
                      const double *Z, const int32_t *stop_iter, void *nu, void *dem,
                      void *normal_x, void *normal_y);
+
+int fsb_postproc_run_proj_device(const fsb_postproc_desc *pp, int64_t npts, int32_t n_rows,
+                                 const double *d_Z, const int32_t *d_stop_iter,
+                                 const double *d_c_pix, void *d_nu, void *d_dem,
+                                 void *d_normal_x, void *d_normal_y);
+int fsb_postproc_run_proj(const fsb_postproc_desc *pp, int64_t npts, int32_t n_rows,
+                          const double *Z, const int32_t *stop_iter, const double *c_pix,
+                          void *nu, void *dem, void *normal_x, void *normal_y);
 
 /* ---- field lines and Blinn shading (second part) -------------
  * Fieldlines_pp (postproc.py:409-531; Fieldlines_pp_infinity[_BS] :1038-1160): the
@@ -302,7 +318,7 @@ int fsb_postproc_run(const fsb_postproc_desc *pp, int64_t npts, int32_t n_rows,
  * the Lambert and the specular coefficient of each light source -- the two
  * per-pixel factors of the shading; the colour arithmetic that multiplies them
  * (XYZ of the base layer, k_diffuse, k_specular, light colour) stays with the
- * caller's layers.  "infinity" potential, Cartesian projection. */
+ * caller's layers.  "infinity" potential. */
 #define FSB_PP_MAX_FL 32
 #define FSB_PP_MAX_LIGHTS 4
 typedef struct fsb_postproc_ext {
@@ -316,10 +332,12 @@ typedef struct fsb_postproc_ext {
     /* get_std_cpt (core.py:2781-2791, perturbation.py:197-208):
      * c = center + scale * lin_mat . pix                                             */
     double c_center[2], c_scale, c_lin_mat[4];
-    int32_t n_lights;  int32_t _pad;
+    int32_t n_lights;
+    int32_t proj_kind;        /* FSB_PROJ_*: proj_impl of get_std_cpt (Expmap: exp(hmoy + k pix)) */
     double normal_coeff;      /* sin(Normal_map_layer.max_slope)                      */
     /* per light: LSx, LSy, LSz, half_x, half_y, half_z, shininess, (k_specular != 0) */
     double light[FSB_PP_MAX_LIGHTS][8];
+    double proj_hmoy, proj_k[2];
 } fsb_postproc_ext;
 /* outputs (NULL = not wanted): fieldlines[npts]; shade[(2 n_lights) x npts] = rows
  * lambert_0, specular_0, lambert_1, ... ; element type as fsb_postproc_desc.out_f64.

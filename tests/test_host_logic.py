@@ -173,16 +173,22 @@ def test_struct_layouts_match_headers():
     #include "fsb200.h"
     #include "fsb200_orbit.h"
     #include <stdio.h>
-    int main(){ printf("%zu %zu %zu %zu\n", sizeof(fsb_stats), sizeof(fsb_std_desc),
-                       sizeof(fsb_frame_desc), sizeof(fsb_orbit_xr)); return 0; }'''
+    #include <stddef.h>
+    int main(){ printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(fsb_stats), sizeof(fsb_std_desc),
+                       sizeof(fsb_frame_desc), sizeof(fsb_orbit_xr), sizeof(fsb_postproc_desc),
+                       sizeof(fsb_postproc_ext), offsetof(fsb_postproc_desc, df_k),
+                       offsetof(fsb_postproc_ext, proj_hmoy)); return 0; }'''
     d = tempfile.mkdtemp()
     open(os.path.join(d, "s.c"), "w").write(src)
     import subprocess
     subprocess.check_call(["/usr/bin/gcc", "-I", os.path.join(REPO, "include"),
                            os.path.join(d, "s.c"), "-o", os.path.join(d, "s")])
     sizes = [int(x) for x in subprocess.check_output([os.path.join(d, "s")]).split()]
+    from fractalshades_b200 import postproc as fpp
     assert sizes == [ctypes.sizeof(_native.FsbStats), ctypes.sizeof(_native.FsbStdDesc),
-                     ctypes.sizeof(_native.FsbFrameDesc), ctypes.sizeof(_native.OrbitXr)]
+                     ctypes.sizeof(_native.FsbFrameDesc), ctypes.sizeof(_native.OrbitXr),
+                     ctypes.sizeof(fpp.FsbPostprocDesc), ctypes.sizeof(fpp.FsbPostprocExt),
+                     fpp.FsbPostprocDesc.df_k.offset, fpp.FsbPostprocExt.proj_hmoy.offset]
 
 
 def test_product_fails_loudly_without_gpu():
