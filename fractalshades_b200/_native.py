@@ -95,7 +95,9 @@ CUDA_SYMBOLS = [
     "fsb_postproc_run_proj", "fsb_postproc_run_proj_device",
 ]
 ORBIT_SYMBOLS = ["fsb_orbit_mandelbrot", "fsb_orbit_burning_ship",
-                 "fsb_ball_method_mandelbrot", "fsb_find_nucleus_mandelbrot"]
+                 "fsb_ball_method_mandelbrot", "fsb_find_nucleus_mandelbrot",
+                 "fsb_ball_method_burning_ship", "fsb_find_any_nucleus_burning_ship",
+                 "fsb_ball_method_mandelbrot_n", "fsb_find_any_nucleus_mandelbrot_n"]
 
 _libs = {}
 
@@ -234,8 +236,39 @@ def load_orbit_lib():
         lib.fsb_find_nucleus_mandelbrot.argtypes = [
             ctypes.c_char_p, ctypes.c_char_p, c_i64, c_i64, c_i64, ctypes.c_char_p,
             ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_char_p, c_i64]
+        cp = ctypes.c_char_p
+        for name, first in (("burning_ship", ctypes.c_int), ("mandelbrot_n", ctypes.c_uint32)):
+            fn = getattr(lib, "fsb_ball_method_" + name)
+            fn.restype = c_i64
+            fn.argtypes = [first, cp, cp, c_i64, cp, c_i64, c_dbl]
+            fn = getattr(lib, "fsb_find_any_nucleus_" + name)
+            fn.restype = ctypes.c_int
+            fn.argtypes = [first, cp, cp, c_i64, c_i64, c_i64, cp, cp, cp, cp, c_i64]
         _libs["orbit"] = lib
     return _libs["orbit"]
+
+
+def newton_call(fn_name, first, c, order, eps_pixel, max_newton, eps_cv):
+    """ shared wrapper of the fsb_find_any_nucleus_* entry points (the argument
+    handling of the reference's model methods, e.g. burning_ship.py:1203-1232) """
+    import mpmath
+    if order is None:
+        raise ValueError("order shall be defined for Newton method")
+    seed_prec = mpmath.mp.prec
+    if max_newton is None:
+        max_newton = 80
+    if eps_cv is None:
+        eps_cv = mpmath.mpf(val=(2, -seed_prec))
+    cap = int(seed_prec * 0.31) + 64
+    bx, by = ctypes.create_string_buffer(cap), ctypes.create_string_buffer(cap)
+    rc = getattr(load_orbit_lib(), fn_name)(
+        first, str(c.real).encode("utf8"), str(c.imag).encode("utf8"), seed_prec, int(order),
+        int(max_newton), str(eps_cv).encode("utf8"), str(eps_pixel).encode("utf8"), bx, by, cap)
+    if rc < 0:
+        raise RuntimeError(f"{fn_name} failed ({rc})")
+    if rc == 0:
+        return False, mpmath.mpc("nan", "nan")
+    return True, mpmath.mpc(mpmath.mpf(bx.value.decode()), mpmath.mpf(by.value.decode()))
 
 
 def ptr(a):

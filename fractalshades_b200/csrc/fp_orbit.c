@@ -76,6 +76,10 @@ extern void mpc_swap(fsb_mpc_struct *, fsb_mpc_struct *);
 extern int mpfr_ui_div(fsb_mpfr_struct *, unsigned long, const fsb_mpfr_struct *, int);
 extern int mpfr_cmp_d(const fsb_mpfr_struct *, double);
 extern int mpfr_greaterequal_p(const fsb_mpfr_struct *, const fsb_mpfr_struct *);
+extern int mpc_mul_ui(fsb_mpc_struct *, const fsb_mpc_struct *, unsigned long, int);
+extern int mpfr_add_si(fsb_mpfr_struct *, const fsb_mpfr_struct *, long, int);
+extern int mpfr_sgn(const fsb_mpfr_struct *);
+extern int mpfr_hypot(fsb_mpfr_struct *, const fsb_mpfr_struct *, const fsb_mpfr_struct *, int);
 extern char *mpfr_get_str(char *, long *, int, size_t, const fsb_mpfr_struct *, int);
 extern void mpfr_free_str(char *);
 
@@ -425,6 +429,348 @@ int fsb_find_nucleus_mandelbrot(const char *seed_x, const char *seed_y, int64_t 
 done:
     mpc_clear(c); mpc_clear(zr); mpc_clear(dzr); mpc_clear(h); mpc_clear(dh); mpc_clear(f);
     mpc_clear(df); mpc_clear(t1); mpc_clear(t2);
+    mpfr_clear(x_t); mpfr_clear(y_t); mpfr_clear(abs_diff); mpfr_clear(eps);
+    return cv;
+}
+
+
+/* ======================================================================== */
+/* Period and nucleus of the reference point, burning-ship family           */
+
+/* FP_loop.pyx:1778-1783: never 0 */
+static int sign_pm(const fsb_mpfr_struct *op) { return mpfr_sgn(op) >= 0 ? 1 : -1; }
+
+/* One step of the Jacobian d(xn, yn)/d(a, b) (var_ab_xy = 0) -- FP_loop.pyx:
+ * iter_J_BS :1458-1512, iter_J_pBS :1514-1565, iter_J_sharkfin :1567-1617,
+ * iter_J_celtic :1619-1675, iter_J_buffalo :1677-1743 -- the same MPFR calls in
+ * the same order.  (xx, xy, yx, yy) = (dxnda, dxndb, dynda, dyndb), updated
+ * in place from the CURRENT (xn, yn): called before the orbit step. */
+static void bs_jacobian_step(int kind, const fsb_mpfr_struct *xn, const fsb_mpfr_struct *yn,
+                             fsb_mpfr_struct *xx, fsb_mpfr_struct *xy, fsb_mpfr_struct *yx,
+                             fsb_mpfr_struct *yy, fsb_mpfr_struct *abs_xn, fsb_mpfr_struct *abs_yn,
+                             fsb_mpfr_struct *t_xx, fsb_mpfr_struct *t_xy, fsb_mpfr_struct *t_yx,
+                             fsb_mpfr_struct *t_yy, fsb_mpfr_struct *tmp)
+{
+    int sgn_xn = 1, sgn_yn = 1, sgn_d = 1;
+    const int first_abs = (kind == FSB_FLAVOR_CELTIC || kind == FSB_FLAVOR_BUFFALO);
+    const int second_abs_xy = (kind == FSB_FLAVOR_BURNING_SHIP || kind == FSB_FLAVOR_BUFFALO);
+    if (first_abs) {                       /* sign of x^2 - y^2 */
+        mpfr_sqr(tmp, xn, RNDN);
+        mpfr_sqr(t_xy, yn, RNDN);
+        mpfr_sub(t_xy, tmp, t_xy, RNDN);
+        sgn_d = sign_pm(t_xy);
+    }
+    if (second_abs_xy) {
+        if (kind == FSB_FLAVOR_BURNING_SHIP) {
+            fsb_mpfr_abs(abs_xn, xn); fsb_mpfr_abs(abs_yn, yn);
+            sgn_xn = sign_pm(xn); sgn_yn = sign_pm(yn);
+        } else {
+            sgn_xn = sign_pm(xn); sgn_yn = sign_pm(yn);
+            fsb_mpfr_abs(abs_xn, xn); fsb_mpfr_abs(abs_yn, yn);
+        }
+    } else if (kind == FSB_FLAVOR_PERPENDICULAR_BS) {
+        fsb_mpfr_abs(abs_yn, yn);
+        sgn_yn = sign_pm(yn);
+    } else if (kind == FSB_FLAVOR_SHARK_FIN) {
+        fsb_mpfr_abs(abs_yn, yn);
+    }
+    /* first row: 2 [sgn] (xn dx - Y dy), Y = yn (|yn| for the shark fin) */
+    {
+        const fsb_mpfr_struct *Y = (kind == FSB_FLAVOR_SHARK_FIN) ? abs_yn : yn;
+        mpfr_mul(t_xx, xn, xx, RNDN);
+        mpfr_mul(tmp, Y, yx, RNDN);
+        mpfr_sub(t_xx, t_xx, tmp, RNDN);
+        if (first_abs) mpfr_mul_si(t_xx, t_xx, sgn_d, RNDN);
+        mpfr_mul(t_xy, xn, xy, RNDN);
+        mpfr_mul(tmp, Y, yy, RNDN);
+        mpfr_sub(t_xy, t_xy, tmp, RNDN);
+        if (first_abs) mpfr_mul_si(t_xy, t_xy, sgn_d, RNDN);
+    }
+    /* second row */
+    if (second_abs_xy) {                   /* 2 (|xn| sgn_yn dy + sgn_xn dx |yn|) */
+        mpfr_mul(t_yx, abs_xn, yx, RNDN);
+        mpfr_mul_si(t_yx, t_yx, sgn_yn, RNDN);
+        mpfr_mul(tmp, abs_yn, xx, RNDN);
+        mpfr_mul_si(tmp, tmp, sgn_xn, RNDN);
+        mpfr_add(t_yx, t_yx, tmp, RNDN);
+        mpfr_mul(t_yy, abs_xn, yy, RNDN);
+        mpfr_mul_si(t_yy, t_yy, sgn_yn, RNDN);
+        mpfr_mul(tmp, abs_yn, xy, RNDN);
+        mpfr_mul_si(tmp, tmp, sgn_xn, RNDN);
+        mpfr_add(t_yy, t_yy, tmp, RNDN);
+    } else if (kind == FSB_FLAVOR_PERPENDICULAR_BS) {   /* 2 (xn sgn_yn dy + dx |yn|) */
+        mpfr_mul(t_yx, xn, yx, RNDN);
+        mpfr_mul_si(t_yx, t_yx, sgn_yn, RNDN);
+        mpfr_mul(tmp, abs_yn, xx, RNDN);
+        mpfr_add(t_yx, t_yx, tmp, RNDN);
+        mpfr_mul(t_yy, xn, yy, RNDN);
+        mpfr_mul_si(t_yy, t_yy, sgn_yn, RNDN);
+        mpfr_mul(tmp, abs_yn, xy, RNDN);
+        mpfr_add(t_yy, t_yy, tmp, RNDN);
+    } else {                               /* shark fin, celtic: 2 (xn dy + dx yn) */
+        mpfr_mul(t_yx, xn, yx, RNDN);
+        mpfr_mul(tmp, yn, xx, RNDN);
+        mpfr_add(t_yx, t_yx, tmp, RNDN);
+        mpfr_mul(t_yy, xn, yy, RNDN);
+        mpfr_mul(tmp, yn, xy, RNDN);
+        mpfr_add(t_yy, t_yy, tmp, RNDN);
+    }
+    mpfr_mul_si(xx, t_xx, 2, RNDN);
+    mpfr_mul_si(xy, t_xy, 2, RNDN);
+    mpfr_mul_si(yx, t_yx, 2, RNDN);
+    mpfr_mul_si(yy, t_yy, 2, RNDN);
+    mpfr_add_si(xx, xx, 1, RNDN);          /* derivatives with respect to (a, b) */
+    mpfr_add_si(yy, yy, -1, RNDN);
+}
+
+/* FP_loop.pyx:1786-1825: (x, y) with [a b; c d] (x, y)^T = (e, f)^T */
+static void matsolve2(fsb_mpfr_struct *x_res, fsb_mpfr_struct *y_res, const fsb_mpfr_struct *a,
+                      const fsb_mpfr_struct *b, const fsb_mpfr_struct *c, const fsb_mpfr_struct *d,
+                      const fsb_mpfr_struct *e, const fsb_mpfr_struct *f, fsb_mpfr_struct *delta,
+                      fsb_mpfr_struct *tmp)
+{
+    mpfr_mul(delta, a, d, RNDN);
+    mpfr_mul(tmp, c, b, RNDN);
+    mpfr_sub(delta, delta, tmp, RNDN);
+    mpfr_ui_div(delta, 1, delta, RNDN);
+    mpfr_mul(x_res, d, e, RNDN);
+    mpfr_mul(tmp, b, f, RNDN);
+    mpfr_sub(x_res, x_res, tmp, RNDN);
+    mpfr_mul(x_res, x_res, delta, RNDN);
+    mpfr_mul(y_res, a, f, RNDN);
+    mpfr_mul(tmp, c, e, RNDN);
+    mpfr_sub(y_res, y_res, tmp, RNDN);
+    mpfr_mul(y_res, y_res, delta, RNDN);
+}
+
+#define BS_NVARS 22
+/* FP_loop.pyx:2357-2465: first i <= maxiter with |J_i^-1 (x_i, y_i)| < px */
+int64_t fsb_ball_method_burning_ship(int flavor, const char *seed_x, const char *seed_y,
+                                     int64_t prec_bits, const char *seed_px, int64_t maxiter,
+                                     double M_divergence)
+{
+    fsb_mpfr_t v[BS_NVARS], lowp;
+    int64_t ret = -1, i;
+    int k;
+    if (flavor < FSB_FLAVOR_BURNING_SHIP || flavor > FSB_FLAVOR_BUFFALO) return -2;
+    for (k = 0; k < BS_NVARS; k++) mpfr_init2(v[k], prec_bits);
+    mpfr_init2(lowp, 54);
+#define xn v[0]
+#define yn v[1]
+#define a_t v[2]
+#define b_t v[3]
+#define xsq v[4]
+#define ysq v[5]
+#define xy_t v[6]
+#define dxa v[7]
+#define dxb v[8]
+#define dya v[9]
+#define dyb v[10]
+#define delta v[11]
+#define abs_xn v[12]
+#define abs_yn v[13]
+#define t_xx v[14]
+#define t_xy v[15]
+#define t_yx v[16]
+#define t_yy v[17]
+#define rx v[18]
+#define ry v[19]
+#define inv_pix v[20]
+#define tmp v[21]
+    if (mpfr_set_str(a_t, seed_x, 10, RNDN) != 0 || mpfr_set_str(b_t, seed_y, 10, RNDN) != 0 ||
+        mpfr_set_str(tmp, seed_px, 10, RNDN) != 0) {
+        ret = -3;
+        goto done;
+    }
+    mpfr_ui_div(inv_pix, 1, tmp, RNDN);
+    mpfr_set_si(xn, 0, RNDN); mpfr_set_si(yn, 0, RNDN);
+    mpfr_set_si(dxa, 0, RNDN); mpfr_set_si(dxb, 0, RNDN);
+    mpfr_set_si(dya, 0, RNDN); mpfr_set_si(dyb, 0, RNDN);
+    for (i = 1; i <= maxiter; i++) {
+        bs_jacobian_step(flavor, xn, yn, dxa, dxb, dya, dyb, abs_xn, abs_yn, t_xx, t_xy, t_yx,
+                         t_yy, tmp);
+        bs_step(flavor, xn, yn, a_t, b_t, xsq, ysq, xy_t);
+        matsolve2(rx, ry, dxa, dxb, dya, dyb, xn, yn, delta, tmp);
+        mpfr_mul(rx, rx, inv_pix, RNDN);
+        mpfr_mul(ry, ry, inv_pix, RNDN);
+        if (hypot(mpfr_get_d(xn, RNDN), mpfr_get_d(yn, RNDN)) > M_divergence) break;
+        fsb_mpfr_abs(lowp, rx);
+        if (mpfr_cmp_d(lowp, 1.) < 0) {
+            fsb_mpfr_abs(lowp, ry);
+            if (mpfr_cmp_d(lowp, 1.) < 0
+                && hypot(mpfr_get_d(rx, RNDN), mpfr_get_d(ry, RNDN)) < 1.) { ret = i; break; }
+        }
+    }
+done:
+    for (k = 0; k < BS_NVARS; k++) mpfr_clear(v[k]);
+    mpfr_clear(lowp);
+    return ret;
+}
+
+/* FP_loop.pyx:2564-2755: Newton on (x_order, y_order)(a, b) with the full Jacobian;
+ * divisors of `order` are not excluded.  Same return convention as
+ * fsb_find_nucleus_mandelbrot. */
+int fsb_find_any_nucleus_burning_ship(int flavor, const char *seed_x, const char *seed_y,
+                                      int64_t prec_bits, int64_t order, int64_t max_newton,
+                                      const char *seed_eps_cv, const char *seed_eps_valid,
+                                      char *out_x, char *out_y, int64_t out_cap)
+{
+    fsb_mpfr_t v[BS_NVARS], eps, abs_diff;
+    int cv = 0, k;
+    int64_t i_newton, i;
+    if (flavor < FSB_FLAVOR_BURNING_SHIP || flavor > FSB_FLAVOR_BUFFALO || order < 1) return -2;
+    for (k = 0; k < BS_NVARS; k++) mpfr_init2(v[k], prec_bits);
+    mpfr_init2(eps, 54); mpfr_init2(abs_diff, 54);
+    if (mpfr_set_str(a_t, seed_x, 10, RNDN) != 0 || mpfr_set_str(b_t, seed_y, 10, RNDN) != 0 ||
+        mpfr_set_str(eps, seed_eps_cv, 10, RNDN) != 0) {
+        cv = -3;
+        goto done;
+    }
+    mpfr_mul_si(eps, eps, 64, RNDN);
+    for (i_newton = 0; i_newton < max_newton; i_newton++) {
+        mpfr_set_si(xn, 0, RNDN); mpfr_set_si(yn, 0, RNDN);
+        mpfr_set_si(dxa, 0, RNDN); mpfr_set_si(dxb, 0, RNDN);
+        mpfr_set_si(dya, 0, RNDN); mpfr_set_si(dyb, 0, RNDN);
+        for (i = 1; i <= order; i++) {
+            bs_jacobian_step(flavor, xn, yn, dxa, dxb, dya, dyb, abs_xn, abs_yn, t_xx, t_xy,
+                             t_yx, t_yy, tmp);
+            bs_step(flavor, xn, yn, a_t, b_t, xsq, ysq, xy_t);
+        }
+        /* (da, db) = J^-1 (xn, yn) ; (a, b) -= (da, db) */
+        matsolve2(rx, ry, dxa, dxb, dya, dyb, xn, yn, delta, tmp);
+        mpfr_sub(a_t, a_t, rx, RNDN);
+        mpfr_sub(b_t, b_t, ry, RNDN);
+        mpfr_hypot(abs_diff, rx, ry, RNDN);
+        if (mpfr_greaterequal_p(eps, abs_diff)) {
+            mpfr_hypot(abs_diff, xn, yn, RNDN);
+            if (mpfr_set_str(eps, seed_eps_valid, 10, RNDN) != 0) { cv = -3; goto done; }
+            cv = mpfr_greaterequal_p(eps, abs_diff) ? 1 : 0;
+            break;
+        }
+    }
+    if (cv == 1 && (put_decimal(out_x, out_cap, a_t) != 0 || put_decimal(out_y, out_cap, b_t) != 0))
+        cv = -4;
+done:
+    for (k = 0; k < BS_NVARS; k++) mpfr_clear(v[k]);
+    mpfr_clear(eps); mpfr_clear(abs_diff);
+    return cv;
+}
+#undef xn
+#undef yn
+#undef a_t
+#undef b_t
+#undef xsq
+#undef ysq
+#undef xy_t
+#undef dxa
+#undef dxb
+#undef dya
+#undef dyb
+#undef delta
+#undef abs_xn
+#undef abs_yn
+#undef t_xx
+#undef t_xy
+#undef t_yx
+#undef t_yy
+#undef rx
+#undef ry
+#undef inv_pix
+#undef tmp
+
+
+/* ======================================================================== */
+/* Period and nucleus of the reference point, z^N + c (N > 2)               */
+
+/* iter_deriv_Mn then iter_Mn, FP_loop.pyx:167-211 */
+static void mn_step_deriv(unsigned long exponent, fsb_mpc_struct *z, fsb_mpc_struct *dz,
+                          const fsb_mpc_struct *c, fsb_mpc_struct *tmp)
+{
+    if (exponent == 2) { m2_step_deriv(z, dz, c, tmp); return; }
+    mpc_pow_ui(tmp, z, exponent - 1, RNDNN);
+    mpc_mul(tmp, dz, tmp, RNDNN);
+    mpc_mul_ui(dz, tmp, exponent, RNDNN);
+    mpc_add_ui(dz, dz, 1, RNDNN);
+    mpc_pow_ui(tmp, z, exponent, RNDNN);
+    mpc_add(z, tmp, c, RNDNN);
+}
+
+/* perturbation_mandelbrotN_select_ball_method, FP_loop.pyx:631-758 */
+int64_t fsb_ball_method_mandelbrot_n(uint32_t exponent, const char *seed_x, const char *seed_y,
+                                     int64_t prec_bits, const char *seed_px, int64_t maxiter,
+                                     double M_divergence)
+{
+    fsb_mpc_t c, z, dz, tmp, r;
+    fsb_mpfr_t ar, x_t, y_t, pix, inv_pix;
+    int64_t ret = -1, i;
+    if (exponent < 2) return -2;
+    mpc_init2(c, prec_bits); mpc_init2(z, prec_bits); mpc_init2(dz, prec_bits);
+    mpc_init2(tmp, prec_bits); mpc_init2(r, prec_bits);
+    mpfr_init2(ar, 54); mpfr_init2(x_t, prec_bits); mpfr_init2(y_t, prec_bits);
+    mpfr_init2(pix, prec_bits); mpfr_init2(inv_pix, prec_bits);
+    if (mpfr_set_str(x_t, seed_x, 10, RNDN) != 0 || mpfr_set_str(y_t, seed_y, 10, RNDN) != 0 ||
+        mpfr_set_str(pix, seed_px, 10, RNDN) != 0) {
+        ret = -3;
+        goto done;
+    }
+    mpc_set_fr_fr(c, x_t, y_t, RNDNN);
+    mpfr_ui_div(inv_pix, 1, pix, RNDN);
+    mpc_set_si_si(z, 0, 0, RNDNN);
+    mpc_set_si_si(dz, 0, 0, RNDNN);
+    for (i = 1; i <= maxiter; i++) {
+        mn_step_deriv(exponent, z, dz, c, tmp);
+        mpc_div(r, z, dz, RNDNN);
+        mpc_mul_fr(r, r, inv_pix, RNDNN);
+        if (hypot(mpfr_get_d(z->re, RNDN), mpfr_get_d(z->im, RNDN)) > M_divergence) break;
+        mpc_abs(ar, r, RNDN);
+        if (mpfr_cmp_d(ar, 1.) < 0) { ret = i; break; }
+    }
+done:
+    mpc_clear(c); mpc_clear(z); mpc_clear(dz); mpc_clear(tmp); mpc_clear(r);
+    mpfr_clear(ar); mpfr_clear(x_t); mpfr_clear(y_t); mpfr_clear(pix); mpfr_clear(inv_pix);
+    return ret;
+}
+
+/* perturbation_mandelbrotN_select_find_any_nucleus, FP_loop.pyx:1159-1340 */
+int fsb_find_any_nucleus_mandelbrot_n(uint32_t exponent, const char *seed_x, const char *seed_y,
+                                      int64_t prec_bits, int64_t order, int64_t max_newton,
+                                      const char *seed_eps_cv, const char *seed_eps_valid,
+                                      char *out_x, char *out_y, int64_t out_cap)
+{
+    fsb_mpc_t c, zr, dzr, t1;
+    fsb_mpfr_t x_t, y_t, abs_diff, eps;
+    int cv = 0;
+    int64_t i_newton, i;
+    if (order < 1 || exponent < 2) return -2;
+    mpc_init2(c, prec_bits); mpc_init2(zr, prec_bits); mpc_init2(dzr, prec_bits);
+    mpc_init2(t1, prec_bits);
+    mpfr_init2(x_t, prec_bits); mpfr_init2(y_t, prec_bits);
+    mpfr_init2(abs_diff, 54); mpfr_init2(eps, 54);
+    if (mpfr_set_str(x_t, seed_x, 10, RNDN) != 0 || mpfr_set_str(y_t, seed_y, 10, RNDN) != 0 ||
+        mpfr_set_str(eps, seed_eps_cv, 10, RNDN) != 0) {
+        cv = -3;
+        goto done;
+    }
+    mpc_set_fr_fr(c, x_t, y_t, RNDNN);
+    mpfr_mul_si(eps, eps, 64, RNDN);
+    for (i_newton = 0; i_newton < max_newton; i_newton++) {
+        mpc_set_si_si(zr, 0, 0, RNDNN);
+        mpc_set_si_si(dzr, 0, 0, RNDNN);
+        for (i = 1; i <= order; i++) mn_step_deriv(exponent, zr, dzr, c, t1);
+        mpc_div(t1, zr, dzr, RNDNN);
+        mpc_sub(c, c, t1, RNDNN);
+        mpc_abs(abs_diff, t1, RNDN);
+        if (mpfr_greaterequal_p(eps, abs_diff)) {
+            mpc_abs(abs_diff, zr, RNDN);
+            if (mpfr_set_str(eps, seed_eps_valid, 10, RNDN) != 0) { cv = -3; goto done; }
+            cv = mpfr_greaterequal_p(eps, abs_diff) ? 1 : 0;
+            break;
+        }
+    }
+    if (cv == 1 && (put_decimal(out_x, out_cap, c->re) != 0 || put_decimal(out_y, out_cap, c->im) != 0))
+        cv = -4;
+done:
+    mpc_clear(c); mpc_clear(zr); mpc_clear(dzr); mpc_clear(t1);
     mpfr_clear(x_t); mpfr_clear(y_t); mpfr_clear(abs_diff); mpfr_clear(eps);
     return cv;
 }

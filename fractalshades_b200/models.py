@@ -263,9 +263,9 @@ class Perturbation_mandelbrot(PerturbationFractal):
 class Perturbation_mandelbrot_N(PerturbationFractal):
     """ Arbitrary-precision power-N Mandelbrot z -> z^N + c
     (models/mandelbrot_Mn.py:387-742): same perturbation loop, model formulas
-    as full binomial expansions.  No native nucleus search for N > 2
-    (FP_loop.pyx: perturbation_mandelbrotN_ball_method / find_nucleus): the
-    image centre is the reference point, as with settings.no_newton. """
+    as full binomial expansions.  Reference point: ball method + Newton descent
+    (fsb_ball_method_mandelbrot_n / fsb_find_any_nucleus_mandelbrot_n), as the
+    reference's model (mandelbrot_Mn.py:744-810). """
 
     def __init__(self, directory: str, exponent: int):
         super().__init__(directory)
@@ -283,6 +283,25 @@ class Perturbation_mandelbrot_N(PerturbationFractal):
     def FP_loop(self, NP_orbit, c0):
         """ models/mandelbrot_Mn.py:438-460 -> native MPFR orbit """
         return self._native_orbit(NP_orbit, c0, flavor=None, exponent=self.exponent)
+
+    def _ball_method(self, c, px, maxiter, M_divergence):
+        """ models/mandelbrot_Mn.py:744-762 -> fsb_ball_method_mandelbrot_n """
+        order = _native.load_orbit_lib().fsb_ball_method_mandelbrot_n(
+            self.exponent, str(c.real).encode("utf8"), str(c.imag).encode("utf8"),
+            mpmath.mp.prec, str(px).encode("utf8"), int(maxiter), float(M_divergence))
+        if order < -1:
+            raise RuntimeError(f"fsb_ball_method_mandelbrot_n failed ({order})")
+        return None if order == -1 else int(order)
+
+    def find_nucleus(self, c, order, eps_pixel, max_newton=None, eps_cv=None):
+        """ models/mandelbrot_Mn.py:765-779 """
+        raise NotImplementedError("Divide by undesired roots technique not implemented, "
+                                  "Use 'find_any_nucleus'")
+
+    def find_any_nucleus(self, c, order, eps_pixel, max_newton=None, eps_cv=None):
+        """ models/mandelbrot_Mn.py:782-810 -> fsb_find_any_nucleus_mandelbrot_n """
+        return _native.newton_call("fsb_find_any_nucleus_mandelbrot_n", self.exponent, c, order,
+                                   eps_pixel, max_newton, eps_cv)
 
     @calc_options
     def calc_std_div(self, *, calc_name: str, subset, max_iter: int,
@@ -343,6 +362,27 @@ class Perturbation_burning_ship(PerturbationFractal):
         """ models/burning_ship.py:937-968 """
         return self._native_orbit(NP_orbit, c0,
                                   flavor=get_flavor_int(self.flavor))
+
+    def _ball_method(self, c, px, maxiter, M_divergence):
+        """ models/burning_ship.py:1167-1186 -> fsb_ball_method_burning_ship """
+        order = _native.load_orbit_lib().fsb_ball_method_burning_ship(
+            get_flavor_int(self.flavor), str(c.real).encode("utf8"), str(c.imag).encode("utf8"),
+            mpmath.mp.prec, str(px).encode("utf8"), int(maxiter), float(M_divergence))
+        if order < -1:
+            raise RuntimeError(f"fsb_ball_method_burning_ship failed ({order})")
+        return None if order == -1 else int(order)
+
+    @staticmethod
+    def find_nucleus(c, order, eps_pixel, max_newton=None, eps_cv=None):
+        """ models/burning_ship.py:1189-1200 """
+        raise NotImplementedError("Divide by undesired roots technique "
+                                  "not implemented for burning ship")
+
+    def find_any_nucleus(self, c, order, eps_pixel, max_newton=None, eps_cv=None):
+        """ models/burning_ship.py:1203-1232 -> fsb_find_any_nucleus_burning_ship """
+        return _native.newton_call("fsb_find_any_nucleus_burning_ship",
+                                   get_flavor_int(self.flavor), c, order, eps_pixel,
+                                   max_newton, eps_cv)
 
     @calc_options
     def calc_std_div(self, *, calc_name: str, subset, max_iter: int,

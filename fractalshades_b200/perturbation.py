@@ -328,8 +328,8 @@ class PerturbationFractal(Fractal):
         """ perturbation.py:651-768 : reference point = the nucleus found by
         the ball method + Newton descent around the image centre (periodic
         reference, `ref_order` wrap), or the image centre itself when
-        settings.no_newton is set, the descent fails, or the model has no
-        native nucleus search. """
+        settings.no_newton is set or the descent fails.  Every model has its
+        native search (holomorphic power 2 / power N, burning-ship family). """
         if newton == "step":
             raise NotImplementedError("step option not Implemented (yet)")
         if self.ref_point_matching():
@@ -340,16 +340,6 @@ class PerturbationFractal(Fractal):
         if c0 is None:
             c0 = self.x + 1j * self.y
         if settings.no_newton or (newton is None) or (newton == "None"):
-            self.compute_FP_orbit(c0, None)
-            return
-        if not hasattr(self, "find_any_nucleus"):
-            # the burning-ship family: no native nucleus search (reference
-            # FP_loop.pyx:2217-2755) -- documented deviation, image centre
-            import warnings
-            warnings.warn(
-                f"{type(self).__name__}: no native nucleus search (ball method "
-                "+ Newton); the image centre is used as reference point, as "
-                "with settings.no_newton = True", RuntimeWarning)
             self.compute_FP_orbit(c0, None)
             return
         if order is None:

@@ -10,8 +10,8 @@ std_zoom_level = 1.e-8         # settings.py:18
 xrange_zoom_level = 1.e-300    # settings.py:22
 # False (the reference's default): the reference point of a perturbation frame
 # is the nucleus found by the ball method + Newton descent around the image
-# centre (holomorphic power-2 model; the burning-ship family has no native
-# nucleus search and uses the image centre with a warning).  True: always the
+# centre (every model: holomorphic power 2 and power N, burning-ship family).
+# True: always the
 # image centre -- what bench.py and the parity fixtures use.
 no_newton = False              # settings.py:25
 inspect_calc = False           # settings.py:30

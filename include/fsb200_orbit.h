@@ -92,6 +92,47 @@ int fsb_find_nucleus_mandelbrot(const char *seed_x, const char *seed_y, int64_t 
                                 const char *seed_eps_valid, int any_nucleus, char *out_x,
                                 char *out_y, int64_t out_cap);
 
+/* ---- the same for the burning-ship family --------------------------------
+ *   fsb_ball_method_burning_ship       <- perturbation_nonholomorphic_ball_method
+ *                                         (FP_loop.pyx:2357-2465; the per-flavour
+ *                                         wrappers :2217-2355): first iteration i with
+ *                                         |J_i^-1 (x_i, y_i)| < px, J the Jacobian of
+ *                                         (x_i, y_i) with respect to (a, b)
+ *                                         (iter_J_* :1458-1743); -1 / -3 as above,
+ *                                         -2 unknown flavour
+ *   fsb_find_any_nucleus_burning_ship  <- perturbation_nonholomorphic_find_any_nucleus
+ *                                         (:2564-2755): Newton descent with the full
+ *                                         Jacobian (matsolve :1799-1825); divisors of
+ *                                         `order` are not excluded (the reference has
+ *                                         no other form for this family,
+ *                                         burning_ship.py:1189-1200); returns as
+ *                                         fsb_find_nucleus_mandelbrot
+ */
+int64_t fsb_ball_method_burning_ship(int flavor, const char *seed_x, const char *seed_y,
+                                     int64_t prec_bits, const char *seed_px, int64_t maxiter,
+                                     double M_divergence);
+int fsb_find_any_nucleus_burning_ship(int flavor, const char *seed_x, const char *seed_y,
+                                      int64_t prec_bits, int64_t order, int64_t max_newton,
+                                      const char *seed_eps_cv, const char *seed_eps_valid,
+                                      char *out_x, char *out_y, int64_t out_cap);
+
+/* ---- and for z^N + c --------------------------------------------------------
+ *   fsb_ball_method_mandelbrot_n       <- perturbation_mandelbrotN_select_ball_method
+ *                                         (FP_loop.pyx:631-758; iter_deriv_Mn / iter_Mn
+ *                                         :167-211)
+ *   fsb_find_any_nucleus_mandelbrot_n  <- perturbation_mandelbrotN_select_find_any_nucleus
+ *                                         (:1159-1340); the reference has no
+ *                                         divide-by-divisors form for N > 2
+ *                                         (mandelbrot_Mn.py:765-779)
+ */
+int64_t fsb_ball_method_mandelbrot_n(uint32_t exponent, const char *seed_x, const char *seed_y,
+                                     int64_t prec_bits, const char *seed_px, int64_t maxiter,
+                                     double M_divergence);
+int fsb_find_any_nucleus_mandelbrot_n(uint32_t exponent, const char *seed_x, const char *seed_y,
+                                      int64_t prec_bits, int64_t order, int64_t max_newton,
+                                      const char *seed_eps_cv, const char *seed_eps_valid,
+                                      char *out_x, char *out_y, int64_t out_cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -139,6 +139,13 @@ for _i, _fl in enumerate(("Perpendicular burning ship", "Shark fin", "Celtic",
         calc=dict(max_iter=20000, M_divergence=1e3, BLA_eps=1e-6,
                   calc_hessian=True, calc_orbit=(_i == 0),
                   backshift=(2 if _i == 0 else 0)))
+# the reference's default flow for the family: ball method + Newton descent with
+# the full Jacobian (FP_loop.pyx:2357-2755) -> periodic reference (order 156 here)
+CASES["p_BS_f1_E12_newton"] = dict(
+    kind="perturb_BS", init=dict(flavor="Burning ship"), precision=30,
+    x=_BS_PTS[1][0], y=_BS_PTS[1][1], dx="1e-12", nx=32, newton=True,
+    calc=dict(max_iter=20000, M_divergence=1e3, BLA_eps=1e-6,
+              calc_hessian=True))
 CASES["p_BS_f1_E12_nohess_nobla"] = dict(
     kind="perturb_BS", init=dict(flavor="Burning ship"), precision=30,
     x=_BS_PTS[1][0], y=_BS_PTS[1][1], dx="1e-12", nx=32,
@@ -248,6 +255,13 @@ _MN_PTS = {
 CASES["p_M3_E20"] = dict(
     kind="perturb_M2", init=dict(exponent=3), precision=40, x=_MN_PTS[3][0],
     y=_MN_PTS[3][1], dx="3.e-20", nx=64, xy_ratio=1.25, theta_deg=25.,
+    calc=dict(max_iter=20000, BLA_eps=1e-6, interior_detect=False,
+              calc_dzndc=True, **_STD))
+# the reference's default flow for z^3 + c: ball method + Newton (FP_loop.pyx:631-758,
+# 1159-1340) -> periodic reference
+CASES["p_M3_E20_newton"] = dict(
+    kind="perturb_M2", init=dict(exponent=3), precision=40, x=_MN_PTS[3][0],
+    y=_MN_PTS[3][1], dx="3.e-20", nx=64, xy_ratio=1.25, theta_deg=25., newton=True,
     calc=dict(max_iter=20000, BLA_eps=1e-6, interior_detect=False,
               calc_dzndc=True, **_STD))
 CASES["p_M4_E18_interior"] = dict(

@@ -131,6 +131,56 @@ def _make_shim(fsx):
                                         mpmath.mpf(by.value.decode()))
         return impl
 
+    # burning-ship family and z^N + c: same contracts (FP_loop.pyx:2357-2755, 631-758,
+    # 1159-1340), served by the native library as well
+    cp = ctypes.c_char_p
+    for name, first in (("burning_ship", ctypes.c_int), ("mandelbrot_n", ctypes.c_uint32)):
+        fn = getattr(lib, "fsb_ball_method_" + name)
+        fn.restype = ctypes.c_int64
+        fn.argtypes = [first, cp, cp, ctypes.c_int64, cp, ctypes.c_int64, ctypes.c_double]
+        fn = getattr(lib, "fsb_find_any_nucleus_" + name)
+        fn.restype = ctypes.c_int
+        fn.argtypes = [first, cp, cp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, cp, cp,
+                       cp, cp, ctypes.c_int64]
+
+    def _any(fn_name, first, seed_x, seed_y, seed_prec, order, max_newton, seed_eps_cv,
+             seed_eps_valid):
+        import mpmath
+        cap = int(seed_prec * 0.31) + 64
+        bx = ctypes.create_string_buffer(cap)
+        by = ctypes.create_string_buffer(cap)
+        rc = getattr(lib, fn_name)(first, seed_x, seed_y, seed_prec, order, max_newton,
+                                   seed_eps_cv, seed_eps_valid, bx, by, cap)
+        if rc != 1:
+            return False, mpmath.mpc("nan", "nan")
+        with mpmath.workprec(seed_prec):
+            return True, mpmath.mpc(mpmath.mpf(bx.value.decode()), mpmath.mpf(by.value.decode()))
+
+    def perturbation_nonholomorphic_ball_method(seed_x, seed_y, seed_prec, seed_px, maxiter,
+                                                M_divergence, kind):
+        return int(lib.fsb_ball_method_burning_ship(kind, seed_x, seed_y, seed_prec, seed_px,
+                                                    maxiter, M_divergence))
+
+    def perturbation_nonholomorphic_find_any_nucleus(seed_x, seed_y, seed_prec, order,
+                                                     max_newton, seed_eps_cv, seed_eps_valid,
+                                                     kind):
+        return _any("fsb_find_any_nucleus_burning_ship", kind, seed_x, seed_y, seed_prec, order,
+                    max_newton, seed_eps_cv, seed_eps_valid)
+
+    def perturbation_mandelbrotN_ball_method(seed_x, seed_y, seed_prec, seed_px, exponent,
+                                             maxiter, M_divergence):
+        return int(lib.fsb_ball_method_mandelbrot_n(exponent, seed_x, seed_y, seed_prec, seed_px,
+                                                    maxiter, M_divergence))
+
+    def perturbation_mandelbrotN_find_any_nucleus(seed_x, seed_y, seed_prec, exponent, order,
+                                                  max_newton, seed_eps_cv, seed_eps_valid):
+        return _any("fsb_find_any_nucleus_mandelbrot_n", exponent, seed_x, seed_y, seed_prec,
+                    order, max_newton, seed_eps_cv, seed_eps_valid)
+
+    shim.perturbation_nonholomorphic_ball_method = perturbation_nonholomorphic_ball_method
+    shim.perturbation_nonholomorphic_find_any_nucleus = perturbation_nonholomorphic_find_any_nucleus
+    shim.perturbation_mandelbrotN_ball_method = perturbation_mandelbrotN_ball_method
+    shim.perturbation_mandelbrotN_find_any_nucleus = perturbation_mandelbrotN_find_any_nucleus
     shim.perturbation_mandelbrot_ball_method = perturbation_mandelbrot_ball_method
     shim.perturbation_mandelbrot_find_nucleus = _newton(0)
     shim.perturbation_mandelbrot_find_any_nucleus = _newton(1)
