@@ -789,11 +789,11 @@ int gpu_dzndc_m2(fsb_frame *f)
         CK(cudaMemcpy(&last, dm + i, sizeof(C), cudaMemcpyDeviceToHost));
         if (d.xr_detect) {
             CK(cudaMemcpy(&last_e, de + i, sizeof(int), cudaMemcpyDeviceToHost));
-            XC w = (2. * Zn[i]) * mkXC(last, last_e) + scale;
+            XC w = h_dfdz(d.nexp, to_xr(Zn[i])) * mkXC(last, last_e) + scale;
             CK(cudaMemcpy(dm, &w.m, sizeof(C), cudaMemcpyHostToDevice));
             CK(cudaMemcpy(de, &w.e, sizeof(int), cudaMemcpyHostToDevice));
         } else {
-            C w = (2. * Zn[i]) * last + to_std(scale);
+            C w = h_dfdz(d.nexp, Zn[i]) * last + to_std(scale);
             CK(cudaMemcpy(dm, &w, sizeof(C), cudaMemcpyHostToDevice));
         }
     }
@@ -1418,7 +1418,7 @@ int fsb_frame_create(const fsb_frame_desc *desc, fsb_frame **out)
         f->gpu_scan = false;              /* serial host loop: bit-exact with the oracle */
 #else
         const char *host = getenv("FSB200_HOST_DZNDC");
-        f->gpu_scan = d.model == FSB_MODEL_M2 && d.nexp == 0 && !(host && host[0] == '1');
+        f->gpu_scan = d.model == FSB_MODEL_M2 && !(host && host[0] == '1');
         f->gpu_scan_bs = d.model == FSB_MODEL_BS && !(host && host[0] == '1');
 #endif
     }

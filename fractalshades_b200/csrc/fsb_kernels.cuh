@@ -1678,12 +1678,14 @@ __device__ __forceinline__ AffXC aff_compose(const AffXC &first, const AffXC &th
 }
 __device__ __forceinline__ XC scan_coef(const FrameDev &f, long long j)
 {
-    /* a = 2 * Z[j], with the Xrange value for the sub-1e-300 orbit points */
+    /* a = dfdz(Z[j]) = 2 Z[j], with the Xrange value for the sub-1e-300 orbit points */
     const C z = ldC(f.Zn, j);
     int k = -1;
     if (f.n_xr_i > 0 && j != 0 && fabs(z.re) < 1.e-300 && fabs(z.im) < 1.e-300)
         k = xr_find(f.ref_index_xr, f.n_xr_i, (int)j);
     const XC rz = (k >= 0) ? mkXC(ldC(f.ref_xr, k), __ldg(f.ref_xr_e + k)) : to_xr(z);
+    /* z^N + c: dfdz = N z^(N-1) (mandelbrot_Mn.py:643-649) */
+    if (f.nexp > 2) return mn_dfdz(f.nexp, rz);
     return 2. * rz;
 }
 

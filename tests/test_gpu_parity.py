@@ -256,8 +256,11 @@ def test_power_n_xrange_with_derivatives_matches_oracle():
     assert pc.same_bits(Z, Zo) and pc.same_bits(U, Uo)
     d, de = gx["dzndc"]
     assert pc.same_bits(d, t["dZndc"]) and np.array_equal(de, t["dZndc_e"])
-    Z2, U2, sr2, si2, _ = pc.run_gpu_case("p_M5_E340_xr", strict=False, tables=(dict(t), c_pix))
+    Z2, U2, sr2, si2, gx2 = pc.run_gpu_case("p_M5_E340_xr", strict=False, tables=(dict(t), c_pix))
     assert ((si2 == sio) & (sr2 == sro)).mean() >= 0.999
+    # default build: the Xrange dZndc path of z^5 + c by the GPU affine scan
+    d2, de2 = gx2["dzndc"]
+    _assert_dzndc_close(d2, de2, t["dZndc"], t["dZndc_e"])
 
 
 def test_empty_and_ragged_inputs():
@@ -281,7 +284,10 @@ def test_empty_and_ragged_inputs():
 
 
 @pytest.mark.parametrize("name", ["p_M2_E20", "p_M2_shallow", "p_M2_flake", "p_M2_divref_orbit",
-                                  "p_M2_deep1000_xr", "p_M2_ultradeep_xr", "p_M2_deep250"])
+                                  "p_M2_deep1000_xr", "p_M2_ultradeep_xr", "p_M2_deep250",
+                                  "p_M2_E20_newton",
+                                  # z^N + c: dfdz = N z^(N-1) (mandelbrot_Mn.py:643-649)
+                                  "p_M3_E20", "p_M3_E20_newton"])
 def test_gpu_dzndc_scan_matches_serial_path(name, oracle_results):
     """ K6: the default build computes the dZndc path by a parallel affine scan
     on the GPU (perturbation.py:2282-2336 is a serial recurrence).  Different
@@ -291,7 +297,10 @@ def test_gpu_dzndc_scan_matches_serial_path(name, oracle_results):
     t = ex["tables"]
     Z, U, sr, si, gx = pc.run_gpu_case(name, strict=False, tables=(dict(t), ex["c_pix"]))
     d, de = gx["dzndc"]
-    ref, ref_e = t["dZndc"], t["dZndc_e"]
+    _assert_dzndc_close(d, de, t["dZndc"], t["dZndc_e"])
+
+
+def _assert_dzndc_close(d, de, ref, ref_e):
     if ref_e is None:
         fin = np.isfinite(ref) & np.isfinite(d) & (np.abs(ref) > 1e-290)
         assert fin.sum() > 10
