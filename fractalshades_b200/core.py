@@ -757,26 +757,39 @@ class Fractal(metaclass=_FractalMeta):
                 else:
                     runs.append([beg, end, off])
                 off += n
+            # The slabs go to the files with pwrite: filling fresh page-cache pages
+            # through a write call costs half of what page-faulting them through the
+            # mapping does (265 MB, 8 threads: 73 ms against 143 ms); the memmaps of
+            # the readers share the same page cache.
             jobs = []
             step = 1 << 20
+            fds = {key: os.open(mm[key].filename, os.O_RDWR) for key in self.SAVE_ARRS}
             for beg, end, o in runs:
                 for key in self.SAVE_ARRS:
+                    item, ncol, base = mm[key].itemsize, mm[key].shape[1], mm[key].offset
                     for field, f_field in enumerate(rows[key]):
                         for a0 in range(0, end - beg, step):
                             a1 = min(a0 + step, end - beg)
-                            jobs.append((mm[key], field, beg + a0, beg + a1,
+                            jobs.append((fds[key], base + (field * ncol + beg + a0) * item,
                                          arrs[key], f_field, o + a0, o + a1))
 
             def copy(job):
-                dst, field, b0, b1, src, f_field, s0, s1 = job
-                dst[field, b0:b1] = src[f_field, s0:s1]
-            if len(jobs) > 4 and settings.enable_multithreading:
-                with concurrent.futures.ThreadPoolExecutor(
-                        max_workers=min(8, os.cpu_count() or 1)) as pool:
-                    list(pool.map(copy, jobs))
-            else:
-                for job in jobs:
-                    copy(job)
+                fd, pos, src, f_field, s0, s1 = job
+                buf = np.ascontiguousarray(src[f_field, s0:s1]).view(np.uint8)
+                done = 0
+                while done < buf.size:
+                    done += os.pwrite(fd, buf[done:], pos + done)
+            try:
+                if len(jobs) > 4 and settings.enable_multithreading:
+                    with concurrent.futures.ThreadPoolExecutor(
+                            max_workers=min(settings.io_threads, os.cpu_count() or 1)) as pool:
+                        list(pool.map(copy, jobs))
+                else:
+                    for job in jobs:
+                        copy(job)
+            finally:
+                for fd in fds.values():
+                    os.close(fd)
             for rank, cs in batch:
                 rep[rank, done_col] = 1
             rep.flush()

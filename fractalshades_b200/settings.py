@@ -25,3 +25,5 @@ strict_ieee = False
 # Maximum number of points submitted to the GPU in one launch by the tile
 # scheduler (bounds device memory: ~60 B/pt for zn+dzndc).
 gpu_batch_pts = 1 << 25
+# Threads writing the raw planes of a batch of tiles to the memmap files (pwrite).
+io_threads = 16
