@@ -172,12 +172,36 @@ struct Ctx {
     }
 };
 thread_local Ctx *t_ctx = nullptr;
+/* frees the context of a worker thread when the thread ends (the seam is called
+ * from thread-per-tile pools); skipped once the CUDA runtime is unloading */
+struct CtxReaper {
+    ~CtxReaper()
+    {
+        if (t_ctx && g_device >= 0 && cudaSetDevice(g_device) == cudaSuccess) delete t_ctx;
+        t_ctx = nullptr;
+    }
+};
+thread_local CtxReaper t_ctx_reaper;
 
+static int ctx_build(Ctx *c);
 int get_ctx(Ctx **out)
 {
     if (ensure_init() != 0) return -1;
     if (!t_ctx) {
+        (void)&t_ctx_reaper;                      /* instantiate this thread's reaper */
         Ctx *c = new Ctx();
+        if (ctx_build(c) != 0) { delete c; return -1; }   /* no half-built context is kept */
+        t_ctx = c;
+    } else {
+        CK(cudaSetDevice(g_device));
+    }
+    *out = t_ctx;
+    return 0;
+}
+
+static int ctx_build(Ctx *c)
+{
+    {
         CK(cudaSetDevice(g_device));
         for (cudaStream_t *st : {&c->stream, &c->side, &c->s_alt, &c->s_h2d, &c->s_d2h})
             CK(cudaStreamCreateWithFlags(st, cudaStreamNonBlocking));
@@ -189,11 +213,7 @@ int get_ctx(Ctx **out)
         const size_t ctl_bytes = (MAX_CHUNKS * CTL_WORDS + 2) * sizeof(unsigned long long);
         CK(cudaMalloc(&c->d_ctl, ctl_bytes));
         CK(cudaHostAlloc(&c->h_ctl, ctl_bytes, cudaHostAllocDefault));
-        t_ctx = c;
-    } else {
-        CK(cudaSetDevice(g_device));
     }
-    *out = t_ctx;
     return 0;
 }
 
@@ -1466,7 +1486,7 @@ int fsb_frame_create(const fsb_frame_desc *desc, fsb_frame **out)
         UP(gpu_flush_mirror(f, (const double *)v.dZndc, v.dZndc_e, L, 2, 1, &dp));
         v.dZndc_std = (const C *)dp;
     }
-    CK(cudaDeviceSynchronize());
+    if (cudaDeviceSynchronize() != cudaSuccess) { fsb_frame_destroy(f); return fail(-1, "derivative path kernels failed"); }
     if (d.calc_dzndz) {
         if (d.dZndz) {
             UP(upload(f, (const C *)d.dZndz, L + 1, &v.dZndz));
