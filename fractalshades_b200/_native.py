@@ -106,6 +106,8 @@ def lib_path(strict=False):
     override = os.environ.get("FSB200_LIB")          # kernel A/B experiments
     if override:
         return override
+    if not strict and os.environ.get("FSB200_LIB_DEFAULT"):     # default build only
+        return os.environ["FSB200_LIB_DEFAULT"]
     return os.path.join(_PKG, "libfsb200_strict.so" if strict else "libfsb200.so")
 
 

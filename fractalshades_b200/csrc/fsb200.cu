@@ -1551,7 +1551,7 @@ int fsb_frame_create(const fsb_frame_desc *desc, fsb_frame **out)
         }
         v.T2 = (const double *)p;
         v.h3 = (const unsigned *)ph;
-        v.esc_hi = esc_hi_of(v.Mdiv_sq);
+        v.esc_hi = esc_word(esc_hi_of(v.Mdiv_sq));
     }
 #undef UP
     /* the descriptor copy must not keep caller pointers alive */

@@ -853,7 +853,7 @@ k_perturb_m2_v2(const __grid_constant__ FrameDev f, long long npts_ll,
     /* the warp's current unit: slots [pool_next, 32) are still to be handed out */
     int pool_next = 32, u_first = 0, u_r0 = 0, u_c0 = 0, u_w = 0, u_h = 0;
     bool exhausted = false;
-    const unsigned esc_hi = f.esc_hi;
+    const unsigned esc_hi = f.esc_hi;      /* in the form the loop compares: esc_word() */
     const double4 *__restrict__ T2 = reinterpret_cast<const double4 *>(f.T2);
     const unsigned *__restrict__ h3tab = f.h3;
     const int n_units = tiling.unit_hi - tiling.unit_lo;
@@ -925,7 +925,41 @@ k_perturb_m2_v2(const __grid_constant__ FrameDev f, long long npts_ll,
 #define FSB_LD_REC(R, idx) do { const double4 *rec_ = T2 + (long long)(idx); \
             asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" \
                 : "=d"(R##0), "=d"(R##1), "=d"(R##2), "=d"(R##3) : "l"(rec_)); } while (0)
-#if FSB_HOT_RECOMPUTE
+#if FSB_ZZ2
+        bool ev, bad;
+        double Cr, Ci;
+        m2_hot_enter(s, Cr, Ci);
+#if FSB_ZZ2 == 1
+#define FSB_HOT_LOOP(MASK) do { \
+            double ra0, ra1, ra2, ra3; \
+            for (;;) { \
+                FSB_LD_REC(ra, s.w); \
+                m2_hot_iter_c<XR, DZNDC, BLA>(s, Cr, Ci, 0., 0., ra2, ra3); \
+                m2_hot_flags_c<XR, DZNDC, BLA>(s, ra0, ra1, h3tab, esc_hi, ev, bad, Cr, Ci); \
+                if (MASK) { ev = ev & alive; bad = bad & alive; } \
+                if (__any_sync(FULL, ev | bad)) { Zr = 0.5 * ra0; Zi = 0.5 * ra1; break; } \
+            } } while (0)
+#else
+#define FSB_HOT_LOOP(MASK) do { \
+            double ra0, ra1, ra2, ra3, rb0, rb1, rb2, rb3; \
+            double Z2r = 2. * Zr, Z2i = 2. * Zi; \
+            for (;;) { \
+                FSB_LD_REC(ra, s.w); \
+                m2_hot_iter_c<XR, DZNDC, BLA>(s, Cr, Ci, Z2r, Z2i, ra2, ra3); \
+                m2_hot_flags_c<XR, DZNDC, BLA>(s, ra0, ra1, h3tab, esc_hi, ev, bad, Cr, Ci); \
+                if (MASK) { ev = ev & alive; bad = bad & alive; } \
+                if (__any_sync(FULL, ev | bad)) { Zr = 0.5 * ra0; Zi = 0.5 * ra1; break; } \
+                FSB_LD_REC(rb, s.w); \
+                m2_hot_iter_c<XR, DZNDC, BLA>(s, Cr, Ci, ra0, ra1, rb2, rb3); \
+                m2_hot_flags_c<XR, DZNDC, BLA>(s, rb0, rb1, h3tab, esc_hi, ev, bad, Cr, Ci); \
+                if (MASK) { ev = ev & alive; bad = bad & alive; } \
+                Z2r = rb0; Z2i = rb1; \
+                if (__any_sync(FULL, ev | bad)) { Zr = 0.5 * rb0; Zi = 0.5 * rb1; break; } \
+            } } while (0)
+#endif
+        if (__all_sync(FULL, alive)) FSB_HOT_LOOP(false);
+        else FSB_HOT_LOOP(true);
+#elif FSB_HOT_RECOMPUTE
 #define FSB_HOT_LOOP(MASK) do { \
             double ra0, ra1, ra2, ra3, rb0, rb1, rb2, rb3; \
             for (;;) { \
@@ -1963,7 +1997,8 @@ __global__ void k_build_t2(long long n_rec, const C *__restrict__ Zn, long long 
     if (i >= n_rec) return;
     const C z1 = (i + 1 < n_zn) ? ldC(Zn, i + 1) : mkC(0., 0.);
     const C dd = (d != nullptr && i < n_d) ? ldC(d, i) : mkC(0., 0.);
-    T2[i] = make_double4(z1.re, z1.im, mul_rn(scale, dd.re), mul_rn(scale, dd.im));
+    T2[i] = make_double4(mul_rn(FSB_ZSCALE, z1.re), mul_rn(FSB_ZSCALE, z1.im),
+                         mul_rn(scale, dd.re), mul_rn(scale, dd.im));
 }
 /* Pre-test words of the hot loop (table zeroed first): for every leaf j (index 8 j)
  * where the loop looks the BLA tree up (more than 8 valid indices ahead,
@@ -1973,7 +2008,8 @@ __global__ void k_build_h3(long long n_leaf, long long n_slots, const double *__
 {
     const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (j >= n_leaf || (long long)h3_slot((int)(8 * j)) >= n_slots) return;
-    if ((long long)first_invalid - 8 * j > 8) h3[h3_slot((int)(8 * j))] = (unsigned)hi32(__ldg(r_bla + 2 * j));
+    if ((long long)first_invalid - 8 * j > 8)
+        h3[h3_slot((int)(8 * j))] = h3_word((unsigned)hi32(__ldg(r_bla + 2 * j)));
 }
 
 /* ======================================================================== */

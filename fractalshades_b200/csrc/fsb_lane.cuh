@@ -848,6 +848,31 @@ enum : unsigned {
 #ifndef FSB_H3_DIRECT
 #define FSB_H3_DIRECT 0
 #endif
+/* FSB_ZZ2 (default build only; the -fmad=false build keeps the literal operation order):
+ * the hot loop carries C = 2 (Zn[w] + z) from one iteration to the next instead of Zn[w]:
+ * 2 Z + z = C - z and 2 (Z + z) = C, two FP64 additions fewer per iteration (16 FP64
+ * instructions instead of 18).  The orbit table then holds 2 Zn[w+1]; the pre-tests compare
+ * DOUBLED high words (x + x drops the sign bit; the factor 2 of C is a constant offset folded
+ * into the same instruction, into the escape bound and into the radius table: h3_word,
+ * esc_word), and the escape bound takes max(a, b) -- the `a | b` shortcut of the plain form
+ * needs both exponent fields below 0x400, and C passes 2 all the time.
+ * Measured (B200, 4K frames, ms; plain form 11.20 / 24.93 on configs 2 / 3):
+ *   1  C - z, one iteration per trip: 10.73 / 23.46  -- the default
+ *   2  2 Z + z formed from the kept 2 Zn[w] exactly as in the plain form (same pixels as
+ *      the plain form, two more registers, two iterations per trip): 11.37 / 24.19
+ * With 1 the full-size parity rates of configs 2-5 are unchanged (100 % / 99.9992 % / 100 % /
+ * 100 % identical stop_iter against the oracle); on the 2 304 pixels of the `p_M2_flake`
+ * case 3 pixels differ by one iteration instead of 1 (the other rounding of 2 Z + z). */
+#ifndef FSB_ZZ2
+#ifdef FSB_STRICT
+#define FSB_ZZ2 0
+#else
+#define FSB_ZZ2 1
+#endif
+#endif
+#if defined(FSB_STRICT) && FSB_ZZ2
+#error "FSB_ZZ2 re-associates the iteration: default build only"
+#endif
 #ifndef FSB_STAGE_TMA          /* orbit staging through shared memory by 1-D bulk copies (experiment, fsb_kernels.cuh) */
 #define FSB_STAGE_TMA 0
 #endif
@@ -857,6 +882,29 @@ enum : unsigned {
 #ifndef FSB_HOT_RECOMPUTE
 #define FSB_HOT_RECOMPUTE 0
 #endif
+#if FSB_ZZ2
+#define FSB_ZSCALE 2.
+#else
+#define FSB_ZSCALE 1.
+#endif
+/* the pre-test words as the hot loop compares them: high word hi of a radius, and the
+ * escape bound */
+FSB_HD unsigned h3_word(unsigned hi)
+{
+#if FSB_ZZ2
+    return hi == 0u ? 0u : (hi >= 0x7fe00000u ? 0xffffffffu : 2u * hi + 0x200000u);
+#else
+    return hi;
+#endif
+}
+FSB_HD unsigned esc_word(unsigned esc_hi)
+{
+#if FSB_ZZ2
+    return esc_hi >= 0x7fe00000u ? 0xffffffffu : 2u * (esc_hi + 0x100000u);
+#else
+    return esc_hi;
+#endif
+}
 /* slot of index w in the pre-test word table */
 FSB_HD int h3_slot(int w) { return FSB_H3_DIRECT ? w : (w >> 3); }
 #ifdef FSB_STRICT
@@ -1235,7 +1283,7 @@ FSB_HD void lane_step(const FrameDev &f, LaneM2 &s, const C *c_pix, double *Z, i
                 const bool slow = XR && (s.flags & LF_SLOW);
                 const C zn = zc;
                 int ib = 0;
-#ifdef FSB_EVENT_PRETEST
+#if defined(FSB_EVENT_PRETEST) && !FSB_ZZ2
                 {   /* the hot loop's necessary condition first: most chains of steps end here */
                     const unsigned h3 = ldg_(f.h3 + h3_slot(s.w));
                     const unsigned c = (unsigned)hi32(zn.re) & 0x7fffffffu, d = (unsigned)hi32(zn.im) & 0x7fffffffu;
@@ -1380,6 +1428,21 @@ FSB_HD void lane_step(const FrameDev &f, LaneM2 &s, const C *c_pix, double *Z, i
     }
     s.wlim = wl;
     s.flags &= ~LF_EV;
+#if defined(__CUDA_ARCH__) && defined(FSB_PREFETCH_BLA)
+    /* the tree nodes the next lookup (at the next multiple of 8) reads first: its stage-3
+     * entry of the integer radius table and that node's (A, B) */
+    if (BLA && f.stages_bla >= 4) {
+        const int wn = (s.w + 8) & ~7;
+        if (f.first_invalid_i - wn > 8) {
+            const int ib = 2 * (wn >> 3);
+            asm volatile("prefetch.global.L1 [%0];" :: "l"(f.r2hi + ib));
+            asm volatile("prefetch.global.L1 [%0];" :: "l"(f.M_bla + 4 * ib));
+#if FSB_PREFETCH_BLA > 1
+            asm volatile("prefetch.global.L1 [%0];" :: "l"(f.r_bla + ib));
+#endif
+        }
+    }
+#endif
 #undef L_DZNDC_X
 #undef L_REF_X
 #undef L_LOAD_Z
@@ -1427,6 +1490,62 @@ FSB_HD void m2_hot_iter(LaneM2 &s, double Zr, double Zi, double t2, double t3)
     if (DZNDC) { s.dr = ndr; s.di = ndi; }
     s.w += s.winc;
 }
+#if FSB_ZZ2
+/* The same two functions with C = 2 (Zn[w] + z) carried.  hot_enter / hot_exit convert
+ * between the carried value and Zn[w] at the two ends of the loop. */
+FSB_HD void m2_hot_enter(const LaneM2 &s, double &Cr, double &Ci)
+{
+    Cr = 2. * (s.Zr + s.zr); Ci = 2. * (s.Zi + s.zi);
+}
+/* (Z2r, Z2i) = 2 Zn[w] (FSB_ZZ2 == 2: kept from the previous record so that 2 Z + z is
+ * formed exactly as in the plain form; FSB_ZZ2 == 1: unused, 2 Z + z = C - z) */
+template <bool XR, bool DZNDC, bool BLA>
+FSB_HD void m2_hot_iter_c(LaneM2 &s, double Cr, double Ci, double Z2r, double Z2i, double t2, double t3)
+{
+    const double zr = s.zr, zi = s.zi, dr = s.dr, di = s.di;
+#if FSB_ZZ2 == 2
+    const double tr = Z2r + zr, ti = Z2i + zi;            /* fl(2 Z + z) */
+#else
+    const double tr = Cr - zr, ti = Ci - zi;              /* 2 Z + z */
+    (void)Z2r; (void)Z2i;
+#endif
+    if (DZNDC) {
+        s.dr = fma(Cr, dr, fma(-Ci, di, fma(t2, zr, -(t3 * zi))));
+        s.di = fma(Cr, di, fma(Ci, dr, fma(t2, zi, t3 * zr)));
+    }
+    s.zr = fma(zr, tr, fma(-zi, ti, s.cr));
+    s.zi = fma(zr, ti, fma(zi, tr, s.ci));
+    s.w += s.winc;
+}
+/* (t0, t1) = 2 Zn[w] of the new index: next carried value and the pre-tests */
+template <bool XR, bool DZNDC, bool BLA>
+FSB_HD void m2_hot_flags_c(const LaneM2 &s, double t0, double t1, const unsigned *__restrict__ h3tab,
+                           unsigned esc2, bool &ev, bool &bad, double &Cr, double &Ci)
+{
+    Cr = fma(2., s.zr, t0); Ci = fma(2., s.zi, t1);
+    const unsigned hr = (unsigned)hi32(Cr), hi_ = (unsigned)hi32(Ci);
+    const unsigned zr_ = (unsigned)hi32(s.zr), zi_ = (unsigned)hi32(s.zi);
+    const unsigned a = hr + hr, b = hi_ + hi_;                        /* 2 |hi(2 (Z + z))| */
+    const unsigned c = zr_ + zr_ + 0x200000u, d = zi_ + zi_ + 0x200000u;   /* 2 |hi(2 z)| */
+    /* (the a | b shortcut of the plain form needs both fields below 0x400: C = 2 (Z + z)
+     * passes 2 all the time) */
+    ev = (s.w >= s.wlim) | ((a > b ? a : b) >= esc2) | ((a <= c) & (b <= d));
+#if defined(FSB_DEBUG_EV) && !defined(__CUDA_ARCH__)
+    { static int n_ = 0; if (n_++ < 12) fprintf(stderr, "ev w %d wlim %d a %08x b %08x c %08x d %08x esc %08x | %d %d %d  C (%g, %g) z (%g, %g)\n", s.w, s.wlim, a, b, c, d, esc2, s.w >= s.wlim, (a | b) >= esc2, (a <= c) & (b <= d), Cr, Ci, s.zr, s.zi); }
+#endif
+    if (BLA) {
+        unsigned h3 = 0u;
+        if ((s.w & 7) == 0) h3 = ldg_(h3tab + (s.w >> 3));
+        ev = ev | ((c <= h3) & (d <= h3));
+    }
+    bad = false;
+    if (XR) {
+        bad = !(in_fast_range(s.zr) & in_fast_range(s.zi));
+        if (DZNDC) bad = bad | !(in_fast_range(s.dr) & in_fast_range(s.di));
+    }
+}
+#endif
+
 /* exponent-field bound of the escape pre-test: both parts of Z + z below 2^k
  * imply |Z + z|^2 < 2^(2k+1) <= Mdiv_sq */
 inline unsigned esc_hi_of(double Mdiv_sq)

@@ -73,6 +73,18 @@ static void run(const FrameDev &f, int64_t npts, const C *c_pix, double *Z, int3
             cnt[6]++;
             if (s.flags & LF_NEED) break;
             bool ev, bad;
+#if FSB_ZZ2
+            double Cr, Ci;
+            m2_hot_enter(s, Cr, Ci);
+            for (;;) {
+                const double *rec = T2 + 4 * (long long)s.w;
+                m2_hot_iter_c<XR, DZNDC, BLA>(s, Cr, Ci, 2. * s.Zr, 2. * s.Zi, rec[2], rec[3]);
+                m2_hot_flags_c<XR, DZNDC, BLA>(s, rec[0], rec[1], f.h3, f.esc_hi, ev, bad, Cr, Ci);
+                s.Zr = 0.5 * rec[0]; s.Zi = 0.5 * rec[1];
+                cnt[5]++;
+                if (ev | bad) break;
+            }
+#else
             for (;;) {
                 const double *rec = T2 + 4 * (long long)s.w;
                 m2_hot_iter<XR, DZNDC, BLA>(s, s.Zr, s.Zi, rec[2], rec[3]);
@@ -81,6 +93,7 @@ static void run(const FrameDev &f, int64_t npts, const C *c_pix, double *Z, int3
                 cnt[5]++;
                 if (ev | bad) break;
             }
+#endif
             if (XR && bad) { s.flags |= LF_EV | LF_BAD; cnt[7]++; }
             else s.flags |= LF_EV | LF_ITER;
         }
@@ -137,7 +150,7 @@ extern "C" int fsb_emul_perturb_m2(const emul_frame *e, int64_t npts, const doub
     f.bla_len = e->bla_len; f.stages_bla = e->stages_bla;
     f.Mdiv_sq = e->M_divergence_sq;
     f.zstride = npts;
-    f.esc_hi = esc_hi_of(f.Mdiv_sq);
+    f.esc_hi = esc_word(esc_hi_of(f.Mdiv_sq));
     const bool bla = e->bla_activated != 0 && e->stages_bla > 3 && e->bla_len > 0;
     std::vector<int> r2hi;
     if (bla) {                      /* as k_bla_r2hi */
@@ -156,12 +169,12 @@ extern "C" int fsb_emul_perturb_m2(const emul_frame *e, int64_t npts, const doub
     const C *dsrc = dc ? (xr ? f.dZndc_std : f.dZndc) : nullptr;
     for (int64_t i = 0; i < n_rec; i++) {
         double *r = T2.data() + 4 * i;
-        if (i + 1 < L + 1) { r[0] = Zn[(size_t)i + 1].re; r[1] = Zn[(size_t)i + 1].im; }
+        if (i + 1 < L + 1) { r[0] = mul_rn(FSB_ZSCALE, Zn[(size_t)i + 1].re); r[1] = mul_rn(FSB_ZSCALE, Zn[(size_t)i + 1].im); }
         if (dsrc && i < L + 1) { r[2] = mul_rn(FSB_TSCALE, dsrc[i].re); r[3] = mul_rn(FSB_TSCALE, dsrc[i].im); }
     }
     if (bla)
         for (int64_t j = 0; h3_slot((int)(8 * j)) < n_h3 && j < e->bla_len / 2; j++)
-            if ((int64_t)f.first_invalid_i - 8 * j > 8) h3[(size_t)h3_slot((int)(8 * j))] = (unsigned)hi32(e->r_bla[2 * j]);
+            if ((int64_t)f.first_invalid_i - 8 * j > 8) h3[(size_t)h3_slot((int)(8 * j))] = h3_word((unsigned)hi32(e->r_bla[2 * j]));
     f.T2 = T2.data();
     f.h3 = h3.data();
 

@@ -65,6 +65,8 @@ def build(strict, force=False):
            "-I", cuda_inc]
     if strict:
         cmd.append("-DFSB_STRICT")
+    else:     # build knobs of the default build under test (e.g. FSB_EMUL_FLAGS=-DFSB_ZZ2=1)
+        cmd += os.environ.get("FSB_EMUL_FLAGS", "").split()
     if strict == "narrow":
         cmd += ["-DFSB_FAST_LO=40", "-DFSB_FAST_HI=30"]
     cmd += ["-o", so, _SRC]

@@ -31,6 +31,10 @@ FAST_FLOOR = {n: 0.999 for n in ALL}
 FAST_FLOOR.update({
     "std_M2_seahorse_orbit": 0.99, "std_BS_f1": 0.99, "std_BS_f4": 0.99,
     "std_BS_f5": 0.99, "p_M2_shallow": 0.995, "p_M2_divref_orbit": 0.95,
+    # 2 304 pixels at 1.8e-157 on a dynamic-glitch view: the default build (2 Z + z formed as
+    # 2 (Z + z) - z, fsb_lane.cuh FSB_ZZ2) differs from the oracle by ONE iteration on 3 pixels
+    # (0.99870); the oracle itself equals the fastmath reference on all of them
+    "p_M2_flake": 0.998,
     "p_M2_ultradeep_xr": 0.8, "p_BS_f2_E12": 0.5, "p_BS_f5_E12": 0.6,
     "p_BS_f1_E12_nohess_nobla": 0.15,
     # same view with the periodic reference of the nucleus search: the reference's own
@@ -58,7 +62,11 @@ FAST_FLOOR.update({
 # fp64 resolution where that tail is large.
 NU_FLOOR = {n: 0.995 for n in ALL}
 NU_FLOOR.update({
-    "p_BS_f1_E12_nohess_nobla": 0.0, "p_BS_f1_E12_newton": 0.0, "p_BS_f2_E12": 0.8, "p_BS_f5_E12": 0.0,
+    "p_BS_f1_E12_nohess_nobla": 0.0, "p_BS_f1_E12_newton": 0.0, "p_BS_f2_E12": 0.8,
+    # dynamic-glitch view, the most ill-conditioned holomorphic case: 98.7 % with the default
+    # build's FSB_ZZ2 form of the iteration (99.8 % with the plain form; median relative
+    # error of Z 1.8e-12 against 1.4e-12) -- the full-size BASELINE configs are unchanged
+    "p_M2_flake": 0.98, "p_BS_f5_E12": 0.0,
     "p_M2_divref_orbit": 0.85, "p_M2_shallow": 0.95, "std_BS_f4": 0.99,
     "p_BS_f4_E12": 0.99, "p_BS_f5_E330_xr": 0.9,
     # 55-decade exponential maps: reference strict-vs-fastmath = 98.7 %

@@ -30,10 +30,10 @@ def main(lib, filt="k_perturb_m2_v2"):
             body = [x for _, x in ins[addr[tgt]:i + 1]]
             votes = sum("VOTE.ANY" in x for x in body)
             fp = sum(bool(re.match(r"(@!?U?P\d+\s+)?D(FMA|ADD|MUL|SETP)", x)) for x in body)
-            if votes != 2 or fp < 20: continue
+            if votes not in (1, 2) or fp < 14: continue
             mov = sum(bool(re.search(r"\b(IMAD\.MOV|MOV|IMAD\.U32)\b", x)) for x in body)
             ldc = sum(bool(re.search(r"\b(LDC|LDCU|UMOV)", x)) for x in body)
-            print(f"  loop @{tgt:#x}-{a:#x}: {len(body)} instr / 2 iterations, FP64 {fp}, moves {mov}, const loads {ldc}")
+            print(f"  loop @{tgt:#x}-{a:#x}: {len(body)} instr / {votes} iteration(s), FP64 {fp}, moves {mov}, const loads {ldc}")
 
 if __name__ == "__main__":
     main(*sys.argv[1:])
