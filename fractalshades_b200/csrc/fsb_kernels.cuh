@@ -929,7 +929,22 @@ k_perturb_m2_v2(const __grid_constant__ FrameDev f, long long npts_ll,
         bool ev, bad;
         double Cr, Ci;
         m2_hot_enter(s, Cr, Ci);
-#if FSB_ZZ2 == 1
+#if FSB_ZZ2 == 1 && FSB_V2_UNROLL == 2
+#define FSB_HOT_LOOP(MASK) do { \
+            double ra0, ra1, ra2, ra3; \
+            for (;;) { \
+                FSB_LD_REC(ra, s.w); \
+                m2_hot_iter_c<XR, DZNDC, BLA>(s, Cr, Ci, 0., 0., ra2, ra3); \
+                m2_hot_flags_c<XR, DZNDC, BLA>(s, ra0, ra1, h3tab, esc_hi, ev, bad, Cr, Ci); \
+                if (MASK) { ev = ev & alive; bad = bad & alive; } \
+                if (__any_sync(FULL, ev | bad)) { Zr = 0.5 * ra0; Zi = 0.5 * ra1; break; } \
+                FSB_LD_REC(ra, s.w); \
+                m2_hot_iter_c<XR, DZNDC, BLA>(s, Cr, Ci, 0., 0., ra2, ra3); \
+                m2_hot_flags_c<XR, DZNDC, BLA>(s, ra0, ra1, h3tab, esc_hi, ev, bad, Cr, Ci); \
+                if (MASK) { ev = ev & alive; bad = bad & alive; } \
+                if (__any_sync(FULL, ev | bad)) { Zr = 0.5 * ra0; Zi = 0.5 * ra1; break; } \
+            } } while (0)
+#elif FSB_ZZ2 == 1
 #define FSB_HOT_LOOP(MASK) do { \
             double ra0, ra1, ra2, ra3; \
             for (;;) { \

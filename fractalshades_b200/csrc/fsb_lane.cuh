@@ -860,6 +860,10 @@ enum : unsigned {
  *   1  C - z, one iteration per trip: 10.73 / 23.46  -- the default
  *   2  2 Z + z formed from the kept 2 Zn[w] exactly as in the plain form (same pixels as
  *      the plain form, two more registers, two iterations per trip): 11.37 / 24.19
+ *   1 with two iterations per trip (FSB_V2_UNROLL=2): 10.88 / 23.65; 1 with the w-indexed
+ *     pre-test table (FSB_H3_DIRECT=1): 11.53 / 24.37 (8 moves per trip), the two together:
+ *     10.99 / 24.36 (39 instructions per iteration against 42, and still slower: the extra
+ *     load per iteration costs more than the four instructions it saves)
  * With 1 the full-size parity rates of configs 2-5 are unchanged (100 % / 99.9992 % / 100 % /
  * 100 % identical stop_iter against the oracle); on the 2 304 pixels of the `p_M2_flake`
  * case 3 pixels differ by one iteration instead of 1 (the other rounding of 2 Z + z). */
@@ -1534,8 +1538,12 @@ FSB_HD void m2_hot_flags_c(const LaneM2 &s, double t0, double t1, const unsigned
     { static int n_ = 0; if (n_++ < 12) fprintf(stderr, "ev w %d wlim %d a %08x b %08x c %08x d %08x esc %08x | %d %d %d  C (%g, %g) z (%g, %g)\n", s.w, s.wlim, a, b, c, d, esc2, s.w >= s.wlim, (a | b) >= esc2, (a <= c) & (b <= d), Cr, Ci, s.zr, s.zi); }
 #endif
     if (BLA) {
+#if FSB_H3_DIRECT
+        const unsigned h3 = ldg_(h3tab + s.w);
+#else
         unsigned h3 = 0u;
         if ((s.w & 7) == 0) h3 = ldg_(h3tab + (s.w >> 3));
+#endif
         ev = ev | ((c <= h3) & (d <= h3));
     }
     bad = false;
