@@ -883,11 +883,28 @@ def tile_shape_arrays(tiles, npts):
 
 
 def _picklable(fp):
-    """ fingerprints may hold mpmath numbers / objects: store their repr """
+    """ fingerprints may hold mpmath numbers / objects: store a STABLE text for them.
+    A default `repr` carries the object's address and would never match on reload
+    (every run would silently recompute): objects are described by their class and
+    their primitive public attributes instead (a projection: its constructor
+    parameters; a subset array: the calculation and field it was built from). """
     def conv(v):
         if isinstance(v, dict):
             return {k: conv(x) for k, x in v.items()}
         if isinstance(v, (int, float, str, bool, type(None))):
             return v
-        return repr(v)
+        if isinstance(v, (list, tuple)):
+            return repr([conv(x) for x in v])
+        r = repr(v)
+        if " at 0x" not in r:
+            return r
+        attrs = {}
+        for k, x in sorted(getattr(v, "__dict__", {}).items()):
+            if k.startswith("_") or k == "fractal":
+                continue
+            if isinstance(x, (int, float, str, bool, type(None))):
+                attrs[k] = x
+            elif isinstance(x, (complex, np.generic)) or type(x).__module__.startswith("mpmath"):
+                attrs[k] = repr(x)
+        return f"{type(v).__module__}.{type(v).__qualname__}{attrs}"
     return conv(fp)

@@ -345,3 +345,17 @@ def test_seam_validates_caller_buffers():
         kw.update(bad)
         with pytest.raises(ValueError):
             check_outputs(n, kw["Z"], kw["U"], kw["sr"], kw["si"], 2, kw["c"])
+
+
+def test_fingerprint_of_objects_is_stable():
+    """ objects in a fingerprint (projection, ...) are described by class and parameters,
+    not by an address: the stored results of a previous run are found again """
+    from fractalshades_b200.core import _picklable
+    from fractalshades_b200 import projection as prj
+    a = _picklable({"zoom_kwargs": {"projection": prj.Expmap(0., 12.5, rotates_df=False), "nx": 64}})
+    b = _picklable({"zoom_kwargs": {"projection": prj.Expmap(0., 12.5, rotates_df=False), "nx": 64}})
+    c = _picklable({"zoom_kwargs": {"projection": prj.Expmap(0., 13.5, rotates_df=False), "nx": 64}})
+    assert a == b and a != c
+    assert " at 0x" not in a["zoom_kwargs"]["projection"]
+    assert _picklable({"p": prj.Cartesian()}) == _picklable({"p": prj.Cartesian()})
+    assert _picklable({"p": prj.Cartesian()}) != _picklable({"p": prj.Cartesian(expmap_seam=1.0)})
