@@ -1522,10 +1522,12 @@ int fsb_frame_create(const fsb_frame_desc *desc, fsb_frame **out)
     }
     if (f->v2 && f->bla_on) {
         int *t = nullptr;
-        if (dev_zeros(f, 2 * v.bla_len, &t)) { fsb_frame_destroy(f); return -1; }
-        k_bla_r2hi<<<(int)((v.bla_len + 255) / 256), 256>>>(v.bla_len, v.r_bla, t, t + v.bla_len);
+        if (dev_zeros(f, 3 * v.bla_len, &t)) { fsb_frame_destroy(f); return -1; }
+        k_bla_r2hi<<<(int)((v.bla_len + 255) / 256), 256>>>(v.bla_len, v.r_bla, t, t + v.bla_len,
+                                                           t + 2 * v.bla_len);
         v.r2hi = t;
         v.r2hi_up = t + v.bla_len;
+        v.rhi = t + 2 * v.bla_len;
     }
     if (f->v2) {
         const long long n_rec = L + 16 + FSB_STAGE_WIN /* a staged window may start at the last index */, n_h3 = FSB_H3_DIRECT ? n_rec : L / 8 + 4;

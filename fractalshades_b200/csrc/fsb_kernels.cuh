@@ -1991,13 +1991,14 @@ __global__ void k_flush_mirror(long long n, const double *__restrict__ m, const 
 
 /* integer radius tables of the square-free BLA lookup (bla_r2hi) */
 __global__ void k_bla_r2hi(long long n, const double *__restrict__ r, int *__restrict__ t1,
-                           int *__restrict__ t2)
+                           int *__restrict__ t2, int *__restrict__ t3)
 {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double v = r[i];
     t1[i] = bla_r2hi(v, 1.);
     t2[i] = bla_r2hi(v, 0x1p600);
+    t3[i] = bla_rhi(v);
 }
 
 /* Interleaved orbit table of k_perturb_m2_v2 (HBM-bound, once per frame):

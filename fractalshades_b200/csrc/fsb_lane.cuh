@@ -12,6 +12,14 @@
 #pragma once
 #include "fsb_math.cuh"
 
+/* FSB_BLA_LOOKUP4=1: radius tests of the BLA lookup decided on the larger component alone
+ * where that is conclusive (ref_bla_get4_).  Same decisions; measured slower (config 2 / 3:
+ * 10.91 / 24.69 ms against 10.75 / 23.52): one more table in the walk, and the square test it
+ * saves was not the expensive part.  Off. */
+#ifndef FSB_BLA_LOOKUP4
+#define FSB_BLA_LOOKUP4 0
+#endif
+
 namespace fsb {
 
 #ifdef __CUDA_ARCH__
@@ -80,6 +88,8 @@ struct FrameDev {
     unsigned esc_hi;
     /* high words of fl((r up)^2) per BLA node, up = 1 and 2^600 (bla_r2hi) */
     const int *r2hi, *r2hi_up;
+    /* high word of r per BLA node, 0 when |z| < r can never hold (bla_rhi) */
+    const int *rhi;
 };
 
 struct StdDev {
@@ -733,13 +743,24 @@ FSB_HD int bla_r2hi(double r, double up)
     return hi32(mul_rn(ru, ru));
 }
 
+/* high word of r for the component test of ref_bla_get4_ (0: never) */
+FSB_HD int bla_rhi(double r)
+{
+    if (!(r > 0.)) return 0;                 /* r <= 0 or NaN */
+    return hi32(r);                          /* +inf: above every finite |z| */
+}
+
 /* perturbation.py:2116-2170 with the lookup order of ref_bla_get (lowest
  * stored stage first) and the square-free comparison above, on the integer
  * tables.  The per-component pre-test `|re|, |im| < r3` of ref_bla_get is
  * implied by |z| < r3 and left out. */
 FSB_HD int ref_bla_get3_(const FrameDev &f, C zn, int w, int &index_out);
+FSB_HD int ref_bla_get4_(const FrameDev &f, C zn, int w, int &index_out);
 FSB_HD int ref_bla_get3(const FrameDev &f, C zn, int w, int &index_out)
 {
+#if FSB_BLA_LOOKUP4
+    return ref_bla_get4_(f, zn, w, index_out);
+#endif
 #if defined(FSB_DEBUG_BLA) && !defined(__CUDA_ARCH__)
     int i2 = -1, i3 = -1;
     const int s2 = ref_bla_get2(f.r_bla, f.stages_bla, zn, w, f.first_invalid_i, i2);
@@ -797,6 +818,60 @@ FSB_HD int ref_bla_get3_(const FrameDev &f, C zn, int w, int &index_out)
     return 8;
 }
 
+/* The same lookup deciding most radius tests on the larger component alone.
+ * With m = max(|re|, |im|):  m <= |z| <= sqrt(2) m, and the rounded hypot is never
+ * below its larger argument.  On sign-stripped high words (hm of m, hr of r):
+ *   hm > hr                 =>  m > r                  =>  not (|z| < r)
+ *   hm + 0xA0000 < hr       =>  1.4545 m < r           =>  |z| < r, rounded or not
+ * (adding 0xA0000 to a high word multiplies the value by at least 2 / 1.375 = 1.4545;
+ * sqrt(2) m (1 + a few ulp) stays below that).  What falls in between -- a band of
+ * ratio 1.45 -- takes the square test of ref_bla_get3_, its sum of squares formed once,
+ * on demand.  Same decisions, bit for bit; rhi[] is 0 where |z| < r can never hold. */
+FSB_HD int ref_bla_get4_(const FrameDev &f, C zn, int w, int &index_out)
+{
+    const int it = w >> 3;
+    const int invalid_step = f.first_invalid_i - w;
+    if (invalid_step <= 8 || f.stages_bla < 4) return 0;
+    const int base = 2 * it - 1;
+    const int hm = imax(hi32(zn.re) & 0x7fffffff, hi32(zn.im) & 0x7fffffff);
+    if (hm > 0x7fe00000 - 0xA0000) {          /* huge, inf or NaN: the exact walk */
+        int ib = 0;
+        const int step = ref_bla_get2_cold(f.r_bla, f.stages_bla, zn, w, f.first_invalid_i, &ib);
+        index_out = ib;
+        return step;
+    }
+    const int hm_pass = hm + 0xA0000;
+    /* the square test, prepared on first use */
+    int hs = -1;
+    const int *__restrict__ tab = f.r2hi;
+    auto square_lt = [&](int ib) -> bool {
+        if (hs < 0) {
+            const double a = fabs(zn.re), b = fabs(zn.im);
+            const bool tiny = imax(expfield(a), expfield(b)) < 1023 - 500;
+            tab = tiny ? f.r2hi_up : f.r2hi;
+            const double up = tiny ? 0x1p600 : 1.;
+            const double au = mul_rn(a, up), bu = mul_rn(b, up);
+            hs = imin(hi32(add_rn(mul_rn(au, au), mul_rn(bu, bu))) & 0x7fffffff, 0x7ff80000);
+        }
+        const int d = ldg_(tab + ib) - hs;
+        return d >= 2 || (d > -2 && abs_lt_exact(zn, ldg_(f.r_bla + ib)));
+    };
+    const int h3 = ldg_(f.rhi + base + 1);
+    if (hm > h3) return 0;
+    if (!(hm_pass < h3) && !square_lt(base + 1)) return 0;
+    int stages = f.stages_bla - 1;
+    if (it != 0) stages = imin(stages, 3 + (ffs_(it) - 1));
+    stages = imin(stages, 31 - clz_(invalid_step - 1));   /* largest stg with 2^stg < invalid_step */
+    for (int stg = stages; stg > 3; stg--) {
+        const int ib = base + (1 << (stg - 3));
+        const int hr = ldg_(f.rhi + ib);
+        if (hm > hr) continue;
+        if (hm_pass < hr || square_lt(ib)) { index_out = ib; return 1 << stg; }
+    }
+    index_out = base + 1;
+    return 8;
+}
+
 /* ======================================================================== */
 /* Lane state machine of the persistent holomorphic kernel (k_perturb_m2_v2).
  *
@@ -848,6 +923,7 @@ enum : unsigned {
 #ifndef FSB_H3_DIRECT
 #define FSB_H3_DIRECT 0
 #endif
+
 /* FSB_ZZ2 (default build only; the -fmad=false build keeps the literal operation order):
  * the hot loop carries C = 2 (Zn[w] + z) from one iteration to the next instead of Zn[w]:
  * 2 Z + z = C - z and 2 (Z + z) = C, two FP64 additions fewer per iteration (16 FP64

@@ -154,13 +154,15 @@ extern "C" int fsb_emul_perturb_m2(const emul_frame *e, int64_t npts, const doub
     const bool bla = e->bla_activated != 0 && e->stages_bla > 3 && e->bla_len > 0;
     std::vector<int> r2hi;
     if (bla) {                      /* as k_bla_r2hi */
-        r2hi.resize((size_t)(2 * e->bla_len));
+        r2hi.resize((size_t)(3 * e->bla_len));
         for (int64_t i = 0; i < e->bla_len; i++) {
             r2hi[(size_t)i] = bla_r2hi(e->r_bla[i], 1.);
             r2hi[(size_t)(e->bla_len + i)] = bla_r2hi(e->r_bla[i], 0x1p600);
+            r2hi[(size_t)(2 * e->bla_len + i)] = bla_rhi(e->r_bla[i]);
         }
         f.r2hi = r2hi.data();
         f.r2hi_up = r2hi.data() + e->bla_len;
+        f.rhi = r2hi.data() + 2 * e->bla_len;
     }
     /* interleaved orbit table and pre-test words, as k_build_t2 / k_build_h3 */
     const int64_t n_rec = L + 16, n_h3 = FSB_H3_DIRECT ? n_rec : L / 8 + 4;
