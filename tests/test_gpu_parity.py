@@ -24,6 +24,19 @@ from test_oracle_golden import FAST_FLOOR, NU_FLOOR, ALL, PERTURB
 
 pytestmark = pytest.mark.gpu
 
+# measured match rates of the default build, per case (not only ">= floor"):
+# gpurun_out/parity_rates_cases.json, committed copy profiles/parity_rates_cases_r2.json
+CASE_RATES = {}
+
+
+def _dump_case_rates():
+    import json
+    import os
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "parity_rates_cases.json"), "w") as fh:
+        json.dump(CASE_RATES, fh, indent=1, sort_keys=True)
+
 
 @pytest.fixture(scope="module")
 def oracle_results():
@@ -97,9 +110,15 @@ def test_default_build_tolerance(name, oracle_results):
     assert same_ref.mean() >= floor, same_ref.mean()
     kind = CASES[name]["kind"]
     M = float(CASES[name]["calc"]["M_divergence"])
-    for ref_Z, ref_n, msk in ((Zo, sio, same), (g["Z"], g["stop_iter"], same_ref)):
+    rec = {"points": int(si.size), "vs_oracle_stop_iter_and_reason": float(same.mean()),
+           "vs_fastmath_reference_stop_iter_and_reason": float(same_ref.mean()),
+           "floor": floor, "nu_floor": NU_FLOOR[name]}
+    for tag, ref_Z, ref_n, msk in (("oracle", Zo, sio, same), ("fastmath_reference", g["Z"], g["stop_iter"], same_ref)):
         frac = pc.nu_within(kind, M, Z, si, ref_Z, ref_n, msk & (sr[0] == 1))
+        rec["nu_within_1e-9_vs_" + tag] = frac
         assert frac is None or frac >= NU_FLOOR[name], frac
+    CASE_RATES[name] = rec
+    _dump_case_rates()
 
 
 @pytest.mark.parametrize("name", ["p_M2_E20", "p_M2_ultradeep_xr", "p_BS_f1_E500_xr",
