@@ -1058,7 +1058,6 @@ static int std_fill(const fsb_std_desc *d, StdDev &p, long long zstride)
     if (d->nexp != 0) {
         if (d->model != FSB_MODEL_M2) return fail(-3, "nexp is only defined for the Mandelbrot model");
         if (d->nexp < 2 || d->nexp > 32) return fail(-3, "exponent %d out of the supported range [2, 32]", d->nexp);
-        if (d->calc_orbit) return fail(-3, "calc_orbit is not supported for the power-N model");
     }
     p.nexp = d->nexp;
     p.center_re = d->center_re; p.center_im = d->center_im; p.dx = d->dx;
@@ -1366,7 +1365,6 @@ int fsb_frame_create(const fsb_frame_desc *desc, fsb_frame **out)
     if (desc->nexp != 0) {
         if (desc->model != FSB_MODEL_M2) return fail(-3, "nexp is only defined for the holomorphic model");
         if (desc->nexp < 2 || desc->nexp > 32) return fail(-3, "exponent %d out of the supported range [2, 32]", desc->nexp);
-        if (desc->calc_orbit) return fail(-3, "calc_orbit is not supported for the power-N model");
     }
     {
         ProjDev chk;

@@ -261,11 +261,14 @@ k_std_mn(StdDev p, long long npts, const C *__restrict__ c_pix,
         const long long i = ipt_;
         C c = c_from_pix(ldC(c_pix, i), p.lin_mat, p.dx, mkC(p.center_re, p.center_im));
         C zn = mkC(0., 0.), dzndz = zn, dzndc = zn, d2 = zn;
-        long long n_iter = 0;
+        long long n_iter = 0, div_shift = 0, orbit_i1 = 0, orbit_i2 = 0;
+        C orbit_zn1 = zn, orbit_zn2 = zn;
         int reason = -1;
         for (;;) {
             n_iter += 1;
-            if (n_iter >= p.max_iter) { reason = 0; break; }
+            int ret = 0;
+            if (n_iter >= p.max_iter) { reason = 0; ret = 1; }
+            else {
             C zn_m1, zn_m;
             if (p.calc_d2) {
                 const C zn_m2 = cpow_chain(zn, deg - 2);
@@ -282,14 +285,29 @@ k_std_mn(StdDev p, long long npts, const C *__restrict__ c_pix,
             zn = cadd_rn(zn_m, c);
             if (n_iter == 1) dzndz = mkC(1., 0.);
             n_exec++;
-            if (norm2_rn(zn) > p.Mdiv_sq) { reason = 1; break; }
-            if (norm2_rn(dzndz) < p.eps_sq) { reason = 2; break; }
+            if (norm2_rn(zn) > p.Mdiv_sq) { reason = 1; ret = 1; }
+            else if (norm2_rn(dzndz) < p.eps_sq) { reason = 2; ret = 1; }
+            }
+            if (p.calc_orbit) {
+                long long div = n_iter / p.backshift;
+                if (div > div_shift) {
+                    div_shift = div;
+                    orbit_i2 = orbit_i1; orbit_zn2 = orbit_zn1;
+                    orbit_i1 = n_iter; orbit_zn1 = zn;
+                }
+            }
+            if (ret) break;
         }
         long long row = 0;
         stC(Z, row++, p.zstride, i, zn);
         stC(Z, row++, p.zstride, i, dzndz);
         stC(Z, row++, p.zstride, i, dzndc);
         if (p.calc_d2) stC(Z, row++, p.zstride, i, d2);
+        if (p.calc_orbit) {       /* back-shift with zn_iterate = zn ** N + c (mandelbrot_Mn.py:13-17) */
+            C zo = orbit_zn2;
+            while (orbit_i2 < n_iter - p.backshift) { zo = cadd_rn(cpow_chain(zo, deg), c); orbit_i2 += 1; }
+            stC(Z, row++, p.zstride, i, zo);
+        }
         stop_reason[i] = (signed char)reason;
         stop_iter[i] = (int)n_iter;
         n_sum += (unsigned long long)n_iter;
@@ -771,7 +789,14 @@ k_perturb_m2(const __grid_constant__ FrameDev f, long long npts_ll,
         if (orbit) {
             C zo = orbit_zn2;
             C CC = c + ldC(Zn, 1);
-            while (orbit_i2 < n_iter - (int)f.backshift) { zo = zo * zo + CC; orbit_i2 += 1; }
+            while (orbit_i2 < n_iter - (int)f.backshift) {
+                if (POWN) {            /* zn_iterate = zn ** N + c: the power as a product chain */
+                    C pw = zo;
+                    for (int q = 1; q < f.nexp; q++) pw = pw * zo;
+                    zo = pw + CC;
+                } else zo = zo * zo + CC;
+                orbit_i2 += 1;
+            }
             stC(Z, row++, f.zstride, ipt, zo);
         }
         stop_reason[ipt] = (signed char)stop;

@@ -95,14 +95,15 @@ class Mandelbrot_N(Fractal):
                      M_divergence: float, epsilon_stationnary: float,
                      calc_d2zndc2: bool = False, calc_orbit: bool = False,
                      backshift: int = 0):
-        """ models/mandelbrot_Mn.py:63-145 """
-        if calc_orbit:
-            raise NotImplementedError(
-                "calc_orbit is not supported for Mandelbrot_N (the reference "
-                "back-shifts with the C library's polar-form complex power)")
+        """ models/mandelbrot_Mn.py:63-145.  calc_orbit: the reference back-shifts the
+        stored orbit point with `zn ** N` = the C library's polar-form complex power;
+        here the power is the same product chain as in the loop (a few ulp apart,
+        tolerance-tested against the reference's fixtures) """
         complex_codes = ["zn", "dzndz", "dzndc"]
         if calc_d2zndc2:
             complex_codes += ["d2zndc2"]
+        if calc_orbit:
+            complex_codes += ["zn_orbit"]
         int_codes = []
         stop_codes = ["max_iter", "divergence", "stationnary"]
 
@@ -111,14 +112,15 @@ class Mandelbrot_N(Fractal):
                 instance.codes = (complex_codes, int_codes, stop_codes)
                 instance.complex_type = np.complex128
                 instance.potential_M = M_divergence
-                instance.backshift = None
+                instance.backshift = backshift if calc_orbit else None
             return impl
 
         spec = KernelSpec(kind="std_M2", model=_native.FSB_MODEL_M2, flavor=0,
                           nexp=self.exponent, max_iter=max_iter,
                           M_divergence=M_divergence,
                           epsilon_stationnary=epsilon_stationnary,
-                          calc_d2zndc2=calc_d2zndc2, calc_orbit=False, backshift=0)
+                          calc_d2zndc2=calc_d2zndc2, calc_orbit=calc_orbit,
+                          backshift=backshift)
         return {"set_state": set_state, "initialize": lambda: spec,
                 "iterate": lambda: spec}
 
@@ -309,17 +311,16 @@ class Perturbation_mandelbrot_N(PerturbationFractal):
                      BLA_eps: float = 1e-6, interior_detect: bool = False,
                      calc_dzndc: bool = True, calc_orbit: bool = False,
                      backshift: int = 0):
-        """ models/mandelbrot_Mn.py:463-606 """
-        if calc_orbit:
-            # the reference back-shifts the stored orbit point with zn ** N,
-            # i.e. the C library's polar-form cpow: no bit-defined restatement
-            raise NotImplementedError(
-                "calc_orbit is not supported for Perturbation_mandelbrot_N")
+        """ models/mandelbrot_Mn.py:463-606.  calc_orbit: `zn ** N` of the back-shift is
+        a product chain here, the C library's polar-form power in the reference
+        (tolerance-tested against its fixtures) """
         complex_codes = ["zn"]
         if interior_detect:
             complex_codes += ["dzndz"]
         if calc_dzndc:
             complex_codes += ["dzndc"]
+        if calc_orbit:
+            complex_codes += ["zn_orbit"]
         int_codes = ["ref_cycle_iter"]
         stop_codes = ["max_iter", "divergence", "stationnary"]
         BLA_activated = ((BLA_eps is not None)
@@ -333,6 +334,7 @@ class Perturbation_mandelbrot_N(PerturbationFractal):
                 instance.codes = (complex_codes, int_codes, stop_codes)
                 instance.calc_dZndz = interior_detect
                 instance.calc_dZndc = calc_dzndc
+                instance.backshift = backshift if calc_orbit else None
             return impl
 
         spec = KernelSpec(kind="perturb_M2", nexp=nexp, max_iter=max_iter,
@@ -340,7 +342,7 @@ class Perturbation_mandelbrot_N(PerturbationFractal):
                           epsilon_stationnary=epsilon_stationnary,
                           BLA_eps=BLA_eps, bla_activated=BLA_activated,
                           calc_dzndc=calc_dzndc, calc_dzndz=interior_detect,
-                          calc_orbit=False, backshift=0)
+                          calc_orbit=calc_orbit, backshift=backshift)
         return {"set_state": set_state, "initialize": lambda: spec,
                 "iterate": lambda: spec}
 

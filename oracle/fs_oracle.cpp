@@ -408,16 +408,19 @@ static inline C c_pow_int(C a, int n, int use_cpow)
 }
 
 static void std_mn_pixel(int deg, int use_cpow, C c, int64_t max_iter, double Mdiv_sq,
-                         double epscv_sq, int calc_d2, double *Z, int64_t stride,
-                         int8_t *stop, int32_t *niter)
+                         double epscv_sq, int calc_d2, int calc_orbit, int64_t backshift,
+                         double *Z, int64_t stride, int8_t *stop, int32_t *niter)
 {
     C zn = mkC(0., 0.), dzndz = zn, dzndc = zn, d2 = zn;
     const double fdeg = (double)deg, fdeg_m1 = (double)(deg - 1);
-    int64_t n_iter = 0;
+    int64_t n_iter = 0, div_shift = 0, orbit_i1 = 0, orbit_i2 = 0;
+    C orbit_zn1 = zn, orbit_zn2 = zn;
     int8_t reason = -1;
     for (;;) {
         n_iter += 1;
-        if (n_iter >= max_iter) { reason = 0; break; }
+        int ret = 0;
+        if (n_iter >= max_iter) { reason = 0; ret = 1; }
+        else {
         C zn_m1, zn_m;
         if (calc_d2) {
             C zn_m2 = c_pow_int(zn, deg - 2, use_cpow);
@@ -432,14 +435,29 @@ static void std_mn_pixel(int deg, int use_cpow, C c, int64_t max_iter, double Md
         dzndz = (fdeg * dzndz) * zn_m1;
         zn = zn_m + c;
         if (n_iter == 1) dzndz = mkC(1., 0.);
-        if (zn.re * zn.re + zn.im * zn.im > Mdiv_sq) { reason = 1; break; }
-        if (dzndz.re * dzndz.re + dzndz.im * dzndz.im < epscv_sq) { reason = 2; break; }
+        if (zn.re * zn.re + zn.im * zn.im > Mdiv_sq) { reason = 1; ret = 1; }
+        else if (dzndz.re * dzndz.re + dzndz.im * dzndz.im < epscv_sq) { reason = 2; ret = 1; }
+        }
+        if (calc_orbit) {                       /* core.py:3034-3046 */
+            int64_t div = n_iter / backshift;
+            if (div > div_shift) {
+                div_shift = div;
+                orbit_i2 = orbit_i1; orbit_zn2 = orbit_zn1;
+                orbit_i1 = n_iter; orbit_zn1 = zn;
+            }
+        }
+        if (ret) break;
     }
     int row = 0;
     Z[2 * stride * row] = zn.re; Z[2 * stride * row + 1] = zn.im; row++;
     Z[2 * stride * row] = dzndz.re; Z[2 * stride * row + 1] = dzndz.im; row++;
     Z[2 * stride * row] = dzndc.re; Z[2 * stride * row + 1] = dzndc.im; row++;
     if (calc_d2) { Z[2 * stride * row] = d2.re; Z[2 * stride * row + 1] = d2.im; row++; }
+    if (calc_orbit) {       /* back-shift with zn_iterate = zn ** N + c (mandelbrot_Mn.py:13-17) */
+        C zo = orbit_zn2;
+        while (orbit_i2 < n_iter - backshift) { zo = c_pow_int(zo, deg, use_cpow) + c; orbit_i2 += 1; }
+        Z[2 * stride * row] = zo.re; Z[2 * stride * row + 1] = zo.im; row++;
+    }
     *stop = reason;
     *niter = (int32_t)n_iter;
 }
@@ -886,7 +904,12 @@ static void perturb_m2_pixel(const fso_frame_m2 *f, C pix, double *Z,
     if (f->calc_orbit) {
         C zo = orbit_zn2;
         C CC = c + path_c(f->Zn_path, 1);
-        while (orbit_i2 < n_iter - f->backshift) { zo = m2_iterate(zo, CC); orbit_i2 += 1; }
+        while (orbit_i2 < n_iter - f->backshift) {
+            /* zn_iterate: zn * zn + c, or zn ** N + c for Perturbation_mandelbrot_N
+             * (polar form when f->use_cpow, as the reference runs it) */
+            zo = (f->nexp > 2) ? c_pow_int(zo, f->nexp, f->use_cpow) + CC : m2_iterate(zo, CC);
+            orbit_i2 += 1;
+        }
         Z[2 * stride * row] = zo.re; Z[2 * stride * row + 1] = zo.im; row++;
     }
     *stop_out = stop;
@@ -1386,16 +1409,16 @@ int fso_std_m2(int64_t npts, const double *c_pix, double center_re,
 int fso_std_mn(int nexp, int use_cpow, int64_t npts, const double *c_pix, double center_re,
                double center_im, double dx, const double *lin_mat,
                int64_t max_iter, double Mdiv_sq, double epscv_sq,
-               int calc_d2zndc2, double *Z, int8_t *stop_reason, int32_t *stop_iter,
-               int nthreads)
+               int calc_d2zndc2, int calc_orbit, int64_t backshift, double *Z,
+               int8_t *stop_reason, int32_t *stop_iter, int nthreads)
 {
     C center = mkC(center_re, center_im);
     int nt = resolve_threads(nthreads);
 #pragma omp parallel for schedule(dynamic, 64) num_threads(nt)
     for (int64_t i = 0; i < npts; i++) {
         C c = c_from_pix(path_c(c_pix, i), lin_mat, dx, center);
-        std_mn_pixel(nexp, use_cpow, c, max_iter, Mdiv_sq, epscv_sq, calc_d2zndc2,
-                     Z + 2 * i, npts, stop_reason + i, stop_iter + i);
+        std_mn_pixel(nexp, use_cpow, c, max_iter, Mdiv_sq, epscv_sq, calc_d2zndc2, calc_orbit,
+                     backshift, Z + 2 * i, npts, stop_reason + i, stop_iter + i);
     }
     return 0;
 }

@@ -264,6 +264,12 @@ CASES["p_M3_E20_newton"] = dict(
     y=_MN_PTS[3][1], dx="3.e-20", nx=64, xy_ratio=1.25, theta_deg=25., newton=True,
     calc=dict(max_iter=20000, BLA_eps=1e-6, interior_detect=False,
               calc_dzndc=True, **_STD))
+# calc_orbit for z^N + c: the back-shift runs zn_iterate = zn ** N + c
+CASES["p_M3_E20_orbit"] = dict(
+    kind="perturb_M2", init=dict(exponent=3), precision=40, x=_MN_PTS[3][0],
+    y=_MN_PTS[3][1], dx="3.e-20", nx=48, xy_ratio=1.25, theta_deg=25.,
+    calc=dict(max_iter=20000, BLA_eps=1e-6, interior_detect=False,
+              calc_dzndc=True, calc_orbit=True, backshift=3, **_STD))
 CASES["p_M4_E18_interior"] = dict(
     kind="perturb_M2", init=dict(exponent=4), precision=40, x=_MN_PTS[4][0],
     y=_MN_PTS[4][1], dx="2.e-18", nx=48,
@@ -305,6 +311,10 @@ CASES["std_M6_d2"] = dict(     # examples/interactive_standard/S03: exponent 6
     theta_deg=15.,
     calc=dict(max_iter=2000, M_divergence=1000., epsilon_stationnary=1e-3,
               calc_d2zndc2=True))
+CASES["std_M3_orbit"] = dict(  # calc_orbit: back-shift with zn ** 3 + c
+    kind="std_M2", init=dict(exponent=3), x=0.1, y=0.05, dx=2.5, nx=48, theta_deg=10.,
+    calc=dict(max_iter=2000, M_divergence=1000., epsilon_stationnary=1e-3,
+              calc_orbit=True, backshift=3))
 CASES["std_M4_zoom"] = dict(
     kind="std_M2", init=dict(exponent=4), x=-0.6548, y=0.4686, dx=2e-3, nx=64,
     calc=dict(max_iter=3000, M_divergence=1000., epsilon_stationnary=1e-3))

@@ -37,7 +37,7 @@ class FrameM2(ctypes.Structure):
         ("bla_activated", c_i32), ("calc_dzndc", c_i32), ("calc_dzndz", c_i32),
         ("calc_orbit", c_i32), ("backshift", c_i64), ("max_iter", c_i64),
         ("M_divergence_sq", c_dbl), ("epsilon_stationnary_sq", c_dbl),
-        ("nexp", c_i32), ("_pad", c_i32),
+        ("nexp", c_i32), ("use_cpow", c_i32),
     ]
 
 
@@ -120,18 +120,20 @@ def std_m2(c_pix, center, dx, lin_mat, max_iter, M_divergence,
 
 
 def std_mn(nexp, c_pix, center, dx, lin_mat, max_iter, M_divergence,
-           epsilon_stationnary, calc_d2zndc2=False, use_cpow=True, nthreads=0):
+           epsilon_stationnary, calc_d2zndc2=False, calc_orbit=False, backshift=0,
+           use_cpow=True, nthreads=0):
     """ Mandelbrot_N; use_cpow: see fs_oracle.h """
     c_pix = _c128(c_pix)
     n = c_pix.shape[0]
-    Z = np.zeros((3 + int(calc_d2zndc2), n), np.complex128)
+    Z = np.zeros((3 + int(calc_d2zndc2) + int(calc_orbit), n), np.complex128)
     sr = np.full((1, n), -1, np.int8)
     si = np.zeros((1, n), np.int32)
     lm = _f64(lin_mat).ravel()
     lib().fso_std_mn(int(nexp), int(bool(use_cpow)), c_i64(n), c_vp(_p(c_pix)),
                      c_dbl(center.real), c_dbl(center.imag), c_dbl(dx), c_vp(_p(lm)),
                      c_i64(max_iter), c_dbl(M_divergence ** 2),
-                     c_dbl(epsilon_stationnary ** 2), int(calc_d2zndc2), c_vp(_p(Z)),
+                     c_dbl(epsilon_stationnary ** 2), int(calc_d2zndc2), int(calc_orbit),
+                     c_i64(backshift), c_vp(_p(Z)),
                      c_vp(_p(sr)), c_vp(_p(si)), int(nthreads))
     return Z, np.zeros((0, n), np.int32), sr, si
 
@@ -187,6 +189,7 @@ def _frame_m2(t, keep):
     f.M_divergence_sq = float(t["M_divergence"]) ** 2
     f.epsilon_stationnary_sq = float(t.get("epsilon_stationnary", 0.)) ** 2
     f.nexp = int(t.get("nexp", 0) or 0)       # Perturbation_mandelbrot_N
+    f.use_cpow = int(bool(t.get("use_cpow", False)))
     return f
 
 
@@ -271,7 +274,9 @@ def perturb(t, c_pix, nthreads=0, det=False):
     pj = t.get("proj")
     pix = project(pj, c_pix, det)
     if t["kind"] == "perturb_M2":
-        out = perturb_m2(t, pix, nthreads)
+        # power N with calc_orbit: zn ** N as the reference runs it (C library) or as the
+        # CUDA library defines it (product chain), like the projections
+        out = perturb_m2(dict(t, use_cpow=not det), pix, nthreads)
     else:
         out = perturb_bs(t, pix, nthreads)
     apply_modifier(t, out[0], modifier(pj, c_pix, det))
