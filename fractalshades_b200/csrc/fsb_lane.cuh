@@ -994,7 +994,9 @@ FSB_HD int h3_slot(int w) { return FSB_H3_DIRECT ? w : (w >> 3); }
 #endif
 /* Xrange frames: the hot loop returns to the event section at least this often
  * (bounds the replay after a failed range guard) */
-#define FSB_XR_STRETCH 64
+#ifndef FSB_XR_STRETCH
+#define FSB_XR_STRETCH 128   /* measured on config 3: 32 / 64 / 128 / 256 -> 24.16 / 23.50 / 23.08 / 23.33 ms */
+#endif
 
 /* Rare paths of the event section.  Measured: making them real calls on the
  * device (__noinline__, the lane passed through a copy) puts the lane in local
