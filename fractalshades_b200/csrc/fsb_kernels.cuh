@@ -1231,8 +1231,13 @@ k_perturb_bs(const __grid_constant__ FrameDev f, long long npts_ll,
         for (;;) {
             if (BLA && (w_iter & 7) == 0) {
                 int ib = 0;
+#ifdef FSB_BS_LOOKUP2   /* square-free comparison: same decisions; measured 22.45 ms against 22.23 on config 4 */
+                const int step = ref_bla_get2(f.r_bla, f.stages_bla, mkC(x, y), w_iter,
+                                              first_invalid, ib);
+#else
                 const int step = ref_bla_get(f.r_bla, f.stages_bla, mkC(x, y), w_iter,
                                              first_invalid, ib);
+#endif
                 if (step != 0) {
                     double M[8];
                     const double2 *Mp = reinterpret_cast<const double2 *>(f.M_bla + 8 * (long long)ib);
