@@ -145,11 +145,33 @@ class Db_writer:
     def _render(self, tiles):
         """ fields of the listed tiles: dict name -> 1-D tile-ordered array """
         f = self.fractal
-        out, stats = fpp.frame_fields(f, self.calc_name, fields=self.fields,
-                                      floor_iter=self.floor_iter, px_snap=self.px_snap,
-                                      dtype=self.post_dtype, tiles=tiles, copy=False,
-                                      fieldlines=self.fieldlines)
-        self.last_stats.append(stats)
+        indep = f._calc_data[self.calc_name]["cycle_indep_args"]
+        if indep[0] == "perturb":
+            out, stats = fpp.frame_fields(f, self.calc_name, fields=self.fields,
+                                          floor_iter=self.floor_iter, px_snap=self.px_snap,
+                                          dtype=self.post_dtype, tiles=tiles, copy=False,
+                                          fieldlines=self.fieldlines)
+            self.last_stats.append(stats)
+            return out
+        # standard (double-precision) models: the raw seam with per-tile axes, then the
+        # stand-alone post-processing call on the raw rows
+        from .core import TileAxes
+        state = f._calc_data[self.calc_name]["state"]
+        axes = TileAxes(f, tiles)
+        n_Z = len(state.codes[0])
+        Z = np.zeros((n_Z, axes.npts), state.complex_type)
+        U = np.zeros((len(state.codes[1]), axes.npts), np.int32)
+        sr = -np.ones((1, axes.npts), np.int8)
+        si = np.zeros((1, axes.npts), np.int32)
+        rc = f.numba_cycle_call((axes, Z, U, sr, si), indep)
+        if rc != 0:
+            raise RuntimeError("frame interrupted")
+        self.last_stats.append(dict(type(f)._last_stats or {}))
+        c_pix = np.concatenate([np.ravel(f.chunk_pixel_pos(cs, False, None)) for cs in tiles])
+        out = fpp.fields_from_raw(f, self.calc_name, Z, si, fields=self.fields,
+                                  floor_iter=self.floor_iter, px_snap=self.px_snap,
+                                  dtype=self.post_dtype, c_pix=c_pix, fieldlines=self.fieldlines)
+        out["stop_reason"] = sr[0]
         return out
 
     def _push(self, mm, status, tiles, out, layer):
@@ -230,9 +252,10 @@ class Db_writer:
             shape, dtype = (len(self.postnames),) + self.db_shape, self.post_dtype
         mm, status = self._open_db(path, shape, dtype, recovery_mode)
         self.last_stats = []
-        if isinstance(f.projection, _projection.Expmap):
-            if not hasattr(f, "reset_bla_tree"):
-                raise NotImplementedError("stepped exponential maps: perturbation fractals only")
+        if isinstance(f.projection, _projection.Expmap) and hasattr(f, "reset_bla_tree"):
+            # (the reference steps every Expmap; its stepping only re-derives the BLA tree
+            # and the derivative scale of a perturbation frame -- a standard model has
+            # neither, and one pass gives the same arrays)
             self.n_steps = self._save_expdb_by_steps(mm, status, postdb_layer)
         else:
             self._run(mm, status, postdb_layer)

@@ -168,3 +168,33 @@ def test_projection_df_kinds():
     assert fpp.projection_df(e2)[0] == 3
     e2.set_exp_zoom_step(4., 2.)
     assert fpp.projection_df(e2)[0] == 0
+
+
+@pytest.mark.gpu
+def test_db_of_a_standard_model(chunk_guard):
+    """ double-precision models go through the raw seam + the stand-alone post-processing """
+    f = _fractal("std_M2_seahorse_orbit", 32)
+    from fractalshades_b200 import postproc as fpp
+    w = fdb.Db_writer(f, "c", fields=("cont_iter", "DEM", "normal"),
+                      fieldlines=fpp.Fieldlines_pp(n_iter=3))
+    path = w.save_db(relpath="std.db")
+    got = np.array(open_memmap(path, mode="r"))
+    assert got.shape == (5, f.ny, f.nx) and w.postnames[-1] == "fieldlines"
+    # same fields as the reference's post-processing of the same case (pp fixture)
+    g = np.load(os.path.join(pc.GOLDEN, "pp_std_M2_seahorse_orbit.npz"))
+    assert f.chunks_count > 1 and w.n_steps == 1
+    settings.chunk_size = 200                    # the fixture's tiling: one tile
+    f1, _ = pc.make_fractal("std_M2_seahorse_orbit")
+    assert f1.chunks_count == 1
+    esc = fpp.to_image(f1, np.asarray(g["stop_reason"])[0]) == 1
+    ref = fpp.to_image(f1, np.asarray(g["cont_iter"], np.float32))
+    # (another tiling: the pixel abscissas of a tile are its own linspace, a last-bit
+    # difference that the boundary pixels of this seahorse view amplify: 99.8 %)
+    same = got[0][esc] == ref[esc]
+    assert np.mean(same) > 0.995
+    ref_dem = fpp.to_image(f1, np.asarray(g["DEM"], np.float64))
+    rel = np.abs(got[1][esc][same] - ref_dem[esc][same]) / np.abs(ref_dem[esc][same])
+    assert np.mean(rel < 1e-4) > 0.99, (np.mean(rel < 1e-4), np.nanmax(rel))
+    ref_fl = fpp.to_image(f1, np.asarray(g["fieldlines"], np.float64))
+    # (the fixture's field lines use other parameters: only the shapes are comparable)
+    assert np.isfinite(got[4][esc]).all() and ref_fl.shape == got[4].shape
