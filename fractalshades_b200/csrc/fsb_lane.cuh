@@ -12,6 +12,14 @@
 #pragma once
 #include "fsb_math.cuh"
 
+/* FSB_XF_FUSED_DOT=1: burning-ship Xrange BLA step, dot products with ONE alignment
+ * (xf_dot2 / xf_dot4).  Bit-exact (strict build against the oracle, full-size config 4 tiles)
+ * and half the instructions of the chain on paper -- but the chain has to stay as the guarded
+ * fallback, and this kernel is bound by instruction fetch: 23.5 ms inlined, 25.4 ms with the
+ * fallback out of line (more spills), against 22.3 ms.  Off. */
+#ifndef FSB_XF_FUSED_DOT
+#define FSB_XF_FUSED_DOT 0
+#endif
 /* FSB_BLA_LOOKUP4=1: radius tests of the BLA lookup decided on the larger component alone
  * where that is conclusive (ref_bla_get4_).  Same decisions; measured slower (config 2 / 3:
  * 10.91 / 24.69 ms against 10.75 / 23.52): one more table in the walk, and the square test it
@@ -559,14 +567,66 @@ FSB_HD XF xf_sum(XF s, XF p)
     const int e = imax(se, p.e);
     return mkXF(xshift(s.m, se - e) + xshift(p.m, p.e - e), e);
 }
-FSB_HD XF xf_dot2(double m0, XF u, double m1, XF v)
+#if defined(__CUDA_ARCH__) && FSB_XF_FUSED_DOT
+#define FSB_CHAIN_FN static __device__ __noinline__      /* the rare fallback stays out of line */
+#else
+#define FSB_CHAIN_FN FSB_HD
+#endif
+FSB_CHAIN_FN XF xf_dot2_chain(double m0, XF u, double m1, XF v)
 {
     return xf_sum(xf_prod(m0, u), xf_prod(m1, v));
+}
+FSB_CHAIN_FN XF xf_dot4_chain(double m0, XF u, double m1, XF v, double m2, XF a,
+                                      double m3, XF b)
+{
+    return xf_sum(xf_sum(xf_dot2_chain(m0, u, m1, v), xf_prod(m2, a)), xf_prod(m3, b));
+}
+/* The same sums with ONE alignment: every product is scaled to the largest exponent of
+ * the lot and the additions run left to right on the scaled mantissas.  A scaling by a
+ * power of two is exact and commutes with rounding, so each partial sum is the chain's
+ * partial sum at another scale -- bit for bit -- as long as no scaled term leaves the
+ * normal range: guarded (exponents within 900 of the largest, no zero / denormal /
+ * non-finite product field), the chain otherwise.  An Xrange value does not depend on its
+ * mantissa / exponent split (when leading terms cancel exactly the split differs from the
+ * chain's, the value does not).  One shift per term instead of up to three. */
+FSB_HD double xf_scaled(double p, int f, int shift)      /* p 2^shift, field stays in [1, 2046] */
+{
+    (void)f;
+    return mk64(hi32(p) + (shift << 20), lo32(p));
+}
+FSB_HD XF xf_dot2(double m0, XF u, double m1, XF v)
+{
+#if FSB_XF_FUSED_DOT
+    const double p0 = m0 * u.m, p1 = m1 * v.m;
+    const int f0 = expfield(p0), f1 = expfield(p1);
+    const int E0 = u.e + f0, E1 = v.e + f1;
+    const int Emax = imax(E0, E1), Emin = imin(E0, E1);
+    if ((unsigned)(f0 - 1) < 2046u && (unsigned)(f1 - 1) < 2046u && Emax - Emin <= 900) {
+        const double t0 = xf_scaled(p0, f0, (1023 - f0) - (Emax - E0));
+        const double t1 = xf_scaled(p1, f1, (1023 - f1) - (Emax - E1));
+        return mkXF(t0 + t1, Emax - 1023);
+    }
+#endif
+    return xf_dot2_chain(m0, u, m1, v);
 }
 FSB_HD XF xf_dot4(double m0, XF u, double m1, XF v, double m2, XF a,
                                       double m3, XF b)
 {
-    return xf_sum(xf_sum(xf_dot2(m0, u, m1, v), xf_prod(m2, a)), xf_prod(m3, b));
+#if FSB_XF_FUSED_DOT
+    const double p0 = m0 * u.m, p1 = m1 * v.m, p2 = m2 * a.m, p3 = m3 * b.m;
+    const int f0 = expfield(p0), f1 = expfield(p1), f2 = expfield(p2), f3 = expfield(p3);
+    const int E0 = u.e + f0, E1 = v.e + f1, E2 = a.e + f2, E3 = b.e + f3;
+    const int Emax = imax(imax(E0, E1), imax(E2, E3)), Emin = imin(imin(E0, E1), imin(E2, E3));
+    if ((unsigned)(f0 - 1) < 2046u && (unsigned)(f1 - 1) < 2046u && (unsigned)(f2 - 1) < 2046u
+        && (unsigned)(f3 - 1) < 2046u && Emax - Emin <= 900) {
+        const double t0 = xf_scaled(p0, f0, (1023 - f0) - (Emax - E0));
+        const double t1 = xf_scaled(p1, f1, (1023 - f1) - (Emax - E1));
+        const double t2 = xf_scaled(p2, f2, (1023 - f2) - (Emax - E2));
+        const double t3 = xf_scaled(p3, f3, (1023 - f3) - (Emax - E3));
+        return mkXF(((t0 + t1) + t2) + t3, Emax - 1023);
+    }
+#endif
+    return xf_dot4_chain(m0, u, m1, v, m2, a, m3, b);
 }
 FSB_HD XF xf_clean(XF x)      /* zero results carry exponent 0 */
 {
