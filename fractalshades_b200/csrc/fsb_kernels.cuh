@@ -946,6 +946,7 @@ k_perturb_m2_v2(const __grid_constant__ FrameDev f, long long npts_ll,
          * is Zn[w] of the next iteration without a move.  Parked lanes run along on
          * zeros (winc = 0); a second copy of the loop masks their pre-tests. */
         const bool alive = (s.flags & (LF_DEAD | LF_NEED)) == 0;
+        for (;;) {                               /* hot loop, short trips, hot loop ... */
         double Zr = s.Zr, Zi = s.Zi;
 #define FSB_LD_REC(R, idx) do { const double4 *rec_ = T2 + (long long)(idx); \
             asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" \
@@ -1085,9 +1086,23 @@ k_perturb_m2_v2(const __grid_constant__ FrameDev f, long long npts_ll,
 #endif
 #undef FSB_HOT_LOOP
 #undef FSB_LD_REC
+        s.Zr = Zr; s.Zi = Zi;                    /* Zn[w] for the event section */
+#if FSB_SHORT_TRIP
+        if (BLA) {
+            const bool mine = ev && !bad && m2_trip_is_short<XR>(f, s, Zr, Zi);
+            if (!__any_sync(FULL, (ev | bad) && !mine)) {
+                bool ok = true;
+                if (mine) ok = lane_bla_short<XR, DZNDC>(f, s, k);
+                if (!ok) s.flags |= LF_EV;       /* lane_step, at its BLA loop */
+                if (!__any_sync(FULL, !ok)) continue;
+                break;
+            }
+        }
+#endif
         if (XR && bad) s.flags |= LF_EV | LF_BAD;
         else if (ev) s.flags |= LF_EV | LF_ITER;
-        s.Zr = Zr; s.Zi = Zi;                    /* Zn[w] for the event section */
+        break;
+        }
     }
     __syncthreads();
     if (threadIdx.x < 5) {

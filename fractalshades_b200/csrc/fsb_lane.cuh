@@ -983,6 +983,14 @@ enum : unsigned {
 #ifndef FSB_H3_DIRECT
 #define FSB_H3_DIRECT 0
 #endif
+/* FSB_SHORT_TRIP=1: events that are only a BLA pre-test (three visits of lane_step in four)
+ * handled next to the hot loop (lane_bla_short): same pixels and counters, 63 % fewer visits of
+ * lane_step -- and slower (config 2 / 3: 10.88 / 23.64 ms against 10.73 / 23.10): the flag and
+ * arming traffic it avoids is not what an event costs, the lookup and the step are, and a
+ * second inlined copy of them is more code.  Off. */
+#ifndef FSB_SHORT_TRIP
+#define FSB_SHORT_TRIP 0
+#endif
 
 /* FSB_ZZ2 (default build only; the -fmad=false build keeps the literal operation order):
  * the hot loop carries C = 2 (Zn[w] + z) from one iteration to the next instead of Zn[w]:
@@ -1691,6 +1699,60 @@ FSB_HD void m2_hot_flags_c(const LaneM2 &s, double t0, double t1, const unsigned
     }
 }
 #endif
+
+/* ---- the short trip ----------------------------------------------------------
+ * Three event visits in four are a lane at a multiple of 8 whose BLA pre-test fired
+ * and nothing else: no stop test can fire (checked here with the exact tests of the
+ * iteration just done, not their pre-tests), the lane is on the fp64 lane.  Those
+ * lanes take their BLA steps right here -- lookup, (A, B), `A z [+ B c]`, guard -- and go
+ * back to the hot loop without the flag / arming / cold-state traffic of lane_step.
+ * Anything else (another test true, a guard that fails, a pixel whose c is not tiny in
+ * an Xrange frame) leaves the lane to lane_step, state untouched or consistent at a
+ * multiple of 8 (`false`: the caller sets LF_EV without LF_ITER -- the tests of the
+ * iteration are known to be false -- and lane_step resumes at its BLA loop). */
+template <bool XR>
+FSB_HD bool m2_trip_is_short(const FrameDev &f, const LaneM2 &s, double Zr, double Zi)
+{
+    const double ZZr = s.zr + Zr, ZZi = s.zi + Zi;
+    const bool stop = (s.w >= s.wlim) | (ZZr * ZZr + ZZi * ZZi > f.Mdiv_sq);
+    const bool dyn = (fabs(ZZr) <= fabs(s.zr)) & (fabs(ZZi) <= fabs(s.zi));
+    return !(stop | dyn);
+}
+template <bool XR, bool DZNDC>
+FSB_HD bool lane_bla_short(const FrameDev &f, LaneM2 &s, LaneCold &k)
+{
+    if (XR && !k.c_tiny) return false;
+    while ((s.w & 7) == 0) {
+        const C zn = mkC(s.zr, s.zi);
+        int ib = 0;
+        const int step = ref_bla_get3(f, zn, s.w, ib);
+        if (step == 0) break;
+        const C *M = reinterpret_cast<const C *>(f.M_bla);
+        const C A = ldC(M, 2 * ib), B = ldC(M, 2 * ib + 1);
+        C nz, nd = mkC(s.dr, s.di);
+        if (!XR) {
+            nz = A * zn + B * mkC(s.cr, s.ci);
+            if (DZNDC) nd = A * nd;
+        } else {
+            nz = A * zn;                       /* B c is below half an ulp: see lane_step */
+            if (DZNDC) nd = A * nd;
+            if (!(in_fast_range(nz) & (!DZNDC || in_fast_range(nd))
+                  & (imax(expfield(B.re), expfield(B.im)) != 0x7ff))) return false;
+        }
+        s.zr = nz.re; s.zi = nz.im;
+        if (DZNDC) { s.dr = nd.re; s.di = nd.im; }
+        k.p_skip += (unsigned)step;
+        k.p_bla++;
+        s.w += step;
+        const C Zw = ldC(f.Zn, s.w);
+        s.Zr = Zw.re; s.Zi = Zw.im;
+    }
+    if (XR) {                                  /* new checkpoint, as when lane_step arms the loop */
+        s.wlim = imin(imin(f.ref_div_m1_i, f.max_iter_i - k.nbase), s.w + FSB_XR_STRETCH);
+        k.ck.zr = s.zr; k.ck.zi = s.zi; k.ck.dr = s.dr; k.ck.di = s.di; k.ck.w = s.w;
+    }
+    return true;
+}
 
 /* exponent-field bound of the escape pre-test: both parts of Z + z below 2^k
  * imply |Z + z|^2 < 2^(2k+1) <= Mdiv_sq */

@@ -72,6 +72,7 @@ static void run(const FrameDev &f, int64_t npts, const C *c_pix, double *Z, int3
             lane_step<XR, DZNDC, BLA>(f, s, c_pix, Z, U, (signed char *)sr, si, cnt, 1, k);
             cnt[6]++;
             if (s.flags & LF_NEED) break;
+        hot:
             bool ev, bad;
 #if FSB_ZZ2
             double Cr, Ci;
@@ -92,6 +93,13 @@ static void run(const FrameDev &f, int64_t npts, const C *c_pix, double *Z, int3
                 m2_hot_flags<XR, DZNDC, BLA>(s, s.Zr, s.Zi, f.h3, f.esc_hi, ev, bad);
                 cnt[5]++;
                 if (ev | bad) break;
+            }
+#endif
+#if FSB_SHORT_TRIP
+            if (BLA && ev && !bad && m2_trip_is_short<XR>(f, s, s.Zr, s.Zi)) {
+                if (lane_bla_short<XR, DZNDC>(f, s, k)) { s.flags &= ~LF_EV; goto hot; }
+                s.flags |= LF_EV;
+                continue;
             }
 #endif
             if (XR && bad) { s.flags |= LF_EV | LF_BAD; cnt[7]++; }
